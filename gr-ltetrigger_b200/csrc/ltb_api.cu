@@ -1,0 +1,626 @@
+// C ABI of libltetrigger_b200.so (declared in include/ltetrigger_b200.h): context
+// management, launch sequencing on one CUDA stream, record hand-back.  No CPU fallback:
+// every compute entry point fails with LTB_ERROR when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ltetrigger_b200.h"
+#include "ltb_kernels.cuh"
+#include "ltb_tables.h"
+
+using namespace ltb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define LTB_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      return fail(LTB_ERROR, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+    }                                                                                       \
+  } while (0)
+
+int next_pow2(long long v) {
+  long long p = 1;
+  while (p < v) p <<= 1;
+  return (int)p;
+}
+
+// ---- constant tables, uploaded once per device ------------------------------------------
+std::mutex g_const_mu;
+bool g_const_done[64] = {false};
+
+int ensure_constants(int device) {
+  std::lock_guard<std::mutex> lk(g_const_mu);
+  if (device < 0 || device >= 64) return fail(LTB_ERROR_INVALID_INPUTS, "device ordinal out of range");
+  if (g_const_done[device]) return LTB_SUCCESS;
+  PssTaps taps[3];
+  for (int r = 0; r < 3; ++r) make_pss_taps(r, taps[r]);
+  float2 coef[2][65][2];
+  for (int g = 0; g < 2; ++g)
+    for (int m = 0; m <= 64; ++m) {
+      coef[g][m][0] = make_float2(taps[g].re[m], taps[g].im[m]);
+      coef[g][m][1] = make_float2(taps[g].im[m], taps[g].re[m]);
+    }
+  LTB_CUDA(cudaMemcpyToSymbol(c_pss_coef, coef, sizeof coef));
+  float2 full[3][128];
+  for (int r = 0; r < 3; ++r)
+    for (int n = 0; n < 128; ++n) full[r][n] = make_float2(taps[r].re[n], taps[r].im[n]);
+  LTB_CUDA(cudaMemcpyToSymbol(c_pss_taps, full, sizeof full));
+  float dt[1000];
+  std::memset(dt, 0, sizeof dt);
+  const int ds[4] = {2, 4, 8, 16};
+  for (int i = 0; i < 4; ++i) {
+    std::vector<float> v = make_decim_taps(ds[i]);
+    if ((int)v.size() != decim_ntaps(ds[i])) return fail(LTB_ERROR, "unexpected decimator tap count");
+    std::memcpy(dt + decim_tap_offset(ds[i]), v.data(), v.size() * sizeof(float));
+  }
+  LTB_CUDA(cudaMemcpyToSymbol(c_decim_taps, dt, sizeof dt));
+  float twr[64], twi[64];
+  make_fft128_twiddles(twr, twi);
+  float2 tw[64];
+  for (int k = 0; k < 64; ++k) tw[k] = make_float2(twr[k], twi[k]);
+  LTB_CUDA(cudaMemcpyToSymbol(c_fft128_tw, tw, sizeof tw));
+  float c0[3][32], c1[3][32], sv[32], zv[32];
+  short nid[900];
+  std::memset(c0, 0, sizeof c0); std::memset(c1, 0, sizeof c1);
+  std::memset(sv, 0, sizeof sv); std::memset(zv, 0, sizeof zv);
+  for (int r = 0; r < 3; ++r) {
+    SssTables st;
+    make_sss_tables(r, st);
+    for (int i = 0; i < 31; ++i) { c0[r][i] = (float)st.c0[i]; c1[r][i] = (float)st.c1[i]; }
+    if (r == 0) {
+      for (int i = 0; i < 31; ++i) { sv[i] = (float)st.s_tilde[i]; zv[i] = (float)st.z_tilde[i]; }
+      for (int i = 0; i < 900; ++i) nid[i] = (short)st.n_id_1[i];
+    }
+  }
+  LTB_CUDA(cudaMemcpyToSymbol(c_sss_c0, c0, sizeof c0));
+  LTB_CUDA(cudaMemcpyToSymbol(c_sss_c1, c1, sizeof c1));
+  LTB_CUDA(cudaMemcpyToSymbol(c_sss_s, sv, sizeof sv));
+  LTB_CUDA(cudaMemcpyToSymbol(c_sss_z, zv, sizeof zv));
+  LTB_CUDA(cudaMemcpyToSymbol(c_sss_nid1, nid, sizeof nid));
+  LTB_CUDA(cudaFuncSetAttribute(pss_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(TrackShared)));
+  g_const_done[device] = true;
+  return LTB_SUCCESS;
+}
+
+int make_cexp_device(float2 **out) {
+  std::vector<float> re(4097), im(4097);
+  make_cexp_table(re.data(), im.data());
+  std::vector<float2> tab(4097);
+  for (int i = 0; i < 4097; ++i) tab[i] = make_float2(re[i], im[i]);
+  LTB_CUDA(cudaMalloc(out, sizeof(float2) * 4097));
+  LTB_CUDA(cudaMemcpy(*out, tab.data(), sizeof(float2) * 4097, cudaMemcpyHostToDevice));
+  return LTB_SUCCESS;
+}
+
+bool valid_decim(int d) { return d == 1 || d == 2 || d == 4 || d == 8 || d == 16; }
+
+// ---- front-end launchers ---------------------------------------------------------------
+template <int FMT>
+int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams, int m, float2 *tail_old,
+                    float2 *tail_new, float2 *y_ring, long long n_base, unsigned mask, int cap,
+                    cudaStream_t st, int *launches) {
+  if (decim == 1) {
+    int gx = (m / 2 + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    ingest_kernel<FMT><<<dim3(gx, n_streams), 256, 0, st>>>(d_iq, stride, m, y_ring, n_base, mask, cap);
+    *launches += 1;
+    return LTB_SUCCESS;
+  }
+  const dim3 grid((m + 255) / 256, n_streams);
+#define LTB_DECIM_CASE(D)                                                                             \
+  case D: {                                                                                           \
+    const size_t smem = sizeof(float2) * (size_t)(255 * D + decim_ntaps(D));                          \
+    decimate_kernel<FMT, D><<<grid, 256, smem, st>>>(d_iq, stride, m, tail_old, y_ring, n_base, mask, cap); \
+  } break;
+  switch (decim) {
+    LTB_DECIM_CASE(2)
+    LTB_DECIM_CASE(4)
+    LTB_DECIM_CASE(8)
+    LTB_DECIM_CASE(16)
+    default: return fail(LTB_ERROR_INVALID_INPUTS, "unsupported decimation");
+  }
+#undef LTB_DECIM_CASE
+  tail_kernel<FMT><<<n_streams, 256, 0, st>>>(d_iq, stride, (long long)m * decim, tail_old, tail_new);
+  *launches += 2;
+  return LTB_SUCCESS;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// batched trigger engine
+// ==========================================================================================
+struct ltb_trigger {
+  ltb_trigger_config cfg;
+  int n_chains = 0, cap = 0, max_m = 0, w_cap = 0, w_cur = 0;
+  unsigned cap_mask = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void *d_in = nullptr;
+  size_t d_in_stride = 0;
+  float2 *d_y = nullptr;
+  float *d_p = nullptr;
+  ChainState *d_state = nullptr;
+  float *d_avg = nullptr;
+  float *d_thr = nullptr;
+  ltb_window_rec *d_recs = nullptr;
+  int *d_rec_count = nullptr;
+  float2 *d_sss_sym = nullptr;
+  int *d_sss_rec = nullptr;
+  int *d_sss_count = nullptr;
+  int sss_cap = 0;
+  float2 *d_hf = nullptr;
+  float2 *d_tail[2] = {nullptr, nullptr};
+  int tail_cur = 0;
+  float2 *d_cexp = nullptr;
+  long long n_total = 0;
+  ltb_window_rec *h_recs = nullptr;
+  int *h_rec_count = nullptr;
+  std::vector<float> h_thr;
+  bool pending = false;
+  int last_launches = 0;
+  float last_ms = 0.f;
+};
+
+namespace {
+
+int trigger_zero_state(ltb_trigger *t) {
+  const int S = t->cfg.n_streams;
+  LTB_CUDA(cudaMemsetAsync(t->d_y, 0, sizeof(float2) * (size_t)S * t->cap, t->stream));
+  LTB_CUDA(cudaMemsetAsync(t->d_p, 0, sizeof(float) * (size_t)S * 3 * t->cap, t->stream));
+  LTB_CUDA(cudaMemsetAsync(t->d_state, 0, sizeof(ChainState) * t->n_chains, t->stream));
+  LTB_CUDA(cudaMemsetAsync(t->d_avg, 0, sizeof(float) * (size_t)t->n_chains * kAvgLen, t->stream));
+  LTB_CUDA(cudaMemsetAsync(t->d_tail[0], 0, sizeof(float2) * (size_t)S * kTailCap, t->stream));
+  LTB_CUDA(cudaMemsetAsync(t->d_tail[1], 0, sizeof(float2) * (size_t)S * kTailCap, t->stream));
+  LTB_CUDA(cudaMemcpyAsync(t->d_thr, t->h_thr.data(), sizeof(float) * t->n_chains, cudaMemcpyHostToDevice, t->stream));
+  LTB_CUDA(cudaStreamSynchronize(t->stream));
+  t->n_total = 0;
+  t->tail_cur = 0;
+  t->pending = false;
+  return LTB_SUCCESS;
+}
+
+void trigger_free(ltb_trigger *t) {
+  if (!t) return;
+  cudaSetDevice(t->cfg.device);
+  cudaFree(t->d_in); cudaFree(t->d_y); cudaFree(t->d_p); cudaFree(t->d_state); cudaFree(t->d_avg);
+  cudaFree(t->d_thr); cudaFree(t->d_recs); cudaFree(t->d_rec_count); cudaFree(t->d_sss_sym);
+  cudaFree(t->d_sss_rec); cudaFree(t->d_sss_count); cudaFree(t->d_hf); cudaFree(t->d_tail[0]);
+  cudaFree(t->d_tail[1]); cudaFree(t->d_cexp);
+  if (t->h_recs) cudaFreeHost(t->h_recs);
+  if (t->h_rec_count) cudaFreeHost(t->h_rec_count);
+  if (t->ev0) cudaEventDestroy(t->ev0);
+  if (t->ev1) cudaEventDestroy(t->ev1);
+  if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
+  delete t;
+}
+
+int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long long n_samples) {
+  const ltb_trigger_config &c = t->cfg;
+  if (t->pending) return fail(LTB_ERROR_INVALID_INPUTS, "previous submit not collected");
+  if (!d_iq || n_samples <= 0 || n_samples > c.max_chunk || (n_samples % (8 * c.decim)) != 0)
+    return fail(LTB_ERROR_INVALID_INPUTS, "n_samples must be a positive multiple of 8*decim and <= max_chunk");
+  const int m = (int)(n_samples / c.decim);
+  const int S = c.n_streams;
+  const long long n_base = t->n_total;
+  int launches = 0;
+  LTB_CUDA(cudaEventRecord(t->ev0, t->stream));
+  int rc;
+  if (c.input_format == LTB_FMT_FC32)
+    rc = launch_frontend<LTB_FMT_FC32>(c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
+                                       t->d_y, n_base, t->cap_mask, t->cap, t->stream, &launches);
+  else
+    rc = launch_frontend<LTB_FMT_SC16>(c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
+                                       t->d_y, n_base, t->cap_mask, t->cap, t->stream, &launches);
+  if (rc) return rc;
+  if (c.decim > 1) t->tail_cur ^= 1;
+  pss_corr_kernel<<<dim3((m + kCorrTile - 1) / kCorrTile, S), kCorrThreads, 0, t->stream>>>(
+      t->d_y, t->d_p, n_base, m, t->cap_mask, t->cap);
+  launches++;
+  t->n_total += m;
+  t->w_cur = m / (kHalf - kSlot) + 4;
+  if (t->w_cur > t->w_cap) t->w_cur = t->w_cap;
+  LTB_CUDA(cudaMemsetAsync(t->d_sss_count, 0, sizeof(int), t->stream));
+  TrackParams P;
+  P.y_ring = t->d_y; P.p_ring = t->d_p; P.state = t->d_state; P.avg = t->d_avg; P.thr = t->d_thr;
+  P.recs = t->d_recs; P.rec_count = t->d_rec_count; P.sss_sym = t->d_sss_sym; P.sss_rec = t->d_sss_rec;
+  P.sss_count = t->d_sss_count; P.sss_cap = t->sss_cap; P.hf_out = t->d_hf; P.cexp = t->d_cexp;
+  P.n_total = t->n_total; P.cap_mask = t->cap_mask; P.cap = t->cap; P.w_max = t->w_cur;
+  P.track_after = c.track_after; P.track_every = c.track_every; P.record_all = c.record_all;
+  P.root_mask = c.root_mask;
+  pss_track_kernel<<<t->n_chains, kTrackThreads, sizeof(TrackShared), t->stream>>>(P);
+  launches++;
+  int sss_grid = (t->n_chains * t->w_cur + kSssWarps - 1) / kSssWarps;
+  if (sss_grid > 148 * 8) sss_grid = 148 * 8;
+  sss_kernel<<<sss_grid, kSssWarps * 32, 0, t->stream>>>(t->d_sss_sym, t->d_sss_rec, t->d_sss_count, t->sss_cap, t->d_recs);
+  launches++;
+  LTB_CUDA(cudaEventRecord(t->ev1, t->stream));
+  LTB_CUDA(cudaMemcpyAsync(t->h_rec_count, t->d_rec_count, sizeof(int) * t->n_chains, cudaMemcpyDeviceToHost, t->stream));
+  LTB_CUDA(cudaMemcpyAsync(t->h_recs, t->d_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cur,
+                           cudaMemcpyDeviceToHost, t->stream));
+  LTB_CUDA(cudaGetLastError());
+  t->last_launches = launches;
+  t->pending = true;
+  return LTB_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ltb_last_error(void) { return g_err.c_str(); }
+const char *ltb_version(void) { return "ltetrigger_b200 0.1 (sm_100a)"; }
+
+int ltb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
+  if (!cfg || !out || cfg->struct_size != sizeof(ltb_trigger_config))
+    return fail(LTB_ERROR_INVALID_INPUTS, "bad config pointer or struct_size");
+  *out = nullptr;
+  ltb_trigger_config c = *cfg;
+  if (c.n_streams <= 0 || !valid_decim(c.decim) || (c.input_format != LTB_FMT_FC32 && c.input_format != LTB_FMT_SC16) ||
+      c.max_chunk <= 0 || (c.root_mask & ~7))
+    return fail(LTB_ERROR_INVALID_INPUTS, "invalid trigger configuration");
+  if (c.root_mask == 0) c.root_mask = 7;
+  if (c.track_after <= 0) c.track_after = 16;
+  if (c.track_every <= 0) c.track_every = 8;
+  if (!(c.psr_threshold > LTB_MIN_PSR_THRESHOLD)) c.psr_threshold = LTB_MIN_PSR_THRESHOLD;   // _ensure_safe_threshold
+  c.max_chunk = (c.max_chunk + 8 * c.decim - 1) / (8 * c.decim) * (8 * c.decim);
+  if (ltb_device_count() <= c.device || c.device < 0) return fail(LTB_ERROR, "no such CUDA device");
+  LTB_CUDA(cudaSetDevice(c.device));
+  int rc = ensure_constants(c.device);
+  if (rc) return rc;
+
+  ltb_trigger *t = new ltb_trigger();
+  t->cfg = c;
+  const int S = c.n_streams;
+  t->n_chains = S * 3;
+  t->max_m = (int)(c.max_chunk / c.decim);
+  t->cap = next_pow2((long long)t->max_m + kLookahead + kSlot + 256);
+  t->cap_mask = (unsigned)(t->cap - 1);
+  t->w_cap = t->max_m / (kHalf - kSlot) + 4;
+  t->sss_cap = t->n_chains * t->w_cap;
+  t->h_thr.assign(t->n_chains, c.psr_threshold);
+#define LTB_CUDA_T(call)                                                                   \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      trigger_free(t);                                                                     \
+      return fail(LTB_ERROR, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    }                                                                                      \
+  } while (0)
+  if (c.cuda_stream) t->stream = (cudaStream_t)c.cuda_stream;
+  else { LTB_CUDA_T(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking)); t->own_stream = true; }
+  LTB_CUDA_T(cudaEventCreate(&t->ev0));
+  LTB_CUDA_T(cudaEventCreate(&t->ev1));
+  t->d_in_stride = (size_t)c.max_chunk * (c.input_format == LTB_FMT_FC32 ? 8 : 4);
+  LTB_CUDA_T(cudaMalloc(&t->d_y, sizeof(float2) * (size_t)S * t->cap));
+  LTB_CUDA_T(cudaMalloc(&t->d_p, sizeof(float) * (size_t)S * 3 * t->cap));
+  LTB_CUDA_T(cudaMalloc(&t->d_state, sizeof(ChainState) * t->n_chains));
+  LTB_CUDA_T(cudaMalloc(&t->d_avg, sizeof(float) * (size_t)t->n_chains * kAvgLen));
+  LTB_CUDA_T(cudaMalloc(&t->d_thr, sizeof(float) * t->n_chains));
+  LTB_CUDA_T(cudaMalloc(&t->d_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cap));
+  LTB_CUDA_T(cudaMalloc(&t->d_rec_count, sizeof(int) * t->n_chains));
+  LTB_CUDA_T(cudaMalloc(&t->d_sss_sym, sizeof(float2) * 128 * (size_t)t->sss_cap));
+  LTB_CUDA_T(cudaMalloc(&t->d_sss_rec, sizeof(int) * t->sss_cap));
+  LTB_CUDA_T(cudaMalloc(&t->d_sss_count, sizeof(int)));
+  LTB_CUDA_T(cudaMalloc(&t->d_tail[0], sizeof(float2) * (size_t)S * kTailCap));
+  LTB_CUDA_T(cudaMalloc(&t->d_tail[1], sizeof(float2) * (size_t)S * kTailCap));
+  if (c.keep_halfframes) LTB_CUDA_T(cudaMalloc(&t->d_hf, sizeof(float2) * kHalf * (size_t)t->n_chains * t->w_cap));
+  LTB_CUDA_T(cudaMallocHost(&t->h_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cap));
+  LTB_CUDA_T(cudaMallocHost(&t->h_rec_count, sizeof(int) * t->n_chains));
+#undef LTB_CUDA_T
+  rc = make_cexp_device(&t->d_cexp);
+  if (!rc) rc = trigger_zero_state(t);
+  if (rc) { trigger_free(t); return rc; }
+  *out = t;
+  return LTB_SUCCESS;
+}
+
+int ltb_trigger_destroy(ltb_trigger *t) {
+  if (!t) return LTB_ERROR_INVALID_INPUTS;
+  cudaSetDevice(t->cfg.device);
+  cudaStreamSynchronize(t->stream);
+  trigger_free(t);
+  return LTB_SUCCESS;
+}
+
+int ltb_trigger_reset(ltb_trigger *t) {
+  if (!t) return LTB_ERROR_INVALID_INPUTS;
+  LTB_CUDA(cudaSetDevice(t->cfg.device));
+  LTB_CUDA(cudaStreamSynchronize(t->stream));
+  return trigger_zero_state(t);
+}
+
+int ltb_trigger_set_psr_threshold(ltb_trigger *t, int stream, int n_id_2, float thr, int clamp) {
+  if (!t || stream >= t->cfg.n_streams || n_id_2 > 2) return fail(LTB_ERROR_INVALID_INPUTS, "bad chain selector");
+  if (clamp && !(thr > LTB_MIN_PSR_THRESHOLD)) thr = LTB_MIN_PSR_THRESHOLD;
+  for (int s = 0; s < t->cfg.n_streams; ++s)
+    for (int r = 0; r < 3; ++r)
+      if ((stream < 0 || stream == s) && (n_id_2 < 0 || n_id_2 == r)) t->h_thr[s * 3 + r] = thr;
+  LTB_CUDA(cudaSetDevice(t->cfg.device));
+  LTB_CUDA(cudaMemcpyAsync(t->d_thr, t->h_thr.data(), sizeof(float) * t->n_chains, cudaMemcpyHostToDevice, t->stream));
+  LTB_CUDA(cudaStreamSynchronize(t->stream));
+  return LTB_SUCCESS;
+}
+
+int ltb_trigger_submit_device(ltb_trigger *t, const void *d_iq, int64_t stride, int64_t n_samples) {
+  if (!t) return LTB_ERROR_INVALID_INPUTS;
+  LTB_CUDA(cudaSetDevice(t->cfg.device));
+  return trigger_enqueue(t, d_iq, stride, n_samples);
+}
+
+int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int *n_recs) {
+  if (!t || !n_recs || (!recs && max_recs > 0)) return LTB_ERROR_INVALID_INPUTS;
+  if (!t->pending) return fail(LTB_ERROR_INVALID_INPUTS, "nothing submitted");
+  LTB_CUDA(cudaSetDevice(t->cfg.device));
+  LTB_CUDA(cudaStreamSynchronize(t->stream));
+  t->pending = false;
+  cudaEventElapsedTime(&t->last_ms, t->ev0, t->ev1);
+  int total = 0, written = 0;
+  for (int ch = 0; ch < t->n_chains; ++ch) {
+    const int n = t->h_rec_count[ch];
+    const ltb_window_rec *src = t->h_recs + (size_t)ch * t->w_cur;
+    for (int i = 0; i < n; ++i) {
+      if (written < max_recs) recs[written++] = src[i];
+      total++;
+    }
+  }
+  *n_recs = total;
+  if (total > max_recs) return fail(LTB_ERROR_INVALID_INPUTS, "record buffer too small");
+  return LTB_SUCCESS;
+}
+
+int ltb_trigger_process_device(ltb_trigger *t, const void *d_iq, int64_t stride, int64_t n_samples,
+                               ltb_window_rec *recs, int max_recs, int *n_recs) {
+  int rc = ltb_trigger_submit_device(t, d_iq, stride, n_samples);
+  if (rc) return rc;
+  return ltb_trigger_collect(t, recs, max_recs, n_recs);
+}
+
+int ltb_trigger_process_host(ltb_trigger *t, const void *iq, int64_t stride, int64_t n_samples,
+                             ltb_window_rec *recs, int max_recs, int *n_recs) {
+  if (!t || !iq) return LTB_ERROR_INVALID_INPUTS;
+  LTB_CUDA(cudaSetDevice(t->cfg.device));
+  if (n_samples <= 0 || n_samples > t->cfg.max_chunk) return fail(LTB_ERROR_INVALID_INPUTS, "n_samples out of range");
+  if (!t->d_in) LTB_CUDA(cudaMalloc(&t->d_in, t->d_in_stride * (size_t)t->cfg.n_streams));
+  const size_t row = (size_t)n_samples * (t->cfg.input_format == LTB_FMT_FC32 ? 8 : 4);
+  LTB_CUDA(cudaMemcpy2DAsync(t->d_in, t->d_in_stride, iq, (size_t)stride, row, (size_t)t->cfg.n_streams,
+                             cudaMemcpyHostToDevice, t->stream));
+  int rc = trigger_enqueue(t, t->d_in, (long long)t->d_in_stride, n_samples);
+  if (rc) return rc;
+  return ltb_trigger_collect(t, recs, max_recs, n_recs);
+}
+
+int ltb_trigger_get_stats(ltb_trigger *t, int stream, int n_id_2, ltb_pss_stats *out) {
+  if (!t || !out || stream < 0 || stream >= t->cfg.n_streams || n_id_2 < 0 || n_id_2 > 2)
+    return fail(LTB_ERROR_INVALID_INPUTS, "bad chain selector");
+  LTB_CUDA(cudaSetDevice(t->cfg.device));
+  ChainState st;
+  LTB_CUDA(cudaMemcpyAsync(&st, t->d_state + (stream * 3 + n_id_2), sizeof st, cudaMemcpyDeviceToHost, t->stream));
+  LTB_CUDA(cudaStreamSynchronize(t->stream));
+  auto mean = [](const float *d, unsigned n) -> float {      // compute_moving_avg, lib/pss_impl.cc:94-109
+    if (!n) return 0.0f;
+    if (n > (unsigned)kMavg) n = kMavg;
+    double acc = 0.0;
+    for (unsigned i = 0; i < n; ++i) acc += d[i];
+    return (float)(acc / (double)n);
+  };
+  out->max_psr = st.psr_max;
+  out->mean_psr = mean(st.psr_data, st.psr_i);
+  out->mean_cfo = mean(st.cfo_data, st.cfo_i);
+  out->psr_threshold = t->h_thr[stream * 3 + n_id_2];
+  out->tracking_score = (float)st.score;
+  out->tracking = st.tracking;
+  out->next_window = st.next_win;
+  return LTB_SUCCESS;
+}
+
+int ltb_trigger_fetch_halfframes(ltb_trigger *t, ltb_cf *out, int max_hf, int *n_hf) {
+  if (!t || !n_hf || !t->d_hf) return fail(LTB_ERROR_INVALID_INPUTS, "keep_halfframes not enabled");
+  LTB_CUDA(cudaSetDevice(t->cfg.device));
+  LTB_CUDA(cudaStreamSynchronize(t->stream));
+  int total = 0;
+  for (int ch = 0; ch < t->n_chains; ++ch) {
+    const int n = t->h_rec_count[ch];
+    for (int i = 0; i < n; ++i) {
+      const ltb_window_rec &r = t->h_recs[(size_t)ch * t->w_cur + i];
+      if (!(r.flags & LTB_F_EMIT)) continue;
+      if (total < max_hf)
+        LTB_CUDA(cudaMemcpyAsync(out + (size_t)total * kHalf, t->d_hf + ((size_t)ch * t->w_cur + i) * kHalf,
+                                 sizeof(float2) * kHalf, cudaMemcpyDeviceToHost, t->stream));
+      total++;
+    }
+  }
+  LTB_CUDA(cudaStreamSynchronize(t->stream));
+  *n_hf = total;
+  return total > max_hf ? fail(LTB_ERROR_INVALID_INPUTS, "half-frame buffer too small") : LTB_SUCCESS;
+}
+
+int ltb_trigger_last_timing(ltb_trigger *t, float *ms_total, int *n_launches) {
+  if (!t) return LTB_ERROR_INVALID_INPUTS;
+  if (ms_total) *ms_total = t->last_ms;
+  if (n_launches) *n_launches = t->last_launches;
+  return LTB_SUCCESS;
+}
+
+// ==========================================================================================
+// standalone sss block
+// ==========================================================================================
+struct ltb_sss {
+  int device, n_id_2;
+  float *d_cp = nullptr;
+  int *d_count = nullptr;
+};
+
+int ltb_sss_create(int device, int n_id_2, ltb_sss **out) {
+  if (!out || n_id_2 < 0 || n_id_2 > 2) return fail(LTB_ERROR_INVALID_INPUTS, "Error initializing SSS N_id_2");
+  *out = nullptr;
+  if (ltb_device_count() <= device || device < 0) return fail(LTB_ERROR, "no such CUDA device");
+  LTB_CUDA(cudaSetDevice(device));
+  int rc = ensure_constants(device);
+  if (rc) return rc;
+  ltb_sss *s = new ltb_sss();
+  s->device = device; s->n_id_2 = n_id_2;
+  if (cudaMalloc(&s->d_cp, 2 * sizeof(float)) != cudaSuccess || cudaMalloc(&s->d_count, sizeof(int)) != cudaSuccess ||
+      cudaMemset(s->d_cp, 0, 2 * sizeof(float)) != cudaSuccess) {
+    cudaFree(s->d_cp); cudaFree(s->d_count); delete s;
+    return fail(LTB_ERROR, "Error initializing SSS SYNC");
+  }
+  *out = s;
+  return LTB_SUCCESS;
+}
+
+int ltb_sss_destroy(ltb_sss *s) {
+  if (!s) return LTB_ERROR_INVALID_INPUTS;
+  cudaSetDevice(s->device);
+  cudaFree(s->d_cp); cudaFree(s->d_count);
+  delete s;
+  return LTB_SUCCESS;
+}
+
+int ltb_sss_work(ltb_sss *s, const ltb_cf *in, const int32_t *tag_lost, int n, ltb_window_rec *recs) {
+  if (!s || !in || !tag_lost || !recs || n <= 0) return LTB_ERROR_INVALID_INPUTS;
+  LTB_CUDA(cudaSetDevice(s->device));
+  float2 *d_hf = nullptr, *d_sym = nullptr; int *d_tag = nullptr, *d_rec = nullptr; ltb_window_rec *d_recs = nullptr;
+  int rc = LTB_SUCCESS;
+  cudaError_t e = cudaSuccess;
+#define STEP(call) if (e == cudaSuccess) e = (call)
+  STEP(cudaMalloc(&d_hf, sizeof(float2) * kHalf * (size_t)n));
+  STEP(cudaMalloc(&d_sym, sizeof(float2) * 128 * (size_t)n));
+  STEP(cudaMalloc(&d_tag, sizeof(int) * n));
+  STEP(cudaMalloc(&d_rec, sizeof(int) * n));
+  STEP(cudaMalloc(&d_recs, sizeof(ltb_window_rec) * n));
+  STEP(cudaMemcpy(d_hf, in, sizeof(float2) * kHalf * (size_t)n, cudaMemcpyHostToDevice));
+  STEP(cudaMemcpy(d_tag, tag_lost, sizeof(int) * n, cudaMemcpyHostToDevice));
+  STEP(cudaMemcpy(d_recs, recs, sizeof(ltb_window_rec) * n, cudaMemcpyHostToDevice));
+  STEP(cudaMemset(s->d_count, 0, sizeof(int)));
+  if (e == cudaSuccess) {
+    sss_block_front_kernel<<<1, 128>>>(d_hf, d_tag, n, s->n_id_2, s->d_cp, d_recs, d_sym, d_rec, s->d_count);
+    sss_kernel<<<(n + kSssWarps - 1) / kSssWarps, kSssWarps * 32>>>(d_sym, d_rec, s->d_count, n, d_recs);
+    e = cudaGetLastError();
+  }
+  STEP(cudaMemcpy(recs, d_recs, sizeof(ltb_window_rec) * n, cudaMemcpyDeviceToHost));
+#undef STEP
+  if (e != cudaSuccess) rc = fail(LTB_ERROR, std::string("ltb_sss_work: ") + cudaGetErrorString(e));
+  cudaFree(d_hf); cudaFree(d_sym); cudaFree(d_tag); cudaFree(d_rec); cudaFree(d_recs);
+  return rc;
+}
+
+// ==========================================================================================
+// kernel-level entry points
+// ==========================================================================================
+int ltb_kernel_pss_corr_host(int device, const ltb_cf *x, int n_streams, int64_t n, float *power) {
+  if (!x || !power || n_streams <= 0 || n <= 0 || (n % 8) != 0) return fail(LTB_ERROR_INVALID_INPUTS, "n must be a positive multiple of 8");
+  if (ltb_device_count() <= device || device < 0) return fail(LTB_ERROR, "no such CUDA device");
+  LTB_CUDA(cudaSetDevice(device));
+  int rc = ensure_constants(device);
+  if (rc) return rc;
+  const int cap = next_pow2(n + kCorrTile + 256);
+  float2 *d_y = nullptr; float *d_p = nullptr;
+  cudaError_t e = cudaMalloc(&d_y, sizeof(float2) * (size_t)n_streams * cap);
+  if (e == cudaSuccess) e = cudaMalloc(&d_p, sizeof(float) * (size_t)n_streams * 3 * cap);
+  if (e == cudaSuccess) e = cudaMemset(d_y, 0, sizeof(float2) * (size_t)n_streams * cap);
+  if (e == cudaSuccess) e = cudaMemcpy2D(d_y, sizeof(float2) * (size_t)cap, x, sizeof(float2) * (size_t)n, sizeof(float2) * (size_t)n, n_streams, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    pss_corr_kernel<<<dim3((unsigned)((n + kCorrTile - 1) / kCorrTile), n_streams), kCorrThreads>>>(d_y, d_p, 0, (int)n, (unsigned)(cap - 1), cap);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy2D(power, sizeof(float) * (size_t)n, d_p, sizeof(float) * (size_t)cap, sizeof(float) * (size_t)n, (size_t)n_streams * 3, cudaMemcpyDeviceToHost);
+  cudaFree(d_y); cudaFree(d_p);
+  if (e != cudaSuccess) return fail(LTB_ERROR, std::string("ltb_kernel_pss_corr_host: ") + cudaGetErrorString(e));
+  return LTB_SUCCESS;
+}
+
+int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in, int decim, ltb_cf *y) {
+  if (!x || !y || n_streams <= 0 || n_in <= 0 || !valid_decim(decim) || (n_in % decim) != 0 || (fmt != LTB_FMT_FC32 && fmt != LTB_FMT_SC16))
+    return fail(LTB_ERROR_INVALID_INPUTS, "bad decimate arguments");
+  if (ltb_device_count() <= device || device < 0) return fail(LTB_ERROR, "no such CUDA device");
+  LTB_CUDA(cudaSetDevice(device));
+  int rc = ensure_constants(device);
+  if (rc) return rc;
+  const int m = (int)(n_in / decim);
+  const int cap = next_pow2(m + 8);
+  const size_t in_row = (size_t)n_in * (fmt == LTB_FMT_FC32 ? 8 : 4);
+  void *d_in = nullptr; float2 *d_y = nullptr, *d_t0 = nullptr, *d_t1 = nullptr;
+  cudaError_t e = cudaMalloc(&d_in, in_row * n_streams);
+  if (e == cudaSuccess) e = cudaMalloc(&d_y, sizeof(float2) * (size_t)n_streams * cap);
+  if (e == cudaSuccess) e = cudaMalloc(&d_t0, sizeof(float2) * (size_t)n_streams * kTailCap);
+  if (e == cudaSuccess) e = cudaMalloc(&d_t1, sizeof(float2) * (size_t)n_streams * kTailCap);
+  if (e == cudaSuccess) e = cudaMemset(d_t0, 0, sizeof(float2) * (size_t)n_streams * kTailCap);
+  if (e == cudaSuccess) e = cudaMemcpy(d_in, x, in_row * n_streams, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    int launches = 0;
+    if (fmt == LTB_FMT_FC32) rc = launch_frontend<LTB_FMT_FC32>(decim, d_in, (long long)in_row, n_streams, m, d_t0, d_t1, d_y, 0, (unsigned)(cap - 1), cap, 0, &launches);
+    else rc = launch_frontend<LTB_FMT_SC16>(decim, d_in, (long long)in_row, n_streams, m, d_t0, d_t1, d_y, 0, (unsigned)(cap - 1), cap, 0, &launches);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy2D(y, sizeof(float2) * (size_t)m, d_y, sizeof(float2) * (size_t)cap, sizeof(float2) * (size_t)m, n_streams, cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_y); cudaFree(d_t0); cudaFree(d_t1);
+  if (e != cudaSuccess) return fail(LTB_ERROR, std::string("ltb_kernel_decimate_host: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+// ==========================================================================================
+// tables (host only)
+// ==========================================================================================
+int ltb_table_pss_taps(int n_id_2, float h_re[128], float h_im[128]) {
+  if (n_id_2 < 0 || n_id_2 > 2 || !h_re || !h_im) return LTB_ERROR_INVALID_INPUTS;
+  PssTaps t;
+  make_pss_taps(n_id_2, t);
+  std::memcpy(h_re, t.re, sizeof t.re);
+  std::memcpy(h_im, t.im, sizeof t.im);
+  return LTB_SUCCESS;
+}
+
+int ltb_table_decim_taps(int decim, float *taps, int max_taps) {
+  if (!taps || decim < 1) return LTB_ERROR_INVALID_INPUTS;
+  std::vector<float> v = make_decim_taps(decim);
+  if ((int)v.size() > max_taps) return LTB_ERROR_INVALID_INPUTS;
+  std::memcpy(taps, v.data(), v.size() * sizeof(float));
+  return (int)v.size();
+}
+
+int ltb_table_sss(int n_id_2, int32_t c0[31], int32_t c1[31], int32_t s_tilde[31], int32_t z_tilde[31], int32_t n_id_1_table[900]) {
+  if (n_id_2 < 0 || n_id_2 > 2) return LTB_ERROR_INVALID_INPUTS;
+  SssTables st;
+  make_sss_tables(n_id_2, st);
+  std::memcpy(c0, st.c0, sizeof st.c0); std::memcpy(c1, st.c1, sizeof st.c1);
+  std::memcpy(s_tilde, st.s_tilde, sizeof st.s_tilde); std::memcpy(z_tilde, st.z_tilde, sizeof st.z_tilde);
+  std::memcpy(n_id_1_table, st.n_id_1, sizeof st.n_id_1);
+  return LTB_SUCCESS;
+}
+
+int ltb_table_cexp(float tab_re[4097], float tab_im[4097]) {
+  if (!tab_re || !tab_im) return LTB_ERROR_INVALID_INPUTS;
+  make_cexp_table(tab_re, tab_im);
+  return LTB_SUCCESS;
+}
+
+int ltb_table_fft128_twiddles(float w_re[64], float w_im[64]) {
+  if (!w_re || !w_im) return LTB_ERROR_INVALID_INPUTS;
+  make_fft128_twiddles(w_re, w_im);
+  return LTB_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,856 @@
+// sm_100a kernels of the PSS+SSS search path.  Included once by ltb_api.cu.
+//
+// Arithmetic contract ("canonical arithmetic"): float32, every fused
+// multiply-add is an explicit fma (FFMA / packed FFMA2), every other product or sum is an
+// individually rounded __fmul_rn/__fadd_rn, accumulation orders are fixed.  The CPU oracle
+// (oracle/ltetrigger_oracle.c, test-only) evaluates the same expression trees, so the
+// parity tests compare bits, not tolerances.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ltetrigger_b200.h"
+
+namespace ltb {
+
+// ------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------
+constexpr int kSlot = LTB_SLOT_LEN;        // 960
+constexpr int kHalf = LTB_HALF_FRAME;      // 9600
+constexpr int kSym = LTB_SYMBOL_SZ;        // 128
+constexpr int kNLag = LTB_CONV_LEN;        // 9726
+constexpr int kAvgLen = 9732;              // 9729 used (fft+frame+1), padded to 16 B
+constexpr int kLookahead = LTB_LOOKAHEAD;  // 18365
+constexpr int kMavg = LTB_MOVING_AVG_SZ;   // 200
+constexpr int kMaxDecimTaps = 528;         // 525 for D=16
+constexpr int kTailCap = 528;              // decimator history kept per stream (input samples)
+
+// folded matched-filter coefficients, group 0 = root 25, group 1 = root 29 (root 34 = conj):
+//   [g][m][0] = (hr, hi)   [g][m][1] = (hi, hr)      m = 0..64
+__constant__ float2 c_pss_coef[2][65][2];
+// full 128-tap filters per N_id_2 (CFO estimate): (re, im)
+__constant__ float2 c_pss_taps[3][128];
+// decimator taps for D = 2, 4, 8, 16 at offsets 0, 72, 208, 472 (padded with zeros)
+__constant__ float c_decim_taps[1000];
+__constant__ float2 c_fft128_tw[64];
+// SSS tables per N_id_2: c0, c1 (31 each); shared s_tilde, z_tilde; N_id_1 table
+__constant__ float c_sss_c0[3][32];
+__constant__ float c_sss_c1[3][32];
+__constant__ float c_sss_s[32];
+__constant__ float c_sss_z[32];
+__constant__ short c_sss_nid1[900];
+
+__host__ __device__ constexpr int decim_tap_offset(int d) { return d == 2 ? 0 : d == 4 ? 72 : d == 8 ? 208 : 472; }
+__host__ __device__ constexpr int decim_ntaps(int d) { return d == 2 ? 65 : d == 4 ? 131 : d == 8 ? 263 : d == 16 ? 525 : 0; }
+
+// ------------------------------------------------------------------------------------
+// per-chain state (one pss block + one sss block of the reference)
+// ------------------------------------------------------------------------------------
+struct ChainState {
+  long long next_win;        // absolute search-rate index of the next general_work call (nitems_read)
+  int score, timer, tracking, lost;   // tracking_t + d_tracking_lost (lib/pss_impl.h:41-63)
+  int peak_pos;              // d_peak_pos
+  int win_index;
+  float psr, psr_max, peak_value;
+  unsigned psr_i, cfo_i;
+  float cfo_last_freq;       // d_cfo.last_freq
+  float cfo_table_freq;      // frequency the phasor table currently holds
+  float cp_norm_avg, cp_ext_avg;   // srslte_sync_t M_norm_avg / M_ext_avg
+  float psr_data[kMavg];
+  float cfo_data[kMavg];
+};
+
+struct TrackParams {
+  const float2 *y_ring;      // [n_streams][cap]
+  const float *p_ring;       // [n_streams][3][cap]
+  ChainState *state;         // [n_streams*3]
+  float *avg;                // [n_streams*3][kAvgLen]
+  const float *thr;          // [n_streams*3]
+  ltb_window_rec *recs;      // [n_streams*3][w_max]
+  int *rec_count;            // [n_streams*3]
+  float2 *sss_sym;           // [sss_cap][128]
+  int *sss_rec;              // [sss_cap] -> index into recs
+  int *sss_count;            // global counter
+  int sss_cap;
+  float2 *hf_out;            // [n_streams*3][w_max][9600] or null
+  const float2 *cexp;        // 4097 entries
+  long long n_total;         // search-rate samples received so far
+  unsigned cap_mask;
+  int cap;
+  int w_max;
+  int track_after, track_every;
+  int record_all;
+  int root_mask;
+};
+
+// ------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+
+// canonical complex product a*b:  re = fma(ar, br, -(ai*bi)),  im = fma(ar, bi, ai*br)
+__device__ __forceinline__ float2 cmul_canon(float2 a, float2 b) {
+  float2 r;
+  r.x = __fmaf_rn(a.x, b.x, -__fmul_rn(a.y, b.y));
+  r.y = __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x));
+  return r;
+}
+
+// canonical atan2 (double): fixed range reduction + 18-term odd series, explicit fma only
+__device__ double canon_atan2(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const double mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
+  if (mx == 0.0) return 0.0;
+  const double q = __ddiv_rn(mn, mx);
+  double t = q, off = 0.0;
+  if (q > 0.41421356237309503) {
+    t = __ddiv_rn(__dadd_rn(q, -1.0), __dadd_rn(q, 1.0));
+    off = 0.78539816339744828;
+  }
+  const double t2 = __dmul_rn(t, t);
+  double p = 1.0 / 35.0;
+#pragma unroll 1
+  for (int k = 16; k >= 0; --k) {
+    const double c = __ddiv_rn(1.0, (double)(2 * k + 1));
+    p = -p;
+    p = __fma_rn(p, t2, c);
+  }
+  double r = __fma_rn(t, p, off);
+  if (ay > ax) r = __dadd_rn(1.5707963267948966, -r);
+  if (x < 0.0) r = __dadd_rn(3.1415926535897931, -r);
+  if (y < 0.0) r = -r;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------
+// K0: ingest at D = 1 -- convert (sc16) / copy (fc32) the new chunk into the sample ring
+// ------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) ingest_kernel(const void *__restrict__ in, long long stride_bytes,
+                                                     int n_new, float2 *__restrict__ y_ring,
+                                                     long long n_base, unsigned cap_mask, int cap) {
+  const int stream = blockIdx.y;
+  const char *src = (const char *)in + (long long)stream * stride_bytes;
+  float2 *dst = y_ring + (size_t)stream * cap;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n_new; i += gridDim.x * blockDim.x * 2) {
+    float4 v;
+    if (FMT == LTB_FMT_FC32) {
+      v = *reinterpret_cast<const float4 *>(src + (size_t)i * 8);
+    } else {
+      const short4 s = *reinterpret_cast<const short4 *>(src + (size_t)i * 4);
+      const float k = 1.0f / 32768.0f;
+      v = make_float4(__fmul_rn((float)s.x, k), __fmul_rn((float)s.y, k), __fmul_rn((float)s.z, k),
+                      __fmul_rn((float)s.w, k));
+    }
+    *reinterpret_cast<float4 *>(&dst[(unsigned)((n_base + i) & cap_mask)]) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K1: polyphase decimator  y[k] = sum_j taps[j] x[kD - j]   (rational_resampler_ccc(1, D))
+// canonical order: branch v = j mod D outer, q = j div D inner, one fma chain per component.
+// ------------------------------------------------------------------------------------
+template <int FMT>
+__device__ __forceinline__ float2 load_in_sample(const char *src, long long idx) {
+  if (FMT == LTB_FMT_FC32) return *reinterpret_cast<const float2 *>(src + idx * 8);
+  const short2 s = *reinterpret_cast<const short2 *>(src + idx * 4);
+  const float k = 1.0f / 32768.0f;
+  return make_float2(__fmul_rn((float)s.x, k), __fmul_rn((float)s.y, k));
+}
+
+// Tile of TILE_OUT outputs per CTA; the (TILE_OUT-1)*D + NTAPS input samples it touches are
+// staged once in shared memory (coalesced 8-byte loads, converted on the way in), then each
+// thread walks its own polyphase branches.
+template <int FMT, int D>
+__global__ void __launch_bounds__(256) decimate_kernel(const void *__restrict__ in, long long stride_bytes,
+                                                       int n_out, const float2 *__restrict__ tail_in,
+                                                       float2 *__restrict__ y_ring, long long n_base,
+                                                       unsigned cap_mask, int cap) {
+  constexpr int NT = decim_ntaps(D);
+  constexpr int OFF = decim_tap_offset(D);
+  constexpr int TILE_OUT = 256;
+  constexpr int SPAN = (TILE_OUT - 1) * D + NT;     // input samples needed by the tile
+  extern __shared__ float2 s_in[];                  // [SPAN]
+  const int stream = blockIdx.y;
+  const int k0 = blockIdx.x * TILE_OUT;
+  const char *src = (const char *)in + (long long)stream * stride_bytes;
+  const float2 *tail = tail_in + (size_t)stream * kTailCap;
+  const long long first = (long long)k0 * D - (NT - 1);   // input index of s_in[0]
+  const long long n_in = (long long)n_out * D;
+  for (int i = threadIdx.x; i < SPAN; i += blockDim.x) {
+    const long long idx = first + i;
+    float2 v = make_float2(0.f, 0.f);
+    if (idx >= 0) { if (idx < n_in) v = load_in_sample<FMT>(src, idx); }
+    else if (idx >= -kTailCap) v = tail[kTailCap + idx];
+    s_in[i] = v;
+  }
+  __syncthreads();
+  const int k = k0 + threadIdx.x;
+  if (k >= n_out) return;
+  // x[kD - j] = s_in[(k - k0)*D + (NT-1) - j]
+  const float2 *base = s_in + threadIdx.x * D + (NT - 1);
+  float ar = 0.f, ai = 0.f;
+#pragma unroll 1
+  for (int v = 0; v < D; ++v) {
+#pragma unroll 4
+    for (int j = v; j < NT; j += D) {
+      const float2 x = base[-j];
+      const float t = c_decim_taps[OFF + j];
+      ar = __fmaf_rn(t, x.x, ar);
+      ai = __fmaf_rn(t, x.y, ai);
+    }
+  }
+  y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = make_float2(ar, ai);
+}
+
+// keep the last kTailCap converted input samples of each stream for the next call
+template <int FMT>
+__global__ void __launch_bounds__(256) tail_kernel(const void *__restrict__ in, long long stride_bytes,
+                                                   long long n_in, const float2 *__restrict__ tail_old,
+                                                   float2 *__restrict__ tail_new) {
+  const int stream = blockIdx.x;
+  const char *src = (const char *)in + (long long)stream * stride_bytes;
+  for (int i = threadIdx.x; i < kTailCap; i += blockDim.x) {
+    const long long idx = n_in - kTailCap + i;      // index into the new chunk (may be negative)
+    float2 v;
+    if (idx >= 0) v = load_in_sample<FMT>(src, idx);
+    else v = (idx >= -kTailCap) ? tail_old[(size_t)stream * kTailCap + kTailCap + idx] : make_float2(0.f, 0.f);
+    tail_new[(size_t)stream * kTailCap + i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K2: three-root matched filter + |.|^2 over the new samples of every stream
+//
+// Folded direct form.  h[128-m] == h[m] and h_34 == conj(h_29), so per output n
+//   s_0 = x[n],  s_m = x[n-m] + x[n-128+m] (m=1..63),  s_64 = x[n-64]
+//   (A,B)_g += (hr,hi)_g[m] * (s.re, s.im)      (D,C)_g += (hi,hr)_g[m] * (s.re, s.im)
+// for g = root 25, root 29: 1 FADD2 + 4 FFMA2 per folded tap instead of 12 FFMA per tap pair.
+//   root 25 / 29: y = (A-B, C+D)     root 34: y = (A+B, C-D)     P = fma(re, re, im*im)
+// Each thread owns 8 consecutive outputs and slides two 8-sample register windows over a
+// shared-memory tile stored 8-way de-interleaved (row = index mod 8), which makes every
+// LDS.64 of a warp hit 32 consecutive 8-byte words: no bank conflicts, 2 LDS per 40 FP ops.
+// ------------------------------------------------------------------------------------
+constexpr int kCorrT = 8;
+constexpr int kCorrThreads = 256;
+constexpr int kCorrTile = kCorrT * kCorrThreads;          // 2048 outputs per CTA
+constexpr int kCorrCols = (kCorrTile + 128) / 8;          // 272
+constexpr int kCorrRowStride = kCorrCols + 2;             // 274 float2 = 548 words == 4 (mod 16)
+
+__device__ __forceinline__ float2 corr_lds(const float2 *row_base, int e) {
+  // tile sample index e (compile-time after unrolling, relative to 8*t) -> row e&7, column t + (e>>3)
+  return row_base[(e & 7) * kCorrRowStride + (e >> 3)];
+}
+
+__global__ void __launch_bounds__(kCorrThreads, 2)
+pss_corr_kernel(const float2 *__restrict__ y_ring, float *__restrict__ p_ring, long long n_base, int n_new,
+                unsigned cap_mask, int cap) {
+  __shared__ float2 sx[8 * kCorrRowStride];
+  const int stream = blockIdx.y;
+  const long long n0 = n_base + (long long)blockIdx.x * kCorrTile;   // absolute index of output 0
+  const float2 *yr = y_ring + (size_t)stream * cap;
+
+  // stage samples n0-128 .. n0+2048 (tile index u = n - n0 + 128), two per thread per step
+  for (int u = threadIdx.x * 2; u < kCorrTile + 128; u += kCorrThreads * 2) {
+    const float4 v = *reinterpret_cast<const float4 *>(&yr[(unsigned)((n0 - 128 + u) & cap_mask)]);
+    sx[(u & 7) * kCorrRowStride + (u >> 3)] = make_float2(v.x, v.y);
+    sx[((u + 1) & 7) * kCorrRowStride + (u >> 3)] = make_float2(v.z, v.w);
+  }
+  __syncthreads();
+
+  const int t = threadIdx.x;
+  const float2 *rb = sx + t;          // column offset t; corr_lds adds row and the constant column
+  float2 wa[8], wb[8];                // sliding windows, tile element e lives in slot e & 7
+  float2 ab[8][2], dc[8][2];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    ab[o][0] = ab[o][1] = dc[o][0] = dc[o][1] = make_float2(0.f, 0.f);
+  }
+  // m = 0 : s = x[n] -> tile element 8t + 128 + o
+#pragma unroll
+  for (int o = 0; o < 8; ++o) wa[o] = corr_lds(rb, 128 + o);
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const float2 s = wa[o];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      ab[o][g] = ffma2(c_pss_coef[g][0][0], s, ab[o][g]);
+      dc[o][g] = ffma2(c_pss_coef[g][0][1], s, dc[o][g]);
+    }
+  }
+  // b-window for m = 1: tile elements 8t + 1 .. 8t + 7 (element 8t + 8 arrives with step m = 1)
+#pragma unroll
+  for (int o = 1; o < 8; ++o) wb[o] = corr_lds(rb, o);
+
+  // step m = 8*mb + m1 (m1 = 1..8): a-window slides down (new element 128-m: row (8-m1)&7,
+  // column 15-mb), b-window slides up (new element m+7: row m1-1, column mb+1).  The slot
+  // arithmetic only depends on m1, so an 8-step body is fully static and is rolled 7 times.
+#define LTB_CORR_STEP(M1, PA, PB, COEF, WITH_B)                                        \
+  {                                                                                    \
+    wa[(8 - (M1)) & 7] = (PA)[((8 - (M1)) & 7) * kCorrRowStride];                      \
+    if (WITH_B) wb[((M1) - 1) & 7] = (PB)[(((M1) - 1) & 7) * kCorrRowStride];          \
+    const float2 c00 = (COEF)[0][0], c01 = (COEF)[0][1];                               \
+    const float2 c10 = (COEF)[65][0], c11 = (COEF)[65][1];                         \
+    _Pragma("unroll") for (int o = 0; o < 8; ++o) {                                    \
+      const float2 s = (WITH_B) ? fadd2(wa[(o - (M1)) & 7], wb[(o + (M1)) & 7])        \
+                                : wa[(o - (M1)) & 7];                                  \
+      ab[o][0] = ffma2(c00, s, ab[o][0]);                                              \
+      dc[o][0] = ffma2(c01, s, dc[o][0]);                                              \
+      ab[o][1] = ffma2(c10, s, ab[o][1]);                                              \
+      dc[o][1] = ffma2(c11, s, dc[o][1]);                                              \
+    }                                                                                  \
+  }
+  typedef float2 coef_pair_t[2];
+  const float2 *pa = rb + 15, *pb = rb + 1;
+#pragma unroll 1
+  for (int mb = 0; mb < 7; ++mb) {
+    const coef_pair_t *cf = &c_pss_coef[0][8 * mb];
+#pragma unroll
+    for (int m1 = 1; m1 <= 8; ++m1) LTB_CORR_STEP(m1, pa, pb, cf + m1, true)
+    pa -= 1;
+    pb += 1;
+  }
+  {
+    const coef_pair_t *cf = &c_pss_coef[0][56];
+#pragma unroll
+    for (int m1 = 1; m1 <= 7; ++m1) LTB_CORR_STEP(m1, pa, pb, cf + m1, true)
+    LTB_CORR_STEP(8, pa, pb, cf + 8, false)      // m = 64 : s = x[n-64], no partner
+  }
+#undef LTB_CORR_STEP
+
+  const int local = t * 8;
+  if ((long long)blockIdx.x * kCorrTile + local >= n_new) return;   // n_new is a multiple of 8
+  float p0[8], p1[8], p2[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    // ab = (A, B), dc = (D, C)
+    float re = __fadd_rn(ab[o][0].x, -ab[o][0].y), im = __fadd_rn(dc[o][0].y, dc[o][0].x);
+    p0[o] = __fmaf_rn(re, re, __fmul_rn(im, im));
+    re = __fadd_rn(ab[o][1].x, -ab[o][1].y); im = __fadd_rn(dc[o][1].y, dc[o][1].x);
+    p1[o] = __fmaf_rn(re, re, __fmul_rn(im, im));
+    re = __fadd_rn(ab[o][1].x, ab[o][1].y); im = __fadd_rn(dc[o][1].y, -dc[o][1].x);
+    p2[o] = __fmaf_rn(re, re, __fmul_rn(im, im));
+  }
+  const unsigned slot = (unsigned)((n0 + local) & cap_mask);
+  float *pp = p_ring + (size_t)stream * 3 * cap + slot;
+  reinterpret_cast<float4 *>(pp)[0] = make_float4(p0[0], p0[1], p0[2], p0[3]);
+  reinterpret_cast<float4 *>(pp)[1] = make_float4(p0[4], p0[5], p0[6], p0[7]);
+  reinterpret_cast<float4 *>(pp + cap)[0] = make_float4(p1[0], p1[1], p1[2], p1[3]);
+  reinterpret_cast<float4 *>(pp + cap)[1] = make_float4(p1[4], p1[5], p1[6], p1[7]);
+  reinterpret_cast<float4 *>(pp + 2 * (size_t)cap)[0] = make_float4(p2[0], p2[1], p2[2], p2[3]);
+  reinterpret_cast<float4 *>(pp + 2 * (size_t)cap)[1] = make_float4(p2[4], p2[5], p2[6], p2[7]);
+}
+
+// ------------------------------------------------------------------------------------
+// K3: per-chain sequential phase = pss::general_work + the head of sss::work
+//     (lib/pss_impl.cc:154-223, lib/sss_impl.cc:83-110), one CTA per (stream, N_id_2) chain.
+// ------------------------------------------------------------------------------------
+constexpr int kTrackThreads = 256;
+constexpr int kNEdge = 253;            // lags 0..126 and 9600..9725 see a truncated window
+
+struct TrackShared {
+  float avg[kAvgLen];
+  float2 lead[256];                    // window samples 0..126 at [128..255), zeros elsewhere
+  float2 trail[256];                   // window samples 9473..9599 at [1..128), zeros elsewhere
+  float edge[256];                     // power at the truncated lags
+  float2 rot[480];                     // CFO-corrected samples 480..959 of the emitted half-frame
+  unsigned short ph_idx[960];          // phasor table index per sample
+  float red_v[8]; int red_i[8]; float red_l[8]; float red_r[8];
+  float cp_part[12];
+  float2 y01[2];
+  // broadcast slots
+  int p, lb, ub; float peak, lmax, rmax;
+  int do_emit, do_track, zero_avg, frame_start, rec_slot, sss_slot, cp_len;
+  long long emit_abs;
+  ChainState st;
+};
+
+// canonical folded correlation power at one lag of a zero-padded window; buf index of x[k]
+// is `pos`, buf[pos-127 .. pos] readable
+__device__ __forceinline__ float edge_power(const float2 *buf, int pos, int n_id_2) {
+  const int g = n_id_2 == 0 ? 0 : 1;
+  float2 ab = make_float2(0.f, 0.f), dc = make_float2(0.f, 0.f);
+  {
+    const float2 s = buf[pos];
+    ab = ffma2(c_pss_coef[g][0][0], s, ab);
+    dc = ffma2(c_pss_coef[g][0][1], s, dc);
+  }
+#pragma unroll 1
+  for (int m = 1; m <= 63; ++m) {
+    const float2 s = fadd2(buf[pos - m], buf[pos - 128 + m]);
+    ab = ffma2(c_pss_coef[g][m][0], s, ab);
+    dc = ffma2(c_pss_coef[g][m][1], s, dc);
+  }
+  {
+    const float2 s = buf[pos - 64];
+    ab = ffma2(c_pss_coef[g][64][0], s, ab);
+    dc = ffma2(c_pss_coef[g][64][1], s, dc);
+  }
+  float re, im;
+  if (n_id_2 == 2) { re = __fadd_rn(ab.x, ab.y); im = __fadd_rn(dc.y, -dc.x); }
+  else             { re = __fadd_rn(ab.x, -ab.y); im = __fadd_rn(dc.y, dc.x); }
+  return __fmaf_rn(re, re, __fmul_rn(im, im));
+}
+
+__global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TrackShared &S = *reinterpret_cast<TrackShared *>(smem_raw);
+  const int chain = blockIdx.x;
+  const int stream = chain / 3, n_id_2 = chain % 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!((P.root_mask >> n_id_2) & 1)) { if (tid == 0) P.rec_count[chain] = 0; return; }
+
+  const float2 *yr = P.y_ring + (size_t)stream * P.cap;
+  const float *pr = P.p_ring + ((size_t)stream * 3 + n_id_2) * P.cap;
+  float *avg_g = P.avg + (size_t)chain * kAvgLen;
+  const float thr = P.thr[chain];
+
+  if (tid == 0) S.st = P.state[chain];
+  for (int k = tid; k < kAvgLen; k += kTrackThreads) S.avg[k] = avg_g[k];
+  S.lead[tid] = make_float2(0.f, 0.f);
+  S.trail[tid] = make_float2(0.f, 0.f);
+  int n_rec = 0;
+  __syncthreads();
+
+  for (;;) {
+    const long long R = S.st.next_win;
+    if (R + kLookahead > P.n_total) break;
+    const bool search = !S.st.tracking || S.st.timer == 0;          // lib/pss_impl.cc:163
+    __syncthreads();                                                // everyone has read S.st
+    if (search) {
+      // ---- srslte_pss_find_pss ------------------------------------------------
+      if (tid < 127) {
+        S.lead[128 + tid] = yr[(unsigned)((R + tid) & P.cap_mask)];
+        S.trail[1 + tid] = yr[(unsigned)((R + 9473 + tid) & P.cap_mask)];
+      }
+      __syncthreads();
+      if (tid < kNEdge) {
+        // lag k<127: x[k] at lead[128+k];  lag k>=9600: x[k] at trail[k-9472]
+        S.edge[tid] = (tid < 127) ? edge_power(S.lead, 128 + tid, n_id_2)
+                                  : edge_power(S.trail, 128 + (tid - 127), n_id_2);
+      }
+      __syncthreads();
+      float best = -3.402823466e+38f; int bi = 0;
+      for (int k = tid; k < kNLag; k += kTrackThreads) {
+        float a;
+        if (k < 127) a = S.edge[k];
+        else if (k >= kHalf) a = S.edge[127 + (k - kHalf)];
+        else a = pr[(unsigned)((R + k) & P.cap_mask)];
+        const float v = __fadd_rn(__fmul_rn(a, 0.2f), __fmul_rn(S.avg[k], 0.8f));   // EMA, alpha 0.2
+        S.avg[k] = v;
+        if (v > best) { best = v; bi = k; }
+      }
+      // first-index argmax over the block
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) { S.red_v[warp] = best; S.red_i[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        float bv = S.red_v[0]; int bidx = S.red_i[0];
+        for (int w = 1; w < kTrackThreads / 32; ++w)
+          if (S.red_v[w] > bv || (S.red_v[w] == bv && S.red_i[w] < bidx)) { bv = S.red_v[w]; bidx = S.red_i[w]; }
+        const int p = bidx;
+        // main-lobe walk
+        const int conv_output_len = kNLag + 1;
+        int ub = p + 1;
+        while (S.avg[ub + 1] <= S.avg[ub] && ub < conv_output_len) ub++;
+        int lb;
+        if (p > 2) { lb = p - 1; while (S.avg[lb - 1] <= S.avg[lb] && lb > 1) lb--; }
+        else lb = 0;
+        S.p = p; S.peak = S.avg[p]; S.lb = lb; S.ub = ub;
+      }
+      __syncthreads();
+      {
+        const int lb = S.lb, ub = S.ub;
+        float lm = -3.402823466e+38f, rm = -3.402823466e+38f;
+        for (int k = tid; k < kNLag; k += kTrackThreads) {
+          const float v = S.avg[k];
+          if (k < lb) lm = fmaxf(lm, v);
+          if (k >= ub) rm = fmaxf(rm, v);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          lm = fmaxf(lm, __shfl_down_sync(0xffffffffu, lm, off));
+          rm = fmaxf(rm, __shfl_down_sync(0xffffffffu, rm, off));
+        }
+        if (lane == 0) { S.red_l[warp] = lm; S.red_r[warp] = rm; }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      ChainState &st = S.st;
+      unsigned flags = 0;
+      if (search) {
+        float lm = S.red_l[0], rm = S.red_r[0];
+        for (int w = 1; w < kTrackThreads / 32; ++w) { lm = fmaxf(lm, S.red_l[w]); rm = fmaxf(rm, S.red_r[w]); }
+        // vec_max_fi over an empty range returns index 0
+        const float left = (S.lb > 0) ? lm : S.avg[0];
+        const float right = (S.ub < kNLag) ? rm : S.avg[S.ub];
+        const float side = left > right ? left : right;
+        st.timer = P.track_every;
+        st.peak_pos = S.p;
+        st.peak_value = S.peak;
+        st.psr = __fdiv_rn(S.peak, side);
+        st.psr_data[st.psr_i++ % kMavg] = st.psr;
+        flags |= LTB_F_SEARCHED;
+      } else {
+        st.timer--;
+      }
+      const bool over = st.psr > thr;                               // :174
+      int zero_avg = 0;
+      if (over) {                                                   // incr_score :111-127
+        flags |= LTB_F_OVER;
+        if (!(st.tracking && st.score == P.track_after)) {
+          st.score++;
+          if (!st.tracking && st.score == P.track_after) { st.tracking = 1; zero_avg = 1; }
+        }
+      } else if (st.score != 0) {                                   // reset_score :129-152
+        st.score = 0; st.timer = 0; st.tracking = 0;
+        zero_avg = 1;
+        for (int i = 0; i < kMavg; ++i) { st.psr_data[i] = 0.f; st.cfo_data[i] = 0.f; }
+        st.psr_i = 0; st.cfo_i = 0; st.cfo_last_freq = 0.f;
+        st.lost = 1;
+      }
+      if (st.psr > st.psr_max) st.psr_max = st.psr;                 // :181
+      const int peak_used = st.peak_pos;
+      int nconsume = kHalf, do_emit = 0, do_track = 0, frame_start = 0;
+      if (over || st.lost) {                                        // :184
+        frame_start = st.peak_pos - kSlot;
+        st.peak_pos = kSlot;
+        nconsume = frame_start + kHalf;
+        do_emit = 1; flags |= LTB_F_EMIT;
+        if (st.tracking) { do_track = 1; flags |= LTB_F_TRACKING; }
+        else { flags |= LTB_F_TAG_LOST; st.lost = 0; }
+      }
+      S.do_emit = do_emit; S.do_track = do_track; S.zero_avg = zero_avg;
+      S.frame_start = frame_start; S.emit_abs = R + frame_start;
+      S.rec_slot = -1;
+      if ((do_emit || P.record_all) && n_rec < P.w_max) {
+        S.rec_slot = chain * P.w_max + n_rec;
+        ltb_window_rec r;
+        r.win_start = R; r.emit_start = do_emit ? R + frame_start : -1;
+        r.stream = stream; r.n_id_2 = n_id_2; r.win_index = st.win_index; r.flags = flags;
+        r.peak_pos = peak_used; r.score = st.score; r.psr = st.psr; r.peak_value = st.peak_value;
+        r.cfo = 0.f; r.mean_cfo = 0.f; r.m0 = -1; r.m1 = -1; r.m0_val = 0.f; r.m1_val = 0.f;
+        r.n_id_1 = -1; r.cell_id = -1; r.cp_norm_avg = 0.f; r.cp_ext_avg = 0.f;
+        P.recs[S.rec_slot] = r;
+      }
+      if (do_emit && !do_track) { st.cp_norm_avg = 0.f; st.cp_ext_avg = 0.f; }   // sss: srslte_sync_reset on the tag
+      st.win_index++;
+      st.next_win = R + nconsume;
+    }
+    __syncthreads();
+    if (S.rec_slot >= 0) n_rec++;
+    if (S.zero_avg) {                                               // srslte_pss_reset
+      for (int k = tid; k < kAvgLen; k += kTrackThreads) S.avg[k] = 0.f;
+    }
+    if (S.do_emit) {
+      const long long E = S.emit_abs;
+      float2 *hf = nullptr;
+      if (P.hf_out != nullptr && S.rec_slot >= 0) hf = P.hf_out + (size_t)S.rec_slot * kHalf;
+      if (S.do_track) {
+        // ---- srslte_pss_cfo_compute on out[832..960) (lib/pss_impl.cc:199) --------------
+        if (tid < 2) {
+          float yr_ = 0.f, yi_ = 0.f;
+          const int nb = tid * 64;
+          for (int n = nb; n < nb + 64; ++n) {
+            const float2 h = c_pss_taps[n_id_2][n];
+            const float2 r = yr[(unsigned)((E + 832 + n) & P.cap_mask)];
+            yr_ = __fmaf_rn(h.x, r.x, yr_); yr_ = __fmaf_rn(-h.y, r.y, yr_);
+            yi_ = __fmaf_rn(h.x, r.y, yi_); yi_ = __fmaf_rn(h.y, r.x, yi_);
+          }
+          S.y01[tid] = make_float2(yr_, yi_);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          ChainState &st = S.st;
+          const float2 y0 = S.y01[0], y1 = S.y01[1];
+          const float pre = __fmaf_rn(y0.x, y1.x, __fmul_rn(y0.y, y1.y));       // conj(y0)*y1
+          const float pim = __fmaf_rn(y0.x, y1.y, -__fmul_rn(y0.y, y1.x));
+          const float cfo = (float)__ddiv_rn(canon_atan2((double)pim, (double)pre), 3.14159265358979323846);
+          st.cfo_data[st.cfo_i++ % kMavg] = cfo;                                 // :200
+          unsigned npts = st.cfo_i > (unsigned)kMavg ? (unsigned)kMavg : st.cfo_i;
+          double acc = 0.0;
+          for (unsigned i = 0; i < npts; ++i) acc = __dadd_rn(acc, (double)st.cfo_data[i]);
+          const float mcfo = (float)__ddiv_rn(acc, (double)npts);
+          const float freq = __fdiv_rn(-mcfo, 128.0f);                           // :204
+          if (fabsf(__fadd_rn(st.cfo_last_freq, -freq)) > 0.0f) { st.cfo_last_freq = freq; st.cfo_table_freq = freq; }
+          if (S.rec_slot >= 0) { P.recs[S.rec_slot].cfo = cfo; P.recs[S.rec_slot].mean_cfo = mcfo; }
+        }
+        __syncthreads();
+        // ---- srslte_cfo_correct: phasor index scan (sequential float phase), then rotate -----
+        const float phase_inc = __fmul_rn(S.st.cfo_table_freq, 4096.0f);
+        const int n_blocks = hf ? 10 : 1;
+        float phase = 0.f;       // carried by thread 0 across blocks
+        for (int b = 0; b < n_blocks; ++b) {
+          if (tid == 0) {
+            for (int i = 0; i < 960; ++i) {
+              while (phase >= 4096.0f) phase = __fadd_rn(phase, -4096.0f);
+              while (phase < 0.f) phase = __fadd_rn(phase, 4096.0f);
+              S.ph_idx[i] = (unsigned short)(unsigned)phase;
+              phase = __fadd_rn(phase, phase_inc);
+            }
+          }
+          __syncthreads();
+          if (b == 0) {
+            for (int i = tid; i < 480; i += kTrackThreads) {
+              const float2 x = yr[(unsigned)((E + 480 + i) & P.cap_mask)];
+              S.rot[i] = cmul_canon(P.cexp[S.ph_idx[480 + i]], x);
+            }
+          }
+          if (hf) {
+            for (int i = tid; i < 960; i += kTrackThreads) {
+              const float2 x = yr[(unsigned)((E + b * 960 + i) & P.cap_mask)];
+              hf[b * 960 + i] = cmul_canon(P.cexp[S.ph_idx[i]], x);
+            }
+          }
+          __syncthreads();
+        }
+        // ---- srslte_sync_detect_cp(in, 960) (lib/sss_impl.cc:104) ----------------------------
+        if (tid < 12) {
+          const int h = tid / 6, sy = (tid % 6) / 2, kind = tid & 1;
+          const int cp = h ? 32 : 9;
+          const int j0 = 960 - 3 * (128 + cp) + sy * (128 + cp) - 480;   // index into rot
+          float acc = 0.f;
+          if (kind == 0) {
+            for (int i = 0; i < cp; ++i) {
+              acc = __fmaf_rn(S.rot[j0 + 128 + i].x, S.rot[j0 + i].x, acc);
+              acc = __fmaf_rn(S.rot[j0 + 128 + i].y, S.rot[j0 + i].y, acc);
+            }
+          } else {
+            for (int i = 0; i < cp; ++i) {
+              acc = __fmaf_rn(S.rot[j0 + i].x, S.rot[j0 + i].x, acc);
+              acc = __fmaf_rn(S.rot[j0 + i].y, S.rot[j0 + i].y, acc);
+            }
+          }
+          S.cp_part[tid] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          ChainState &st = S.st;
+          float Rv[2], Mv[2];
+          for (int h = 0; h < 2; ++h) {
+            const float cpf = h ? 32.0f : 9.0f;
+            float Rs = 0.f, Cs = 0.f;
+            for (int sy = 0; sy < 3; ++sy) {
+              Rs = __fadd_rn(Rs, S.cp_part[h * 6 + sy * 2]);
+              Cs = __fadd_rn(Cs, __fmul_rn(cpf, __fdiv_rn(S.cp_part[h * 6 + sy * 2 + 1], cpf)));
+            }
+            Rv[h] = Rs;
+            Mv[h] = (Cs > 0.f) ? __fdiv_rn(Rs, Cs) : 0.f;
+          }
+          const float mn = __fdiv_rn(Mv[0], 3.0f), me = __fdiv_rn(Mv[1], 3.0f);
+          const double one_m = __dadd_rn(1.0, -0.1);
+          st.cp_norm_avg = (float)__dadd_rn(__dmul_rn(0.1, (double)mn), __dmul_rn(one_m, (double)st.cp_norm_avg));
+          st.cp_ext_avg = (float)__dadd_rn(__dmul_rn(0.1, (double)me), __dmul_rn(one_m, (double)st.cp_ext_avg));
+          int cp_norm;
+          if (st.cp_norm_avg > st.cp_ext_avg) cp_norm = 1;
+          else if (st.cp_norm_avg < st.cp_ext_avg) cp_norm = 0;
+          else cp_norm = Rv[0] > Rv[1] ? 1 : 0;
+          S.cp_len = cp_norm ? 9 : 32;
+          S.sss_slot = -1;
+          if (S.rec_slot >= 0) {
+            ltb_window_rec &r = P.recs[S.rec_slot];
+            r.flags |= LTB_F_SSS | (cp_norm ? LTB_F_CP_NORM : 0u);
+            r.cp_norm_avg = st.cp_norm_avg; r.cp_ext_avg = st.cp_ext_avg;
+            const int slot = atomicAdd(P.sss_count, 1);
+            if (slot < P.sss_cap) { S.sss_slot = slot; P.sss_rec[slot] = S.rec_slot; }
+          }
+        }
+        __syncthreads();
+        if (S.sss_slot >= 0 && tid < 128) {
+          const int sss_idx = kSlot - 2 * kSym - S.cp_len;             // lib/sss_impl.cc:110
+          P.sss_sym[(size_t)S.sss_slot * 128 + tid] = S.rot[sss_idx - 480 + tid];
+        }
+      } else if (hf) {
+        for (int i = tid; i < kHalf; i += kTrackThreads) hf[i] = yr[(unsigned)((E + i) & P.cap_mask)];
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) { P.state[chain] = S.st; P.rec_count[chain] = n_rec; }
+  for (int k = tid; k < kAvgLen; k += kTrackThreads) avg_g[k] = S.avg[k];
+}
+
+// ------------------------------------------------------------------------------------
+// K4: batched SSS decode -- srslte_sss_m0m1_partial(M=1, ce=NULL) + srslte_sss_N_id_1 +
+//     srslte_sync_get_cell_id (lib/sss_impl.cc:112-124) -- one warp per candidate symbol.
+// ------------------------------------------------------------------------------------
+constexpr int kSssWarps = 4;
+
+__device__ __forceinline__ void fft128_warp(float2 *a, int lane) {
+  // radix-2 DIT on bit-reversed input in shared memory a[128]; 64 butterflies per stage,
+  // two per lane.  Same butterfly as the oracle: t = w*b (canonical), a' = a+t, b' = a-t.
+#pragma unroll
+  for (int half = 1; half < 128; half <<= 1) {
+    const int step = 64 / half;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int bf = lane + rep * 32;            // butterfly id 0..63
+      const int j = bf & (half - 1);
+      const int base = (bf / half) * 2 * half;
+      const float2 w = c_fft128_tw[j * step];
+      const float2 b = a[base + j + half];
+      const float2 u = a[base + j];
+      const float2 tw = cmul_canon(w, b);
+      a[base + j] = make_float2(__fadd_rn(u.x, tw.x), __fadd_rn(u.y, tw.y));
+      a[base + j + half] = make_float2(__fadd_rn(u.x, -tw.x), __fadd_rn(u.y, -tw.y));
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ int sss_corr_argmax(const float2 *y, int lane, float *val_out) {
+  // lane m < 31: |sum_i y[i] * s_tilde[(i+m)%31]|^2, sequential i; first-index argmax
+  float v = -3.402823466e+38f;
+  if (lane < 31) {
+    float ar = 0.f, ai = 0.f;
+    for (int i = 0; i < 31; ++i) {
+      const float sv = c_sss_s[(i + lane) % 31];
+      ar = __fmaf_rn(y[i].x, sv, ar);
+      ai = __fmaf_rn(y[i].y, sv, ai);
+    }
+    v = __fmaf_rn(ar, ar, __fmul_rn(ai, ai));
+  }
+  int idx = lane;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ov = __shfl_down_sync(0xffffffffu, v, off);
+    const int oi = __shfl_down_sync(0xffffffffu, idx, off);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  idx = __shfl_sync(0xffffffffu, idx, 0);
+  *val_out = __shfl_sync(0xffffffffu, v, 0);
+  return idx;
+}
+
+__global__ void __launch_bounds__(kSssWarps * 32) sss_kernel(const float2 *__restrict__ sss_sym,
+                                                              const int *__restrict__ sss_rec,
+                                                              const int *__restrict__ sss_count, int sss_cap,
+                                                              ltb_window_rec *__restrict__ recs) {
+  __shared__ float2 sa[kSssWarps][128];
+  __shared__ float2 sy[kSssWarps][2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int count = *sss_count;
+  if (count > sss_cap) count = sss_cap;
+  for (int slot = blockIdx.x * kSssWarps + warp; slot < count; slot += gridDim.x * kSssWarps) {
+    float2 *a = sa[warp];
+    for (int i = lane; i < 128; i += 32) a[__brev((unsigned)i) >> 25] = sss_sym[(size_t)slot * 128 + i];
+    __syncwarp();
+    fft128_warp(a, lane);
+    ltb_window_rec &r = recs[sss_rec[slot]];
+    const int n_id_2 = r.n_id_2;
+    if (lane < 31) {
+      const int e = 2 * lane, o = 2 * lane + 1;
+      const int be = (e < 31) ? 97 + e : e - 30;
+      const int bo = (o < 31) ? 97 + o : o - 30;
+      const float c0 = c_sss_c0[n_id_2][lane], c1 = c_sss_c1[n_id_2][lane];
+      sy[warp][0][lane] = make_float2(__fmul_rn(a[be].x, c0), __fmul_rn(a[be].y, c0));
+      sy[warp][1][lane] = make_float2(__fmul_rn(a[bo].x, c1), __fmul_rn(a[bo].y, c1));
+    }
+    __syncwarp();
+    float m0v, m1v;
+    const int m0 = sss_corr_argmax(sy[warp][0], lane, &m0v);
+    if (lane < 31) {
+      const float z = c_sss_z[(lane + (m0 % 8)) % 31];
+      sy[warp][1][lane] = make_float2(__fmul_rn(sy[warp][1][lane].x, z), __fmul_rn(sy[warp][1][lane].y, z));
+    }
+    __syncwarp();
+    const int m1 = sss_corr_argmax(sy[warp][1], lane, &m1v);
+    if (lane == 0) {
+      int nid = -1;
+      const unsigned um0 = (unsigned)m0, um1 = (unsigned)m1;
+      if (um1 > um0) { if (um0 < 30u && um1 - 1u < 30u) nid = c_sss_nid1[um0 * 30 + (um1 - 1)]; }
+      else           { if (um1 < 30u && um0 - 1u < 30u) nid = c_sss_nid1[um1 * 30 + (um0 - 1)]; }
+      r.m0 = m0; r.m1 = m1; r.m0_val = m0v; r.m1_val = m1v; r.n_id_1 = nid;
+      if (nid >= 0) { r.cell_id = 3 * nid + n_id_2; r.flags |= LTB_F_CELL; }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// standalone sss block: CP detection + symbol extraction for n consecutive half-frames of one
+// chain (sequential EMA), feeding sss_kernel.  One CTA.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sss_block_front_kernel(const float2 *__restrict__ hf, const int *__restrict__ tag_lost,
+                                                              int n_hf, int n_id_2, float *cp_state /*2*/,
+                                                              ltb_window_rec *recs, float2 *sss_sym, int *sss_rec,
+                                                              int *sss_count) {
+  __shared__ float part[12];
+  __shared__ int s_cp_len, s_slot;
+  const int tid = threadIdx.x;
+  float cpn = cp_state[0], cpe = cp_state[1];
+  for (int f = 0; f < n_hf; ++f) {
+    const float2 *in = hf + (size_t)f * kHalf;
+    if (tag_lost[f]) { cpn = 0.f; cpe = 0.f; __syncthreads(); continue; }
+    if (tid < 12) {
+      const int h = tid / 6, sy = (tid % 6) / 2, kind = tid & 1;
+      const int cp = h ? 32 : 9;
+      const int j0 = 960 - 3 * (128 + cp) + sy * (128 + cp);
+      float acc = 0.f;
+      if (kind == 0) {
+        for (int i = 0; i < cp; ++i) {
+          acc = __fmaf_rn(in[j0 + 128 + i].x, in[j0 + i].x, acc);
+          acc = __fmaf_rn(in[j0 + 128 + i].y, in[j0 + i].y, acc);
+        }
+      } else {
+        for (int i = 0; i < cp; ++i) {
+          acc = __fmaf_rn(in[j0 + i].x, in[j0 + i].x, acc);
+          acc = __fmaf_rn(in[j0 + i].y, in[j0 + i].y, acc);
+        }
+      }
+      part[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float Rv[2], Mv[2];
+      for (int h = 0; h < 2; ++h) {
+        const float cpf = h ? 32.0f : 9.0f;
+        float Rs = 0.f, Cs = 0.f;
+        for (int sy = 0; sy < 3; ++sy) {
+          Rs = __fadd_rn(Rs, part[h * 6 + sy * 2]);
+          Cs = __fadd_rn(Cs, __fmul_rn(cpf, __fdiv_rn(part[h * 6 + sy * 2 + 1], cpf)));
+        }
+        Rv[h] = Rs;
+        Mv[h] = (Cs > 0.f) ? __fdiv_rn(Rs, Cs) : 0.f;
+      }
+      const float mn = __fdiv_rn(Mv[0], 3.0f), me = __fdiv_rn(Mv[1], 3.0f);
+      const double one_m = __dadd_rn(1.0, -0.1);
+      cpn = (float)__dadd_rn(__dmul_rn(0.1, (double)mn), __dmul_rn(one_m, (double)cpn));
+      cpe = (float)__dadd_rn(__dmul_rn(0.1, (double)me), __dmul_rn(one_m, (double)cpe));
+      int cp_norm;
+      if (cpn > cpe) cp_norm = 1; else if (cpn < cpe) cp_norm = 0; else cp_norm = Rv[0] > Rv[1] ? 1 : 0;
+      s_cp_len = cp_norm ? 9 : 32;
+      ltb_window_rec &r = recs[f];
+      r.n_id_2 = n_id_2;
+      r.flags |= LTB_F_SSS | (cp_norm ? LTB_F_CP_NORM : 0u);
+      r.cp_norm_avg = cpn; r.cp_ext_avg = cpe;
+      r.m0 = r.m1 = -1; r.n_id_1 = -1; r.cell_id = -1;
+      s_slot = atomicAdd(sss_count, 1);
+      sss_rec[s_slot] = f;
+    }
+    __syncthreads();
+    // broadcast the EMA state held by thread 0 to the others through shared memory
+    {
+      __shared__ float s_cpn, s_cpe;
+      if (tid == 0) { s_cpn = cpn; s_cpe = cpe; }
+      __syncthreads();
+      cpn = s_cpn; cpe = s_cpe;
+    }
+    const int sss_idx = kSlot - 2 * kSym - s_cp_len;
+    sss_sym[(size_t)s_slot * 128 + tid] = in[sss_idx + tid];
+    __syncthreads();
+  }
+  if (tid == 0) { cp_state[0] = cpn; cp_state[1] = cpe; }
+}
+
+}  // namespace ltb

@@ -1,0 +1,153 @@
+// Constant tables.  All values are computed in double precision on the host and rounded
+// to float once; the device kernels only ever see these floats.
+//
+// Reference call sites these stand in for:
+//   srslte_pss_init / srslte_pss_set_N_id_2     lib/pss_impl.cc:72-75
+//   srslte_cfo_init (cexptab)                   lib/pss_impl.cc:78
+//   srslte_sync_init / srslte_sss_set_N_id_2    lib/sss_impl.cc:63-70
+//   gr_filter.rational_resampler_ccc(1, D)      examples/cell_search_file.py:56-57
+#include "ltb_tables.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace ltb {
+
+namespace {
+const double kPi = 3.14159265358979323846;
+
+inline double unit_cos(int j) { return std::cos(2.0 * kPi * (double)(j & 127) / 128.0); }
+inline double unit_sin(int j) { return std::sin(2.0 * kPi * (double)(j & 127) / 128.0); }
+
+// 36.211 6.11.1.1 Zadoff-Chu root sequence; the angle is reduced with integer arithmetic
+// (u*k mod 126) so d[i] == d[61-i] holds exactly and root 34 is the conjugate of root 29.
+void zadoff_chu(int root, double *dre, double *dim) {
+  for (int i = 0; i < 62; ++i) {
+    const long k = (i < 31) ? (long)i * (i + 1) : (long)(i + 1) * (i + 2);
+    const long r = ((long)root * k) % 126;
+    const double ang = -kPi * (double)r / 63.0;
+    dre[i] = std::cos(ang);
+    dim[i] = std::sin(ang);
+  }
+}
+
+// modified Bessel I0 by its power series (gr::fft::window::kaiser's Izero)
+double bessel_i0(double x) {
+  double sum = 1, u = 1;
+  const double halfx = x / 2.0;
+  int n = 1;
+  do {
+    double t = halfx / (double)n;
+    n += 1;
+    t *= t;
+    u *= t;
+    sum += u;
+  } while (u >= 1e-21 * sum);
+  return sum;
+}
+
+void m_sequence(const int *taps, int ntaps, int *out) {
+  int x[31];
+  std::memset(x, 0, sizeof x);
+  x[4] = 1;
+  for (int i = 0; i < 26; ++i) {
+    int acc = 0;
+    for (int t = 0; t < ntaps; ++t) acc += x[i + taps[t]];
+    x[i + 5] = acc % 2;
+  }
+  for (int i = 0; i < 31; ++i) out[i] = 1 - 2 * x[i];
+}
+}  // namespace
+
+void make_pss_taps(int n_id_2, PssTaps &out) {
+  double dre[62], dim[62];
+  zadoff_chu(n_id_2 == 0 ? 25 : 29, dre, dim);
+  const double scale = 1.0 / std::sqrt(128.0) / 62.0;
+  for (int n = 0; n <= 64; ++n) {
+    double tr = 0.0, ti = 0.0;
+    for (int i = 0; i < 62; ++i) {
+      const int bin = (i < 31) ? i - 31 : i - 30;   // -31..-1, +1..+31 (DC empty)
+      const int j = ((bin * n) % 128 + 128) % 128;
+      const double c = unit_cos(j), s = unit_sin(j);
+      tr += dre[i] * c - dim[i] * s;
+      ti += dre[i] * s + dim[i] * c;
+    }
+    out.re[n] = (float)(tr * scale);
+    out.im[n] = (float)(-ti * scale);
+    if (n_id_2 == 2) out.im[n] = -out.im[n];
+  }
+  for (int n = 65; n < 128; ++n) {
+    out.re[n] = out.re[128 - n];
+    out.im[n] = out.im[128 - n];
+  }
+}
+
+std::vector<float> make_decim_taps(int decim) {
+  std::vector<float> taps;
+  if (decim <= 1) return taps;
+  const double beta = 7.0, fractional_bw = 0.4, halfband = 0.5;
+  const double rate = 1.0 / (double)decim;
+  const double trans_width = rate * (halfband - fractional_bw);
+  const double mid = rate * halfband - trans_width / 2.0;
+  const double atten = beta / 0.1102 + 8.7;
+  int ntaps = (int)(atten * 1.0 / (22.0 * trans_width));
+  if ((ntaps & 1) == 0) ntaps++;
+  std::vector<float> w(ntaps);
+  const double ibeta = 1.0 / bessel_i0(beta), inm1 = 1.0 / (double)(ntaps - 1);
+  for (int i = 0; i < ntaps; ++i) {
+    const double t = 2 * i * inm1 - 1;
+    w[i] = (float)(bessel_i0(beta * std::sqrt(1.0 - t * t)) * ibeta);
+  }
+  taps.resize(ntaps);
+  const int M = (ntaps - 1) / 2;
+  const double fwT0 = 2 * kPi * mid / 1.0;
+  for (int n = -M; n <= M; ++n) {
+    if (n == 0) taps[n + M] = (float)(fwT0 / kPi * w[n + M]);
+    else        taps[n + M] = (float)(std::sin(n * fwT0) / (n * kPi) * w[n + M]);
+  }
+  double fmax = taps[M];
+  for (int n = 1; n <= M; ++n) fmax += 2 * taps[n + M];
+  const double gain = 1.0 / fmax;
+  for (int i = 0; i < ntaps; ++i) taps[i] = (float)(taps[i] * gain);
+  return taps;
+}
+
+void make_sss_tables(int n_id_2, SssTables &out) {
+  int c_tilde[31];
+  const int s_taps[2] = {2, 0}, c_taps[2] = {3, 0}, z_taps[4] = {4, 2, 1, 0};
+  m_sequence(s_taps, 2, out.s_tilde);
+  m_sequence(c_taps, 2, c_tilde);
+  m_sequence(z_taps, 4, out.z_tilde);
+  for (int i = 0; i < 31; ++i) {
+    out.c0[i] = c_tilde[(i + n_id_2) % 31];
+    out.c1[i] = c_tilde[(i + n_id_2 + 3) % 31];
+  }
+  std::memset(out.n_id_1, 0, sizeof out.n_id_1);
+  for (int nid = 0; nid < 168; ++nid) {
+    const int qp = nid / 30;
+    const int q = (nid + qp * (qp + 1) / 2) / 30;
+    const int mp = nid + q * (q + 1) / 2;
+    const int m0 = mp % 31;
+    const int m1 = (m0 + mp / 31 + 1) % 31;
+    out.n_id_1[m0 * 30 + (m1 - 1)] = nid;
+  }
+}
+
+void make_cexp_table(float *re, float *im) {
+  for (int i = 0; i < 4096; ++i) {
+    const double a = 2.0 * kPi * (double)i / 4096.0;
+    re[i] = (float)std::cos(a);
+    im[i] = (float)std::sin(a);
+  }
+  re[4096] = re[0];
+  im[4096] = im[0];
+}
+
+void make_fft128_twiddles(float *re, float *im) {
+  for (int k = 0; k < 64; ++k) {
+    re[k] = (float)unit_cos(k);
+    im[k] = (float)(-unit_sin(k));
+  }
+}
+
+}  // namespace ltb

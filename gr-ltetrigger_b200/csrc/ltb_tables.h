@@ -1,0 +1,26 @@
+// Host-side constant tables of the PSS+SSS search path (see DESIGN.md "Canonical tables").
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace ltb {
+
+struct PssTaps { float re[128]; float im[128]; };
+
+// srslte_pss_init_N_id_2 restated: conj(IDFT_128(ZC_u))/sqrt(128)/62, taps 0..64 rounded to
+// float, 65..127 mirrored; N_id_2 = 2 is the exact conjugate of N_id_2 = 1.
+void make_pss_taps(int n_id_2, PssTaps &out);
+
+// gr-filter rational_resampler.design_filter(1, decim, 0.4) -> firdes.low_pass(Kaiser, beta 7)
+std::vector<float> make_decim_taps(int decim);
+
+struct SssTables {
+  int32_t c0[31], c1[31], s_tilde[31], z_tilde[31];
+  int32_t n_id_1[900];
+};
+void make_sss_tables(int n_id_2, SssTables &out);
+
+void make_cexp_table(float *re, float *im);        // 4097 entries
+void make_fft128_twiddles(float *re, float *im);   // 64 entries
+
+}  // namespace ltb

@@ -1,0 +1,280 @@
+"""Drop-in mirrors of the reference's blocks for the PSS+SSS path.
+
+    ltetrigger.pss                 include/ltetrigger/pss.h:36-88,  lib/pss_impl.cc
+    ltetrigger.sss                 include/ltetrigger/sss.h:36-52,  lib/sss_impl.cc
+    ltetrigger.downlink_trigger_c  python/downlink_trigger_c.py:13-73
+
+Same constructor arguments, accessors, stream-tag keys/values and message-port names.
+GNU Radio itself is not importable here, so the classes expose the block contract
+(`history`, `output_multiple`, `general_work`/`work`, `consume_each`, tags) as plain
+Python; `gr_emu.py` drives them the way the GR scheduler would.  All arithmetic runs in
+the CUDA library (no CPU fallback).  pmt values are represented as: PMT_NIL -> None,
+PMT_T/PMT_F -> True/False, pmt.from_long -> int.
+"""
+import ctypes as C
+from collections import deque
+
+import numpy as np
+
+from . import _abi as A
+from .engine import Trigger
+
+SLOT_LENGTH = 960
+HALF_FRAME_LENGTH = 10 * SLOT_LENGTH
+SYMBOL_SZ = 128
+
+TRACKING_LOST_TAG_KEY = "tracking_lost"     # lib/pss_impl.cc:39-40
+CELL_ID_TAG_KEY = "cell_id"                 # lib/sss_impl.cc:38
+CP_TYPE_TAG_KEY = "cp_type"                 # lib/sss_impl.cc:40
+
+
+class tag_t:
+    """gr::tag_t: absolute item offset, key, value."""
+    __slots__ = ("offset", "key", "value")
+
+    def __init__(self, offset, key, value):
+        self.offset, self.key, self.value = offset, key, value
+
+    def __repr__(self):
+        return "tag_t(%d, %r, %r)" % (self.offset, self.key, self.value)
+
+
+class _block:
+    """The slice of gr::block both mirrors need."""
+
+    def __init__(self, name):
+        self._name = name
+        self._history = 1
+        self._output_multiple = 1
+        self._nitems_read = 0
+        self._nitems_written = 0
+        self._consumed = 0
+        self._out_tags = []
+        self._in_tags = []
+
+    def name(self): return self._name
+    def history(self): return self._history
+    def set_history(self, h): self._history = h
+    def output_multiple(self): return self._output_multiple
+    def set_output_multiple(self, m): self._output_multiple = m
+    def nitems_read(self, port=0): return self._nitems_read
+    def nitems_written(self, port=0): return self._nitems_written
+    def consume_each(self, n): self._consumed = n
+    def add_item_tag(self, port, offset, key, value): self._out_tags.append(tag_t(offset, key, value))
+
+    def get_tags_in_window(self, port, rel_start, rel_end, key=None):
+        a, b = self._nitems_read + rel_start, self._nitems_read + rel_end
+        return [t for t in self._in_tags if a <= t.offset < b and (key is None or t.key == key)]
+
+
+class pss(_block):
+    """ltetrigger.pss(N_id_2, psr_threshold, track_after=16, track_every=8)
+
+    One general_work call handles exactly one 9600-sample window, as in the reference
+    (lib/pss_impl.cc:154-223): returns 0 or 9600 produced items, consumes 9600 (drop) or
+    peak_pos-960+9600 (emit), tags the first item of every half-frame emitted while not
+    tracking with "tracking_lost".  The forecast asks for the reference's history plus the
+    largest possible consume (9599 + 18365 items) so a call never reads past its input.
+    """
+
+    def __init__(self, N_id_2, psr_threshold, track_after=16, track_every=8, device=0, max_chunk=1 << 18):
+        _block.__init__(self, "pss")
+        if N_id_2 not in (0, 1, 2):
+            raise RuntimeError("Error initializing PSS N_id_2")          # lib/pss_impl.cc:75-76
+        self._n_id_2 = N_id_2
+        self._engine = Trigger(1, decim=1, psr_threshold=psr_threshold, max_chunk=max_chunk,
+                               track_after=track_after, track_every=track_every, record_all=True,
+                               keep_halfframes=True, device=device, root_mask=1 << N_id_2)
+        # pss applies no clamp of its own (the hier block does): set the raw value
+        self._engine.set_psr_threshold(psr_threshold, clamp=False)
+        self._max_chunk = max_chunk
+        self._pushed = 0                       # absolute count of samples handed to the engine
+        self._queue = deque()                  # (record, halfframe or None) not yet released
+        self.set_history(HALF_FRAME_LENGTH)    # :81
+        self.set_output_multiple(HALF_FRAME_LENGTH)   # :82
+
+    def forecast(self, noutput_items):
+        return [self.history() - 1 + A.LOOKAHEAD]
+
+    # accessors, lib/pss_impl.h:95-100
+    def max_psr(self): return self._engine.stats(0, self._n_id_2).max_psr
+    def mean_psr(self): return self._engine.stats(0, self._n_id_2).mean_psr
+    def mean_cfo(self): return self._engine.stats(0, self._n_id_2).mean_cfo
+    def psr_threshold(self): return self._engine.stats(0, self._n_id_2).psr_threshold
+    def tracking_score(self): return self._engine.stats(0, self._n_id_2).tracking_score
+    def set_psr_threshold(self, threshold): self._engine.set_psr_threshold(threshold, clamp=False)
+
+    def _push(self, samples):
+        step = 8
+        n = len(samples) // step * step
+        pos = 0
+        while pos < n:
+            take = min(n - pos, self._max_chunk)
+            recs = self._engine.process(samples[None, pos:pos + take])
+            n_emit = int(((recs["flags"] & A.F_EMIT) != 0).sum())
+            hfs = self._engine.fetch_halfframes(n_emit) if n_emit else None
+            k = 0
+            for r in recs:
+                if r["flags"] & A.F_EMIT:
+                    self._queue.append((r.copy(), hfs[k].copy()))
+                    k += 1
+                else:
+                    self._queue.append((r.copy(), None))
+            pos += take
+        self._pushed += n
+
+    def general_work(self, noutput_items, ninput_items, input_items, output_items):
+        """input_items[0]: complex64 view whose element history()-1 is the first new item."""
+        inp = input_items[0]
+        first_new = self.history() - 1
+        avail_end = self._nitems_read + (ninput_items[0] - first_new)     # absolute end of readable input
+        if avail_end > self._pushed:
+            off = first_new + (self._pushed - self._nitems_read)
+            self._push(np.ascontiguousarray(inp[off:off + (avail_end - self._pushed)], np.complex64))
+        if not self._queue:
+            self.consume_each(0)
+            return 0
+        rec, hf = self._queue.popleft()
+        assert rec["win_start"] == self._nitems_read, (rec["win_start"], self._nitems_read)
+        if rec["flags"] & A.F_EMIT:
+            nconsume = int(rec["emit_start"] - rec["win_start"]) + HALF_FRAME_LENGTH
+            output_items[0][:HALF_FRAME_LENGTH] = hf
+            if rec["flags"] & A.F_TAG_LOST:
+                self.add_item_tag(0, self.nitems_written(0), TRACKING_LOST_TAG_KEY, None)
+            self.consume_each(nconsume)
+            self.last_record = rec
+            return HALF_FRAME_LENGTH
+        self.consume_each(HALF_FRAME_LENGTH)
+        self.last_record = rec
+        return 0
+
+
+class sss(_block):
+    """ltetrigger.sss(N_id_2): gr::sync_block, one aligned half-frame per work call
+    (lib/sss_impl.cc:83-156).  Consumes "tracking_lost", emits "cell_id" (int) and
+    "cp_type" (True = normal) on item 0 of each decoded half-frame, passes samples through."""
+
+    def __init__(self, N_id_2, device=0):
+        _block.__init__(self, "sss")
+        self._n_id_2 = N_id_2
+        self._h = C.c_void_p()
+        rc = A.lib().ltb_sss_create(device, N_id_2, C.byref(self._h))
+        if rc != A.SUCCESS:
+            raise RuntimeError(A.lib().ltb_last_error().decode() or "Error initializing SSS SYNC")
+        self.set_output_multiple(HALF_FRAME_LENGTH)
+        self.last_record = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            A.lib().ltb_sss_destroy(self._h)
+            self._h = None
+
+    def work(self, noutput_items, input_items, output_items):
+        inp = np.ascontiguousarray(input_items[0][:HALF_FRAME_LENGTH], np.complex64)
+        lost = self.get_tags_in_window(0, 0, 1, TRACKING_LOST_TAG_KEY)
+        rec = np.zeros(1, A.WINDOW_REC)
+        rec["m0"] = rec["m1"] = rec["n_id_1"] = rec["cell_id"] = -1
+        tag = np.array([1 if lost else 0], np.int32)
+        A.check(A.lib().ltb_sss_work(self._h, inp.ctypes.data, tag.ctypes.data, 1, rec.ctypes.data), "ltb_sss_work")
+        self.last_record = rec[0]
+        if lost:
+            output_items[0][:HALF_FRAME_LENGTH] = inp
+            return HALF_FRAME_LENGTH
+        if not (rec[0]["flags"] & A.F_CELL):
+            return HALF_FRAME_LENGTH            # :119-120: no tags, output not written
+        self.add_item_tag(0, self.nitems_written(0), CELL_ID_TAG_KEY, int(rec[0]["cell_id"]))
+        self.add_item_tag(0, self.nitems_written(0), CP_TYPE_TAG_KEY, bool(rec[0]["flags"] & A.F_CP_NORM))
+        output_items[0][:HALF_FRAME_LENGTH] = inp
+        return HALF_FRAME_LENGTH
+
+
+class _chain_view:
+    """What `downlink_trigger_c.pssK` exposes: the pss accessors of chain K of the fused engine
+    (GRC probes poll e.g. pss0.tracking_score, examples/rtlsdr_ltetrigger.grc:735-752)."""
+
+    def __init__(self, engine, k):
+        self._e, self._k = engine, k
+
+    def max_psr(self): return self._e.stats(0, self._k).max_psr
+    def mean_psr(self): return self._e.stats(0, self._k).mean_psr
+    def mean_cfo(self): return self._e.stats(0, self._k).mean_cfo
+    def psr_threshold(self): return self._e.stats(0, self._k).psr_threshold
+    def tracking_score(self): return self._e.stats(0, self._k).tracking_score
+    def set_psr_threshold(self, t): self._e.set_psr_threshold(t, n_id_2=self._k, clamp=False)
+
+
+MIN_PSR_THRESHOLD = 1.5  # python/downlink_trigger_c.py:10
+
+
+class downlink_trigger_c:
+    """Hier block: one complex input at 1.92 Msps, three pss->sss chains, message ports
+    "track" and "drop" (python/downlink_trigger_c.py:18-61).
+
+    The three chains run fused in one batched engine (one stream, root_mask 7).  The mib
+    stage stays on the host as in the reference (lib/mib_impl.cc; out of scope here): tagged
+    half-frames are handed to `mib_sink(k, tags, halfframe)` if one is attached, and whatever
+    it returns for "track"/"drop" is forwarded to subscribers of those ports.
+    """
+
+    def __init__(self, psr_threshold, exit_on_success=False, device=0, max_chunk=1 << 18, keep_halfframes=False):
+        self.psr_threshold = self._ensure_safe_threshold(psr_threshold)
+        self.exit_on_success = exit_on_success
+        self._engine = Trigger(1, decim=1, psr_threshold=self.psr_threshold, max_chunk=max_chunk,
+                               record_all=True, keep_halfframes=keep_halfframes, device=device)
+        self._keep = keep_halfframes
+        self.pss0, self.pss1, self.pss2 = (_chain_view(self._engine, k) for k in range(3))
+        self._ports = {"track": [], "drop": []}
+        self.mib_sink = None
+        self._carry = np.zeros(0, np.complex64)
+        self.records = []
+
+    def message_ports(self): return list(self._ports)
+    def msg_connect(self, port, callback): self._ports[port].append(callback)
+
+    def set_psr_threshold(self, t):
+        t = self._ensure_safe_threshold(t)
+        self.psr_threshold = t
+        self._engine.set_psr_threshold(t, clamp=True)
+
+    @staticmethod
+    def _ensure_safe_threshold(t):
+        return t if t > MIN_PSR_THRESHOLD else MIN_PSR_THRESHOLD
+
+    def work(self, samples):
+        """Consume a run of input items; returns the stream tags produced by the three sss
+        blocks as (k, tag_t) pairs (offsets count items written by chain k's pss)."""
+        x = np.concatenate([self._carry, np.asarray(samples, np.complex64)])
+        n = len(x) // 8 * 8
+        self._carry = x[n:].copy()
+        tags = []
+        pos = 0
+        while pos < n:
+            take = min(n - pos, self._engine.max_chunk // 8 * 8)
+            recs = self._engine.process(x[None, pos:pos + take])
+            hfs = None
+            if self._keep:
+                n_emit = int(((recs["flags"] & A.F_EMIT) != 0).sum())
+                hfs = self._engine.fetch_halfframes(n_emit) if n_emit else None
+            k_emit = 0
+            for r in recs:
+                self.records.append(r.copy())
+                if not (r["flags"] & A.F_EMIT):
+                    continue
+                k = int(r["n_id_2"])
+                off = getattr(self, "_written%d" % k, 0)
+                setattr(self, "_written%d" % k, off + HALF_FRAME_LENGTH)
+                these = []
+                if r["flags"] & A.F_TAG_LOST:
+                    these.append(tag_t(off, TRACKING_LOST_TAG_KEY, None))
+                if r["flags"] & A.F_CELL:
+                    these.append(tag_t(off, CELL_ID_TAG_KEY, int(r["cell_id"])))
+                    these.append(tag_t(off, CP_TYPE_TAG_KEY, bool(r["flags"] & A.F_CP_NORM)))
+                tags.extend((k, t) for t in these)
+                if self.mib_sink is not None:
+                    msgs = self.mib_sink(k, these, hfs[k_emit] if hfs is not None else None) or []
+                    for port, msg in msgs:
+                        for cb in self._ports[port]:
+                            cb(msg)
+                k_emit += 1
+            pos += take
+        return tags

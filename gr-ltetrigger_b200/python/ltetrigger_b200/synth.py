@@ -1,0 +1,130 @@
+"""Seeded synthetic LTE FDD downlink captures (BASELINE config C4/C5).
+
+Normal-CP frames with the 36.211 PSS (last symbol of slots 0 and 10) and SSS (the symbol
+before it, SF0/SF5 variants) on the 62 centre carriers and unit-power QPSK on every other
+occupied resource element, OFDM-modulated at 128*decim points (1.92*decim Msps), cut at a
+random timing offset, with complex AWGN at a requested SNR and an optional carrier offset.
+Models examples/snr_ltetrigger.grc (fixture x gain + Gaussian noise) of the reference.
+Pure numpy: this is input generation, not part of the search path.
+"""
+import numpy as np
+
+PSS_ROOTS = (25, 29, 34)
+
+
+def _mseq(taps):
+    x = [0, 0, 0, 0, 1] + [0] * 26
+    for i in range(26):
+        x[i + 5] = sum(x[i + t] for t in taps) % 2
+    return 1 - 2 * np.array(x[:31])
+
+
+S_TILDE, C_TILDE, Z_TILDE = _mseq((2, 0)), _mseq((3, 0)), _mseq((4, 2, 1, 0))
+
+
+def pss_freq(n_id_2):
+    u = PSS_ROOTS[n_id_2]
+    n = np.arange(62)
+    k = np.where(n < 31, n * (n + 1), (n + 1) * (n + 2))
+    return np.exp(-1j * np.pi * u * k / 63.0)
+
+
+def m0m1(n_id_1):
+    qp = n_id_1 // 30
+    q = (n_id_1 + qp * (qp + 1) // 2) // 30
+    mp = n_id_1 + q * (q + 1) // 2
+    m0 = mp % 31
+    return m0, (m0 + mp // 31 + 1) % 31
+
+
+def sss_freq(cell_id, subframe):
+    n_id_1, n_id_2 = cell_id // 3, cell_id % 3
+    m0, m1 = m0m1(n_id_1)
+    n = np.arange(31)
+    s0, s1 = S_TILDE[(n + m0) % 31], S_TILDE[(n + m1) % 31]
+    c0, c1 = C_TILDE[(n + n_id_2) % 31], C_TILDE[(n + n_id_2 + 3) % 31]
+    z0, z1 = Z_TILDE[(n + m0 % 8) % 31], Z_TILDE[(n + m1 % 8) % 31]
+    d = np.zeros(62)
+    if subframe == 0:
+        d[0::2], d[1::2] = s0 * c0, s1 * c1 * z0
+    else:
+        d[0::2], d[1::2] = s1 * c0, s0 * c1 * z1
+    return d
+
+
+def lte_frame(cell_id, decim=1, rng=None, n_frames=1):
+    """n_frames radio frames (19200*decim samples each) at 1.92*decim Msps, mean power ~1."""
+    rng = rng or np.random.default_rng(cell_id)
+    nfft = 128 * decim
+    n_used = {1: 72, 2: 180, 4: 300, 8: 600, 16: 1200}[decim]
+    half = n_used // 2
+    cp0, cp = 10 * decim, 9 * decim
+    nsym = 140 * n_frames
+    bits = rng.integers(0, 2, size=(nsym, n_used, 2)) * 2 - 1
+    qpsk = (bits[..., 0] + 1j * bits[..., 1]) / np.sqrt(2.0)
+    grid = np.zeros((nsym, nfft), np.complex128)
+    grid[:, 1:half + 1] = qpsk[:, half:]
+    grid[:, nfft - half:] = qpsk[:, :half]
+    pss = pss_freq(cell_id % 3)
+    for f in range(n_frames):
+        for slot, sf in ((0, 0), (10, 5)):
+            sym_pss = f * 140 + slot * 7 + 6
+            sym_sss = sym_pss - 1
+            for sym, seq in ((sym_pss, pss), (sym_sss, sss_freq(cell_id, sf))):
+                grid[sym, 1:37] = 0
+                grid[sym, nfft - 36:] = 0
+                grid[sym, 1:32] = seq[31:]
+                grid[sym, nfft - 31:] = seq[:31]
+    time = np.fft.ifft(grid, axis=1) * (nfft / np.sqrt(n_used))
+    out = np.empty(n_frames * 19200 * decim, np.complex128)
+    pos = 0
+    for s in range(nsym):
+        c = cp0 if s % 7 == 0 else cp
+        out[pos:pos + c] = time[s, nfft - c:]
+        out[pos + c:pos + c + nfft] = time[s]
+        pos += c + nfft
+    assert pos == len(out)
+    return out
+
+
+def capture(cell_id, n_samples, snr_db=None, decim=1, seed=0, offset=None, cfo_hz=0.0, noise_only=False):
+    """One capture of n_samples at 1.92*decim Msps as complex64."""
+    rng = np.random.default_rng([seed, cell_id, 0x5EED])
+    frame_len = 19200 * decim
+    if offset is None:
+        offset = int(rng.integers(0, frame_len))
+    n_frames = (offset + n_samples + frame_len - 1) // frame_len
+    # a few distinct frames tiled keeps generation cheap while payload still varies
+    uniq = min(n_frames, 4)
+    base = lte_frame(cell_id, decim, rng, uniq)
+    reps = (n_frames + uniq - 1) // uniq
+    sig = np.tile(base, reps)[offset:offset + n_samples]
+    if cfo_hz:
+        fs = 1.92e6 * decim
+        sig = sig * np.exp(2j * np.pi * cfo_hz / fs * np.arange(n_samples))
+    if noise_only:
+        sig = np.zeros_like(sig)
+    if snr_db is not None:
+        p_sig = 1.0
+        sigma = np.sqrt(p_sig / (10.0 ** (snr_db / 10.0)) / 2.0)
+        sig = sig + sigma * (rng.standard_normal(n_samples) + 1j * rng.standard_normal(n_samples))
+    return sig.astype(np.complex64)
+
+
+def batch(n_streams, n_samples, snr_db, decim=1, master_seed=1234, cell_ids=None):
+    """[n_streams, n_samples] complex64; cell ids dealt from a seeded permutation of 0..503."""
+    perm = np.random.default_rng(master_seed).permutation(504)
+    ids = np.array([perm[i % 504] for i in range(n_streams)]) if cell_ids is None else np.asarray(cell_ids)
+    out = np.empty((n_streams, n_samples), np.complex64)
+    for i in range(n_streams):
+        out[i] = capture(int(ids[i]), n_samples, snr_db, decim, seed=master_seed ^ i)
+    return out, ids
+
+
+def to_sc16(x, full_scale=4.0):
+    """Quantise complex64 to interleaved int16 (I, Q) with |x| = full_scale -> 32767."""
+    s = 32767.0 / full_scale
+    iq = np.empty(x.shape + (2,), np.int16)
+    iq[..., 0] = np.clip(np.round(x.real * s), -32768, 32767)
+    iq[..., 1] = np.clip(np.round(x.imag * s), -32768, 32767)
+    return iq

@@ -1,0 +1,200 @@
+/*
+ * ltetrigger_b200.h -- C ABI of libltetrigger_b200.so
+ *
+ * B200-native (sm_100a) implementation of the one hot path of NTIA/gr-ltetrigger:
+ * the LTE PSS+SSS synchronisation-signal search.  Plain C, caller-owned buffers, no
+ * exceptions, no torch/GNU Radio types.  Every entry point names the reference
+ * interface it replaces (paths are relative to the reference tree; "srslte_*" symbols
+ * are the srsLTE release_18_06_1 calls made from those lines -- the reference's inner
+ * FFI boundary).
+ *
+ * Return convention (same as srsLTE, tested at lib/sss_impl.cc:119):
+ *    0  LTB_SUCCESS
+ *   -1  LTB_ERROR                 (CUDA failure, no device, ...; see ltb_last_error)
+ *   -2  LTB_ERROR_INVALID_INPUTS
+ * One host thread per object at a time (as the reference's blocks: one scheduler
+ * thread calls work); accessors may be polled from other threads and are, like the
+ * reference's (lib/pss_impl.h:95-100), unsynchronised snapshots.
+ */
+#ifndef LTETRIGGER_B200_H
+#define LTETRIGGER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTB_API __attribute__((visibility("default")))
+
+#define LTB_SUCCESS               0
+#define LTB_ERROR                (-1)
+#define LTB_ERROR_INVALID_INPUTS (-2)
+
+/* geometry at the 1.92 Msps search rate (lib/pss_impl.h:52-55, lib/sss_impl.h:43-47) */
+#define LTB_SLOT_LEN      960
+#define LTB_HALF_FRAME    9600
+#define LTB_SYMBOL_SZ     128
+#define LTB_CONV_LEN      9726     /* lags examined per window by srslte_pss_find_pss */
+#define LTB_LOOKAHEAD     18365    /* largest consume of one general_work call: (9725-960)+9600 */
+#define LTB_MOVING_AVG_SZ 200      /* lib/pss_impl.h:31 */
+#define LTB_MIN_PSR_THRESHOLD 1.5f /* python/downlink_trigger_c.py:10 */
+
+/* input sample formats (little-endian interleaved I/Q) */
+#define LTB_FMT_FC32 0             /* gr_complex, 8 B/sample: what the reference consumes */
+#define LTB_FMT_SC16 1             /* int16 I/Q, 4 B/sample, scaled by 1/32768 on device */
+
+typedef struct { float re, im; } ltb_cf;
+
+/* ---- per-window record ---------------------------------------------------------
+ * One record per pss::general_work call of one chain (stream, N_id_2), carrying what
+ * the reference expresses as return values, consume counts, stream tags and the
+ * downstream sss::work result for the half-frame that call emitted.                */
+#define LTB_F_SEARCHED 0x01u  /* srslte_pss_find_pss ran (lib/pss_impl.cc:163-169) */
+#define LTB_F_OVER     0x02u  /* d_psr > d_psr_threshold (:174) */
+#define LTB_F_EMIT     0x04u  /* one aligned half-frame produced (:184-195) */
+#define LTB_F_TRACKING 0x08u  /* emitted in tracking state: CFO-corrected, no pss tag (:197-209) */
+#define LTB_F_TAG_LOST 0x10u  /* stream tag "tracking_lost" on item 0 (:210-213) */
+#define LTB_F_SSS      0x20u  /* sss::work decoded this half-frame (lib/sss_impl.cc:104-118) */
+#define LTB_F_CELL     0x40u  /* stream tags "cell_id" and "cp_type" attached (:141-150) */
+#define LTB_F_CP_NORM  0x80u  /* cp_type == PMT_T (normal CP) */
+
+typedef struct {
+  int64_t  win_start;    /* absolute search-rate index of the call's first new sample (nitems_read) */
+  int64_t  emit_start;   /* absolute index of the emitted half-frame's first sample; -1 if none */
+  int32_t  stream;
+  int32_t  n_id_2;
+  int32_t  win_index;    /* ordinal of the general_work call on this chain */
+  uint32_t flags;        /* LTB_F_* */
+  int32_t  peak_pos;     /* d_peak_pos used by this call (stale 960 on skipped searches) */
+  int32_t  score;        /* tracking_score() after the call */
+  float    psr;          /* d_psr (stale on skipped searches) */
+  float    peak_value;   /* averaged correlation power at the peak of the last search */
+  float    cfo;          /* srslte_pss_cfo_compute (tracking emits only) */
+  float    mean_cfo;     /* mean_cfo() used for the in-place correction */
+  int32_t  m0, m1;       /* srslte_sss_m0m1_partial results (-1 if SSS not run) */
+  float    m0_val, m1_val;
+  int32_t  n_id_1;       /* srslte_sss_N_id_1; -1 on SRSLTE_ERROR / not run */
+  int32_t  cell_id;      /* srslte_sync_get_cell_id = 3*N_id_1 + N_id_2; -1 if none */
+  float    cp_norm_avg, cp_ext_avg;  /* srslte_sync_detect_cp EMA state after the call */
+} ltb_window_rec;        /* 88 bytes */
+
+/* accessors of ltetrigger::pss (include/ltetrigger/pss.h:72-87, lib/pss_impl.h:95-100) */
+typedef struct {
+  float   max_psr;
+  float   mean_psr;
+  float   mean_cfo;
+  float   psr_threshold;
+  float   tracking_score;
+  int32_t tracking;      /* bool(d_tracking) */
+  int64_t next_window;   /* absolute index the chain's next general_work call starts at */
+} ltb_pss_stats;
+
+/* ---- batched trigger engine -----------------------------------------------------
+ * Replaces, for n_streams independent IQ streams at once, the stream path of
+ *   rational_resampler_ccc(1, decim)            examples/cell_search_file.py:56-57
+ *   -> downlink_trigger_c(psr_threshold)        python/downlink_trigger_c.py:18-45
+ *        3 x ( pss(N_id_2=k) -> sss(N_id_2=k) )   lib/pss_impl.cc, lib/sss_impl.cc
+ * up to (not including) the host-side mib block.  The GNU Radio scheduler's role is
+ * fixed to: a chain's general_work is called only while win_start + 18365 <= samples
+ * received, so results do not depend on how the stream is cut into chunks.          */
+typedef struct ltb_trigger ltb_trigger;
+
+typedef struct {
+  uint32_t struct_size;       /* sizeof(ltb_trigger_config), for ABI evolution */
+  int32_t  device;            /* CUDA device ordinal */
+  int32_t  n_streams;
+  int32_t  input_format;      /* LTB_FMT_* */
+  int32_t  decim;             /* input rate / 1.92 Msps: 1, 2, 4, 8 or 16 */
+  int32_t  root_mask;         /* bit k set: run the N_id_2 = k chain; 0 -> 7 (all three) */
+  int64_t  max_chunk;         /* largest n_samples (input rate, per stream) of one process call */
+  float    psr_threshold;     /* clamped to > 1.5 like downlink_trigger_c.py:71-73 */
+  int32_t  track_after;       /* 0 -> 16  (include/ltetrigger/pss.h:68) */
+  int32_t  track_every;       /* 0 -> 8 */
+  int32_t  record_all;        /* 1: record every general_work call; 0: emitted half-frames only */
+  int32_t  keep_halfframes;   /* 1: keep each emitted (CFO-corrected) half-frame for ltb_trigger_fetch_halfframes */
+  void    *cuda_stream;       /* cudaStream_t to launch on; NULL -> the library's own stream */
+} ltb_trigger_config;
+
+/* pss::make + sss::make + hier-block construction (lib/pss_impl.cc:42-83,
+ * lib/sss_impl.cc:45-73, python/downlink_trigger_c.py:18-45). */
+LTB_API int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out);
+/* ~pss_impl / ~sss_impl (lib/pss_impl.cc:88-92, lib/sss_impl.cc:78-81) */
+LTB_API int ltb_trigger_destroy(ltb_trigger *t);
+/* back to the just-constructed state (new flowgraph run) */
+LTB_API int ltb_trigger_reset(ltb_trigger *t);
+/* downlink_trigger_c.set_psr_threshold (python/downlink_trigger_c.py:63-69) /
+ * pss::set_psr_threshold (lib/pss_impl.h:98).  stream / n_id_2 = -1 selects all;
+ * clamp != 0 applies the hier block's > 1.5 floor. */
+LTB_API int ltb_trigger_set_psr_threshold(ltb_trigger *t, int stream, int n_id_2, float thr, int clamp);
+
+/* Feed n_samples new input-rate samples per stream (a multiple of 8*decim) and run every
+ * chain as far as the lookahead rule allows.  Stream s starts at
+ * (char*)iq + s*stream_stride_bytes.  *_host takes host memory (pinned for full PCIe
+ * rate) and copies it in; *_device takes device memory on cfg.device.  Records are
+ * written to `recs` ordered by (stream, n_id_2, win_index); *n_recs is the count
+ * (if it exceeds max_recs the call returns LTB_ERROR_INVALID_INPUTS after filling
+ * max_recs).  Replaces one scheduler pass of general_work/work calls over the chunk
+ * (lib/pss_impl.cc:154-223, lib/sss_impl.cc:83-156). */
+LTB_API int ltb_trigger_process_host(ltb_trigger *t, const void *iq, int64_t stream_stride_bytes,
+                                     int64_t n_samples, ltb_window_rec *recs, int max_recs, int *n_recs);
+LTB_API int ltb_trigger_process_device(ltb_trigger *t, const void *d_iq, int64_t stream_stride_bytes,
+                                       int64_t n_samples, ltb_window_rec *recs, int max_recs, int *n_recs);
+/* Asynchronous halves of process_device: submit enqueues all kernels on the stream and
+ * returns; collect waits for them and copies the records out. */
+LTB_API int ltb_trigger_submit_device(ltb_trigger *t, const void *d_iq, int64_t stream_stride_bytes,
+                                      int64_t n_samples);
+LTB_API int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int *n_recs);
+
+/* max_psr / mean_psr / mean_cfo / psr_threshold / tracking_score of one chain */
+LTB_API int ltb_trigger_get_stats(ltb_trigger *t, int stream, int n_id_2, ltb_pss_stats *out);
+/* The half-frames emitted by the last process call (cfg.keep_halfframes): 9600 samples
+ * each, in record order over records with LTB_F_EMIT -- what pss writes to its output
+ * port (lib/pss_impl.cc:193,204) and sss passes through (lib/sss_impl.cc:152). */
+LTB_API int ltb_trigger_fetch_halfframes(ltb_trigger *t, ltb_cf *out, int max_halfframes, int *n_halfframes);
+/* device time of the last process/submit call's kernels, measured with CUDA events on
+ * the launch stream (ms); and the number of kernel launches it made */
+LTB_API int ltb_trigger_last_timing(ltb_trigger *t, float *ms_total, int *n_launches);
+LTB_API const char *ltb_last_error(void);
+LTB_API const char *ltb_version(void);
+LTB_API int ltb_device_count(void);
+
+/* ---- standalone sss block ----------------------------------------------------------
+ * ltetrigger::sss for one N_id_2 on caller-supplied aligned half-frames
+ * (lib/sss_impl.cc:45-156): srslte_sync_detect_cp / set_cp, srslte_sss_m0m1_partial,
+ * srslte_sss_N_id_1, srslte_sync_get_cell_id, srslte_sync_reset on "tracking_lost". */
+typedef struct ltb_sss ltb_sss;
+LTB_API int ltb_sss_create(int device, int n_id_2, ltb_sss **out);
+LTB_API int ltb_sss_destroy(ltb_sss *s);
+/* n_halfframes consecutive work() calls: in = n*9600 host samples, tag_lost[i] != 0 if
+ * the i-th half-frame carries "tracking_lost".  Fills the SSS fields and flag bits of
+ * recs[i] (other fields untouched).  Returns LTB_SUCCESS. */
+LTB_API int ltb_sss_work(ltb_sss *s, const ltb_cf *in, const int32_t *tag_lost, int n_halfframes,
+                         ltb_window_rec *recs);
+
+/* ---- kernel-level entry points (parity tests, profiling) ----------------------------- */
+/* Sliding matched-filter power |x (*) h_k|^2, k = 0,1,2, for n (multiple of 8) samples of
+ * each of n_streams host streams; x[<0] = 0.  power: [n_streams][3][n].
+ * = srslte_pss_find_pss's convolution + srslte_vec_abs_square_cf without window truncation. */
+LTB_API int ltb_kernel_pss_corr_host(int device, const ltb_cf *x, int n_streams, int64_t n, float *power);
+/* rational_resampler_ccc(1, decim) with default taps on host streams of n_in samples
+ * (multiple of decim); fmt as above; y: [n_streams][n_in/decim]. */
+LTB_API int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in,
+                                     int decim, ltb_cf *y);
+
+/* ---- tables (host only; no GPU needed) -------------------------------------------------- */
+/* srslte_pss_init + srslte_pss_set_N_id_2: 128 conj time-domain taps (lib/pss_impl.cc:72-75) */
+LTB_API int ltb_table_pss_taps(int n_id_2, float h_re[128], float h_im[128]);
+/* gr::filter::rational_resampler_ccc(1, decim) default taps; returns ntaps or <0 */
+LTB_API int ltb_table_decim_taps(int decim, float *taps, int max_taps);
+/* srslte_sss_init + srslte_sss_set_N_id_2 tables (lib/sss_impl.cc:63-70) */
+LTB_API int ltb_table_sss(int n_id_2, int32_t c0[31], int32_t c1[31], int32_t s_tilde[31],
+                          int32_t z_tilde[31], int32_t n_id_1_table[900]);
+/* srslte_cfo_init's cexptab, 4096 (+1 spare) entries (lib/pss_impl.cc:78) */
+LTB_API int ltb_table_cexp(float tab_re[4097], float tab_im[4097]);
+LTB_API int ltb_table_fft128_twiddles(float w_re[64], float w_im[64]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTETRIGGER_B200_H */

@@ -1,0 +1,79 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol the header
+declares, its host-side tables equal the oracle's bit for bit, and compute entry points
+fail loudly (never fall back) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "ltetrigger_b200.h")).read()
+    return sorted(set(re.findall(r"LTB_API\s+[\w\s\*]+?\b(ltb_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ltetrigger_b200 as lt
+    from ltetrigger_b200 import _abi
+    L = lt.lib()
+    declared = header_symbols()
+    assert len(declared) >= 20
+    assert sorted(_abi.SYMBOLS) == declared
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.ltb_version()
+
+
+def test_struct_layouts():
+    from ltetrigger_b200 import _abi
+    assert _abi.WINDOW_REC.itemsize == 88
+    assert C.sizeof(_abi.TriggerConfig) == 64
+    assert C.sizeof(_abi.PssStats) == 32
+    from oracle import oracle as O
+    assert O.REC_DTYPE == _abi.WINDOW_REC
+
+
+def test_tables_match_oracle(oracle):
+    import ltetrigger_b200 as lt
+    for r in range(3):
+        assert np.array_equal(lt.tables.pss_taps(r).view(np.uint32), oracle.pss_taps(r).view(np.uint32))
+        for a, b in zip(lt.tables.sss(r), oracle.sss_tables(r)):
+            assert np.array_equal(a, b)
+    for d in (2, 4, 8, 16):
+        assert np.array_equal(lt.tables.decim_taps(d).view(np.uint32), oracle.decim_taps(d).view(np.uint32))
+    for a, b in zip(lt.tables.cexp(), oracle.cexptab()):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for a, b in zip(lt.tables.fft128_twiddles(), oracle.fft128_twiddles()):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_invalid_inputs():
+    import ltetrigger_b200 as lt
+    from ltetrigger_b200 import _abi
+    L = lt.lib()
+    h = C.c_void_p()
+    cfg = _abi.TriggerConfig()
+    assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS    # struct_size 0
+    cfg.struct_size = C.sizeof(_abi.TriggerConfig)
+    cfg.n_streams, cfg.decim, cfg.max_chunk = 1, 3, 9600
+    assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS    # decim 3
+    re_, im_ = np.zeros(128, np.float32), np.zeros(128, np.float32)
+    assert L.ltb_table_pss_taps(3, _abi.fptr(re_), _abi.fptr(im_)) == lt.ERROR_INVALID_INPUTS
+    s = C.c_void_p()
+    assert L.ltb_sss_create(0, 5, C.byref(s)) == lt.ERROR_INVALID_INPUTS
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
+def test_no_device_fails_loudly():
+    import ltetrigger_b200 as lt
+    assert lt.device_count() == 0
+    with pytest.raises(lt.LtbError):
+        lt.Trigger(n_streams=1)
+    with pytest.raises(lt.LtbError):
+        lt.kernel_pss_corr(np.zeros((1, 64), np.complex64))
+    with pytest.raises(RuntimeError):
+        lt.sss(0)

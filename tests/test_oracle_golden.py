@@ -1,0 +1,125 @@
+"""The oracle against everything the reference's own tests pin for this path
+(python/qa_downlink_trigger_c.py:67-203: cell_id and cp_len for the four test_frames,
+threshold 4, <= 1 s of repeated input), plus the fixture facts of SURVEY Appendix B."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, GOLDEN, load_fixture
+
+
+@pytest.mark.parametrize("name", list(FIXTURES))
+def test_reference_known_answers(oracle, name):
+    x, decim, cell_id = load_fixture(name, 1.0)
+    recs = oracle.trigger_run(x[None, :], decim=decim, psr_threshold=4.0)
+    cells = recs[(recs["flags"] & oracle.F_CELL) != 0]
+    assert len(cells) >= 1                                     # ">= 1 track message"
+    assert set(np.unique(cells["cell_id"])) == {cell_id}       # _check_cell_id
+    assert ((cells["flags"] & oracle.F_CP_NORM) != 0).all()    # _check_cp_len: "Normal"
+    assert set(np.unique(cells["n_id_2"])) == {cell_id % 3}
+    assert set(np.unique(cells["n_id_1"])) == {cell_id // 3}
+    # the two non-matching chains never fire (PSR <= 1.37)
+    other = recs[recs["n_id_2"] != cell_id % 3]
+    assert (other["flags"] & oracle.F_EMIT == 0).all()
+    assert other["psr"].max() < 1.5
+
+
+def test_appendix_b_trace_6prb(oracle):
+    x, decim, _ = load_fixture("6prb", 0.3)
+    recs = oracle.chain_run(x, 0, 4.0)
+    assert recs["peak_pos"][0] == 960
+    np.testing.assert_allclose(recs["psr"][:3], [4.935, 6.413, 6.021], rtol=1e-3)
+    assert (recs["win_start"][:17] == 9600 * np.arange(17)).all()
+    assert (recs["score"][:16] == np.arange(1, 17)).all()
+    # windows 0..14: emitted with tracking_lost; 15: first tracking half-frame, SF5 -> (13, 11)
+    assert ((recs["flags"][:15] & oracle.F_TAG_LOST) != 0).all()
+    assert recs["flags"][15] & oracle.F_TRACKING and recs["flags"][15] & oracle.F_CELL
+    assert (recs["m0"][15], recs["m1"][15]) == (13, 11)
+    assert (recs["m0"][16], recs["m1"][16]) == (11, 13)
+    # tracking: searches only every 9th call
+    searched = (recs["flags"][15:60] & oracle.F_SEARCHED) != 0
+    assert searched[0] and searched[9] and searched[18] and searched.sum() == 5
+
+
+def test_appendix_b_trace_25prb(oracle):
+    x, decim, _ = load_fixture("25prb", 0.3)
+    y = oracle.decimate(x, decim)
+    recs = oracle.chain_run(y, 1, 4.0)
+    assert recs["peak_pos"][0] == 976                           # decimator group delay 16
+    np.testing.assert_allclose(recs["psr"][:3], [6.445, 1.239, 6.445], rtol=1e-3)
+    assert list(recs["win_start"][:3]) == [0, 9616, 19216]
+    assert recs["score"][1] == 0 and recs["flags"][1] & oracle.F_TAG_LOST   # EMA dip -> reset, forced emit
+    first = int(np.argmax((recs["flags"] & oracle.F_TRACKING) != 0))
+    assert first == 17 and recs["cell_id"][first] == 124
+
+
+def test_fft_mode_agrees(oracle):
+    """Reference-class evaluation (9728-point FFT convolution) vs the canonical direct form:
+    identical decisions, magnitudes within 1e-4 relative (north_star tolerance)."""
+    x, decim, _ = load_fixture("6prb", 0.5)
+    a = oracle.trigger_run(x[None, :], decim=1, conv_mode=oracle.CONV_DIRECT)
+    b = oracle.trigger_run(x[None, :], decim=1, conv_mode=oracle.CONV_FFT)
+    assert len(a) == len(b)
+    for f in ("win_start", "emit_start", "flags", "peak_pos", "score", "m0", "m1", "n_id_1", "cell_id"):
+        assert (a[f] == b[f]).all(), f
+    np.testing.assert_allclose(a["psr"], b["psr"], rtol=1e-4)
+    np.testing.assert_allclose(a["peak_value"], b["peak_value"], rtol=1e-4)
+    win = x[:9600]
+    for r in range(3):
+        pd = oracle.pss_corr_window(win, r, oracle.CONV_DIRECT)
+        pf = oracle.pss_corr_window(win, r, oracle.CONV_FFT)
+        assert np.abs(pd - pf).max() <= 1e-4 * pd.max()
+
+
+def test_golden_traces(oracle):
+    """Committed per-window traces (tests/golden/fixture_traces.json, written by
+    tests/golden/make_golden.py) still come out of the oracle bit for bit."""
+    with open(os.path.join(GOLDEN, "fixture_traces.json")) as f:
+        gold = json.load(f)
+    for name in FIXTURES:
+        x, decim, _ = load_fixture(name, 0.5)
+        recs = oracle.trigger_run(x[None, :], decim=decim)
+        g = gold[name]
+        assert len(recs) == g["n_records"]
+        for field in ("win_start", "emit_start", "flags", "peak_pos", "score", "m0", "m1", "cell_id"):
+            assert recs[field].tolist() == g[field], (name, field)
+        assert recs["psr"].view(np.uint32).tolist() == g["psr_bits"], name
+        assert recs["cfo"].view(np.uint32).tolist() == g["cfo_bits"], name
+
+
+def test_edge_cases(oracle):
+    # shorter than the lookahead: no general_work call at all
+    assert len(oracle.trigger_run(np.zeros((1, 18360), np.complex64))) == 0
+    # exactly the lookahead: one call per chain
+    assert len(oracle.trigger_run(np.zeros((1, 18368), np.complex64))) == 3
+    # all-zero input: 0/0 PSR is NaN, compares false, nothing emitted
+    recs = oracle.trigger_run(np.zeros((1, 96000), np.complex64))
+    assert np.isnan(recs["psr"]).all() and (recs["flags"] & oracle.F_EMIT == 0).all()
+    # noise only: nothing crosses threshold 4
+    rng = np.random.default_rng(3)
+    n = (rng.standard_normal((2, 192000)) + 1j * rng.standard_normal((2, 192000))).astype(np.complex64)
+    recs = oracle.trigger_run(n)
+    assert (recs["flags"] & oracle.F_CELL == 0).all() and recs["psr"].max() < 4
+    # invalid N_id_2 -> constructor error like the reference's runtime_error
+    with pytest.raises(RuntimeError):
+        oracle.Pss(3, 4.0)
+    # threshold clamp of the hier block (python/downlink_trigger_c.py:71-73)
+    x, _, _ = load_fixture("6prb", 0.2)
+    a = oracle.trigger_run(x[None, :], psr_threshold=0.5)
+    b = oracle.trigger_run(x[None, :], psr_threshold=1.5)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_tables(oracle):
+    for r in range(3):
+        h = oracle.pss_taps(r)
+        assert np.array_equal(h[1:64], h[127:64:-1])            # h[m] == h[128-m]
+    assert np.array_equal(oracle.pss_taps(2), np.conj(oracle.pss_taps(1)))
+    for d, n in ((4, 131), (8, 263), (16, 525)):
+        t = oracle.decim_taps(d)
+        assert len(t) == n and np.array_equal(t, t[::-1]) and abs(t.sum() - 1) < 1e-5
+    c0, c1, s, z, tab = oracle.sss_tables(0)
+    assert tab[11, 12] == 41 and tab[9, 13] == 123              # (m0,m1) = (11,13), (9,14)
+    assert sorted(set(tab.ravel().tolist())) == list(range(168))
