@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- PSS+SSS search throughput (BASELINE.json metric) on N B200s of one node.
+
+Workload (config C5's per-GPU shard): 512 concurrent 30.72 Msps fc32 streams per
+GPU, decimate-by-16 front end, three-root PSS search + tracking state machine + SSS, fed as
+halo-segmented 100 ms segments.  One "step" = one 100 ms segment of all 512 streams
+(1.573 G input samples, 12.6 GB fc32 -- larger than L2, so no flush is needed between steps);
+the default 10 steps are the config's 1 s per stream.  Streams shard by rank with no
+collective on the data path (weak scaling): value = all ranks' samples / max-over-ranks time.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                     # CPU reference arm (oracle, FFT mode)
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gr-ltetrigger_b200", "python"))
+
+SEARCH_RATE = 1.92e6
+F_PSS = 3 * 128 * 8 + 18                     # flop per search-rate sample, direct form
+NTAPS = {1: 0, 2: 65, 4: 131, 8: 263, 16: 525}
+FP32_PEAK_TFLOPS = 72.4                      # measured: tools/ubench_fp32.cu on this pool's B200 (profiles/ubench_fp32_r01.jsonl)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=512, help="streams per GPU")
+    ap.add_argument("--segment-ms", type=int, default=100)
+    ap.add_argument("--decim", type=int, default=16)
+    ap.add_argument("--format", default="fc32", choices=["fc32", "sc16"])
+    ap.add_argument("--snr-db", type=float, default=5.0)
+    ap.add_argument("--unique", type=int, default=8, help="distinct synthetic captures tiled over the streams")
+    ap.add_argument("--e2e-streams", type=int, default=128)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-streams", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "C5 shard: %d streams/GPU x %.2f Msps %s, D=%d, %d ms segments" % (
+        a.streams, 1.92 * a.decim, a.format, a.decim, a.segment_ms)
+
+
+def host_unique(a, n):
+    """`unique` seeded synthetic captures of one segment at the input rate (numpy, host)."""
+    from ltetrigger_b200 import synth
+    perm = np.random.default_rng(2026).permutation(504)
+    base = np.empty((a.unique, n), np.complex64)
+    for u in range(a.unique):
+        # noise-free and frame-periodic (segment = whole frames), so tiling in time stays a valid downlink
+        base[u] = synth.capture(int(perm[u]), n, snr_db=None, decim=a.decim, seed=77 + u, offset=0)
+    return base, perm[:a.unique]
+
+
+def host_batch(base, n_streams, snr_db, seed):
+    """Tile the unique captures over n_streams with per-stream timing shifts and AWGN (host)."""
+    rng = np.random.default_rng(seed)
+    u, n = base.shape
+    out = np.empty((n_streams, n), np.complex64)
+    sigma = np.sqrt(1.0 / (10.0 ** (snr_db / 10.0)) / 2.0)
+    for s in range(n_streams):
+        shift = int(rng.integers(0, n))
+        x = np.roll(base[s % u], shift)
+        noise = rng.standard_normal((n, 2), dtype=np.float32)
+        out[s] = x + sigma * (noise[:, 0] + 1j * noise[:, 1])
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report it rather than inventing numbers
+            self.reasons.add("nvml_unavailable: %s" % type(e).__name__)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_run(iq, decim, nthreads=0, conv_fft=True):
+    """The reference's algorithm class on the host cores: per window and root one zero-padded
+    9728-point FFT convolution (oracle ORC_CONV_FFT), GR-default Kaiser decimator in front."""
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    recs = O.trigger_run(iq, decim=decim, psr_threshold=4.0, conv_mode=O.CONV_FFT if conv_fft else O.CONV_DIRECT,
+                         nthreads=nthreads)
+    return time.perf_counter() - t0, recs
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    n = int(a.segment_ms * 1e-3 * SEARCH_RATE) * a.decim
+    base, _ = host_unique(a, n)
+    iq = host_batch(base, a.cpu_streams, a.snr_db, seed=5)
+    cores = os.cpu_count()
+    for _ in range(max(a.warmup, 0) and 1):
+        cpu_reference_run(iq[:max(2, cores // 4)], a.decim)
+    times = []
+    for _ in range(a.steps):
+        dt, recs = cpu_reference_run(iq, a.decim)
+        times.append(dt)
+    total = sum(times)
+    value = a.cpu_streams * n * a.steps / total / 1e6
+    sample = "%d streams x %d ms per step (same synthetic workload), oracle ORC_CONV_FFT, %d threads" % (
+        a.cpu_streams, a.segment_ms, cores)
+    line = {
+        "impl": "reference", "metric": "PSS+SSS search Msamples/s", "value": value, "unit": "Msamples/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "cpu_sample_streams": a.cpu_streams},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ltetrigger_b200 as lt
+
+    if not torch.cuda.is_available() or lt.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    fmt = lt.FMT_FC32 if a.format == "fc32" else lt.FMT_SC16
+    bps = 8 if fmt == lt.FMT_FC32 else 4
+    n = int(a.segment_ms * 1e-3 * SEARCH_RATE) * a.decim           # input samples per stream per step
+    m = n // a.decim
+
+    # ---- synthetic input, resident in HBM before the timed region --------------------------
+    base, cell_ids = host_unique(a, n)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    base_d = torch.from_numpy(base).to(dev)
+    sigma = float(np.sqrt(1.0 / (10.0 ** (a.snr_db / 10.0)) / 2.0))
+    x = torch.empty((a.streams, n), dtype=torch.complex64, device=dev)
+    shifts = torch.randint(0, n, (a.streams,), generator=torch.Generator().manual_seed(7 + rank))
+    for s in range(a.streams):
+        noise = torch.randn((n, 2), generator=g, device=dev, dtype=torch.float32)
+        x[s] = torch.roll(base_d[s % a.unique], int(shifts[s])) + sigma * torch.view_as_complex(noise)
+    del noise, base_d
+    if fmt == lt.FMT_SC16:
+        xr = torch.view_as_real(x)
+        d_in = torch.clamp(torch.round(xr * (32767.0 / 8.0)), -32768, 32767).to(torch.int16).contiguous()
+        del x, xr
+    else:
+        d_in = x
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    trig = lt.Trigger(n_streams=a.streams, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
+                      record_all=False, device=local_rank, cuda_stream=stream.cuda_stream)
+    ptr, stride = d_in.data_ptr(), n * bps
+
+    def step():
+        return trig.process_device_ptr(ptr, stride, n)
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = np.zeros(4)
+    launches = 0
+    n_cells = 0
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(a.steps):
+        recs = step()
+        stage_ms += np.array(trig.last_kernel_times())
+        launches += trig.last_timing()[1]
+        n_cells += int(((recs["flags"] & lt.F_CELL) != 0).sum())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.result()
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        elapsed_ms = float(tt.item())
+    total_samples = float(a.streams) * n * a.steps * world
+    value = total_samples / (elapsed_ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations of the timed steps) -----
+    stage_ms /= a.steps
+    names = ["frontend(convert+decimate)", "pss_corr(3 roots)", "pss_track", "sss"]
+    alg_flop = [4.0 * NTAPS[a.decim] * m * a.streams, float(F_PSS) * m * a.streams, 0.0, 0.0]
+    dom = int(np.argmax(stage_ms))
+    if alg_flop[dom] == 0.0:
+        dom = int(np.argmax(stage_ms[:2]))
+    achieved = alg_flop[dom] / (stage_ms[dom] * 1e-3) / 1e12
+    f_alg = (F_PSS + 4.0 * NTAPS[a.decim]) / a.decim                # flop per input sample, SURVEY 8d
+    per_gpu_rate = value * 1e6 / world
+    roofline = {
+        "bound": "fp32", "kernel": names[dom], "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+        "frac": achieved / FP32_PEAK_TFLOPS, "traffic": None,
+        "peak_source": "measured FFMA peak, tools/ubench_fp32.cu (profiles/ubench_fp32_r01.jsonl); MEASURED_PEAKS.json has no fp32 figure",
+        "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
+        "path_frac_of_fp32": f_alg * per_gpu_rate / (FP32_PEAK_TFLOPS * 1e12),
+        "path_frac_of_hbm": bps * per_gpu_rate / (6535.7e9),
+        "note": "achieved = SURVEY 8d algorithmic flop (direct form) per launch / CUDA-event duration; the kernels exploit tap symmetry, so frac can exceed 1",
+    }
+
+    out = {
+        "metric": "PSS+SSS search Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "streams_per_gpu": a.streams, "decim": a.decim,
+                   "format": a.format, "segment_ms": a.segment_ms, "snr_db": a.snr_db,
+                   "l2": "inputs larger than L2 (%.1f GB per step)" % (a.streams * n * bps / 1e9),
+                   "input": "%d seeded synthetic LTE captures tiled over the streams with per-stream timing shift + AWGN" % a.unique,
+                   "cells_tagged_per_step": n_cells / a.steps},
+        "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
+    }
+
+    # ---- end to end through the C ABI with host buffers (H2D + D2H inside the timed region) --
+    if not a.no_e2e:
+        se = min(a.e2e_streams, a.streams)
+        host = torch.empty((se,) + tuple(d_in.shape[1:]), dtype=d_in.dtype, pin_memory=True)
+        host.copy_(d_in[:se])
+        torch.cuda.synchronize()
+        trig.close()
+        trig2 = lt.Trigger(n_streams=se, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
+                           record_all=False, device=local_rank, cuda_stream=stream.cuda_stream)
+        hptr = host.data_ptr()
+        trig2.process_host_ptr(hptr, stride, n)                    # warm-up (allocates the staging buffer)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        d2h = 0
+        for _ in range(a.e2e_steps):
+            r = trig2.process_host_ptr(hptr, stride, n)
+            d2h += r.nbytes
+        e1.record(stream)
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tt.item())
+        out["e2e"] = {"value": se * n * a.e2e_steps * world / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                      "h2d_bytes_per_step": se * n * bps, "d2h_bytes_per_step": d2h // a.e2e_steps,
+                      "streams": se, "steps": a.e2e_steps, "host_memory": "pinned",
+                      "api": "ltb_trigger_process_host"}
+        # ---- CPU baseline on the same host sample (rank 0, N=1 only) ---------------------------
+        if rank == 0 and world == 1 and not a.no_cpu_baseline and fmt == lt.FMT_FC32:
+            sc = min(a.cpu_streams, se)
+            iq = host[:sc].numpy()
+            dt, _ = cpu_reference_run(iq, a.decim)
+            out["cpu_baseline"] = {"value": sc * n / dt / 1e6, "unit": "Msamples/s", "cores": os.cpu_count(),
+                                   "kind": "port",
+                                   "sample": "%d streams x %d ms of the same workload; oracle in reference-class FFT mode "
+                                             "(9728-point FFT convolution per window and root), one job per (stream, root), %.1f s wall"
+                                             % (sc, a.segment_ms, dt)}
+        trig2.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -68,6 +68,21 @@ int ensure_constants(int device) {
     std::memcpy(dt + decim_tap_offset(ds[i]), v.data(), v.size() * sizeof(float));
   }
   LTB_CUDA(cudaMemcpyToSymbol(c_decim_taps, dt, sizeof dt));
+  {
+    static float2 pairs[990];
+    std::memset(pairs, 0, sizeof pairs);
+    for (int i = 0; i < 4; ++i) {
+      const int d = ds[i], nt = decim_ntaps(d);
+      const float *tp = dt + decim_tap_offset(d);
+      for (int v = 0; v < d; ++v)
+        for (int q = 0; q < kDecQ; ++q) {
+          const int j = q * d + v;
+          const float c = j < nt ? tp[j] : 0.0f;
+          pairs[decim_pair_offset(d) + v * kDecQ + q] = make_float2(c, c);
+        }
+    }
+    LTB_CUDA(cudaMemcpyToSymbol(c_decim_pairs, pairs, sizeof pairs));
+  }
   float twr[64], twi[64];
   make_fft128_twiddles(twr, twi);
   float2 tw[64];
@@ -93,6 +108,10 @@ int ensure_constants(int device) {
   LTB_CUDA(cudaMemcpyToSymbol(c_sss_nid1, nid, sizeof nid));
   LTB_CUDA(cudaFuncSetAttribute(pss_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(TrackShared)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(16)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(16)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(8)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(8)));
   g_const_done[device] = true;
   return LTB_SUCCESS;
 }
@@ -121,11 +140,11 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
     *launches += 1;
     return LTB_SUCCESS;
   }
-  const dim3 grid((m + 255) / 256, n_streams);
+  const dim3 grid((m + kDecOut - 1) / kDecOut, n_streams);
 #define LTB_DECIM_CASE(D)                                                                             \
   case D: {                                                                                           \
-    const size_t smem = sizeof(float2) * (size_t)(255 * D + decim_ntaps(D));                          \
-    decimate_kernel<FMT, D><<<grid, 256, smem, st>>>(d_iq, stride, m, tail_old, y_ring, n_base, mask, cap); \
+    decimate_kernel<FMT, D><<<grid, 32 * decim_groups(D), decim_smem_bytes(D), st>>>(                 \
+        d_iq, stride, m, tail_old, y_ring, n_base, mask, cap);                                        \
   } break;
   switch (decim) {
     LTB_DECIM_CASE(2)
@@ -152,6 +171,8 @@ struct ltb_trigger {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};   // after front end, corr, track, sss
+  float last_kernel_ms[4] = {0.f, 0.f, 0.f, 0.f};
   void *d_in = nullptr;
   size_t d_in_stride = 0;
   float2 *d_y = nullptr;
@@ -207,6 +228,7 @@ void trigger_free(ltb_trigger *t) {
   if (t->h_rec_count) cudaFreeHost(t->h_rec_count);
   if (t->ev0) cudaEventDestroy(t->ev0);
   if (t->ev1) cudaEventDestroy(t->ev1);
+  for (int i = 0; i < 4; ++i) if (t->ev_k[i]) cudaEventDestroy(t->ev_k[i]);
   if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
@@ -230,9 +252,11 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
                                        t->d_y, n_base, t->cap_mask, t->cap, t->stream, &launches);
   if (rc) return rc;
   if (c.decim > 1) t->tail_cur ^= 1;
+  LTB_CUDA(cudaEventRecord(t->ev_k[0], t->stream));
   pss_corr_kernel<<<dim3((m + kCorrTile - 1) / kCorrTile, S), kCorrThreads, 0, t->stream>>>(
       t->d_y, t->d_p, n_base, m, t->cap_mask, t->cap);
   launches++;
+  LTB_CUDA(cudaEventRecord(t->ev_k[1], t->stream));
   t->n_total += m;
   t->w_cur = m / (kHalf - kSlot) + 4;
   if (t->w_cur > t->w_cap) t->w_cur = t->w_cap;
@@ -246,6 +270,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   P.root_mask = c.root_mask;
   pss_track_kernel<<<t->n_chains, kTrackThreads, sizeof(TrackShared), t->stream>>>(P);
   launches++;
+  LTB_CUDA(cudaEventRecord(t->ev_k[2], t->stream));
   int sss_grid = (t->n_chains * t->w_cur + kSssWarps - 1) / kSssWarps;
   if (sss_grid > 148 * 8) sss_grid = 148 * 8;
   sss_kernel<<<sss_grid, kSssWarps * 32, 0, t->stream>>>(t->d_sss_sym, t->d_sss_rec, t->d_sss_count, t->sss_cap, t->d_recs);
@@ -313,6 +338,7 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   else { LTB_CUDA_T(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking)); t->own_stream = true; }
   LTB_CUDA_T(cudaEventCreate(&t->ev0));
   LTB_CUDA_T(cudaEventCreate(&t->ev1));
+  for (int i = 0; i < 4; ++i) LTB_CUDA_T(cudaEventCreate(&t->ev_k[i]));
   t->d_in_stride = (size_t)c.max_chunk * (c.input_format == LTB_FMT_FC32 ? 8 : 4);
   LTB_CUDA_T(cudaMalloc(&t->d_y, sizeof(float2) * (size_t)S * t->cap));
   LTB_CUDA_T(cudaMalloc(&t->d_p, sizeof(float) * (size_t)S * 3 * t->cap));
@@ -377,6 +403,10 @@ int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int 
   LTB_CUDA(cudaStreamSynchronize(t->stream));
   t->pending = false;
   cudaEventElapsedTime(&t->last_ms, t->ev0, t->ev1);
+  cudaEventElapsedTime(&t->last_kernel_ms[0], t->ev0, t->ev_k[0]);
+  cudaEventElapsedTime(&t->last_kernel_ms[1], t->ev_k[0], t->ev_k[1]);
+  cudaEventElapsedTime(&t->last_kernel_ms[2], t->ev_k[1], t->ev_k[2]);
+  cudaEventElapsedTime(&t->last_kernel_ms[3], t->ev_k[2], t->ev1);
   int total = 0, written = 0;
   for (int ch = 0; ch < t->n_chains; ++ch) {
     const int n = t->h_rec_count[ch];
@@ -461,6 +491,12 @@ int ltb_trigger_last_timing(ltb_trigger *t, float *ms_total, int *n_launches) {
   if (!t) return LTB_ERROR_INVALID_INPUTS;
   if (ms_total) *ms_total = t->last_ms;
   if (n_launches) *n_launches = t->last_launches;
+  return LTB_SUCCESS;
+}
+
+int ltb_trigger_last_kernel_times(ltb_trigger *t, float ms[4]) {
+  if (!t || !ms) return LTB_ERROR_INVALID_INPUTS;
+  for (int i = 0; i < 4; ++i) ms[i] = t->last_kernel_ms[i];
   return LTB_SUCCESS;
 }
 

@@ -91,6 +91,14 @@ struct TrackParams {
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // canonical complex product a*b:  re = fma(ar, br, -(ai*bi)),  im = fma(ar, bi, ai*br)
 __device__ __forceinline__ float2 cmul_canon(float2 a, float2 b) {
   float2 r;
@@ -161,49 +169,134 @@ __device__ __forceinline__ float2 load_in_sample(const char *src, long long idx)
   return make_float2(__fmul_rn((float)s.x, k), __fmul_rn((float)s.y, k));
 }
 
-// Tile of TILE_OUT outputs per CTA; the (TILE_OUT-1)*D + NTAPS input samples it touches are
-// staged once in shared memory (coalesced 8-byte loads, converted on the way in), then each
-// thread walks its own polyphase branches.
+// Canonical order: the D polyphase branches are split into G = min(4, D) groups of
+// D/G consecutive branches; group g accumulates  fma(h[qD+v], x[kD-qD-v], acc)  over its
+// branches v (ascending) and q = 0..32 (ascending, taps beyond ntaps are zeros) in one chain per
+// component, and  y = (p0 + p1) + (p2 + p3).
+//
+// One CTA = 512 outputs of one stream, one warp per branch group, 16 consecutive outputs per
+// lane.  The (512+32)*D input samples of the tile are staged once in shared memory as
+// x_v[n'] = x[(k0-32+n')*D - v], row v, 16-way de-interleaved in n' (sub-row n' & 15), so that
+// the element a warp needs at one step (n' = 32 + 16*lane + e) is 32 consecutive float2: a
+// conflict-free LDS.64.  Each lane slides a 16-sample register window down one sample per tap:
+// 1 LDS.64 + 1 uniform coefficient load per 16 FFMA2.
+constexpr int kDecT = 16;                        // outputs per lane
+constexpr int kDecOut = 32 * kDecT;              // 512 outputs per CTA
+constexpr int kDecQ = 33;                        // taps per polyphase branch (zero padded)
+constexpr int kDecGroups = kDecOut + kDecQ - 1;  // 544 n' values per branch
+constexpr int kDecRow = kDecGroups + 1;          // 545 float2: odd stride -> conflict-free fill
+// (c, c) coefficient pairs per D at offsets 0 (D=2), 66 (D=4), 198 (D=8), 462 (D=16): [v][33]
+__constant__ float2 c_decim_pairs[990];
+__host__ __device__ constexpr int decim_pair_offset(int d) { return d == 2 ? 0 : d == 4 ? 66 : d == 8 ? 198 : 462; }
+__host__ __device__ constexpr int decim_groups(int d) { return d >= 4 ? 4 : d; }
+__host__ __device__ constexpr size_t decim_smem_bytes(int d) { return sizeof(float2) * (size_t)d * kDecRow; }
+
 template <int FMT, int D>
-__global__ void __launch_bounds__(256) decimate_kernel(const void *__restrict__ in, long long stride_bytes,
-                                                       int n_out, const float2 *__restrict__ tail_in,
-                                                       float2 *__restrict__ y_ring, long long n_base,
-                                                       unsigned cap_mask, int cap) {
-  constexpr int NT = decim_ntaps(D);
-  constexpr int OFF = decim_tap_offset(D);
-  constexpr int TILE_OUT = 256;
-  constexpr int SPAN = (TILE_OUT - 1) * D + NT;     // input samples needed by the tile
-  extern __shared__ float2 s_in[];                  // [SPAN]
+__global__ void __launch_bounds__(32 * decim_groups(D))
+decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
+                float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap) {
+  constexpr int G = decim_groups(D);
+  constexpr int PPG = D / G;
+  constexpr int NTHR = 32 * G;
+  constexpr int POFF = decim_pair_offset(D);
+  extern __shared__ __align__(16) float2 s_x[];   // [D][kDecRow]
   const int stream = blockIdx.y;
-  const int k0 = blockIdx.x * TILE_OUT;
+  const int k0 = blockIdx.x * kDecOut;
   const char *src = (const char *)in + (long long)stream * stride_bytes;
   const float2 *tail = tail_in + (size_t)stream * kTailCap;
-  const long long first = (long long)k0 * D - (NT - 1);   // input index of s_in[0]
   const long long n_in = (long long)n_out * D;
-  for (int i = threadIdx.x; i < SPAN; i += blockDim.x) {
-    const long long idx = first + i;
-    float2 v = make_float2(0.f, 0.f);
-    if (idx >= 0) { if (idx < n_in) v = load_in_sample<FMT>(src, idx); }
-    else if (idx >= -kTailCap) v = tail[kTailCap + idx];
-    s_in[i] = v;
-  }
-  __syncthreads();
-  const int k = k0 + threadIdx.x;
-  if (k >= n_out) return;
-  // x[kD - j] = s_in[(k - k0)*D + (NT-1) - j]
-  const float2 *base = s_in + threadIdx.x * D + (NT - 1);
-  float ar = 0.f, ai = 0.f;
-#pragma unroll 1
-  for (int v = 0; v < D; ++v) {
-#pragma unroll 4
-    for (int j = v; j < NT; j += D) {
-      const float2 x = base[-j];
-      const float t = c_decim_taps[OFF + j];
-      ar = __fmaf_rn(t, x.x, ar);
-      ai = __fmaf_rn(t, x.y, ai);
+  // tile element j <-> input index idx0 + j, with  n' = j / D,  v = D-1 - (j % D)
+  const long long idx0 = (long long)(k0 - (kDecQ - 1)) * D - (D - 1);
+  if (FMT == LTB_FMT_FC32) {
+    // asynchronous 8-byte copies straight into the de-interleaved layout (LDGSTS): the whole
+    // tile is in flight at once while the SM's other resident CTAs keep the FMA pipe busy
+    for (int j = threadIdx.x; j < kDecGroups * D; j += NTHR) {
+      const long long idx = idx0 + j;
+      const int np = j / D, v = D - 1 - (j % D);
+      float2 *dst = &s_x[v * kDecRow + (np & 15) * (kDecGroups / 16) + (np >> 4)];
+      if (idx >= 0 && idx < n_in) {
+        cp_async_8(dst, src + idx * 8);
+      } else {
+        *dst = (idx < 0 && idx >= -kTailCap) ? tail[kTailCap + idx] : make_float2(0.f, 0.f);
+      }
+    }
+    cp_async_wait_all();
+  } else {
+    // sc16: convert on the way in; loads batched 8 deep per thread for memory-level parallelism
+    constexpr int U = 8;
+    for (int j0 = threadIdx.x; j0 < kDecGroups * D; j0 += NTHR * U) {
+      float2 val[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * NTHR;
+        const long long idx = idx0 + j;
+        val[u] = make_float2(0.f, 0.f);
+        if (j < kDecGroups * D) {
+          if (idx >= 0) { if (idx < n_in) val[u] = load_in_sample<FMT>(src, idx); }
+          else if (idx >= -kTailCap) val[u] = tail[kTailCap + idx];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * NTHR;
+        if (j < kDecGroups * D) {
+          const int np = j / D, v = D - 1 - (j % D);
+          s_x[v * kDecRow + (np & 15) * (kDecGroups / 16) + (np >> 4)] = val[u];
+        }
+      }
     }
   }
-  y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = make_float2(ar, ai);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  float2 acc[kDecT], w[kDecT];
+#pragma unroll
+  for (int o = 0; o < kDecT; ++o) acc[o] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int vv = 0; vv < PPG; ++vv) {
+    const int v = g * PPG + vv;
+    const float2 *row = s_x + v * kDecRow + 2 + lane;        // n' = 32 + 16*lane + e -> sub-row e & 15, col 2 + lane + (e >> 4)
+    const float2 *cf = c_decim_pairs + POFF + v * kDecQ;
+#pragma unroll
+    for (int o = 0; o < kDecT; ++o) w[o] = row[o * (kDecGroups / 16)];
+#pragma unroll
+    for (int q = 0; q < kDecQ; ++q) {
+      if (q > 0) {
+        const int e = -q;                                    // new window element
+        w[e & 15] = row[(e & 15) * (kDecGroups / 16) + (e >> 4)];
+      }
+      const float2 c = cf[q];
+#pragma unroll
+      for (int o = 0; o < kDecT; ++o) acc[o] = ffma2(c, w[(o - q) & 15], acc[o]);
+    }
+  }
+  if (G == 1) {
+#pragma unroll
+    for (int o = 0; o < kDecT; ++o) {
+      const int k = k0 + lane * kDecT + o;
+      if (k < n_out) y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = acc[o];
+    }
+    return;
+  }
+  // partial sums -> shared memory [g][o][lane] (row stride 33), then (p0+p1)+(p2+p3)
+  __syncthreads();
+  float2 *part = s_x;
+#pragma unroll
+  for (int o = 0; o < kDecT; ++o) part[(g * kDecT + o) * 33 + lane] = acc[o];
+  __syncthreads();
+  for (int i = threadIdx.x; i < kDecOut; i += NTHR) {
+    const int o = i & 15, ln = i >> 4;
+    float2 y;
+    if (G == 2) {
+      y = fadd2(part[o * 33 + ln], part[(kDecT + o) * 33 + ln]);
+    } else {
+      const float2 a = fadd2(part[o * 33 + ln], part[(kDecT + o) * 33 + ln]);
+      const float2 b = fadd2(part[(2 * kDecT + o) * 33 + ln], part[(3 * kDecT + o) * 33 + ln]);
+      y = fadd2(a, b);
+    }
+    const int k = k0 + i;
+    if (k < n_out) y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = y;
+  }
 }
 
 // keep the last kTailCap converted input samples of each stream for the next call
@@ -351,6 +444,58 @@ pss_corr_kernel(const float2 *__restrict__ y_ring, float *__restrict__ p_ring, l
 constexpr int kTrackThreads = 256;
 constexpr int kNEdge = 253;            // lags 0..126 and 9600..9725 see a truncated window
 
+// srslte_cexptab_gen's phase recurrence  phase = fl(phase + inc)  (with the 4096 wraps) is
+// sequential, but inside one float binade it is exactly linear in the bit pattern: a grid point
+// plus a constant rounds to "bits + dk" with a constant dk (after one in-binade step fixes the
+// ties-to-even parity).  Thread 0 therefore only walks binade/wrap boundaries with real float
+// adds and emits (start, bits0, dk, len) segments; all threads expand them in parallel.  The
+// result is bit-identical to the sample-by-sample loop (checked against the oracle, which runs
+// that loop).
+struct PhaseSeg { int start; unsigned bits0; int dk; int len; };
+constexpr int kMaxSeg = 64;
+
+__device__ int plan_phase_scan(float &phase, bool &stable, float inc, int n, PhaseSeg *segs,
+                               unsigned short *idx_out) {
+  int i = 0, ns = 0;
+  while (i < n) {
+    const float before = phase;
+    while (phase >= 4096.0f) phase = __fadd_rn(phase, -4096.0f);
+    while (phase < 0.f) phase = __fadd_rn(phase, 4096.0f);
+    if (phase != before) stable = false;
+    if (ns == kMaxSeg) {                           // table full (huge |inc|): finish one by one
+      idx_out[i++] = (unsigned short)(unsigned)phase;
+      phase = __fadd_rn(phase, inc);
+      stable = false;
+      continue;
+    }
+    const float nxt = __fadd_rn(phase, inc);
+    const unsigned pb = __float_as_uint(phase), nb = __float_as_uint(nxt);
+    const bool same = phase > 0.f && nxt > 0.f && ((pb ^ nb) >> 23) == 0u;
+    int len = 1, dk = 0;
+    float phase_next = nxt;
+    bool stable_next = same;
+    if (stable && same) {
+      dk = (int)nb - (int)pb;
+      const unsigned lo = pb & 0xFF800000u, hi = lo | 0x007FFFFFu;
+      unsigned avail;                              // further steps that stay inside the binade
+      if (dk < 0) avail = (pb - lo) / (unsigned)(-dk);
+      else if (dk > 0) avail = (hi - pb) / (unsigned)dk;
+      else avail = (unsigned)n;
+      len = (avail + 1u < (unsigned)(n - i)) ? (int)(avail + 1u) : (n - i);
+      const unsigned lb = pb + (unsigned)((len - 1) * dk);
+      const float last = __uint_as_float(lb);
+      phase_next = __fadd_rn(last, inc);
+      stable_next = phase_next > 0.f && ((lb ^ __float_as_uint(phase_next)) >> 23) == 0u;
+    }
+    segs[ns].start = i; segs[ns].bits0 = pb; segs[ns].dk = dk; segs[ns].len = len;
+    ns++;
+    i += len;
+    phase = phase_next;
+    stable = stable_next;
+  }
+  return ns;
+}
+
 struct TrackShared {
   float avg[kAvgLen];
   float2 lead[256];                    // window samples 0..126 at [128..255), zeros elsewhere
@@ -358,6 +503,8 @@ struct TrackShared {
   float edge[256];                     // power at the truncated lags
   float2 rot[480];                     // CFO-corrected samples 480..959 of the emitted half-frame
   unsigned short ph_idx[960];          // phasor table index per sample
+  PhaseSeg seg[kMaxSeg];
+  int nseg;
   float red_v[8]; int red_i[8]; float red_l[8]; float red_r[8];
   float cp_part[12];
   float2 y01[2];
@@ -434,14 +581,29 @@ __global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P)
       }
       __syncthreads();
       float best = -3.402823466e+38f; int bi = 0;
-      for (int k = tid; k < kNLag; k += kTrackThreads) {
-        float a;
-        if (k < 127) a = S.edge[k];
-        else if (k >= kHalf) a = S.edge[127 + (k - kHalf)];
-        else a = pr[(unsigned)((R + k) & P.cap_mask)];
-        const float v = __fadd_rn(__fmul_rn(a, 0.2f), __fmul_rn(S.avg[k], 0.8f));   // EMA, alpha 0.2
-        S.avg[k] = v;
-        if (v > best) { best = v; bi = k; }
+      // 38 lags per thread, loads issued 8 at a time so their latencies overlap
+#pragma unroll 1
+      for (int base = tid; base < kNLag; base += kTrackThreads * 8) {
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = base + u * kTrackThreads;
+          a[u] = 0.f;
+          if (k < kNLag) {
+            if (k < 127) a[u] = S.edge[k];
+            else if (k >= kHalf) a[u] = S.edge[127 + (k - kHalf)];
+            else a[u] = __ldg(&pr[(unsigned)((R + k) & P.cap_mask)]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = base + u * kTrackThreads;
+          if (k < kNLag) {
+            const float v = __fadd_rn(__fmul_rn(a[u], 0.2f), __fmul_rn(S.avg[k], 0.8f));   // EMA, alpha 0.2
+            S.avg[k] = v;
+            if (v > best) { best = v; bi = k; }
+          }
+        }
       }
       // first-index argmax over the block
 #pragma unroll
@@ -589,14 +751,14 @@ __global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P)
         const float phase_inc = __fmul_rn(S.st.cfo_table_freq, 4096.0f);
         const int n_blocks = hf ? 10 : 1;
         float phase = 0.f;       // carried by thread 0 across blocks
+        bool stable = false;
         for (int b = 0; b < n_blocks; ++b) {
-          if (tid == 0) {
-            for (int i = 0; i < 960; ++i) {
-              while (phase >= 4096.0f) phase = __fadd_rn(phase, -4096.0f);
-              while (phase < 0.f) phase = __fadd_rn(phase, 4096.0f);
-              S.ph_idx[i] = (unsigned short)(unsigned)phase;
-              phase = __fadd_rn(phase, phase_inc);
-            }
+          if (tid == 0) S.nseg = plan_phase_scan(phase, stable, phase_inc, 960, S.seg, S.ph_idx);
+          __syncthreads();
+          for (int sg = 0; sg < S.nseg; ++sg) {
+            const PhaseSeg q = S.seg[sg];
+            for (int j = tid; j < q.len; j += kTrackThreads)
+              S.ph_idx[q.start + j] = (unsigned short)(unsigned)__uint_as_float(q.bits0 + (unsigned)(j * q.dk));
           }
           __syncthreads();
           if (b == 0) {

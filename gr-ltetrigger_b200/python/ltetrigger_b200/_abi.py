@@ -49,7 +49,7 @@ SYMBOLS = [
     "ltb_trigger_create", "ltb_trigger_destroy", "ltb_trigger_reset", "ltb_trigger_set_psr_threshold",
     "ltb_trigger_process_host", "ltb_trigger_process_device", "ltb_trigger_submit_device",
     "ltb_trigger_collect", "ltb_trigger_get_stats", "ltb_trigger_fetch_halfframes",
-    "ltb_trigger_last_timing", "ltb_last_error", "ltb_version", "ltb_device_count",
+    "ltb_trigger_last_timing", "ltb_trigger_last_kernel_times", "ltb_last_error", "ltb_version", "ltb_device_count",
     "ltb_sss_create", "ltb_sss_destroy", "ltb_sss_work",
     "ltb_kernel_pss_corr_host", "ltb_kernel_decimate_host",
     "ltb_table_pss_taps", "ltb_table_decim_taps", "ltb_table_sss", "ltb_table_cexp",
@@ -81,6 +81,7 @@ def lib():
     L.ltb_trigger_get_stats.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PssStats)]
     L.ltb_trigger_fetch_halfframes.argtypes = [vp, vp, C.c_int, ip]
     L.ltb_trigger_last_timing.argtypes = [vp, fp, ip]
+    L.ltb_trigger_last_kernel_times.argtypes = [vp, fp]
     L.ltb_sss_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     L.ltb_sss_destroy.argtypes = [vp]
     L.ltb_sss_work.argtypes = [vp, vp, vp, C.c_int, vp]

@@ -117,6 +117,12 @@ class Trigger:
         A.lib().ltb_trigger_last_timing(self._h, C.byref(ms), C.byref(nl))
         return ms.value, nl.value
 
+    def last_kernel_times(self):
+        """ms of the last call's [front end, PSS correlator, track, SSS] stages (CUDA events)."""
+        ms = (C.c_float * 4)()
+        A.lib().ltb_trigger_last_kernel_times(self._h, ms)
+        return list(ms)
+
 
 def kernel_pss_corr(x, device=0):
     """x: [n_streams, n] complex64 -> power [n_streams, 3, n] (sliding, x[<0]=0)."""

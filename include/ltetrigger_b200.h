@@ -155,6 +155,9 @@ LTB_API int ltb_trigger_fetch_halfframes(ltb_trigger *t, ltb_cf *out, int max_ha
 /* device time of the last process/submit call's kernels, measured with CUDA events on
  * the launch stream (ms); and the number of kernel launches it made */
 LTB_API int ltb_trigger_last_timing(ltb_trigger *t, float *ms_total, int *n_launches);
+/* the same split by stage, CUDA events between the launches: [0] convert+decimate front end,
+ * [1] three-root PSS correlator, [2] per-chain track kernel, [3] batched SSS */
+LTB_API int ltb_trigger_last_kernel_times(ltb_trigger *t, float ms[4]);
 LTB_API const char *ltb_last_error(void);
 LTB_API const char *ltb_version(void);
 LTB_API int ltb_device_count(void);

@@ -169,25 +169,38 @@ void orc_sc16_to_fc32(const int16_t *iq, int64_t n, float scale, orc_cf *out)
 }
 
 /* rational_resampler_ccc(1, D): y[k] = sum_j taps[j] x[kD - j], zero history [A.7].
- * Canonical order: polyphase branch v = j mod D outer (ascending), q = j div D inner. */
+ * Canonical order: the D polyphase branches v = j mod D are split into G = min(4, D) groups
+ * of D/G consecutive branches; each group accumulates fma(taps[qD+v], x[kD-qD-v], acc) over
+ * v ascending, q = 0..32 ascending (taps beyond ntaps are zeros) in one chain per component,
+ * and y = (p0 + p1) + (p2 + p3)   [G=2: p0 + p1]. */
 int64_t orc_decimate(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
 {
   if (decim <= 1) { memcpy(y, x, sizeof(orc_cf) * n_in); return n_in; }
   float taps[1024];
   int ntaps = orc_decim_taps(decim, taps, 1024);
+  const int Q = (ntaps - 1) / decim + 1;
+  const int G = decim >= 4 ? 4 : decim, ppg = decim / G;
   int64_t n_out = (n_in + decim - 1) / decim;
   for (int64_t k = 0; k < n_out; k++) {
-    float ar = 0.f, ai = 0.f;
-    for (int v = 0; v < decim; v++) {
-      for (int j = v; j < ntaps; j += decim) {
-        int64_t idx = k * decim - j;
-        float xr = 0.f, xi = 0.f;
-        if (idx >= 0) { xr = x[idx].re; xi = x[idx].im; }
-        ar = fmaf(taps[j], xr, ar);
-        ai = fmaf(taps[j], xi, ai);
+    float pr[4] = {0, 0, 0, 0}, pi[4] = {0, 0, 0, 0};
+    for (int g = 0; g < G; g++) {
+      float ar = 0.f, ai = 0.f;
+      for (int v = g * ppg; v < (g + 1) * ppg; v++) {
+        for (int q = 0; q < Q; q++) {
+          int j = q * decim + v;
+          float t = j < ntaps ? taps[j] : 0.f;
+          int64_t idx = k * decim - j;
+          float xr = 0.f, xi = 0.f;
+          if (idx >= 0) { xr = x[idx].re; xi = x[idx].im; }
+          ar = fmaf(t, xr, ar);
+          ai = fmaf(t, xi, ai);
+        }
       }
+      pr[g] = ar; pi[g] = ai;
     }
-    y[k].re = ar; y[k].im = ai;
+    if (G == 4) { y[k].re = (pr[0] + pr[1]) + (pr[2] + pr[3]); y[k].im = (pi[0] + pi[1]) + (pi[2] + pi[3]); }
+    else if (G == 2) { y[k].re = pr[0] + pr[1]; y[k].im = pi[0] + pi[1]; }
+    else { y[k].re = pr[0]; y[k].im = pi[0]; }
   }
   return n_out;
 }

@@ -164,3 +164,33 @@ def test_record_all_off_keeps_only_emitted(lt):
     full = lt.Trigger(n_streams=1, max_chunk=384000).run(x[None, :])
     emit = lt.Trigger(n_streams=1, max_chunk=384000, record_all=False).run(x[None, :])
     assert_recs_equal(emit, full[(full["flags"] & lt.F_EMIT) != 0])
+
+
+def test_large_cfo_exercises_phasor_scan(lt, oracle):
+    """Large carrier offsets make srslte_cfo_correct's phase wrap often and visit many float
+    binades: the segmented scan in the track kernel must stay bit-identical to the oracle's
+    sample-by-sample loop, also over full half-frames (keep_halfframes)."""
+    from ltetrigger_b200 import synth
+    cfos = (-6000.0, 4000.0, 7400.0, -250.0, 15.0, 0.0)
+    x = np.stack([synth.capture(30 + 7 * i, 480000, snr_db=15.0, seed=i, cfo_hz=f) for i, f in enumerate(cfos)])
+    trig = lt.Trigger(n_streams=len(cfos), decim=1, max_chunk=480000, psr_threshold=2.5, keep_halfframes=True)
+    got = trig.run(x)
+    want = oracle.trigger_run(x, decim=1, psr_threshold=2.5)
+    assert_recs_equal(got, want)
+    assert ((got["flags"] & lt.F_TRACKING) != 0).sum() > 100
+    # emitted half-frames (CFO-corrected when tracking) against the oracle's pss block output
+    n_emit = int(((got["flags"] & lt.F_EMIT) != 0).sum())
+    hfs = trig.fetch_halfframes(n_emit)
+    k = 0
+    for s in range(len(cfos)):
+        buf = np.concatenate([np.zeros(960, np.complex64), x[s]])
+        for r in range(3):
+            blk = oracle.Pss(r, 2.5)
+            pos = 960
+            while pos - 960 + oracle.LOOKAHEAD <= x.shape[1]:
+                nout, ncons, out, rec = blk.work(buf, pos)
+                if nout:
+                    assert np.array_equal(hfs[k].view(np.uint32), out.view(np.uint32)), (s, r, pos)
+                    k += 1
+                pos += ncons
+    assert k == n_emit
