@@ -108,10 +108,12 @@ int ensure_constants(int device) {
   LTB_CUDA(cudaMemcpyToSymbol(c_sss_nid1, nid, sizeof nid));
   LTB_CUDA(cudaFuncSetAttribute(pss_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(TrackShared)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(16)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(16)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(16) + 120 * 1024));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(16) + 120 * 1024));
   LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(8)));
   LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(8)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(4)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(4)));
   g_const_done[device] = true;
   return LTB_SUCCESS;
 }
@@ -125,6 +127,8 @@ int make_cexp_device(float2 **out) {
   LTB_CUDA(cudaMemcpy(*out, tab.data(), sizeof(float2) * 4097, cudaMemcpyHostToDevice));
   return LTB_SUCCESS;
 }
+
+int g_debug_flags[4] = {0, 0, 0, 0};   // ltb_debug_set_flag: kernel dissection for profiling only
 
 bool valid_decim(int d) { return d == 1 || d == 2 || d == 4 || d == 8 || d == 16; }
 
@@ -143,8 +147,8 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
   const dim3 grid((m + kDecOut - 1) / kDecOut, n_streams);
 #define LTB_DECIM_CASE(D)                                                                             \
   case D: {                                                                                           \
-    decimate_kernel<FMT, D><<<grid, 32 * decim_groups(D), decim_smem_bytes(D), st>>>(                 \
-        d_iq, stride, m, tail_old, y_ring, n_base, mask, cap);                                        \
+    decimate_kernel<FMT, D><<<grid, 32 * decim_groups(D), decim_smem_bytes(D) + g_debug_flags[2], st>>>( \
+        d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, n_streams, g_debug_flags[0]);           \
   } break;
   switch (decim) {
     LTB_DECIM_CASE(2)
@@ -491,6 +495,17 @@ int ltb_trigger_last_timing(ltb_trigger *t, float *ms_total, int *n_launches) {
   if (!t) return LTB_ERROR_INVALID_INPUTS;
   if (ms_total) *ms_total = t->last_ms;
   if (n_launches) *n_launches = t->last_launches;
+  return LTB_SUCCESS;
+}
+
+int ltb_debug_set_trace(void *device_buffer) {
+  unsigned long long *p = (unsigned long long *)device_buffer;
+  return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof p) == cudaSuccess ? LTB_SUCCESS : LTB_ERROR;
+}
+
+int ltb_debug_set_flag(int flag, int value) {
+  if (flag < 0 || flag >= 4) return LTB_ERROR_INVALID_INPUTS;
+  g_debug_flags[flag] = value;
   return LTB_SUCCESS;
 }
 

@@ -96,7 +96,7 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
 // canonical complex product a*b:  re = fma(ar, br, -(ai*bi)),  im = fma(ar, bi, ai*br)
@@ -169,103 +169,139 @@ __device__ __forceinline__ float2 load_in_sample(const char *src, long long idx)
   return make_float2(__fmul_rn((float)s.x, k), __fmul_rn((float)s.y, k));
 }
 
-// Canonical order: the D polyphase branches are split into G = min(4, D) groups of
-// D/G consecutive branches; group g accumulates  fma(h[qD+v], x[kD-qD-v], acc)  over its
-// branches v (ascending) and q = 0..32 (ascending, taps beyond ntaps are zeros) in one chain per
-// component, and  y = (p0 + p1) + (p2 + p3).
+// Canonical order.  Write the input as aligned blocks X[b][p] = x[b*D + p]
+// (p = "position" 0..D-1).  Output k needs, for polyphase branch v = (D - p) % D and tap q,
+//   x[kD - qD - v] = X[k - q - (p > 0)][p].
+// The D positions are dealt to G = min(4, D) groups: group g owns positions p = g + G*h,
+// h = 0..D/G-1, and accumulates  fma(taps[qD+v], x[kD-qD-v], acc)  over h ascending, q = 0..32
+// ascending (taps beyond ntaps are zeros) in one chain per component; the G partials are then
+// summed as a balanced binary tree  (p0+p1)+(p2+p3).
 //
-// One CTA = 512 outputs of one stream, one warp per branch group, 16 consecutive outputs per
-// lane.  The (512+32)*D input samples of the tile are staged once in shared memory as
-// x_v[n'] = x[(k0-32+n')*D - v], row v, 16-way de-interleaved in n' (sub-row n' & 15), so that
-// the element a warp needs at one step (n' = 32 + 16*lane + e) is 32 consecutive float2: a
-// conflict-free LDS.64.  Each lane slides a 16-sample register window down one sample per tap:
-// 1 LDS.64 + 1 uniform coefficient load per 16 FFMA2.
+// Kernel: one CTA = 512 outputs of one stream, one warp per group, 16 consecutive outputs per
+// lane.  The (512+32) blocks x D positions the tile needs are staged once in shared memory, row
+// = position, 16-way de-interleaved in the block index so that the element a warp needs at one
+// step (block 32 + 16*lane + e) is 32 consecutive float2: a conflict-free LDS.64.  The staging
+// copies are 8-byte cp.async (LDGSTS) that write straight into that layout; three CTAs per SM
+// overlap one tile's copies with the others' arithmetic.  Each lane slides a 16-sample register
+// window down one block per tap: 1 LDS.64 + 1 coefficient load per 16 FFMA2, both issued
+// kDecPF steps ahead of their use so that shared-memory latency under load stays hidden.
 constexpr int kDecT = 16;                        // outputs per lane
-constexpr int kDecOut = 32 * kDecT;              // 512 outputs per CTA
+constexpr int kDecOut = 32 * kDecT;              // 512 outputs per tile
 constexpr int kDecQ = 33;                        // taps per polyphase branch (zero padded)
-constexpr int kDecGroups = kDecOut + kDecQ - 1;  // 544 n' values per branch
+constexpr int kDecGroups = kDecOut + kDecQ - 1;  // 544 blocks per position row
+constexpr int kDecSub = kDecGroups / 16;         // 34 columns per sub-row
 constexpr int kDecRow = kDecGroups + 1;          // 545 float2: odd stride -> conflict-free fill
+constexpr int kDecPF = 3;                        // software prefetch distance (taps)
 // (c, c) coefficient pairs per D at offsets 0 (D=2), 66 (D=4), 198 (D=8), 462 (D=16): [v][33]
 __constant__ float2 c_decim_pairs[990];
+__device__ unsigned long long *g_trace_buf = nullptr;   // profiling aid: per-CTA timestamps
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 __host__ __device__ constexpr int decim_pair_offset(int d) { return d == 2 ? 0 : d == 4 ? 66 : d == 8 ? 198 : 462; }
 __host__ __device__ constexpr int decim_groups(int d) { return d >= 4 ? 4 : d; }
 __host__ __device__ constexpr size_t decim_smem_bytes(int d) { return sizeof(float2) * (size_t)d * kDecRow; }
 
 template <int FMT, int D>
-__global__ void __launch_bounds__(32 * decim_groups(D))
+__global__ void __launch_bounds__(32 * decim_groups(D), D == 16 ? 3 : 4)
 decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
-                float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap) {
+                float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int n_streams, int dbg) {
   constexpr int G = decim_groups(D);
-  constexpr int PPG = D / G;
+  constexpr int PW = D / G;                       // positions per warp
   constexpr int NTHR = 32 * G;
   constexpr int POFF = decim_pair_offset(D);
+  constexpr int ITER = kDecGroups * D / NTHR;     // 68 / 34 / 17 / 17 for D = 16 / 8 / 4 / 2
+  constexpr int BSTEP = NTHR / D;                 // blocks advanced per fill iteration: 8 / 16 / 32 / 32
+  static_assert((kDecGroups * D) % NTHR == 0 && NTHR % D == 0, "tile geometry");
   extern __shared__ __align__(16) float2 s_x[];   // [D][kDecRow]
   const int stream = blockIdx.y;
   const int k0 = blockIdx.x * kDecOut;
   const char *src = (const char *)in + (long long)stream * stride_bytes;
   const float2 *tail = tail_in + (size_t)stream * kTailCap;
   const long long n_in = (long long)n_out * D;
-  // tile element j <-> input index idx0 + j, with  n' = j / D,  v = D-1 - (j % D)
-  const long long idx0 = (long long)(k0 - (kDecQ - 1)) * D - (D - 1);
-  if (FMT == LTB_FMT_FC32) {
-    // asynchronous 8-byte copies straight into the de-interleaved layout (LDGSTS): the whole
-    // tile is in flight at once while the SM's other resident CTAs keep the FMA pipe busy
-    for (int j = threadIdx.x; j < kDecGroups * D; j += NTHR) {
-      const long long idx = idx0 + j;
-      const int np = j / D, v = D - 1 - (j % D);
-      float2 *dst = &s_x[v * kDecRow + (np & 15) * (kDecGroups / 16) + (np >> 4)];
-      if (idx >= 0 && idx < n_in) {
-        cp_async_8(dst, src + idx * 8);
+
+  unsigned long long t_start = 0, t_fill = 0;
+  if ((dbg & 4) && threadIdx.x == 0) t_start = gtimer();
+  // ---- stage blocks k0-33 .. k0+510 (position 0: k0-32 .. k0+511) --------------------------------
+  {
+    const int p = threadIdx.x % D, c = threadIdx.x / D;
+    // block index np = c + BSTEP*it -> offset (np & 15)*kDecSub + (np >> 4), affine in `it`
+    float2 *d = s_x + p * kDecRow + (c & 15) * kDecSub + (c >> 4);
+    const long long i0 = (long long)D * (k0 - 33 + c) + p + (p == 0 ? D : 0);
+    const long long i_first = (long long)D * (k0 - 33), i_last = (long long)D * (k0 + 512);
+    if (dbg & 1) {
+      // profiling aid: skip the staging copies
+    } else if (i_first >= 0 && i_last < n_in) {
+      if (FMT == LTB_FMT_FC32) {
+        const float2 *gp = reinterpret_cast<const float2 *>(src) + i0;
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+          const int off = (BSTEP == 8) ? (it & 1) * 8 * kDecSub + (it >> 1) : (BSTEP / 16) * it;
+          cp_async_8(d + off, gp + (long long)NTHR * it);
+        }
+        if (!(dbg & 16)) cp_async_wait_all();
       } else {
-        *dst = (idx < 0 && idx >= -kTailCap) ? tail[kTailCap + idx] : make_float2(0.f, 0.f);
-      }
-    }
-    cp_async_wait_all();
-  } else {
-    // sc16: convert on the way in; loads batched 8 deep per thread for memory-level parallelism
-    constexpr int U = 8;
-    for (int j0 = threadIdx.x; j0 < kDecGroups * D; j0 += NTHR * U) {
-      float2 val[U];
+        const short2 *gp = reinterpret_cast<const short2 *>(src) + i0;
+        const float k = 1.0f / 32768.0f;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * NTHR;
-        const long long idx = idx0 + j;
-        val[u] = make_float2(0.f, 0.f);
-        if (j < kDecGroups * D) {
-          if (idx >= 0) { if (idx < n_in) val[u] = load_in_sample<FMT>(src, idx); }
-          else if (idx >= -kTailCap) val[u] = tail[kTailCap + idx];
+        for (int b0 = 0; b0 < ITER; b0 += 17) {
+          short2 raw[17];
+#pragma unroll
+          for (int u = 0; u < 17; ++u) raw[u] = __ldg(gp + (long long)NTHR * (b0 + u));
+#pragma unroll
+          for (int u = 0; u < 17; ++u) {
+            const int it = b0 + u;
+            const int off = (BSTEP == 8) ? (it & 1) * 8 * kDecSub + (it >> 1) : (BSTEP / 16) * it;
+            d[off] = make_float2(__fmul_rn((float)raw[u].x, k), __fmul_rn((float)raw[u].y, k));
+          }
         }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * NTHR;
-        if (j < kDecGroups * D) {
-          const int np = j / D, v = D - 1 - (j % D);
-          s_x[v * kDecRow + (np & 15) * (kDecGroups / 16) + (np >> 4)] = val[u];
-        }
+    } else {
+      // first / last tile of the chunk: samples before it come from the carried tail, samples
+      // past its end do not exist yet (the outputs that would need them are not stored)
+#pragma unroll 1
+      for (int it = 0; it < ITER; ++it) {
+        const long long idx = i0 + (long long)NTHR * it;
+        const int off = (BSTEP == 8) ? (it & 1) * 8 * kDecSub + (it >> 1) : (BSTEP / 16) * it;
+        float2 val = make_float2(0.f, 0.f);
+        if (idx >= 0) { if (idx < n_in) val = load_in_sample<FMT>(src, idx); }
+        else if (idx >= -kTailCap) val = tail[kTailCap + idx];
+        d[off] = val;
       }
     }
   }
   __syncthreads();
+  if ((dbg & 4) && threadIdx.x == 0) t_fill = gtimer();
 
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   float2 acc[kDecT], w[kDecT];
 #pragma unroll
   for (int o = 0; o < kDecT; ++o) acc[o] = make_float2(0.f, 0.f);
 #pragma unroll 1
-  for (int vv = 0; vv < PPG; ++vv) {
-    const int v = g * PPG + vv;
-    const float2 *row = s_x + v * kDecRow + 2 + lane;        // n' = 32 + 16*lane + e -> sub-row e & 15, col 2 + lane + (e >> 4)
+  for (int h = 0; h < ((dbg & 2) ? 0 : PW); ++h) {
+    const int p = g + G * h;
+    const int v = (D - p) % D;
+    // block 32 + 16*lane + e  ->  sub-row e & 15, column 2 + lane + (e >> 4)
+    const float2 *row = s_x + p * kDecRow + 2 + lane;
     const float2 *cf = c_decim_pairs + POFF + v * kDecQ;
+    const int qs = (dbg & 8) ? 0 : 1;
 #pragma unroll
-    for (int o = 0; o < kDecT; ++o) w[o] = row[o * (kDecGroups / 16)];
+    for (int o = 0; o < kDecT; ++o) w[o] = row[o * kDecSub];
+    float2 pre_x[kDecPF], pre_c[kDecPF];         // elements / coefficients of taps q+1 .. q+PF
+#pragma unroll
+    for (int j = 0; j < kDecPF; ++j) {
+      const int e = -(j + 1);
+      pre_x[j] = row[(e & 15) * kDecSub + (e >> 4)];
+      pre_c[j] = cf[j * qs];
+    }
 #pragma unroll
     for (int q = 0; q < kDecQ; ++q) {
-      if (q > 0) {
-        const int e = -q;                                    // new window element
-        w[e & 15] = row[(e & 15) * (kDecGroups / 16) + (e >> 4)];
+      if (q > 0) w[(-q) & 15] = pre_x[(q - 1) % kDecPF];
+      const float2 c = pre_c[q % kDecPF];
+      if (q > 0 && q - 1 + kDecPF + 1 < kDecQ) {
+        const int e = -(q + kDecPF);
+        pre_x[(q - 1) % kDecPF] = row[(e & 15) * kDecSub + (e >> 4)];
       }
-      const float2 c = cf[q];
+      if (q + kDecPF < kDecQ) pre_c[q % kDecPF] = cf[(q + kDecPF) * qs];
 #pragma unroll
       for (int o = 0; o < kDecT; ++o) acc[o] = ffma2(c, w[(o - q) & 15], acc[o]);
     }
@@ -278,7 +314,7 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
     }
     return;
   }
-  // partial sums -> shared memory [g][o][lane] (row stride 33), then (p0+p1)+(p2+p3)
+  // partial sums -> shared memory [g][o][lane] (row stride 33), then the balanced tree
   __syncthreads();
   float2 *part = s_x;
 #pragma unroll
@@ -286,16 +322,20 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
   __syncthreads();
   for (int i = threadIdx.x; i < kDecOut; i += NTHR) {
     const int o = i & 15, ln = i >> 4;
-    float2 y;
-    if (G == 2) {
-      y = fadd2(part[o * 33 + ln], part[(kDecT + o) * 33 + ln]);
-    } else {
-      const float2 a = fadd2(part[o * 33 + ln], part[(kDecT + o) * 33 + ln]);
-      const float2 b = fadd2(part[(2 * kDecT + o) * 33 + ln], part[(3 * kDecT + o) * 33 + ln]);
-      y = fadd2(a, b);
+    float2 pp[G];
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg) pp[gg] = part[(gg * kDecT + o) * 33 + ln];
+#pragma unroll
+    for (int w2 = 1; w2 < G; w2 <<= 1) {
+#pragma unroll
+      for (int gg = 0; gg < G; gg += 2 * w2) pp[gg] = fadd2(pp[gg], pp[gg + w2]);
     }
     const int k = k0 + i;
-    if (k < n_out) y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = y;
+    if (k < n_out) y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = pp[0];
+  }
+  if ((dbg & 4) && threadIdx.x == 0 && g_trace_buf != nullptr) {
+    unsigned long long *t = g_trace_buf + 4 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+    t[0] = t_start; t[1] = t_fill; t[2] = gtimer(); t[3] = smid();
   }
 }
 

@@ -1,0 +1,25 @@
+"""Times the decimator / correlator with parts switched off (ltb_debug_set_flag) to separate
+fill, FMA body and epilogue costs.  Profiling aid; run on a GPU box."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gr-ltetrigger_b200", "python"))
+import torch
+import ltetrigger_b200 as lt
+
+S, D = int(os.environ.get("S", 256)), int(os.environ.get("D", 16))
+n = 192000 * D
+x = torch.randn((S, n, 2), device="cuda", dtype=torch.float32)
+stream = torch.cuda.current_stream()
+for flag, name in ((0, "decimator"), (1, "correlator")):
+    for val, what in ((0, "normal"), (1, "no fill"), (2, "no fma body"), (3, "neither")):
+        lt.lib().ltb_debug_set_flag(flag, val)
+        trig = lt.Trigger(n_streams=S, decim=D, max_chunk=n, record_all=False, cuda_stream=stream.cuda_stream)
+        ts = []
+        for i in range(4):
+            trig.process_device_ptr(x.data_ptr(), n * 8, n)
+            ts.append(trig.last_kernel_times())
+        t = np.array(ts[1:]).mean(axis=0)
+        print("%-10s %-12s frontend %.3f ms  corr %.3f ms  track %.3f ms" % (name, what, t[0], t[1], t[2]), flush=True)
+        trig.close()
+    lt.lib().ltb_debug_set_flag(flag, 0)
