@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Turn ncu outputs into the small text summaries committed under profiles/.
+
+  ncu_summary.py launches <launches.csv> [--last-steps N]     per-launch list of this repo's kernels + shares
+  ncu_summary.py raw <report.ncu-rep>                         key metrics per profiled launch (needs ncu on PATH)
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEY_METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
+    "smsp__inst_executed.sum", "sm__cycles_elapsed.avg", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "lts__t_bytes.sum", "launch__grid_size", "launch__block_size",
+]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ci = {h: i for i, h in enumerate(hdr)}
+    mine = [r for r in rows[1:] if "ltb::" in r[ci["Kernel Name"]]]
+    print("# our kernels in %s: %d launches (torch data-generation kernels of bench.py omitted)" % (path, len(mine)))
+    print("id,kernel,grid,block,ns")
+    tot = collections.OrderedDict()
+    for r in mine:
+        name = r[ci["Kernel Name"]].split("(")[0].replace("void ", "")
+        ns = float(r[ci["Metric Value"]].replace(",", ""))
+        print("%s,%s,%s,%s,%.0f" % (r[ci["ID"]], name, r[ci["Grid Size"]].replace(",", " "), r[ci["Block Size"]].replace(",", " "), ns))
+        a = tot.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += ns
+    s = sum(v[1] for v in tot.values())
+    print("# kernel,launches,avg_us,share_of_our_gpu_time")
+    for k, (n, t) in tot.items():
+        print("# %s,%d,%.1f,%.3f" % (k, n, t / n / 1e3, t / s))
+
+
+def raw(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ci = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        print("kernel: %s" % r[ci["Kernel Name"]].split("(")[0])
+        for m in KEY_METRICS:
+            if m in ci:
+                print("  %-62s %s %s" % (m, r[ci[m]], units[ci[m]]))
+        rd, wr = float(r[ci["dram__bytes_read.sum"]]), float(r[ci["dram__bytes_write.sum"]])
+        u = units[ci["dram__bytes_read.sum"]]
+        print("  %-62s %.4f %s" % ("traffic = dram read + write", rd + wr, u))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2])
+    else:
+        raw(sys.argv[2])
