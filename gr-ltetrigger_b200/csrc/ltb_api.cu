@@ -41,6 +41,7 @@ int next_pow2(long long v) {
 // ---- constant tables, uploaded once per device ------------------------------------------
 std::mutex g_const_mu;
 bool g_const_done[64] = {false};
+int g_sm_count[64] = {0};
 
 int ensure_constants(int device) {
   std::lock_guard<std::mutex> lk(g_const_mu);
@@ -108,8 +109,9 @@ int ensure_constants(int device) {
   LTB_CUDA(cudaMemcpyToSymbol(c_sss_nid1, nid, sizeof nid));
   LTB_CUDA(cudaFuncSetAttribute(pss_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(TrackShared)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(16) + 120 * 1024));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(16) + 120 * 1024));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_stream_kernel<LTB_FMT_FC32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_stream_smem_bytes<LTB_FMT_FC32>()));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_stream_kernel<LTB_FMT_SC16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_stream_smem_bytes<LTB_FMT_SC16>()));
+  LTB_CUDA(cudaDeviceGetAttribute(&g_sm_count[device], cudaDevAttrMultiProcessorCount, device));
   LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(8)));
   LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(8)));
   LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(4)));
@@ -128,7 +130,9 @@ int make_cexp_device(float2 **out) {
   return LTB_SUCCESS;
 }
 
-int g_debug_flags[4] = {0, 0, 0, 0};   // ltb_debug_set_flag: kernel dissection for profiling only
+// ltb_debug_set_flag: [0] decimator dissection bits, [1] unused, [2] extra dynamic smem for the
+// tiled decimator (occupancy experiments), [3] unused
+int g_debug_flags[4] = {0, 0, 0, 0};
 
 bool valid_decim(int d) { return d == 1 || d == 2 || d == 4 || d == 8 || d == 16; }
 
@@ -145,6 +149,21 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
     return LTB_SUCCESS;
   }
   const dim3 grid((m + kDecOut - 1) / kDecOut, n_streams);
+  if (decim == 16) {
+    // streaming variant: four persistent CTAs per SM, each a contiguous run of 128-output segments
+    int dev = 0;
+    LTB_CUDA(cudaGetDevice(&dev));
+    const int sps = (m + kStrSeg - 1) / kStrSeg;
+    const long long total = (long long)sps * n_streams;
+    if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator segments in one call");
+    long long ctas = 4LL * (g_sm_count[dev] > 0 ? g_sm_count[dev] : 148);
+    if (ctas > total) ctas = total;
+    decimate_stream_kernel<FMT><<<(unsigned)ctas, 128, decim_stream_smem_bytes<FMT>(), st>>>(
+        d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total, g_debug_flags[0]);
+    tail_kernel<FMT><<<n_streams, 256, 0, st>>>(d_iq, stride, (long long)m * decim, tail_old, tail_new);
+    *launches += 2;
+    return LTB_SUCCESS;
+  }
 #define LTB_DECIM_CASE(D)                                                                             \
   case D: {                                                                                           \
     decimate_kernel<FMT, D><<<grid, 32 * decim_groups(D), decim_smem_bytes(D) + g_debug_flags[2], st>>>( \
@@ -154,7 +173,6 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
     LTB_DECIM_CASE(2)
     LTB_DECIM_CASE(4)
     LTB_DECIM_CASE(8)
-    LTB_DECIM_CASE(16)
     default: return fail(LTB_ERROR_INVALID_INPUTS, "unsupported decimation");
   }
 #undef LTB_DECIM_CASE
@@ -496,11 +514,6 @@ int ltb_trigger_last_timing(ltb_trigger *t, float *ms_total, int *n_launches) {
   if (ms_total) *ms_total = t->last_ms;
   if (n_launches) *n_launches = t->last_launches;
   return LTB_SUCCESS;
-}
-
-int ltb_debug_set_trace(void *device_buffer) {
-  unsigned long long *p = (unsigned long long *)device_buffer;
-  return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof p) == cudaSuccess ? LTB_SUCCESS : LTB_ERROR;
 }
 
 int ltb_debug_set_flag(int flag, int value) {

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/ltetrigger_b200.h"
 
 namespace ltb {
@@ -172,19 +174,18 @@ __device__ __forceinline__ float2 load_in_sample(const char *src, long long idx)
 // Canonical order.  Write the input as aligned blocks X[b][p] = x[b*D + p]
 // (p = "position" 0..D-1).  Output k needs, for polyphase branch v = (D - p) % D and tap q,
 //   x[kD - qD - v] = X[k - q - (p > 0)][p].
-// The D positions are dealt to G = min(4, D) groups: group g owns positions p = g + G*h,
-// h = 0..D/G-1, and accumulates  fma(taps[qD+v], x[kD-qD-v], acc)  over h ascending, q = 0..32
-// ascending (taps beyond ntaps are zeros) in one chain per component; the G partials are then
-// summed as a balanced binary tree  (p0+p1)+(p2+p3).
+// Every position accumulates  P[p] = fma(taps[qD+v], x[kD-qD-v], P[p])  over q = 0..32 ascending
+// (taps beyond ntaps are zeros) in one chain per component; the D partials are then summed by the
+// butterfly tree  P[p] += P[p + s] (p < s)  for s = D/2, D/4, .., 1.
 //
-// Kernel: one CTA = 512 outputs of one stream, one warp per group, 16 consecutive outputs per
-// lane.  The (512+32) blocks x D positions the tile needs are staged once in shared memory, row
-// = position, 16-way de-interleaved in the block index so that the element a warp needs at one
-// step (block 32 + 16*lane + e) is 32 consecutive float2: a conflict-free LDS.64.  The staging
-// copies are 8-byte cp.async (LDGSTS) that write straight into that layout; three CTAs per SM
-// overlap one tile's copies with the others' arithmetic.  Each lane slides a 16-sample register
-// window down one block per tap: 1 LDS.64 + 1 coefficient load per 16 FFMA2, both issued
-// kDecPF steps ahead of their use so that shared-memory latency under load stays hidden.
+// decimate_kernel (D = 2, 4, 8): one CTA = 512 outputs of one stream, one warp per position, 16
+// consecutive outputs per lane.  The (512+32) blocks x D positions the tile needs are staged once
+// in shared memory, row = position, 16-way de-interleaved in the block index so that the element
+// a warp needs at one step (block 32 + 16*lane + e) is 32 consecutive float2: a conflict-free
+// LDS.64.  The staging copies are 8-byte cp.async (LDGSTS) that write straight into that layout.
+// Each lane slides a 16-sample register window down one block per tap: 1 LDS.64 + 1 coefficient
+// load per 16 FFMA2, both issued kDecPF steps ahead of their use.  D = 16 has its own kernel
+// (decimate_stream_kernel below).
 constexpr int kDecT = 16;                        // outputs per lane
 constexpr int kDecOut = 32 * kDecT;              // 512 outputs per tile
 constexpr int kDecQ = 33;                        // taps per polyphase branch (zero padded)
@@ -194,15 +195,12 @@ constexpr int kDecRow = kDecGroups + 1;          // 545 float2: odd stride -> co
 constexpr int kDecPF = 3;                        // software prefetch distance (taps)
 // (c, c) coefficient pairs per D at offsets 0 (D=2), 66 (D=4), 198 (D=8), 462 (D=16): [v][33]
 __constant__ float2 c_decim_pairs[990];
-__device__ unsigned long long *g_trace_buf = nullptr;   // profiling aid: per-CTA timestamps
-__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 __host__ __device__ constexpr int decim_pair_offset(int d) { return d == 2 ? 0 : d == 4 ? 66 : d == 8 ? 198 : 462; }
-__host__ __device__ constexpr int decim_groups(int d) { return d >= 4 ? 4 : d; }
+__host__ __device__ constexpr int decim_groups(int d) { return d > 8 ? 8 : d; }   // one warp per position (D <= 8)
 __host__ __device__ constexpr size_t decim_smem_bytes(int d) { return sizeof(float2) * (size_t)d * kDecRow; }
 
 template <int FMT, int D>
-__global__ void __launch_bounds__(32 * decim_groups(D), D == 16 ? 3 : 4)
+__global__ void __launch_bounds__(32 * decim_groups(D), D == 8 ? 2 : 4)
 decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
                 float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int n_streams, int dbg) {
   constexpr int G = decim_groups(D);
@@ -212,6 +210,7 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
   constexpr int ITER = kDecGroups * D / NTHR;     // 68 / 34 / 17 / 17 for D = 16 / 8 / 4 / 2
   constexpr int BSTEP = NTHR / D;                 // blocks advanced per fill iteration: 8 / 16 / 32 / 32
   static_assert((kDecGroups * D) % NTHR == 0 && NTHR % D == 0, "tile geometry");
+  static_assert(G == D && PW == 1, "one warp per position: D <= 8 (D = 16 uses decimate_stream_kernel)");
   extern __shared__ __align__(16) float2 s_x[];   // [D][kDecRow]
   const int stream = blockIdx.y;
   const int k0 = blockIdx.x * kDecOut;
@@ -219,8 +218,6 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
   const float2 *tail = tail_in + (size_t)stream * kTailCap;
   const long long n_in = (long long)n_out * D;
 
-  unsigned long long t_start = 0, t_fill = 0;
-  if ((dbg & 4) && threadIdx.x == 0) t_start = gtimer();
   // ---- stage blocks k0-33 .. k0+510 (position 0: k0-32 .. k0+511) --------------------------------
   {
     const int p = threadIdx.x % D, c = threadIdx.x / D;
@@ -238,7 +235,7 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
           const int off = (BSTEP == 8) ? (it & 1) * 8 * kDecSub + (it >> 1) : (BSTEP / 16) * it;
           cp_async_8(d + off, gp + (long long)NTHR * it);
         }
-        if (!(dbg & 16)) cp_async_wait_all();
+        cp_async_wait_all();
       } else {
         const short2 *gp = reinterpret_cast<const short2 *>(src) + i0;
         const float k = 1.0f / 32768.0f;
@@ -270,7 +267,6 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
     }
   }
   __syncthreads();
-  if ((dbg & 4) && threadIdx.x == 0) t_fill = gtimer();
 
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   float2 acc[kDecT], w[kDecT];
@@ -283,7 +279,6 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
     // block 32 + 16*lane + e  ->  sub-row e & 15, column 2 + lane + (e >> 4)
     const float2 *row = s_x + p * kDecRow + 2 + lane;
     const float2 *cf = c_decim_pairs + POFF + v * kDecQ;
-    const int qs = (dbg & 8) ? 0 : 1;
 #pragma unroll
     for (int o = 0; o < kDecT; ++o) w[o] = row[o * kDecSub];
     float2 pre_x[kDecPF], pre_c[kDecPF];         // elements / coefficients of taps q+1 .. q+PF
@@ -291,7 +286,7 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
     for (int j = 0; j < kDecPF; ++j) {
       const int e = -(j + 1);
       pre_x[j] = row[(e & 15) * kDecSub + (e >> 4)];
-      pre_c[j] = cf[j * qs];
+      pre_c[j] = cf[j];
     }
 #pragma unroll
     for (int q = 0; q < kDecQ; ++q) {
@@ -301,7 +296,7 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
         const int e = -(q + kDecPF);
         pre_x[(q - 1) % kDecPF] = row[(e & 15) * kDecSub + (e >> 4)];
       }
-      if (q + kDecPF < kDecQ) pre_c[q % kDecPF] = cf[(q + kDecPF) * qs];
+      if (q + kDecPF < kDecQ) pre_c[q % kDecPF] = cf[q + kDecPF];
 #pragma unroll
       for (int o = 0; o < kDecT; ++o) acc[o] = ffma2(c, w[(o - q) & 15], acc[o]);
     }
@@ -326,16 +321,200 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
 #pragma unroll
     for (int gg = 0; gg < G; ++gg) pp[gg] = part[(gg * kDecT + o) * 33 + ln];
 #pragma unroll
-    for (int w2 = 1; w2 < G; w2 <<= 1) {
+    for (int w2 = G / 2; w2 >= 1; w2 >>= 1) {           // butterfly tree: P[p] += P[p + w2], p < w2
 #pragma unroll
-      for (int gg = 0; gg < G; gg += 2 * w2) pp[gg] = fadd2(pp[gg], pp[gg + w2]);
+      for (int gg = 0; gg < w2; ++gg) pp[gg] = fadd2(pp[gg], pp[gg + w2]);
     }
     const int k = k0 + i;
     if (k < n_out) y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = pp[0];
   }
-  if ((dbg & 4) && threadIdx.x == 0 && g_trace_buf != nullptr) {
-    unsigned long long *t = g_trace_buf + 4 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
-    t[0] = t_start; t[1] = t_fill; t[2] = gtimer(); t[3] = smid();
+}
+
+// ------------------------------------------------------------------------------------
+// K1s: streaming decimator for D = 16 (the rate where the front end dominates the step).
+//
+// decimate_kernel above stages a transposed tile with 8-byte cp.async; ncu and a dissection
+// (copies only: 3-4 TB/s) showed that path cannot feed the FMA pipe at D = 16.  Here the input is
+// copied *as it lies in memory* -- one cp.async.bulk (TMA, UBLKCP) of 20.6 kB per 128 outputs,
+// completion on an mbarrier, two buffers per CTA, four persistent CTAs per SM -- and the
+// layout problem is solved in the thread mapping instead: lane = (position p, half s), so the 16
+// lanes of a half-warp read the 16 positions of one input block, 128 contiguous bytes, for every
+// tap (conflict-free LDS.64 in natural layout).  Each lane runs the canonical chain of its own
+// position for 16 consecutive outputs (sliding 16-sample register window, 1 LDS per 16 FFMA2, its
+// 33 taps in registers), and the 16 position partials of every output are summed with the
+// canonical butterfly tree by shuffles, which leaves lane l with output 32*warp + l: one coalesced
+// store.  A CTA walks a contiguous run of 128-output segments; segment i+2 is requested as soon
+// as segment i's buffer is free, so one segment (20.6 kB) per CTA, ~100 kB per SM, is always in
+// flight while 16 warps per SM keep the FMA pipe covered across the per-segment tree and barrier.
+// ------------------------------------------------------------------------------------
+constexpr int kStrSeg = 128;                          // outputs per segment (4 warps x 32)
+constexpr int kStrBlocks = kStrSeg + kDecQ;           // 161 input blocks per segment
+constexpr int kStrBufs = 2;
+
+template <int FMT> __host__ __device__ constexpr int str_buf_bytes() { return kStrBlocks * 16 * (FMT == LTB_FMT_FC32 ? 8 : 4); }
+template <int FMT> __host__ __device__ constexpr size_t decim_stream_smem_bytes() { return (size_t)kStrBufs * str_buf_bytes<FMT>(); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "LTB_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra LTB_DONE_%=;\n\t"
+      "bra LTB_WAIT_%=;\n\t"
+      "LTB_DONE_%=:\n\t"
+      "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+               "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+               "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(128, 4)
+decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
+                       float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int segs_per_stream,
+                       int total_segs, int dbg) {
+  constexpr int D = 16;
+  constexpr int BPS = FMT == LTB_FMT_FC32 ? 8 : 4;                 // bytes per input sample
+  constexpr int BUF = str_buf_bytes<FMT>();
+  typedef typename std::conditional<FMT == LTB_FMT_FC32, float2, short2>::type elem_t;
+  extern __shared__ __align__(128) unsigned char s_raw[];          // [kStrBufs][161 blocks][16 positions]
+  __shared__ __align__(8) unsigned long long s_full[kStrBufs];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p = lane & 15, half = lane >> 4;
+  const long long n_in = (long long)n_out * D;
+
+  const int s_begin = (int)((long long)total_segs * blockIdx.x / gridDim.x);
+  const int s_end = (int)((long long)total_segs * (blockIdx.x + 1) / gridDim.x);
+  if (s_begin >= s_end) return;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < kStrBufs; ++b) mbar_init(&s_full[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  // this lane's taps: position p <-> polyphase branch v = (16 - p) % 16, c[q] = taps[16 q + v]
+  // (sc16: the 1/32768 input scale is folded into the taps; both products are exact, so
+  //  fma(c * 2^-15, s, acc) == fma(c, s * 2^-15, acc) bit for bit)
+  float c[kDecQ];
+  {
+    const int v = (D - p) % D;
+#pragma unroll
+    for (int q = 0; q < kDecQ; ++q) {
+      const float t = c_decim_taps[decim_tap_offset(D) + q * D + v];   // zero padded beyond ntaps
+      c[q] = FMT == LTB_FMT_FC32 ? t : __fmul_rn(t, 1.0f / 32768.0f);
+      // keep the 33 taps in registers: without this the compiler re-reads them from the constant
+      // bank inside the FMA loop, and a lane-indexed LDC replays once per distinct address
+      asm volatile("" : "+f"(c[q]));
+    }
+  }
+
+  // segment cursors (stream, k0), advanced incrementally: `cur` is computed on, `req` is the next
+  // one to request (kStrBufs ahead)
+  struct Seg { int stream, k0; };
+  const int k_end = segs_per_stream * kStrSeg;
+  auto advance = [&](Seg &S) { S.k0 += kStrSeg; if (S.k0 >= k_end) { S.k0 = 0; S.stream++; } };
+  auto is_fast = [&](const Seg &S) { return S.k0 >= kDecQ && (long long)D * (S.k0 + kStrSeg) <= n_in && !(dbg & 1); };
+  auto request = [&](const Seg &S, int b) {                        // one thread: TMA for segment S into buffer b
+    const char *src = (const char *)in + (long long)S.stream * stride_bytes;
+    mbar_expect_tx(&s_full[b], BUF);
+    bulk_copy_g2s(s_raw + b * BUF, src + (long long)D * (S.k0 - kDecQ) * BPS, BUF, &s_full[b]);
+  };
+  Seg cur, req;
+  cur.stream = s_begin / segs_per_stream;
+  cur.k0 = (s_begin - cur.stream * segs_per_stream) * kStrSeg;
+  req = cur;
+  for (int j = 0; j < kStrBufs && s_begin + j < s_end; ++j) {
+    if (tid == 0 && is_fast(req)) request(req, j);
+    advance(req);
+  }
+
+  unsigned phase_bits = 0;                                         // parity of each buffer's barrier
+  // window element e (= o - q) of this lane sits at block  32*warp + 16*half + 32 + (p == 0) + e
+  const int lane_elem = (32 * warp + 16 * half + 32 + (p == 0 ? 1 : 0)) * 16 + p;
+
+  for (int i = s_begin; i < s_end; ++i) {
+    const int b = (i - s_begin) % kStrBufs;
+    const Seg S = cur;
+    elem_t *buf = reinterpret_cast<elem_t *>(s_raw + b * BUF);
+    if (is_fast(S)) {
+      mbar_wait(&s_full[b], (phase_bits >> b) & 1u);
+      phase_bits ^= 1u << b;
+    } else if (!(dbg & 1)) {
+      // boundary segment: element-wise, with the carried tail before the chunk and zeros after it
+      const char *src = (const char *)in + (long long)S.stream * stride_bytes;
+      const long long i_first = (long long)D * (S.k0 - kDecQ);
+      const float2 *tail = tail_in + (size_t)S.stream * kTailCap;
+      for (int j = tid; j < kStrBlocks * 16; j += 128) {
+        const long long idx = i_first + j;
+        float2 val = make_float2(0.f, 0.f);
+        if (idx >= 0) { if (idx < n_in) val = load_in_sample<FMT>(src, idx); }
+        else if (idx >= -kTailCap) val = tail[kTailCap + idx];
+        if (FMT == LTB_FMT_FC32) reinterpret_cast<float2 *>(buf)[j] = val;
+        else reinterpret_cast<short2 *>(buf)[j] = make_short2((short)__fmul_rn(val.x, 32768.0f), (short)__fmul_rn(val.y, 32768.0f));
+      }
+      __syncthreads();
+    }
+
+    float2 acc[kDecT], w[kDecT];
+#pragma unroll
+    for (int o = 0; o < kDecT; ++o) acc[o] = make_float2(0.f, 0.f);
+    if (!(dbg & 2)) {
+      const elem_t *base = buf + lane_elem;
+      auto ld = [&](int e) -> float2 {                             // element e of the window
+        if (FMT == LTB_FMT_FC32) return reinterpret_cast<const float2 *>(base)[e * 16];
+        const short2 r = reinterpret_cast<const short2 *>(base)[e * 16];
+        return make_float2((float)r.x, (float)r.y);
+      };
+#pragma unroll
+      for (int o = 0; o < kDecT; ++o) w[o] = ld(o);
+      float2 pre[2];
+      pre[0] = ld(-1);
+      pre[1] = ld(-2);
+#pragma unroll
+      for (int q = 0; q < kDecQ; ++q) {
+        if (q > 0) w[(-q) & 15] = pre[(q - 1) & 1];
+        if (q > 0 && q + 2 < kDecQ) pre[(q - 1) & 1] = ld(-(q + 2));
+        const float2 cc = make_float2(c[q], c[q]);
+#pragma unroll
+        for (int o = 0; o < kDecT; ++o) acc[o] = ffma2(cc, w[(o - q) & 15], acc[o]);
+      }
+    }
+    // butterfly tree over the 16 positions: after the stage with lane mask m a lane keeps the
+    // half of its outputs selected by its own bit m; lane l ends with output o = l & 15
+#pragma unroll
+    for (int m = 8, n = 8; m >= 1; m >>= 1, n >>= 1) {
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        const float2 keep = up ? acc[j + n] : acc[j];
+        const float2 send = up ? acc[j] : acc[j + n];
+        float2 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, m);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, m);
+        acc[j] = fadd2(keep, recv);
+      }
+    }
+    {
+      const int k = S.k0 + 32 * warp + lane;
+      if (k < n_out) y_ring[(size_t)S.stream * cap + (unsigned)((n_base + k) & cap_mask)] = acc[0];
+    }
+    __syncthreads();                                               // everyone is done with buffer b
+    if (i + kStrBufs < s_end) {
+      if (tid == ((i & 3) << 5) && is_fast(req)) request(req, b);  // the four warps take turns
+      advance(req);
+    }
+    advance(cur);
   }
 }
 

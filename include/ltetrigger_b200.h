@@ -185,13 +185,9 @@ LTB_API int ltb_kernel_pss_corr_host(int device, const ltb_cf *x, int n_streams,
 LTB_API int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in,
                                      int decim, ltb_cf *y);
 
-/* Profiling aid, never needed for results: flag 0 dissects the decimator (bit 0: skip the tile
- * fill, bit 1: skip the FMA body); flag 1 dissects the correlator the same way.  Outputs are
- * garbage while a flag is set. */
+/* Profiling aid, never needed for results.  flag 0: decimator dissection (bit 0: skip the staging
+ * copies, bit 1: skip the FMA body; outputs are garbage while set). */
 LTB_API int ltb_debug_set_flag(int flag, int value);
-/* flag 0 bit 2: every decimator CTA writes {t_start, t_after_staging, t_end (globaltimer ns), smid}
- * to this device buffer (4 x u64 per CTA). */
-LTB_API int ltb_debug_set_trace(void *device_buffer);
 
 /* ---- tables (host only; no GPU needed) -------------------------------------------------- */
 /* srslte_pss_init + srslte_pss_set_N_id_2: 128 conj time-domain taps (lib/pss_impl.cc:72-75) */

@@ -170,40 +170,35 @@ void orc_sc16_to_fc32(const int16_t *iq, int64_t n, float scale, orc_cf *out)
 
 /* rational_resampler_ccc(1, D): y[k] = sum_j taps[j] x[kD - j], zero history [A.7].
  * Canonical order: the polyphase branches v = j mod D are addressed by their position
- * p = (D - v) % D inside an aligned block of D input samples; the D positions are dealt to
- * G = min(4, D) groups, group g owning p = g + G*h for h = 0..D/G-1.  Each group accumulates
- * fma(taps[qD+v], x[kD-qD-v], acc) over h ascending and q = 0..32 ascending (taps beyond ntaps
- * are zeros) in one chain per component, and the G partials are summed as a balanced binary
- * tree (p0+p1)+(p2+p3). */
+ * p = (D - v) % D inside an aligned block of D input samples.  Each position accumulates
+ *   P[p] = fma(taps[qD+v], x[kD-qD-v], P[p])   over q = 0..32 ascending
+ * (taps beyond ntaps are zeros) in one chain per component, and the D partials are summed by
+ * the butterfly tree  P[p] += P[p + s]  (p < s)  for s = D/2, D/4, ..., 1. */
 int64_t orc_decimate(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
 {
   if (decim <= 1) { memcpy(y, x, sizeof(orc_cf) * n_in); return n_in; }
   float taps[1024];
   int ntaps = orc_decim_taps(decim, taps, 1024);
   const int Q = (ntaps - 1) / decim + 1;
-  const int G = decim >= 4 ? 4 : decim, nh = decim / G;
   int64_t n_out = (n_in + decim - 1) / decim;
   for (int64_t k = 0; k < n_out; k++) {
-    float pr[16] = {0}, pi[16] = {0};
-    for (int g = 0; g < G; g++) {
+    float pr[16], pi[16];
+    for (int p = 0; p < decim; p++) {
+      const int v = (decim - p) % decim;
       float ar = 0.f, ai = 0.f;
-      for (int h = 0; h < nh; h++) {
-        int p = g + G * h;
-        int v = (decim - p) % decim;
-        for (int q = 0; q < Q; q++) {
-          int j = q * decim + v;
-          float t = j < ntaps ? taps[j] : 0.f;
-          int64_t idx = k * decim - j;
-          float xr = 0.f, xi = 0.f;
-          if (idx >= 0) { xr = x[idx].re; xi = x[idx].im; }
-          ar = fmaf(t, xr, ar);
-          ai = fmaf(t, xi, ai);
-        }
+      for (int q = 0; q < Q; q++) {
+        int j = q * decim + v;
+        float t = j < ntaps ? taps[j] : 0.f;
+        int64_t idx = k * decim - j;
+        float xr = 0.f, xi = 0.f;
+        if (idx >= 0) { xr = x[idx].re; xi = x[idx].im; }
+        ar = fmaf(t, xr, ar);
+        ai = fmaf(t, xi, ai);
       }
-      pr[g] = ar; pi[g] = ai;
+      pr[p] = ar; pi[p] = ai;
     }
-    for (int w = 1; w < G; w <<= 1)
-      for (int g = 0; g < G; g += 2 * w) { pr[g] = pr[g] + pr[g + w]; pi[g] = pi[g] + pi[g + w]; }
+    for (int s2 = decim / 2; s2 >= 1; s2 >>= 1)
+      for (int p = 0; p < s2; p++) { pr[p] = pr[p] + pr[p + s2]; pi[p] = pi[p] + pi[p + s2]; }
     y[k].re = pr[0]; y[k].im = pi[0];
   }
   return n_out;

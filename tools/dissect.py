@@ -11,9 +11,10 @@ S, D = int(os.environ.get("S", 256)), int(os.environ.get("D", 16))
 n = 192000 * D
 x = torch.randn((S, n, 2), device="cuda", dtype=torch.float32)
 stream = torch.cuda.current_stream()
-for flag, name in ((0, "decimator"), (1, "correlator")):
+for variant in (0,):
+    name = "decimator"
     for val, what in ((0, "normal"), (1, "no fill"), (2, "no fma body"), (3, "neither")):
-        lt.lib().ltb_debug_set_flag(flag, val)
+        lt.lib().ltb_debug_set_flag(0, val)
         trig = lt.Trigger(n_streams=S, decim=D, max_chunk=n, record_all=False, cuda_stream=stream.cuda_stream)
         ts = []
         for i in range(4):
@@ -22,4 +23,4 @@ for flag, name in ((0, "decimator"), (1, "correlator")):
         t = np.array(ts[1:]).mean(axis=0)
         print("%-10s %-12s frontend %.3f ms  corr %.3f ms  track %.3f ms" % (name, what, t[0], t[1], t[2]), flush=True)
         trig.close()
-    lt.lib().ltb_debug_set_flag(flag, 0)
+    lt.lib().ltb_debug_set_flag(0, 0)

@@ -51,9 +51,9 @@ def raw(path):
         for m in KEY_METRICS:
             if m in ci:
                 print("  %-62s %s %s" % (m, r[ci[m]], units[ci[m]]))
-        rd, wr = float(r[ci["dram__bytes_read.sum"]]), float(r[ci["dram__bytes_write.sum"]])
-        u = units[ci["dram__bytes_read.sum"]]
-        print("  %-62s %.4f %s" % ("traffic = dram read + write", rd + wr, u))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = sum(float(r[ci[m]]) * scale[units[ci[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        print("  %-62s %.4f Gbyte" % ("traffic = dram read + write", tot / 1e9))
 
 
 if __name__ == "__main__":
