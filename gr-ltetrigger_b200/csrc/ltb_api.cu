@@ -150,15 +150,15 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
   }
   const dim3 grid((m + kDecOut - 1) / kDecOut, n_streams);
   if (decim == 16) {
-    // streaming variant: four persistent CTAs per SM, each a contiguous run of 128-output segments
+    // streaming variant: two persistent 8-warp CTAs per SM, each a contiguous run of 256-output segments
     int dev = 0;
     LTB_CUDA(cudaGetDevice(&dev));
     const int sps = (m + kStrSeg - 1) / kStrSeg;
     const long long total = (long long)sps * n_streams;
     if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator segments in one call");
-    long long ctas = 4LL * (g_sm_count[dev] > 0 ? g_sm_count[dev] : 148);
+    long long ctas = 2LL * (g_sm_count[dev] > 0 ? g_sm_count[dev] : 148);
     if (ctas > total) ctas = total;
-    decimate_stream_kernel<FMT><<<(unsigned)ctas, 128, decim_stream_smem_bytes<FMT>(), st>>>(
+    decimate_stream_kernel<FMT><<<(unsigned)ctas, kStrThreads, decim_stream_smem_bytes<FMT>(), st>>>(
         d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total, g_debug_flags[0]);
     tail_kernel<FMT><<<n_streams, 256, 0, st>>>(d_iq, stride, (long long)m * decim, tail_old, tail_new);
     *launches += 2;

@@ -176,7 +176,7 @@ __device__ __forceinline__ float2 load_in_sample(const char *src, long long idx)
 //   x[kD - qD - v] = X[k - q - (p > 0)][p].
 // Every position accumulates  P[p] = fma(taps[qD+v], x[kD-qD-v], P[p])  over q = 0..32 ascending
 // (taps beyond ntaps are zeros) in one chain per component; the D partials are then summed by the
-// butterfly tree  P[p] += P[p + s] (p < s)  for s = D/2, D/4, .., 1.
+// balanced pairwise tree  ((P0+P1)+(P2+P3)) + ((P4+P5)+(P6+P7)) ...
 //
 // decimate_kernel (D = 2, 4, 8): one CTA = 512 outputs of one stream, one warp per position, 16
 // consecutive outputs per lane.  The (512+32) blocks x D positions the tile needs are staged once
@@ -321,9 +321,9 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
 #pragma unroll
     for (int gg = 0; gg < G; ++gg) pp[gg] = part[(gg * kDecT + o) * 33 + ln];
 #pragma unroll
-    for (int w2 = G / 2; w2 >= 1; w2 >>= 1) {           // butterfly tree: P[p] += P[p + w2], p < w2
+    for (int w2 = 1; w2 < G; w2 <<= 1) {                // pairwise tree: (P0+P1)+(P2+P3), ...
 #pragma unroll
-      for (int gg = 0; gg < w2; ++gg) pp[gg] = fadd2(pp[gg], pp[gg + w2]);
+      for (int gg = 0; gg < G; gg += 2 * w2) pp[gg] = fadd2(pp[gg], pp[gg + w2]);
     }
     const int k = k0 + i;
     if (k < n_out) y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = pp[0];
@@ -335,24 +335,34 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
 //
 // decimate_kernel above stages a transposed tile with 8-byte cp.async; ncu and a dissection
 // (copies only: 3-4 TB/s) showed that path cannot feed the FMA pipe at D = 16.  Here the input is
-// copied *as it lies in memory* -- one cp.async.bulk (TMA, UBLKCP) of 20.6 kB per 128 outputs,
-// completion on an mbarrier, two buffers per CTA, four persistent CTAs per SM -- and the
+// copied *as it lies in memory* -- one cp.async.bulk (TMA, UBLKCP) of 37 kB per 256 outputs,
+// completion on an mbarrier, two buffers per CTA, two persistent 8-warp CTAs per SM -- and the
 // layout problem is solved in the thread mapping instead: lane = (position p, half s), so the 16
 // lanes of a half-warp read the 16 positions of one input block, 128 contiguous bytes, for every
 // tap (conflict-free LDS.64 in natural layout).  Each lane runs the canonical chain of its own
 // position for 16 consecutive outputs (sliding 16-sample register window, 1 LDS per 16 FFMA2, its
-// 33 taps in registers), and the 16 position partials of every output are summed with the
-// canonical butterfly tree by shuffles, which leaves lane l with output 32*warp + l: one coalesced
-// store.  A CTA walks a contiguous run of 128-output segments; segment i+2 is requested as soon
-// as segment i's buffer is free, so one segment (20.6 kB) per CTA, ~100 kB per SM, is always in
-// flight while 16 warps per SM keep the FMA pipe covered across the per-segment tree and barrier.
+// 33 taps in registers; FFMA2 takes the tap as a scalar .F32 operand), and the 16 position
+// partials of every output are summed in the canonical pairwise tree after a transposition
+// through a per-warp shared-memory scratch, which leaves lane l with output 32*warp + l: one
+// coalesced store.  The FFMA2 stream saturates register-file read bandwidth (measured,
+// tools/ubench_issue.cu: other instructions do not hide in its shadow, they add), so the design
+// goal is the fewest non-FFMA2 instructions per 528 FFMA2: 48 LDS + a 47-instruction reduction.
+// A CTA walks a contiguous run of 256-output segments; the last warp to finish segment i requests
+// segment i+2 into the buffer it frees (a shared-memory counter, no CTA barrier), so warps drift
+// freely and one segment per CTA is always in flight.
 // ------------------------------------------------------------------------------------
-constexpr int kStrSeg = 128;                          // outputs per segment (4 warps x 32)
-constexpr int kStrBlocks = kStrSeg + kDecQ;           // 161 input blocks per segment
+constexpr int kStrWarps = 8;
+constexpr int kStrThreads = 32 * kStrWarps;
+constexpr int kStrSeg = 32 * kStrWarps;               // outputs per segment
+constexpr int kStrBlocks = kStrSeg + kDecQ;           // 289 input blocks per segment
 constexpr int kStrBufs = 2;
+constexpr int kStrScratchRow = 17;                    // float2 per (half, position) row: 16 outputs + 1 pad
+constexpr int kStrScratch = 2 * 16 * kStrScratchRow;  // float2 per warp
 
 template <int FMT> __host__ __device__ constexpr int str_buf_bytes() { return kStrBlocks * 16 * (FMT == LTB_FMT_FC32 ? 8 : 4); }
-template <int FMT> __host__ __device__ constexpr size_t decim_stream_smem_bytes() { return (size_t)kStrBufs * str_buf_bytes<FMT>(); }
+template <int FMT> __host__ __device__ constexpr size_t decim_stream_smem_bytes() {
+  return (size_t)kStrBufs * str_buf_bytes<FMT>() + sizeof(float2) * kStrScratch * kStrWarps;
+}
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
@@ -378,7 +388,7 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(kStrThreads, 2)
 decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
                        float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int segs_per_stream,
                        int total_segs, int dbg) {
@@ -386,8 +396,9 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
   constexpr int BPS = FMT == LTB_FMT_FC32 ? 8 : 4;                 // bytes per input sample
   constexpr int BUF = str_buf_bytes<FMT>();
   typedef typename std::conditional<FMT == LTB_FMT_FC32, float2, short2>::type elem_t;
-  extern __shared__ __align__(128) unsigned char s_raw[];          // [kStrBufs][161 blocks][16 positions]
+  extern __shared__ __align__(128) unsigned char s_raw[];          // [kStrBufs][289 blocks][16 positions], scratch
   __shared__ __align__(8) unsigned long long s_full[kStrBufs];
+  __shared__ unsigned s_done[kStrBufs];                            // warps finished with a buffer (monotonic)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = lane & 15, half = lane >> 4;
   const long long n_in = (long long)n_out * D;
@@ -398,7 +409,7 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
 
   if (tid == 0) {
 #pragma unroll
-    for (int b = 0; b < kStrBufs; ++b) mbar_init(&s_full[b], 1);
+    for (int b = 0; b < kStrBufs; ++b) { mbar_init(&s_full[b], 1); s_done[b] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -442,6 +453,7 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
   unsigned phase_bits = 0;                                         // parity of each buffer's barrier
   // window element e (= o - q) of this lane sits at block  32*warp + 16*half + 32 + (p == 0) + e
   const int lane_elem = (32 * warp + 16 * half + 32 + (p == 0 ? 1 : 0)) * 16 + p;
+  float2 *scratch = reinterpret_cast<float2 *>(s_raw + kStrBufs * BUF) + warp * kStrScratch + half * 16 * kStrScratchRow;
 
   for (int i = s_begin; i < s_end; ++i) {
     const int b = (i - s_begin) % kStrBufs;
@@ -452,10 +464,12 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
       phase_bits ^= 1u << b;
     } else if (!(dbg & 1)) {
       // boundary segment: element-wise, with the carried tail before the chunk and zeros after it
+      // (rare: two per stream and call; the only place where the warps of a CTA meet)
+      __syncthreads();                                             // every warp has left buffer b
       const char *src = (const char *)in + (long long)S.stream * stride_bytes;
       const long long i_first = (long long)D * (S.k0 - kDecQ);
       const float2 *tail = tail_in + (size_t)S.stream * kTailCap;
-      for (int j = tid; j < kStrBlocks * 16; j += 128) {
+      for (int j = tid; j < kStrBlocks * 16; j += kStrThreads) {
         const long long idx = i_first + j;
         float2 val = make_float2(0.f, 0.f);
         if (idx >= 0) { if (idx < n_in) val = load_in_sample<FMT>(src, idx); }
@@ -466,52 +480,61 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
       __syncthreads();
     }
 
-    float2 acc[kDecT], w[kDecT];
-#pragma unroll
-    for (int o = 0; o < kDecT; ++o) acc[o] = make_float2(0.f, 0.f);
-    if (!(dbg & 2)) {
+    // Element-major order: window element e (block offset from the lane's base) feeds output o
+    // with tap q = o - e.  Walking e downwards keeps every accumulator's chain in ascending q
+    // (the canonical order) while the up-to-16 consecutive FFMA2 of one element share their data
+    // operand through the register reuse cache: 3 register reads per FFMA2 instead of 4, which is
+    // what lets the pipe run at 2 cycles per FFMA2 (tools/ubench_issue.cu).
+    float2 acc[kDecT];
+    {
       const elem_t *base = buf + lane_elem;
       auto ld = [&](int e) -> float2 {                             // element e of the window
         if (FMT == LTB_FMT_FC32) return reinterpret_cast<const float2 *>(base)[e * 16];
         const short2 r = reinterpret_cast<const short2 *>(base)[e * 16];
         return make_float2((float)r.x, (float)r.y);
       };
+      constexpr int PF = 4;                                        // elements loaded ahead of their use
+      float2 x[PF];
 #pragma unroll
-      for (int o = 0; o < kDecT; ++o) w[o] = ld(o);
-      float2 pre[2];
-      pre[0] = ld(-1);
-      pre[1] = ld(-2);
+      for (int j = 0; j < PF; ++j) x[j] = ld(kDecT - 1 - j);
 #pragma unroll
-      for (int q = 0; q < kDecQ; ++q) {
-        if (q > 0) w[(-q) & 15] = pre[(q - 1) & 1];
-        if (q > 0 && q + 2 < kDecQ) pre[(q - 1) & 1] = ld(-(q + 2));
-        const float2 cc = make_float2(c[q], c[q]);
+      for (int e = kDecT - 1; e >= -(kDecQ - 1); --e) {
+        const int slot = (kDecT - 1 - e) % PF;
+        const float2 xe = x[slot];
+        if (e - PF >= -(kDecQ - 1)) x[slot] = ld(e - PF);
 #pragma unroll
-        for (int o = 0; o < kDecT; ++o) acc[o] = ffma2(cc, w[(o - q) & 15], acc[o]);
+        for (int o = 0; o < kDecT; ++o) {
+          const int q = o - e;
+          if (q >= 0 && q < kDecQ) {
+            const float2 cc = make_float2(c[q], c[q]);
+            acc[o] = ffma2(cc, xe, q == 0 ? make_float2(0.f, 0.f) : acc[o]);
+          }
+        }
       }
     }
-    // butterfly tree over the 16 positions: after the stage with lane mask m a lane keeps the
-    // half of its outputs selected by its own bit m; lane l ends with output o = l & 15
-#pragma unroll
-    for (int m = 8, n = 8; m >= 1; m >>= 1, n >>= 1) {
-      const bool up = (lane & m) != 0;
-#pragma unroll
-      for (int j = 0; j < n; ++j) {
-        const float2 keep = up ? acc[j + n] : acc[j];
-        const float2 send = up ? acc[j] : acc[j + n];
-        float2 recv;
-        recv.x = __shfl_xor_sync(0xffffffffu, send.x, m);
-        recv.y = __shfl_xor_sync(0xffffffffu, send.y, m);
-        acc[j] = fadd2(keep, recv);
-      }
-    }
+    // transpose through the warp's scratch: row = (half, position), column = output; then lane
+    // (o, half) sums the 16 position partials of output o in the canonical pairwise tree
     {
+      float2 *wr = scratch + p * kStrScratchRow;
+#pragma unroll
+      for (int o = 0; o < kDecT; ++o) wr[o] = acc[o];
+      __syncwarp();
+      float2 pp[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) pp[r] = scratch[r * kStrScratchRow + p];
+#pragma unroll
+      for (int w2 = 1; w2 < 16; w2 <<= 1) {
+#pragma unroll
+        for (int r = 0; r < 16; r += 2 * w2) pp[r] = fadd2(pp[r], pp[r + w2]);
+      }
       const int k = S.k0 + 32 * warp + lane;
-      if (k < n_out) y_ring[(size_t)S.stream * cap + (unsigned)((n_base + k) & cap_mask)] = acc[0];
+      if (k < n_out) y_ring[(size_t)S.stream * cap + (unsigned)((n_base + k) & cap_mask)] = pp[0];
     }
-    __syncthreads();                                               // everyone is done with buffer b
+    // release buffer b without a CTA barrier: the last of the warps to get here requests the
+    // segment that goes into it next, so no warp ever waits for its siblings
+    __syncwarp();
     if (i + kStrBufs < s_end) {
-      if (tid == ((i & 3) << 5) && is_fast(req)) request(req, b);  // the four warps take turns
+      if (lane == 0 && (atomicAdd(&s_done[b], 1u) % kStrWarps) == kStrWarps - 1 && is_fast(req)) request(req, b);
       advance(req);
     }
     advance(cur);

@@ -173,7 +173,7 @@ void orc_sc16_to_fc32(const int16_t *iq, int64_t n, float scale, orc_cf *out)
  * p = (D - v) % D inside an aligned block of D input samples.  Each position accumulates
  *   P[p] = fma(taps[qD+v], x[kD-qD-v], P[p])   over q = 0..32 ascending
  * (taps beyond ntaps are zeros) in one chain per component, and the D partials are summed by
- * the butterfly tree  P[p] += P[p + s]  (p < s)  for s = D/2, D/4, ..., 1. */
+ * the balanced pairwise tree  ((P0+P1)+(P2+P3)) + ((P4+P5)+(P6+P7)) ... */
 int64_t orc_decimate(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
 {
   if (decim <= 1) { memcpy(y, x, sizeof(orc_cf) * n_in); return n_in; }
@@ -197,8 +197,8 @@ int64_t orc_decimate(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
       }
       pr[p] = ar; pi[p] = ai;
     }
-    for (int s2 = decim / 2; s2 >= 1; s2 >>= 1)
-      for (int p = 0; p < s2; p++) { pr[p] = pr[p] + pr[p + s2]; pi[p] = pi[p] + pi[p + s2]; }
+    for (int w = 1; w < decim; w <<= 1)
+      for (int p = 0; p < decim; p += 2 * w) { pr[p] = pr[p] + pr[p + w]; pi[p] = pi[p] + pi[p + w]; }
     y[k].re = pr[0]; y[k].im = pi[0];
   }
   return n_out;
