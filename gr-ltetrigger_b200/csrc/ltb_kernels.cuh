@@ -375,7 +375,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       "{\n\t"
       ".reg .pred p;\n\t"
       "LTB_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra LTB_DONE_%=;\n\t"
       "bra LTB_WAIT_%=;\n\t"
       "LTB_DONE_%=:\n\t"
