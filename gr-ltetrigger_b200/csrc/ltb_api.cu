@@ -275,8 +275,14 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   if (rc) return rc;
   if (c.decim > 1) t->tail_cur ^= 1;
   LTB_CUDA(cudaEventRecord(t->ev_k[0], t->stream));
-  pss_corr_kernel<<<dim3((m + kCorrTile - 1) / kCorrTile, S), kCorrThreads, 0, t->stream>>>(
-      t->d_y, t->d_p, n_base, m, t->cap_mask, t->cap);
+  {
+    const int tps = (m + kCorrTile - 1) / kCorrTile;
+    const long long total = (long long)tps * S;
+    if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many correlator tiles in one call");
+    long long ctas = 2LL * (g_sm_count[c.device] > 0 ? g_sm_count[c.device] : 148);
+    if (ctas > total) ctas = total;
+    pss_corr_kernel<<<(unsigned)ctas, kCorrThreads, 0, t->stream>>>(t->d_y, t->d_p, n_base, m, t->cap_mask, t->cap, tps, (int)total);
+  }
   launches++;
   LTB_CUDA(cudaEventRecord(t->ev_k[1], t->stream));
   t->n_total += m;
@@ -607,7 +613,11 @@ int ltb_kernel_pss_corr_host(int device, const ltb_cf *x, int n_streams, int64_t
   if (e == cudaSuccess) e = cudaMemset(d_y, 0, sizeof(float2) * (size_t)n_streams * cap);
   if (e == cudaSuccess) e = cudaMemcpy2D(d_y, sizeof(float2) * (size_t)cap, x, sizeof(float2) * (size_t)n, sizeof(float2) * (size_t)n, n_streams, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    pss_corr_kernel<<<dim3((unsigned)((n + kCorrTile - 1) / kCorrTile), n_streams), kCorrThreads>>>(d_y, d_p, 0, (int)n, (unsigned)(cap - 1), cap);
+    const int tps = (int)((n + kCorrTile - 1) / kCorrTile);
+    const long long total = (long long)tps * n_streams;
+    long long ctas = 2LL * (g_sm_count[device] > 0 ? g_sm_count[device] : 148);
+    if (ctas > total) ctas = total;
+    pss_corr_kernel<<<(unsigned)ctas, kCorrThreads>>>(d_y, d_p, 0, (int)n, (unsigned)(cap - 1), cap, tps, (int)total);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy2D(power, sizeof(float) * (size_t)n, d_p, sizeof(float) * (size_t)cap, sizeof(float) * (size_t)n, (size_t)n_streams * 3, cudaMemcpyDeviceToHost);

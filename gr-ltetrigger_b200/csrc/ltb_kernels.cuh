@@ -580,21 +580,36 @@ __device__ __forceinline__ float2 corr_lds(const float2 *row_base, int e) {
   return row_base[(e & 7) * kCorrRowStride + (e >> 3)];
 }
 
+// Persistent: a CTA walks a contiguous run of (stream, tile) pairs with two tile buffers; the
+// 8-byte cp.async copies of tile i+1 (straight into the de-interleaved layout) are issued before
+// the arithmetic of tile i, so staging latency -- 38 % of the warp time in the one-tile-per-CTA
+// version (ncu) -- is hidden behind ~2600 FP instructions per thread.
 __global__ void __launch_bounds__(kCorrThreads, 2)
 pss_corr_kernel(const float2 *__restrict__ y_ring, float *__restrict__ p_ring, long long n_base, int n_new,
-                unsigned cap_mask, int cap) {
-  __shared__ float2 sx[8 * kCorrRowStride];
-  const int stream = blockIdx.y;
-  const long long n0 = n_base + (long long)blockIdx.x * kCorrTile;   // absolute index of output 0
-  const float2 *yr = y_ring + (size_t)stream * cap;
-
-  // stage samples n0-128 .. n0+2048 (tile index u = n - n0 + 128), two per thread per step
-  for (int u = threadIdx.x * 2; u < kCorrTile + 128; u += kCorrThreads * 2) {
-    const float4 v = *reinterpret_cast<const float4 *>(&yr[(unsigned)((n0 - 128 + u) & cap_mask)]);
-    sx[(u & 7) * kCorrRowStride + (u >> 3)] = make_float2(v.x, v.y);
-    sx[((u + 1) & 7) * kCorrRowStride + (u >> 3)] = make_float2(v.z, v.w);
-  }
-  __syncthreads();
+                unsigned cap_mask, int cap, int tiles_per_stream, int total_tiles) {
+  __shared__ float2 sx2[2][8 * kCorrRowStride];
+  const int t_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
+  // stage samples n0-128 .. n0+2048 of tile `tile` (tile index u = n - n0 + 128)
+  auto stage = [&](int tile, float2 *dst) {
+    const int st = tile / tiles_per_stream;
+    const long long n0 = n_base + (long long)(tile - st * tiles_per_stream) * kCorrTile;
+    const float2 *yr = y_ring + (size_t)st * cap;
+#pragma unroll
+    for (int j = 0; j < (kCorrTile + 128 + kCorrThreads - 1) / kCorrThreads; ++j) {
+      const int u = threadIdx.x + j * kCorrThreads;
+      if (u < kCorrTile + 128) cp_async_8(&dst[(u & 7) * kCorrRowStride + (u >> 3)], &yr[(unsigned)((n0 - 128 + u) & cap_mask)]);
+    }
+  };
+  if (t_begin < t_end) stage(t_begin, sx2[0]);
+  for (int tile = t_begin; tile < t_end; ++tile) {
+  const float2 *sx = sx2[(tile - t_begin) & 1];
+  const int stream = tile / tiles_per_stream;
+  const int tile_x = tile - stream * tiles_per_stream;
+  const long long n0 = n_base + (long long)tile_x * kCorrTile;   // absolute index of output 0
+  cp_async_wait_all();
+  __syncthreads();                       // tile landed; everyone is done with the other buffer
+  if (tile + 1 < t_end) stage(tile + 1, sx2[(tile - t_begin + 1) & 1]);
 
   const int t = threadIdx.x;
   const float2 *rb = sx + t;          // column offset t; corr_lds adds row and the constant column
@@ -657,7 +672,7 @@ pss_corr_kernel(const float2 *__restrict__ y_ring, float *__restrict__ p_ring, l
 #undef LTB_CORR_STEP
 
   const int local = t * 8;
-  if ((long long)blockIdx.x * kCorrTile + local >= n_new) return;   // n_new is a multiple of 8
+  if ((long long)tile_x * kCorrTile + local >= n_new) continue;   // n_new is a multiple of 8
   float p0[8], p1[8], p2[8];
 #pragma unroll
   for (int o = 0; o < 8; ++o) {
@@ -677,6 +692,7 @@ pss_corr_kernel(const float2 *__restrict__ y_ring, float *__restrict__ p_ring, l
   reinterpret_cast<float4 *>(pp + cap)[1] = make_float4(p1[4], p1[5], p1[6], p1[7]);
   reinterpret_cast<float4 *>(pp + 2 * (size_t)cap)[0] = make_float4(p2[0], p2[1], p2[2], p2[3]);
   reinterpret_cast<float4 *>(pp + 2 * (size_t)cap)[1] = make_float4(p2[4], p2[5], p2[6], p2[7]);
+  }
 }
 
 // ------------------------------------------------------------------------------------
