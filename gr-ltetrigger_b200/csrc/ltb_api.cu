@@ -206,7 +206,7 @@ struct ltb_trigger {
   int *d_rec_count = nullptr;
   float2 *d_sss_sym = nullptr;
   int *d_sss_rec = nullptr;
-  int *d_sss_count = nullptr;
+  int *d_sss_count = nullptr;     // [0] SSS candidate count, [1] track-kernel chain queue head
   int sss_cap = 0;
   float2 *d_hf = nullptr;
   float2 *d_tail[2] = {nullptr, nullptr};
@@ -288,7 +288,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   t->n_total += m;
   t->w_cur = m / (kHalf - kSlot) + 4;
   if (t->w_cur > t->w_cap) t->w_cur = t->w_cap;
-  LTB_CUDA(cudaMemsetAsync(t->d_sss_count, 0, sizeof(int), t->stream));
+  LTB_CUDA(cudaMemsetAsync(t->d_sss_count, 0, 2 * sizeof(int), t->stream));
   TrackParams P;
   P.y_ring = t->d_y; P.p_ring = t->d_p; P.state = t->d_state; P.avg = t->d_avg; P.thr = t->d_thr;
   P.recs = t->d_recs; P.rec_count = t->d_rec_count; P.sss_sym = t->d_sss_sym; P.sss_rec = t->d_sss_rec;
@@ -296,7 +296,12 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   P.n_total = t->n_total; P.cap_mask = t->cap_mask; P.cap = t->cap; P.w_max = t->w_cur;
   P.track_after = c.track_after; P.track_every = c.track_every; P.record_all = c.record_all;
   P.root_mask = c.root_mask;
-  pss_track_kernel<<<t->n_chains, kTrackThreads, sizeof(TrackShared), t->stream>>>(P);
+  P.chain_counter = t->d_sss_count + 1; P.n_chains = t->n_chains;
+  {
+    int ctas = 4 * (g_sm_count[c.device] > 0 ? g_sm_count[c.device] : 148);
+    if (ctas > t->n_chains) ctas = t->n_chains;
+    pss_track_kernel<<<ctas, kTrackThreads, sizeof(TrackShared), t->stream>>>(P);
+  }
   launches++;
   LTB_CUDA(cudaEventRecord(t->ev_k[2], t->stream));
   int sss_grid = (t->n_chains * t->w_cur + kSssWarps - 1) / kSssWarps;
@@ -377,7 +382,7 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   LTB_CUDA_T(cudaMalloc(&t->d_rec_count, sizeof(int) * t->n_chains));
   LTB_CUDA_T(cudaMalloc(&t->d_sss_sym, sizeof(float2) * 128 * (size_t)t->sss_cap));
   LTB_CUDA_T(cudaMalloc(&t->d_sss_rec, sizeof(int) * t->sss_cap));
-  LTB_CUDA_T(cudaMalloc(&t->d_sss_count, sizeof(int)));
+  LTB_CUDA_T(cudaMalloc(&t->d_sss_count, 2 * sizeof(int)));
   LTB_CUDA_T(cudaMalloc(&t->d_tail[0], sizeof(float2) * (size_t)S * kTailCap));
   LTB_CUDA_T(cudaMalloc(&t->d_tail[1], sizeof(float2) * (size_t)S * kTailCap));
   if (c.keep_halfframes) LTB_CUDA_T(cudaMalloc(&t->d_hf, sizeof(float2) * kHalf * (size_t)t->n_chains * t->w_cap));

@@ -75,6 +75,8 @@ struct TrackParams {
   float2 *sss_sym;           // [sss_cap][128]
   int *sss_rec;              // [sss_cap] -> index into recs
   int *sss_count;            // global counter
+  int *chain_counter;        // work queue head (zeroed before every launch)
+  int n_chains;
   int sss_cap;
   float2 *hf_out;            // [n_streams*3][w_max][9600] or null
   const float2 *cexp;        // 4097 entries
@@ -121,12 +123,15 @@ __device__ double canon_atan2(double y, double x) {
     off = 0.78539816339744828;
   }
   const double t2 = __dmul_rn(t, t);
-  double p = 1.0 / 35.0;
-#pragma unroll 1
+  // 1/(2k+1), k = 0..17: compile-time IEEE quotients, the same doubles the oracle's divisions give
+  constexpr double kInvOdd[18] = {1.0 / 1.0,  1.0 / 3.0,  1.0 / 5.0,  1.0 / 7.0,  1.0 / 9.0,  1.0 / 11.0,
+                                  1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0, 1.0 / 21.0, 1.0 / 23.0,
+                                  1.0 / 25.0, 1.0 / 27.0, 1.0 / 29.0, 1.0 / 31.0, 1.0 / 33.0, 1.0 / 35.0};
+  double p = kInvOdd[17];
+#pragma unroll
   for (int k = 16; k >= 0; --k) {
-    const double c = __ddiv_rn(1.0, (double)(2 * k + 1));
     p = -p;
-    p = __fma_rn(p, t2, c);
+    p = __fma_rn(p, t2, kInvOdd[k]);
   }
   double r = __fma_rn(t, p, off);
   if (ay > ax) r = __dadd_rn(1.5707963267948966, -r);
@@ -768,31 +773,34 @@ struct TrackShared {
   float2 y01[2];
   // broadcast slots
   int p, lb, ub; float peak, lmax, rmax;
-  int do_emit, do_track, zero_avg, frame_start, rec_slot, sss_slot, cp_len;
+  int do_emit, do_track, zero_avg, frame_start, rec_slot, sss_slot, cp_len, chain;
   long long emit_abs;
   ChainState st;
 };
 
 // canonical folded correlation power at one lag of a zero-padded window; buf index of x[k]
-// is `pos`, buf[pos-127 .. pos] readable
+// is `pos`, buf[pos-127 .. pos] readable.  G = coefficient group (0: root 25, 1: roots 29/34) is a
+// template parameter and the tap loop is fully unrolled so that every coefficient is a
+// constant-bank operand of its FFMA2: with a run-time group the loop issued two indexed constant
+// loads per tap and took 14k cycles per window (measured with clock64 instrumentation).
+template <int G>
 __device__ __forceinline__ float edge_power(const float2 *buf, int pos, int n_id_2) {
-  const int g = n_id_2 == 0 ? 0 : 1;
   float2 ab = make_float2(0.f, 0.f), dc = make_float2(0.f, 0.f);
   {
     const float2 s = buf[pos];
-    ab = ffma2(c_pss_coef[g][0][0], s, ab);
-    dc = ffma2(c_pss_coef[g][0][1], s, dc);
+    ab = ffma2(c_pss_coef[G][0][0], s, ab);
+    dc = ffma2(c_pss_coef[G][0][1], s, dc);
   }
-#pragma unroll 1
+#pragma unroll
   for (int m = 1; m <= 63; ++m) {
     const float2 s = fadd2(buf[pos - m], buf[pos - 128 + m]);
-    ab = ffma2(c_pss_coef[g][m][0], s, ab);
-    dc = ffma2(c_pss_coef[g][m][1], s, dc);
+    ab = ffma2(c_pss_coef[G][m][0], s, ab);
+    dc = ffma2(c_pss_coef[G][m][1], s, dc);
   }
   {
     const float2 s = buf[pos - 64];
-    ab = ffma2(c_pss_coef[g][64][0], s, ab);
-    dc = ffma2(c_pss_coef[g][64][1], s, dc);
+    ab = ffma2(c_pss_coef[G][64][0], s, ab);
+    dc = ffma2(c_pss_coef[G][64][1], s, dc);
   }
   float re, im;
   if (n_id_2 == 2) { re = __fadd_rn(ab.x, ab.y); im = __fadd_rn(dc.y, -dc.x); }
@@ -800,13 +808,20 @@ __device__ __forceinline__ float edge_power(const float2 *buf, int pos, int n_id
   return __fmaf_rn(re, re, __fmul_rn(im, im));
 }
 
-__global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P) {
+__global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackShared &S = *reinterpret_cast<TrackShared *>(smem_raw);
-  const int chain = blockIdx.x;
-  const int stream = chain / 3, n_id_2 = chain % 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (!((P.root_mask >> n_id_2) & 1)) { if (tid == 0) P.rec_count[chain] = 0; return; }
+  // Persistent CTAs pull chains from a queue: a tracking chain costs ~1.5x a searching one, and
+  // 1536 chains over 444 resident CTAs were 3.46 waves, i.e. four rounds of the slowest chain.
+  for (;;) {
+  __syncthreads();                                                  // previous chain fully written back
+  if (tid == 0) S.chain = atomicAdd(P.chain_counter, 1);
+  __syncthreads();
+  const int chain = S.chain;
+  if (chain >= P.n_chains) break;
+  const int stream = chain / 3, n_id_2 = chain % 3;
+  if (!((P.root_mask >> n_id_2) & 1)) { if (tid == 0) P.rec_count[chain] = 0; continue; }
 
   const float2 *yr = P.y_ring + (size_t)stream * P.cap;
   const float *pr = P.p_ring + ((size_t)stream * 3 + n_id_2) * P.cap;
@@ -827,6 +842,17 @@ __global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P)
     __syncthreads();                                                // everyone has read S.st
     if (search) {
       // ---- srslte_pss_find_pss ------------------------------------------------
+      // the lags this thread owns (k = tid + 256 j) are requested in two batches of 19 (register
+      // budget for four CTAs per SM); the first batch is in flight during the edge computation,
+      // and both mostly hit L2 thanks to the prefetch issued at the end of the previous window
+      constexpr int kPerThread = (kNLag + kTrackThreads - 1) / kTrackThreads;   // 38
+      constexpr int kBatch = kPerThread / 2;                                    // 19
+      float a[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int k = tid + j * kTrackThreads;
+        a[j] = (k >= 127 && k < kHalf) ? __ldg(&pr[(unsigned)((R + k) & P.cap_mask)]) : 0.f;
+      }
       if (tid < 127) {
         S.lead[128 + tid] = yr[(unsigned)((R + tid) & P.cap_mask)];
         S.trail[1 + tid] = yr[(unsigned)((R + 9473 + tid) & P.cap_mask)];
@@ -834,30 +860,29 @@ __global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P)
       __syncthreads();
       if (tid < kNEdge) {
         // lag k<127: x[k] at lead[128+k];  lag k>=9600: x[k] at trail[k-9472]
-        S.edge[tid] = (tid < 127) ? edge_power(S.lead, 128 + tid, n_id_2)
-                                  : edge_power(S.trail, 128 + (tid - 127), n_id_2);
+        const float2 *eb = (tid < 127) ? S.lead : S.trail;
+        const int ep = (tid < 127) ? 128 + tid : 128 + (tid - 127);
+        S.edge[tid] = (n_id_2 == 0) ? edge_power<0>(eb, ep, n_id_2) : edge_power<1>(eb, ep, n_id_2);
       }
       __syncthreads();
       float best = -3.402823466e+38f; int bi = 0;
-      // 38 lags per thread, loads issued 8 at a time so their latencies overlap
-#pragma unroll 1
-      for (int base = tid; base < kNLag; base += kTrackThreads * 8) {
-        float a[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int k = base + u * kTrackThreads;
-          a[u] = 0.f;
-          if (k < kNLag) {
-            if (k < 127) a[u] = S.edge[k];
-            else if (k >= kHalf) a[u] = S.edge[127 + (k - kHalf)];
-            else a[u] = __ldg(&pr[(unsigned)((R + k) & P.cap_mask)]);
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1) {
+#pragma unroll
+          for (int j = 0; j < kBatch; ++j) {
+            const int k = tid + (kBatch + j) * kTrackThreads;
+            a[j] = (k >= 127 && k < kHalf) ? __ldg(&pr[(unsigned)((R + k) & P.cap_mask)]) : 0.f;
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int k = base + u * kTrackThreads;
+        for (int j = 0; j < kBatch; ++j) {
+          const int k = tid + (h * kBatch + j) * kTrackThreads;
           if (k < kNLag) {
-            const float v = __fadd_rn(__fmul_rn(a[u], 0.2f), __fmul_rn(S.avg[k], 0.8f));   // EMA, alpha 0.2
+            float av = a[j];
+            if (k < 127) av = S.edge[k];
+            else if (k >= kHalf) av = S.edge[127 + (k - kHalf)];
+            const float v = __fadd_rn(__fmul_rn(av, 0.2f), __fmul_rn(S.avg[k], 0.8f));   // EMA, alpha 0.2
             S.avg[k] = v;
             if (v > best) { best = v; bi = k; }
           }
@@ -968,6 +993,20 @@ __global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P)
     }
     __syncthreads();
     if (S.rec_slot >= 0) n_rec++;
+    {
+      // the next window starts at S.st.next_win: pull its power lags and edge samples into L2 now
+      // (prefetch only: no registers, harmless if the chain stops or skips the search), so the
+      // round trip to HBM overlaps the rest of this window instead of opening the next one
+      const long long Rn = S.st.next_win;
+      if (Rn + kLookahead <= P.n_total && (!S.st.tracking || S.st.timer == 0)) {
+        for (int i = tid; i < (kHalf - 127 + 31) / 32 + 1; i += kTrackThreads)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(&pr[(unsigned)((Rn + 127 + 32 * i) & P.cap_mask)]));
+        if (tid < 18) {
+          const long long o = (tid < 9) ? Rn + 16 * tid : Rn + 9473 + 16 * (tid - 9);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(&yr[(unsigned)(o & P.cap_mask)]));
+        }
+      }
+    }
     if (S.zero_avg) {                                               // srslte_pss_reset
       for (int k = tid; k < kAvgLen; k += kTrackThreads) S.avg[k] = 0.f;
     }
@@ -977,12 +1016,14 @@ __global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P)
       if (P.hf_out != nullptr && S.rec_slot >= 0) hf = P.hf_out + (size_t)S.rec_slot * kHalf;
       if (S.do_track) {
         // ---- srslte_pss_cfo_compute on out[832..960) (lib/pss_impl.cc:199) --------------
+        for (int i = tid; i < 480; i += kTrackThreads) S.rot[i] = yr[(unsigned)((E + 480 + i) & P.cap_mask)];   // raw
+        __syncthreads();
         if (tid < 2) {
           float yr_ = 0.f, yi_ = 0.f;
           const int nb = tid * 64;
           for (int n = nb; n < nb + 64; ++n) {
             const float2 h = c_pss_taps[n_id_2][n];
-            const float2 r = yr[(unsigned)((E + 832 + n) & P.cap_mask)];
+            const float2 r = S.rot[352 + n];                                     // out[832 + n]
             yr_ = __fmaf_rn(h.x, r.x, yr_); yr_ = __fmaf_rn(-h.y, r.y, yr_);
             yi_ = __fmaf_rn(h.x, r.y, yi_); yi_ = __fmaf_rn(h.y, r.x, yi_);
           }
@@ -1020,10 +1061,7 @@ __global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P)
           }
           __syncthreads();
           if (b == 0) {
-            for (int i = tid; i < 480; i += kTrackThreads) {
-              const float2 x = yr[(unsigned)((E + 480 + i) & P.cap_mask)];
-              S.rot[i] = cmul_canon(P.cexp[S.ph_idx[480 + i]], x);
-            }
+            for (int i = tid; i < 480; i += kTrackThreads) S.rot[i] = cmul_canon(P.cexp[S.ph_idx[480 + i]], S.rot[i]);
           }
           if (hf) {
             for (int i = tid; i < 960; i += kTrackThreads) {
@@ -1098,6 +1136,7 @@ __global__ void __launch_bounds__(kTrackThreads) pss_track_kernel(TrackParams P)
   __syncthreads();
   if (tid == 0) { P.state[chain] = S.st; P.rec_count[chain] = n_rec; }
   for (int k = tid; k < kAvgLen; k += kTrackThreads) avg_g[k] = S.avg[k];
+  }
 }
 
 // ------------------------------------------------------------------------------------

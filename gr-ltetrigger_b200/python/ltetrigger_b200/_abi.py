@@ -11,7 +11,8 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.abspath(os.path.join(_PKG, "..", ".."))          # gr-ltetrigger_b200/
-LIB_PATH = os.path.join(ROOT, "lib", "libltetrigger_b200.so")
+# LTB200_LIB overrides the in-tree build (e.g. an instrumented build while profiling)
+LIB_PATH = os.environ.get("LTB200_LIB") or os.path.join(ROOT, "lib", "libltetrigger_b200.so")
 
 SUCCESS, ERROR, ERROR_INVALID_INPUTS = 0, -1, -2
 SLOT_LEN, HALF_FRAME, SYMBOL_SZ, CONV_LEN, LOOKAHEAD = 960, 9600, 128, 9726, 18365
