@@ -192,8 +192,17 @@ struct ltb_trigger {
   unsigned cap_mask = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};   // after front end, corr, track, sss
+  // up to two submitted-but-not-collected calls: the host enqueues call i+1 while the records
+  // of call i are still in flight, so the stream never idles between calls
+  struct Slot {
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
+    cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};   // after front end, corr, track, sss
+    ltb_window_rec *h_recs = nullptr;     // pinned
+    int *h_rec_count = nullptr;           // pinned
+    int w_cur = 0, launches = 0;
+  } slot[2];
+  int n_pending = 0, head = 0;            // slot[head] is the oldest pending call
+  int last = 0;                           // slot of the most recently collected call
   float last_kernel_ms[4] = {0.f, 0.f, 0.f, 0.f};
   void *d_in = nullptr;
   size_t d_in_stride = 0;
@@ -213,10 +222,7 @@ struct ltb_trigger {
   int tail_cur = 0;
   float2 *d_cexp = nullptr;
   long long n_total = 0;
-  ltb_window_rec *h_recs = nullptr;
-  int *h_rec_count = nullptr;
   std::vector<float> h_thr;
-  bool pending = false;
   int last_launches = 0;
   float last_ms = 0.f;
 };
@@ -235,7 +241,7 @@ int trigger_zero_state(ltb_trigger *t) {
   LTB_CUDA(cudaStreamSynchronize(t->stream));
   t->n_total = 0;
   t->tail_cur = 0;
-  t->pending = false;
+  t->n_pending = 0; t->head = 0;
   return LTB_SUCCESS;
 }
 
@@ -246,25 +252,30 @@ void trigger_free(ltb_trigger *t) {
   cudaFree(t->d_thr); cudaFree(t->d_recs); cudaFree(t->d_rec_count); cudaFree(t->d_sss_sym);
   cudaFree(t->d_sss_rec); cudaFree(t->d_sss_count); cudaFree(t->d_hf); cudaFree(t->d_tail[0]);
   cudaFree(t->d_tail[1]); cudaFree(t->d_cexp);
-  if (t->h_recs) cudaFreeHost(t->h_recs);
-  if (t->h_rec_count) cudaFreeHost(t->h_rec_count);
-  if (t->ev0) cudaEventDestroy(t->ev0);
-  if (t->ev1) cudaEventDestroy(t->ev1);
-  for (int i = 0; i < 4; ++i) if (t->ev_k[i]) cudaEventDestroy(t->ev_k[i]);
+  for (auto &sl : t->slot) {
+    if (sl.h_recs) cudaFreeHost(sl.h_recs);
+    if (sl.h_rec_count) cudaFreeHost(sl.h_rec_count);
+    if (sl.ev0) cudaEventDestroy(sl.ev0);
+    if (sl.ev1) cudaEventDestroy(sl.ev1);
+    if (sl.done) cudaEventDestroy(sl.done);
+    for (int i = 0; i < 4; ++i) if (sl.ev_k[i]) cudaEventDestroy(sl.ev_k[i]);
+  }
   if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
 
 int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long long n_samples) {
   const ltb_trigger_config &c = t->cfg;
-  if (t->pending) return fail(LTB_ERROR_INVALID_INPUTS, "previous submit not collected");
+  // emitted half-frames live in one device buffer, so keep_halfframes allows one call in flight
+  if (t->n_pending >= (c.keep_halfframes ? 1 : 2)) return fail(LTB_ERROR_INVALID_INPUTS, "too many submits not collected");
+  ltb_trigger::Slot &sl = t->slot[(t->head + t->n_pending) & 1];
   if (!d_iq || n_samples <= 0 || n_samples > c.max_chunk || (n_samples % (8 * c.decim)) != 0)
     return fail(LTB_ERROR_INVALID_INPUTS, "n_samples must be a positive multiple of 8*decim and <= max_chunk");
   const int m = (int)(n_samples / c.decim);
   const int S = c.n_streams;
   const long long n_base = t->n_total;
   int launches = 0;
-  LTB_CUDA(cudaEventRecord(t->ev0, t->stream));
+  LTB_CUDA(cudaEventRecord(sl.ev0, t->stream));
   int rc;
   if (c.input_format == LTB_FMT_FC32)
     rc = launch_frontend<LTB_FMT_FC32>(c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
@@ -274,7 +285,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
                                        t->d_y, n_base, t->cap_mask, t->cap, t->stream, &launches);
   if (rc) return rc;
   if (c.decim > 1) t->tail_cur ^= 1;
-  LTB_CUDA(cudaEventRecord(t->ev_k[0], t->stream));
+  LTB_CUDA(cudaEventRecord(sl.ev_k[0], t->stream));
   {
     const int tps = (m + kCorrTile - 1) / kCorrTile;
     const long long total = (long long)tps * S;
@@ -284,7 +295,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
     pss_corr_kernel<<<(unsigned)ctas, kCorrThreads, 0, t->stream>>>(t->d_y, t->d_p, n_base, m, t->cap_mask, t->cap, tps, (int)total);
   }
   launches++;
-  LTB_CUDA(cudaEventRecord(t->ev_k[1], t->stream));
+  LTB_CUDA(cudaEventRecord(sl.ev_k[1], t->stream));
   t->n_total += m;
   t->w_cur = m / (kHalf - kSlot) + 4;
   if (t->w_cur > t->w_cap) t->w_cur = t->w_cap;
@@ -303,18 +314,20 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
     pss_track_kernel<<<ctas, kTrackThreads, sizeof(TrackShared), t->stream>>>(P);
   }
   launches++;
-  LTB_CUDA(cudaEventRecord(t->ev_k[2], t->stream));
+  LTB_CUDA(cudaEventRecord(sl.ev_k[2], t->stream));
   int sss_grid = (t->n_chains * t->w_cur + kSssWarps - 1) / kSssWarps;
   if (sss_grid > 148 * 8) sss_grid = 148 * 8;
   sss_kernel<<<sss_grid, kSssWarps * 32, 0, t->stream>>>(t->d_sss_sym, t->d_sss_rec, t->d_sss_count, t->sss_cap, t->d_recs);
   launches++;
-  LTB_CUDA(cudaEventRecord(t->ev1, t->stream));
-  LTB_CUDA(cudaMemcpyAsync(t->h_rec_count, t->d_rec_count, sizeof(int) * t->n_chains, cudaMemcpyDeviceToHost, t->stream));
-  LTB_CUDA(cudaMemcpyAsync(t->h_recs, t->d_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cur,
+  LTB_CUDA(cudaEventRecord(sl.ev1, t->stream));
+  LTB_CUDA(cudaMemcpyAsync(sl.h_rec_count, t->d_rec_count, sizeof(int) * t->n_chains, cudaMemcpyDeviceToHost, t->stream));
+  LTB_CUDA(cudaMemcpyAsync(sl.h_recs, t->d_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cur,
                            cudaMemcpyDeviceToHost, t->stream));
+  LTB_CUDA(cudaEventRecord(sl.done, t->stream));
   LTB_CUDA(cudaGetLastError());
-  t->last_launches = launches;
-  t->pending = true;
+  sl.launches = launches;
+  sl.w_cur = t->w_cur;
+  t->n_pending++;
   return LTB_SUCCESS;
 }
 
@@ -369,9 +382,12 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   } while (0)
   if (c.cuda_stream) t->stream = (cudaStream_t)c.cuda_stream;
   else { LTB_CUDA_T(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking)); t->own_stream = true; }
-  LTB_CUDA_T(cudaEventCreate(&t->ev0));
-  LTB_CUDA_T(cudaEventCreate(&t->ev1));
-  for (int i = 0; i < 4; ++i) LTB_CUDA_T(cudaEventCreate(&t->ev_k[i]));
+  for (auto &sl : t->slot) {
+    LTB_CUDA_T(cudaEventCreate(&sl.ev0));
+    LTB_CUDA_T(cudaEventCreate(&sl.ev1));
+    LTB_CUDA_T(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) LTB_CUDA_T(cudaEventCreate(&sl.ev_k[i]));
+  }
   t->d_in_stride = (size_t)c.max_chunk * (c.input_format == LTB_FMT_FC32 ? 8 : 4);
   LTB_CUDA_T(cudaMalloc(&t->d_y, sizeof(float2) * (size_t)S * t->cap));
   LTB_CUDA_T(cudaMalloc(&t->d_p, sizeof(float) * (size_t)S * 3 * t->cap));
@@ -386,8 +402,10 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   LTB_CUDA_T(cudaMalloc(&t->d_tail[0], sizeof(float2) * (size_t)S * kTailCap));
   LTB_CUDA_T(cudaMalloc(&t->d_tail[1], sizeof(float2) * (size_t)S * kTailCap));
   if (c.keep_halfframes) LTB_CUDA_T(cudaMalloc(&t->d_hf, sizeof(float2) * kHalf * (size_t)t->n_chains * t->w_cap));
-  LTB_CUDA_T(cudaMallocHost(&t->h_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cap));
-  LTB_CUDA_T(cudaMallocHost(&t->h_rec_count, sizeof(int) * t->n_chains));
+  for (auto &sl : t->slot) {
+    LTB_CUDA_T(cudaMallocHost(&sl.h_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cap));
+    LTB_CUDA_T(cudaMallocHost(&sl.h_rec_count, sizeof(int) * t->n_chains));
+  }
 #undef LTB_CUDA_T
   rc = make_cexp_device(&t->d_cexp);
   if (!rc) rc = trigger_zero_state(t);
@@ -431,19 +449,23 @@ int ltb_trigger_submit_device(ltb_trigger *t, const void *d_iq, int64_t stride, 
 
 int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int *n_recs) {
   if (!t || !n_recs || (!recs && max_recs > 0)) return LTB_ERROR_INVALID_INPUTS;
-  if (!t->pending) return fail(LTB_ERROR_INVALID_INPUTS, "nothing submitted");
+  if (t->n_pending == 0) return fail(LTB_ERROR_INVALID_INPUTS, "nothing submitted");
   LTB_CUDA(cudaSetDevice(t->cfg.device));
-  LTB_CUDA(cudaStreamSynchronize(t->stream));
-  t->pending = false;
-  cudaEventElapsedTime(&t->last_ms, t->ev0, t->ev1);
-  cudaEventElapsedTime(&t->last_kernel_ms[0], t->ev0, t->ev_k[0]);
-  cudaEventElapsedTime(&t->last_kernel_ms[1], t->ev_k[0], t->ev_k[1]);
-  cudaEventElapsedTime(&t->last_kernel_ms[2], t->ev_k[1], t->ev_k[2]);
-  cudaEventElapsedTime(&t->last_kernel_ms[3], t->ev_k[2], t->ev1);
+  ltb_trigger::Slot &sl = t->slot[t->head];
+  LTB_CUDA(cudaEventSynchronize(sl.done));
+  t->last = t->head;
+  t->head ^= 1;
+  t->n_pending--;
+  t->last_launches = sl.launches;
+  cudaEventElapsedTime(&t->last_ms, sl.ev0, sl.ev1);
+  cudaEventElapsedTime(&t->last_kernel_ms[0], sl.ev0, sl.ev_k[0]);
+  cudaEventElapsedTime(&t->last_kernel_ms[1], sl.ev_k[0], sl.ev_k[1]);
+  cudaEventElapsedTime(&t->last_kernel_ms[2], sl.ev_k[1], sl.ev_k[2]);
+  cudaEventElapsedTime(&t->last_kernel_ms[3], sl.ev_k[2], sl.ev1);
   int total = 0, written = 0;
   for (int ch = 0; ch < t->n_chains; ++ch) {
-    const int n = t->h_rec_count[ch];
-    const ltb_window_rec *src = t->h_recs + (size_t)ch * t->w_cur;
+    const int n = sl.h_rec_count[ch];
+    const ltb_window_rec *src = sl.h_recs + (size_t)ch * sl.w_cur;
     for (int i = 0; i < n; ++i) {
       if (written < max_recs) recs[written++] = src[i];
       total++;
@@ -456,6 +478,7 @@ int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int 
 
 int ltb_trigger_process_device(ltb_trigger *t, const void *d_iq, int64_t stride, int64_t n_samples,
                                ltb_window_rec *recs, int max_recs, int *n_recs) {
+  if (t && t->n_pending) return fail(LTB_ERROR_INVALID_INPUTS, "collect the submitted calls before a synchronous process call");
   int rc = ltb_trigger_submit_device(t, d_iq, stride, n_samples);
   if (rc) return rc;
   return ltb_trigger_collect(t, recs, max_recs, n_recs);
@@ -466,6 +489,7 @@ int ltb_trigger_process_host(ltb_trigger *t, const void *iq, int64_t stride, int
   if (!t || !iq) return LTB_ERROR_INVALID_INPUTS;
   LTB_CUDA(cudaSetDevice(t->cfg.device));
   if (n_samples <= 0 || n_samples > t->cfg.max_chunk) return fail(LTB_ERROR_INVALID_INPUTS, "n_samples out of range");
+  if (t->n_pending) return fail(LTB_ERROR_INVALID_INPUTS, "collect the submitted calls before a synchronous process call");
   if (!t->d_in) LTB_CUDA(cudaMalloc(&t->d_in, t->d_in_stride * (size_t)t->cfg.n_streams));
   const size_t row = (size_t)n_samples * (t->cfg.input_format == LTB_FMT_FC32 ? 8 : 4);
   LTB_CUDA(cudaMemcpy2DAsync(t->d_in, t->d_in_stride, iq, (size_t)stride, row, (size_t)t->cfg.n_streams,
@@ -505,12 +529,13 @@ int ltb_trigger_fetch_halfframes(ltb_trigger *t, ltb_cf *out, int max_hf, int *n
   LTB_CUDA(cudaStreamSynchronize(t->stream));
   int total = 0;
   for (int ch = 0; ch < t->n_chains; ++ch) {
-    const int n = t->h_rec_count[ch];
+    const ltb_trigger::Slot &sl = t->slot[t->last];
+    const int n = sl.h_rec_count[ch];
     for (int i = 0; i < n; ++i) {
-      const ltb_window_rec &r = t->h_recs[(size_t)ch * t->w_cur + i];
+      const ltb_window_rec &r = sl.h_recs[(size_t)ch * sl.w_cur + i];
       if (!(r.flags & LTB_F_EMIT)) continue;
       if (total < max_hf)
-        LTB_CUDA(cudaMemcpyAsync(out + (size_t)total * kHalf, t->d_hf + ((size_t)ch * t->w_cur + i) * kHalf,
+        LTB_CUDA(cudaMemcpyAsync(out + (size_t)total * kHalf, t->d_hf + ((size_t)ch * sl.w_cur + i) * kHalf,
                                  sizeof(float2) * kHalf, cudaMemcpyDeviceToHost, t->stream));
       total++;
     }

@@ -141,7 +141,10 @@ LTB_API int ltb_trigger_process_host(ltb_trigger *t, const void *iq, int64_t str
 LTB_API int ltb_trigger_process_device(ltb_trigger *t, const void *d_iq, int64_t stream_stride_bytes,
                                        int64_t n_samples, ltb_window_rec *recs, int max_recs, int *n_recs);
 /* Asynchronous halves of process_device: submit enqueues all kernels on the stream and
- * returns; collect waits for them and copies the records out. */
+ * returns; collect waits for the oldest submitted call and copies its records out.  Up to two
+ * calls may be submitted before the first is collected (one with cfg.keep_halfframes), which
+ * keeps the stream busy across calls; the input buffer of a call must stay valid until it is
+ * collected. */
 LTB_API int ltb_trigger_submit_device(ltb_trigger *t, const void *d_iq, int64_t stream_stride_bytes,
                                       int64_t n_samples);
 LTB_API int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int *n_recs);

@@ -194,3 +194,28 @@ def test_large_cfo_exercises_phasor_scan(lt, oracle):
                     k += 1
                 pos += ncons
     assert k == n_emit
+
+
+def test_two_calls_in_flight_match_synchronous_calls(lt, oracle):
+    """submit/submit/collect/collect (two calls in flight) gives the same records as the
+    synchronous path; a third submit and a process call while calls are pending are refused."""
+    import torch
+    x, decim, _ = load_fixture("25prb", 0.3)
+    n = len(x) // 3 // (8 * decim) * (8 * decim)
+    want = oracle.trigger_run(x[None, :3 * n], decim=decim)
+    d = torch.from_numpy(x[:3 * n].copy()).cuda()
+    trig = lt.Trigger(n_streams=1, decim=decim, max_chunk=n)
+    trig.submit_device_ptr(d.data_ptr(), 0, n)
+    trig.submit_device_ptr(d.data_ptr() + 8 * n, 0, n)
+    with pytest.raises(lt.LtbError):
+        trig.submit_device_ptr(d.data_ptr() + 16 * n, 0, n)
+    with pytest.raises(lt.LtbError):
+        trig.process_device_ptr(d.data_ptr() + 16 * n, 0, n)
+    got = [trig.collect().copy()]
+    trig.submit_device_ptr(d.data_ptr() + 16 * n, 0, n)
+    got += [trig.collect().copy(), trig.collect().copy()]
+    with pytest.raises(lt.LtbError):
+        trig.collect()
+    recs = np.concatenate(got)
+    recs = recs[np.lexsort((recs["win_index"], recs["n_id_2"], recs["stream"]))]
+    assert_recs_equal(recs, want)
