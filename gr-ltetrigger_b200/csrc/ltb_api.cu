@@ -199,6 +199,8 @@ struct ltb_trigger {
     cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};   // after front end, corr, track, sss
     ltb_window_rec *h_recs = nullptr;     // pinned
     int *h_rec_count = nullptr;           // pinned
+    ltb_window_rec *d_recs = nullptr;     // this call's records on the device
+    int *d_rec_count = nullptr;
     int w_cur = 0, launches = 0;
   } slot[2];
   int n_pending = 0, head = 0;            // slot[head] is the oldest pending call
@@ -211,8 +213,7 @@ struct ltb_trigger {
   ChainState *d_state = nullptr;
   float *d_avg = nullptr;
   float *d_thr = nullptr;
-  ltb_window_rec *d_recs = nullptr;
-  int *d_rec_count = nullptr;
+  cudaStream_t copy_stream = nullptr;     // record read-back, overlaps the next call's kernels
   float2 *d_sss_sym = nullptr;
   int *d_sss_rec = nullptr;
   int *d_sss_count = nullptr;     // [0] SSS candidate count, [1] track-kernel chain queue head
@@ -249,10 +250,11 @@ void trigger_free(ltb_trigger *t) {
   if (!t) return;
   cudaSetDevice(t->cfg.device);
   cudaFree(t->d_in); cudaFree(t->d_y); cudaFree(t->d_p); cudaFree(t->d_state); cudaFree(t->d_avg);
-  cudaFree(t->d_thr); cudaFree(t->d_recs); cudaFree(t->d_rec_count); cudaFree(t->d_sss_sym);
+  cudaFree(t->d_thr); cudaFree(t->d_sss_sym);
   cudaFree(t->d_sss_rec); cudaFree(t->d_sss_count); cudaFree(t->d_hf); cudaFree(t->d_tail[0]);
   cudaFree(t->d_tail[1]); cudaFree(t->d_cexp);
   for (auto &sl : t->slot) {
+    cudaFree(sl.d_recs); cudaFree(sl.d_rec_count);
     if (sl.h_recs) cudaFreeHost(sl.h_recs);
     if (sl.h_rec_count) cudaFreeHost(sl.h_rec_count);
     if (sl.ev0) cudaEventDestroy(sl.ev0);
@@ -260,6 +262,7 @@ void trigger_free(ltb_trigger *t) {
     if (sl.done) cudaEventDestroy(sl.done);
     for (int i = 0; i < 4; ++i) if (sl.ev_k[i]) cudaEventDestroy(sl.ev_k[i]);
   }
+  if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
@@ -302,7 +305,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   LTB_CUDA(cudaMemsetAsync(t->d_sss_count, 0, 2 * sizeof(int), t->stream));
   TrackParams P;
   P.y_ring = t->d_y; P.p_ring = t->d_p; P.state = t->d_state; P.avg = t->d_avg; P.thr = t->d_thr;
-  P.recs = t->d_recs; P.rec_count = t->d_rec_count; P.sss_sym = t->d_sss_sym; P.sss_rec = t->d_sss_rec;
+  P.recs = sl.d_recs; P.rec_count = sl.d_rec_count; P.sss_sym = t->d_sss_sym; P.sss_rec = t->d_sss_rec;
   P.sss_count = t->d_sss_count; P.sss_cap = t->sss_cap; P.hf_out = t->d_hf; P.cexp = t->d_cexp;
   P.n_total = t->n_total; P.cap_mask = t->cap_mask; P.cap = t->cap; P.w_max = t->w_cur;
   P.track_after = c.track_after; P.track_every = c.track_every; P.record_all = c.record_all;
@@ -317,13 +320,15 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   LTB_CUDA(cudaEventRecord(sl.ev_k[2], t->stream));
   int sss_grid = (t->n_chains * t->w_cur + kSssWarps - 1) / kSssWarps;
   if (sss_grid > 148 * 8) sss_grid = 148 * 8;
-  sss_kernel<<<sss_grid, kSssWarps * 32, 0, t->stream>>>(t->d_sss_sym, t->d_sss_rec, t->d_sss_count, t->sss_cap, t->d_recs);
+  sss_kernel<<<sss_grid, kSssWarps * 32, 0, t->stream>>>(t->d_sss_sym, t->d_sss_rec, t->d_sss_count, t->sss_cap, sl.d_recs);
   launches++;
   LTB_CUDA(cudaEventRecord(sl.ev1, t->stream));
-  LTB_CUDA(cudaMemcpyAsync(sl.h_rec_count, t->d_rec_count, sizeof(int) * t->n_chains, cudaMemcpyDeviceToHost, t->stream));
-  LTB_CUDA(cudaMemcpyAsync(sl.h_recs, t->d_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cur,
-                           cudaMemcpyDeviceToHost, t->stream));
-  LTB_CUDA(cudaEventRecord(sl.done, t->stream));
+  // read the records back on the copy stream: the next call's kernels need not wait for it
+  LTB_CUDA(cudaStreamWaitEvent(t->copy_stream, sl.ev1, 0));
+  LTB_CUDA(cudaMemcpyAsync(sl.h_rec_count, sl.d_rec_count, sizeof(int) * t->n_chains, cudaMemcpyDeviceToHost, t->copy_stream));
+  LTB_CUDA(cudaMemcpyAsync(sl.h_recs, sl.d_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cur,
+                           cudaMemcpyDeviceToHost, t->copy_stream));
+  LTB_CUDA(cudaEventRecord(sl.done, t->copy_stream));
   LTB_CUDA(cudaGetLastError());
   sl.launches = launches;
   sl.w_cur = t->w_cur;
@@ -394,8 +399,11 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   LTB_CUDA_T(cudaMalloc(&t->d_state, sizeof(ChainState) * t->n_chains));
   LTB_CUDA_T(cudaMalloc(&t->d_avg, sizeof(float) * (size_t)t->n_chains * kAvgLen));
   LTB_CUDA_T(cudaMalloc(&t->d_thr, sizeof(float) * t->n_chains));
-  LTB_CUDA_T(cudaMalloc(&t->d_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cap));
-  LTB_CUDA_T(cudaMalloc(&t->d_rec_count, sizeof(int) * t->n_chains));
+  LTB_CUDA_T(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+  for (auto &sl : t->slot) {
+    LTB_CUDA_T(cudaMalloc(&sl.d_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cap));
+    LTB_CUDA_T(cudaMalloc(&sl.d_rec_count, sizeof(int) * t->n_chains));
+  }
   LTB_CUDA_T(cudaMalloc(&t->d_sss_sym, sizeof(float2) * 128 * (size_t)t->sss_cap));
   LTB_CUDA_T(cudaMalloc(&t->d_sss_rec, sizeof(int) * t->sss_cap));
   LTB_CUDA_T(cudaMalloc(&t->d_sss_count, 2 * sizeof(int)));
@@ -418,6 +426,7 @@ int ltb_trigger_destroy(ltb_trigger *t) {
   if (!t) return LTB_ERROR_INVALID_INPUTS;
   cudaSetDevice(t->cfg.device);
   cudaStreamSynchronize(t->stream);
+  if (t->copy_stream) cudaStreamSynchronize(t->copy_stream);
   trigger_free(t);
   return LTB_SUCCESS;
 }
@@ -426,6 +435,7 @@ int ltb_trigger_reset(ltb_trigger *t) {
   if (!t) return LTB_ERROR_INVALID_INPUTS;
   LTB_CUDA(cudaSetDevice(t->cfg.device));
   LTB_CUDA(cudaStreamSynchronize(t->stream));
+  LTB_CUDA(cudaStreamSynchronize(t->copy_stream));
   return trigger_zero_state(t);
 }
 

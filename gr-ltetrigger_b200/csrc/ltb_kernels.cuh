@@ -1145,7 +1145,7 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
 // ------------------------------------------------------------------------------------
 constexpr int kSssWarps = 4;
 
-__device__ __forceinline__ void fft128_warp(float2 *a, int lane) {
+__device__ __forceinline__ void fft128_warp(float2 *a, int lane, const float2 *tw) {
   // radix-2 DIT on bit-reversed input in shared memory a[128]; 64 butterflies per stage,
   // two per lane.  Same butterfly as the oracle: t = w*b (canonical), a' = a+t, b' = a-t.
 #pragma unroll
@@ -1156,7 +1156,7 @@ __device__ __forceinline__ void fft128_warp(float2 *a, int lane) {
       const int bf = lane + rep * 32;            // butterfly id 0..63
       const int j = bf & (half - 1);
       const int base = (bf / half) * 2 * half;
-      const float2 w = c_fft128_tw[j * step];
+      const float2 w = tw[j * step];
       const float2 b = a[base + j + half];
       const float2 u = a[base + j];
       const float2 tw = cmul_canon(w, b);
@@ -1167,13 +1167,15 @@ __device__ __forceinline__ void fft128_warp(float2 *a, int lane) {
   }
 }
 
-__device__ __forceinline__ int sss_corr_argmax(const float2 *y, int lane, float *val_out) {
-  // lane m < 31: |sum_i y[i] * s_tilde[(i+m)%31]|^2, sequential i; first-index argmax
+__device__ __forceinline__ int sss_corr_argmax(const float2 *y, int lane, float *val_out, const float *s2) {
+  // lane m < 31: |sum_i y[i] * s_tilde[(i+m)%31]|^2, sequential i; first-index argmax.
+  // s2 = s_tilde repeated twice in shared memory: no modulo, no lane-indexed constant loads
   float v = -3.402823466e+38f;
   if (lane < 31) {
     float ar = 0.f, ai = 0.f;
+#pragma unroll
     for (int i = 0; i < 31; ++i) {
-      const float sv = c_sss_s[(i + lane) % 31];
+      const float sv = s2[i + lane];
       ar = __fmaf_rn(y[i].x, sv, ar);
       ai = __fmaf_rn(y[i].y, sv, ai);
     }
@@ -1197,14 +1199,20 @@ __global__ void __launch_bounds__(kSssWarps * 32) sss_kernel(const float2 *__res
                                                               ltb_window_rec *__restrict__ recs) {
   __shared__ float2 sa[kSssWarps][128];
   __shared__ float2 sy[kSssWarps][2][32];
+  __shared__ float2 s_tw[64];
+  __shared__ float s_s2[62];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // lane-indexed reads of __constant__ tables replay once per distinct address: stage them
+  if (threadIdx.x < 64) s_tw[threadIdx.x] = c_fft128_tw[threadIdx.x];
+  if (threadIdx.x < 62) s_s2[threadIdx.x] = c_sss_s[threadIdx.x % 31];
+  __syncthreads();
   int count = *sss_count;
   if (count > sss_cap) count = sss_cap;
   for (int slot = blockIdx.x * kSssWarps + warp; slot < count; slot += gridDim.x * kSssWarps) {
     float2 *a = sa[warp];
     for (int i = lane; i < 128; i += 32) a[__brev((unsigned)i) >> 25] = sss_sym[(size_t)slot * 128 + i];
     __syncwarp();
-    fft128_warp(a, lane);
+    fft128_warp(a, lane, s_tw);
     ltb_window_rec &r = recs[sss_rec[slot]];
     const int n_id_2 = r.n_id_2;
     if (lane < 31) {
@@ -1217,13 +1225,13 @@ __global__ void __launch_bounds__(kSssWarps * 32) sss_kernel(const float2 *__res
     }
     __syncwarp();
     float m0v, m1v;
-    const int m0 = sss_corr_argmax(sy[warp][0], lane, &m0v);
+    const int m0 = sss_corr_argmax(sy[warp][0], lane, &m0v, s_s2);
     if (lane < 31) {
       const float z = c_sss_z[(lane + (m0 % 8)) % 31];
       sy[warp][1][lane] = make_float2(__fmul_rn(sy[warp][1][lane].x, z), __fmul_rn(sy[warp][1][lane].y, z));
     }
     __syncwarp();
-    const int m1 = sss_corr_argmax(sy[warp][1], lane, &m1v);
+    const int m1 = sss_corr_argmax(sy[warp][1], lane, &m1v, s_s2);
     if (lane == 0) {
       int nid = -1;
       const unsigned um0 = (unsigned)m0, um1 = (unsigned)m1;
