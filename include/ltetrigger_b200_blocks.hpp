@@ -1,0 +1,233 @@
+// ltetrigger_b200_blocks.hpp -- C++ host side above the C ABI (include/ltetrigger_b200.h).
+//
+// Mirrors the reference's compiled block interface for the PSS+SSS path without GNU Radio
+// types (GNU Radio is absent where this is built; the thin gr::block subclass a maintainer
+// would wrap around these classes is shown in INTEGRATION.md):
+//
+//   gr::ltetrigger::pss   include/ltetrigger/pss.h:36-88   lib/pss_impl.{h,cc}
+//   gr::ltetrigger::sss   include/ltetrigger/sss.h:36-52   lib/sss_impl.{h,cc}
+//
+// Same factory names and arguments (`make`), accessors, history / output_multiple, work
+// signatures (raw item pointers and counts), consume/return semantics, stream-tag keys and
+// values, and the same error behaviour: construction failures throw std::runtime_error with the
+// reference's messages (lib/pss_impl.cc:72-79, lib/sss_impl.cc:63-70).  All arithmetic runs in
+// libltetrigger_b200.so on the GPU; there is no CPU path.
+#ifndef LTETRIGGER_B200_BLOCKS_HPP
+#define LTETRIGGER_B200_BLOCKS_HPP
+
+#include <complex>
+#include <cstdint>
+#include <deque>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "ltetrigger_b200.h"
+
+namespace ltetrigger_b200 {
+
+typedef std::complex<float> gr_complex;
+
+static const int slot_length = LTB_SLOT_LEN;             // lib/pss_impl.h:52-55
+static const int half_frame_length = LTB_HALF_FRAME;
+static const int symbol_sz = LTB_SYMBOL_SZ;
+
+// stream tags: pmt values reduced to what this path uses (PMT_NIL, PMT_T / PMT_F, pmt::from_long)
+struct tag_t {
+  enum kind_t { NIL, BOOL, LONG };
+  uint64_t offset;
+  std::string key;
+  kind_t kind;
+  long value;
+};
+static const char *const tracking_lost_tag_key = "tracking_lost";   // lib/pss_impl.cc:39-40
+static const char *const cell_id_tag_key = "cell_id";               // lib/sss_impl.cc:38
+static const char *const cp_type_tag_key = "cp_type";               // lib/sss_impl.cc:40
+
+// the slice of gr::block the two blocks use
+class block {
+ public:
+  explicit block(const std::string &name) : d_name(name) {}
+  virtual ~block() {}
+  const std::string &name() const { return d_name; }
+  unsigned history() const { return d_history; }
+  int output_multiple() const { return d_output_multiple; }
+  uint64_t nitems_read(unsigned) const { return d_nitems_read; }
+  uint64_t nitems_written(unsigned) const { return d_nitems_written; }
+  // scheduler side: tags arriving on the input, tags produced, consumed count of the last call
+  std::vector<tag_t> &input_tags() { return d_in_tags; }
+  std::vector<tag_t> &output_tags() { return d_out_tags; }
+  int consumed() const { return d_consumed; }
+  void advance(int nconsumed, int nproduced) { d_nitems_read += nconsumed; d_nitems_written += nproduced; }
+
+ protected:
+  void set_history(unsigned h) { d_history = h; }
+  void set_output_multiple(int m) { d_output_multiple = m; }
+  void consume_each(int n) { d_consumed = n; }
+  void add_item_tag(unsigned, uint64_t offset, const std::string &key, tag_t::kind_t kind, long value) {
+    d_out_tags.push_back(tag_t{offset, key, kind, value});
+  }
+  void get_tags_in_window(std::vector<tag_t> &v, unsigned, uint64_t rel_start, uint64_t rel_end, const std::string &key) {
+    for (const tag_t &t : d_in_tags)
+      if (t.offset >= d_nitems_read + rel_start && t.offset < d_nitems_read + rel_end && t.key == key) v.push_back(t);
+  }
+
+ private:
+  std::string d_name;
+  unsigned d_history = 1;
+  int d_output_multiple = 1;
+  uint64_t d_nitems_read = 0, d_nitems_written = 0;
+  int d_consumed = 0;
+  std::vector<tag_t> d_in_tags, d_out_tags;
+};
+
+// ---- ltetrigger::pss ---------------------------------------------------------------------
+class pss : public block {
+ public:
+  typedef std::shared_ptr<pss> sptr;
+  // include/ltetrigger/pss.h:66-69
+  static sptr make(int N_id_2, float psr_threshold, int track_after = 16, int track_every = 8, int device = 0) {
+    return sptr(new pss(N_id_2, psr_threshold, track_after, track_every, device));
+  }
+  ~pss() { if (d_ltb) ltb_trigger_destroy(d_ltb); }
+
+  // accessors, lib/pss_impl.h:95-100
+  float max_psr() const { return stats().max_psr; }
+  float mean_psr() const { return stats().mean_psr; }
+  float mean_cfo() const { return stats().mean_cfo; }
+  void set_psr_threshold(float threshold) { ltb_trigger_set_psr_threshold(d_ltb, 0, d_N_id_2, threshold, 0); }
+  float psr_threshold() const { return stats().psr_threshold; }
+  float tracking_score() const { return stats().tracking_score; }
+
+  // items the scheduler must provide before calling general_work: the reference's history plus the
+  // largest consume of one call (its assert at lib/pss_impl.cc:191 states the same requirement)
+  void forecast(int, std::vector<int> &ninput_items_required) {
+    ninput_items_required.assign(1, (int)history() - 1 + LTB_LOOKAHEAD);
+  }
+
+  // lib/pss_impl.cc:154-223.  input_items[0] holds history()-1 old items followed by the new ones;
+  // returns 0 or 9600 produced items, consume count via consumed().
+  int general_work(int, std::vector<int> &ninput_items, std::vector<const void *> &input_items,
+                   std::vector<void *> &output_items) {
+    const gr_complex *in = static_cast<const gr_complex *>(input_items[0]) + (history() - 1);
+    gr_complex *out = static_cast<gr_complex *>(output_items[0]);
+    const uint64_t avail_end = nitems_read(0) + (uint64_t)(ninput_items[0] - (int)(history() - 1));
+    while (avail_end > d_pushed + 7) {                   // hand new items to the engine, multiples of 8
+      int64_t n = (int64_t)((avail_end - d_pushed) / 8 * 8);
+      if (n > d_max_chunk) n = d_max_chunk;
+      push(in + (d_pushed - nitems_read(0)), n);
+    }
+    if (d_ready.empty()) { consume_each(0); return 0; }
+    ltb_window_rec rec = d_ready.front().first;
+    std::vector<gr_complex> hf = std::move(d_ready.front().second);
+    d_ready.pop_front();
+    if ((uint64_t)rec.win_start != nitems_read(0)) throw std::runtime_error("pss: scheduler and engine out of step");
+    d_last = rec;
+    if (rec.flags & LTB_F_EMIT) {
+      std::copy(hf.begin(), hf.end(), out);                                         // :193 (+ :204 when tracking)
+      if (rec.flags & LTB_F_TAG_LOST)
+        add_item_tag(0, nitems_written(0), tracking_lost_tag_key, tag_t::NIL, 0);   // :212
+      consume_each((int)(rec.emit_start - rec.win_start) + half_frame_length);      // :195
+      return half_frame_length;
+    }
+    consume_each(half_frame_length);                                                // :217
+    return 0;
+  }
+  const ltb_window_rec &last_record() const { return d_last; }
+
+ private:
+  pss(int N_id_2, float psr_threshold, int track_after, int track_every, int device) : block("pss"), d_N_id_2(N_id_2) {
+    if (N_id_2 < 0 || N_id_2 > 2) throw std::runtime_error("Error initializing PSS N_id_2");
+    ltb_trigger_config cfg = ltb_trigger_config();
+    cfg.struct_size = sizeof cfg;
+    cfg.device = device;
+    cfg.n_streams = 1;
+    cfg.input_format = LTB_FMT_FC32;
+    cfg.decim = 1;
+    cfg.root_mask = 1 << N_id_2;
+    cfg.max_chunk = d_max_chunk;
+    cfg.psr_threshold = psr_threshold;
+    cfg.track_after = track_after;
+    cfg.track_every = track_every;
+    cfg.record_all = 1;
+    cfg.keep_halfframes = 1;
+    if (ltb_trigger_create(&cfg, &d_ltb)) throw std::runtime_error(std::string("Error initializing PSS: ") + ltb_last_error());
+    ltb_trigger_set_psr_threshold(d_ltb, 0, N_id_2, psr_threshold, 0);   // the block itself does not clamp
+    set_history(half_frame_length);           // lib/pss_impl.cc:81
+    set_output_multiple(half_frame_length);   // :82
+  }
+  ltb_pss_stats stats() const {
+    ltb_pss_stats s = ltb_pss_stats();
+    ltb_trigger_get_stats(d_ltb, 0, d_N_id_2, &s);
+    return s;
+  }
+  void push(const gr_complex *x, int64_t n) {
+    std::vector<ltb_window_rec> recs((size_t)(n / 8640 + 8));
+    int n_recs = 0;
+    if (ltb_trigger_process_host(d_ltb, x, 0, n, recs.data(), (int)recs.size(), &n_recs))
+      throw std::runtime_error(std::string("pss: ") + ltb_last_error());
+    std::vector<ltb_cf> hf((size_t)(n_recs > 0 ? n_recs : 1) * half_frame_length);
+    int n_hf = 0;
+    if (n_recs > 0 && ltb_trigger_fetch_halfframes(d_ltb, hf.data(), n_recs, &n_hf))
+      throw std::runtime_error(std::string("pss: ") + ltb_last_error());
+    for (int i = 0, k = 0; i < n_recs; ++i) {
+      std::vector<gr_complex> v;
+      if (recs[i].flags & LTB_F_EMIT) {
+        const gr_complex *p = reinterpret_cast<const gr_complex *>(&hf[(size_t)k++ * half_frame_length]);
+        v.assign(p, p + half_frame_length);
+      }
+      d_ready.push_back(std::make_pair(recs[i], std::move(v)));
+    }
+    d_pushed += (uint64_t)n;
+  }
+
+  int d_N_id_2;
+  ltb_trigger *d_ltb = nullptr;
+  int64_t d_max_chunk = 1 << 18;
+  uint64_t d_pushed = 0;                                   // absolute count of items handed to the engine
+  std::deque<std::pair<ltb_window_rec, std::vector<gr_complex> > > d_ready;   // calls already evaluated
+  ltb_window_rec d_last = ltb_window_rec();
+};
+
+// ---- ltetrigger::sss ---------------------------------------------------------------------
+class sss : public block {
+ public:
+  typedef std::shared_ptr<sss> sptr;
+  static sptr make(int N_id_2, int device = 0) { return sptr(new sss(N_id_2, device)); }   // include/ltetrigger/sss.h:51
+  ~sss() { if (d_sss) ltb_sss_destroy(d_sss); }
+
+  // lib/sss_impl.cc:83-156: one aligned half-frame per call, returns 9600
+  int work(int, std::vector<const void *> &input_items, std::vector<void *> &output_items) {
+    const gr_complex *in = static_cast<const gr_complex *>(input_items[0]);
+    gr_complex *out = static_cast<gr_complex *>(output_items[0]);
+    std::vector<tag_t> tags;
+    get_tags_in_window(tags, 0, 0, 1, tracking_lost_tag_key);                       // :91
+    int32_t lost = !tags.empty();
+    ltb_window_rec rec = ltb_window_rec();
+    rec.m0 = rec.m1 = rec.n_id_1 = rec.cell_id = -1;
+    if (ltb_sss_work(d_sss, reinterpret_cast<const ltb_cf *>(in), &lost, 1, &rec))
+      throw std::runtime_error(std::string("sss: ") + ltb_last_error());
+    d_last = rec;
+    if (!lost && !(rec.flags & LTB_F_CELL)) return half_frame_length;               // :119-120, out not written
+    if (!lost) {
+      add_item_tag(0, nitems_written(0), cell_id_tag_key, tag_t::LONG, rec.cell_id);                        // :141-145
+      add_item_tag(0, nitems_written(0), cp_type_tag_key, tag_t::BOOL, (rec.flags & LTB_F_CP_NORM) ? 1 : 0);  // :146-150
+    }
+    std::copy(in, in + half_frame_length, out);                                     // :98 / :152
+    return half_frame_length;
+  }
+  const ltb_window_rec &last_record() const { return d_last; }
+
+ private:
+  sss(int N_id_2, int device) : block("sss") {
+    if (ltb_sss_create(device, N_id_2, &d_sss)) throw std::runtime_error("Error initializing SSS SYNC");
+    set_output_multiple(half_frame_length);   // lib/sss_impl.cc:72
+  }
+  ltb_sss *d_sss = nullptr;
+  ltb_window_rec d_last = ltb_window_rec();
+};
+
+}  // namespace ltetrigger_b200
+#endif  // LTETRIGGER_B200_BLOCKS_HPP

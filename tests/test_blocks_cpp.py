@@ -1,0 +1,62 @@
+"""The C++ block adapters (include/ltetrigger_b200_blocks.hpp): they compile and link against the
+C-ABI library on any machine; on a GPU box the scheduler-style driver tests/cpp/test_blocks.cpp
+must reproduce the oracle's restated blocks call by call."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+SRC = os.path.join(ROOT, "tests", "cpp", "test_blocks.cpp")
+LIBDIR = os.path.join(ROOT, "gr-ltetrigger_b200", "lib")
+
+
+def build(tmp_path):
+    exe = str(tmp_path / "test_blocks")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), SRC,
+                           "-L", LIBDIR, "-lltetrigger_b200", "-Wl,-rpath," + LIBDIR, "-o", exe])
+    return exe
+
+
+def test_adapters_compile_and_link(tmp_path):
+    exe = build(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 2 and "usage" in out.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_blocks_match_oracle(tmp_path, oracle):
+    exe = build(tmp_path)
+    fixture = os.path.join(GOLDEN, "test_frames", "lte_frame_6prb_cellid_123")
+    out = subprocess.run([exe, fixture, "0.4", "0", "4"], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0] == "E Error initializing PSS N_id_2"                      # lib/pss_impl.cc:75-76
+    x = np.fromfile(fixture, np.complex64)
+    n = int(0.4 * 1.92e6) // 8 * 8
+    x = np.tile(x, -(-n // len(x)))[:n]
+    op, os_ = oracle.Pss(0, 4.0), oracle.Sss(0)
+    buf = np.concatenate([np.zeros(960, np.complex64), x])
+    pos, written = 960, 0
+    lines = iter(out[1:])
+    n_calls = 0
+    while pos - 960 + oracle.LOOKAHEAD <= n:
+        nout, ncons, o, rec = op.work(buf, pos)
+        lost = int(bool(rec["flags"] & oracle.F_TAG_LOST))
+        assert next(lines) == "P %d %d %d %d" % (pos - 960, nout, ncons, lost)
+        if nout:
+            _, srec = os_.work(o, lost)
+            cell = int(srec["cell_id"]) if srec["flags"] & oracle.F_CELL else -1
+            cp = int(bool(srec["flags"] & oracle.F_CP_NORM)) if srec["flags"] & oracle.F_CELL else -1
+            s = 0
+            for w in o.view(np.uint32).tolist():
+                s = (s * 1000003 + w) & 0xFFFFFFFFFFFFFFFF
+            assert next(lines) == "S %d %d %d %d" % (written, cell, cp, s)
+            written += nout
+        pos += ncons
+        n_calls += 1
+    assert n_calls >= 70
+    acc = next(lines).split()
+    assert acc[0] == "A"
+    want = [op.max_psr(), op.mean_psr(), op.mean_cfo(), op.psr_threshold(), op.tracking_score()]
+    assert [np.float32(v) for v in acc[1:]] == [np.float32(v) for v in want]

@@ -1,0 +1,109 @@
+"""The drop-in block mirrors (blocks.py: pss, sss, downlink_trigger_c) driven like the reference's
+QA flowgraphs (python/qa_downlink_trigger_c.py:67-203), call by call against the oracle's
+restated blocks: produced/consumed counts, stream tags, emitted samples, accessors."""
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lt():
+    import ltetrigger_b200 as lt
+    if lt.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU path")
+    return lt
+
+
+def search_rate(lt, name, seconds):
+    x, decim, cell_id = load_fixture(name, seconds)
+    if decim > 1:
+        x = lt.kernel_decimate(x[None, :], decim)[0]        # rational_resampler_ccc(1, D) in front
+    return x, cell_id
+
+
+@pytest.mark.parametrize("name", ["6prb", "25prb"])
+def test_pss_sss_blocks_call_by_call(lt, oracle, name):
+    from ltetrigger_b200 import gr_emu
+    x, cell_id = search_rate(lt, name, 0.4)
+    k = cell_id % 3
+    p, s = lt.pss(k, 4.0), lt.sss(k)
+    assert p.history() == 9600 and p.output_multiple() == 9600 and s.output_multiple() == 9600
+    tr = gr_emu.run_chain(x, p, s)
+    assert len(tr.pss_calls) >= 70
+    # oracle blocks driven over the same stream
+    op, os_ = oracle.Pss(k, 4.0), oracle.Sss(k)
+    buf = np.concatenate([np.zeros(960, np.complex64), x])
+    pos, written, i_emit = 960, 0, 0
+    for (r, nout, ncons, tags) in tr.pss_calls:
+        assert r == pos - 960
+        w_nout, w_ncons, w_out, w_rec = op.work(buf, pos)
+        assert (nout, ncons) == (w_nout, w_ncons), (r, nout, ncons, w_nout, w_ncons)
+        lost = bool(w_rec["flags"] & oracle.F_TAG_LOST)
+        assert [(t.key, t.offset, t.value) for t in tags] == ([("tracking_lost", written, None)] if lost else [])
+        if nout:
+            assert np.array_equal(tr.pss_out[i_emit].view(np.uint32), w_out.view(np.uint32))
+            s_out, s_rec = os_.work(w_out, lost)
+            _, in_tags, out_tags = tr.sss_calls[i_emit]
+            want = []
+            if s_rec["flags"] & oracle.F_CELL:
+                want = [("cell_id", written, int(s_rec["cell_id"])), ("cp_type", written, bool(s_rec["flags"] & oracle.F_CP_NORM))]
+            assert [(t.key, t.offset, t.value) for t in out_tags] == want
+            if lost or (s_rec["flags"] & oracle.F_CELL):
+                assert np.array_equal(tr.sss_out[i_emit].view(np.uint32), w_out.view(np.uint32))   # pass-through
+            else:
+                assert tr.sss_out[i_emit] is None                                                   # :119-120
+            i_emit += 1
+            written += nout
+        pos += ncons
+    cells = {t.value for (_, _, out_tags) in tr.sss_calls for t in out_tags if t.key == "cell_id"}
+    assert cells == {cell_id}
+    # accessors (lib/pss_impl.h:95-100)
+    assert p.tracking_score() == op.tracking_score() == 16.0
+    assert p.max_psr() == op.max_psr() and p.mean_psr() == op.mean_psr() and p.mean_cfo() == op.mean_cfo()
+    assert p.psr_threshold() == 4.0
+    p.set_psr_threshold(1.0)                       # the block itself does not clamp
+    assert p.psr_threshold() == 1.0
+
+
+def test_pss_constructor_errors(lt):
+    with pytest.raises(RuntimeError):
+        lt.pss(3, 4.0)                             # lib/pss_impl.cc:75-76
+    with pytest.raises(RuntimeError):
+        lt.sss(7)
+
+
+@pytest.mark.parametrize("name", list(FIXTURES))
+def test_downlink_trigger_c_like_reference_qa(lt, name):
+    """qa_downlink_trigger_c.py: file_source(repeat) -> head(1 s) -> [resampler] -> trigger(4);
+    at least one cell, every reported cell_id and cp type right."""
+    x, cell_id = search_rate(lt, name, 1.0)
+    trig = lt.downlink_trigger_c(psr_threshold=4, exit_on_success=True)
+    assert trig.message_ports() == ["track", "drop"]
+    tracked, dropped = [], []
+    trig.msg_connect("track", tracked.append)
+    trig.msg_connect("drop", dropped.append)
+    # host-side mib stand-in: publish a track message for the first tagged half-frame of a chain
+    seen = set()
+
+    def mib_sink(k, tags, halfframe):
+        ids = [t.value for t in tags if t.key == "cell_id"]
+        if ids and k not in seen:
+            seen.add(k)
+            return [("track", {"cell_id": ids[0], "cp_len": "Normal" if [t.value for t in tags if t.key == "cp_type"][0] else "Extended"})]
+        return []
+
+    trig.mib_sink = mib_sink
+    tags = []
+    for a in range(0, len(x), 96000):              # the scheduler hands over arbitrary chunks
+        tags += trig.work(x[a:a + 96000])
+    ids = [(k, t.value) for k, t in tags if t.key == "cell_id"]
+    assert len(ids) >= 1 and {v for _, v in ids} == {cell_id} and {k for k, _ in ids} == {cell_id % 3}
+    assert all(t.value is True for _, t in tags if t.key == "cp_type")
+    assert tracked == [{"cell_id": cell_id, "cp_len": "Normal"}] and dropped == []
+    assert trig.pss0.tracking_score() == (16.0 if cell_id % 3 == 0 else 0.0)
+    # threshold clamp (python/downlink_trigger_c.py:63-73)
+    trig.set_psr_threshold(0.5)
+    assert trig.psr_threshold == 1.5 and trig.pss1.psr_threshold() == 1.5
