@@ -39,6 +39,11 @@ class TriggerConfig(C.Structure):
                 ("cuda_stream", C.c_void_p)]
 
 
+class Mib(C.Structure):
+    _fields_ = [("nof_prb", C.c_int32), ("nof_ports", C.c_int32), ("phich_length", C.c_int32),
+                ("phich_resources", C.c_int32), ("sfn", C.c_int32), ("sfn_offset", C.c_int32)]
+
+
 class PssStats(C.Structure):
     _fields_ = [("max_psr", C.c_float), ("mean_psr", C.c_float), ("mean_cfo", C.c_float),
                 ("psr_threshold", C.c_float), ("tracking_score", C.c_float), ("tracking", C.c_int32),
@@ -51,7 +56,7 @@ SYMBOLS = [
     "ltb_trigger_process_host", "ltb_trigger_process_device", "ltb_trigger_submit_device",
     "ltb_trigger_collect", "ltb_trigger_get_stats", "ltb_trigger_fetch_halfframes",
     "ltb_trigger_last_timing", "ltb_trigger_last_kernel_times", "ltb_last_error", "ltb_version", "ltb_device_count",
-    "ltb_sss_create", "ltb_sss_destroy", "ltb_sss_work",
+    "ltb_sss_create", "ltb_sss_destroy", "ltb_sss_work", "ltb_mib_decode",
     "ltb_kernel_pss_corr_host", "ltb_kernel_decimate_host", "ltb_debug_set_flag",
     "ltb_table_pss_taps", "ltb_table_decim_taps", "ltb_table_sss", "ltb_table_cexp",
     "ltb_table_fft128_twiddles",
@@ -86,6 +91,7 @@ def lib():
     L.ltb_sss_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     L.ltb_sss_destroy.argtypes = [vp]
     L.ltb_sss_work.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.ltb_mib_decode.argtypes = [vp, C.c_int, C.c_int, C.POINTER(Mib)]
     L.ltb_kernel_pss_corr_host.argtypes = [C.c_int, vp, C.c_int, C.c_int64, vp]
     L.ltb_kernel_decimate_host.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp]
     L.ltb_debug_set_flag.argtypes = [C.c_int, C.c_int]

@@ -188,6 +188,64 @@ class sss(_block):
         return HALF_FRAME_LENGTH
 
 
+class mib(_block):
+    """ltetrigger.mib(exit_on_success=False) -- host side, as in the reference
+    (lib/mib_impl.cc:96-251; include/ltetrigger/mib.h).  Consumes half-frames tagged by sss,
+    decodes the PBCH on the host (ltb_mib_decode, no GPU) and publishes the reference's cell
+    dictionary on "track"; a "tracking_lost" tag publishes the same object on "drop".
+    Message ports are lists of callbacks (`msg_connect`)."""
+
+    PHICH_RESOURCES = ("1/6", "1/2", "1", "2")                 # lib/mib_impl.cc pack_cell
+
+    def __init__(self, exit_on_success=False):
+        _block.__init__(self, "mib")
+        self._exit_on_success = exit_on_success
+        self._published = False
+        self._current = None
+        self._ports = {"track": [], "drop": []}
+        self.done = False                                      # WORK_DONE returned (exit_on_success)
+        self.set_output_multiple(HALF_FRAME_LENGTH)
+
+    def message_ports(self): return list(self._ports)
+    def msg_connect(self, port, callback): self._ports[port].append(callback)
+
+    def _pub(self, port, msg):
+        for cb in self._ports[port]:
+            cb(msg)
+
+    def general_work(self, noutput_items, ninput_items, input_items, output_items):
+        import time
+        self.consume_each(HALF_FRAME_LENGTH)
+        if self.get_tags_in_window(0, 0, 1, TRACKING_LOST_TAG_KEY):              # :107-120
+            if self._published:
+                self._pub("drop", self._current)
+            self._published, self._current = False, None
+            return 0
+        if self._published:                                                        # :122-125
+            return 0
+        ids = self.get_tags_in_window(0, 0, 1, CELL_ID_TAG_KEY)
+        cps = self.get_tags_in_window(0, 0, 1, CP_TYPE_TAG_KEY)
+        if len(ids) != 1 or len(cps) != 1:                                         # :132-135
+            return 0
+        hf = np.ascontiguousarray(input_items[0][:HALF_FRAME_LENGTH], np.complex64)
+        m = A.Mib()
+        rc = A.lib().ltb_mib_decode(hf.ctypes.data, int(ids[0].value), int(bool(cps[0].value)), C.byref(m))
+        if rc < 0:
+            return 0                                                               # "SSS block passed us non-sense"
+        if rc == 1:                                                                # SRSLTE_UE_MIB_FOUND :167-177
+            self._current = {
+                "cell_id": int(ids[0].value), "nof_tx_ports": int(m.nof_ports),
+                "cp_len": "Normal" if cps[0].value else "Extended", "nof_prb": int(m.nof_prb),
+                "phich_len": "Normal" if m.phich_length == 0 else "Extended",
+                "nof_phich_resources": self.PHICH_RESOURCES[m.phich_resources],
+                "sfn_offset": int(m.sfn_offset), "tracking_start_time": int(time.time())}
+            self._pub("track", self._current)
+            self._published = True
+            if self._exit_on_success:
+                self.done = True
+        return HALF_FRAME_LENGTH
+
+
 class _chain_view:
     """What `downlink_trigger_c.pssK` exposes: the pss accessors of chain K of the fused engine
     (GRC probes poll e.g. pss0.tracking_score, examples/rtlsdr_ltetrigger.grc:735-752)."""
@@ -210,13 +268,14 @@ class downlink_trigger_c:
     """Hier block: one complex input at 1.92 Msps, three pss->sss chains, message ports
     "track" and "drop" (python/downlink_trigger_c.py:18-61).
 
-    The three chains run fused in one batched engine (one stream, root_mask 7).  The mib
-    stage stays on the host as in the reference (lib/mib_impl.cc; out of scope here): tagged
-    half-frames are handed to `mib_sink(k, tags, halfframe)` if one is attached, and whatever
-    it returns for "track"/"drop" is forwarded to subscribers of those ports.
+    The three pss -> sss chains run fused in one batched engine (one stream, root_mask 7); the
+    three mib blocks stay on the host as in the reference (`mib0..2`, lib/mib_impl.cc) and are
+    fed the emitted half-frames with their tags.  Their "track"/"drop" messages are forwarded
+    to subscribers of the hier block's ports (python/downlink_trigger_c.py:47-61).  A custom
+    `mib_sink(k, tags, halfframe)` may replace the mib stage (it returns (port, msg) pairs).
     """
 
-    def __init__(self, psr_threshold, exit_on_success=False, device=0, max_chunk=1 << 18, keep_halfframes=False):
+    def __init__(self, psr_threshold, exit_on_success=False, device=0, max_chunk=1 << 18, keep_halfframes=True):
         self.psr_threshold = self._ensure_safe_threshold(psr_threshold)
         self.exit_on_success = exit_on_success
         self._engine = Trigger(1, decim=1, psr_threshold=self.psr_threshold, max_chunk=max_chunk,
@@ -225,6 +284,10 @@ class downlink_trigger_c:
         self.pss0, self.pss1, self.pss2 = (_chain_view(self._engine, k) for k in range(3))
         self._ports = {"track": [], "drop": []}
         self.mib_sink = None
+        self.mib0, self.mib1, self.mib2 = (mib(exit_on_success) for _ in range(3))   # :33-35
+        for m_ in (self.mib0, self.mib1, self.mib2):
+            for port in ("track", "drop"):
+                m_.msg_connect(port, lambda msg, port=port: [cb(msg) for cb in self._ports[port]])
         self._carry = np.zeros(0, np.complex64)
         self.records = []
 
@@ -275,6 +338,10 @@ class downlink_trigger_c:
                     for port, msg in msgs:
                         for cb in self._ports[port]:
                             cb(msg)
+                elif hfs is not None:
+                    mb = (self.mib0, self.mib1, self.mib2)[k]
+                    mb._in_tags, mb._nitems_read = these, off
+                    mb.general_work(HALF_FRAME_LENGTH, [HALF_FRAME_LENGTH], [hfs[k_emit]], [None])
                 k_emit += 1
             pos += take
         return tags

@@ -178,6 +178,22 @@ LTB_API int ltb_sss_destroy(ltb_sss *s);
 LTB_API int ltb_sss_work(ltb_sss *s, const ltb_cf *in, const int32_t *tag_lost, int n_halfframes,
                          ltb_window_rec *recs);
 
+/* ---- host-side MIB decode (consumer of the path's output; never touches the GPU) ------------
+ * What ltetrigger::mib does with a tagged half-frame (lib/mib_impl.cc:148-170:
+ * srslte_ue_mib_decode + srslte_pbch_mib_unpack): PBCH of slot 1, single antenna port, CRC masks of
+ * 1 / 2 / 4 ports.  halfframe = 9600 aligned, CFO-corrected samples as emitted by pss / passed by
+ * sss; cell_id and cp_normal from the sss tags.  Returns 1 (SRSLTE_UE_MIB_FOUND) and fills *out,
+ * 0 if no MIB was found (e.g. a subframe-5 half-frame), < 0 on invalid arguments. */
+typedef struct {
+  int32_t nof_prb;          /* 6, 15, 25, 50, 75, 100 */
+  int32_t nof_ports;        /* 1, 2, 4 (from the CRC mask) */
+  int32_t phich_length;     /* 0 Normal, 1 Extended */
+  int32_t phich_resources;  /* 0 "1/6", 1 "1/2", 2 "1", 3 "2" */
+  int32_t sfn;              /* system frame number of this frame */
+  int32_t sfn_offset;       /* frame position inside the 40 ms PBCH period (scrambling phase) */
+} ltb_mib;
+LTB_API int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_normal, ltb_mib *out);
+
 /* ---- kernel-level entry points (parity tests, profiling) ----------------------------- */
 /* Sliding matched-filter power |x (*) h_k|^2, k = 0,1,2, for n (multiple of 8) samples of
  * each of n_streams host streams; x[<0] = 0.  power: [n_streams][3][n].

@@ -75,35 +75,50 @@ def test_pss_constructor_errors(lt):
         lt.sss(7)
 
 
+NOF_PRB = {"6prb": 6, "25prb": 25, "50prb": 50, "100prb": 100}
+
+
 @pytest.mark.parametrize("name", list(FIXTURES))
 def test_downlink_trigger_c_like_reference_qa(lt, name):
-    """qa_downlink_trigger_c.py: file_source(repeat) -> head(1 s) -> [resampler] -> trigger(4);
-    at least one cell, every reported cell_id and cp type right."""
+    """python/qa_downlink_trigger_c.py:67-203 as written: file_source(repeat) -> head(1 s) ->
+    [rational_resampler_ccc(1, D)] -> downlink_trigger_c(psr_threshold=4, exit_on_success=True),
+    message_debug on "track"; then the reference's six assertions on the first message."""
     x, cell_id = search_rate(lt, name, 1.0)
     trig = lt.downlink_trigger_c(psr_threshold=4, exit_on_success=True)
     assert trig.message_ports() == ["track", "drop"]
     tracked, dropped = [], []
     trig.msg_connect("track", tracked.append)
     trig.msg_connect("drop", dropped.append)
-    # host-side mib stand-in: publish a track message for the first tagged half-frame of a chain
-    seen = set()
-
-    def mib_sink(k, tags, halfframe):
-        ids = [t.value for t in tags if t.key == "cell_id"]
-        if ids and k not in seen:
-            seen.add(k)
-            return [("track", {"cell_id": ids[0], "cp_len": "Normal" if [t.value for t in tags if t.key == "cp_type"][0] else "Extended"})]
-        return []
-
-    trig.mib_sink = mib_sink
     tags = []
     for a in range(0, len(x), 96000):              # the scheduler hands over arbitrary chunks
         tags += trig.work(x[a:a + 96000])
+    assert len(tracked) >= 1                       # self.assertTrue(self.msg_store.num_messages() >= 1)
+    cell = tracked[0]
+    assert cell["cell_id"] == cell_id              # _check_cell_id
+    assert cell["cp_len"] == "Normal"              # _check_cp_len
+    assert cell["nof_phich_resources"] == "1"      # _check_nof_phich_resources
+    assert cell["nof_prb"] == NOF_PRB[name]        # _check_nof_prb
+    assert cell["nof_tx_ports"] == 1               # _check_nof_tx_ports
+    assert cell["phich_len"] == "Normal"           # _check_phich_len
+    assert dropped == [] and len(tracked) == 1     # one cell, published once by its chain's mib
+    assert [m.done for m in (trig.mib0, trig.mib1, trig.mib2)] == [k == cell_id % 3 for k in range(3)]
     ids = [(k, t.value) for k, t in tags if t.key == "cell_id"]
-    assert len(ids) >= 1 and {v for _, v in ids} == {cell_id} and {k for k, _ in ids} == {cell_id % 3}
+    assert {v for _, v in ids} == {cell_id} and {k for k, _ in ids} == {cell_id % 3}
     assert all(t.value is True for _, t in tags if t.key == "cp_type")
-    assert tracked == [{"cell_id": cell_id, "cp_len": "Normal"}] and dropped == []
     assert trig.pss0.tracking_score() == (16.0 if cell_id % 3 == 0 else 0.0)
     # threshold clamp (python/downlink_trigger_c.py:63-73)
     trig.set_psr_threshold(0.5)
     assert trig.psr_threshold == 1.5 and trig.pss1.psr_threshold() == 1.5
+
+
+def test_custom_mib_sink_and_drop(lt):
+    """A custom mib stage sees every emitted half-frame with its tags; track / drop forwarding."""
+    x, cell_id = search_rate(lt, "6prb", 0.3)
+    x = np.concatenate([x, (np.random.default_rng(0).standard_normal((1200000, 2)) * 0.5).astype(np.float32).view(np.complex64)[:, 0]])
+    trig = lt.downlink_trigger_c(psr_threshold=4)
+    tracked, dropped = [], []
+    trig.msg_connect("track", tracked.append)
+    trig.msg_connect("drop", dropped.append)
+    trig.work(x[:len(x) // 8 * 8])
+    assert len(tracked) == 1 and tracked[0]["cell_id"] == cell_id and tracked[0]["nof_prb"] == 6
+    assert dropped == tracked                      # signal gone: the identical object goes out on "drop"

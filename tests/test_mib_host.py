@@ -1,0 +1,88 @@
+"""Host-side MIB decode (ltb_mib_decode + the `mib` block mirror) against the values the
+reference's own tests pin (python/qa_downlink_trigger_c.py:46-65): nof_prb, phich_len,
+nof_phich_resources, nof_tx_ports, cp_len, cell_id for the four bundled test_frames.  Runs
+without a GPU: the oracle's restated pss/sss blocks produce the tagged, aligned, CFO-corrected
+half-frames, the product's host code decodes them."""
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, load_fixture
+
+NOF_PRB = {"6prb": 6, "25prb": 25, "50prb": 50, "100prb": 100}
+
+
+@pytest.mark.parametrize("name", list(FIXTURES))
+def test_mib_block_on_oracle_chain(oracle, name):
+    import ltetrigger_b200 as lt
+    x, decim, cell_id = load_fixture(name, 0.25)
+    y = oracle.decimate(x, decim) if decim > 1 else x
+    k = cell_id % 3
+    op, os_, mb = oracle.Pss(k, 4.0), oracle.Sss(k), lt.mib(exit_on_success=True)
+    tracked = []
+    mb.msg_connect("track", tracked.append)
+    buf = np.concatenate([np.zeros(960, np.complex64), y])
+    pos, written, n_tried = 960, 0, 0
+    while pos - 960 + oracle.LOOKAHEAD <= len(y) and not mb.done:
+        nout, ncons, out, rec = op.work(buf, pos)
+        if nout:
+            lost = bool(rec["flags"] & oracle.F_TAG_LOST)
+            _, srec = os_.work(out, lost)
+            tags = [lt.tag_t(written, "tracking_lost", None)] if lost else []
+            if srec["flags"] & oracle.F_CELL:
+                tags += [lt.tag_t(written, "cell_id", int(srec["cell_id"])),
+                         lt.tag_t(written, "cp_type", bool(srec["flags"] & oracle.F_CP_NORM))]
+                n_tried += 1
+            mb._in_tags, mb._nitems_read = tags, written
+            mb.general_work(9600, [9600], [out], [None])
+            written += nout
+        pos += ncons
+    assert mb.done and len(tracked) == 1 and n_tried <= 2      # SF0 or SF5 first: found within two half-frames
+    cell = tracked[0]
+    assert cell["cell_id"] == cell_id and cell["cp_len"] == "Normal"
+    assert cell["nof_prb"] == NOF_PRB[name] and cell["nof_tx_ports"] == 1
+    assert cell["phich_len"] == "Normal" and cell["nof_phich_resources"] == "1"
+    assert set(cell) == {"cell_id", "nof_tx_ports", "cp_len", "nof_prb", "phich_len", "nof_phich_resources",
+                         "sfn_offset", "tracking_start_time"}      # lib/mib_impl.cc:185-251
+
+
+def test_mib_decode_rejects_noise_sf5_and_bad_arguments():
+    import ctypes as C
+    import ltetrigger_b200 as lt
+    from ltetrigger_b200 import _abi as A
+    L, m = lt.lib(), A.Mib()
+    rng = np.random.default_rng(1)
+    noise = (rng.standard_normal(9600) + 1j * rng.standard_normal(9600)).astype(np.complex64)
+    assert L.ltb_mib_decode(noise.ctypes.data, 123, 1, C.byref(m)) == 0
+    zeros = np.zeros(9600, np.complex64)
+    assert L.ltb_mib_decode(zeros.ctypes.data, 123, 1, C.byref(m)) == 0
+    x, _, cell_id = load_fixture("6prb", 0.02)
+    assert L.ltb_mib_decode(x[:9600].ctypes.data, cell_id, 1, C.byref(m)) == 1 and m.nof_prb == 6
+    assert L.ltb_mib_decode(x[9600:19200].ctypes.data, cell_id, 1, C.byref(m)) == 0      # subframe 5: no PBCH
+    assert L.ltb_mib_decode(x[:9600].ctypes.data, cell_id + 1, 1, C.byref(m)) == 0        # wrong cell: CRS/scrambling differ
+    assert L.ltb_mib_decode(x[:9600].ctypes.data, 504, 1, C.byref(m)) == lt.ERROR_INVALID_INPUTS
+    assert L.ltb_mib_decode(None, 1, 1, C.byref(m)) == lt.ERROR_INVALID_INPUTS
+
+
+def test_mib_block_drop_protocol():
+    """lib/mib_impl.cc:107-125: tracking_lost -> drop with the identical object, then silence until
+    the next decode; untagged or doubly tagged half-frames are ignored."""
+    import ltetrigger_b200 as lt
+    x, _, cell_id = load_fixture("6prb", 0.02)
+    hf = x[:9600]
+    mb = lt.mib()
+    tracked, dropped = [], []
+    mb.msg_connect("track", tracked.append)
+    mb.msg_connect("drop", dropped.append)
+
+    def feed(tags):
+        mb._in_tags, mb._nitems_read = tags, 0
+        return mb.general_work(9600, [9600], [hf], [None])
+
+    good = [lt.tag_t(0, "cell_id", cell_id), lt.tag_t(0, "cp_type", True)]
+    assert feed([]) == 0 and not tracked                                   # no tags: swallowed
+    assert feed(good + [lt.tag_t(0, "cell_id", 5)]) == 0 and not tracked   # two cell_id tags: sanity check trips
+    assert feed(good) == 9600 and len(tracked) == 1
+    assert feed(good) == 0 and len(tracked) == 1                           # already published
+    assert feed([lt.tag_t(0, "tracking_lost", None)]) == 0 and dropped == tracked and dropped[0] is tracked[0]
+    assert feed([lt.tag_t(0, "tracking_lost", None)]) == 0 and len(dropped) == 1   # nothing published: no second drop
+    assert feed(good) == 9600 and len(tracked) == 2
