@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""cell_search_file.py -- search an IQ capture for LTE cells on the GPU.
+
+Same command line and output as the reference's examples/cell_search_file.py:33-204:
+file_source(repeat) -> [rational_resampler_ccc(1, D)] -> [throttle] -> [head] ->
+downlink_trigger_c(threshold, exit_on_success=True) -> cellstore, then one JSON object per found
+cell ("status": "FOUND") or {"status": "NOT_FOUND"}, optionally also written to a FIFO as
+"<length>\\n<json>".  The resampler is fused into the engine's front end; --throttle is accepted
+and ignored (there is no CPU load to lower).
+
+  python examples/cell_search_file.py tests/golden/test_frames/lte_frame_50prb_cellid_125 -s 15.36M --repeat --time-out 1
+"""
+from __future__ import print_function
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gr-ltetrigger_b200", "python"))
+
+REQUIRED_SAMPLE_RATE = 1.92e6
+
+
+def eng_float(s):
+    """gnuradio.eng_arg.eng_float: 15.36M, 1.92e6, 30720k ..."""
+    mult = {"k": 1e3, "M": 1e6, "G": 1e9, "m": 1e-3, "u": 1e-6}
+    s = s.strip()
+    if s and s[-1] in mult:
+        return float(s[:-1]) * mult[s[-1]]
+    return float(s)
+
+
+def eng_int(s):
+    return int(eng_float(s))
+
+
+def search(args):
+    import ltetrigger_b200 as lt
+    if args.sample_rate % REQUIRED_SAMPLE_RATE:
+        sys.stderr.write("Sample rate {:.2f} MHz is not a multiple of 1.92 MHz. "
+                         "Arbitrary resampling not supported at this time.\n".format(args.sample_rate / 1e6))
+        sys.exit(-1)
+    decim = int(args.sample_rate / REQUIRED_SAMPLE_RATE)
+    trigger = lt.downlink_trigger_c(psr_threshold=args.threshold, exit_on_success=True, decim=decim)
+    store = lt.cellstore().connect(trigger)
+    data = np.fromfile(args.filename, np.complex64)
+    chunk = 96000 * decim                                     # 50 ms per scheduler pass
+    fed, t_start = 0, time.time()
+    done = lambda: any(m.done for m in (trigger.mib0, trigger.mib1, trigger.mib2))   # WORK_DONE
+    while not done():
+        if args.cut_off > -1 and fed >= args.cut_off:
+            break
+        if args.cut_off == -1 and args.time_out > -1 and time.time() - t_start >= args.time_out:
+            break
+        pos = fed % len(data) if args.repeat else fed
+        if pos >= len(data):
+            break                                             # end of file without --repeat
+        take = min(chunk, len(data) - pos)
+        if args.cut_off > -1:
+            take = min(take, args.cut_off - fed)
+        trigger.work(data[pos:pos + take])
+        fed += take
+    return store
+
+
+def main(args):
+    print("Starting cell search... ", end="")
+    sys.stdout.flush()
+    store = search(args)
+    print("done.")
+    results = []
+    if store.tracking():
+        for cell in store.cells():
+            cell_json = dict(cell)
+            cell_json["status"] = "FOUND"
+            results.append(json.dumps(cell_json, indent=4))
+    else:
+        results.append(json.dumps({"status": "NOT_FOUND"}))
+    for cell in results:
+        print(cell)
+    if args.fifoname:
+        if not os.path.exists(args.fifoname):
+            os.mkfifo(args.fifoname)
+        pipeout = os.open(args.fifoname, os.O_WRONLY)
+        for cell in results:
+            os.write(pipeout, (str(len(cell)) + "\n" + cell).encode())
+        os.close(pipeout)
+    return results
+
+
+def parse(argv=None):
+    def filetype(fname):
+        if os.path.isfile(fname):
+            return fname
+        raise argparse.ArgumentTypeError("file {} does not exist".format(fname))
+
+    parser = argparse.ArgumentParser()
+    parser.add_argument("filename", type=filetype)
+    parser.add_argument("-s", "--sample-rate", type=eng_float, required=True, metavar="Hz",
+                        help="input data's sample rate [Required]")
+    parser.add_argument("-f", "--frequency", type=eng_float, metavar="Hz", help="input data's center frequency")
+    parser.add_argument("--repeat", action="store_true",
+                        help="loop file until cell found or cut-off reached [default=%(default)s]")
+    parser.add_argument("-c", "--cut-off", type=eng_int, metavar="N", default=-1,
+                        help="stop looping after N samples [default=%(default)s]")
+    parser.add_argument("--throttle", type=eng_float, metavar="Hz",
+                        help="throttle file source to lower CPU load [default=%(default)s]")
+    parser.add_argument("--time-out", type=eng_float, metavar="sec", default=-1,
+                        help="max time in seconds to perform search [default=%(default)s]")
+    parser.add_argument("--threshold", type=eng_float, default=4,
+                        help="set peak to side-lobe ratio threshold [default=%(default)s]")
+    parser.add_argument("--gui", action="store_true", help=argparse.SUPPRESS)
+    parser.add_argument("--debug", action="store_true", help=argparse.SUPPRESS)
+    parser.add_argument("--fifoname", default=None, required=False, help="FIFO name to which to write output")
+    return parser.parse_args(argv)
+
+
+if __name__ == "__main__":
+    main(parse())

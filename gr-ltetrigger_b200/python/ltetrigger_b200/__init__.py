@@ -13,4 +13,4 @@ from ._abi import (LIB_PATH, SUCCESS, ERROR, ERROR_INVALID_INPUTS, SLOT_LEN, HAL
                    LOOKAHEAD, FMT_FC32, FMT_SC16, MIN_PSR_THRESHOLD, F_SEARCHED, F_OVER, F_EMIT, F_TRACKING,
                    F_TAG_LOST, F_SSS, F_CELL, F_CP_NORM, WINDOW_REC, LtbError, lib)
 from .engine import Trigger, device_count, kernel_pss_corr, kernel_decimate, tables
-from .blocks import pss, sss, mib, downlink_trigger_c, tag_t
+from .blocks import pss, sss, mib, cellstore, downlink_trigger_c, tag_t

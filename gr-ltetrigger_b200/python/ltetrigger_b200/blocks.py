@@ -275,10 +275,15 @@ class downlink_trigger_c:
     `mib_sink(k, tags, halfframe)` may replace the mib stage (it returns (port, msg) pairs).
     """
 
-    def __init__(self, psr_threshold, exit_on_success=False, device=0, max_chunk=1 << 18, keep_halfframes=True):
+    def __init__(self, psr_threshold, exit_on_success=False, device=0, max_chunk=1 << 18, keep_halfframes=True,
+                 decim=1):
+        """`decim` > 1 fuses the `rational_resampler_ccc(1, decim)` the reference's apps put in
+        front of the hier block (examples/cell_search_file.py:56-57) into the engine's front end;
+        the input of work() is then at decim x 1.92 Msps.  Default: the reference's interface."""
         self.psr_threshold = self._ensure_safe_threshold(psr_threshold)
         self.exit_on_success = exit_on_success
-        self._engine = Trigger(1, decim=1, psr_threshold=self.psr_threshold, max_chunk=max_chunk,
+        self._step = 8 * decim
+        self._engine = Trigger(1, decim=decim, psr_threshold=self.psr_threshold, max_chunk=max_chunk * decim,
                                record_all=True, keep_halfframes=keep_halfframes, device=device)
         self._keep = keep_halfframes
         self.pss0, self.pss1, self.pss2 = (_chain_view(self._engine, k) for k in range(3))
@@ -307,12 +312,12 @@ class downlink_trigger_c:
         """Consume a run of input items; returns the stream tags produced by the three sss
         blocks as (k, tag_t) pairs (offsets count items written by chain k's pss)."""
         x = np.concatenate([self._carry, np.asarray(samples, np.complex64)])
-        n = len(x) // 8 * 8
+        n = len(x) // self._step * self._step
         self._carry = x[n:].copy()
         tags = []
         pos = 0
         while pos < n:
-            take = min(n - pos, self._engine.max_chunk // 8 * 8)
+            take = min(n - pos, self._engine.max_chunk // self._step * self._step)
             recs = self._engine.process(x[None, pos:pos + take])
             hfs = None
             if self._keep:
@@ -345,3 +350,42 @@ class downlink_trigger_c:
                 k_emit += 1
             pos += take
         return tags
+
+
+class cellstore:
+    """ltetrigger.cellstore() -- message-only block keeping the tracked cells
+    (lib/cellstore_impl.cc:46-105, include/ltetrigger/cellstore.h:59-65): "track" appends the
+    cell, "drop" removes that same object; tracking() / cells() / latest_cell()."""
+
+    def __init__(self):
+        import threading
+        self._cells = []
+        self._mu = threading.Lock()                            # the reference guards its list too
+
+    def message_ports(self): return ["track", "drop"]
+
+    def track_cell(self, cell):
+        with self._mu:
+            self._cells.append(cell)
+
+    def drop_cell(self, cell):
+        with self._mu:
+            self._cells = [c for c in self._cells if c is not cell]   # removal by identity (:103)
+
+    def tracking(self):
+        with self._mu:
+            return len(self._cells) > 0
+
+    def cells(self):
+        with self._mu:
+            return list(self._cells)
+
+    def latest_cell(self):
+        with self._mu:
+            return self._cells[-1] if self._cells else None
+
+    def connect(self, trigger):
+        """msg_connect(trigger, "track"/"drop", self, ...) of examples/cell_search_file.py:82-88."""
+        trigger.msg_connect("track", self.track_cell)
+        trigger.msg_connect("drop", self.drop_cell)
+        return self

@@ -122,3 +122,35 @@ def test_custom_mib_sink_and_drop(lt):
     trig.work(x[:len(x) // 8 * 8])
     assert len(tracked) == 1 and tracked[0]["cell_id"] == cell_id and tracked[0]["nof_prb"] == 6
     assert dropped == tracked                      # signal gone: the identical object goes out on "drop"
+
+
+@pytest.mark.parametrize("name,rate", [("6prb", "1.92M"), ("25prb", "7.68M"), ("50prb", "15.36M"), ("100prb", "30.72M")])
+def test_cell_search_file_cli(lt, name, rate, capsys):
+    """examples/test.sh:3-6: the CLI over the four fixtures with --repeat --time-out 1."""
+    import importlib.util
+    import json
+    import os
+    from conftest import GOLDEN, ROOT
+    spec = importlib.util.spec_from_file_location("cell_search_file", os.path.join(ROOT, "examples", "cell_search_file.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    fname, _, cell_id = FIXTURES[name]
+    args = cli.parse([os.path.join(GOLDEN, "test_frames", fname), "-s", rate, "--repeat", "--time-out", "5"])
+    results = cli.main(args)
+    out = capsys.readouterr().out
+    assert out.startswith("Starting cell search... done.")
+    assert len(results) == 1
+    cell = json.loads(results[0])
+    assert cell["status"] == "FOUND" and cell["cell_id"] == cell_id and cell["nof_prb"] == NOF_PRB[name]
+    assert cell["cp_len"] == "Normal" and cell["nof_tx_ports"] == 1
+    # no cell: noise capture without --repeat runs to the end of the file
+    noise = (np.random.default_rng(3).standard_normal((400000, 2)) * 0.3).astype(np.float32)
+    path = os.path.join(str(os.environ.get("TMPDIR", "/tmp")), "ltb_noise_%d.fc32" % os.getpid())
+    noise.tofile(path)
+    try:
+        res = cli.main(cli.parse([path, "-s", "1.92M"]))
+        assert json.loads(res[0]) == {"status": "NOT_FOUND"}
+        with pytest.raises(SystemExit):
+            cli.main(cli.parse([path, "-s", "2M"]))          # not a multiple of 1.92 MHz
+    finally:
+        os.remove(path)
