@@ -351,7 +351,10 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
 // through a per-warp shared-memory scratch, which leaves lane l with output 32*warp + l: one
 // coalesced store.  The FFMA2 stream saturates register-file read bandwidth (measured,
 // tools/ubench_issue.cu: other instructions do not hide in its shadow, they add), so the design
-// goal is the fewest non-FFMA2 instructions per 528 FFMA2: 48 LDS + a 47-instruction reduction.
+// goal is the fewest non-FFMA2 instructions per 528 FFMA2: 48 LDS + a ~55-instruction reduction.
+// Warps per CTA must be a multiple of 4: warp w runs on scheduler w % 4, and every warp does the
+// same work, so 6- or 10-warp CTAs overload two of the four schedulers (measured: 4.5 / 4.3 ms
+// against 3.6 ms for 8 warps x 2 CTAs or 20 warps x 1 CTA).
 // A CTA walks a contiguous run of 256-output segments; the last warp to finish segment i requests
 // segment i+2 into the buffer it frees (a shared-memory counter, no CTA barrier), so warps drift
 // freely and one segment per CTA is always in flight.
@@ -361,7 +364,7 @@ constexpr int kStrThreads = 32 * kStrWarps;
 constexpr int kStrSeg = 32 * kStrWarps;               // outputs per segment
 constexpr int kStrBlocks = kStrSeg + kDecQ;           // 289 input blocks per segment
 constexpr int kStrBufs = 2;
-constexpr int kStrScratchRow = 17;                    // float2 per (half, position) row: 16 outputs + 1 pad
+constexpr int kStrScratchRow = 9;                     // float2 per (half, position) row: 8 outputs + 1 pad
 constexpr int kStrScratch = 2 * 16 * kStrScratchRow;  // float2 per warp
 
 template <int FMT> __host__ __device__ constexpr int str_buf_bytes() { return kStrBlocks * 16 * (FMT == LTB_FMT_FC32 ? 8 : 4); }
@@ -517,23 +520,37 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
         }
       }
     }
-    // transpose through the warp's scratch: row = (half, position), column = output; then lane
-    // (o, half) sums the 16 position partials of output o in the canonical pairwise tree
+    // transpose through the warp's scratch in two passes of 8 outputs (row = (half, position),
+    // column = output): lane (g, oo) of a half-warp sums positions 8g..8g+7 of output 8*pass + oo
+    // in the canonical pairwise tree, one shuffle adds the two halves of the tree, and the lane
+    // whose g equals the pass keeps the result, so lane l ends with output 32*warp + l
     {
+      const int g8 = (lane >> 3) & 1, oo = lane & 7;
       float2 *wr = scratch + p * kStrScratchRow;
+      const float2 *rd = scratch + (8 * g8) * kStrScratchRow + oo;
+      float2 res = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int o = 0; o < kDecT; ++o) wr[o] = acc[o];
-      __syncwarp();
-      float2 pp[16];
+      for (int pass = 0; pass < 2; ++pass) {
+        __syncwarp();
 #pragma unroll
-      for (int r = 0; r < 16; ++r) pp[r] = scratch[r * kStrScratchRow + p];
+        for (int o = 0; o < 8; ++o) wr[o] = acc[8 * pass + o];
+        __syncwarp();
+        float2 pp[8];
 #pragma unroll
-      for (int w2 = 1; w2 < 16; w2 <<= 1) {
+        for (int r = 0; r < 8; ++r) pp[r] = rd[r * kStrScratchRow];
 #pragma unroll
-        for (int r = 0; r < 16; r += 2 * w2) pp[r] = fadd2(pp[r], pp[r + w2]);
+        for (int w2 = 1; w2 < 8; w2 <<= 1) {
+#pragma unroll
+          for (int r = 0; r < 8; r += 2 * w2) pp[r] = fadd2(pp[r], pp[r + w2]);
+        }
+        float2 other;
+        other.x = __shfl_xor_sync(0xffffffffu, pp[0].x, 8);
+        other.y = __shfl_xor_sync(0xffffffffu, pp[0].y, 8);
+        const float2 tot = g8 ? fadd2(other, pp[0]) : fadd2(pp[0], other);   // (P0..7) + (P8..15)
+        if (g8 == pass) res = tot;
       }
       const int k = S.k0 + 32 * warp + lane;
-      if (k < n_out) y_ring[(size_t)S.stream * cap + (unsigned)((n_base + k) & cap_mask)] = pp[0];
+      if (k < n_out) y_ring[(size_t)S.stream * cap + (unsigned)((n_base + k) & cap_mask)] = res;
     }
     // release buffer b without a CTA barrier: the last of the warps to get here requests the
     // segment that goes into it next, so no warp ever waits for its siblings
