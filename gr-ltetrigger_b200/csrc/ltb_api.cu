@@ -206,8 +206,10 @@ struct ltb_trigger {
   int n_pending = 0, head = 0;            // slot[head] is the oldest pending call
   int last = 0;                           // slot of the most recently collected call
   float last_kernel_ms[4] = {0.f, 0.f, 0.f, 0.f};
-  void *d_in = nullptr;
+  void *d_in[2] = {nullptr, nullptr};     // host-input staging, one per call in flight
   size_t d_in_stride = 0;
+  cudaStream_t in_stream = nullptr;       // host->device copies, overlap the previous call's kernels
+  cudaEvent_t in_ready[2] = {nullptr, nullptr};
   float2 *d_y = nullptr;
   float *d_p = nullptr;
   ChainState *d_state = nullptr;
@@ -249,7 +251,7 @@ int trigger_zero_state(ltb_trigger *t) {
 void trigger_free(ltb_trigger *t) {
   if (!t) return;
   cudaSetDevice(t->cfg.device);
-  cudaFree(t->d_in); cudaFree(t->d_y); cudaFree(t->d_p); cudaFree(t->d_state); cudaFree(t->d_avg);
+  cudaFree(t->d_in[0]); cudaFree(t->d_in[1]); cudaFree(t->d_y); cudaFree(t->d_p); cudaFree(t->d_state); cudaFree(t->d_avg);
   cudaFree(t->d_thr); cudaFree(t->d_sss_sym);
   cudaFree(t->d_sss_rec); cudaFree(t->d_sss_count); cudaFree(t->d_hf); cudaFree(t->d_tail[0]);
   cudaFree(t->d_tail[1]); cudaFree(t->d_cexp);
@@ -263,6 +265,8 @@ void trigger_free(ltb_trigger *t) {
     for (int i = 0; i < 4; ++i) if (sl.ev_k[i]) cudaEventDestroy(sl.ev_k[i]);
   }
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  if (t->in_stream) cudaStreamDestroy(t->in_stream);
+  for (auto &e : t->in_ready) if (e) cudaEventDestroy(e);
   if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
@@ -400,6 +404,8 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   LTB_CUDA_T(cudaMalloc(&t->d_avg, sizeof(float) * (size_t)t->n_chains * kAvgLen));
   LTB_CUDA_T(cudaMalloc(&t->d_thr, sizeof(float) * t->n_chains));
   LTB_CUDA_T(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+  LTB_CUDA_T(cudaStreamCreateWithFlags(&t->in_stream, cudaStreamNonBlocking));
+  for (auto &e : t->in_ready) LTB_CUDA_T(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &sl : t->slot) {
     LTB_CUDA_T(cudaMalloc(&sl.d_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cap));
     LTB_CUDA_T(cudaMalloc(&sl.d_rec_count, sizeof(int) * t->n_chains));
@@ -425,6 +431,7 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
 int ltb_trigger_destroy(ltb_trigger *t) {
   if (!t) return LTB_ERROR_INVALID_INPUTS;
   cudaSetDevice(t->cfg.device);
+  if (t->in_stream) cudaStreamSynchronize(t->in_stream);
   cudaStreamSynchronize(t->stream);
   if (t->copy_stream) cudaStreamSynchronize(t->copy_stream);
   trigger_free(t);
@@ -434,6 +441,7 @@ int ltb_trigger_destroy(ltb_trigger *t) {
 int ltb_trigger_reset(ltb_trigger *t) {
   if (!t) return LTB_ERROR_INVALID_INPUTS;
   LTB_CUDA(cudaSetDevice(t->cfg.device));
+  LTB_CUDA(cudaStreamSynchronize(t->in_stream));
   LTB_CUDA(cudaStreamSynchronize(t->stream));
   LTB_CUDA(cudaStreamSynchronize(t->copy_stream));
   return trigger_zero_state(t);
@@ -494,17 +502,27 @@ int ltb_trigger_process_device(ltb_trigger *t, const void *d_iq, int64_t stride,
   return ltb_trigger_collect(t, recs, max_recs, n_recs);
 }
 
-int ltb_trigger_process_host(ltb_trigger *t, const void *iq, int64_t stride, int64_t n_samples,
-                             ltb_window_rec *recs, int max_recs, int *n_recs) {
+int ltb_trigger_submit_host(ltb_trigger *t, const void *iq, int64_t stride, int64_t n_samples) {
   if (!t || !iq) return LTB_ERROR_INVALID_INPUTS;
   LTB_CUDA(cudaSetDevice(t->cfg.device));
   if (n_samples <= 0 || n_samples > t->cfg.max_chunk) return fail(LTB_ERROR_INVALID_INPUTS, "n_samples out of range");
-  if (t->n_pending) return fail(LTB_ERROR_INVALID_INPUTS, "collect the submitted calls before a synchronous process call");
-  if (!t->d_in) LTB_CUDA(cudaMalloc(&t->d_in, t->d_in_stride * (size_t)t->cfg.n_streams));
+  if (t->n_pending >= (t->cfg.keep_halfframes ? 1 : 2)) return fail(LTB_ERROR_INVALID_INPUTS, "too many submits not collected");
+  // staging buffer of the slot this call will occupy; the call that used it last has been
+  // collected (at most two in flight), so its front end is done with it
+  const int slot = (t->head + t->n_pending) & 1;
+  if (!t->d_in[slot]) LTB_CUDA(cudaMalloc(&t->d_in[slot], t->d_in_stride * (size_t)t->cfg.n_streams));
   const size_t row = (size_t)n_samples * (t->cfg.input_format == LTB_FMT_FC32 ? 8 : 4);
-  LTB_CUDA(cudaMemcpy2DAsync(t->d_in, t->d_in_stride, iq, (size_t)stride, row, (size_t)t->cfg.n_streams,
-                             cudaMemcpyHostToDevice, t->stream));
-  int rc = trigger_enqueue(t, t->d_in, (long long)t->d_in_stride, n_samples);
+  LTB_CUDA(cudaMemcpy2DAsync(t->d_in[slot], t->d_in_stride, iq, (size_t)stride, row, (size_t)t->cfg.n_streams,
+                             cudaMemcpyHostToDevice, t->in_stream));
+  LTB_CUDA(cudaEventRecord(t->in_ready[slot], t->in_stream));
+  LTB_CUDA(cudaStreamWaitEvent(t->stream, t->in_ready[slot], 0));
+  return trigger_enqueue(t, t->d_in[slot], (long long)t->d_in_stride, n_samples);
+}
+
+int ltb_trigger_process_host(ltb_trigger *t, const void *iq, int64_t stride, int64_t n_samples,
+                             ltb_window_rec *recs, int max_recs, int *n_recs) {
+  if (t && t->n_pending) return fail(LTB_ERROR_INVALID_INPUTS, "collect the submitted calls before a synchronous process call");
+  int rc = ltb_trigger_submit_host(t, iq, stride, n_samples);
   if (rc) return rc;
   return ltb_trigger_collect(t, recs, max_recs, n_recs);
 }

@@ -53,7 +53,7 @@ class PssStats(C.Structure):
 # every symbol include/ltetrigger_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "ltb_trigger_create", "ltb_trigger_destroy", "ltb_trigger_reset", "ltb_trigger_set_psr_threshold",
-    "ltb_trigger_process_host", "ltb_trigger_process_device", "ltb_trigger_submit_device",
+    "ltb_trigger_process_host", "ltb_trigger_process_device", "ltb_trigger_submit_device", "ltb_trigger_submit_host",
     "ltb_trigger_collect", "ltb_trigger_get_stats", "ltb_trigger_fetch_halfframes",
     "ltb_trigger_last_timing", "ltb_trigger_last_kernel_times", "ltb_last_error", "ltb_version", "ltb_device_count",
     "ltb_sss_create", "ltb_sss_destroy", "ltb_sss_work", "ltb_mib_decode",
@@ -83,6 +83,7 @@ def lib():
     L.ltb_trigger_process_host.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int, ip]
     L.ltb_trigger_process_device.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int, ip]
     L.ltb_trigger_submit_device.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    L.ltb_trigger_submit_host.argtypes = [vp, vp, C.c_int64, C.c_int64]
     L.ltb_trigger_collect.argtypes = [vp, vp, C.c_int, ip]
     L.ltb_trigger_get_stats.argtypes = [vp, C.c_int, C.c_int, C.POINTER(PssStats)]
     L.ltb_trigger_fetch_halfframes.argtypes = [vp, vp, C.c_int, ip]

@@ -82,6 +82,9 @@ class Trigger:
     def submit_device_ptr(self, dptr, stride_bytes, n):
         A.check(A.lib().ltb_trigger_submit_device(self._h, dptr, stride_bytes, n), "ltb_trigger_submit_device")
 
+    def submit_host_ptr(self, ptr, stride_bytes, n):
+        A.check(A.lib().ltb_trigger_submit_host(self._h, ptr, stride_bytes, n), "ltb_trigger_submit_host")
+
     def collect(self):
         nrec = C.c_int32(0)
         A.check(A.lib().ltb_trigger_collect(self._h, self._recs.ctypes.data, len(self._recs), C.byref(nrec)),

@@ -148,6 +148,10 @@ LTB_API int ltb_trigger_process_device(ltb_trigger *t, const void *d_iq, int64_t
 LTB_API int ltb_trigger_submit_device(ltb_trigger *t, const void *d_iq, int64_t stream_stride_bytes,
                                       int64_t n_samples);
 LTB_API int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int *n_recs);
+/* The same for host input: the host->device copy of call i+1 runs on its own stream while the
+ * kernels of call i execute.  The host buffer must stay valid (and, for full PCIe rate, pinned)
+ * until the call is collected. */
+LTB_API int ltb_trigger_submit_host(ltb_trigger *t, const void *iq, int64_t stream_stride_bytes, int64_t n_samples);
 
 /* max_psr / mean_psr / mean_cfo / psr_threshold / tracking_score of one chain */
 LTB_API int ltb_trigger_get_stats(ltb_trigger *t, int stream, int n_id_2, ltb_pss_stats *out);

@@ -219,3 +219,22 @@ def test_two_calls_in_flight_match_synchronous_calls(lt, oracle):
     recs = np.concatenate(got)
     recs = recs[np.lexsort((recs["win_index"], recs["n_id_2"], recs["stream"]))]
     assert_recs_equal(recs, want)
+
+
+def test_two_host_calls_in_flight(lt, oracle):
+    """ltb_trigger_submit_host: the copy of call i+1 overlaps call i; records equal the oracle's."""
+    import torch
+    x, decim, _ = load_fixture("50prb", 0.3)
+    n = len(x) // 3 // (8 * decim) * (8 * decim)
+    want = oracle.trigger_run(x[None, :3 * n], decim=decim)
+    h = torch.from_numpy(x[:3 * n].copy()).pin_memory()
+    trig = lt.Trigger(n_streams=1, decim=decim, max_chunk=n)
+    got = []
+    trig.submit_host_ptr(h.data_ptr(), 0, n)
+    trig.submit_host_ptr(h.data_ptr() + 8 * n, 0, n)
+    got.append(trig.collect().copy())
+    trig.submit_host_ptr(h.data_ptr() + 16 * n, 0, n)
+    got += [trig.collect().copy(), trig.collect().copy()]
+    recs = np.concatenate(got)
+    recs = recs[np.lexsort((recs["win_index"], recs["n_id_2"], recs["stream"]))]
+    assert_recs_equal(recs, want)
