@@ -846,7 +846,15 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
   const float thr = P.thr[chain];
 
   if (tid == 0) S.st = P.state[chain];
-  for (int k = tid; k < kAvgLen; k += kTrackThreads) S.avg[k] = avg_g[k];
+  {
+    // 39 kB of EMA state per chain: all of a thread's loads in flight at once (one round trip)
+    constexpr int kN = (kAvgLen + kTrackThreads - 1) / kTrackThreads;   // 39
+    float v[kN];
+#pragma unroll
+    for (int j = 0; j < kN; ++j) { const int k = tid + j * kTrackThreads; v[j] = k < kAvgLen ? avg_g[k] : 0.f; }
+#pragma unroll
+    for (int j = 0; j < kN; ++j) { const int k = tid + j * kTrackThreads; if (k < kAvgLen) S.avg[k] = v[j]; }
+  }
   S.lead[tid] = make_float2(0.f, 0.f);
   S.trail[tid] = make_float2(0.f, 0.f);
   int n_rec = 0;
