@@ -29,7 +29,17 @@ sys.path.insert(0, os.path.join(ROOT, "gr-ltetrigger_b200", "python"))
 
 SEARCH_RATE = 1.92e6
 F_PSS = 3 * 128 * 8 + 18                     # flop per search-rate sample, direct form
-NTAPS = {1: 0, 2: 65, 4: 131, 8: 263, 16: 525}
+
+
+def ntaps(decim):
+    """gr-filter rational_resampler_ccc(1, D) default design: tap count."""
+    if decim <= 1:
+        return 0
+    n = int((7.0 / 0.1102 + 8.7) / (22.0 * 0.1 / decim))
+    return n + 1 - (n & 1)
+
+
+FMT_BYTES = {"fc32": 8, "sc16": 4, "sc8": 2}
 FP32_PEAK_TFLOPS = 72.4                      # measured: tools/ubench_fp32.cu on this pool's B200 (profiles/ubench_fp32_r01.jsonl)
 
 
@@ -42,7 +52,7 @@ def parse():
     ap.add_argument("--streams", type=int, default=512, help="streams per GPU")
     ap.add_argument("--segment-ms", type=int, default=100)
     ap.add_argument("--decim", type=int, default=16)
-    ap.add_argument("--format", default="fc32", choices=["fc32", "sc16"])
+    ap.add_argument("--format", default="fc32", choices=["fc32", "sc16", "sc8"])
     ap.add_argument("--snr-db", type=float, default=5.0)
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic captures tiled over the streams")
     ap.add_argument("--e2e-streams", type=int, default=128)
@@ -50,6 +60,7 @@ def parse():
     ap.add_argument("--cpu-streams", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-formats", action="store_true", help="skip the e2e legs on the other wire formats")
     return ap.parse_args()
 
 
@@ -187,8 +198,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    fmt = lt.FMT_FC32 if a.format == "fc32" else lt.FMT_SC16
-    bps = 8 if fmt == lt.FMT_FC32 else 4
+    fmts = {"fc32": lt.FMT_FC32, "sc16": lt.FMT_SC16, "sc8": lt.FMT_SC8}
+    fmt = fmts[a.format]
+    bps = FMT_BYTES[a.format]
     n = int(a.segment_ms * 1e-3 * SEARCH_RATE) * a.decim           # input samples per stream per step
     m = n // a.decim
 
@@ -204,12 +216,21 @@ def main():
         noise = torch.randn((n, 2), generator=g, device=dev, dtype=torch.float32)
         x[s] = torch.roll(base_d[s % a.unique], int(shifts[s])) + sigma * torch.view_as_complex(noise)
     del noise, base_d
-    if fmt == lt.FMT_SC16:
-        xr = torch.view_as_real(x)
-        d_in = torch.clamp(torch.round(xr * (32767.0 / 8.0)), -32768, 32767).to(torch.int16).contiguous()
-        del x, xr
+    def quantise(xc, name):
+        """fc32 -> the named wire format (full scale = 8 x the signal's rms)."""
+        if name == "fc32":
+            return xc
+        xr = torch.view_as_real(xc)
+        if name == "sc16":
+            return torch.clamp(torch.round(xr * (32767.0 / 8.0)), -32768, 32767).to(torch.int16).contiguous()
+        return torch.clamp(torch.round(xr * (127.0 / 8.0)), -128, 127).to(torch.int8).contiguous()
+
+    d_in = quantise(x, a.format)
+    if a.format != "fc32":
+        x_e2e = x[:min(a.e2e_streams, a.streams)].clone()         # fc32 source of the per-format e2e legs
+        del x
     else:
-        d_in = x
+        x_e2e = x
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
@@ -263,7 +284,7 @@ def main():
     stage_ms /= a.steps
     names = ["frontend(convert+decimate)", "pss_corr(3 roots)", "pss_track", "sss"]
     names_short = ["frontend", "pss_corr", "pss_track", "sss"]
-    alg_flop = [4.0 * NTAPS[a.decim] * m * a.streams, float(F_PSS) * m * a.streams, 0.0, 0.0]
+    alg_flop = [4.0 * ntaps(a.decim) * m * a.streams, float(F_PSS) * m * a.streams, 0.0, 0.0]
     dom = int(np.argmax(stage_ms))
     if alg_flop[dom] == 0.0:
         dom = int(np.argmax(stage_ms[:2]))
@@ -276,7 +297,7 @@ def main():
             traffic = tr["dram_bytes_per_launch"].get(names_short[dom])
     except Exception:
         pass
-    f_alg = (F_PSS + 4.0 * NTAPS[a.decim]) / a.decim                # flop per input sample, SURVEY 8d
+    f_alg = (F_PSS + 4.0 * ntaps(a.decim)) / a.decim                # flop per input sample, SURVEY 8d
     per_gpu_rate = value * 1e6 / world
     roofline = {
         "bound": "fp32", "kernel": names[dom], "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
@@ -307,36 +328,48 @@ def main():
     # ---- end to end through the C ABI with host buffers (H2D + D2H inside the timed region) --
     if not a.no_e2e:
         se = min(a.e2e_streams, a.streams)
-        host = torch.empty((se,) + tuple(d_in.shape[1:]), dtype=d_in.dtype, pin_memory=True)
-        host.copy_(d_in[:se])
-        torch.cuda.synchronize()
         trig.close()
-        trig2 = lt.Trigger(n_streams=se, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
-                           record_all=False, device=local_rank, cuda_stream=stream.cuda_stream)
-        hptr = host.data_ptr()
-        trig2.process_host_ptr(hptr, stride, n)                    # warm-up (allocates the staging buffer)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        d2h = 0
-        trig2.submit_host_ptr(hptr, stride, n)               # two calls in flight: the H2D of call i+1
-        for _ in range(a.e2e_steps - 1):                     # overlaps the kernels of call i
-            trig2.submit_host_ptr(hptr, stride, n)
+
+        def run_e2e(name):
+            src = d_in[:se] if name == a.format else quantise(x_e2e[:se], name)
+            host = torch.empty(tuple(src.shape), dtype=src.dtype, pin_memory=True)
+            host.copy_(src)
+            del src
+            torch.cuda.synchronize()
+            b = FMT_BYTES[name]
+            trig2 = lt.Trigger(n_streams=se, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmts[name],
+                               record_all=False, device=local_rank, cuda_stream=stream.cuda_stream)
+            hptr, hstride = host.data_ptr(), n * b
+            trig2.process_host_ptr(hptr, hstride, n)                # warm-up (allocates the staging buffer)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0.record(stream)
+            d2h = 0
+            trig2.submit_host_ptr(hptr, hstride, n)             # two calls in flight: the H2D of call i+1
+            for _ in range(a.e2e_steps - 1):                     # overlaps the kernels of call i
+                trig2.submit_host_ptr(hptr, hstride, n)
+                d2h += trig2.collect().nbytes
             d2h += trig2.collect().nbytes
-        d2h += trig2.collect().nbytes
-        e1.record(stream)
-        torch.cuda.synchronize()
-        e2e_ms = e0.elapsed_time(e1)
-        if world > 1:
-            tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_ms = float(tt.item())
-        out["e2e"] = {"value": se * n * a.e2e_steps * world / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
-                      "h2d_bytes_per_step": se * n * bps, "d2h_bytes_per_step": d2h // a.e2e_steps,
-                      "streams": se, "steps": a.e2e_steps, "host_memory": "pinned",
-                      "api": "ltb_trigger_submit_host + ltb_trigger_collect (two calls in flight)"}
+            e1.record(stream)
+            torch.cuda.synchronize()
+            e2e_ms = e0.elapsed_time(e1)
+            if world > 1:
+                tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                e2e_ms = float(tt.item())
+            trig2.close()
+            return host, {"value": se * n * a.e2e_steps * world / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                          "h2d_bytes_per_step": se * n * b, "d2h_bytes_per_step": d2h // a.e2e_steps,
+                          "streams": se, "steps": a.e2e_steps, "host_memory": "pinned", "format": name,
+                          "api": "ltb_trigger_submit_host + ltb_trigger_collect (two calls in flight)"}
+
+        host, out["e2e"] = run_e2e(a.format)
+        # the same streams on the narrower wire formats an SDR delivers: the host link is the e2e bound
+        out["e2e_by_format"] = {a.format: out["e2e"]["value"]}
+        for name in ("fc32", "sc16", "sc8"):
+            if name != a.format and not a.no_e2e_formats:
+                out["e2e_by_format"][name] = run_e2e(name)[1]["value"]
         # ---- CPU baseline on the same host sample (rank 0, N=1 only) ---------------------------
         if rank == 0 and world == 1 and not a.no_cpu_baseline and fmt == lt.FMT_FC32:
             sc = min(a.cpu_streams, se)
@@ -351,7 +384,6 @@ def main():
                                    "sample": "%d passes over %d streams x %d ms of the same workload (%.1f s wall); oracle in "
                                              "reference-class FFT mode (9728-point FFT convolution per window and root), "
                                              "one job per (stream, root) on all cores" % (reps, sc, a.segment_ms, dt)}
-        trig2.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -62,25 +62,20 @@ int ensure_constants(int device) {
   LTB_CUDA(cudaMemcpyToSymbol(c_pss_taps, full, sizeof full));
   float dt[1000];
   std::memset(dt, 0, sizeof dt);
-  const int ds[4] = {2, 4, 8, 16};
-  for (int i = 0; i < 4; ++i) {
-    std::vector<float> v = make_decim_taps(ds[i]);
-    if ((int)v.size() != decim_ntaps(ds[i])) return fail(LTB_ERROR, "unexpected decimator tap count");
-    std::memcpy(dt + decim_tap_offset(ds[i]), v.data(), v.size() * sizeof(float));
+  {
+    std::vector<float> v = make_decim_taps(16);
+    if ((int)v.size() != decim_ntaps(16)) return fail(LTB_ERROR, "unexpected decimator tap count");
+    std::memcpy(dt + decim_tap_offset(16), v.data(), v.size() * sizeof(float));
   }
   LTB_CUDA(cudaMemcpyToSymbol(c_decim_taps, dt, sizeof dt));
   {
-    static float2 pairs[990];
+    static float2 pairs[sizeof(c_decim_pairs) / sizeof(float2)];
     std::memset(pairs, 0, sizeof pairs);
-    for (int i = 0; i < 4; ++i) {
-      const int d = ds[i], nt = decim_ntaps(d);
-      const float *tp = dt + decim_tap_offset(d);
-      for (int v = 0; v < d; ++v)
-        for (int q = 0; q < kDecQ; ++q) {
-          const int j = q * d + v;
-          const float c = j < nt ? tp[j] : 0.0f;
-          pairs[decim_pair_offset(d) + v * kDecQ + q] = make_float2(c, c);
-        }
+    for (int d = 2; d <= 12; ++d) {
+      if (!decim_is_tiled(d)) continue;
+      std::vector<float> vq = make_decim_branch_taps(d);
+      if (vq.empty()) return fail(LTB_ERROR, "unexpected decimator tap count");
+      for (int j = 0; j < d * kDecQ; ++j) pairs[decim_pair_offset(d) + j] = make_float2(vq[j], vq[j]);
     }
     LTB_CUDA(cudaMemcpyToSymbol(c_decim_pairs, pairs, sizeof pairs));
   }
@@ -109,13 +104,20 @@ int ensure_constants(int device) {
   LTB_CUDA(cudaMemcpyToSymbol(c_sss_nid1, nid, sizeof nid));
   LTB_CUDA(cudaFuncSetAttribute(pss_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(TrackShared)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_stream_kernel<LTB_FMT_FC32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_stream_smem_bytes<LTB_FMT_FC32>()));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_stream_kernel<LTB_FMT_SC16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_stream_smem_bytes<LTB_FMT_SC16>()));
   LTB_CUDA(cudaDeviceGetAttribute(&g_sm_count[device], cudaDevAttrMultiProcessorCount, device));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(8)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(8)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_FC32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(4)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_kernel<LTB_FMT_SC16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decim_smem_bytes(4)));
+#define LTB_SMEM_ATTR(kernel, bytes) LTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+#define LTB_SMEM_ATTR_FMT(FMT)                                                                  \
+  LTB_SMEM_ATTR(decimate_stream_kernel<FMT>, decim_stream_smem_bytes<FMT>());                   \
+  LTB_SMEM_ATTR(decimate_any_kernel<FMT>, decim_any_smem_bytes(kMaxDecim));                     \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 4>), decim_smem_bytes(4));                                \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 6>), decim_smem_bytes(6));                                \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 8>), decim_smem_bytes(8));                                \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 12>), decim_smem_bytes(12));
+  LTB_SMEM_ATTR_FMT(LTB_FMT_FC32)
+  LTB_SMEM_ATTR_FMT(LTB_FMT_SC16)
+  LTB_SMEM_ATTR_FMT(LTB_FMT_SC8)
+#undef LTB_SMEM_ATTR_FMT
+#undef LTB_SMEM_ATTR
   g_const_done[device] = true;
   return LTB_SUCCESS;
 }
@@ -130,17 +132,29 @@ int make_cexp_device(float2 **out) {
   return LTB_SUCCESS;
 }
 
-// ltb_debug_set_flag: [0] decimator dissection bits, [1] unused, [2] extra dynamic smem for the
-// tiled decimator (occupancy experiments), [3] unused
+// ltb_debug_set_flag: [0] decimator dissection bits, [1] bit 0: decimate with the general kernel at
+// every rate, [2] extra dynamic smem for the tiled decimator (occupancy experiments), [3] unused
 int g_debug_flags[4] = {0, 0, 0, 0};
 
-bool valid_decim(int d) { return d == 1 || d == 2 || d == 4 || d == 8 || d == 16; }
+bool valid_decim(int d) { return d >= 1 && d <= kMaxDecim; }
+bool valid_format(int f) { return f == LTB_FMT_FC32 || f == LTB_FMT_SC16 || f == LTB_FMT_SC8; }
+
+// branch-major taps [v][33] of rational_resampler_ccc(1, decim) on the device (decimate_any_kernel)
+int make_branch_taps_device(int decim, float **out) {
+  *out = nullptr;
+  if (decim < 2) return LTB_SUCCESS;
+  std::vector<float> vq = make_decim_branch_taps(decim);
+  if (vq.empty()) return fail(LTB_ERROR, "unexpected decimator tap count");
+  LTB_CUDA(cudaMalloc(out, sizeof(float) * vq.size()));
+  LTB_CUDA(cudaMemcpy(*out, vq.data(), sizeof(float) * vq.size(), cudaMemcpyHostToDevice));
+  return LTB_SUCCESS;
+}
 
 // ---- front-end launchers ---------------------------------------------------------------
 template <int FMT>
 int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams, int m, float2 *tail_old,
-                    float2 *tail_new, float2 *y_ring, long long n_base, unsigned mask, int cap,
-                    cudaStream_t st, int *launches) {
+                    float2 *tail_new, const float *branch_taps, float2 *y_ring, long long n_base, unsigned mask,
+                    int cap, cudaStream_t st, int *launches) {
   if (decim == 1) {
     int gx = (m / 2 + 255) / 256;
     if (gx > 1024) gx = 1024;
@@ -149,7 +163,8 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
     return LTB_SUCCESS;
   }
   const dim3 grid((m + kDecOut - 1) / kDecOut, n_streams);
-  if (decim == 16) {
+  const bool force_any = (g_debug_flags[1] & 1) != 0;      // parity tests: run the general kernel at every rate
+  if (decim == 16 && !force_any) {
     // streaming variant: two persistent 8-warp CTAs per SM, each a contiguous run of 256-output segments
     int dev = 0;
     LTB_CUDA(cudaGetDevice(&dev));
@@ -160,25 +175,43 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
     if (ctas > total) ctas = total;
     decimate_stream_kernel<FMT><<<(unsigned)ctas, kStrThreads, decim_stream_smem_bytes<FMT>(), st>>>(
         d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total, g_debug_flags[0]);
-    tail_kernel<FMT><<<n_streams, 256, 0, st>>>(d_iq, stride, (long long)m * decim, tail_old, tail_new);
-    *launches += 2;
-    return LTB_SUCCESS;
-  }
+  } else if (decim_is_tiled(decim) && !force_any) {
 #define LTB_DECIM_CASE(D)                                                                             \
   case D: {                                                                                           \
-    decimate_kernel<FMT, D><<<grid, 32 * decim_groups(D), decim_smem_bytes(D) + g_debug_flags[2], st>>>( \
+    decimate_kernel<FMT, D><<<grid, 32 * D, decim_smem_bytes(D) + g_debug_flags[2], st>>>(            \
         d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, n_streams, g_debug_flags[0]);           \
   } break;
-  switch (decim) {
-    LTB_DECIM_CASE(2)
-    LTB_DECIM_CASE(4)
-    LTB_DECIM_CASE(8)
-    default: return fail(LTB_ERROR_INVALID_INPUTS, "unsupported decimation");
-  }
+    switch (decim) {
+      LTB_DECIM_CASE(2)
+      LTB_DECIM_CASE(3)
+      LTB_DECIM_CASE(4)
+      LTB_DECIM_CASE(6)
+      LTB_DECIM_CASE(8)
+      LTB_DECIM_CASE(12)
+      default: return fail(LTB_ERROR_INVALID_INPUTS, "unsupported decimation");
+    }
 #undef LTB_DECIM_CASE
+  } else {
+    if (!branch_taps) return fail(LTB_ERROR, "decimator tap table missing");
+    const dim3 g2((m + kAnyOut - 1) / kAnyOut, n_streams);
+    decimate_any_kernel<FMT><<<g2, kAnyOut, decim_any_smem_bytes(decim), st>>>(
+        d_iq, stride, m, decim, branch_taps, tail_old, y_ring, n_base, mask, cap);
+  }
   tail_kernel<FMT><<<n_streams, 256, 0, st>>>(d_iq, stride, (long long)m * decim, tail_old, tail_new);
   *launches += 2;
   return LTB_SUCCESS;
+}
+
+// format dispatch
+int launch_frontend_fmt(int fmt, int decim, const void *d_iq, long long stride, int n_streams, int m, float2 *tail_old,
+                        float2 *tail_new, const float *branch_taps, float2 *y_ring, long long n_base, unsigned mask,
+                        int cap, cudaStream_t st, int *launches) {
+  switch (fmt) {
+    case LTB_FMT_FC32: return launch_frontend<LTB_FMT_FC32>(decim, d_iq, stride, n_streams, m, tail_old, tail_new, branch_taps, y_ring, n_base, mask, cap, st, launches);
+    case LTB_FMT_SC16: return launch_frontend<LTB_FMT_SC16>(decim, d_iq, stride, n_streams, m, tail_old, tail_new, branch_taps, y_ring, n_base, mask, cap, st, launches);
+    case LTB_FMT_SC8:  return launch_frontend<LTB_FMT_SC8>(decim, d_iq, stride, n_streams, m, tail_old, tail_new, branch_taps, y_ring, n_base, mask, cap, st, launches);
+    default: return fail(LTB_ERROR_INVALID_INPUTS, "unknown input format");
+  }
 }
 
 }  // namespace
@@ -224,6 +257,7 @@ struct ltb_trigger {
   float2 *d_tail[2] = {nullptr, nullptr};
   int tail_cur = 0;
   float2 *d_cexp = nullptr;
+  float *d_branch_taps = nullptr;         // [decim][33], decimate_any_kernel
   long long n_total = 0;
   std::vector<float> h_thr;
   int last_launches = 0;
@@ -254,7 +288,7 @@ void trigger_free(ltb_trigger *t) {
   cudaFree(t->d_in[0]); cudaFree(t->d_in[1]); cudaFree(t->d_y); cudaFree(t->d_p); cudaFree(t->d_state); cudaFree(t->d_avg);
   cudaFree(t->d_thr); cudaFree(t->d_sss_sym);
   cudaFree(t->d_sss_rec); cudaFree(t->d_sss_count); cudaFree(t->d_hf); cudaFree(t->d_tail[0]);
-  cudaFree(t->d_tail[1]); cudaFree(t->d_cexp);
+  cudaFree(t->d_tail[1]); cudaFree(t->d_cexp); cudaFree(t->d_branch_taps);
   for (auto &sl : t->slot) {
     cudaFree(sl.d_recs); cudaFree(sl.d_rec_count);
     if (sl.h_recs) cudaFreeHost(sl.h_recs);
@@ -283,13 +317,8 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   const long long n_base = t->n_total;
   int launches = 0;
   LTB_CUDA(cudaEventRecord(sl.ev0, t->stream));
-  int rc;
-  if (c.input_format == LTB_FMT_FC32)
-    rc = launch_frontend<LTB_FMT_FC32>(c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
-                                       t->d_y, n_base, t->cap_mask, t->cap, t->stream, &launches);
-  else
-    rc = launch_frontend<LTB_FMT_SC16>(c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
-                                       t->d_y, n_base, t->cap_mask, t->cap, t->stream, &launches);
+  int rc = launch_frontend_fmt(c.input_format, c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
+                               t->d_branch_taps, t->d_y, n_base, t->cap_mask, t->cap, t->stream, &launches);
   if (rc) return rc;
   if (c.decim > 1) t->tail_cur ^= 1;
   LTB_CUDA(cudaEventRecord(sl.ev_k[0], t->stream));
@@ -358,7 +387,7 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
     return fail(LTB_ERROR_INVALID_INPUTS, "bad config pointer or struct_size");
   *out = nullptr;
   ltb_trigger_config c = *cfg;
-  if (c.n_streams <= 0 || !valid_decim(c.decim) || (c.input_format != LTB_FMT_FC32 && c.input_format != LTB_FMT_SC16) ||
+  if (c.n_streams <= 0 || !valid_decim(c.decim) || !valid_format(c.input_format) ||
       c.max_chunk <= 0 || (c.root_mask & ~7))
     return fail(LTB_ERROR_INVALID_INPUTS, "invalid trigger configuration");
   if (c.root_mask == 0) c.root_mask = 7;
@@ -397,7 +426,7 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
     LTB_CUDA_T(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) LTB_CUDA_T(cudaEventCreate(&sl.ev_k[i]));
   }
-  t->d_in_stride = (size_t)c.max_chunk * (c.input_format == LTB_FMT_FC32 ? 8 : 4);
+  t->d_in_stride = (size_t)c.max_chunk * fmt_bytes(c.input_format);
   LTB_CUDA_T(cudaMalloc(&t->d_y, sizeof(float2) * (size_t)S * t->cap));
   LTB_CUDA_T(cudaMalloc(&t->d_p, sizeof(float) * (size_t)S * 3 * t->cap));
   LTB_CUDA_T(cudaMalloc(&t->d_state, sizeof(ChainState) * t->n_chains));
@@ -422,6 +451,7 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   }
 #undef LTB_CUDA_T
   rc = make_cexp_device(&t->d_cexp);
+  if (!rc) rc = make_branch_taps_device(c.decim, &t->d_branch_taps);
   if (!rc) rc = trigger_zero_state(t);
   if (rc) { trigger_free(t); return rc; }
   *out = t;
@@ -511,7 +541,7 @@ int ltb_trigger_submit_host(ltb_trigger *t, const void *iq, int64_t stride, int6
   // collected (at most two in flight), so its front end is done with it
   const int slot = (t->head + t->n_pending) & 1;
   if (!t->d_in[slot]) LTB_CUDA(cudaMalloc(&t->d_in[slot], t->d_in_stride * (size_t)t->cfg.n_streams));
-  const size_t row = (size_t)n_samples * (t->cfg.input_format == LTB_FMT_FC32 ? 8 : 4);
+  const size_t row = (size_t)n_samples * fmt_bytes(t->cfg.input_format);
   LTB_CUDA(cudaMemcpy2DAsync(t->d_in[slot], t->d_in_stride, iq, (size_t)stride, row, (size_t)t->cfg.n_streams,
                              cudaMemcpyHostToDevice, t->in_stream));
   LTB_CUDA(cudaEventRecord(t->in_ready[slot], t->in_stream));
@@ -685,7 +715,7 @@ int ltb_kernel_pss_corr_host(int device, const ltb_cf *x, int n_streams, int64_t
 }
 
 int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in, int decim, ltb_cf *y) {
-  if (!x || !y || n_streams <= 0 || n_in <= 0 || !valid_decim(decim) || (n_in % decim) != 0 || (fmt != LTB_FMT_FC32 && fmt != LTB_FMT_SC16))
+  if (!x || !y || n_streams <= 0 || n_in <= 0 || !valid_decim(decim) || (n_in % decim) != 0 || !valid_format(fmt))
     return fail(LTB_ERROR_INVALID_INPUTS, "bad decimate arguments");
   if (ltb_device_count() <= device || device < 0) return fail(LTB_ERROR, "no such CUDA device");
   LTB_CUDA(cudaSetDevice(device));
@@ -693,8 +723,11 @@ int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, 
   if (rc) return rc;
   const int m = (int)(n_in / decim);
   const int cap = next_pow2(m + 8);
-  const size_t in_row = (size_t)n_in * (fmt == LTB_FMT_FC32 ? 8 : 4);
+  const size_t in_row = (size_t)n_in * fmt_bytes(fmt);
   void *d_in = nullptr; float2 *d_y = nullptr, *d_t0 = nullptr, *d_t1 = nullptr;
+  float *d_bt = nullptr;
+  rc = make_branch_taps_device(decim, &d_bt);
+  if (rc) return rc;
   cudaError_t e = cudaMalloc(&d_in, in_row * n_streams);
   if (e == cudaSuccess) e = cudaMalloc(&d_y, sizeof(float2) * (size_t)n_streams * cap);
   if (e == cudaSuccess) e = cudaMalloc(&d_t0, sizeof(float2) * (size_t)n_streams * kTailCap);
@@ -703,12 +736,11 @@ int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, 
   if (e == cudaSuccess) e = cudaMemcpy(d_in, x, in_row * n_streams, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     int launches = 0;
-    if (fmt == LTB_FMT_FC32) rc = launch_frontend<LTB_FMT_FC32>(decim, d_in, (long long)in_row, n_streams, m, d_t0, d_t1, d_y, 0, (unsigned)(cap - 1), cap, 0, &launches);
-    else rc = launch_frontend<LTB_FMT_SC16>(decim, d_in, (long long)in_row, n_streams, m, d_t0, d_t1, d_y, 0, (unsigned)(cap - 1), cap, 0, &launches);
+    rc = launch_frontend_fmt(fmt, decim, d_in, (long long)in_row, n_streams, m, d_t0, d_t1, d_bt, d_y, 0, (unsigned)(cap - 1), cap, 0, &launches);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy2D(y, sizeof(float2) * (size_t)m, d_y, sizeof(float2) * (size_t)cap, sizeof(float2) * (size_t)m, n_streams, cudaMemcpyDeviceToHost);
-  cudaFree(d_in); cudaFree(d_y); cudaFree(d_t0); cudaFree(d_t1);
+  cudaFree(d_in); cudaFree(d_y); cudaFree(d_t0); cudaFree(d_t1); cudaFree(d_bt);
   if (e != cudaSuccess) return fail(LTB_ERROR, std::string("ltb_kernel_decimate_host: ") + cudaGetErrorString(e));
   return rc;
 }

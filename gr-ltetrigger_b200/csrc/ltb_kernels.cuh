@@ -26,15 +26,24 @@ constexpr int kNLag = LTB_CONV_LEN;        // 9726
 constexpr int kAvgLen = 9732;              // 9729 used (fft+frame+1), padded to 16 B
 constexpr int kLookahead = LTB_LOOKAHEAD;  // 18365
 constexpr int kMavg = LTB_MOVING_AVG_SZ;   // 200
-constexpr int kMaxDecimTaps = 528;         // 525 for D=16
-constexpr int kTailCap = 528;              // decimator history kept per stream (input samples)
+constexpr int kMaxDecim = 64;              // rational_resampler_ccc(1, D) for D = 1..64
+constexpr int kTailCap = 33 * kMaxDecim;   // decimator history kept per stream (input samples)
+
+// input formats: bytes per complex sample and the scale applied on conversion to float
+__host__ __device__ constexpr int fmt_bytes(int fmt) { return fmt == LTB_FMT_FC32 ? 8 : fmt == LTB_FMT_SC16 ? 4 : 2; }
+__host__ __device__ constexpr float fmt_scale(int fmt) {
+  return fmt == LTB_FMT_SC16 ? 1.0f / 32768.0f : fmt == LTB_FMT_SC8 ? 1.0f / 128.0f : 1.0f;
+}
+template <int FMT> struct fmt_elem { typedef float2 type; };
+template <> struct fmt_elem<LTB_FMT_SC16> { typedef short2 type; };
+template <> struct fmt_elem<LTB_FMT_SC8> { typedef char2 type; };
 
 // folded matched-filter coefficients, group 0 = root 25, group 1 = root 29 (root 34 = conj):
 //   [g][m][0] = (hr, hi)   [g][m][1] = (hi, hr)      m = 0..64
 __constant__ float2 c_pss_coef[2][65][2];
 // full 128-tap filters per N_id_2 (CFO estimate): (re, im)
 __constant__ float2 c_pss_taps[3][128];
-// decimator taps for D = 2, 4, 8, 16 at offsets 0, 72, 208, 472 (padded with zeros)
+// decimator taps for D = 16 at offset 472 (padded with zeros): decimate_stream_kernel
 __constant__ float c_decim_taps[1000];
 __constant__ float2 c_fft128_tw[64];
 // SSS tables per N_id_2: c0, c1 (31 each); shared s_tilde, z_tilde; N_id_1 table
@@ -154,9 +163,14 @@ __global__ void __launch_bounds__(256) ingest_kernel(const void *__restrict__ in
     float4 v;
     if (FMT == LTB_FMT_FC32) {
       v = *reinterpret_cast<const float4 *>(src + (size_t)i * 8);
-    } else {
+    } else if (FMT == LTB_FMT_SC16) {
       const short4 s = *reinterpret_cast<const short4 *>(src + (size_t)i * 4);
-      const float k = 1.0f / 32768.0f;
+      const float k = fmt_scale(FMT);
+      v = make_float4(__fmul_rn((float)s.x, k), __fmul_rn((float)s.y, k), __fmul_rn((float)s.z, k),
+                      __fmul_rn((float)s.w, k));
+    } else {
+      const char4 s = *reinterpret_cast<const char4 *>(src + (size_t)i * 2);
+      const float k = fmt_scale(FMT);
       v = make_float4(__fmul_rn((float)s.x, k), __fmul_rn((float)s.y, k), __fmul_rn((float)s.z, k),
                       __fmul_rn((float)s.w, k));
     }
@@ -171,8 +185,9 @@ __global__ void __launch_bounds__(256) ingest_kernel(const void *__restrict__ in
 template <int FMT>
 __device__ __forceinline__ float2 load_in_sample(const char *src, long long idx) {
   if (FMT == LTB_FMT_FC32) return *reinterpret_cast<const float2 *>(src + idx * 8);
-  const short2 s = *reinterpret_cast<const short2 *>(src + idx * 4);
-  const float k = 1.0f / 32768.0f;
+  typedef typename fmt_elem<FMT>::type raw_t;
+  const raw_t s = *reinterpret_cast<const raw_t *>(src + idx * fmt_bytes(FMT));
+  const float k = fmt_scale(FMT);
   return make_float2(__fmul_rn((float)s.x, k), __fmul_rn((float)s.y, k));
 }
 
@@ -183,14 +198,14 @@ __device__ __forceinline__ float2 load_in_sample(const char *src, long long idx)
 // (taps beyond ntaps are zeros) in one chain per component; the D partials are then summed by the
 // balanced pairwise tree  ((P0+P1)+(P2+P3)) + ((P4+P5)+(P6+P7)) ...
 //
-// decimate_kernel (D = 2, 4, 8): one CTA = 512 outputs of one stream, one warp per position, 16
+// decimate_kernel (D = 2, 3, 4, 6, 8, 12): one CTA = 512 outputs of one stream, one warp per position, 16
 // consecutive outputs per lane.  The (512+32) blocks x D positions the tile needs are staged once
 // in shared memory, row = position, 16-way de-interleaved in the block index so that the element
 // a warp needs at one step (block 32 + 16*lane + e) is 32 consecutive float2: a conflict-free
 // LDS.64.  The staging copies are 8-byte cp.async (LDGSTS) that write straight into that layout.
 // Each lane slides a 16-sample register window down one block per tap: 1 LDS.64 + 1 coefficient
 // load per 16 FFMA2, both issued kDecPF steps ahead of their use.  D = 16 has its own kernel
-// (decimate_stream_kernel below).
+// (decimate_stream_kernel below); the remaining rates run decimate_any_kernel.
 constexpr int kDecT = 16;                        // outputs per lane
 constexpr int kDecOut = 32 * kDecT;              // 512 outputs per tile
 constexpr int kDecQ = 33;                        // taps per polyphase branch (zero padded)
@@ -198,24 +213,28 @@ constexpr int kDecGroups = kDecOut + kDecQ - 1;  // 544 blocks per position row
 constexpr int kDecSub = kDecGroups / 16;         // 34 columns per sub-row
 constexpr int kDecRow = kDecGroups + 1;          // 545 float2: odd stride -> conflict-free fill
 constexpr int kDecPF = 3;                        // software prefetch distance (taps)
-// (c, c) coefficient pairs per D at offsets 0 (D=2), 66 (D=4), 198 (D=8), 462 (D=16): [v][33]
-__constant__ float2 c_decim_pairs[990];
-__host__ __device__ constexpr int decim_pair_offset(int d) { return d == 2 ? 0 : d == 4 ? 66 : d == 8 ? 198 : 462; }
-__host__ __device__ constexpr int decim_groups(int d) { return d > 8 ? 8 : d; }   // one warp per position (D <= 8)
+// (c, c) coefficient pairs [v][33] of the tiled kernel's rates D = 2, 3, 4, 6, 8, 12, back to back
+__constant__ float2 c_decim_pairs[33 * (2 + 3 + 4 + 6 + 8 + 12)];
+__host__ __device__ constexpr bool decim_is_tiled(int d) { return d == 2 || d == 3 || d == 4 || d == 6 || d == 8 || d == 12; }
+__host__ __device__ constexpr int decim_pair_offset(int d) {
+  return kDecQ * (d == 2 ? 0 : d == 3 ? 2 : d == 4 ? 5 : d == 6 ? 9 : d == 8 ? 15 : 23);
+}
+__host__ __device__ constexpr int decim_pow2(int d) { int p = 1; while (p < d) p <<= 1; return p; }
+__host__ __device__ constexpr int decim_min_ctas(int d) { return d <= 4 ? 4 : 2; }
 __host__ __device__ constexpr size_t decim_smem_bytes(int d) { return sizeof(float2) * (size_t)d * kDecRow; }
 
 template <int FMT, int D>
-__global__ void __launch_bounds__(32 * decim_groups(D), D == 8 ? 2 : 4)
+__global__ void __launch_bounds__(32 * D, decim_min_ctas(D))
 decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
                 float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int n_streams, int dbg) {
-  constexpr int G = decim_groups(D);
-  constexpr int PW = D / G;                       // positions per warp
+  constexpr int G = D;                            // one warp per position
+  constexpr int PW = 1;
   constexpr int NTHR = 32 * G;
   constexpr int POFF = decim_pair_offset(D);
-  constexpr int ITER = kDecGroups * D / NTHR;     // 68 / 34 / 17 / 17 for D = 16 / 8 / 4 / 2
-  constexpr int BSTEP = NTHR / D;                 // blocks advanced per fill iteration: 8 / 16 / 32 / 32
+  constexpr int ITER = kDecGroups * D / NTHR;     // 17
+  constexpr int BSTEP = NTHR / D;                 // blocks advanced per fill iteration: 32
   static_assert((kDecGroups * D) % NTHR == 0 && NTHR % D == 0, "tile geometry");
-  static_assert(G == D && PW == 1, "one warp per position: D <= 8 (D = 16 uses decimate_stream_kernel)");
+  static_assert(decim_is_tiled(D), "D = 16 uses decimate_stream_kernel, other rates decimate_any_kernel");
   extern __shared__ __align__(16) float2 s_x[];   // [D][kDecRow]
   const int stream = blockIdx.y;
   const int k0 = blockIdx.x * kDecOut;
@@ -242,11 +261,12 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
         }
         cp_async_wait_all();
       } else {
-        const short2 *gp = reinterpret_cast<const short2 *>(src) + i0;
-        const float k = 1.0f / 32768.0f;
+        typedef typename fmt_elem<FMT>::type raw_t;
+        const raw_t *gp = reinterpret_cast<const raw_t *>(src) + i0;
+        const float k = fmt_scale(FMT);
 #pragma unroll
         for (int b0 = 0; b0 < ITER; b0 += 17) {
-          short2 raw[17];
+          raw_t raw[17];
 #pragma unroll
           for (int u = 0; u < 17; ++u) raw[u] = __ldg(gp + (long long)NTHR * (b0 + u));
 #pragma unroll
@@ -322,13 +342,14 @@ decimate_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, 
   __syncthreads();
   for (int i = threadIdx.x; i < kDecOut; i += NTHR) {
     const int o = i & 15, ln = i >> 4;
-    float2 pp[G];
+    constexpr int P2 = decim_pow2(G);                   // D not a power of two: zero partials pad the tree
+    float2 pp[P2];
 #pragma unroll
-    for (int gg = 0; gg < G; ++gg) pp[gg] = part[(gg * kDecT + o) * 33 + ln];
+    for (int gg = 0; gg < P2; ++gg) pp[gg] = gg < G ? part[(gg * kDecT + o) * 33 + ln] : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int w2 = 1; w2 < G; w2 <<= 1) {                // pairwise tree: (P0+P1)+(P2+P3), ...
+    for (int w2 = 1; w2 < P2; w2 <<= 1) {               // pairwise tree: (P0+P1)+(P2+P3), ...
 #pragma unroll
-      for (int gg = 0; gg < G; gg += 2 * w2) pp[gg] = fadd2(pp[gg], pp[gg + w2]);
+      for (int gg = 0; gg < P2; gg += 2 * w2) pp[gg] = fadd2(pp[gg], pp[gg + w2]);
     }
     const int k = k0 + i;
     if (k < n_out) y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = pp[0];
@@ -367,7 +388,7 @@ constexpr int kStrBufs = 2;
 constexpr int kStrScratchRow = 9;                     // float2 per (half, position) row: 8 outputs + 1 pad
 constexpr int kStrScratch = 2 * 16 * kStrScratchRow;  // float2 per warp
 
-template <int FMT> __host__ __device__ constexpr int str_buf_bytes() { return kStrBlocks * 16 * (FMT == LTB_FMT_FC32 ? 8 : 4); }
+template <int FMT> __host__ __device__ constexpr int str_buf_bytes() { return kStrBlocks * 16 * fmt_bytes(FMT); }
 template <int FMT> __host__ __device__ constexpr size_t decim_stream_smem_bytes() {
   return (size_t)kStrBufs * str_buf_bytes<FMT>() + sizeof(float2) * kStrScratch * kStrWarps;
 }
@@ -401,9 +422,10 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
                        float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int segs_per_stream,
                        int total_segs, int dbg) {
   constexpr int D = 16;
-  constexpr int BPS = FMT == LTB_FMT_FC32 ? 8 : 4;                 // bytes per input sample
+  constexpr int BPS = fmt_bytes(FMT);                              // bytes per input sample
   constexpr int BUF = str_buf_bytes<FMT>();
-  typedef typename std::conditional<FMT == LTB_FMT_FC32, float2, short2>::type elem_t;
+  static_assert(BUF % 16 == 0, "cp.async.bulk size");
+  typedef typename fmt_elem<FMT>::type elem_t;
   extern __shared__ __align__(128) unsigned char s_raw[];          // [kStrBufs][289 blocks][16 positions], scratch
   __shared__ __align__(8) unsigned long long s_full[kStrBufs];
   __shared__ unsigned s_done[kStrBufs];                            // warps finished with a buffer (monotonic)
@@ -423,15 +445,15 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
   __syncthreads();
 
   // this lane's taps: position p <-> polyphase branch v = (16 - p) % 16, c[q] = taps[16 q + v]
-  // (sc16: the 1/32768 input scale is folded into the taps; both products are exact, so
-  //  fma(c * 2^-15, s, acc) == fma(c, s * 2^-15, acc) bit for bit)
+  // (sc16 / sc8: the 2^-15 / 2^-7 input scale is folded into the taps; both products are exact,
+  //  so fma(c * 2^-15, s, acc) == fma(c, s * 2^-15, acc) bit for bit)
   float c[kDecQ];
   {
     const int v = (D - p) % D;
 #pragma unroll
     for (int q = 0; q < kDecQ; ++q) {
       const float t = c_decim_taps[decim_tap_offset(D) + q * D + v];   // zero padded beyond ntaps
-      c[q] = FMT == LTB_FMT_FC32 ? t : __fmul_rn(t, 1.0f / 32768.0f);
+      c[q] = FMT == LTB_FMT_FC32 ? t : __fmul_rn(t, fmt_scale(FMT));
       // keep the 33 taps in registers: without this the compiler re-reads them from the constant
       // bank inside the FMA loop, and a lane-indexed LDC replays once per distinct address
       asm volatile("" : "+f"(c[q]));
@@ -483,7 +505,8 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
         if (idx >= 0) { if (idx < n_in) val = load_in_sample<FMT>(src, idx); }
         else if (idx >= -kTailCap) val = tail[kTailCap + idx];
         if (FMT == LTB_FMT_FC32) reinterpret_cast<float2 *>(buf)[j] = val;
-        else reinterpret_cast<short2 *>(buf)[j] = make_short2((short)__fmul_rn(val.x, 32768.0f), (short)__fmul_rn(val.y, 32768.0f));
+        else if (FMT == LTB_FMT_SC16) reinterpret_cast<short2 *>(buf)[j] = make_short2((short)__fmul_rn(val.x, 32768.0f), (short)__fmul_rn(val.y, 32768.0f));
+        else reinterpret_cast<char2 *>(buf)[j] = make_char2((signed char)__fmul_rn(val.x, 128.0f), (signed char)__fmul_rn(val.y, 128.0f));
       }
       __syncthreads();
     }
@@ -498,7 +521,7 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
       const elem_t *base = buf + lane_elem;
       auto ld = [&](int e) -> float2 {                             // element e of the window
         if (FMT == LTB_FMT_FC32) return reinterpret_cast<const float2 *>(base)[e * 16];
-        const short2 r = reinterpret_cast<const short2 *>(base)[e * 16];
+        const elem_t r = base[e * 16];
         return make_float2((float)r.x, (float)r.y);
       };
       constexpr int PF = 4;                                        // elements loaded ahead of their use
@@ -561,6 +584,74 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
     }
     advance(cur);
   }
+}
+
+// ------------------------------------------------------------------------------------
+// K1a: decimator for every other integer rate (D = 5, 7, 9..11, 13..15, 17..64): the reference
+// accepts any multiple of 1.92 Msps (examples/cell_search_file.py:50-57).  One CTA = 256 outputs
+// of one stream, one output per thread.  The 289 input blocks are staged transposed (row =
+// position, odd row stride) so that the lanes of a warp read consecutive float2 for every tap;
+// the branch taps [v][33] come from a per-rate table in global memory and sit in shared memory
+// (broadcast reads).  Same canonical order: one fma chain per position over q ascending, then the
+// balanced pairwise tree over the partials padded with zeros to a power of two, evaluated with a
+// binary-counter stack so that no partial has to be kept.
+// ------------------------------------------------------------------------------------
+constexpr int kAnyOut = 256;
+constexpr int kAnyBlocks = kAnyOut + kDecQ;           // 289
+__host__ __device__ constexpr size_t decim_any_smem_bytes(int d) {
+  return sizeof(float2) * (size_t)d * kAnyBlocks + sizeof(float) * (size_t)d * kDecQ;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kAnyOut)
+decimate_any_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, int D, const float *__restrict__ taps_vq,
+                    const float2 *__restrict__ tail_in, float2 *__restrict__ y_ring, long long n_base,
+                    unsigned cap_mask, int cap) {
+  extern __shared__ __align__(16) float2 s_any[];     // [D][289] samples, then [D][33] taps
+  float *s_taps = reinterpret_cast<float *>(s_any + (size_t)D * kAnyBlocks);
+  const int stream = blockIdx.y, t = threadIdx.x;
+  const int k0 = blockIdx.x * kAnyOut;
+  const char *src = (const char *)in + (long long)stream * stride_bytes;
+  const float2 *tail = tail_in + (size_t)stream * kTailCap;
+  const long long n_in = (long long)n_out * D;
+  const long long i_first = (long long)D * (k0 - kDecQ);
+  for (int j = t; j < D * kDecQ; j += kAnyOut) s_taps[j] = taps_vq[j];
+  for (int j = t; j < D * kAnyBlocks; j += kAnyOut) {
+    const long long idx = i_first + j;
+    float2 val = make_float2(0.f, 0.f);
+    if (idx >= 0) { if (idx < n_in) val = load_in_sample<FMT>(src, idx); }
+    else if (idx >= -kTailCap) val = tail[kTailCap + idx];
+    const int b = j / D, p = j - b * D;
+    s_any[p * kAnyBlocks + b] = val;
+  }
+  __syncthreads();
+  int P2 = 1;
+  while (P2 < D) P2 <<= 1;
+  float2 stk[7], val = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int p = 0; p < P2; ++p) {
+    val = make_float2(0.f, 0.f);
+    if (p < D) {
+      // X[k - q - (p > 0)][p], block index relative to k0 - 33
+      const float2 *row = s_any + p * kAnyBlocks + t + kDecQ - (p > 0 ? 1 : 0);
+      const float *cf = s_taps + ((D - p) % D) * kDecQ;
+#pragma unroll
+      for (int q = 0; q < kDecQ; ++q) {
+        const float c = cf[q];
+        val = ffma2(make_float2(c, c), row[-q], val);
+      }
+    }
+    bool merging = true;                              // (P0+P1)+(P2+P3) ... : carry chain of p + 1
+#pragma unroll
+    for (int l = 0; l < 7; ++l) {
+      if (merging) {
+        if ((p >> l) & 1) val = fadd2(stk[l], val);
+        else { stk[l] = val; merging = false; }
+      }
+    }
+  }
+  const int k = k0 + t;
+  if (k < n_out) y_ring[(size_t)stream * cap + (unsigned)((n_base + k) & cap_mask)] = val;
 }
 
 // keep the last kTailCap converted input samples of each stream for the next call

@@ -112,6 +112,19 @@ std::vector<float> make_decim_taps(int decim) {
   return taps;
 }
 
+std::vector<float> make_decim_branch_taps(int decim) {
+  const int Q = 33;
+  const std::vector<float> taps = make_decim_taps(decim);
+  if (decim < 2 || (int)taps.size() > Q * decim) return std::vector<float>();
+  std::vector<float> out((size_t)decim * Q, 0.0f);
+  for (int v = 0; v < decim; ++v)
+    for (int q = 0; q < Q; ++q) {
+      const int j = q * decim + v;
+      if (j < (int)taps.size()) out[(size_t)v * Q + q] = taps[j];
+    }
+  return out;
+}
+
 void make_sss_tables(int n_id_2, SssTables &out) {
   int c_tilde[31];
   const int s_taps[2] = {2, 0}, c_taps[2] = {3, 0}, z_taps[4] = {4, 2, 1, 0};

@@ -13,6 +13,9 @@ void make_pss_taps(int n_id_2, PssTaps &out);
 
 // gr-filter rational_resampler.design_filter(1, decim, 0.4) -> firdes.low_pass(Kaiser, beta 7)
 std::vector<float> make_decim_taps(int decim);
+// the same taps by polyphase branch, zero padded: out[v * 33 + q] = taps[q * decim + v]; empty if
+// a branch would need more than 33 taps (never for decim <= 64)
+std::vector<float> make_decim_branch_taps(int decim);
 
 struct SssTables {
   int32_t c0[31], c1[31], s_tilde[31], z_tilde[31];

@@ -16,7 +16,10 @@ LIB_PATH = os.environ.get("LTB200_LIB") or os.path.join(ROOT, "lib", "libltetrig
 
 SUCCESS, ERROR, ERROR_INVALID_INPUTS = 0, -1, -2
 SLOT_LEN, HALF_FRAME, SYMBOL_SZ, CONV_LEN, LOOKAHEAD = 960, 9600, 128, 9726, 18365
-FMT_FC32, FMT_SC16 = 0, 1
+FMT_FC32, FMT_SC16, FMT_SC8 = 0, 1, 2
+MAX_DECIM = 64
+FMT_BYTES = {FMT_FC32: 8, FMT_SC16: 4, FMT_SC8: 2}
+FMT_DTYPE = {FMT_FC32: np.complex64, FMT_SC16: np.int16, FMT_SC8: np.int8}
 MIN_PSR_THRESHOLD = 1.5
 F_SEARCHED, F_OVER, F_EMIT, F_TRACKING, F_TAG_LOST, F_SSS, F_CELL, F_CP_NORM = (
     0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80)

@@ -48,15 +48,12 @@ class Trigger:
                 "ltb_trigger_set_psr_threshold")
 
     def _bytes_per_sample(self):
-        return 8 if self.input_format == A.FMT_FC32 else 4
+        return A.FMT_BYTES[self.input_format]
 
     def process(self, iq):
-        """iq: host array [n_streams, n] complex64 (fc32) or [n_streams, n, 2] int16 (sc16).
-        Returns the window records of this chunk as a WINDOW_REC array."""
-        if self.input_format == A.FMT_FC32:
-            iq = np.ascontiguousarray(iq, np.complex64)
-        else:
-            iq = np.ascontiguousarray(iq, np.int16)
+        """iq: host array [n_streams, n] complex64 (fc32), [n_streams, n, 2] int16 (sc16) or int8
+        (sc8).  Returns the window records of this chunk as a WINDOW_REC array."""
+        iq = np.ascontiguousarray(iq, A.FMT_DTYPE[self.input_format])
         assert iq.shape[0] == self.n_streams
         n = iq.shape[1]
         nrec = C.c_int32(0)
@@ -140,7 +137,7 @@ def kernel_decimate(x, decim, fmt=A.FMT_FC32, device=0):
     if fmt == A.FMT_FC32:
         x = np.ascontiguousarray(np.atleast_2d(x), np.complex64)
     else:
-        x = np.ascontiguousarray(x, np.int16)
+        x = np.ascontiguousarray(x, A.FMT_DTYPE[fmt])
     s, n = x.shape[0], x.shape[1]
     y = np.zeros((s, n // decim), np.complex64)
     A.check(A.lib().ltb_kernel_decimate_host(device, x.ctypes.data, fmt, s, n, decim, y.ctypes.data),
@@ -159,8 +156,8 @@ class tables:
 
     @staticmethod
     def decim_taps(decim):
-        t = np.zeros(1024, np.float32)
-        n = A.lib().ltb_table_decim_taps(decim, A.fptr(t), 1024)
+        t = np.zeros(4096, np.float32)
+        n = A.lib().ltb_table_decim_taps(decim, A.fptr(t), 4096)
         if n < 0:
             raise A.LtbError("ltb_table_decim_taps failed")
         return t[:n].copy()

@@ -1,7 +1,7 @@
 """Seeded synthetic LTE FDD downlink captures (BASELINE config C4/C5).
 
-Normal-CP frames with the 36.211 PSS (last symbol of slots 0 and 10) and SSS (the symbol
-before it, SF0/SF5 variants) on the 62 centre carriers and unit-power QPSK on every other
+Normal-CP (or, with ext_cp, extended-CP) frames with the 36.211 PSS (last symbol of slots 0
+and 10) and SSS (the symbol before it, SF0/SF5 variants) on the 62 centre carriers and unit-power QPSK on every other
 occupied resource element, OFDM-modulated at 128*decim points (1.92*decim Msps), cut at a
 random timing offset, with complex AWGN at a requested SNR and an optional carrier offset.
 Models examples/snr_ltetrigger.grc (fixture x gain + Gaussian noise) of the reference.
@@ -52,14 +52,19 @@ def sss_freq(cell_id, subframe):
     return d
 
 
-def lte_frame(cell_id, decim=1, rng=None, n_frames=1):
-    """n_frames radio frames (19200*decim samples each) at 1.92*decim Msps, mean power ~1."""
+N_USED = {1: 72, 2: 180, 4: 300, 8: 600, 12: 900, 16: 1200}
+
+
+def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False):
+    """n_frames radio frames (19200*decim samples each) at 1.92*decim Msps, mean power ~1.
+    ext_cp: 6 symbols per slot with a 32*decim-sample prefix (36.211 table 6.12-1)."""
     rng = rng or np.random.default_rng(cell_id)
     nfft = 128 * decim
-    n_used = {1: 72, 2: 180, 4: 300, 8: 600, 16: 1200}[decim]
+    n_used = N_USED.get(decim, 12 * (6 * decim - decim // 2))
     half = n_used // 2
-    cp0, cp = 10 * decim, 9 * decim
-    nsym = 140 * n_frames
+    cp0, cp = (32 * decim, 32 * decim) if ext_cp else (10 * decim, 9 * decim)
+    per_slot = 6 if ext_cp else 7
+    nsym = 20 * per_slot * n_frames
     bits = rng.integers(0, 2, size=(nsym, n_used, 2)) * 2 - 1
     qpsk = (bits[..., 0] + 1j * bits[..., 1]) / np.sqrt(2.0)
     grid = np.zeros((nsym, nfft), np.complex128)
@@ -68,7 +73,7 @@ def lte_frame(cell_id, decim=1, rng=None, n_frames=1):
     pss = pss_freq(cell_id % 3)
     for f in range(n_frames):
         for slot, sf in ((0, 0), (10, 5)):
-            sym_pss = f * 140 + slot * 7 + 6
+            sym_pss = (f * 20 + slot) * per_slot + per_slot - 1
             sym_sss = sym_pss - 1
             for sym, seq in ((sym_pss, pss), (sym_sss, sss_freq(cell_id, sf))):
                 grid[sym, 1:37] = 0
@@ -79,7 +84,7 @@ def lte_frame(cell_id, decim=1, rng=None, n_frames=1):
     out = np.empty(n_frames * 19200 * decim, np.complex128)
     pos = 0
     for s in range(nsym):
-        c = cp0 if s % 7 == 0 else cp
+        c = cp0 if s % per_slot == 0 else cp
         out[pos:pos + c] = time[s, nfft - c:]
         out[pos + c:pos + c + nfft] = time[s]
         pos += c + nfft
@@ -87,7 +92,8 @@ def lte_frame(cell_id, decim=1, rng=None, n_frames=1):
     return out
 
 
-def capture(cell_id, n_samples, snr_db=None, decim=1, seed=0, offset=None, cfo_hz=0.0, noise_only=False):
+def capture(cell_id, n_samples, snr_db=None, decim=1, seed=0, offset=None, cfo_hz=0.0, noise_only=False,
+            ext_cp=False):
     """One capture of n_samples at 1.92*decim Msps as complex64."""
     rng = np.random.default_rng([seed, cell_id, 0x5EED])
     frame_len = 19200 * decim
@@ -96,7 +102,7 @@ def capture(cell_id, n_samples, snr_db=None, decim=1, seed=0, offset=None, cfo_h
     n_frames = (offset + n_samples + frame_len - 1) // frame_len
     # a few distinct frames tiled keeps generation cheap while payload still varies
     uniq = min(n_frames, 4)
-    base = lte_frame(cell_id, decim, rng, uniq)
+    base = lte_frame(cell_id, decim, rng, uniq, ext_cp)
     reps = (n_frames + uniq - 1) // uniq
     sig = np.tile(base, reps)[offset:offset + n_samples]
     if cfo_hz:
@@ -119,6 +125,15 @@ def batch(n_streams, n_samples, snr_db, decim=1, master_seed=1234, cell_ids=None
     for i in range(n_streams):
         out[i] = capture(int(ids[i]), n_samples, snr_db, decim, seed=master_seed ^ i)
     return out, ids
+
+
+def to_sc8(x, full_scale=4.0):
+    """Quantise complex64 to interleaved int8 (I, Q) with |x| = full_scale -> 127."""
+    s = 127.0 / full_scale
+    iq = np.empty(x.shape + (2,), np.int8)
+    iq[..., 0] = np.clip(np.round(x.real * s), -128, 127)
+    iq[..., 1] = np.clip(np.round(x.imag * s), -128, 127)
+    return iq
 
 
 def to_sc16(x, full_scale=4.0):

@@ -43,6 +43,8 @@ extern "C" {
 /* input sample formats (little-endian interleaved I/Q) */
 #define LTB_FMT_FC32 0             /* gr_complex, 8 B/sample: what the reference consumes */
 #define LTB_FMT_SC16 1             /* int16 I/Q, 4 B/sample, scaled by 1/32768 on device */
+#define LTB_FMT_SC8  2             /* int8 I/Q, 2 B/sample, scaled by 1/128 on device */
+#define LTB_MAX_DECIM 64
 
 typedef struct { float re, im; } ltb_cf;
 
@@ -105,7 +107,9 @@ typedef struct {
   int32_t  device;            /* CUDA device ordinal */
   int32_t  n_streams;
   int32_t  input_format;      /* LTB_FMT_* */
-  int32_t  decim;             /* input rate / 1.92 Msps: 1, 2, 4, 8 or 16 */
+  int32_t  decim;             /* input rate / 1.92 Msps, any integer 1..LTB_MAX_DECIM as the reference's
+                                 CLI accepts (examples/cell_search_file.py:50-57); tuned kernels for the
+                                 LTE rates 2, 4, 8, 12, 16 (and 3, 6) */
   int32_t  root_mask;         /* bit k set: run the N_id_2 = k chain; 0 -> 7 (all three) */
   int64_t  max_chunk;         /* largest n_samples (input rate, per stream) of one process call */
   float    psr_threshold;     /* clamped to > 1.5 like downlink_trigger_c.py:71-73 */

@@ -168,21 +168,36 @@ void orc_sc16_to_fc32(const int16_t *iq, int64_t n, float scale, orc_cf *out)
   }
 }
 
+void orc_sc8_to_fc32(const int8_t *iq, int64_t n, float scale, orc_cf *out)
+{
+  for (int64_t i = 0; i < n; i++) {
+    out[i].re = (float)iq[2 * i] * scale;
+    out[i].im = (float)iq[2 * i + 1] * scale;
+  }
+}
+
 /* rational_resampler_ccc(1, D): y[k] = sum_j taps[j] x[kD - j], zero history [A.7].
  * Canonical order: the polyphase branches v = j mod D are addressed by their position
  * p = (D - v) % D inside an aligned block of D input samples.  Each position accumulates
  *   P[p] = fma(taps[qD+v], x[kD-qD-v], P[p])   over q = 0..32 ascending
  * (taps beyond ntaps are zeros) in one chain per component, and the D partials are summed by
- * the balanced pairwise tree  ((P0+P1)+(P2+P3)) + ((P4+P5)+(P6+P7)) ... */
+ * the balanced pairwise tree  ((P0+P1)+(P2+P3)) + ((P4+P5)+(P6+P7)) ...; when D is not a power
+ * of two the tree is padded with zero partials up to the next one.  D = 1..64: the reference
+ * resamples by any integer ratio (examples/cell_search_file.py:50-57). */
 int64_t orc_decimate(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
 {
   if (decim <= 1) { memcpy(y, x, sizeof(orc_cf) * n_in); return n_in; }
-  float taps[1024];
-  int ntaps = orc_decim_taps(decim, taps, 1024);
-  const int Q = (ntaps - 1) / decim + 1;
+  if (decim > 64) return -1;
+  float taps[4096];
+  int ntaps = orc_decim_taps(decim, taps, 4096);
+  const int Q = 33;                       /* ceil(ntaps / D) <= 33 for every D */
+  if (ntaps <= 0 || ntaps > Q * decim) return -1;
+  int P2 = 1;
+  while (P2 < decim) P2 <<= 1;
   int64_t n_out = (n_in + decim - 1) / decim;
   for (int64_t k = 0; k < n_out; k++) {
-    float pr[16], pi[16];
+    float pr[64], pi[64];
+    for (int p = decim; p < P2; p++) { pr[p] = 0.f; pi[p] = 0.f; }
     for (int p = 0; p < decim; p++) {
       const int v = (decim - p) % decim;
       float ar = 0.f, ai = 0.f;
@@ -197,8 +212,8 @@ int64_t orc_decimate(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
       }
       pr[p] = ar; pi[p] = ai;
     }
-    for (int w = 1; w < decim; w <<= 1)
-      for (int p = 0; p < decim; p += 2 * w) { pr[p] = pr[p] + pr[p + w]; pi[p] = pi[p] + pi[p + w]; }
+    for (int w = 1; w < P2; w <<= 1)
+      for (int p = 0; p < P2; p += 2 * w) { pr[p] = pr[p] + pr[p + w]; pi[p] = pi[p] + pi[p + w]; }
     y[k].re = pr[0]; y[k].im = pi[0];
   }
   return n_out;
@@ -868,6 +883,7 @@ static void trig_frontend(int s, void *arg)
   trig_t *t = (trig_t *)arg;
   orc_cf *x = malloc(sizeof(orc_cf) * t->n_in);
   if (t->fmt == 1) orc_sc16_to_fc32((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, 1.0f / 32768.0f, x);
+  else if (t->fmt == 2) orc_sc8_to_fc32((const int8_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, 1.0f / 128.0f, x);
   else memcpy(x, (const orc_cf *)t->iq + (size_t)s * t->n_in, sizeof(orc_cf) * t->n_in);
   if (t->decim > 1) { t->ys[s] = malloc(sizeof(orc_cf) * t->n_out); orc_decimate(x, t->n_in, t->decim, t->ys[s]); free(x); }
   else t->ys[s] = x;

@@ -91,9 +91,10 @@ void orc_cexptab(float tab_re[4097], float tab_im[4097]);   /* entry 4096 == ent
 void orc_fft128_twiddles(float w_re[64], float w_im[64]);
 
 /* ---- front end ----------------------------------------------------------- */
-/* y[k] = sum_j taps[j] x[kD-j], zero initial state; n_out = ceil(n_in/D). */
+/* y[k] = sum_j taps[j] x[kD-j], zero initial state; n_out = ceil(n_in/D); -1 if D > 64. */
 int64_t orc_decimate(const orc_cf *x, int64_t n_in, int decim, orc_cf *y);
 void    orc_sc16_to_fc32(const int16_t *iq, int64_t n, float scale, orc_cf *out);
+void    orc_sc8_to_fc32(const int8_t *iq, int64_t n, float scale, orc_cf *out);
 
 /* ---- srsLTE pieces, exposed for unit tests -------------------------------- */
 /* Raw correlation power |x (*) h|^2 at the 9726 lags of one zero-padded 9600-sample window. */
@@ -133,7 +134,7 @@ int orc_chain_run(const orc_cf *y, int64_t n, int stream, int n_id_2, float psr_
                   orc_rec *recs, int max_recs);
 
 /* downlink_trigger_c topology over a batch of equal-length streams of raw input
- * (fc32 if fmt==0, sc16 if fmt==1, `decim` in {1,4,8,16}); three chains per stream.
+ * (fc32 if fmt==0, sc16 if fmt==1, sc8 if fmt==2; `decim` 1..64); three chains per stream.
  * Records are ordered (stream, n_id_2, win_index).  nthreads<=0 -> all cores.
  * Returns the record count, or -1 if max_recs is too small. */
 int orc_trigger_run(const void *iq, int fmt, int64_t n_in_per_stream, int n_streams, int decim,

@@ -55,6 +55,7 @@ def lib():
         L.orc_decimate.argtypes = [vp, C.c_int64, C.c_int, vp]
         L.orc_decimate.restype = C.c_int64
         L.orc_sc16_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
+        L.orc_sc8_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_pss_corr_window.argtypes = [vp, C.c_int, C.c_int, fp]
         L.orc_pss_corr_stream.argtypes = [vp, C.c_int64, C.c_int, fp]
         L.orc_fft128.argtypes = [vp, vp]
@@ -97,8 +98,8 @@ def pss_taps(n_id_2):
 
 
 def decim_taps(decim):
-    t = np.zeros(1024, np.float32)
-    n = lib().orc_decim_taps(decim, _fptr(t), 1024)
+    t = np.zeros(4096, np.float32)
+    n = lib().orc_decim_taps(decim, _fptr(t), 4096)
     return t[:n].copy()
 
 
@@ -125,7 +126,8 @@ def decimate(x, decim):
     x = np.ascontiguousarray(x, np.complex64)
     n_out = (len(x) + decim - 1) // decim if decim > 1 else len(x)
     y = np.zeros(n_out, np.complex64)
-    lib().orc_decimate(x.ctypes.data, len(x), decim, y.ctypes.data)
+    if lib().orc_decimate(x.ctypes.data, len(x), decim, y.ctypes.data) < 0:
+        raise RuntimeError("orc_decimate: unsupported decimation %d" % decim)
     return y
 
 
@@ -133,6 +135,13 @@ def sc16_to_fc32(iq, scale=1.0 / 32768.0):
     iq = np.ascontiguousarray(iq, np.int16)
     out = np.zeros(iq.size // 2, np.complex64)
     lib().orc_sc16_to_fc32(iq.ctypes.data, iq.size // 2, scale, out.ctypes.data)
+    return out
+
+
+def sc8_to_fc32(iq, scale=1.0 / 128.0):
+    iq = np.ascontiguousarray(iq, np.int8)
+    out = np.zeros(iq.size // 2, np.complex64)
+    lib().orc_sc8_to_fc32(iq.ctypes.data, iq.size // 2, scale, out.ctypes.data)
     return out
 
 
@@ -225,12 +234,12 @@ def chain_run(y, n_id_2, psr_threshold=4.0, track_after=16, track_every=8, conv_
 
 def trigger_run(iq, decim=1, fmt=0, psr_threshold=4.0, track_after=16, track_every=8,
                 conv_mode=CONV_DIRECT, nthreads=0):
-    """iq: [n_streams, n_in] complex64 (fmt 0) or [n_streams, n_in, 2] int16 (fmt 1)."""
+    """iq: [n_streams, n_in] complex64 (fmt 0), [n_streams, n_in, 2] int16 (fmt 1) or int8 (fmt 2)."""
     if fmt == 0:
         iq = np.ascontiguousarray(iq, np.complex64)
         n_streams, n_in = iq.shape
     else:
-        iq = np.ascontiguousarray(iq, np.int16)
+        iq = np.ascontiguousarray(iq, np.int16 if fmt == 1 else np.int8)
         n_streams, n_in = iq.shape[0], iq.shape[1]
     n_out = (n_in + decim - 1) // decim if decim > 1 else n_in
     max_recs = n_streams * 3 * (n_out // (HALF - SLOT) + 2)

@@ -43,7 +43,7 @@ def test_tables_match_oracle(oracle):
         assert np.array_equal(lt.tables.pss_taps(r).view(np.uint32), oracle.pss_taps(r).view(np.uint32))
         for a, b in zip(lt.tables.sss(r), oracle.sss_tables(r)):
             assert np.array_equal(a, b)
-    for d in (2, 4, 8, 16):
+    for d in range(2, lt.MAX_DECIM + 1):
         assert np.array_equal(lt.tables.decim_taps(d).view(np.uint32), oracle.decim_taps(d).view(np.uint32))
     for a, b in zip(lt.tables.cexp(), oracle.cexptab()):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
@@ -59,8 +59,10 @@ def test_invalid_inputs():
     cfg = _abi.TriggerConfig()
     assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS    # struct_size 0
     cfg.struct_size = C.sizeof(_abi.TriggerConfig)
-    cfg.n_streams, cfg.decim, cfg.max_chunk = 1, 3, 9600
-    assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS    # decim 3
+    cfg.n_streams, cfg.decim, cfg.max_chunk = 1, lt.MAX_DECIM + 1, 9600
+    assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS    # decim 65
+    cfg.decim, cfg.input_format = 3, 7
+    assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS    # unknown format
     re_, im_ = np.zeros(128, np.float32), np.zeros(128, np.float32)
     assert L.ltb_table_pss_taps(3, _abi.fptr(re_), _abi.fptr(im_)) == lt.ERROR_INVALID_INPUTS
     s = C.c_void_p()

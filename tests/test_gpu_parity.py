@@ -44,20 +44,46 @@ def test_pss_corr_kernel_linearity_full_size(lt):
     assert np.array_equal(p2, 4 * p1)
 
 
-@pytest.mark.parametrize("decim", [2, 4, 8, 16])
-@pytest.mark.parametrize("fmt", [0, 1])
-def test_decimate_kernel_bit_exact(lt, oracle, decim, fmt):
-    rng = np.random.default_rng(decim + 10 * fmt)
-    n = 1000 * decim
+def _decim_case(oracle, rng, decim, fmt, n):
     if fmt == 0:
         x = rand_c64(rng, 2, n)
         want = [oracle.decimate(x[s], decim) for s in range(2)]
-    else:
+    elif fmt == 1:
         x = rng.integers(-32768, 32767, size=(2, n, 2), dtype=np.int16)
         want = [oracle.decimate(oracle.sc16_to_fc32(x[s]), decim) for s in range(2)]
+    else:
+        x = rng.integers(-128, 127, size=(2, n, 2), dtype=np.int8)
+        want = [oracle.decimate(oracle.sc8_to_fc32(x[s]), decim) for s in range(2)]
+    return x, want
+
+
+@pytest.mark.parametrize("decim", [2, 3, 4, 5, 6, 7, 8, 11, 12, 13, 16, 24, 64])
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_decimate_kernel_bit_exact(lt, oracle, decim, fmt):
+    """rational_resampler_ccc(1, D) for any integer D (examples/cell_search_file.py:50-57): the
+    tiled kernel (2, 3, 4, 6, 8, 12), the streaming kernel (16) and the general kernel."""
+    rng = np.random.default_rng(decim + 100 * fmt)
+    x, want = _decim_case(oracle, rng, decim, fmt, 1000 * decim)
     got = lt.kernel_decimate(x, decim, fmt)
     for s in range(2):
         assert np.array_equal(got[s].view(np.uint32), want[s].view(np.uint32))
+
+
+@pytest.mark.parametrize("decim", [2, 8, 12, 16])
+def test_general_decimator_agrees_with_tuned_kernels(lt, oracle, decim):
+    """Debug flag 1 routes every rate through decimate_any_kernel: three independent kernels and
+    the oracle give the same bits."""
+    rng = np.random.default_rng(decim)
+    x, want = _decim_case(oracle, rng, decim, 0, 777 * decim)
+    tuned = lt.kernel_decimate(x, decim, 0)
+    lt.lib().ltb_debug_set_flag(1, 1)
+    try:
+        general = lt.kernel_decimate(x, decim, 0)
+    finally:
+        lt.lib().ltb_debug_set_flag(1, 0)
+    for s in range(2):
+        assert np.array_equal(general[s].view(np.uint32), want[s].view(np.uint32))
+        assert np.array_equal(tuned[s].view(np.uint32), want[s].view(np.uint32))
 
 
 # ---- engine: the four bundled test_frames ------------------------------------------------
@@ -102,6 +128,48 @@ def test_sc16_input(lt, oracle):
     want = oracle.trigger_run(iq, decim=1, fmt=1)
     assert_recs_equal(got, want)
     assert 200 in got["cell_id"]
+
+
+@pytest.mark.parametrize("decim", [1, 16])
+def test_sc8_input(lt, oracle, decim):
+    from ltetrigger_b200 import synth
+    x = synth.capture(77, 288000 * decim, snr_db=8.0, seed=5, decim=decim)
+    iq = synth.to_sc8(x)[None]
+    trig = lt.Trigger(n_streams=1, decim=decim, input_format=lt.FMT_SC8, max_chunk=96000 * decim)
+    got = trig.run(iq, chunk=96000 * decim)
+    want = oracle.trigger_run(iq, decim=decim, fmt=2)
+    assert_recs_equal(got, want)
+    assert 77 in got["cell_id"]
+
+
+@pytest.mark.parametrize("decim,fmt", [(12, 0), (12, 1), (3, 0), (6, 2), (5, 0), (20, 1)])
+def test_any_integer_sample_rate(lt, oracle, decim, fmt):
+    """Sample rates that are not 1.92 MHz * 2^k (23.04 Msps = 15 MHz LTE at D = 12, ...), fed in
+    ragged chunks: records identical to the oracle's."""
+    from ltetrigger_b200 import synth
+    x = np.stack([synth.capture(c, 240000 * decim, snr_db=7.0, decim=decim, seed=c) for c in (91, 502)])
+    iq = x if fmt == 0 else (synth.to_sc16(x) if fmt == 1 else synth.to_sc8(x))
+    chunk = 8 * decim * 7001
+    trig = lt.Trigger(n_streams=2, decim=decim, input_format=fmt, max_chunk=chunk)
+    got = trig.run(iq, chunk=chunk)
+    want = oracle.trigger_run(iq, decim=decim, fmt=fmt)
+    assert_recs_equal(got, want)
+    assert {91, 502} <= set(got["cell_id"].tolist())
+
+
+def test_extended_cp_capture(lt, oracle):
+    """Extended-CP cells: srslte_sync_detect_cp picks the extended hypothesis and the SSS symbol
+    is taken 128 + 32 samples before the PSS (lib/sss_impl.cc:104-110)."""
+    from ltetrigger_b200 import synth
+    x = np.stack([synth.capture(c, 384000, snr_db=9.0, seed=c, ext_cp=e) for c, e in ((311, True), (40, False), (167, True))])
+    trig = lt.Trigger(n_streams=3, decim=1, max_chunk=384000)
+    got = trig.run(x)
+    want = oracle.trigger_run(x)
+    assert_recs_equal(got, want)
+    for s, (c, e) in enumerate(((311, True), (40, False), (167, True))):
+        cells = got[(got["stream"] == s) & ((got["flags"] & lt.F_CELL) != 0)]
+        assert len(cells) > 5 and set(cells["cell_id"].tolist()) == {c}
+        assert (((cells["flags"] & lt.F_CP_NORM) != 0) == (not e)).all()
 
 
 def test_synthetic_snr_sweep_batched(lt, oracle):

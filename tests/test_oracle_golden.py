@@ -123,3 +123,33 @@ def test_tables(oracle):
     c0, c1, s, z, tab = oracle.sss_tables(0)
     assert tab[11, 12] == 41 and tab[9, 13] == 123              # (m0,m1) = (11,13), (9,14)
     assert sorted(set(tab.ravel().tolist())) == list(range(168))
+
+
+@pytest.mark.parametrize("decim", [3, 5, 12, 24])
+def test_decimator_any_integer_rate(oracle, decim):
+    """The reference resamples by any integer ratio (examples/cell_search_file.py:50-57): the
+    canonical-order decimator against a float64 convolution with the same taps."""
+    rng = np.random.default_rng(decim)
+    x = (rng.standard_normal(300 * decim) + 1j * rng.standard_normal(300 * decim)).astype(np.complex64)
+    t = oracle.decim_taps(decim)
+    assert len(t) % 2 == 1 and len(t) <= 33 * decim and np.array_equal(t, t[::-1])
+    want = np.convolve(x.astype(np.complex128), t.astype(np.float64))[:len(x):decim]
+    got = oracle.decimate(x, decim)
+    assert len(got) == 300 and np.abs(got - want).max() < 2e-6
+    with pytest.raises(RuntimeError):
+        oracle.decimate(x, 65)
+
+
+def test_sc8_and_extended_cp(oracle):
+    """sc8 ingest (scale 2^-7) equals the float path on the converted samples, and an
+    extended-CP capture is tagged cp_type = extended with the right cell_id
+    (lib/sss_impl.cc:104-110: sss_idx follows the detected CP length)."""
+    from ltetrigger_b200 import synth
+    x = synth.capture(311, 19200 * 14, snr_db=12.0, seed=4, ext_cp=True)
+    iq = synth.to_sc8(x)[None]
+    a = oracle.trigger_run(iq, fmt=2)
+    b = oracle.trigger_run(oracle.sc8_to_fc32(iq[0])[None, :], fmt=0)
+    assert a.tobytes() == b.tobytes()
+    cells = a[(a["flags"] & oracle.F_CELL) != 0]
+    assert len(cells) > 5 and set(cells["cell_id"].tolist()) == {311}
+    assert ((cells["flags"] & oracle.F_CP_NORM) == 0).all()
