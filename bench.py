@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--snr-db", type=float, default=5.0)
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic captures tiled over the streams")
     ap.add_argument("--e2e-streams", type=int, default=128)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-streams", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -340,7 +340,10 @@ def main():
             trig2 = lt.Trigger(n_streams=se, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmts[name],
                                record_all=False, device=local_rank, cuda_stream=stream.cuda_stream)
             hptr, hstride = host.data_ptr(), n * b
-            trig2.process_host_ptr(hptr, hstride, n)                # warm-up (allocates the staging buffer)
+            for _ in range(3):                                      # warm-up: allocates both staging buffers,
+                trig2.submit_host_ptr(hptr, hstride, n)             # touches every pinned page
+                trig2.submit_host_ptr(hptr, hstride, n)
+                trig2.collect(); trig2.collect()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
