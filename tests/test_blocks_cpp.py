@@ -1,6 +1,8 @@
-"""The C++ block adapters (include/ltetrigger_b200_blocks.hpp): they compile and link against the
-C-ABI library on any machine; on a GPU box the scheduler-style driver tests/cpp/test_blocks.cpp
-must reproduce the oracle's restated blocks call by call."""
+"""The C++ block adapters (include/ltetrigger_b200_blocks.hpp) and the GNU Radio wrappers around them
+(gr-ltetrigger_b200/gr_oot/lib, compiled against the stand-in GNU Radio headers of
+tests/cpp/gr_stub): they compile and link against the C-ABI library on any machine; on a GPU box
+the scheduler-style drivers tests/cpp/test_blocks.cpp and tests/cpp/test_gr_oot.cpp must
+reproduce the oracle's restated blocks call by call."""
 import os
 import subprocess
 
@@ -13,22 +15,32 @@ SRC = os.path.join(ROOT, "tests", "cpp", "test_blocks.cpp")
 LIBDIR = os.path.join(ROOT, "gr-ltetrigger_b200", "lib")
 
 
-def build(tmp_path):
-    exe = str(tmp_path / "test_blocks")
-    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), SRC,
-                           "-L", LIBDIR, "-lltetrigger_b200", "-Wl,-rpath," + LIBDIR, "-o", exe])
+OOT = os.path.join(ROOT, "gr-ltetrigger_b200", "gr_oot", "lib")
+OOT_SRC = [os.path.join(ROOT, "tests", "cpp", "test_gr_oot.cpp"), os.path.join(OOT, "pss_b200_impl.cc"),
+           os.path.join(OOT, "sss_b200_impl.cc")]
+
+
+def build(tmp_path, gr_oot=False):
+    exe = str(tmp_path / ("test_gr_oot" if gr_oot else "test_blocks"))
+    inc = ["-I", os.path.join(ROOT, "include")]
+    if gr_oot:
+        inc += ["-I", os.path.join(ROOT, "tests", "cpp", "gr_stub"), "-I", OOT]
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-Werror"] + inc + (OOT_SRC if gr_oot else [SRC]) +
+                          ["-L", LIBDIR, "-lltetrigger_b200", "-Wl,-rpath," + LIBDIR, "-o", exe])
     return exe
 
 
-def test_adapters_compile_and_link(tmp_path):
-    exe = build(tmp_path)
+@pytest.mark.parametrize("gr_oot", [False, True])
+def test_adapters_compile_and_link(tmp_path, gr_oot):
+    exe = build(tmp_path, gr_oot)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 2 and "usage" in out.stderr
 
 
 @pytest.mark.gpu
-def test_cpp_blocks_match_oracle(tmp_path, oracle):
-    exe = build(tmp_path)
+@pytest.mark.parametrize("gr_oot", [False, True])
+def test_cpp_blocks_match_oracle(tmp_path, oracle, gr_oot):
+    exe = build(tmp_path, gr_oot)
     fixture = os.path.join(GOLDEN, "test_frames", "lte_frame_6prb_cellid_123")
     out = subprocess.run([exe, fixture, "0.4", "0", "4"], capture_output=True, text=True, check=True).stdout.splitlines()
     assert out[0] == "E Error initializing PSS N_id_2"                      # lib/pss_impl.cc:75-76
