@@ -232,6 +232,9 @@ typedef struct {
   float *twN_re, *twN_im;             /* W_9728^(n1*k2), [k2][n1] */
   float w19_re[19], w19_im[19];
   float *H_re[3], *H_im[3];           /* FFT_9728(h_pad) per root, natural order, with 1/N folded in */
+  /* overlap-save mode tables */
+  float tw1024_re[1024], tw1024_im[1024];   /* W_1024^i */
+  float os_H_re[3][1024], os_H_im[3][1024]; /* DFT_1024(h zero padded) * 2^-10, natural order */
   int ready;
 } tables_t;
 
@@ -273,6 +276,8 @@ static void tables_build(void)
         for (int k = 0; k < FFTN; k++) { T.H_re[r][k] /= (float)FFTN; T.H_im[r][k] /= (float)FFTN; }
       }
       free(pr); free(pi); free(wk);
+      orc_fft1024_twiddles(T.tw1024_re, T.tw1024_im);
+      for (int r = 0; r < 3; r++) orc_os_filter(r, T.os_H_re[r], T.os_H_im[r]);
       T.ready = 1;
     }
   }
@@ -447,6 +452,195 @@ void orc_pss_corr_stream(const orc_cf *x, int64_t n, int n_id_2, float *power)
 }
 
 /* ------------------------------------------------------------------------- */
+/* Overlap-save mode (ORC_CONV_OS): the matched filter as 1024-point FFT blocks  */
+/* aligned to absolute sample indices.  This is the canonical arithmetic of the  */
+/* GPU's pss_corr_fft_kernel, restated here operation for operation.             */
+/*                                                                               */
+/* Block b covers outputs n in [896 b, 896 b + 896) from inputs                   */
+/* x[896 b - 128 .. 896 b + 896): X = FFT(x_blk), Y_g = H_g . X, y_g = IFFT(Y_g),  */
+/* P_g[896 b - 128 + n] = |y_g[n]|^2 for n in [128, 1024).                         */
+/* FFT_1024 is a four-step transform, n = 32 n1 + n2, f = k1 + 32 k2:              */
+/*   A[k1][n2] = DFT32_{n1} x[32 n1 + n2]        radix-2 DIF, W_32 literals         */
+/*   B[k1][n2] = W_1024^(n2 k1) A[k1][n2]        table, canonical complex product   */
+/*   X[k1 + 32 k2] = DFT32_{n2} B[k1][n2]        radix-2 DIF                        */
+/* and the inverse runs the mirrored graph (DIT over k2, conjugate table twiddle,   */
+/* DIF over k1) with conjugated twiddles; 2^-10 is folded into H.  Butterflies:     */
+/*   DIF: a' = a + b, b' = w (a - b)      DIT: t = w b, a' = a + t, b' = a - t        */
+/* with w b = (fma(wr, br, -(wi*bi)), fma(wr, bi, wi*br)); w = 1 and w = -+j are      */
+/* applied exactly (copy / swap with a sign).                                         */
+/* ------------------------------------------------------------------------- */
+static const float W32[16][2] = {
+  {1.000000000e+00f, 0.000000000e+00f},   {9.807852507e-01f, -1.950903237e-01f},
+  {9.238795042e-01f, -3.826834261e-01f},  {8.314695954e-01f, -5.555702448e-01f},
+  {7.071067691e-01f, -7.071067691e-01f},  {5.555702448e-01f, -8.314695954e-01f},
+  {3.826834261e-01f, -9.238795042e-01f},  {1.950903237e-01f, -9.807852507e-01f},
+  {0.000000000e+00f, -1.000000000e+00f},  {-1.950903237e-01f, -9.807852507e-01f},
+  {-3.826834261e-01f, -9.238795042e-01f}, {-5.555702448e-01f, -8.314695954e-01f},
+  {-7.071067691e-01f, -7.071067691e-01f}, {-8.314695954e-01f, -5.555702448e-01f},
+  {-9.238795042e-01f, -3.826834261e-01f}, {-9.807852507e-01f, -1.950903237e-01f}};
+
+void orc_fft1024_twiddles(float w_re[1024], float w_im[1024])
+{
+  for (int i = 0; i < 1024; i++) {
+    double a = 2.0 * M_PI * (double)i / 1024.0;
+    w_re[i] = (float)cos(a); w_im[i] = (float)(-sin(a));
+  }
+  w_re[0] = 1.f;    w_im[0] = 0.f;   w_re[256] = 0.f; w_im[256] = -1.f;
+  w_re[512] = -1.f; w_im[512] = 0.f; w_re[768] = 0.f; w_im[768] = 1.f;
+}
+
+/* H_g[f] = 2^-10 sum_m h_g[m] W_1024^(f m), double accumulation in ascending m */
+void orc_os_filter(int n_id_2, float H_re[1024], float H_im[1024])
+{
+  float hr[128], hi[128];
+  orc_pss_taps(n_id_2, hr, hi);
+  for (int f = 0; f < 1024; f++) {
+    double ar = 0.0, ai = 0.0;
+    for (int m = 0; m < 128; m++) {
+      double a = 2.0 * M_PI * (double)((f * m) & 1023) / 1024.0;
+      double c = cos(a), sn = -sin(a);
+      ar += (double)hr[m] * c - (double)hi[m] * sn;
+      ai += (double)hr[m] * sn + (double)hi[m] * c;
+    }
+    H_re[f] = (float)(ar / 1024.0); H_im[f] = (float)(ai / 1024.0);
+  }
+}
+
+static inline void cmul_w(float wr, float wi, float br, float bi, float *re, float *im)
+{
+  *re = fmaf(wr, br, -(wi * bi));
+  *im = fmaf(wr, bi, wi * br);
+}
+
+/* twiddle W_32^idx (conj if inv) times (dr, di), exact for idx 0 and 8 */
+static inline void tw32(int idx, int inv, float dr, float di, float *re, float *im)
+{
+  if (idx == 0) { *re = dr; *im = di; }
+  else if (idx == 8) { if (inv) { *re = -di; *im = dr; } else { *re = di; *im = -dr; } }
+  else cmul_w(W32[idx][0], inv ? -W32[idx][1] : W32[idx][1], dr, di, re, im);
+}
+
+/* radix-2 DIF, natural order in, bit-reversed order out */
+static void fft32_dif(float *vr, float *vi, int inv)
+{
+  for (int s = 0; s < 5; s++) {
+    int half = 16 >> s;
+    for (int base = 0; base < 32; base += 2 * half)
+      for (int k = 0; k < half; k++) {
+        int i = base + k, j = i + half;
+        float ar = vr[i], ai = vi[i], br = vr[j], bi = vi[j];
+        vr[i] = ar + br; vi[i] = ai + bi;
+        tw32(k << s, inv, ar - br, ai - bi, &vr[j], &vi[j]);
+      }
+  }
+}
+
+/* radix-2 DIT, bit-reversed order in, natural order out */
+static void fft32_dit(float *vr, float *vi, int inv)
+{
+  for (int s = 0; s < 5; s++) {
+    int half = 1 << s;
+    for (int base = 0; base < 32; base += 2 * half)
+      for (int k = 0; k < half; k++) {
+        int i = base + k, j = i + half;
+        float tr, ti;
+        tw32(k * (16 >> s), inv, vr[j], vi[j], &tr, &ti);
+        float ar = vr[i], ai = vi[i];
+        vr[i] = ar + tr; vi[i] = ai + ti;
+        vr[j] = ar - tr; vi[j] = ai - ti;
+      }
+  }
+}
+
+static int bitrev5(int v) { return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4); }
+
+/* forward: x natural (n = 32 n1 + n2) -> X stored at [r][k1] with f = k1 + 32 bitrev5(r) */
+static void fft1024_fwd(const float *xr, const float *xi, float *Xr, float *Xi)
+{
+  static __thread float Br[32][32], Bi[32][32];     /* [k1][n2] */
+  float vr[32], vi[32];
+  for (int n2 = 0; n2 < 32; n2++) {
+    for (int n1 = 0; n1 < 32; n1++) { vr[n1] = xr[32 * n1 + n2]; vi[n1] = xi[32 * n1 + n2]; }
+    fft32_dif(vr, vi, 0);
+    for (int r = 0; r < 32; r++) {
+      int k1 = bitrev5(r), t = (n2 * k1) & 1023;
+      cmul_w(T.tw1024_re[t], T.tw1024_im[t], vr[r], vi[r], &Br[k1][n2], &Bi[k1][n2]);
+    }
+  }
+  for (int k1 = 0; k1 < 32; k1++) {
+    for (int n2 = 0; n2 < 32; n2++) { vr[n2] = Br[k1][n2]; vi[n2] = Bi[k1][n2]; }
+    fft32_dif(vr, vi, 0);
+    for (int r = 0; r < 32; r++) { Xr[r * 32 + k1] = vr[r]; Xi[r * 32 + k1] = vi[r]; }
+  }
+}
+
+/* inverse (unscaled): Y at [r][k1] as above -> y natural */
+static void fft1024_inv(const float *Yr, const float *Yi, float *yr, float *yi)
+{
+  static __thread float Dr[32][32], Di[32][32];     /* [n2][k1] */
+  float vr[32], vi[32];
+  for (int k1 = 0; k1 < 32; k1++) {
+    for (int r = 0; r < 32; r++) { vr[r] = Yr[r * 32 + k1]; vi[r] = Yi[r * 32 + k1]; }
+    fft32_dit(vr, vi, 1);                               /* over k2 -> n2 natural */
+    for (int n2 = 0; n2 < 32; n2++) {
+      int t = (k1 * n2) & 1023;
+      cmul_w(T.tw1024_re[t], -T.tw1024_im[t], vr[n2], vi[n2], &Dr[n2][k1], &Di[n2][k1]);
+    }
+  }
+  for (int n2 = 0; n2 < 32; n2++) {
+    for (int k1 = 0; k1 < 32; k1++) { vr[k1] = Dr[n2][k1]; vi[k1] = Di[n2][k1]; }
+    fft32_dif(vr, vi, 1);                               /* over k1 -> n1 bit-reversed */
+    for (int r = 0; r < 32; r++) { yr[32 * bitrev5(r) + n2] = vr[r]; yi[32 * bitrev5(r) + n2] = vi[r]; }
+  }
+}
+
+void orc_fft1024(const orc_cf *in, orc_cf *out, int inverse)
+{
+  tables_init();
+  float xr[1024], xi[1024], Xr[1024], Xi[1024];
+  if (!inverse) {
+    for (int i = 0; i < 1024; i++) { xr[i] = in[i].re; xi[i] = in[i].im; }
+    fft1024_fwd(xr, xi, Xr, Xi);
+    for (int r = 0; r < 32; r++)
+      for (int k1 = 0; k1 < 32; k1++) { out[k1 + 32 * bitrev5(r)].re = Xr[r * 32 + k1]; out[k1 + 32 * bitrev5(r)].im = Xi[r * 32 + k1]; }
+  } else {
+    for (int r = 0; r < 32; r++)
+      for (int k1 = 0; k1 < 32; k1++) { Xr[r * 32 + k1] = in[k1 + 32 * bitrev5(r)].re; Xi[r * 32 + k1] = in[k1 + 32 * bitrev5(r)].im; }
+    fft1024_inv(Xr, Xi, xr, xi);
+    for (int i = 0; i < 1024; i++) { out[i].re = xr[i]; out[i].im = xi[i]; }
+  }
+}
+
+/* power of all three roots for the whole blocks of x[0..n): out[g][i], i < 896 * (n / 896);
+ * x[<0] = 0.  Returns the number of outputs per root. */
+int64_t orc_pss_corr_os(const orc_cf *x, int64_t n, float *p0, float *p1, float *p2)
+{
+  tables_init();
+  float *pw[3] = {p0, p1, p2};
+  float xr[1024], xi[1024], Xr[1024], Xi[1024], Yr[1024], Yi[1024], yr[1024], yi[1024];
+  int64_t nblk = n / ORC_OS_STEP;
+  for (int64_t b = 0; b < nblk; b++) {
+    int64_t base = b * ORC_OS_STEP - 128;
+    for (int i = 0; i < 1024; i++) {
+      int64_t idx = base + i;
+      xr[i] = idx >= 0 ? x[idx].re : 0.f; xi[i] = idx >= 0 ? x[idx].im : 0.f;
+    }
+    fft1024_fwd(xr, xi, Xr, Xi);
+    for (int g = 0; g < 3; g++) {
+      if (!pw[g]) continue;
+      for (int r = 0; r < 32; r++)
+        for (int k1 = 0; k1 < 32; k1++) {
+          int f = k1 + 32 * bitrev5(r);
+          cmul_w(T.os_H_re[g][f], T.os_H_im[g][f], Xr[r * 32 + k1], Xi[r * 32 + k1], &Yr[r * 32 + k1], &Yi[r * 32 + k1]);
+        }
+      fft1024_inv(Yr, Yi, yr, yi);
+      for (int i = 128; i < 1024; i++) pw[g][base + i] = fmaf(yr[i], yr[i], yi[i] * yi[i]);
+    }
+  }
+  return nblk * ORC_OS_STEP;
+}
+
+/* ------------------------------------------------------------------------- */
 /* srslte_pss_find_pss [A.2]                                                  */
 /* ------------------------------------------------------------------------- */
 
@@ -457,6 +651,7 @@ typedef struct {
   float *power;
   float *fftwk;
   int conv_mode, n_id_2;
+  const float *os_power;       /* ORC_CONV_OS: whole-stream block powers, os_power[k] = lag k of this window */
 } pss_core_t;
 
 static int vec_max_fi(const float *x, int len)
@@ -470,6 +665,13 @@ static int find_pss(pss_core_t *q, const orc_cf *in, float *psr_out)
 {
   if (q->conv_mode == ORC_CONV_FFT) {
     corr_fft(in, q->n_id_2, q->power, q->fftwk);
+  } else if (q->conv_mode == ORC_CONV_OS) {
+    /* lags that see the window's zero padding (k < 127, k >= 9600): direct form on the window;
+     * interior lags: the stream's overlap-save block values */
+    for (int i = 0; i < ORC_HALF; i++) { q->xr[128 + i] = in[i].re; q->xi[128 + i] = in[i].im; }
+    corr_direct(q->xr + 128, q->xi + 128, 0, 127, q->n_id_2, q->power);
+    corr_direct(q->xr + 128, q->xi + 128, ORC_HALF, NLAG - ORC_HALF, q->n_id_2, q->power + ORC_HALF);
+    memcpy(q->power + 127, q->os_power + 127, sizeof(float) * (ORC_HALF - 127));
   } else {
     for (int i = 0; i < ORC_HALF; i++) { q->xr[128 + i] = in[i].re; q->xi[128 + i] = in[i].im; }
     corr_direct(q->xr + 128, q->xi + 128, 0, NLAG, q->n_id_2, q->power);
@@ -681,6 +883,7 @@ int orc_pss_work(orc_pss *b, const orc_cf *in, orc_cf *out, int *nconsume, orc_r
   return noutput;
 }
 
+void orc_pss_set_os_power(orc_pss *b, const float *os_power) { b->core.os_power = os_power; }
 float orc_pss_max_psr(const orc_pss *b) { return b->psr_max; }
 float orc_pss_mean_psr(const orc_pss *b) { return moving_avg(b->psr_data, b->psr_i); }
 float orc_pss_mean_cfo(const orc_pss *b) { return moving_avg(b->cfo_data, b->cfo_i); }
@@ -856,11 +1059,19 @@ int orc_chain_run(const orc_cf *y, int64_t n, int stream, int n_id_2, float thr,
   orc_cf *buf = calloc(n + ORC_SLOT, sizeof(orc_cf));       /* GR zero history in front */
   memcpy(buf + ORC_SLOT, y, sizeof(orc_cf) * n);
   orc_cf *out = malloc(sizeof(orc_cf) * ORC_HALF);
+  float *os = NULL;
+  if (conv_mode == ORC_CONV_OS) {
+    /* whole blocks of the stream; a window's interior lags end 8765 samples before the data the
+     * scheduler rule requires, so the incomplete last block is never read */
+    os = calloc(n + 1024, sizeof(float));
+    orc_pss_corr_os(y, n, n_id_2 == 0 ? os : NULL, n_id_2 == 1 ? os : NULL, n_id_2 == 2 ? os : NULL);
+  }
   int nrec = 0; int64_t R = 0;
   while (R + ORC_LOOKAHEAD <= n) {
     if (nrec >= max_recs) { nrec = -1; break; }
     orc_rec *rec = &recs[nrec];
     int nconsume = 0;
+    orc_pss_set_os_power(p, os ? os + R : NULL);
     int nout = orc_pss_work(p, buf + ORC_SLOT + R, out, &nconsume, rec);
     rec->stream = stream; rec->win_start = R;
     rec->emit_start = nout ? R + rec->emit_start : -1;
@@ -868,7 +1079,7 @@ int orc_chain_run(const orc_cf *y, int64_t n, int stream, int n_id_2, float thr,
     R += nconsume;
     nrec++;
   }
-  free(buf); free(out); orc_pss_free(p); orc_sss_free(s);
+  free(buf); free(out); free(os); orc_pss_free(p); orc_sss_free(s);
   return nrec;
 }
 

@@ -41,7 +41,8 @@ extern "C" {
 
 typedef struct { float re, im; } orc_cf;
 
-enum { ORC_CONV_DIRECT = 0, ORC_CONV_FFT = 1 };
+enum { ORC_CONV_DIRECT = 0, ORC_CONV_FFT = 1, ORC_CONV_OS = 2 };
+#define ORC_OS_STEP 896        /* outputs per 1024-point overlap-save block (ORC_CONV_OS) */
 
 #define ORC_SLOT      960
 #define ORC_HALF      9600
@@ -102,6 +103,14 @@ void orc_pss_corr_window(const orc_cf *win, int n_id_2, int conv_mode, float *po
 /* Sliding (untruncated) correlation power for a whole stream: P[n] for n in [0,n). x[<0]=0. */
 void orc_pss_corr_stream(const orc_cf *x, int64_t n, int n_id_2, float *power);
 void orc_fft128(const orc_cf *in, orc_cf *out);   /* forward, unnormalised, natural order */
+/* ORC_CONV_OS: the canonical arithmetic of the GPU's overlap-save FFT correlator.  1024-point
+ * four-step FFT (natural order in and out; inverse unscaled), its twiddle table, the filter
+ * spectra (2^-10 folded in), and the block correlator over a whole stream (powers of the whole
+ * 896-output blocks of x[0..n), x[<0] = 0; NULL skips a root; returns outputs per root). */
+void orc_fft1024(const orc_cf *in, orc_cf *out, int inverse);
+void orc_fft1024_twiddles(float w_re[1024], float w_im[1024]);
+void orc_os_filter(int n_id_2, float H_re[1024], float H_im[1024]);
+int64_t orc_pss_corr_os(const orc_cf *x, int64_t n, float *p0, float *p1, float *p2);
 
 /* ---- blocks ---------------------------------------------------------------- */
 typedef struct orc_pss orc_pss;
@@ -112,6 +121,9 @@ void     orc_pss_free(orc_pss *);
 /* One general_work call.  `in` points at the first new sample; in[-960 .. 18365) must be
  * readable.  Writes 0 or 9600 samples to out, returns noutput; *nconsume as consume_each. */
 int      orc_pss_work(orc_pss *, const orc_cf *in, orc_cf *out, int *nconsume, orc_rec *rec);
+/* ORC_CONV_OS only: os_power[k] = overlap-save power at lag k of the window the next work call
+ * searches (orc_chain_run sets it; the block cannot know the stream's absolute alignment) */
+void     orc_pss_set_os_power(orc_pss *, const float *os_power);
 float    orc_pss_max_psr(const orc_pss *);
 float    orc_pss_mean_psr(const orc_pss *);
 float    orc_pss_mean_cfo(const orc_pss *);

@@ -11,7 +11,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libltetrigger_oracle.so")
 
-CONV_DIRECT, CONV_FFT = 0, 1
+CONV_DIRECT, CONV_FFT, CONV_OS = 0, 1, 2
+OS_STEP = 896
 SLOT, HALF, SYM, CONV_LEN, LOOKAHEAD = 960, 9600, 128, 9726, 18365
 
 F_SEARCHED, F_OVER, F_EMIT, F_TRACKING, F_TAG_LOST, F_SSS, F_CELL, F_CP_NORM = (
@@ -59,6 +60,11 @@ def lib():
         L.orc_pss_corr_window.argtypes = [vp, C.c_int, C.c_int, fp]
         L.orc_pss_corr_stream.argtypes = [vp, C.c_int64, C.c_int, fp]
         L.orc_fft128.argtypes = [vp, vp]
+        L.orc_fft1024.argtypes = [vp, vp, C.c_int]
+        L.orc_fft1024_twiddles.argtypes = [fp, fp]
+        L.orc_os_filter.argtypes = [C.c_int, fp, fp]
+        L.orc_pss_corr_os.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.orc_pss_corr_os.restype = C.c_int64
         L.orc_pss_new.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
         L.orc_pss_new.restype = vp
         L.orc_pss_free.argtypes = [vp]
@@ -143,6 +149,36 @@ def sc8_to_fc32(iq, scale=1.0 / 128.0):
     out = np.zeros(iq.size // 2, np.complex64)
     lib().orc_sc8_to_fc32(iq.ctypes.data, iq.size // 2, scale, out.ctypes.data)
     return out
+
+
+def fft1024(x, inverse=False):
+    """Canonical 1024-point four-step FFT of the overlap-save mode (inverse: unscaled)."""
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.zeros(1024, np.complex64)
+    lib().orc_fft1024(x.ctypes.data, out.ctypes.data, int(inverse))
+    return out
+
+
+def fft1024_twiddles():
+    r, i = np.zeros(1024, np.float32), np.zeros(1024, np.float32)
+    lib().orc_fft1024_twiddles(_fptr(r), _fptr(i))
+    return r, i
+
+
+def os_filter(n_id_2):
+    r, i = np.zeros(1024, np.float32), np.zeros(1024, np.float32)
+    lib().orc_os_filter(n_id_2, _fptr(r), _fptr(i))
+    return r, i
+
+
+def pss_corr_os(x):
+    """Overlap-save block powers of the whole 896-output blocks of x: [3, 896 * (len(x) // 896)]."""
+    x = np.ascontiguousarray(x, np.complex64)
+    n = len(x) // OS_STEP * OS_STEP
+    p = np.zeros((3, max(n, 1)), np.float32)
+    got = lib().orc_pss_corr_os(x.ctypes.data, len(x), p[0].ctypes.data, p[1].ctypes.data, p[2].ctypes.data)
+    assert got == n
+    return p[:, :n]
 
 
 def pss_corr_window(win, n_id_2, conv_mode=CONV_DIRECT):
