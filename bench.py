@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--segment-ms", type=int, default=100)
     ap.add_argument("--decim", type=int, default=16)
     ap.add_argument("--format", default="fc32", choices=["fc32", "sc16", "sc8"])
+    ap.add_argument("--corr", default="fft", choices=["direct", "fft"],
+                    help="matched-filter evaluation: folded direct form or overlap-save FFT blocks")
     ap.add_argument("--snr-db", type=float, default=5.0)
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic captures tiled over the streams")
     ap.add_argument("--e2e-streams", type=int, default=128)
@@ -234,8 +236,9 @@ def main():
     torch.cuda.synchronize()
 
     stream = torch.cuda.current_stream()
+    corr_mode = lt.CORR_FFT if a.corr == "fft" else lt.CORR_DIRECT
     trig = lt.Trigger(n_streams=a.streams, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
-                      record_all=False, device=local_rank, cuda_stream=stream.cuda_stream)
+                      record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode)
     ptr, stride = d_in.data_ptr(), n * bps
 
     def step():
@@ -318,7 +321,7 @@ def main():
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "streams_per_gpu": a.streams, "decim": a.decim,
-                   "format": a.format, "segment_ms": a.segment_ms, "snr_db": a.snr_db,
+                   "format": a.format, "correlator": a.corr, "segment_ms": a.segment_ms, "snr_db": a.snr_db,
                    "l2": "inputs larger than L2 (%.1f GB per step)" % (a.streams * n * bps / 1e9),
                    "input": "%d seeded synthetic LTE captures tiled over the streams with per-stream timing shift + AWGN" % a.unique,
                    "cells_tagged_per_step": n_cells / a.steps},
@@ -338,7 +341,7 @@ def main():
             torch.cuda.synchronize()
             b = FMT_BYTES[name]
             trig2 = lt.Trigger(n_streams=se, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmts[name],
-                               record_all=False, device=local_rank, cuda_stream=stream.cuda_stream)
+                               record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode)
             hptr, hstride = host.data_ptr(), n * b
             for _ in range(3):                                      # warm-up: allocates both staging buffers,
                 trig2.submit_host_ptr(hptr, hstride, n)             # touches every pinned page

@@ -3,6 +3,7 @@
 // every compute entry point fails with LTB_ERROR when no CUDA device is usable.
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -119,6 +120,50 @@ int ensure_constants(int device) {
 #undef LTB_SMEM_ATTR_FMT
 #undef LTB_SMEM_ATTR
   g_const_done[device] = true;
+  return LTB_SUCCESS;
+}
+
+// overlap-save correlator tables in the kernel's access order (one copy per device):
+// tw_perm[r][l] = W_1024^(l * bitrev5(r)),  h_perm[g][r][l] = H_g[l + 32 * bitrev5(r)]
+float2 *g_os_tw[64] = {nullptr};
+float2 *g_os_h[64] = {nullptr};
+
+int ensure_os_tables(int device) {
+  std::lock_guard<std::mutex> lk(g_const_mu);
+  if (g_os_tw[device]) return LTB_SUCCESS;
+  std::vector<float> wr(1024), wi(1024), hr(1024), hi(1024);
+  make_fft1024_twiddles(wr.data(), wi.data());
+  std::vector<float2> tw(1024), hp(3 * 1024);
+  for (int r = 0; r < 32; ++r)
+    for (int l = 0; l < 32; ++l) {
+      const int t = (l * bitrev5(r)) & 1023;
+      tw[r * 32 + l] = make_float2(wr[t], wi[t]);
+    }
+  for (int g = 0; g < 3; ++g) {
+    make_os_filter(g, hr.data(), hi.data());
+    for (int r = 0; r < 32; ++r)
+      for (int l = 0; l < 32; ++l) hp[(size_t)g * 1024 + r * 32 + l] = make_float2(hr[l + 32 * bitrev5(r)], hi[l + 32 * bitrev5(r)]);
+  }
+  float2 *d_tw = nullptr, *d_h = nullptr;
+  LTB_CUDA(cudaMalloc(&d_tw, sizeof(float2) * tw.size()));
+  LTB_CUDA(cudaMalloc(&d_h, sizeof(float2) * hp.size()));
+  LTB_CUDA(cudaMemcpy(d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+  LTB_CUDA(cudaMemcpy(d_h, hp.data(), sizeof(float2) * hp.size(), cudaMemcpyHostToDevice));
+  LTB_CUDA(cudaFuncSetAttribute(pss_corr_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsShared)));
+  g_os_h[device] = d_h;
+  g_os_tw[device] = d_tw;
+  return LTB_SUCCESS;
+}
+
+// whole overlap-save blocks [blk_first, blk_first + blk_count) of every stream
+int launch_corr_fft(int device, const float2 *y_ring, float *p_ring, long long blk_first, int blk_count, unsigned mask,
+                    int cap, int n_streams, cudaStream_t st) {
+  if (blk_count <= 0) return LTB_SUCCESS;
+  const long long total = (long long)blk_count * n_streams;
+  long long ctas = (long long)LTB_OS_MIN_CTAS * (g_sm_count[device] > 0 ? g_sm_count[device] : 148);
+  if (ctas > (total + kOsWarps - 1) / kOsWarps) ctas = (total + kOsWarps - 1) / kOsWarps;
+  pss_corr_fft_kernel<<<(unsigned)ctas, 32 * kOsWarps, sizeof(OsShared), st>>>(y_ring, p_ring, blk_first, blk_count, mask, cap, n_streams,
+                                                                g_os_tw[device], g_os_h[device]);
   return LTB_SUCCESS;
 }
 
@@ -259,6 +304,7 @@ struct ltb_trigger {
   float2 *d_cexp = nullptr;
   float *d_branch_taps = nullptr;         // [decim][33], decimate_any_kernel
   long long n_total = 0;
+  long long os_blocks_done = 0;           // LTB_CORR_FFT: overlap-save blocks already evaluated
   std::vector<float> h_thr;
   int last_launches = 0;
   float last_ms = 0.f;
@@ -277,6 +323,7 @@ int trigger_zero_state(ltb_trigger *t) {
   LTB_CUDA(cudaMemcpyAsync(t->d_thr, t->h_thr.data(), sizeof(float) * t->n_chains, cudaMemcpyHostToDevice, t->stream));
   LTB_CUDA(cudaStreamSynchronize(t->stream));
   t->n_total = 0;
+  t->os_blocks_done = 0;
   t->tail_cur = 0;
   t->n_pending = 0; t->head = 0;
   return LTB_SUCCESS;
@@ -322,7 +369,14 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   if (rc) return rc;
   if (c.decim > 1) t->tail_cur ^= 1;
   LTB_CUDA(cudaEventRecord(sl.ev_k[0], t->stream));
-  {
+  if (c.corr_mode == LTB_CORR_FFT) {
+    // whole 896-output blocks that end inside the received samples; the tail waits for the next call
+    const long long blk_end = (n_base + m) / kOsStep;
+    rc = launch_corr_fft(c.device, t->d_y, t->d_p, t->os_blocks_done, (int)(blk_end - t->os_blocks_done), t->cap_mask, t->cap,
+                         S, t->stream);
+    if (rc) return rc;
+    t->os_blocks_done = blk_end;
+  } else {
     const int tps = (m + kCorrTile - 1) / kCorrTile;
     const long long total = (long long)tps * S;
     if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many correlator tiles in one call");
@@ -383,12 +437,17 @@ int ltb_device_count(void) {
 }
 
 int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
-  if (!cfg || !out || cfg->struct_size != sizeof(ltb_trigger_config))
+  // ABI evolution: a caller built against the header before corr_mode was appended passes the
+  // shorter size and gets the defaults of the fields it does not know
+  constexpr size_t kMinConfig = offsetof(ltb_trigger_config, corr_mode);
+  if (!cfg || !out || cfg->struct_size < kMinConfig || cfg->struct_size > sizeof(ltb_trigger_config))
     return fail(LTB_ERROR_INVALID_INPUTS, "bad config pointer or struct_size");
   *out = nullptr;
-  ltb_trigger_config c = *cfg;
+  ltb_trigger_config c = ltb_trigger_config();
+  std::memcpy(&c, cfg, cfg->struct_size);
+  c.struct_size = sizeof c;
   if (c.n_streams <= 0 || !valid_decim(c.decim) || !valid_format(c.input_format) ||
-      c.max_chunk <= 0 || (c.root_mask & ~7))
+      c.max_chunk <= 0 || (c.root_mask & ~7) || (c.corr_mode != LTB_CORR_DIRECT && c.corr_mode != LTB_CORR_FFT))
     return fail(LTB_ERROR_INVALID_INPUTS, "invalid trigger configuration");
   if (c.root_mask == 0) c.root_mask = 7;
   if (c.track_after <= 0) c.track_after = 16;
@@ -398,6 +457,7 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   if (ltb_device_count() <= c.device || c.device < 0) return fail(LTB_ERROR, "no such CUDA device");
   LTB_CUDA(cudaSetDevice(c.device));
   int rc = ensure_constants(c.device);
+  if (!rc && c.corr_mode == LTB_CORR_FFT) rc = ensure_os_tables(c.device);
   if (rc) return rc;
 
   ltb_trigger *t = new ltb_trigger();
@@ -714,6 +774,31 @@ int ltb_kernel_pss_corr_host(int device, const ltb_cf *x, int n_streams, int64_t
   return LTB_SUCCESS;
 }
 
+int ltb_kernel_pss_corr_fft_host(int device, const ltb_cf *x, int n_streams, int64_t n, float *power) {
+  if (!x || !power || n_streams <= 0 || n < kOsStep) return fail(LTB_ERROR_INVALID_INPUTS, "n must hold at least one 896-sample block");
+  if (ltb_device_count() <= device || device < 0) return fail(LTB_ERROR, "no such CUDA device");
+  LTB_CUDA(cudaSetDevice(device));
+  int rc = ensure_constants(device);
+  if (!rc) rc = ensure_os_tables(device);
+  if (rc) return rc;
+  const int nblk = (int)(n / kOsStep);
+  const int64_t n_out = (int64_t)nblk * kOsStep;
+  const int cap = next_pow2(n + 1024);
+  float2 *d_y = nullptr; float *d_p = nullptr;
+  cudaError_t e = cudaMalloc(&d_y, sizeof(float2) * (size_t)n_streams * cap);
+  if (e == cudaSuccess) e = cudaMalloc(&d_p, sizeof(float) * (size_t)n_streams * 3 * cap);
+  if (e == cudaSuccess) e = cudaMemset(d_y, 0, sizeof(float2) * (size_t)n_streams * cap);
+  if (e == cudaSuccess) e = cudaMemcpy2D(d_y, sizeof(float2) * (size_t)cap, x, sizeof(float2) * (size_t)n, sizeof(float2) * (size_t)n, n_streams, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = launch_corr_fft(device, d_y, d_p, 0, nblk, (unsigned)(cap - 1), cap, n_streams, 0);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy2D(power, sizeof(float) * (size_t)n_out, d_p, sizeof(float) * (size_t)cap, sizeof(float) * (size_t)n_out, (size_t)n_streams * 3, cudaMemcpyDeviceToHost);
+  cudaFree(d_y); cudaFree(d_p);
+  if (e != cudaSuccess) return fail(LTB_ERROR, std::string("ltb_kernel_pss_corr_fft_host: ") + cudaGetErrorString(e));
+  return rc;
+}
+
 int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in, int decim, ltb_cf *y) {
   if (!x || !y || n_streams <= 0 || n_in <= 0 || !valid_decim(decim) || (n_in % decim) != 0 || !valid_format(fmt))
     return fail(LTB_ERROR_INVALID_INPUTS, "bad decimate arguments");
@@ -772,6 +857,18 @@ int ltb_table_sss(int n_id_2, int32_t c0[31], int32_t c1[31], int32_t s_tilde[31
   std::memcpy(c0, st.c0, sizeof st.c0); std::memcpy(c1, st.c1, sizeof st.c1);
   std::memcpy(s_tilde, st.s_tilde, sizeof st.s_tilde); std::memcpy(z_tilde, st.z_tilde, sizeof st.z_tilde);
   std::memcpy(n_id_1_table, st.n_id_1, sizeof st.n_id_1);
+  return LTB_SUCCESS;
+}
+
+int ltb_table_fft1024_twiddles(float w_re[1024], float w_im[1024]) {
+  if (!w_re || !w_im) return LTB_ERROR_INVALID_INPUTS;
+  make_fft1024_twiddles(w_re, w_im);
+  return LTB_SUCCESS;
+}
+
+int ltb_table_os_filter(int n_id_2, float H_re[1024], float H_im[1024]) {
+  if (n_id_2 < 0 || n_id_2 > 2 || !H_re || !H_im) return LTB_ERROR_INVALID_INPUTS;
+  make_os_filter(n_id_2, H_re, H_im);
   return LTB_SUCCESS;
 }
 

@@ -809,6 +809,203 @@ pss_corr_kernel(const float2 *__restrict__ y_ring, float *__restrict__ p_ring, l
 }
 
 // ------------------------------------------------------------------------------------
+// K2f: the same three-root matched filter as overlap-save FFT blocks (corr_mode LTB_CORR_FFT).
+//
+// Block b of a stream = 1024 samples x[896 b - 128 .. 896 b + 896) -> the 896 correlation powers
+// P_g[896 b .. 896 b + 896) of the three roots: X = FFT(x), Y_g = H_g X, y_g = IFFT(Y_g),
+// P = |y_g[n]|^2 for n >= 128.  Blocks are aligned to absolute sample indices and only whole
+// blocks are evaluated (the tail waits for the next call), so results do not depend on how the
+// stream is cut into calls; a window's interior lags end 8765 samples before the data the
+// scheduler rule requires, so the waiting tail is never needed.
+//
+// One warp per block, everything in registers: lane l holds 32 complex values.  FFT_1024 is a
+// four-step transform (n = 32 n1 + n2, f = k1 + 32 k2): 32-point radix-2 DIF over the registers
+// with W_32 twiddles as immediates, one table twiddle W_1024^(n2 k1) per value, a 32 x 32
+// transpose through 8.4 kB of shared memory, another 32-point DIF.  The inverse runs the
+// mirrored graph (DIT, conjugate table twiddle, transpose, DIF) three times on H_g X with X kept
+// in registers.  Per lane and block: about 4700 FP32 operations against 20700 lane-cycles of the
+// folded direct form for the same 896 x 3 outputs.  The arithmetic (every butterfly, the
+// canonical complex product, exact shortcuts for w = 1, -+j) is the oracle's ORC_CONV_OS.
+// ------------------------------------------------------------------------------------
+constexpr int kOsStep = 896;
+constexpr int kOsWarps = 4;
+
+__device__ __forceinline__ float2 w32_const(int i) {
+  switch (i) {
+    case 1: return make_float2(9.807852507e-01f, -1.950903237e-01f);
+    case 2: return make_float2(9.238795042e-01f, -3.826834261e-01f);
+    case 3: return make_float2(8.314695954e-01f, -5.555702448e-01f);
+    case 4: return make_float2(7.071067691e-01f, -7.071067691e-01f);
+    case 5: return make_float2(5.555702448e-01f, -8.314695954e-01f);
+    case 6: return make_float2(3.826834261e-01f, -9.238795042e-01f);
+    case 7: return make_float2(1.950903237e-01f, -9.807852507e-01f);
+    case 9: return make_float2(-1.950903237e-01f, -9.807852507e-01f);
+    case 10: return make_float2(-3.826834261e-01f, -9.238795042e-01f);
+    case 11: return make_float2(-5.555702448e-01f, -8.314695954e-01f);
+    case 12: return make_float2(-7.071067691e-01f, -7.071067691e-01f);
+    case 13: return make_float2(-8.314695954e-01f, -5.555702448e-01f);
+    case 14: return make_float2(-9.238795042e-01f, -3.826834261e-01f);
+    case 15: return make_float2(-9.807852507e-01f, -1.950903237e-01f);
+    default: return make_float2(1.f, 0.f);
+  }
+}
+
+// W_32^idx (conjugated if INV) times d; idx is a compile-time constant after unrolling
+template <bool INV>
+__device__ __forceinline__ float2 tw32_mul(int idx, float2 d) {
+  if (idx == 0) return d;
+  if (idx == 8) return INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+  float2 w = w32_const(idx);
+  if (INV) w.y = -w.y;
+  return cmul_canon(w, d);
+}
+
+// radix-2 DIF over the 32 registers: natural order in, bit-reversed order out.  One stage = 16
+// butterflies in a flat loop of constant trip count (nested loops with stage-dependent bounds
+// were left rolled by the compiler, which put the array in local memory).
+template <bool INV, int S>
+__device__ __forceinline__ void fft32_dif_stage(float2 (&v)[32]) {
+  constexpr int half = 16 >> S;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const int k = t % half, i = (t / half) * 2 * half + k, j = i + half;
+    const float2 a = v[i], b = v[j];
+    v[i] = make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+    v[j] = tw32_mul<INV>(k << S, make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)));
+  }
+}
+template <bool INV>
+__device__ __forceinline__ void fft32_dif(float2 (&v)[32]) {
+  fft32_dif_stage<INV, 0>(v); fft32_dif_stage<INV, 1>(v); fft32_dif_stage<INV, 2>(v);
+  fft32_dif_stage<INV, 3>(v); fft32_dif_stage<INV, 4>(v);
+}
+
+// radix-2 DIT: bit-reversed order in, natural order out
+template <bool INV, int S>
+__device__ __forceinline__ void fft32_dit_stage(float2 (&v)[32]) {
+  constexpr int half = 1 << S;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const int k = t % half, i = (t / half) * 2 * half + k, j = i + half;
+    const float2 w = tw32_mul<INV>(k * (16 >> S), v[j]);
+    const float2 a = v[i];
+    v[i] = make_float2(__fadd_rn(a.x, w.x), __fadd_rn(a.y, w.y));
+    v[j] = make_float2(__fsub_rn(a.x, w.x), __fsub_rn(a.y, w.y));
+  }
+}
+template <bool INV>
+__device__ __forceinline__ void fft32_dit(float2 (&v)[32]) {
+  fft32_dit_stage<INV, 0>(v); fft32_dit_stage<INV, 1>(v); fft32_dit_stage<INV, 2>(v);
+  fft32_dit_stage<INV, 3>(v); fft32_dit_stage<INV, 4>(v);
+}
+
+__host__ __device__ constexpr int bitrev5(int v) {
+  return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
+}
+
+// tw_perm[r][l] = W_1024^(l * bitrev5(r));  h_perm[g][r][l] = 2^-10 DFT_1024(h_g)[l + 32 bitrev5(r)]
+//
+// The work of one block is a loop over five stages that share ONE copy of the 32-point DIF code
+// (and one of the DIT): stage 0 loads x and ends in the twiddle + transpose, stage 1 finishes the
+// forward transform and parks X in shared memory, stages 2..4 are the three roots.  The inverse
+// DIF with conjugated twiddles is evaluated as conj(DIF(conj(.))), which is exact (negation
+// commutes with rounding): the conjugation of its input is folded into the table-twiddle
+// product, and the conjugation of its output does not change |y|^2.  A first version with four
+// inlined FFT bodies and X in registers spilled 400 B per thread to local memory and stalled on
+// instruction fetch (ncu: long_scoreboard 3.8, no_instruction 1.9 warps per issue).
+#ifndef LTB_OS_MIN_CTAS
+#define LTB_OS_MIN_CTAS 3
+#endif
+struct OsShared {
+  float2 tw[32 * 32];
+  float2 tr[kOsWarps][32 * 33];
+  float2 X[kOsWarps][32 * 32];
+};
+
+__global__ void __launch_bounds__(32 * kOsWarps, LTB_OS_MIN_CTAS)
+pss_corr_fft_kernel(const float2 *__restrict__ y_ring, float *__restrict__ p_ring, long long blk_first, int blk_count,
+                    unsigned cap_mask, int cap, int n_streams, const float2 *__restrict__ tw_perm,
+                    const float2 *__restrict__ h_perm) {
+  extern __shared__ __align__(16) unsigned char os_raw[];
+  OsShared &S = *reinterpret_cast<OsShared *>(os_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 1024; i += 32 * kOsWarps) S.tw[i] = tw_perm[i];
+  __syncthreads();
+  float2 *tr = S.tr[warp];
+  float2 *Xs = S.X[warp] + lane;
+  const float2 *twl = S.tw + lane;
+  const long long total = (long long)blk_count * n_streams;
+  for (long long w = (long long)blockIdx.x * kOsWarps + warp; w < total; w += (long long)gridDim.x * kOsWarps) {
+    const int stream = (int)(w / blk_count);
+    const long long b = blk_first + (w - (long long)stream * blk_count);
+    const long long base = b * kOsStep - 128;                       // absolute index of block sample 0
+    const float2 *yr = y_ring + (size_t)stream * cap;
+    float2 v[32];
+#pragma unroll 1
+    for (int stage = 0; stage < 5; ++stage) {
+      if (stage == 0) {
+        // lane = n2, j = n1; base is a multiple of 128 and so is the ring size: a 128-sample chunk
+        // never straddles the ring end, one masked offset serves four loads
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float2 *src = yr + (unsigned)((base + 128 * q) & cap_mask) + lane;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) v[4 * q + jj] = src[32 * jj];
+        }
+      } else if (stage >= 2) {
+        const float2 *hp = h_perm + (size_t)(stage - 2) * 1024 + lane;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          v[r] = cmul_canon(__ldg(hp + r * 32), Xs[r * 32]);
+          if ((r & 7) == 7) asm volatile("" ::: "memory");          // at most 8 + 8 loads in flight: no spills
+        }
+        fft32_dit<true>(v);                                         // over k2: v[c], c = n2, lane = k1
+        // conj(W_1024^(lane c)) v[c], conjugated: the DIF below then yields conj(y)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float2 t = twl[bitrev5(c) * 32];
+          const float2 d = v[c];
+          v[c].x = __fmaf_rn(t.x, d.x, __fmul_rn(t.y, d.y));
+          v[c].y = __fmaf_rn(t.x, -d.y, __fmul_rn(t.y, d.x));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tr[c * 33 + lane] = v[c];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = tr[lane * 33 + c];      // lane = n2, c = k1
+      }
+      fft32_dif<false>(v);
+      if (stage == 0) {                                             // v[r]: k1 = bitrev5(r), lane = n2
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = cmul_canon(twl[r * 32], v[r]);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tr[bitrev5(r) * 33 + lane] = v[r];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = tr[lane * 33 + c];      // lane = k1, c = n2
+      } else if (stage == 1) {                                      // v[r]: f = lane + 32 bitrev5(r)
+#pragma unroll
+        for (int r = 0; r < 32; ++r) Xs[r * 32] = v[r];
+        __syncwarp();
+      } else {                                                      // v[r] = conj(y[32 bitrev5(r) + lane])
+        float *pr = p_ring + ((size_t)stream * 3 + (stage - 2)) * cap + lane;
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+          float *dst = pr + (unsigned)((base + 128 * q) & cap_mask);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float2 y = v[bitrev5(4 * q + jj)];                // n1 = 4 q + jj
+            dst[32 * jj] = __fmaf_rn(y.x, y.x, __fmul_rn(y.y, y.y));
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // K3: per-chain sequential phase = pss::general_work + the head of sss::work
 //     (lib/pss_impl.cc:154-223, lib/sss_impl.cc:83-110), one CTA per (stream, N_id_2) chain.
 // ------------------------------------------------------------------------------------

@@ -146,6 +146,32 @@ void make_sss_tables(int n_id_2, SssTables &out) {
   }
 }
 
+void make_fft1024_twiddles(float *re, float *im) {
+  for (int i = 0; i < 1024; ++i) {
+    const double a = 2.0 * kPi * (double)i / 1024.0;
+    re[i] = (float)std::cos(a);
+    im[i] = (float)(-std::sin(a));
+  }
+  re[0] = 1.f;    im[0] = 0.f;   re[256] = 0.f; im[256] = -1.f;
+  re[512] = -1.f; im[512] = 0.f; re[768] = 0.f; im[768] = 1.f;
+}
+
+void make_os_filter(int n_id_2, float *H_re, float *H_im) {
+  PssTaps h;
+  make_pss_taps(n_id_2, h);
+  for (int f = 0; f < 1024; ++f) {
+    double ar = 0.0, ai = 0.0;
+    for (int m = 0; m < 128; ++m) {
+      const double a = 2.0 * kPi * (double)((f * m) & 1023) / 1024.0;
+      const double c = std::cos(a), sn = -std::sin(a);
+      ar += (double)h.re[m] * c - (double)h.im[m] * sn;
+      ai += (double)h.re[m] * sn + (double)h.im[m] * c;
+    }
+    H_re[f] = (float)(ar / 1024.0);
+    H_im[f] = (float)(ai / 1024.0);
+  }
+}
+
 void make_cexp_table(float *re, float *im) {
   for (int i = 0; i < 4096; ++i) {
     const double a = 2.0 * kPi * (double)i / 4096.0;

@@ -23,6 +23,11 @@ struct SssTables {
 };
 void make_sss_tables(int n_id_2, SssTables &out);
 
+// overlap-save FFT correlator: W_1024^i (exact at multiples of 256) and the filter spectra
+// 2^-10 * DFT_1024(h zero padded), natural order
+void make_fft1024_twiddles(float *re, float *im);  // 1024 entries
+void make_os_filter(int n_id_2, float *H_re, float *H_im);   // 1024 entries
+
 void make_cexp_table(float *re, float *im);        // 4097 entries
 void make_fft128_twiddles(float *re, float *im);   // 64 entries
 

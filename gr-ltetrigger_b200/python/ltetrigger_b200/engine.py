@@ -19,7 +19,7 @@ class Trigger:
 
     def __init__(self, n_streams, decim=1, psr_threshold=4.0, max_chunk=1 << 20, input_format=A.FMT_FC32,
                  track_after=16, track_every=8, record_all=True, keep_halfframes=False, device=0,
-                 root_mask=7, cuda_stream=None):
+                 root_mask=7, cuda_stream=None, corr_mode=A.CORR_DIRECT):
         cfg = A.TriggerConfig()
         cfg.struct_size = C.sizeof(A.TriggerConfig)
         cfg.device, cfg.n_streams, cfg.input_format, cfg.decim = device, n_streams, input_format, decim
@@ -27,6 +27,7 @@ class Trigger:
         cfg.track_after, cfg.track_every = track_after, track_every
         cfg.record_all, cfg.keep_halfframes = int(record_all), int(keep_halfframes)
         cfg.cuda_stream = cuda_stream
+        cfg.corr_mode = corr_mode
         self._h = C.c_void_p()
         A.check(A.lib().ltb_trigger_create(C.byref(cfg), C.byref(self._h)), "ltb_trigger_create")
         self.n_streams, self.decim, self.input_format = n_streams, decim, input_format
@@ -133,6 +134,15 @@ def kernel_pss_corr(x, device=0):
     return p
 
 
+def kernel_pss_corr_fft(x, device=0):
+    """Overlap-save FFT evaluation: x [n_streams, n] complex64 -> power [n_streams, 3, 896 * (n // 896)]."""
+    x = np.ascontiguousarray(np.atleast_2d(x), np.complex64)
+    s, n = x.shape
+    p = np.zeros((s, 3, n // A.OS_STEP * A.OS_STEP), np.float32)
+    A.check(A.lib().ltb_kernel_pss_corr_fft_host(device, x.ctypes.data, s, n, p.ctypes.data), "ltb_kernel_pss_corr_fft_host")
+    return p
+
+
 def kernel_decimate(x, decim, fmt=A.FMT_FC32, device=0):
     if fmt == A.FMT_FC32:
         x = np.ascontiguousarray(np.atleast_2d(x), np.complex64)
@@ -173,6 +183,18 @@ class tables:
     def cexp():
         r, i = np.zeros(4097, np.float32), np.zeros(4097, np.float32)
         A.check(A.lib().ltb_table_cexp(A.fptr(r), A.fptr(i)), "ltb_table_cexp")
+        return r, i
+
+    @staticmethod
+    def fft1024_twiddles():
+        r, i = np.zeros(1024, np.float32), np.zeros(1024, np.float32)
+        A.check(A.lib().ltb_table_fft1024_twiddles(A.fptr(r), A.fptr(i)), "ltb_table_fft1024_twiddles")
+        return r, i
+
+    @staticmethod
+    def os_filter(n_id_2):
+        r, i = np.zeros(1024, np.float32), np.zeros(1024, np.float32)
+        A.check(A.lib().ltb_table_os_filter(n_id_2, A.fptr(r), A.fptr(i)), "ltb_table_os_filter")
         return r, i
 
     @staticmethod

@@ -46,6 +46,11 @@ extern "C" {
 #define LTB_FMT_SC8  2             /* int8 I/Q, 2 B/sample, scaled by 1/128 on device */
 #define LTB_MAX_DECIM 64
 
+/* evaluation of the three-root matched filter (both bit-exact against the oracle's restatement) */
+#define LTB_CORR_DIRECT 0          /* folded direct form, FFMA2 */
+#define LTB_CORR_FFT    1          /* 1024-point overlap-save FFT blocks aligned to absolute sample indices */
+#define LTB_OS_STEP     896        /* outputs per overlap-save block */
+
 typedef struct { float re, im; } ltb_cf;
 
 /* ---- per-window record ---------------------------------------------------------
@@ -118,6 +123,7 @@ typedef struct {
   int32_t  record_all;        /* 1: record every general_work call; 0: emitted half-frames only */
   int32_t  keep_halfframes;   /* 1: keep each emitted (CFO-corrected) half-frame for ltb_trigger_fetch_halfframes */
   void    *cuda_stream;       /* cudaStream_t to launch on; NULL -> the library's own stream */
+  int32_t  corr_mode;         /* LTB_CORR_*; a struct_size that ends before this field selects LTB_CORR_DIRECT */
 } ltb_trigger_config;
 
 /* pss::make + sss::make + hier-block construction (lib/pss_impl.cc:42-83,
@@ -207,6 +213,9 @@ LTB_API int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_normal, 
  * each of n_streams host streams; x[<0] = 0.  power: [n_streams][3][n].
  * = srslte_pss_find_pss's convolution + srslte_vec_abs_square_cf without window truncation. */
 LTB_API int ltb_kernel_pss_corr_host(int device, const ltb_cf *x, int n_streams, int64_t n, float *power);
+/* The same powers from the overlap-save FFT evaluation (LTB_CORR_FFT) for the whole 896-output blocks
+ * of each stream: power: [n_streams][3][896 * (n / 896)]. */
+LTB_API int ltb_kernel_pss_corr_fft_host(int device, const ltb_cf *x, int n_streams, int64_t n, float *power);
 /* rational_resampler_ccc(1, decim) with default taps on host streams of n_in samples
  * (multiple of decim); fmt as above; y: [n_streams][n_in/decim]. */
 LTB_API int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in,
@@ -227,6 +236,9 @@ LTB_API int ltb_table_sss(int n_id_2, int32_t c0[31], int32_t c1[31], int32_t s_
 /* srslte_cfo_init's cexptab, 4096 (+1 spare) entries (lib/pss_impl.cc:78) */
 LTB_API int ltb_table_cexp(float tab_re[4097], float tab_im[4097]);
 LTB_API int ltb_table_fft128_twiddles(float w_re[64], float w_im[64]);
+/* LTB_CORR_FFT: W_1024^i and the filter spectrum 2^-10 DFT_1024(h) of one N_id_2, natural order */
+LTB_API int ltb_table_fft1024_twiddles(float w_re[1024], float w_im[1024]);
+LTB_API int ltb_table_os_filter(int n_id_2, float H_re[1024], float H_im[1024]);
 
 #ifdef __cplusplus
 }

@@ -18,8 +18,12 @@ inline std::string symbol_to_string(const pmt_t &p) { return p->sym; }
 inline pmt_t from_long(long v) { return make_(2, "", v); }
 inline long to_long(const pmt_t &p) { return p->val; }
 inline bool eq(const pmt_t &a, const pmt_t &b) { return a.get() == b.get(); }
-static const pmt_t PMT_NIL = make_(0, "", 0);
-static const pmt_t PMT_T = make_(1, "", 1);
-static const pmt_t PMT_F = make_(1, "", 0);
+// one object per process, whatever the translation unit (GNU Radio's are library globals)
+inline pmt_t get_PMT_NIL() { static const pmt_t p = make_(0, "", 0); return p; }
+inline pmt_t get_PMT_T() { static const pmt_t p = make_(1, "", 1); return p; }
+inline pmt_t get_PMT_F() { static const pmt_t p = make_(1, "", 0); return p; }
+#define PMT_NIL get_PMT_NIL()
+#define PMT_T get_PMT_T()
+#define PMT_F get_PMT_F()
 inline bool is_true(const pmt_t &p) { return !(p->kind == 1 && p->val == 0); }
 }  // namespace pmt

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts():
     from ltetrigger_b200 import _abi
     assert _abi.WINDOW_REC.itemsize == 88
-    assert C.sizeof(_abi.TriggerConfig) == 64
+    assert C.sizeof(_abi.TriggerConfig) == 72 and _abi.TriggerConfig.corr_mode.offset == 64
     assert C.sizeof(_abi.PssStats) == 32
     from oracle import oracle as O
     assert O.REC_DTYPE == _abi.WINDOW_REC
@@ -49,6 +49,11 @@ def test_tables_match_oracle(oracle):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     for a, b in zip(lt.tables.fft128_twiddles(), oracle.fft128_twiddles()):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for a, b in zip(lt.tables.fft1024_twiddles(), oracle.fft1024_twiddles()):      # overlap-save mode
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for r in range(3):
+        for a, b in zip(lt.tables.os_filter(r), oracle.os_filter(r)):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
 def test_invalid_inputs():
@@ -63,6 +68,17 @@ def test_invalid_inputs():
     assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS    # decim 65
     cfg.decim, cfg.input_format = 3, 7
     assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS    # unknown format
+    # ABI evolution: the config as it was before corr_mode was appended (64 bytes) is still accepted
+    # (validation passes; without a GPU the call then fails on the device, with one it succeeds)
+    cfg.decim, cfg.input_format, cfg.struct_size = 1, 0, 64
+    rc = L.ltb_trigger_create(C.byref(cfg), C.byref(h))
+    assert rc != lt.ERROR_INVALID_INPUTS
+    if rc == lt.SUCCESS:
+        L.ltb_trigger_destroy(h)
+    cfg.struct_size = 60
+    assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS
+    cfg.struct_size, cfg.corr_mode = C.sizeof(_abi.TriggerConfig), 5
+    assert L.ltb_trigger_create(C.byref(cfg), C.byref(h)) == lt.ERROR_INVALID_INPUTS    # unknown correlator
     re_, im_ = np.zeros(128, np.float32), np.zeros(128, np.float32)
     assert L.ltb_table_pss_taps(3, _abi.fptr(re_), _abi.fptr(im_)) == lt.ERROR_INVALID_INPUTS
     s = C.c_void_p()

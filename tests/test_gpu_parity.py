@@ -44,6 +44,22 @@ def test_pss_corr_kernel_linearity_full_size(lt):
     assert np.array_equal(p2, 4 * p1)
 
 
+@pytest.mark.parametrize("n", [896, 3000, 30000])
+def test_pss_corr_fft_kernel_bit_exact(lt, oracle, n):
+    """LTB_CORR_FFT: overlap-save blocks against the oracle's ORC_CONV_OS restatement, bit for bit,
+    and against the direct form within the north_star's tolerance."""
+    rng = np.random.default_rng(n)
+    x = rand_c64(rng, 3, n)
+    got = lt.kernel_pss_corr_fft(x)
+    for s in range(3):
+        want = oracle.pss_corr_os(x[s])
+        assert got[s].shape == want.shape
+        assert np.array_equal(got[s].view(np.uint32), want.view(np.uint32)), s
+        for r in range(3):
+            d = oracle.pss_corr_stream(x[s], r)[:want.shape[1]]
+            assert np.abs(got[s, r] - d).max() < 1e-4 * d.max()
+
+
 def _decim_case(oracle, rng, decim, fmt, n):
     if fmt == 0:
         x = rand_c64(rng, 2, n)
@@ -108,6 +124,37 @@ def test_fixture_records_bit_exact(lt, oracle, name):
     st = trig.stats(0, k)
     assert st.tracking == 1 and st.tracking_score == 16.0
     assert st.max_psr == want[want["n_id_2"] == k]["psr"].max()
+
+
+@pytest.mark.parametrize("name", list(FIXTURES))
+def test_fixture_records_fft_correlator(lt, oracle, name):
+    """The engine with corr_mode = LTB_CORR_FFT: records bit-identical to the oracle's ORC_CONV_OS
+    mode; decisions identical to the direct mode and to the reference's known answers."""
+    x, decim, cell_id = load_fixture(name, 0.5)
+    trig = lt.Trigger(n_streams=1, decim=decim, psr_threshold=4.0, max_chunk=96000 * decim, corr_mode=lt.CORR_FFT)
+    got = trig.run(x[None, :])
+    want = oracle.trigger_run(x[None, :], decim=decim, psr_threshold=4.0, conv_mode=oracle.CONV_OS)
+    assert_recs_equal(got, want)
+    cells = got[(got["flags"] & lt.F_CELL) != 0]
+    assert set(cells["cell_id"].tolist()) == {cell_id}
+    direct = oracle.trigger_run(x[None, :], decim=decim, psr_threshold=4.0)
+    for f in ("win_start", "emit_start", "flags", "peak_pos", "m0", "m1", "n_id_1", "cell_id"):
+        assert (got[f] == direct[f]).all(), f
+    np.testing.assert_allclose(got["psr"], direct["psr"], rtol=1e-4)
+
+
+def test_fft_correlator_chunking_and_batch(lt, oracle):
+    """Blocks are aligned to absolute sample indices and only whole blocks are evaluated, so ragged
+    chunk sizes give the same records; batched noisy streams against the oracle."""
+    from ltetrigger_b200 import synth
+    iq, ids = synth.batch(6, 384000, 0.0, master_seed=77)
+    want = oracle.trigger_run(iq, conv_mode=oracle.CONV_OS)
+    for chunk in (8 * 1117, 8 * 9001, 384000):
+        trig = lt.Trigger(n_streams=6, decim=1, max_chunk=chunk, corr_mode=lt.CORR_FFT)
+        got = trig.run(iq, chunk=chunk)
+        assert_recs_equal(got, want)
+    trig.reset()
+    assert_recs_equal(trig.run(iq), want)
 
 
 def test_chunking_invariance(lt, oracle):

@@ -153,3 +153,32 @@ def test_sc8_and_extended_cp(oracle):
     cells = a[(a["flags"] & oracle.F_CELL) != 0]
     assert len(cells) > 5 and set(cells["cell_id"].tolist()) == {311}
     assert ((cells["flags"] & oracle.F_CP_NORM) == 0).all()
+
+
+def test_overlap_save_mode(oracle):
+    """ORC_CONV_OS (the GPU's LTB_CORR_FFT arithmetic): the canonical 1024-point FFT against numpy,
+    block powers against the direct form, and the chain's decisions against the direct mode on a
+    fixture (magnitudes within the north_star's 1e-4; measured ~1e-6)."""
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(1024) + 1j * rng.standard_normal(1024)).astype(np.complex64)
+    X = oracle.fft1024(x)
+    ref = np.fft.fft(x.astype(np.complex128))
+    assert np.abs(X - ref).max() < 1e-6 * np.abs(ref).max()
+    assert np.abs(oracle.fft1024(X, inverse=True) / 1024 - x).max() < 2e-6
+    x = (rng.standard_normal(3000) + 1j * rng.standard_normal(3000)).astype(np.complex64)
+    p = oracle.pss_corr_os(x)
+    assert p.shape == (3, 2688)
+    for r in range(3):
+        d = oracle.pss_corr_stream(x, r)[:2688]
+        assert np.abs(p[r] - d).max() < 5e-6 * d.max()
+    # H_2 = conj-reversed H_1 (root 34 is the conjugate of root 29)
+    h1, h2 = oracle.os_filter(1), oracle.os_filter(2)
+    assert np.allclose(h2[0][1:], h1[0][:0:-1], atol=1e-9) and np.allclose(h2[1][1:], -h1[1][:0:-1], atol=1e-9)
+    y, decim, cell_id = load_fixture("6prb", 0.5)
+    a = oracle.trigger_run(y[None, :], conv_mode=oracle.CONV_DIRECT)
+    b = oracle.trigger_run(y[None, :], conv_mode=oracle.CONV_OS)
+    for f in ("win_start", "emit_start", "flags", "peak_pos", "m0", "m1", "n_id_1", "cell_id"):
+        assert (a[f] == b[f]).all(), f
+    m = a["psr"] > 0
+    np.testing.assert_allclose(a["psr"][m], b["psr"][m], rtol=1e-4)
+    np.testing.assert_allclose(a["peak_value"][m], b["peak_value"][m], rtol=1e-4)
