@@ -63,10 +63,10 @@ int ensure_constants(int device) {
   LTB_CUDA(cudaMemcpyToSymbol(c_pss_taps, full, sizeof full));
   float dt[1000];
   std::memset(dt, 0, sizeof dt);
-  {
-    std::vector<float> v = make_decim_taps(16);
-    if ((int)v.size() != decim_ntaps(16)) return fail(LTB_ERROR, "unexpected decimator tap count");
-    std::memcpy(dt + decim_tap_offset(16), v.data(), v.size() * sizeof(float));
+  for (int d = 4; d <= 16; d *= 2) {
+    std::vector<float> v = make_decim_taps(d);
+    if ((int)v.size() != decim_ntaps(d)) return fail(LTB_ERROR, "unexpected decimator tap count");
+    std::memcpy(dt + decim_tap_offset(d), v.data(), v.size() * sizeof(float));
   }
   LTB_CUDA(cudaMemcpyToSymbol(c_decim_taps, dt, sizeof dt));
   {
@@ -110,6 +110,8 @@ int ensure_constants(int device) {
 #define LTB_SMEM_ATTR_FMT(FMT)                                                                  \
   LTB_SMEM_ATTR(decimate_stream_kernel<FMT>, decim_stream_smem_bytes<FMT>());                   \
   LTB_SMEM_ATTR(decimate_any_kernel<FMT>, decim_any_smem_bytes(kMaxDecim));                     \
+  LTB_SMEM_ATTR((decimate_stream2_kernel<FMT, 8>), (decim_stream2_smem_bytes<FMT, 8>()));       \
+  LTB_SMEM_ATTR((decimate_stream2_kernel<FMT, 4>), (decim_stream2_smem_bytes<FMT, 4>()));       \
   LTB_SMEM_ATTR((decimate_kernel<FMT, 4>), decim_smem_bytes(4));                                \
   LTB_SMEM_ATTR((decimate_kernel<FMT, 6>), decim_smem_bytes(6));                                \
   LTB_SMEM_ATTR((decimate_kernel<FMT, 8>), decim_smem_bytes(8));                                \
@@ -178,7 +180,7 @@ int make_cexp_device(float2 **out) {
 }
 
 // ltb_debug_set_flag: [0] decimator dissection bits, [1] bit 0: decimate with the general kernel at
-// every rate, [2] extra dynamic smem for the tiled decimator (occupancy experiments), [3] unused
+// every rate, bit 1: D = 8, 4 with the tiled kernel instead of the streaming one, [2] extra dynamic smem for the tiled decimator (occupancy experiments), [3] unused
 int g_debug_flags[4] = {0, 0, 0, 0};
 
 bool valid_decim(int d) { return d >= 1 && d <= kMaxDecim; }
@@ -220,6 +222,22 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
     if (ctas > total) ctas = total;
     decimate_stream_kernel<FMT><<<(unsigned)ctas, kStrThreads, decim_stream_smem_bytes<FMT>(), st>>>(
         d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total, g_debug_flags[0]);
+  } else if ((decim == 8 || decim == 4) && !force_any && !(g_debug_flags[1] & 2)) {
+    // streaming variant for D = 8, 4 (debug flag 1 bit 1 selects the tiled kernel instead)
+    int dev = 0;
+    LTB_CUDA(cudaGetDevice(&dev));
+    const int seg = decim == 8 ? str2_seg<8>() : str2_seg<4>();
+    const int sps = (m + seg - 1) / seg;
+    const long long total = (long long)sps * n_streams;
+    if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator segments in one call");
+    long long ctas = 2LL * (g_sm_count[dev] > 0 ? g_sm_count[dev] : 148);
+    if (ctas > total) ctas = total;
+    if (decim == 8)
+      decimate_stream2_kernel<FMT, 8><<<(unsigned)ctas, kStrThreads, decim_stream2_smem_bytes<FMT, 8>(), st>>>(
+          d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total);
+    else
+      decimate_stream2_kernel<FMT, 4><<<(unsigned)ctas, kStrThreads, decim_stream2_smem_bytes<FMT, 4>(), st>>>(
+          d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total);
   } else if (decim_is_tiled(decim) && !force_any) {
 #define LTB_DECIM_CASE(D)                                                                             \
   case D: {                                                                                           \

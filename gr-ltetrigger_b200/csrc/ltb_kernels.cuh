@@ -43,7 +43,7 @@ template <> struct fmt_elem<LTB_FMT_SC8> { typedef char2 type; };
 __constant__ float2 c_pss_coef[2][65][2];
 // full 128-tap filters per N_id_2 (CFO estimate): (re, im)
 __constant__ float2 c_pss_taps[3][128];
-// decimator taps for D = 16 at offset 472 (padded with zeros): decimate_stream_kernel
+// decimator taps for D = 4, 8, 16 at offsets 72, 208, 472 (padded with zeros): the streaming kernels
 __constant__ float c_decim_taps[1000];
 __constant__ float2 c_fft128_tw[64];
 // SSS tables per N_id_2: c0, c1 (31 each); shared s_tilde, z_tilde; N_id_1 table
@@ -587,6 +587,201 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
 }
 
 // ------------------------------------------------------------------------------------
+// K1s2: the streaming decimator generalised to D = 8 and D = 4 (15.36 and 7.68 Msps), where the
+// tiled kernel below reaches half the FFMA2 rate (shared-memory instruction queue, ncu).  Same
+// machinery as decimate_stream_kernel -- TMA bulk copies of the input as it lies in memory, two
+// buffers, two persistent 8-warp CTAs per SM, taps in registers, element-major FFMA2 order,
+// per-warp scratch transposition for the pairwise tree -- with one more index in the lane
+// mapping: a half-warp is D positions x R = 16 / D output residues, lane (r, p) runs the canonical
+// chain of position p for the 16 outputs k = K0 + R j + r.  The 16 lanes of a half-warp then read
+// R consecutive input blocks, 128 contiguous bytes, for every window element (conflict-free
+// LDS.64 in natural layout, as at D = 16); the price is 15 R + 33 window elements per lane instead
+// of 48, each feeding 33 / R taps.
+// ------------------------------------------------------------------------------------
+template <int D> __host__ __device__ constexpr int str2_R() { return 16 / D; }
+template <int D> __host__ __device__ constexpr int str2_seg() { return kStrWarps * 32 * str2_R<D>(); }   // outputs per segment
+// blocks copied in front of the segment: 33 of filter history, plus what it takes to start the
+// bulk copy on a 16-byte boundary (segments start at multiples of 256 R outputs)
+template <int FMT, int D> __host__ __device__ constexpr int str2_lead() {
+  return (33 * D * fmt_bytes(FMT)) % 16 == 0 ? 33 : (34 * D * fmt_bytes(FMT)) % 16 == 0 ? 34 : 36;
+}
+template <int FMT, int D> __host__ __device__ constexpr int str2_buf_bytes() {
+  return (str2_seg<D>() + str2_lead<FMT, D>()) * D * fmt_bytes(FMT);
+}
+template <int FMT, int D> __host__ __device__ constexpr size_t decim_stream2_smem_bytes() {
+  return (size_t)kStrBufs * str2_buf_bytes<FMT, D>() + sizeof(float2) * kStrScratch * kStrWarps;
+}
+
+template <int FMT, int D>
+__global__ void __launch_bounds__(kStrThreads, 2)
+decimate_stream2_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
+                        float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int segs_per_stream,
+                        int total_segs) {
+  constexpr int R = str2_R<D>();
+  constexpr int SEG = str2_seg<D>();
+  constexpr int LEAD = str2_lead<FMT, D>();
+  constexpr int NBLK = SEG + LEAD;
+  constexpr int BPS = fmt_bytes(FMT);
+  constexpr int BUF = str2_buf_bytes<FMT, D>();
+  constexpr int NE = 15 * R + kDecQ;                               // window elements per lane
+  static_assert(D == 4 || D == 8, "D = 16: decimate_stream_kernel");
+  static_assert(BUF % 16 == 0 && (LEAD * D * BPS) % 16 == 0, "cp.async.bulk size and alignment");
+  typedef typename fmt_elem<FMT>::type elem_t;
+  extern __shared__ __align__(128) unsigned char s_raw[];          // [kStrBufs][NBLK blocks][D positions], scratch
+  __shared__ __align__(8) unsigned long long s_full[kStrBufs];
+  __shared__ unsigned s_done[kStrBufs];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = lane >> 4, q16 = lane & 15, r = q16 / D, p = q16 % D;
+  const long long n_in = (long long)n_out * D;
+
+  const int s_begin = (int)((long long)total_segs * blockIdx.x / gridDim.x);
+  const int s_end = (int)((long long)total_segs * (blockIdx.x + 1) / gridDim.x);
+  if (s_begin >= s_end) return;
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < kStrBufs; ++b) { mbar_init(&s_full[b], 1); s_done[b] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  float c[kDecQ];                                                  // this lane's taps: branch v = (D - p) % D
+  {
+    const int v = (D - p) % D;
+#pragma unroll
+    for (int q = 0; q < kDecQ; ++q) {
+      const float t = c_decim_taps[decim_tap_offset(D) + q * D + v];   // zero padded beyond ntaps
+      c[q] = FMT == LTB_FMT_FC32 ? t : __fmul_rn(t, fmt_scale(FMT));
+      asm volatile("" : "+f"(c[q]));
+    }
+  }
+
+  struct Seg { int stream, k0; };
+  const int k_end = segs_per_stream * SEG;
+  auto advance = [&](Seg &S) { S.k0 += SEG; if (S.k0 >= k_end) { S.k0 = 0; S.stream++; } };
+  auto is_fast = [&](const Seg &S) { return S.k0 >= LEAD && (long long)D * (S.k0 + SEG) <= n_in; };
+  auto request = [&](const Seg &S, int b) {
+    const char *src = (const char *)in + (long long)S.stream * stride_bytes;
+    mbar_expect_tx(&s_full[b], BUF);
+    bulk_copy_g2s(s_raw + b * BUF, src + (long long)D * (S.k0 - LEAD) * BPS, BUF, &s_full[b]);
+  };
+  Seg cur, req;
+  cur.stream = s_begin / segs_per_stream;
+  cur.k0 = (s_begin - cur.stream * segs_per_stream) * SEG;
+  req = cur;
+  for (int j = 0; j < kStrBufs && s_begin + j < s_end; ++j) {
+    if (tid == 0 && is_fast(req)) request(req, j);
+    advance(req);
+  }
+
+  unsigned phase_bits = 0;
+  // window element e of this lane: block K0 + r - (p > 0) + e, K0 = k0 + (2 warp + half) 16 R
+  const int sub0 = (2 * warp + half) * 16 * R;                     // first output of this half-warp in the segment
+  const int lane_elem = (sub0 + r - (p > 0 ? 1 : 0) + LEAD) * D + p;
+  float2 *scratch = reinterpret_cast<float2 *>(s_raw + kStrBufs * BUF) + warp * kStrScratch + half * 16 * kStrScratchRow;
+
+  for (int i = s_begin; i < s_end; ++i) {
+    const int b = (i - s_begin) % kStrBufs;
+    const Seg S = cur;
+    elem_t *buf = reinterpret_cast<elem_t *>(s_raw + b * BUF);
+    if (is_fast(S)) {
+      mbar_wait(&s_full[b], (phase_bits >> b) & 1u);
+      phase_bits ^= 1u << b;
+    } else {
+      // boundary segment: element-wise, with the carried tail before the chunk and zeros after it
+      __syncthreads();
+      const char *src = (const char *)in + (long long)S.stream * stride_bytes;
+      const long long i_first = (long long)D * (S.k0 - LEAD);
+      const float2 *tail = tail_in + (size_t)S.stream * kTailCap;
+      for (int j = tid; j < NBLK * D; j += kStrThreads) {
+        const long long idx = i_first + j;
+        float2 val = make_float2(0.f, 0.f);
+        if (idx >= 0) { if (idx < n_in) val = load_in_sample<FMT>(src, idx); }
+        else if (idx >= -kTailCap) val = tail[kTailCap + idx];
+        if (FMT == LTB_FMT_FC32) reinterpret_cast<float2 *>(buf)[j] = val;
+        else if (FMT == LTB_FMT_SC16) reinterpret_cast<short2 *>(buf)[j] = make_short2((short)__fmul_rn(val.x, 32768.0f), (short)__fmul_rn(val.y, 32768.0f));
+        else reinterpret_cast<char2 *>(buf)[j] = make_char2((signed char)__fmul_rn(val.x, 128.0f), (signed char)__fmul_rn(val.y, 128.0f));
+      }
+      __syncthreads();
+    }
+
+    // element-major: element e feeds output j with tap q = R j - e; walking e downwards keeps every
+    // accumulator's chain in ascending q (the canonical order)
+    float2 acc[kDecT];
+    {
+      const elem_t *base = buf + lane_elem;
+      auto ld = [&](int e) -> float2 {
+        const elem_t v = base[e * D];
+        return make_float2((float)v.x, (float)v.y);
+      };
+      constexpr int PF = 4;
+      constexpr int E_TOP = 15 * R, E_BOT = -(kDecQ - 1);
+      float2 x[PF];
+#pragma unroll
+      for (int j = 0; j < PF; ++j) x[j] = ld(E_TOP - j);
+#pragma unroll
+      for (int e = E_TOP; e >= E_BOT; --e) {
+        const int slot = (E_TOP - e) % PF;
+        const float2 xe = x[slot];
+        if (e - PF >= E_BOT) x[slot] = ld(e - PF);
+#pragma unroll
+        for (int j = 0; j < kDecT; ++j) {
+          const int q = R * j - e;
+          if (q >= 0 && q < kDecQ) {
+            const float2 cc = make_float2(c[q], c[q]);
+            acc[j] = ffma2(cc, xe, q == 0 ? make_float2(0.f, 0.f) : acc[j]);
+          }
+        }
+      }
+      (void)NE;
+    }
+    // transposition through the warp's scratch, two passes of 8 outputs per lane: row = (r, p),
+    // column = j.  Lane (a, jj) of a half-warp then sums the D positions of R / 2 outputs
+    // (residues r' = a R / 2 + u) in the canonical pairwise tree.
+    {
+      const int a = q16 >> 3, jj = q16 & 7;
+      float2 *wr = scratch + q16 * kStrScratchRow;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        __syncwarp();
+#pragma unroll
+        for (int o = 0; o < 8; ++o) wr[o] = acc[8 * pass + o];
+        __syncwarp();
+        float2 res[R / 2];
+#pragma unroll
+        for (int u = 0; u < R / 2; ++u) {
+          const int rr = a * (R / 2) + u;
+          float2 pp[D];
+#pragma unroll
+          for (int t = 0; t < D; ++t) pp[t] = scratch[(rr * D + t) * kStrScratchRow + jj];
+#pragma unroll
+          for (int w2 = 1; w2 < D; w2 <<= 1) {
+#pragma unroll
+            for (int t = 0; t < D; t += 2 * w2) pp[t] = fadd2(pp[t], pp[t + w2]);
+          }
+          res[u] = pp[0];
+        }
+        // outputs K0 + R (8 pass + jj) + a R / 2 + u, u = 0 .. R/2 - 1: consecutive
+        const int k = S.k0 + sub0 + R * (8 * pass + jj) + a * (R / 2);
+        float2 *dst = y_ring + (size_t)S.stream * cap;
+        if (R == 2) {
+          if (k < n_out) dst[(unsigned)((n_base + k) & cap_mask)] = res[0];
+        } else {
+          // two consecutive outputs, k even: one 16-byte store (n_out, n_base and cap are multiples of 8)
+          if (k < n_out)
+            *reinterpret_cast<float4 *>(&dst[(unsigned)((n_base + k) & cap_mask)]) = make_float4(res[0].x, res[0].y, res[R / 2 - 1].x, res[R / 2 - 1].y);
+        }
+      }
+    }
+    __syncwarp();
+    if (i + kStrBufs < s_end) {
+      if (lane == 0 && (atomicAdd(&s_done[b], 1u) % kStrWarps) == kStrWarps - 1 && is_fast(req)) request(req, b);
+      advance(req);
+    }
+    advance(cur);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // K1a: decimator for every other integer rate (D = 5, 7, 9..11, 13..15, 17..64): the reference
 // accepts any multiple of 1.92 Msps (examples/cell_search_file.py:50-57).  One CTA = 256 outputs
 // of one stream, one output per thread.  The 289 input blocks are staged transposed (row =
@@ -869,9 +1064,11 @@ __device__ __forceinline__ void fft32_dif_stage(float2 (&v)[32]) {
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
     const int k = t % half, i = (t / half) * 2 * half + k, j = i + half;
+    // packed add; a - b as fma(b, -1, a), which rounds exactly like the subtraction: one issue
+    // slot per complex add instead of two (the kernel is issue bound)
     const float2 a = v[i], b = v[j];
-    v[i] = make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
-    v[j] = tw32_mul<INV>(k << S, make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)));
+    v[i] = fadd2(a, b);
+    v[j] = tw32_mul<INV>(k << S, ffma2(b, make_float2(-1.f, -1.f), a));
   }
 }
 template <bool INV>
@@ -889,8 +1086,8 @@ __device__ __forceinline__ void fft32_dit_stage(float2 (&v)[32]) {
     const int k = t % half, i = (t / half) * 2 * half + k, j = i + half;
     const float2 w = tw32_mul<INV>(k * (16 >> S), v[j]);
     const float2 a = v[i];
-    v[i] = make_float2(__fadd_rn(a.x, w.x), __fadd_rn(a.y, w.y));
-    v[j] = make_float2(__fsub_rn(a.x, w.x), __fsub_rn(a.y, w.y));
+    v[i] = fadd2(a, w);
+    v[j] = ffma2(w, make_float2(-1.f, -1.f), a);
   }
 }
 template <bool INV>
