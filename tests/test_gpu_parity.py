@@ -79,13 +79,15 @@ def test_decimate_kernel_bit_exact(lt, oracle, decim, fmt):
     """rational_resampler_ccc(1, D) for any integer D (examples/cell_search_file.py:50-57): the
     tiled kernel (2, 3, 4, 6, 8, 12), the streaming kernel (16) and the general kernel."""
     rng = np.random.default_rng(decim + 100 * fmt)
-    x, want = _decim_case(oracle, rng, decim, fmt, 1000 * decim)
-    got = lt.kernel_decimate(x, decim, fmt)
-    for s in range(2):
-        assert np.array_equal(got[s].view(np.uint32), want[s].view(np.uint32))
+    # 1000 outputs: boundary segments only; 5000: whole segments of the streaming kernels too
+    for n_out in (1000, 5000):
+        x, want = _decim_case(oracle, rng, decim, fmt, n_out * decim)
+        got = lt.kernel_decimate(x, decim, fmt)
+        for s in range(2):
+            assert np.array_equal(got[s].view(np.uint32), want[s].view(np.uint32)), n_out
 
 
-@pytest.mark.parametrize("decim", [2, 8, 12, 16])
+@pytest.mark.parametrize("decim", [2, 4, 8, 12, 16])
 def test_general_decimator_agrees_with_tuned_kernels(lt, oracle, decim):
     """Debug flag 1 routes every rate through decimate_any_kernel: three independent kernels and
     the oracle give the same bits."""
@@ -100,6 +102,14 @@ def test_general_decimator_agrees_with_tuned_kernels(lt, oracle, decim):
     for s in range(2):
         assert np.array_equal(general[s].view(np.uint32), want[s].view(np.uint32))
         assert np.array_equal(tuned[s].view(np.uint32), want[s].view(np.uint32))
+    if decim in (4, 8):                      # these rates also have the tiled kernel (flag bit 1)
+        lt.lib().ltb_debug_set_flag(1, 2)
+        try:
+            tiled = lt.kernel_decimate(x, decim, 0)
+        finally:
+            lt.lib().ltb_debug_set_flag(1, 0)
+        for s in range(2):
+            assert np.array_equal(tiled[s].view(np.uint32), want[s].view(np.uint32))
 
 
 # ---- engine: the four bundled test_frames ------------------------------------------------
