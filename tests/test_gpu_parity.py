@@ -363,3 +363,41 @@ def test_two_host_calls_in_flight(lt, oracle):
     recs = np.concatenate(got)
     recs = recs[np.lexsort((recs["win_index"], recs["n_id_2"], recs["stream"]))]
     assert_recs_equal(recs, want)
+
+
+@pytest.mark.parametrize("corr", ["direct", "fft"])
+def test_full_path_scaling_and_permutation_properties(lt, corr):
+    """Size-independent properties of the whole path at a bench-like size (no oracle: 48 streams x
+    30.72 Msps x 100 ms, decimate by 16): doubling the input is exact in float32, so every
+    decision, index, PSR and CFO keeps its bits while powers scale by 4 (SSS correlations by 2);
+    and streams are independent, so permuting them permutes the record lists."""
+    from ltetrigger_b200 import synth
+    rng = np.random.default_rng(11)
+    n, S = 16 * 192000, 48
+    base = np.stack([synth.capture(int(c), n, snr_db=4.0, decim=16, seed=int(c)) for c in rng.integers(0, 504, 6)])
+    x = np.empty((S, n), np.complex64)
+    for s in range(S):
+        x[s] = np.roll(base[s % 6], int(rng.integers(0, n))) + 0.05 * rand_c64(rng, n)
+    mode = lt.CORR_FFT if corr == "fft" else lt.CORR_DIRECT
+
+    def run(iq):
+        trig = lt.Trigger(n_streams=S, decim=16, max_chunk=n, corr_mode=mode)
+        out = trig.run(iq)
+        trig.close()
+        return out
+
+    a, b = run(x), run(2 * x)
+    assert len(a) == len(b) and len(a) > 20 * S
+    for f in a.dtype.names:
+        if f in ("peak_value",):
+            assert np.array_equal(4 * a[f], b[f]), f
+        elif f in ("m0_val", "m1_val"):
+            assert np.array_equal(2 * a[f], b[f]) or np.array_equal(4 * a[f], b[f]), f
+        else:
+            assert a[f].tobytes() == b[f].tobytes(), f
+    perm = rng.permutation(S)
+    c = run(x[perm])
+    for s_new, s_old in enumerate(perm):
+        ra, rc = a[a["stream"] == s_old], c[c["stream"] == s_new].copy()
+        rc["stream"] = s_old
+        assert ra.tobytes() == rc.tobytes(), (s_new, s_old)
