@@ -63,3 +63,15 @@ def assert_recs_equal(got, want, float_fields_exact=True):
                 i = int(np.argmin(g == w))
                 raise AssertionError("field %s differs at record %d: got %r want %r (stream %d root %d win %d)"
                                      % (name, i, g[i], w[i], want["stream"][i], want["n_id_2"][i], want["win_index"][i]))
+
+
+def snr_demo_capture(seconds, seed, snr_db=-10.405):
+    """The state the reference documents in docs/gr_ltetrigger_snr_demo.png (examples/snr_ltetrigger.grc):
+    the 6 PRB test frame plus Gaussian noise at a measured SNR of -10.405 dB (signal power over noise
+    power across the 1.92 MHz band), demod threshold 1.7 -> "Tracking: True, Cell ID: 123, PRBs: 6,
+    PHICH Resources: '1', CP Mode: 'Normal'"."""
+    x, _, _ = load_fixture("6prb", seconds)
+    rng = np.random.default_rng(seed)
+    pn = np.mean(np.abs(x) ** 2) / 10 ** (snr_db / 10)
+    noise = np.sqrt(pn / 2) * (rng.standard_normal(len(x)) + 1j * rng.standard_normal(len(x)))
+    return (x + noise).astype(np.complex64)

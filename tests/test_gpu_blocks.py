@@ -111,6 +111,24 @@ def test_downlink_trigger_c_like_reference_qa(lt, name):
     assert trig.psr_threshold == 1.5 and trig.pss1.psr_threshold() == 1.5
 
 
+def test_reference_snr_demo_screenshot_gpu(lt):
+    """docs/gr_ltetrigger_snr_demo.png of the reference through the GPU hier block: -10.4 dB, threshold
+    1.7 -> cell 123 tracked, 6 PRB, PHICH resources '1', normal CP (tests/conftest.py::snr_demo_capture)."""
+    from conftest import snr_demo_capture
+    y = snr_demo_capture(8.0, 0)
+    trig = lt.downlink_trigger_c(psr_threshold=1.7, exit_on_success=True)
+    tracked = []
+    trig.msg_connect("track", tracked.append)
+    for a in range(0, len(y) // 8 * 8, 96000):
+        trig.work(y[a:a + 96000])
+        if tracked:
+            break
+    assert len(tracked) >= 1
+    cell = tracked[0]
+    assert (cell["cell_id"], cell["nof_prb"], cell["nof_phich_resources"], cell["cp_len"]) == (123, 6, "1", "Normal")
+    assert trig.pss0.tracking_score() > 0
+
+
 def test_custom_mib_sink_and_drop(lt):
     """A custom mib stage sees every emitted half-frame with its tags; track / drop forwarding."""
     x, cell_id = search_rate(lt, "6prb", 0.3)

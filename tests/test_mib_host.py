@@ -6,7 +6,7 @@ half-frames, the product's host code decodes them."""
 import numpy as np
 import pytest
 
-from conftest import FIXTURES, load_fixture
+from conftest import FIXTURES, load_fixture, snr_demo_capture
 
 NOF_PRB = {"6prb": 6, "25prb": 25, "50prb": 50, "100prb": 100}
 
@@ -43,6 +43,38 @@ def test_mib_block_on_oracle_chain(oracle, name):
     assert cell["phich_len"] == "Normal" and cell["nof_phich_resources"] == "1"
     assert set(cell) == {"cell_id", "nof_tx_ports", "cp_len", "nof_prb", "phich_len", "nof_phich_resources",
                          "sfn_offset", "tracking_start_time"}      # lib/mib_impl.cc:185-251
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_reference_snr_demo_screenshot(oracle, seed):
+    """docs/gr_ltetrigger_snr_demo.png of the reference: at -10.4 dB and threshold 1.7 the trigger is
+    tracking cell 123 and has decoded 6 PRB, PHICH resources '1', normal CP.  Same state here (oracle
+    chain N_id_2 = 0 + host mib), within 8 s of signal; junk cell ids from the SSS at this SNR never
+    pass the PBCH CRC."""
+    import ltetrigger_b200 as lt
+    y = snr_demo_capture(8.0, seed)
+    op, os_, mb = oracle.Pss(0, 1.7), oracle.Sss(0), lt.mib(exit_on_success=True)
+    tracked = []
+    mb.msg_connect("track", tracked.append)
+    buf = np.concatenate([np.zeros(960, np.complex64), y])
+    pos, written = 960, 0
+    while pos - 960 + oracle.LOOKAHEAD <= len(y) and not mb.done:
+        nout, ncons, out, rec = op.work(buf, pos)
+        if nout:
+            lost = bool(rec["flags"] & oracle.F_TAG_LOST)
+            _, srec = os_.work(out, lost)
+            tags = [lt.tag_t(written, "tracking_lost", None)] if lost else []
+            if srec["flags"] & oracle.F_CELL:
+                tags += [lt.tag_t(written, "cell_id", int(srec["cell_id"])),
+                         lt.tag_t(written, "cp_type", bool(srec["flags"] & oracle.F_CP_NORM))]
+            mb._in_tags, mb._nitems_read = tags, written
+            mb.general_work(9600, [9600], [out], [None])
+            written += nout
+        pos += ncons
+    assert mb.done and len(tracked) == 1
+    cell = tracked[0]
+    assert (cell["cell_id"], cell["nof_prb"], cell["nof_phich_resources"], cell["cp_len"]) == (123, 6, "1", "Normal")
+    assert op.tracking_score() > 0                                       # "Tracking: True"
 
 
 def test_mib_decode_rejects_noise_sf5_and_bad_arguments():
