@@ -172,3 +172,37 @@ def test_cell_search_file_cli(lt, name, rate, capsys):
             cli.main(cli.parse([path, "-s", "2M"]))          # not a multiple of 1.92 MHz
     finally:
         os.remove(path)
+
+
+def test_cell_search_batch_cli(lt, tmp_path):
+    """examples/cell_search_batch.py: several captures as the streams of one engine; per file the
+    reference's cell dictionary or NOT_FOUND (same fields as cell_search_file.py)."""
+    import importlib.util
+    import json
+    import os
+    import sys
+    from conftest import GOLDEN, ROOT
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    spec = importlib.util.spec_from_file_location("cell_search_batch", os.path.join(ROOT, "examples", "cell_search_batch.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    fixture = os.path.join(GOLDEN, "test_frames", FIXTURES["25prb"][0])
+    x = np.fromfile(fixture, np.complex64)
+    rng = np.random.default_rng(9)
+    noisy = np.tile(x, 8)
+    noisy = (noisy + 0.3 * np.sqrt(np.mean(np.abs(x) ** 2)) * (rng.standard_normal(len(noisy)) + 1j * rng.standard_normal(len(noisy)))).astype(np.complex64)
+    noise = (0.1 * (rng.standard_normal(len(noisy)) + 1j * rng.standard_normal(len(noisy)))).astype(np.complex64)
+    f_noisy, f_noise = str(tmp_path / "noisy.fc32"), str(tmp_path / "noise.fc32")
+    noisy.tofile(f_noisy)
+    noise.tofile(f_noise)
+    res = [json.loads(r) for r in cli.main(cli.parse([fixture, f_noisy, f_noise, "-s", "7.68M", "--repeat", "--cut-off", "7.68M"]))]
+    assert [r["status"] for r in res] == ["FOUND", "FOUND", "NOT_FOUND"]
+    for r in res[:2]:
+        assert (r["cell_id"], r["nof_prb"], r["cp_len"], r["nof_tx_ports"], r["nof_phich_resources"]) == (124, 25, "Normal", 1, "1")
+    assert [os.path.basename(r["file"]) for r in res] == [os.path.basename(fixture), "noisy.fc32", "noise.fc32"]
+    # the same captures as sc16 files
+    f16 = str(tmp_path / "noisy.sc16")
+    s = 32767.0 / (4 * np.abs(noisy).max())
+    np.stack([np.round(noisy.real * s), np.round(noisy.imag * s)], axis=-1).astype(np.int16).tofile(f16)
+    res = [json.loads(r) for r in cli.main(cli.parse([f16, "-s", "7.68M", "--format", "sc16", "--repeat", "--cut-off", "7.68M"]))]
+    assert res[0]["status"] == "FOUND" and res[0]["cell_id"] == 124 and res[0]["nof_prb"] == 25
