@@ -72,7 +72,7 @@ int ensure_constants(int device) {
   {
     static float2 pairs[sizeof(c_decim_pairs) / sizeof(float2)];
     std::memset(pairs, 0, sizeof pairs);
-    for (int d = 2; d <= 12; ++d) {
+    for (int d = 2; d <= 15; ++d) {
       if (!decim_is_tiled(d)) continue;
       std::vector<float> vq = make_decim_branch_taps(d);
       if (vq.empty()) return fail(LTB_ERROR, "unexpected decimator tap count");
@@ -112,10 +112,18 @@ int ensure_constants(int device) {
   LTB_SMEM_ATTR(decimate_any_kernel<FMT>, decim_any_smem_bytes(kMaxDecim));                     \
   LTB_SMEM_ATTR((decimate_stream2_kernel<FMT, 8>), (decim_stream2_smem_bytes<FMT, 8>()));       \
   LTB_SMEM_ATTR((decimate_stream2_kernel<FMT, 4>), (decim_stream2_smem_bytes<FMT, 4>()));       \
-  LTB_SMEM_ATTR((decimate_kernel<FMT, 4>), decim_smem_bytes(4));                                \
-  LTB_SMEM_ATTR((decimate_kernel<FMT, 6>), decim_smem_bytes(6));                                \
-  LTB_SMEM_ATTR((decimate_kernel<FMT, 8>), decim_smem_bytes(8));                                \
-  LTB_SMEM_ATTR((decimate_kernel<FMT, 12>), decim_smem_bytes(12));
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 4>), decim_smem_bytes(4)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 5>), decim_smem_bytes(5)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 6>), decim_smem_bytes(6)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 7>), decim_smem_bytes(7)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 8>), decim_smem_bytes(8)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 9>), decim_smem_bytes(9)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 10>), decim_smem_bytes(10)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 11>), decim_smem_bytes(11)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 12>), decim_smem_bytes(12)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 13>), decim_smem_bytes(13)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 14>), decim_smem_bytes(14)); \
+  LTB_SMEM_ATTR((decimate_kernel<FMT, 15>), decim_smem_bytes(15));
   LTB_SMEM_ATTR_FMT(LTB_FMT_FC32)
   LTB_SMEM_ATTR_FMT(LTB_FMT_SC16)
   LTB_SMEM_ATTR_FMT(LTB_FMT_SC8)
@@ -245,12 +253,9 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
         d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, n_streams, g_debug_flags[0]);           \
   } break;
     switch (decim) {
-      LTB_DECIM_CASE(2)
-      LTB_DECIM_CASE(3)
-      LTB_DECIM_CASE(4)
-      LTB_DECIM_CASE(6)
-      LTB_DECIM_CASE(8)
-      LTB_DECIM_CASE(12)
+      LTB_DECIM_CASE(2) LTB_DECIM_CASE(3) LTB_DECIM_CASE(4) LTB_DECIM_CASE(5) LTB_DECIM_CASE(6) LTB_DECIM_CASE(7)
+      LTB_DECIM_CASE(8) LTB_DECIM_CASE(9) LTB_DECIM_CASE(10) LTB_DECIM_CASE(11) LTB_DECIM_CASE(12)
+      LTB_DECIM_CASE(13) LTB_DECIM_CASE(14) LTB_DECIM_CASE(15)
       default: return fail(LTB_ERROR_INVALID_INPUTS, "unsupported decimation");
     }
 #undef LTB_DECIM_CASE
@@ -415,6 +420,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   P.n_total = t->n_total; P.cap_mask = t->cap_mask; P.cap = t->cap; P.w_max = t->w_cur;
   P.track_after = c.track_after; P.track_every = c.track_every; P.record_all = c.record_all;
   P.root_mask = c.root_mask;
+  P.tdd = c.frame_type == LTB_FRAME_TDD;
   P.chain_counter = t->d_sss_count + 1; P.n_chains = t->n_chains;
   {
     int ctas = 4 * (g_sm_count[c.device] > 0 ? g_sm_count[c.device] : 148);
@@ -465,7 +471,8 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   std::memcpy(&c, cfg, cfg->struct_size);
   c.struct_size = sizeof c;
   if (c.n_streams <= 0 || !valid_decim(c.decim) || !valid_format(c.input_format) ||
-      c.max_chunk <= 0 || (c.root_mask & ~7) || (c.corr_mode != LTB_CORR_DIRECT && c.corr_mode != LTB_CORR_FFT))
+      c.max_chunk <= 0 || (c.root_mask & ~7) || (c.corr_mode != LTB_CORR_DIRECT && c.corr_mode != LTB_CORR_FFT) ||
+      (c.frame_type != LTB_FRAME_FDD && c.frame_type != LTB_FRAME_TDD))
     return fail(LTB_ERROR_INVALID_INPUTS, "invalid trigger configuration");
   if (c.root_mask == 0) c.root_mask = 7;
   if (c.track_after <= 0) c.track_after = 16;
@@ -705,6 +712,7 @@ int ltb_trigger_last_kernel_times(ltb_trigger *t, float ms[4]) {
 // ==========================================================================================
 struct ltb_sss {
   int device, n_id_2;
+  int frame_type = LTB_FRAME_FDD;
   float *d_cp = nullptr;
   int *d_count = nullptr;
 };
@@ -735,6 +743,12 @@ int ltb_sss_destroy(ltb_sss *s) {
   return LTB_SUCCESS;
 }
 
+int ltb_sss_set_frame_type(ltb_sss *s, int frame_type) {
+  if (!s || (frame_type != LTB_FRAME_FDD && frame_type != LTB_FRAME_TDD)) return LTB_ERROR_INVALID_INPUTS;
+  s->frame_type = frame_type;
+  return LTB_SUCCESS;
+}
+
 int ltb_sss_work(ltb_sss *s, const ltb_cf *in, const int32_t *tag_lost, int n, ltb_window_rec *recs) {
   if (!s || !in || !tag_lost || !recs || n <= 0) return LTB_ERROR_INVALID_INPUTS;
   LTB_CUDA(cudaSetDevice(s->device));
@@ -752,7 +766,7 @@ int ltb_sss_work(ltb_sss *s, const ltb_cf *in, const int32_t *tag_lost, int n, l
   STEP(cudaMemcpy(d_recs, recs, sizeof(ltb_window_rec) * n, cudaMemcpyHostToDevice));
   STEP(cudaMemset(s->d_count, 0, sizeof(int)));
   if (e == cudaSuccess) {
-    sss_block_front_kernel<<<1, 128>>>(d_hf, d_tag, n, s->n_id_2, s->d_cp, d_recs, d_sym, d_rec, s->d_count);
+    sss_block_front_kernel<<<1, 128>>>(d_hf, d_tag, n, s->n_id_2, s->frame_type == LTB_FRAME_TDD, s->d_cp, d_recs, d_sym, d_rec, s->d_count);
     sss_kernel<<<(n + kSssWarps - 1) / kSssWarps, kSssWarps * 32>>>(d_sym, d_rec, s->d_count, n, d_recs);
     e = cudaGetLastError();
   }

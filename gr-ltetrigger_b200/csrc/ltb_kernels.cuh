@@ -26,6 +26,8 @@ constexpr int kNLag = LTB_CONV_LEN;        // 9726
 constexpr int kAvgLen = 9732;              // 9729 used (fft+frame+1), padded to 16 B
 constexpr int kLookahead = LTB_LOOKAHEAD;  // 18365
 constexpr int kMavg = LTB_MOVING_AVG_SZ;   // 200
+constexpr int kRotBase = 352;              // first sample of the emitted half-frame kept CFO-corrected in shared memory
+constexpr int kRotLen = kSlot - kRotBase;  // 608: reaches back to the TDD extended-CP SSS symbol
 constexpr int kMaxDecim = 64;              // rational_resampler_ccc(1, D) for D = 1..64
 constexpr int kTailCap = 33 * kMaxDecim;   // decimator history kept per stream (input samples)
 
@@ -96,6 +98,7 @@ struct TrackParams {
   int track_after, track_every;
   int record_all;
   int root_mask;
+  int tdd;                   // LTB_FRAME_TDD: SSS three symbols before the PSS
 };
 
 // ------------------------------------------------------------------------------------
@@ -110,6 +113,14 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+// first sample of the SSS symbol in an aligned half-frame (PSS body at [832, 960)).  FDD: the symbol
+// before the PSS (lib/sss_impl.cc:110).  TDD (frame structure type 2, 36.211 6.11.2.2; not in the
+// reference): the last symbol of the previous slot, three symbols before the PSS, and the first
+// symbol of a normal-CP slot carries one extra prefix sample.
+__host__ __device__ constexpr int sss_symbol_start(int cp_len, int tdd) {
+  return tdd ? kSlot - kSym - (3 * cp_len + 2 * kSym + (cp_len == 9 ? 1 : 0)) - kSym : kSlot - 2 * kSym - cp_len;
 }
 
 // canonical complex product a*b:  re = fma(ar, br, -(ai*bi)),  im = fma(ar, bi, ai*br)
@@ -198,7 +209,7 @@ __device__ __forceinline__ float2 load_in_sample(const char *src, long long idx)
 // (taps beyond ntaps are zeros) in one chain per component; the D partials are then summed by the
 // balanced pairwise tree  ((P0+P1)+(P2+P3)) + ((P4+P5)+(P6+P7)) ...
 //
-// decimate_kernel (D = 2, 3, 4, 6, 8, 12): one CTA = 512 outputs of one stream, one warp per position, 16
+// decimate_kernel (D = 2 .. 15): one CTA = 512 outputs of one stream, one warp per position, 16
 // consecutive outputs per lane.  The (512+32) blocks x D positions the tile needs are staged once
 // in shared memory, row = position, 16-way de-interleaved in the block index so that the element
 // a warp needs at one step (block 32 + 16*lane + e) is 32 consecutive float2: a conflict-free
@@ -213,14 +224,12 @@ constexpr int kDecGroups = kDecOut + kDecQ - 1;  // 544 blocks per position row
 constexpr int kDecSub = kDecGroups / 16;         // 34 columns per sub-row
 constexpr int kDecRow = kDecGroups + 1;          // 545 float2: odd stride -> conflict-free fill
 constexpr int kDecPF = 3;                        // software prefetch distance (taps)
-// (c, c) coefficient pairs [v][33] of the tiled kernel's rates D = 2, 3, 4, 6, 8, 12, back to back
-__constant__ float2 c_decim_pairs[33 * (2 + 3 + 4 + 6 + 8 + 12)];
-__host__ __device__ constexpr bool decim_is_tiled(int d) { return d == 2 || d == 3 || d == 4 || d == 6 || d == 8 || d == 12; }
-__host__ __device__ constexpr int decim_pair_offset(int d) {
-  return kDecQ * (d == 2 ? 0 : d == 3 ? 2 : d == 4 ? 5 : d == 6 ? 9 : d == 8 ? 15 : 23);
-}
+// (c, c) coefficient pairs [v][33] of the tiled kernel's rates D = 2 .. 15, back to back
+__constant__ float2 c_decim_pairs[33 * (15 * 16 / 2 - 1)];
+__host__ __device__ constexpr bool decim_is_tiled(int d) { return d >= 2 && d <= 15; }
+__host__ __device__ constexpr int decim_pair_offset(int d) { return kDecQ * (d * (d - 1) / 2 - 1); }   // 33 * (2 + .. + d-1)
 __host__ __device__ constexpr int decim_pow2(int d) { int p = 1; while (p < d) p <<= 1; return p; }
-__host__ __device__ constexpr int decim_min_ctas(int d) { return d <= 4 ? 4 : 2; }
+__host__ __device__ constexpr int decim_min_ctas(int d) { return d <= 4 ? 4 : d <= 12 ? 2 : 1; }
 __host__ __device__ constexpr size_t decim_smem_bytes(int d) { return sizeof(float2) * (size_t)d * kDecRow; }
 
 template <int FMT, int D>
@@ -1266,7 +1275,7 @@ struct TrackShared {
   float2 lead[256];                    // window samples 0..126 at [128..255), zeros elsewhere
   float2 trail[256];                   // window samples 9473..9599 at [1..128), zeros elsewhere
   float edge[256];                     // power at the truncated lags
-  float2 rot[480];                     // CFO-corrected samples 480..959 of the emitted half-frame
+  float2 rot[kRotLen];                 // CFO-corrected samples kRotBase..959 of the emitted half-frame
   unsigned short ph_idx[960];          // phasor table index per sample
   PhaseSeg seg[kMaxSeg];
   int nseg;
@@ -1526,14 +1535,14 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
       if (P.hf_out != nullptr && S.rec_slot >= 0) hf = P.hf_out + (size_t)S.rec_slot * kHalf;
       if (S.do_track) {
         // ---- srslte_pss_cfo_compute on out[832..960) (lib/pss_impl.cc:199) --------------
-        for (int i = tid; i < 480; i += kTrackThreads) S.rot[i] = yr[(unsigned)((E + 480 + i) & P.cap_mask)];   // raw
+        for (int i = tid; i < kRotLen; i += kTrackThreads) S.rot[i] = yr[(unsigned)((E + kRotBase + i) & P.cap_mask)];   // raw
         __syncthreads();
         if (tid < 2) {
           float yr_ = 0.f, yi_ = 0.f;
           const int nb = tid * 64;
           for (int n = nb; n < nb + 64; ++n) {
             const float2 h = c_pss_taps[n_id_2][n];
-            const float2 r = S.rot[352 + n];                                     // out[832 + n]
+            const float2 r = S.rot[832 - kRotBase + n];                          // out[832 + n]
             yr_ = __fmaf_rn(h.x, r.x, yr_); yr_ = __fmaf_rn(-h.y, r.y, yr_);
             yi_ = __fmaf_rn(h.x, r.y, yi_); yi_ = __fmaf_rn(h.y, r.x, yi_);
           }
@@ -1571,7 +1580,7 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
           }
           __syncthreads();
           if (b == 0) {
-            for (int i = tid; i < 480; i += kTrackThreads) S.rot[i] = cmul_canon(P.cexp[S.ph_idx[480 + i]], S.rot[i]);
+            for (int i = tid; i < kRotLen; i += kTrackThreads) S.rot[i] = cmul_canon(P.cexp[S.ph_idx[kRotBase + i]], S.rot[i]);
           }
           if (hf) {
             for (int i = tid; i < 960; i += kTrackThreads) {
@@ -1585,7 +1594,7 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
         if (tid < 12) {
           const int h = tid / 6, sy = (tid % 6) / 2, kind = tid & 1;
           const int cp = h ? 32 : 9;
-          const int j0 = 960 - 3 * (128 + cp) + sy * (128 + cp) - 480;   // index into rot
+          const int j0 = 960 - 3 * (128 + cp) + sy * (128 + cp) - kRotBase;   // index into rot
           float acc = 0.f;
           if (kind == 0) {
             for (int i = 0; i < cp; ++i) {
@@ -1634,8 +1643,8 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
         }
         __syncthreads();
         if (S.sss_slot >= 0 && tid < 128) {
-          const int sss_idx = kSlot - 2 * kSym - S.cp_len;             // lib/sss_impl.cc:110
-          P.sss_sym[(size_t)S.sss_slot * 128 + tid] = S.rot[sss_idx - 480 + tid];
+          const int sss_idx = sss_symbol_start(S.cp_len, P.tdd);       // lib/sss_impl.cc:110
+          P.sss_sym[(size_t)S.sss_slot * 128 + tid] = S.rot[sss_idx - kRotBase + tid];
         }
       } else if (hf) {
         for (int i = tid; i < kHalf; i += kTrackThreads) hf[i] = yr[(unsigned)((E + i) & P.cap_mask)];
@@ -1759,7 +1768,7 @@ __global__ void __launch_bounds__(kSssWarps * 32) sss_kernel(const float2 *__res
 // chain (sequential EMA), feeding sss_kernel.  One CTA.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) sss_block_front_kernel(const float2 *__restrict__ hf, const int *__restrict__ tag_lost,
-                                                              int n_hf, int n_id_2, float *cp_state /*2*/,
+                                                              int n_hf, int n_id_2, int tdd, float *cp_state /*2*/,
                                                               ltb_window_rec *recs, float2 *sss_sym, int *sss_rec,
                                                               int *sss_count) {
   __shared__ float part[12];
@@ -1823,7 +1832,7 @@ __global__ void __launch_bounds__(128) sss_block_front_kernel(const float2 *__re
       __syncthreads();
       cpn = s_cpn; cpe = s_cpe;
     }
-    const int sss_idx = kSlot - 2 * kSym - s_cp_len;
+    const int sss_idx = sss_symbol_start(s_cp_len, tdd);
     sss_sym[(size_t)s_slot * 128 + tid] = in[sss_idx + tid];
     __syncthreads();
   }

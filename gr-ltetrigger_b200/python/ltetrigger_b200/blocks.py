@@ -154,13 +154,15 @@ class sss(_block):
     (lib/sss_impl.cc:83-156).  Consumes "tracking_lost", emits "cell_id" (int) and
     "cp_type" (True = normal) on item 0 of each decoded half-frame, passes samples through."""
 
-    def __init__(self, N_id_2, device=0):
+    def __init__(self, N_id_2, device=0, frame_type=A.FRAME_FDD):
         _block.__init__(self, "sss")
         self._n_id_2 = N_id_2
         self._h = C.c_void_p()
         rc = A.lib().ltb_sss_create(device, N_id_2, C.byref(self._h))
         if rc != A.SUCCESS:
             raise RuntimeError(A.lib().ltb_last_error().decode() or "Error initializing SSS SYNC")
+        if frame_type != A.FRAME_FDD:                  # TDD SSS position: not in the reference
+            A.check(A.lib().ltb_sss_set_frame_type(self._h, frame_type), "ltb_sss_set_frame_type")
         self.set_output_multiple(HALF_FRAME_LENGTH)
         self.last_record = None
 

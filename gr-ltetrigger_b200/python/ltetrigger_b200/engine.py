@@ -19,7 +19,7 @@ class Trigger:
 
     def __init__(self, n_streams, decim=1, psr_threshold=4.0, max_chunk=1 << 20, input_format=A.FMT_FC32,
                  track_after=16, track_every=8, record_all=True, keep_halfframes=False, device=0,
-                 root_mask=7, cuda_stream=None, corr_mode=A.CORR_DIRECT):
+                 root_mask=7, cuda_stream=None, corr_mode=A.CORR_DIRECT, frame_type=A.FRAME_FDD):
         cfg = A.TriggerConfig()
         cfg.struct_size = C.sizeof(A.TriggerConfig)
         cfg.device, cfg.n_streams, cfg.input_format, cfg.decim = device, n_streams, input_format, decim
@@ -28,6 +28,7 @@ class Trigger:
         cfg.record_all, cfg.keep_halfframes = int(record_all), int(keep_halfframes)
         cfg.cuda_stream = cuda_stream
         cfg.corr_mode = corr_mode
+        cfg.frame_type = frame_type
         self._h = C.c_void_p()
         A.check(A.lib().ltb_trigger_create(C.byref(cfg), C.byref(self._h)), "ltb_trigger_create")
         self.n_streams, self.decim, self.input_format = n_streams, decim, input_format

@@ -55,9 +55,11 @@ def sss_freq(cell_id, subframe):
 N_USED = {1: 72, 2: 180, 4: 300, 8: 600, 12: 900, 16: 1200}
 
 
-def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False):
+def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False, tdd=False):
     """n_frames radio frames (19200*decim samples each) at 1.92*decim Msps, mean power ~1.
-    ext_cp: 6 symbols per slot with a 32*decim-sample prefix (36.211 table 6.12-1)."""
+    ext_cp: 6 symbols per slot with a 32*decim-sample prefix (36.211 table 6.12-1).
+    tdd: frame structure type 2 -- PSS in symbol 2 of slots 2 and 12, SSS in the last symbol of
+    slots 1 and 11 (36.211 6.11.1.2, 6.11.2.2); every subframe is filled like a downlink one."""
     rng = rng or np.random.default_rng(cell_id)
     nfft = 128 * decim
     n_used = N_USED.get(decim, 12 * (6 * decim - decim // 2))
@@ -73,8 +75,12 @@ def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False):
     pss = pss_freq(cell_id % 3)
     for f in range(n_frames):
         for slot, sf in ((0, 0), (10, 5)):
-            sym_pss = (f * 20 + slot) * per_slot + per_slot - 1
-            sym_sss = sym_pss - 1
+            if tdd:
+                sym_pss = (f * 20 + slot + 2) * per_slot + 2
+                sym_sss = (f * 20 + slot + 1) * per_slot + per_slot - 1
+            else:
+                sym_pss = (f * 20 + slot) * per_slot + per_slot - 1
+                sym_sss = sym_pss - 1
             for sym, seq in ((sym_pss, pss), (sym_sss, sss_freq(cell_id, sf))):
                 grid[sym, 1:37] = 0
                 grid[sym, nfft - 36:] = 0
@@ -93,7 +99,7 @@ def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False):
 
 
 def capture(cell_id, n_samples, snr_db=None, decim=1, seed=0, offset=None, cfo_hz=0.0, noise_only=False,
-            ext_cp=False):
+            ext_cp=False, tdd=False):
     """One capture of n_samples at 1.92*decim Msps as complex64."""
     rng = np.random.default_rng([seed, cell_id, 0x5EED])
     frame_len = 19200 * decim
@@ -102,7 +108,7 @@ def capture(cell_id, n_samples, snr_db=None, decim=1, seed=0, offset=None, cfo_h
     n_frames = (offset + n_samples + frame_len - 1) // frame_len
     # a few distinct frames tiled keeps generation cheap while payload still varies
     uniq = min(n_frames, 4)
-    base = lte_frame(cell_id, decim, rng, uniq, ext_cp)
+    base = lte_frame(cell_id, decim, rng, uniq, ext_cp, tdd)
     reps = (n_frames + uniq - 1) // uniq
     sig = np.tile(base, reps)[offset:offset + n_samples]
     if cfo_hz:

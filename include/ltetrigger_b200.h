@@ -51,6 +51,12 @@ extern "C" {
 #define LTB_CORR_FFT    1          /* 1024-point overlap-save FFT blocks aligned to absolute sample indices */
 #define LTB_OS_STEP     896        /* outputs per overlap-save block */
 
+/* frame structure: where the SSS sits relative to the PSS (36.211 6.11.2.2) */
+#define LTB_FRAME_FDD   0          /* the symbol before the PSS: the reference (lib/sss_impl.cc:110) */
+#define LTB_FRAME_TDD   1          /* three symbols before the PSS; cell id and CP type only -- the emitted
+                                      half-frame keeps the reference's PSS alignment, which in TDD does not
+                                      start at a subframe boundary, so ltb_mib_decode does not apply */
+
 typedef struct { float re, im; } ltb_cf;
 
 /* ---- per-window record ---------------------------------------------------------
@@ -113,8 +119,8 @@ typedef struct {
   int32_t  n_streams;
   int32_t  input_format;      /* LTB_FMT_* */
   int32_t  decim;             /* input rate / 1.92 Msps, any integer 1..LTB_MAX_DECIM as the reference's
-                                 CLI accepts (examples/cell_search_file.py:50-57); tuned kernels for the
-                                 LTE rates 2, 4, 8, 12, 16 (and 3, 6) */
+                                 CLI accepts (examples/cell_search_file.py:50-57); streaming kernels for
+                                 4, 8, 16, the tiled kernel for the other rates up to 15, a general one above */
   int32_t  root_mask;         /* bit k set: run the N_id_2 = k chain; 0 -> 7 (all three) */
   int64_t  max_chunk;         /* largest n_samples (input rate, per stream) of one process call */
   float    psr_threshold;     /* clamped to > 1.5 like downlink_trigger_c.py:71-73 */
@@ -124,6 +130,7 @@ typedef struct {
   int32_t  keep_halfframes;   /* 1: keep each emitted (CFO-corrected) half-frame for ltb_trigger_fetch_halfframes */
   void    *cuda_stream;       /* cudaStream_t to launch on; NULL -> the library's own stream */
   int32_t  corr_mode;         /* LTB_CORR_*; a struct_size that ends before this field selects LTB_CORR_DIRECT */
+  int32_t  frame_type;        /* LTB_FRAME_*; default (0, or a shorter struct_size) is FDD like the reference */
 } ltb_trigger_config;
 
 /* pss::make + sss::make + hier-block construction (lib/pss_impl.cc:42-83,
@@ -186,6 +193,8 @@ LTB_API int ltb_device_count(void);
 typedef struct ltb_sss ltb_sss;
 LTB_API int ltb_sss_create(int device, int n_id_2, ltb_sss **out);
 LTB_API int ltb_sss_destroy(ltb_sss *s);
+/* LTB_FRAME_FDD (default) or LTB_FRAME_TDD */
+LTB_API int ltb_sss_set_frame_type(ltb_sss *s, int frame_type);
 /* n_halfframes consecutive work() calls: in = n*9600 host samples, tag_lost[i] != 0 if
  * the i-th half-frame carries "tracking_lost".  Fills the SSS fields and flag bits of
  * recs[i] (other fields untouched).  Returns LTB_SUCCESS. */

@@ -896,6 +896,7 @@ float orc_pss_tracking_score(const orc_pss *b) { return (float)b->score; }
 /* ------------------------------------------------------------------------- */
 struct orc_sss {
   int n_id_2;
+  int frame_type;                  /* 0 FDD (the reference), 1 TDD */
   float m_norm_avg, m_ext_avg;     /* srslte_sync_t CP EMA state [A.4] */
   int c0[31], c1[31], s_tilde[31], z_tilde[31], n_id_1_table[900];
 };
@@ -910,6 +911,7 @@ orc_sss *orc_sss_new(int n_id_2)
   return s;
 }
 void orc_sss_free(orc_sss *s) { free(s); }
+void orc_sss_set_frame_type(orc_sss *s, int frame_type) { s->frame_type = frame_type; }
 
 /* canonical radix-2 DIT, natural-order output, twiddle W[k] = exp(-j 2 pi k/128) */
 void orc_fft128(const orc_cf *in, orc_cf *out)
@@ -1032,6 +1034,10 @@ int orc_sss_work(orc_sss *s, const orc_cf *in, int tag_lost, orc_cf *out, orc_re
   int cp_norm = detect_cp(s, in);                       /* :104-108 */
   int cp_len = cp_norm ? 9 : 32;
   int sss_idx = ORC_SLOT - 2 * ORC_SYM - cp_len;        /* :110 */
+  /* TDD (not in the reference, 36.211 6.11.2.2): the SSS is the last symbol of slots 1 and 11, three
+   * symbols before the PSS (symbol 2 of slots 2 and 12); with the PSS body at [832, 960) slot 2 starts
+   * at 832 - (2 (128 + cp) + cp) - (normal CP: 1 extra sample in symbol 0) and the SSS body ends there */
+  if (s->frame_type == 1) sss_idx = ORC_SLOT - ORC_SYM - (3 * cp_len + 2 * ORC_SYM + (cp_norm ? 1 : 0)) - ORC_SYM;
   int m0, m1; float m0v, m1v;
   sss_m0m1(s, &in[sss_idx], &m0, &m0v, &m1, &m1v);      /* :112-116 */
   int nid = sss_n_id_1(s, (uint32_t)m0, (uint32_t)m1);  /* :118 */
@@ -1053,9 +1059,12 @@ int orc_sss_work(orc_sss *s, const orc_cf *in, int tag_lost, orc_cf *out, orc_re
 int orc_chain_run(const orc_cf *y, int64_t n, int stream, int n_id_2, float thr,
                   int track_after, int track_every, int conv_mode, orc_rec *recs, int max_recs)
 {
+  const int frame_type = (conv_mode >> 8) & 1;              /* ORC_FRAME_TDD rides on conv_mode */
+  conv_mode &= 0xff;
   orc_pss *p = orc_pss_new(n_id_2, thr, track_after, track_every, conv_mode);
   orc_sss *s = orc_sss_new(n_id_2);
   if (!p || !s) return -2;
+  orc_sss_set_frame_type(s, frame_type);
   orc_cf *buf = calloc(n + ORC_SLOT, sizeof(orc_cf));       /* GR zero history in front */
   memcpy(buf + ORC_SLOT, y, sizeof(orc_cf) * n);
   orc_cf *out = malloc(sizeof(orc_cf) * ORC_HALF);

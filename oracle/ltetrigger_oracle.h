@@ -42,6 +42,7 @@ extern "C" {
 typedef struct { float re, im; } orc_cf;
 
 enum { ORC_CONV_DIRECT = 0, ORC_CONV_FFT = 1, ORC_CONV_OS = 2 };
+#define ORC_FRAME_TDD 0x100    /* or-ed into conv_mode of orc_chain_run / orc_trigger_run: TDD SSS position */
 #define ORC_OS_STEP 896        /* outputs per 1024-point overlap-save block (ORC_CONV_OS) */
 
 #define ORC_SLOT      960
@@ -133,6 +134,8 @@ float    orc_pss_tracking_score(const orc_pss *);
 
 orc_sss *orc_sss_new(int n_id_2);
 void     orc_sss_free(orc_sss *);
+/* 0 FDD (the reference): SSS one symbol before the PSS; 1 TDD: three symbols before it */
+void     orc_sss_set_frame_type(orc_sss *, int frame_type);
 /* One work call on an aligned half-frame; tag_lost = "tracking_lost" tag present on item 0.
  * Returns 9600. rec gets the SSS fields and flag bits merged in. */
 int      orc_sss_work(orc_sss *, const orc_cf *in, int tag_lost, orc_cf *out, orc_rec *rec);

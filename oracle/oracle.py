@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libltetrigger_oracle.so")
 
 CONV_DIRECT, CONV_FFT, CONV_OS = 0, 1, 2
+FRAME_TDD = 0x100          # or-ed into conv_mode: TDD SSS position
 OS_STEP = 896
 SLOT, HALF, SYM, CONV_LEN, LOOKAHEAD = 960, 9600, 128, 9726, 18365
 
@@ -78,6 +79,7 @@ def lib():
         L.orc_sss_new.argtypes = [C.c_int]
         L.orc_sss_new.restype = vp
         L.orc_sss_free.argtypes = [vp]
+        L.orc_sss_set_frame_type.argtypes = [vp, C.c_int]
         L.orc_sss_work.argtypes = [vp, vp, C.c_int, vp, vp]
         L.orc_sss_work.restype = C.c_int
         L.orc_chain_run.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, vp, C.c_int]
@@ -237,10 +239,11 @@ class Pss:
 class Sss:
     """ltetrigger.sss restated (lib/sss_impl.cc)."""
 
-    def __init__(self, N_id_2):
+    def __init__(self, N_id_2, frame_type=0):
         self._h = lib().orc_sss_new(N_id_2)
         if not self._h:
             raise RuntimeError("Error initializing SSS N_id_2")
+        lib().orc_sss_set_frame_type(self._h, frame_type)
 
     def __del__(self):
         if getattr(self, "_h", None):

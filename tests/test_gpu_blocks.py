@@ -68,6 +68,36 @@ def test_pss_sss_blocks_call_by_call(lt, oracle, name):
     assert p.psr_threshold() == 1.0
 
 
+def test_sss_block_tdd(lt, oracle):
+    """The standalone sss block with frame_type = TDD (not in the reference) on the half-frames the
+    pss block aligns out of a TDD capture, call by call against the oracle's sss block."""
+    from ltetrigger_b200 import synth
+    x = synth.capture(205, 19200 * 16, snr_db=15.0, seed=3, tdd=True)       # tracking (and SSS) after 16 hits
+    k = 205 % 3
+    blk, ob, op = lt.sss(k, frame_type=lt.FRAME_TDD), oracle.Sss(k, frame_type=1), oracle.Pss(k, 3.0)
+    buf = np.concatenate([np.zeros(960, np.complex64), x])
+    pos, n, cells = 960, 0, []
+    while pos - 960 + oracle.LOOKAHEAD <= len(x):
+        nout, ncons, out, rec = op.work(buf, pos)
+        if nout:
+            lost = bool(rec["flags"] & oracle.F_TAG_LOST)
+            _, want = ob.work(out, lost)
+            blk._in_tags = [lt.tag_t(blk.nitems_read(0), "tracking_lost", None)] if lost else []
+            assert blk.work(9600, [out], [np.zeros(9600, np.complex64)]) == 9600
+            got = blk.last_record
+            mask = lt.F_CELL | lt.F_CP_NORM | lt.F_SSS
+            assert (int(got["flags"]) & mask) == (int(want["flags"]) & mask)
+            for f in ("m0", "m1", "n_id_1", "cell_id"):
+                assert got[f] == want[f], f
+            assert np.float32(got["m0_val"]).tobytes() == np.float32(want["m0_val"]).tobytes()
+            if int(got["flags"]) & lt.F_CELL:
+                cells.append(int(got["cell_id"]))
+            blk._nitems_read += 9600
+            n += 1
+        pos += ncons
+    assert n >= 20 and len(cells) >= 4 and set(cells) == {205}
+
+
 def test_pss_constructor_errors(lt):
     with pytest.raises(RuntimeError):
         lt.pss(3, 4.0)                             # lib/pss_impl.cc:75-76

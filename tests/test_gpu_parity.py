@@ -229,6 +229,30 @@ def test_extended_cp_capture(lt, oracle):
         assert (((cells["flags"] & lt.F_CP_NORM) != 0) == (not e)).all()
 
 
+@pytest.mark.parametrize("corr", ["direct", "fft"])
+def test_tdd_sss_position(lt, oracle, corr):
+    """Frame structure type 2 (not in the reference): SSS three symbols before the PSS, normal and
+    extended CP.  Engine records against the oracle's TDD restatement, and the FDD setting on the same
+    capture does not find the cell."""
+    from ltetrigger_b200 import synth
+    cases = ((301, False), (17, True), (440, False))
+    x = np.stack([synth.capture(c, 384000, snr_db=9.0, seed=c, ext_cp=e, tdd=True) for c, e in cases])
+    mode, conv = (lt.CORR_FFT, oracle.CONV_OS) if corr == "fft" else (lt.CORR_DIRECT, oracle.CONV_DIRECT)
+    trig = lt.Trigger(n_streams=3, decim=1, max_chunk=384000, corr_mode=mode, frame_type=lt.FRAME_TDD)
+    got = trig.run(x)
+    want = oracle.trigger_run(x, conv_mode=conv | oracle.FRAME_TDD)
+    assert_recs_equal(got, want)
+    for s, (c, e) in enumerate(cases):
+        cells = got[(got["stream"] == s) & ((got["flags"] & lt.F_CELL) != 0)]
+        assert len(cells) > 5 and set(cells["cell_id"].tolist()) == {c}
+        assert (((cells["flags"] & lt.F_CP_NORM) != 0) == (not e)).all()
+    fdd = lt.Trigger(n_streams=3, decim=1, max_chunk=384000, corr_mode=mode).run(x)
+    assert_recs_equal(fdd, oracle.trigger_run(x, conv_mode=conv))
+    for s, (c, e) in enumerate(cases):
+        ids = fdd[(fdd["stream"] == s) & ((fdd["flags"] & lt.F_CELL) != 0)]["cell_id"]
+        assert (ids != c).all()
+
+
 def test_synthetic_snr_sweep_batched(lt, oracle):
     """Reduced config C4: 16 streams x 0.25 s per SNR point; event lists identical to the oracle's."""
     from ltetrigger_b200 import synth

@@ -182,3 +182,19 @@ def test_overlap_save_mode(oracle):
     m = a["psr"] > 0
     np.testing.assert_allclose(a["psr"][m], b["psr"][m], rtol=1e-4)
     np.testing.assert_allclose(a["peak_value"][m], b["peak_value"][m], rtol=1e-4)
+
+
+def test_tdd_sss_position(oracle):
+    """Frame structure type 2 (an extension: the reference and srsLTE 18.06 are FDD-only): with the SSS
+    taken three symbols before the PSS the right cell comes out of a TDD capture for both CP lengths;
+    the FDD setting on the same capture does not find it."""
+    from ltetrigger_b200 import synth
+    for cell, ext in ((301, False), (17, True)):
+        x = synth.capture(cell, 19200 * 15, snr_db=10.0, seed=2, ext_cp=ext, tdd=True)
+        for conv in (oracle.CONV_DIRECT, oracle.CONV_OS):
+            r = oracle.trigger_run(x[None, :], conv_mode=conv | oracle.FRAME_TDD)
+            c = r[(r["flags"] & oracle.F_CELL) != 0]
+            assert len(c) >= 8 and set(c["cell_id"].tolist()) == {cell}
+            assert (((c["flags"] & oracle.F_CP_NORM) != 0) == (not ext)).all()
+        r = oracle.trigger_run(x[None, :])
+        assert cell not in r[(r["flags"] & oracle.F_CELL) != 0]["cell_id"]
