@@ -197,8 +197,19 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU: run on the cores next to that GPU, so the pinned buffers of the
+        # end-to-end leg are first touched (and the copy engine reads them) on the GPU's NUMA node
+        # (at N = 1 the process keeps every core: the CPU baseline uses them)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local_rank))
+            numa = "cores %d" % len(os.sched_getaffinity(0))
+        except Exception as e:
+            numa = "unpinned (%s)" % type(e).__name__
 
     fmts = {"fc32": lt.FMT_FC32, "sc16": lt.FMT_SC16, "sc8": lt.FMT_SC8}
     fmt = fmts[a.format]
@@ -374,7 +385,7 @@ def main():
             trig2.close()
             return host, {"value": se * n * a.e2e_steps * world / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
                           "h2d_bytes_per_step": se * n * b, "d2h_bytes_per_step": d2h // a.e2e_steps,
-                          "streams": se, "steps": a.e2e_steps, "host_memory": "pinned", "format": name,
+                          "streams": se, "steps": a.e2e_steps, "host_memory": "pinned", "format": name, "cpu_affinity": numa,
                           "api": "ltb_trigger_submit_host + ltb_trigger_collect (two calls in flight)"}
 
         host, out["e2e"] = run_e2e(a.format)
