@@ -408,6 +408,25 @@ def main():
                                    "sample": "%d passes over %d streams x %d ms of the same workload (%.1f s wall); oracle in "
                                              "reference-class FFT mode (9728-point FFT convolution per window and root), "
                                              "one job per (stream, root) on all cores" % (reps, sc, a.segment_ms, dt)}
+            # the same leg also uses the oracle as what it is, the checker: the benchmarked configuration
+            # (rate, format, correlator) on a few of the bench's own streams, every record compared bit for bit
+            from oracle import oracle as O
+            nchk = min(8, sc)
+            chk = lt.Trigger(n_streams=nchk, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
+                             device=local_rank, corr_mode=corr_mode)
+            got = chk.run(iq[:nchk])
+            chk.close()
+            want = O.trigger_run(iq[:nchk], decim=a.decim, psr_threshold=4.0,
+                                 conv_mode=O.CONV_OS if a.corr == "fft" else O.CONV_DIRECT)
+            same = len(got) == len(want)
+            for f in (want.dtype.names if same else ()):
+                g, w = got[f], want[f]
+                if g.dtype.kind == "f":
+                    same = same and bool(((g.view(np.uint32) == w.view(np.uint32)) | ((g == 0) & (w == 0))).all())
+                else:
+                    same = same and bool((g == w).all())
+            out["cpu_baseline"]["parity_spot_check"] = {"streams": nchk, "records": int(len(want)),
+                                                        "bit_identical_to_oracle": bool(same)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
