@@ -95,3 +95,31 @@ def test_no_device_fails_loudly():
         lt.kernel_pss_corr(np.zeros((1, 64), np.complex64))
     with pytest.raises(RuntimeError):
         lt.sss(0)
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+    libdir = os.path.join(ROOT, "gr-ltetrigger_b200", "lib")
+    exe = str(tmp_path / "test_abi_c")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "test_abi.c"), "-L", libdir, "-lltetrigger_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
+def test_c_client_compiles_links_and_fails_loudly_without_a_device(tmp_path):
+    """include/ltetrigger_b200.h is valid C99 and the library is usable from plain C."""
+    import subprocess
+    out = subprocess.run([_build_c_client(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "taps 525" in out.stdout and "no device: create -> -1" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_client_finds_the_fixture_cell(tmp_path):
+    import subprocess
+    fixture = os.path.join(ROOT, "tests", "golden", "test_frames", "lte_frame_6prb_cellid_123")
+    out = subprocess.run([_build_c_client(tmp_path), fixture], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "cell_id 123" in out.stdout
