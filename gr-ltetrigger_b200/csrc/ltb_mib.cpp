@@ -6,7 +6,8 @@
 // path, and it never touches the GPU.  srsLTE's source is absent, so this restates the 3GPP
 // procedure it implements -- 36.211 6.6 (PBCH), 6.10.1 (CRS), 7.2 (Gold sequence); 36.212 5.1.1
 // (CRC16), 5.1.3.1 (tail-biting convolutional code), 5.1.4.2 (rate matching), 5.3.1 (BCH) -- for
-// the single-antenna-port case plus the CRC masks of 2 and 4 ports.  Its results are pinned by the
+// one antenna port and for two ports with transmit diversity (36.211 6.3.4.3); the 4-port CRC mask is
+// recognised but 4-port SFBC-FSTD is not demodulated.  Its results are pinned by the
 // reference's own tests: nof_prb 6 / 25 / 50 / 100, phich_len Normal, nof_phich_resources "1",
 // nof_tx_ports 1 for the four bundled test_frames (python/qa_downlink_trigger_c.py:46-65).
 #include <cmath>
@@ -131,14 +132,15 @@ extern "C" int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_norma
   // ---- OFDM demodulation of slot 1 -----------------------------------------------------------
   cf grid[7][72];
   for (int l = 0; l < nsym; ++l) demod72(x + sym_start(1, l), grid[l]);
-  // ---- channel estimate from the port-0 CRS of slot 1 (36.211 6.10.1) -------------------------
-  // CRS symbols l = 0 (v = 0) and l = nsym - 3 (v = 3), subcarriers k = 6 m + (v + v_shift) % 6
+  // ---- channel estimates from the CRS of slot 1 (36.211 6.10.1) ------------------------------------
+  // port 0: symbols l = 0 (v = 0) and l = nsym - 3 (v = 3); port 1: the mirrored comb (v = 3, 0);
+  // subcarriers k = 6 m + (v + v_shift) % 6
   const int vshift = cell_id % 6;
-  float hk_re[72], hk_im[72];
-  {
+  cf hk[2][72];
+  for (int port = 0; port < 2; ++port) {
     std::vector<int> pos;
     std::vector<cf> val;
-    const int ls[2] = {0, nsym - 3}, vs[2] = {0, 3};
+    const int ls[2] = {0, nsym - 3}, vs[2] = {port == 0 ? 0 : 3, port == 0 ? 3 : 0};
     for (int a = 0; a < 2; ++a) {
       std::vector<uint8_t> c;
       const int ns = 1, l = ls[a];
@@ -165,59 +167,79 @@ extern "C" int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_norma
         const float t = (float)(k - pos[j]) / (float)(pos[j2] - pos[j]);
         h = val[j] + (val[j2] - val[j]) * t;               // also extrapolates below the first pilot
       }
-      hk_re[k] = h.real(); hk_im[k] = h.imag();
+      hk[port][k] = h;
     }
   }
   // ---- PBCH resource elements: symbols 0..3, all CRS positions of ports 0..3 reserved ----------
-  std::vector<float> llr;
+  std::vector<cf> rx, h0, h1;
   for (int l = 0; l < 4; ++l)
     for (int k = 0; k < 72; ++k) {
       const bool crs_sym = (l == 0 || l == 1 || (!cp_normal && l == 3));
       if (crs_sym && (k % 3) == (cell_id % 3)) continue;
-      const cf h(hk_re[k], hk_im[k]);
-      const cf z = grid[l][k] * std::conj(h);              // matched filter (scale does not matter)
-      llr.push_back(z.real());
-      llr.push_back(z.imag());
+      rx.push_back(grid[l][k]);
+      h0.push_back(hk[0][k]);
+      h1.push_back(hk[1][k]);
     }
-  const int E = (int)llr.size();                           // 480 (normal) / 432 (extended)
-  // ---- scrambling phase hypotheses (frame number mod 4), de-ratematch, decode, CRC --------------
+  const int nre = (int)rx.size();                          // 240 (normal) / 216 (extended)
+  const int E = 2 * nre;
   std::vector<uint8_t> c;
   gold((uint32_t)cell_id, 4 * E, c);
   int order[120];
   ratematch_order(order);
-  for (int off = 0; off < 4; ++off) {
-    float soft[120];
-    std::memset(soft, 0, sizeof soft);
-    for (int k = 0; k < E; ++k) {
-      const int kk = off * E + k;                          // position inside the 4-frame codeword
-      const float v = c[kk] ? -llr[k] : llr[k];
-      soft[order[kk % 120]] += v;
+  // srslte_pbch_decode tries 1, 2 and 4 antenna ports and accepts a CRC that matches that number's
+  // mask; here 1 and 2 (a 4-port mask seen under the 1-port hypothesis is still reported)
+  for (int nant = 1; nant <= 2; ++nant) {
+    std::vector<float> llr((size_t)E);
+    if (nant == 1) {
+      for (int i = 0; i < nre; ++i) {
+        const cf z = rx[i] * std::conj(h0[i]);             // matched filter (scale does not matter)
+        llr[2 * i] = z.real(); llr[2 * i + 1] = z.imag();
+      }
+    } else {
+      // 36.211 6.3.4.3: r(2i) = h0 d(2i) - h1 conj(d(2i+1)),  r(2i+1) = h0 d(2i+1) + h1 conj(d(2i))
+      for (int i = 0; i + 1 < nre; i += 2) {
+        const cf a0 = 0.5f * (h0[i] + h0[i + 1]), a1 = 0.5f * (h1[i] + h1[i + 1]);
+        const cf d0 = std::conj(a0) * rx[i] + a1 * std::conj(rx[i + 1]);
+        const cf d1 = std::conj(a0) * rx[i + 1] - a1 * std::conj(rx[i]);
+        llr[2 * i] = d0.real(); llr[2 * i + 1] = d0.imag();
+        llr[2 * i + 2] = d1.real(); llr[2 * i + 3] = d1.imag();
+      }
     }
-    uint8_t bits[40];
-    viterbi_tb(soft, bits);
-    bool any = false;
-    for (int i = 0; i < 24; ++i) any |= bits[i] != 0;
-    if (!any) continue;                                    // all-zero payload passes the CRC trivially
-    uint32_t rx = 0;
-    for (int i = 0; i < 16; ++i) rx = (rx << 1) | bits[24 + i];
-    const uint32_t diff = crc16(bits, 24) ^ rx;
-    int ports = 0;
-    if (diff == 0x0000u) ports = 1;
-    else if (diff == 0xFFFFu) ports = 2;
-    else if (diff == 0x5555u) ports = 4;
-    if (!ports) continue;
-    static const int prb[8] = {6, 15, 25, 50, 75, 100, 0, 0};
-    const int bw = (bits[0] << 2) | (bits[1] << 1) | bits[2];
-    if (!prb[bw]) continue;
-    int sfn = 0;
-    for (int i = 0; i < 8; ++i) sfn = (sfn << 1) | bits[6 + i];
-    out->nof_prb = prb[bw];
-    out->nof_ports = ports;
-    out->phich_length = bits[3];
-    out->phich_resources = (bits[4] << 1) | bits[5];
-    out->sfn = (sfn << 2) | off;
-    out->sfn_offset = off;
-    return 1;                                              // SRSLTE_UE_MIB_FOUND
+    // ---- scrambling phase hypotheses (frame number mod 4), de-ratematch, decode, CRC --------------
+    for (int off = 0; off < 4; ++off) {
+      float soft[120];
+      std::memset(soft, 0, sizeof soft);
+      for (int k = 0; k < E; ++k) {
+        const int kk = off * E + k;                        // position inside the 4-frame codeword
+        const float v = c[kk] ? -llr[k] : llr[k];
+        soft[order[kk % 120]] += v;
+      }
+      uint8_t bits[40];
+      viterbi_tb(soft, bits);
+      bool any = false;
+      for (int i = 0; i < 24; ++i) any |= bits[i] != 0;
+      if (!any) continue;                                  // all-zero payload passes the CRC trivially
+      uint32_t rxcrc = 0;
+      for (int i = 0; i < 16; ++i) rxcrc = (rxcrc << 1) | bits[24 + i];
+      const uint32_t diff = crc16(bits, 24) ^ rxcrc;
+      int ports = 0;
+      if (nant == 1 && diff == 0x0000u) ports = 1;
+      else if (nant == 2 && diff == 0xFFFFu) ports = 2;
+      else if (nant == 1 && diff == 0x5555u) ports = 4;
+      if (!ports) continue;
+      static const int prb[8] = {6, 15, 25, 50, 75, 100, 0, 0};
+      const int bw = (bits[0] << 2) | (bits[1] << 1) | bits[2];
+      if (!prb[bw]) continue;
+      int sfn = 0;
+      for (int i = 0; i < 8; ++i) sfn = (sfn << 1) | bits[6 + i];
+      out->nof_prb = prb[bw];
+      out->nof_ports = ports;
+      out->phich_length = bits[3];
+      out->phich_resources = (bits[4] << 1) | bits[5];
+      out->sfn = (sfn << 2) | off;
+      out->sfn_offset = off;
+      return 1;                                            // SRSLTE_UE_MIB_FOUND
+    }
   }
   return 0;                                                // SRSLTE_UE_MIB_NOTFOUND
 }

@@ -55,11 +55,100 @@ def sss_freq(cell_id, subframe):
 N_USED = {1: 72, 2: 180, 4: 300, 8: 600, 12: 900, 16: 1200}
 
 
-def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False, tdd=False):
+# ---- PBCH / CRS transmitter (36.211 6.6, 6.10.1, 7.2; 36.212 5.1.1, 5.1.3.1, 5.1.4.2, 5.3.1) -------------
+# Used to make synthetic cells whose MIB the host-side decoder can read, with one or two antenna
+# ports (transmit diversity, 36.211 6.3.4.3).  Input generation only.
+_PERM = (1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31,
+         0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30)
+_PRB_CODE = {6: 0, 15: 1, 25: 2, 50: 3, 75: 4, 100: 5}
+_CRC_MASK = {1: 0x0000, 2: 0xFFFF, 4: 0x5555}
+
+
+def gold(c_init, n):
+    x1 = [1] + [0] * 30
+    x2 = [(c_init >> i) & 1 for i in range(31)]
+    for i in range(1600 + n):
+        x1.append(x1[i + 3] ^ x1[i])
+        x2.append(x2[i + 3] ^ x2[i + 2] ^ x2[i + 1] ^ x2[i])
+    return np.array([x1[i + 1600] ^ x2[i + 1600] for i in range(n)], np.int64)
+
+
+def _crc16(bits):
+    reg = 0
+    for b in bits:
+        fb = ((reg >> 15) & 1) ^ int(b)
+        reg = (reg << 1) & 0xFFFF
+        if fb:
+            reg ^= 0x1021
+    return reg
+
+
+def _tbcc(bits):
+    """Tail-biting K = 7 code, generators 133 / 171 / 165 (octal); output index 3 i + s."""
+    g = (0o133, 0o171, 0o165)
+    n = len(bits)
+    state = 0
+    for b in bits[-6:]:                       # the register starts with the last six information bits
+        state = (state >> 1) | (int(b) << 5)
+    out = np.zeros(3 * n, np.int64)
+    for i, b in enumerate(bits):
+        reg = (int(b) << 6) | state           # newest bit in the MSB
+        for s_ in range(3):
+            out[3 * i + s_] = bin(reg & g[s_]).count("1") & 1
+        state = reg >> 1
+    return out
+
+
+def _ratematch_order():
+    order = []
+    for s_ in range(3):
+        for j in range(32):
+            for r in range(2):
+                y = r * 32 + _PERM[j]
+                if y >= 24:                   # 24 dummy bits in front of the 40
+                    order.append(3 * (y - 24) + s_)
+    return np.array(order)
+
+
+def mib_bits(nof_prb, phich_ext, phich_res, sfn):
+    b = [(_PRB_CODE[nof_prb] >> 2) & 1, (_PRB_CODE[nof_prb] >> 1) & 1, _PRB_CODE[nof_prb] & 1, int(phich_ext),
+         (phich_res >> 1) & 1, phich_res & 1]
+    b += [((sfn >> 2) >> (7 - i)) & 1 for i in range(8)]
+    return b + [0] * 10
+
+
+def pbch_symbols(cell_id, mib24, n_ports, n_bits):
+    """The QPSK symbols of one 40 ms PBCH period (n_bits = 1920 normal CP, 1728 extended)."""
+    crc = _crc16(mib24) ^ _CRC_MASK[n_ports]
+    a = list(mib24) + [(crc >> (15 - i)) & 1 for i in range(16)]
+    coded = _tbcc(a)
+    order = _ratematch_order()
+    e = coded[order[np.arange(n_bits) % 120]] ^ gold(cell_id, n_bits)
+    return ((1 - 2 * e[0::2]) + 1j * (1 - 2 * e[1::2])) / np.sqrt(2.0)
+
+
+def crs_central(cell_id, ns, l, ext_cp):
+    """CRS values r(m') for the twelve pilots of the six central resource blocks (m' = 104 .. 115)."""
+    ncp = 0 if ext_cp else 1
+    c = gold(1024 * (7 * (ns + 1) + l + 1) * (2 * cell_id + 1) + 2 * cell_id + ncp, 2 * 220)
+    m = np.arange(104, 116)
+    return ((1 - 2 * c[2 * m]) + 1j * (1 - 2 * c[2 * m + 1])) / np.sqrt(2.0)
+
+
+def _central(n):
+    """central-72 subcarrier index 0..71 (lowest frequency first, DC skipped) -> signed FFT bin"""
+    return np.where(n < 36, n - 36, n - 35)
+
+
+
+def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False, tdd=False, mib=None):
     """n_frames radio frames (19200*decim samples each) at 1.92*decim Msps, mean power ~1.
     ext_cp: 6 symbols per slot with a 32*decim-sample prefix (36.211 table 6.12-1).
     tdd: frame structure type 2 -- PSS in symbol 2 of slots 2 and 12, SSS in the last symbol of
-    slots 1 and 11 (36.211 6.11.1.2, 6.11.2.2); every subframe is filled like a downlink one."""
+    slots 1 and 11 (36.211 6.11.1.2, 6.11.2.2); every subframe is filled like a downlink one.
+    mib: dict(nof_prb, n_ports=1|2, phich_ext=0, phich_res=2, sfn0=0, h=(h0, h1)) adds the cell-specific
+    reference signals of the central six resource blocks and the PBCH (FDD position: slot 1 of
+    subframe 0), for one antenna port or two with transmit diversity through flat channels h."""
     rng = rng or np.random.default_rng(cell_id)
     nfft = 128 * decim
     n_used = N_USED.get(decim, 12 * (6 * decim - decim // 2))
@@ -86,6 +175,8 @@ def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False, tdd=False):
                 grid[sym, nfft - 36:] = 0
                 grid[sym, 1:32] = seq[31:]
                 grid[sym, nfft - 31:] = seq[:31]
+    if mib is not None:
+        grid = _add_crs_pbch(grid, cell_id, n_frames, per_slot, ext_cp, nfft, mib)
     time = np.fft.ifft(grid, axis=1) * (nfft / np.sqrt(n_used))
     out = np.empty(n_frames * 19200 * decim, np.complex128)
     pos = 0
@@ -98,8 +189,50 @@ def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False, tdd=False):
     return out
 
 
+def _add_crs_pbch(grid, cell_id, n_frames, per_slot, ext_cp, nfft, mib):
+    n_ports = mib.get("n_ports", 1)
+    h = mib.get("h", (1.0, 0.6 - 0.5j))
+    ports = [grid.copy(), np.zeros_like(grid)]        # payload, PSS and SSS leave from port 0 only
+    cols = _central(np.arange(72)) % nfft
+    vshift = cell_id % 6
+    n_bits = 1728 if ext_cp else 1920
+    per_frame = n_bits // 8                           # QPSK symbols per radio frame
+    for f in range(n_frames):
+        sfn = mib.get("sfn0", 0) + f
+        d = pbch_symbols(cell_id, mib_bits(mib["nof_prb"], mib.get("phich_ext", 0), mib.get("phich_res", 2), sfn),
+                         n_ports, n_bits)[(sfn % 4) * per_frame:(sfn % 4 + 1) * per_frame]
+        for ns in range(20):
+            for l, v0 in ((0, 0), (per_slot - 3, 3)):
+                sym = (f * 20 + ns) * per_slot + l
+                r = crs_central(cell_id, ns, l, ext_cp)
+                for p in range(2):                    # port 1 mirrors the comb; its REs are empty on port 0
+                    k = 6 * np.arange(12) + ((v0 if p == 0 else 3 - v0) + vshift) % 6
+                    for q in range(2):
+                        ports[q][sym, cols[k]] = 0
+                    if p < n_ports:
+                        ports[p][sym, cols[k]] = r
+        # PBCH: slot 1, symbols 0..3, the CRS positions of four ports stay empty
+        res = []
+        for l in range(4):
+            crs_sym = l in (0, 1) or (ext_cp and l == 3)
+            for k in range(72):
+                if crs_sym and k % 3 == cell_id % 3:
+                    continue
+                res.append(((f * 20 + 1) * per_slot + l, cols[k]))
+        assert len(res) == per_frame
+        for i in range(0, per_frame, 2):
+            (s0, c0), (s1, c1) = res[i], res[i + 1]
+            if n_ports == 1:
+                ports[0][s0, c0], ports[0][s1, c1] = d[i], d[i + 1]
+                ports[1][s0, c0] = ports[1][s1, c1] = 0
+            else:                                     # 36.211 6.3.4.3
+                ports[0][s0, c0], ports[0][s1, c1] = d[i] / np.sqrt(2), d[i + 1] / np.sqrt(2)
+                ports[1][s0, c0], ports[1][s1, c1] = -np.conj(d[i + 1]) / np.sqrt(2), np.conj(d[i]) / np.sqrt(2)
+    return h[0] * ports[0] + (h[1] * ports[1] if n_ports > 1 else 0)
+
+
 def capture(cell_id, n_samples, snr_db=None, decim=1, seed=0, offset=None, cfo_hz=0.0, noise_only=False,
-            ext_cp=False, tdd=False):
+            ext_cp=False, tdd=False, mib=None):
     """One capture of n_samples at 1.92*decim Msps as complex64."""
     rng = np.random.default_rng([seed, cell_id, 0x5EED])
     frame_len = 19200 * decim
@@ -108,7 +241,7 @@ def capture(cell_id, n_samples, snr_db=None, decim=1, seed=0, offset=None, cfo_h
     n_frames = (offset + n_samples + frame_len - 1) // frame_len
     # a few distinct frames tiled keeps generation cheap while payload still varies
     uniq = min(n_frames, 4)
-    base = lte_frame(cell_id, decim, rng, uniq, ext_cp, tdd)
+    base = lte_frame(cell_id, decim, rng, uniq, ext_cp, tdd, mib)
     reps = (n_frames + uniq - 1) // uniq
     sig = np.tile(base, reps)[offset:offset + n_samples]
     if cfo_hz:

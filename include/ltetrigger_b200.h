@@ -203,8 +203,8 @@ LTB_API int ltb_sss_work(ltb_sss *s, const ltb_cf *in, const int32_t *tag_lost, 
 
 /* ---- host-side MIB decode (consumer of the path's output; never touches the GPU) ------------
  * What ltetrigger::mib does with a tagged half-frame (lib/mib_impl.cc:148-170:
- * srslte_ue_mib_decode + srslte_pbch_mib_unpack): PBCH of slot 1, single antenna port, CRC masks of
- * 1 / 2 / 4 ports.  halfframe = 9600 aligned, CFO-corrected samples as emitted by pss / passed by
+ * srslte_ue_mib_decode + srslte_pbch_mib_unpack): PBCH of slot 1, one antenna port or two with
+ * transmit diversity (hypotheses tried in that order, CRC mask must match the hypothesis).  halfframe = 9600 aligned, CFO-corrected samples as emitted by pss / passed by
  * sss; cell_id and cp_normal from the sss tags.  Returns 1 (SRSLTE_UE_MIB_FOUND) and fills *out,
  * 0 if no MIB was found (e.g. a subframe-5 half-frame), < 0 on invalid arguments. */
 typedef struct {

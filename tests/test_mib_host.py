@@ -77,6 +77,44 @@ def test_reference_snr_demo_screenshot(oracle, seed):
     assert op.tracking_score() > 0                                       # "Tracking: True"
 
 
+@pytest.mark.parametrize("n_ports,nof_prb,decim,ext_cp", [(1, 15, 2, False), (2, 6, 1, False), (2, 75, 12, False),
+                                                         (2, 25, 4, True)])
+def test_mib_on_synthetic_cells_one_and_two_ports(oracle, n_ports, nof_prb, decim, ext_cp):
+    """Synthetic cells with CRS and PBCH (synth.py's transmitter: CRC mask, tail-biting code, rate
+    matching, scrambling, transmit diversity for two ports) through the oracle chain and the host mib:
+    bandwidths the bundled frames do not cover (15 and 75 PRB), extended CP, and two antenna ports
+    -- what srslte_ue_mib_decode reports as nof_ports (lib/mib_impl.cc:163-166)."""
+    import ltetrigger_b200 as lt
+    from ltetrigger_b200 import synth
+    cell_id = 100 + 3 * nof_prb + n_ports
+    x = synth.capture(cell_id, 19200 * decim * 14, snr_db=12.0, decim=decim, seed=nof_prb, ext_cp=ext_cp,
+                      mib=dict(nof_prb=nof_prb, n_ports=n_ports, phich_res=1, sfn0=4, h=(0.9 + 0.2j, -0.4 + 0.7j)))
+    y = oracle.decimate(x, decim) if decim > 1 else x
+    k = cell_id % 3
+    op, os_, mb = oracle.Pss(k, 4.0), oracle.Sss(k), lt.mib(exit_on_success=True)
+    tracked = []
+    mb.msg_connect("track", tracked.append)
+    buf = np.concatenate([np.zeros(960, np.complex64), y])
+    pos, written = 960, 0
+    while pos - 960 + oracle.LOOKAHEAD <= len(y) and not mb.done:
+        nout, ncons, out, rec = op.work(buf, pos)
+        if nout:
+            lost = bool(rec["flags"] & oracle.F_TAG_LOST)
+            _, srec = os_.work(out, lost)
+            tags = [lt.tag_t(written, "tracking_lost", None)] if lost else []
+            if srec["flags"] & oracle.F_CELL:
+                tags += [lt.tag_t(written, "cell_id", int(srec["cell_id"])),
+                         lt.tag_t(written, "cp_type", bool(srec["flags"] & oracle.F_CP_NORM))]
+            mb._in_tags, mb._nitems_read = tags, written
+            mb.general_work(9600, [9600], [out], [None])
+            written += nout
+        pos += ncons
+    assert mb.done and len(tracked) == 1
+    cell = tracked[0]
+    assert (cell["cell_id"], cell["nof_prb"], cell["nof_tx_ports"]) == (cell_id, nof_prb, n_ports)
+    assert cell["cp_len"] == ("Extended" if ext_cp else "Normal") and cell["nof_phich_resources"] == "1/2"
+
+
 def test_mib_decode_rejects_noise_sf5_and_bad_arguments():
     import ctypes as C
     import ltetrigger_b200 as lt
