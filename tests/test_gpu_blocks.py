@@ -236,3 +236,24 @@ def test_cell_search_batch_cli(lt, tmp_path):
     np.stack([np.round(noisy.real * s), np.round(noisy.imag * s)], axis=-1).astype(np.int16).tofile(f16)
     res = [json.loads(r) for r in cli.main(cli.parse([f16, "-s", "7.68M", "--format", "sc16", "--repeat", "--cut-off", "7.68M"]))]
     assert res[0]["status"] == "FOUND" and res[0]["cell_id"] == 124 and res[0]["nof_prb"] == 25
+
+
+def test_cell_search_file_cli_on_synthetic_75prb_two_port_cell(lt, tmp_path):
+    """The CLI at a rate the bundled frames do not cover: a synthetic 15 MHz cell (75 PRB, 23.04 Msps,
+    decimate by 12) with two antenna ports -> FOUND with the MIB the transmitter encoded."""
+    import importlib.util
+    import json
+    import os
+    from conftest import ROOT
+    from ltetrigger_b200 import synth
+    spec = importlib.util.spec_from_file_location("cell_search_file", os.path.join(ROOT, "examples", "cell_search_file.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    x = synth.capture(332, 19200 * 12 * 14, snr_db=10.0, decim=12, seed=8,
+                      mib=dict(nof_prb=75, n_ports=2, phich_res=3, sfn0=8, h=(0.7 - 0.2j, 0.3 + 0.8j)))
+    path = str(tmp_path / "cell332_75prb.fc32")
+    x.tofile(path)
+    results = cli.main(cli.parse([path, "-s", "23.04M"]))
+    cell = json.loads(results[0])
+    assert cell["status"] == "FOUND"
+    assert (cell["cell_id"], cell["nof_prb"], cell["nof_tx_ports"], cell["nof_phich_resources"]) == (332, 75, 2, "2")
