@@ -378,14 +378,28 @@ def main():
             e1.record(stream)
             torch.cuda.synchronize()
             e2e_ms = e0.elapsed_time(e1)
+            e2e_ms_local = e2e_ms
             if world > 1:
                 tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                 e2e_ms = float(tt.item())
             trig2.close()
+            # the host link alone: the same pinned buffer copied to the device, nothing else running
+            dst = torch.empty_like(host, device=dev)
+            dst.copy_(host, non_blocking=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(4):
+                dst.copy_(host, non_blocking=True)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            h2d_gbs = 4 * host.numel() * host.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            del dst
+            link = {"h2d_copy_alone_gbs": h2d_gbs,
+                    "frac_of_h2d_copy": (se * n * b * a.e2e_steps / (e2e_ms_local * 1e-3) / 1e9) / h2d_gbs}
             return host, {"value": se * n * a.e2e_steps * world / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
                           "h2d_bytes_per_step": se * n * b, "d2h_bytes_per_step": d2h // a.e2e_steps,
-                          "streams": se, "steps": a.e2e_steps, "host_memory": "pinned", "format": name, "cpu_affinity": numa,
+                          "streams": se, "steps": a.e2e_steps, "host_memory": "pinned", "format": name, "cpu_affinity": numa, "host_link": link,
                           "api": "ltb_trigger_submit_host + ltb_trigger_collect (two calls in flight)"}
 
         host, out["e2e"] = run_e2e(a.format)
