@@ -37,7 +37,7 @@ def make_batch(pool, n_streams, n, snr, master_seed):
 
 
 def main(check=None):
-    """check(iq, records, threshold) -> dict merged into the SNR point (used by tests/c4_snr_sweep.py)."""
+    """check(iq, records, threshold, corr) -> dict merged into the SNR point (used by tests/c4_snr_sweep.py)."""
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("--streams", type=int, default=256)
     ap.add_argument("--seconds", type=float, default=0.5)
@@ -46,6 +46,7 @@ def main(check=None):
     ap.add_argument("--snr-step", type=int, default=1)
     ap.add_argument("-t", "--threshold", type=float, default=4.0)
     ap.add_argument("--seed", type=int, default=20260)
+    ap.add_argument("--corr", default="fft", choices=["fft", "direct"], help="matched-filter evaluation")
     ap.add_argument("--workers", type=int, default=os.cpu_count())
     ap.add_argument("-o", "--output", default=None)
     a = ap.parse_args()
@@ -53,7 +54,8 @@ def main(check=None):
     import ltetrigger_b200 as lt
     n = int(a.seconds * 1.92e6) // 8 * 8
     pool = mp.get_context("fork").Pool(a.workers) if a.workers > 1 else None
-    trig = lt.Trigger(n_streams=a.streams, decim=1, psr_threshold=a.threshold, max_chunk=n)
+    trig = lt.Trigger(n_streams=a.streams, decim=1, psr_threshold=a.threshold, max_chunk=n,
+                      corr_mode=lt.CORR_FFT if a.corr == "fft" else lt.CORR_DIRECT)
     points = []
     for snr in range(a.snr_min, a.snr_max + 1, a.snr_step):
         iq, ids = make_batch(pool, a.streams, n, float(snr), a.seed + 1000 * (snr + 100))
@@ -78,13 +80,13 @@ def main(check=None):
               "median_first_tag_ms": (float(np.median(first)) / 1920.0 if first else None),
               "engine_wall_ms": 1e3 * dt}
         if check is not None:
-            pt.update(check(iq, got, a.threshold))
+            pt.update(check(iq, got, a.threshold, a.corr))
         points.append(pt)
         print(json.dumps(pt), flush=True)
     if pool:
         pool.close()
-    out = {"config": "C4: %d streams x %.2f s at 1.92 Msps per SNR point, threshold %.1f, seed %d" % (
-        a.streams, a.seconds, a.threshold, a.seed), "points": points}
+    out = {"config": "C4: %d streams x %.2f s at 1.92 Msps per SNR point, threshold %.1f, seed %d, %s correlator" % (
+        a.streams, a.seconds, a.threshold, a.seed, a.corr), "points": points}
     if a.output:
         with open(a.output, "w") as f:
             json.dump(out, f, indent=1)

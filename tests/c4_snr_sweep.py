@@ -16,9 +16,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "examples"))
 
 
-def check(iq, got, threshold):
+def check(iq, got, threshold, corr):
     from oracle import oracle as O
-    want = O.trigger_run(iq, decim=1, psr_threshold=threshold)
+    want = O.trigger_run(iq, decim=1, psr_threshold=threshold, conv_mode=O.CONV_OS if corr == "fft" else O.CONV_DIRECT)
     same = len(want) == len(got)
     for f in (want.dtype.names if same else ()):
         g, w = got[f], want[f]
