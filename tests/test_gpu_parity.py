@@ -425,3 +425,39 @@ def test_full_path_scaling_and_permutation_properties(lt, corr):
         ra, rc = a[a["stream"] == s_old], c[c["stream"] == s_new].copy()
         rc["stream"] = s_old
         assert ra.tobytes() == rc.tobytes(), (s_new, s_old)
+
+
+def test_c_abi_error_behaviour(lt):
+    """Return codes of the engine entry points (srsLTE convention 0 / -1 / -2, lib/sss_impl.cc:119): a
+    record buffer that is too small is filled as far as it goes and reported, oversized and misaligned
+    chunks are refused without side effects, optional features say so when they are off."""
+    import ctypes as C
+    from ltetrigger_b200 import _abi as A
+    L = lt.lib()
+    x, _, _ = load_fixture("6prb", 0.2)
+    trig = lt.Trigger(n_streams=1, max_chunk=96000)
+    full = trig.run(x[None, :96000 * 4]).copy()
+    trig.reset()
+    small = np.zeros(5, A.WINDOW_REC)
+    n = C.c_int32(0)
+    iq = np.ascontiguousarray(x[:96000])
+    rc = L.ltb_trigger_process_host(trig._h, iq.ctypes.data, 0, 96000, small.ctypes.data, 5, C.byref(n))
+    assert rc == lt.ERROR_INVALID_INPUTS and n.value > 5              # says how many there were
+    assert small.tobytes() == full[:5].tobytes()                      # and filled what fitted
+    big = np.zeros(96008, np.complex64)
+    assert L.ltb_trigger_process_host(trig._h, big.ctypes.data, 0, 96008, small.ctypes.data, 5, C.byref(n)) == lt.ERROR_INVALID_INPUTS
+    assert L.ltb_trigger_process_host(trig._h, None, 0, 96000, small.ctypes.data, 5, C.byref(n)) == lt.ERROR_INVALID_INPUTS
+    assert L.ltb_trigger_collect(trig._h, small.ctypes.data, 5, C.byref(n)) == lt.ERROR_INVALID_INPUTS   # nothing submitted
+    with pytest.raises(lt.LtbError):
+        trig.fetch_halfframes(4)                                      # keep_halfframes is off
+    st = A.PssStats()
+    assert L.ltb_trigger_get_stats(trig._h, 3, 0, C.byref(st)) == lt.ERROR_INVALID_INPUTS
+    assert L.ltb_trigger_get_stats(trig._h, 0, 3, C.byref(st)) == lt.ERROR_INVALID_INPUTS
+    # the refused calls left the engine where it was: the remaining chunks give the remaining records
+    rest = trig.run(x[None, 96000:96000 * 4])
+    assert len(rest) == len(full) - n.value
+    for k in range(3):
+        fk, rk = full[full["n_id_2"] == k], rest[rest["n_id_2"] == k]
+        assert fk[len(fk) - len(rk):].tobytes() == rk.tobytes()
+    with pytest.raises(lt.LtbError):
+        lt.Trigger(n_streams=1, device=99)                            # no such CUDA device
