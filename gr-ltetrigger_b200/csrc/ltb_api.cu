@@ -319,7 +319,8 @@ struct ltb_trigger {
   cudaStream_t copy_stream = nullptr;     // record read-back, overlaps the next call's kernels
   float2 *d_sss_sym = nullptr;
   int *d_sss_rec = nullptr;
-  int *d_sss_count = nullptr;     // [0] SSS candidate count, [1] track-kernel chain queue head
+  int *d_sss_count = nullptr;     // [0] SSS candidate count, [1] track-kernel chain queue head, [2..3] chain_order_kernel
+  int *d_chain_order = nullptr;   // [n_chains]
   int sss_cap = 0;
   float2 *d_hf = nullptr;
   float2 *d_tail[2] = {nullptr, nullptr};
@@ -357,7 +358,7 @@ void trigger_free(ltb_trigger *t) {
   cudaSetDevice(t->cfg.device);
   cudaFree(t->d_in[0]); cudaFree(t->d_in[1]); cudaFree(t->d_y); cudaFree(t->d_p); cudaFree(t->d_state); cudaFree(t->d_avg);
   cudaFree(t->d_thr); cudaFree(t->d_sss_sym);
-  cudaFree(t->d_sss_rec); cudaFree(t->d_sss_count); cudaFree(t->d_hf); cudaFree(t->d_tail[0]);
+  cudaFree(t->d_sss_rec); cudaFree(t->d_sss_count); cudaFree(t->d_chain_order); cudaFree(t->d_hf); cudaFree(t->d_tail[0]);
   cudaFree(t->d_tail[1]); cudaFree(t->d_cexp); cudaFree(t->d_branch_taps);
   for (auto &sl : t->slot) {
     cudaFree(sl.d_recs); cudaFree(sl.d_rec_count);
@@ -412,7 +413,9 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   t->n_total += m;
   t->w_cur = m / (kHalf - kSlot) + 4;
   if (t->w_cur > t->w_cap) t->w_cur = t->w_cap;
-  LTB_CUDA(cudaMemsetAsync(t->d_sss_count, 0, 2 * sizeof(int), t->stream));
+  LTB_CUDA(cudaMemsetAsync(t->d_sss_count, 0, 4 * sizeof(int), t->stream));
+  chain_order_kernel<<<(t->n_chains + 255) / 256, 256, 0, t->stream>>>(t->d_state, t->n_chains, t->d_chain_order, t->d_sss_count + 2);
+  launches++;
   TrackParams P;
   P.y_ring = t->d_y; P.p_ring = t->d_p; P.state = t->d_state; P.avg = t->d_avg; P.thr = t->d_thr;
   P.recs = sl.d_recs; P.rec_count = sl.d_rec_count; P.sss_sym = t->d_sss_sym; P.sss_rec = t->d_sss_rec;
@@ -422,6 +425,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   P.root_mask = c.root_mask;
   P.tdd = c.frame_type == LTB_FRAME_TDD;
   P.chain_counter = t->d_sss_count + 1; P.n_chains = t->n_chains;
+  P.chain_order = t->d_chain_order;
   {
     int ctas = 4 * (g_sm_count[c.device] > 0 ? g_sm_count[c.device] : 148);
     if (ctas > t->n_chains) ctas = t->n_chains;
@@ -526,7 +530,8 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   }
   LTB_CUDA_T(cudaMalloc(&t->d_sss_sym, sizeof(float2) * 128 * (size_t)t->sss_cap));
   LTB_CUDA_T(cudaMalloc(&t->d_sss_rec, sizeof(int) * t->sss_cap));
-  LTB_CUDA_T(cudaMalloc(&t->d_sss_count, 2 * sizeof(int)));
+  LTB_CUDA_T(cudaMalloc(&t->d_sss_count, 4 * sizeof(int)));
+  LTB_CUDA_T(cudaMalloc(&t->d_chain_order, sizeof(int) * t->n_chains));
   LTB_CUDA_T(cudaMalloc(&t->d_tail[0], sizeof(float2) * (size_t)S * kTailCap));
   LTB_CUDA_T(cudaMalloc(&t->d_tail[1], sizeof(float2) * (size_t)S * kTailCap));
   if (c.keep_halfframes) LTB_CUDA_T(cudaMalloc(&t->d_hf, sizeof(float2) * kHalf * (size_t)t->n_chains * t->w_cap));

@@ -87,6 +87,7 @@ struct TrackParams {
   int *sss_rec;              // [sss_cap] -> index into recs
   int *sss_count;            // global counter
   int *chain_counter;        // work queue head (zeroed before every launch)
+  const int *chain_order;    // queue position -> chain: tracking chains (the long jobs) first
   int n_chains;
   int sss_cap;
   float2 *hf_out;            // [n_streams*3][w_max][9600] or null
@@ -1319,6 +1320,19 @@ __device__ __forceinline__ float edge_power(const float2 *buf, int pos, int n_id
   return __fmaf_rn(re, re, __fmul_rn(im, im));
 }
 
+// Queue order for pss_track_kernel: a tracking chain (CFO, CP metric and SSS extraction on every
+// window) runs ~1.5x as long as a searching one, and 1536 chains over 592 resident CTAs are 2.6
+// rounds, so the long jobs go first and the short ones fill the tail.  Tracking chains are placed
+// from the front, the others from the back; the order inside a class does not matter (chains are
+// independent and write to slots fixed by their own index).  counters: [0] front, [1] back.
+__global__ void __launch_bounds__(256) chain_order_kernel(const ChainState *__restrict__ state, int n_chains,
+                                                          int *__restrict__ order, int *__restrict__ counters) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chains; i += gridDim.x * blockDim.x) {
+    if (state[i].tracking) order[atomicAdd(&counters[0], 1)] = i;
+    else order[n_chains - 1 - atomicAdd(&counters[1], 1)] = i;
+  }
+}
+
 __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TrackShared &S = *reinterpret_cast<TrackShared *>(smem_raw);
@@ -1327,7 +1341,10 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
   // 1536 chains over 444 resident CTAs were 3.46 waves, i.e. four rounds of the slowest chain.
   for (;;) {
   __syncthreads();                                                  // previous chain fully written back
-  if (tid == 0) S.chain = atomicAdd(P.chain_counter, 1);
+  if (tid == 0) {
+    const int q = atomicAdd(P.chain_counter, 1);
+    S.chain = q < P.n_chains ? P.chain_order[q] : P.n_chains;
+  }
   __syncthreads();
   const int chain = S.chain;
   if (chain >= P.n_chains) break;

@@ -159,7 +159,7 @@ def test_fft_correlator_chunking_and_batch(lt, oracle):
     from ltetrigger_b200 import synth
     iq, ids = synth.batch(6, 384000, 0.0, master_seed=77)
     want = oracle.trigger_run(iq, conv_mode=oracle.CONV_OS)
-    for chunk in (8 * 1117, 8 * 9001, 384000):
+    for chunk in (8 * 100, 8 * 1117, 8 * 9001, 384000):        # 800 < one 896-sample block: calls without a new block
         trig = lt.Trigger(n_streams=6, decim=1, max_chunk=chunk, corr_mode=lt.CORR_FFT)
         got = trig.run(iq, chunk=chunk)
         assert_recs_equal(got, want)
