@@ -24,7 +24,7 @@ def launches(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     hdr = rows[0]
     ci = {h: i for i, h in enumerate(hdr)}
-    ours = ("ltb::", "decimate_", "pss_corr", "pss_track", "sss_kernel", "sss_block", "tail_kernel", "ingest_kernel")
+    ours = ("ltb::", "decimate_", "pss_corr", "pss_track", "sss_kernel", "sss_block", "tail_kernel", "ingest_kernel", "chain_order")
     mine = [r for r in rows[1:] if any(k in r[ci["Kernel Name"]] for k in ours)]
     print("# our kernels in %s: %d launches (torch data-generation kernels of bench.py omitted)" % (path, len(mine)))
     print("id,kernel,grid,block,ns")
