@@ -94,30 +94,29 @@ def main(args):
 
 
 def parse(argv=None):
-    def filetype(fname):
-        if os.path.isfile(fname):
-            return fname
-        raise argparse.ArgumentTypeError("file {} does not exist".format(fname))
+    """The reference CLI's flags (examples/cell_search_file.py:140-200): same names, types and defaults."""
+    def existing_file(name):
+        if not os.path.isfile(name):
+            raise argparse.ArgumentTypeError("file {} does not exist".format(name))
+        return name
 
-    parser = argparse.ArgumentParser()
-    parser.add_argument("filename", type=filetype)
-    parser.add_argument("-s", "--sample-rate", type=eng_float, required=True, metavar="Hz",
-                        help="input data's sample rate [Required]")
-    parser.add_argument("-f", "--frequency", type=eng_float, metavar="Hz", help="input data's center frequency")
-    parser.add_argument("--repeat", action="store_true",
-                        help="loop file until cell found or cut-off reached [default=%(default)s]")
-    parser.add_argument("-c", "--cut-off", type=eng_int, metavar="N", default=-1,
-                        help="stop looping after N samples [default=%(default)s]")
-    parser.add_argument("--throttle", type=eng_float, metavar="Hz",
-                        help="throttle file source to lower CPU load [default=%(default)s]")
-    parser.add_argument("--time-out", type=eng_float, metavar="sec", default=-1,
-                        help="max time in seconds to perform search [default=%(default)s]")
-    parser.add_argument("--threshold", type=eng_float, default=4,
-                        help="set peak to side-lobe ratio threshold [default=%(default)s]")
-    parser.add_argument("--gui", action="store_true", help=argparse.SUPPRESS)
-    parser.add_argument("--debug", action="store_true", help=argparse.SUPPRESS)
-    parser.add_argument("--fifoname", default=None, required=False, help="FIFO name to which to write output")
-    return parser.parse_args(argv)
+    ap = argparse.ArgumentParser(description="search an IQ capture (fc32) for LTE cells on the GPU")
+    ap.add_argument("filename", type=existing_file)
+    options = [
+        (("-s", "--sample-rate"), dict(type=eng_float, required=True, metavar="Hz", help="sample rate of the capture (a multiple of 1.92 MHz)")),
+        (("-f", "--frequency"), dict(type=eng_float, metavar="Hz", help="center frequency of the capture (informational)")),
+        (("--repeat",), dict(action="store_true", help="start over at the end of the file until a cell is found, the cut-off or the time-out")),
+        (("-c", "--cut-off"), dict(type=eng_int, metavar="N", default=-1, help="give up after N input samples")),
+        (("--throttle",), dict(type=eng_float, metavar="Hz", help="accepted for compatibility; the GPU path is not throttled")),
+        (("--time-out",), dict(type=eng_float, metavar="sec", default=-1, help="give up after this many seconds")),
+        (("--threshold",), dict(type=eng_float, default=4, help="PSR threshold of the trigger (clamped to > 1.5)")),
+        (("--gui",), dict(action="store_true", help=argparse.SUPPRESS)),
+        (("--debug",), dict(action="store_true", help=argparse.SUPPRESS)),
+        (("--fifoname",), dict(default=None, help="also write every result to this FIFO as '<length>\\n<json>'")),
+    ]
+    for flags, kw in options:
+        ap.add_argument(*flags, **kw)
+    return ap.parse_args(argv)
 
 
 if __name__ == "__main__":
