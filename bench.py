@@ -166,7 +166,7 @@ def run_reference(a, rank, world):
         times.append(dt)
     total = sum(times)
     value = a.cpu_streams * n * a.steps / total / 1e6
-    sample = "%d streams x %d ms per step (same synthetic workload), oracle ORC_CONV_FFT, %d threads" % (
+    sample = "%d streams x %d ms per step (same synthetic workload), oracle ORC_CONV_FFT (SIMD decimator, FFT convolution), %d threads" % (
         a.cpu_streams, a.segment_ms, cores)
     line = {
         "impl": "reference", "metric": "PSS+SSS search Msamples/s", "value": value, "unit": "Msamples/s",
@@ -420,8 +420,8 @@ def main():
             out["cpu_baseline"] = {"value": sc * n * reps / dt / 1e6, "unit": "Msamples/s", "cores": os.cpu_count(),
                                    "kind": "port",
                                    "sample": "%d passes over %d streams x %d ms of the same workload (%.1f s wall); oracle in "
-                                             "reference-class FFT mode (9728-point FFT convolution per window and root), "
-                                             "one job per (stream, root) on all cores" % (reps, sc, a.segment_ms, dt)}
+                                             "reference-class mode (SIMD dot-product decimator, 9728-point FFT convolution per window "
+                                             "and root), one job per stream / (stream, root) on all cores" % (reps, sc, a.segment_ms, dt)}
             # the same leg also uses the oracle as what it is, the checker: the benchmarked configuration
             # (rate, format, correlator) on a few of the bench's own streams, every record compared bit for bit
             from oracle import oracle as O

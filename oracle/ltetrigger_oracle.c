@@ -219,6 +219,41 @@ int64_t orc_decimate(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
   return n_out;
 }
 
+/* The same filter the way a CPU implementation evaluates it (gr::filter::fir_filter_ccf /
+ * volk dot product: one output at a time over contiguous taps, SIMD lanes as independent
+ * accumulators).  Used for the timed CPU baseline only (ORC_CONV_FFT, the reference-class mode):
+ * the canonical order above is scalar by construction and would charge the reference path for
+ * something its own resampler does not do.  Same taps, rounding differs in the last bits. */
+int64_t orc_decimate_fast(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
+{
+  if (decim <= 1) { memcpy(y, x, sizeof(orc_cf) * n_in); return n_in; }
+  if (decim > 64) return -1;
+  float taps[4096];
+  int ntaps = orc_decim_taps(decim, taps, 4096);
+  if (ntaps <= 0) return -1;
+  /* reversed taps, each twice (re, im lanes), zero padded to a multiple of 32 floats */
+  const int nt2 = ((2 * ntaps + 31) / 32) * 32;
+  float *t2 = calloc(nt2 + 32, sizeof(float));
+  for (int j = 0; j < ntaps; j++) { t2[2 * j] = taps[ntaps - 1 - j]; t2[2 * j + 1] = taps[ntaps - 1 - j]; }
+  /* input with ntaps - 1 zeros in front (zero initial state) and padding behind, as floats */
+  const int64_t lead = ntaps - 1;
+  float *xf = calloc(2 * (size_t)(lead + n_in) + nt2 + 32, sizeof(float));
+  memcpy(xf + 2 * lead, x, sizeof(orc_cf) * n_in);
+  int64_t n_out = (n_in + decim - 1) / decim;
+  for (int64_t k = 0; k < n_out; k++) {
+    const float *w = xf + 2 * (k * decim);                /* x[kD - (ntaps-1)] .. x[kD] */
+    float acc[32];                                        /* four 8-float vectors in flight */
+    for (int l = 0; l < 32; l++) acc[l] = 0.f;
+    for (int i = 0; i < nt2; i += 32)
+      for (int l = 0; l < 32; l++) acc[l] = fmaf(t2[i + l], w[i + l], acc[l]);
+    float re = 0.f, im = 0.f;
+    for (int l = 0; l < 32; l += 2) { re += acc[l]; im += acc[l + 1]; }
+    y[k].re = re; y[k].im = im;
+  }
+  free(t2); free(xf);
+  return n_out;
+}
+
 /* ------------------------------------------------------------------------- */
 /* PSS matched filter                                                         */
 /* ------------------------------------------------------------------------- */
@@ -1105,7 +1140,12 @@ static void trig_frontend(int s, void *arg)
   if (t->fmt == 1) orc_sc16_to_fc32((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, 1.0f / 32768.0f, x);
   else if (t->fmt == 2) orc_sc8_to_fc32((const int8_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, 1.0f / 128.0f, x);
   else memcpy(x, (const orc_cf *)t->iq + (size_t)s * t->n_in, sizeof(orc_cf) * t->n_in);
-  if (t->decim > 1) { t->ys[s] = malloc(sizeof(orc_cf) * t->n_out); orc_decimate(x, t->n_in, t->decim, t->ys[s]); free(x); }
+  if (t->decim > 1) {
+    t->ys[s] = malloc(sizeof(orc_cf) * t->n_out);
+    if ((t->conv_mode & 0xff) == ORC_CONV_FFT) orc_decimate_fast(x, t->n_in, t->decim, t->ys[s]);   /* timed baseline */
+    else orc_decimate(x, t->n_in, t->decim, t->ys[s]);
+    free(x);
+  }
   else t->ys[s] = x;
 }
 

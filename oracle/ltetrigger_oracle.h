@@ -95,6 +95,9 @@ void orc_fft128_twiddles(float w_re[64], float w_im[64]);
 /* ---- front end ----------------------------------------------------------- */
 /* y[k] = sum_j taps[j] x[kD-j], zero initial state; n_out = ceil(n_in/D); -1 if D > 64. */
 int64_t orc_decimate(const orc_cf *x, int64_t n_in, int decim, orc_cf *y);
+/* the same filter evaluated output by output with SIMD-lane accumulators (what a CPU resampler does);
+ * used by the timed reference-class mode (ORC_CONV_FFT) only */
+int64_t orc_decimate_fast(const orc_cf *x, int64_t n_in, int decim, orc_cf *y);
 void    orc_sc16_to_fc32(const int16_t *iq, int64_t n, float scale, orc_cf *out);
 void    orc_sc8_to_fc32(const int8_t *iq, int64_t n, float scale, orc_cf *out);
 

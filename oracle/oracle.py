@@ -56,6 +56,8 @@ def lib():
         L.orc_fft128_twiddles.argtypes = [fp, fp]
         L.orc_decimate.argtypes = [vp, C.c_int64, C.c_int, vp]
         L.orc_decimate.restype = C.c_int64
+        L.orc_decimate_fast.argtypes = [vp, C.c_int64, C.c_int, vp]
+        L.orc_decimate_fast.restype = C.c_int64
         L.orc_sc16_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_sc8_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_pss_corr_window.argtypes = [vp, C.c_int, C.c_int, fp]
@@ -136,6 +138,16 @@ def decimate(x, decim):
     y = np.zeros(n_out, np.complex64)
     if lib().orc_decimate(x.ctypes.data, len(x), decim, y.ctypes.data) < 0:
         raise RuntimeError("orc_decimate: unsupported decimation %d" % decim)
+    return y
+
+
+def decimate_fast(x, decim):
+    """The CPU-style evaluation used by the timed baseline (same taps, last-bit differences)."""
+    x = np.ascontiguousarray(x, np.complex64)
+    n_out = (len(x) + decim - 1) // decim if decim > 1 else len(x)
+    y = np.zeros(n_out, np.complex64)
+    if lib().orc_decimate_fast(x.ctypes.data, len(x), decim, y.ctypes.data) < 0:
+        raise RuntimeError("orc_decimate_fast: unsupported decimation %d" % decim)
     return y
 
 
