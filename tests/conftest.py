@@ -53,7 +53,8 @@ def assert_recs_equal(got, want, float_fields_exact=True):
         g, w = got[name], want[name]
         if g.dtype.kind == "f":
             gb, wb = g.view(np.uint32), w.view(np.uint32)
-            same = (gb == wb) | ((g == 0) & (w == 0))          # +0 == -0
+            same = (gb == wb) | ((g == 0) & (w == 0)) | (np.isnan(g) & np.isnan(w))   # +0 == -0; NaN payloads (0/0 on
+            # silent input: x86 gives the negative quiet NaN, the GPU the canonical one) are not part of the contract
             if not same.all():
                 i = int(np.argmin(same))
                 raise AssertionError("field %s differs at record %d: got %r want %r (stream %d root %d win %d)"

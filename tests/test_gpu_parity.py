@@ -461,3 +461,21 @@ def test_c_abi_error_behaviour(lt):
         assert fk[len(fk) - len(rk):].tobytes() == rk.tobytes()
     with pytest.raises(lt.LtbError):
         lt.Trigger(n_streams=1, device=99)                            # no such CUDA device
+
+
+def test_fft_correlator_edge_cases(lt, oracle):
+    """LTB_CORR_FFT on degenerate input: shorter than the lookahead -> no call; all zeros -> NaN PSR and
+    nothing emitted; a stream that starts mid-frame and a silent stream next to it; reset."""
+    trig = lt.Trigger(n_streams=2, decim=1, max_chunk=96000, corr_mode=lt.CORR_FFT)
+    assert len(trig.process(np.zeros((2, 18360), np.complex64))) == 0
+    recs = trig.process(np.zeros((2, 96000), np.complex64))
+    assert len(recs) > 0 and np.isnan(recs["psr"]).all() and (recs["flags"] & lt.F_EMIT == 0).all()
+    x, _, _ = load_fixture("6prb", 0.3)
+    iq = np.stack([x[5000:5000 + 480000], np.zeros(480000, np.complex64)])
+    trig.reset()
+    a = trig.run(iq).copy()
+    want = oracle.trigger_run(iq, conv_mode=oracle.CONV_OS)
+    assert_recs_equal(a, want)
+    assert 123 in a[a["stream"] == 0]["cell_id"] and np.isnan(a[a["stream"] == 1]["psr"]).all()
+    trig.reset()
+    assert trig.run(iq).tobytes() == a.tobytes()
