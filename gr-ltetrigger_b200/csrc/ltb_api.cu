@@ -61,9 +61,10 @@ int ensure_constants(int device) {
   for (int r = 0; r < 3; ++r)
     for (int n = 0; n < 128; ++n) full[r][n] = make_float2(taps[r].re[n], taps[r].im[n]);
   LTB_CUDA(cudaMemcpyToSymbol(c_pss_taps, full, sizeof full));
-  float dt[1000];
+  float dt[1400];
   std::memset(dt, 0, sizeof dt);
-  for (int d = 4; d <= 16; d *= 2) {
+  const int stream_rates[4] = {4, 8, 12, 16};
+  for (int d : stream_rates) {
     std::vector<float> v = make_decim_taps(d);
     if ((int)v.size() != decim_ntaps(d)) return fail(LTB_ERROR, "unexpected decimator tap count");
     std::memcpy(dt + decim_tap_offset(d), v.data(), v.size() * sizeof(float));
@@ -110,6 +111,7 @@ int ensure_constants(int device) {
 #define LTB_SMEM_ATTR_FMT(FMT)                                                                  \
   LTB_SMEM_ATTR(decimate_stream_kernel<FMT>, decim_stream_smem_bytes<FMT>());                   \
   LTB_SMEM_ATTR(decimate_any_kernel<FMT>, decim_any_smem_bytes(kMaxDecim));                     \
+  LTB_SMEM_ATTR(decimate_stream12_kernel<FMT>, decim_stream12_smem_bytes<FMT>());               \
   LTB_SMEM_ATTR((decimate_stream2_kernel<FMT, 8>), (decim_stream2_smem_bytes<FMT, 8>()));       \
   LTB_SMEM_ATTR((decimate_stream2_kernel<FMT, 4>), (decim_stream2_smem_bytes<FMT, 4>()));       \
   LTB_SMEM_ATTR((decimate_kernel<FMT, 4>), decim_smem_bytes(4)); \
@@ -188,7 +190,7 @@ int make_cexp_device(float2 **out) {
 }
 
 // ltb_debug_set_flag: [0] decimator dissection bits, [1] bit 0: decimate with the general kernel at
-// every rate, bit 1: D = 8, 4 with the tiled kernel instead of the streaming one, [2] extra dynamic smem for the tiled decimator (occupancy experiments), [3] unused
+// every rate, bit 1: D = 12, 8, 4 with the tiled kernel instead of the streaming one, [2] extra dynamic smem for the tiled decimator (occupancy experiments), [3] unused
 int g_debug_flags[4] = {0, 0, 0, 0};
 
 bool valid_decim(int d) { return d >= 1 && d <= kMaxDecim; }
@@ -229,6 +231,17 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
     long long ctas = 2LL * (g_sm_count[dev] > 0 ? g_sm_count[dev] : 148);
     if (ctas > total) ctas = total;
     decimate_stream_kernel<FMT><<<(unsigned)ctas, kStrThreads, decim_stream_smem_bytes<FMT>(), st>>>(
+        d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total, g_debug_flags[0]);
+  } else if (decim == 12 && !force_any && !(g_debug_flags[1] & 2)) {
+    // streaming variant for D = 12: the D = 16 kernel with twelve of sixteen lanes at work
+    int dev = 0;
+    LTB_CUDA(cudaGetDevice(&dev));
+    const int sps = (m + kStrSeg - 1) / kStrSeg;
+    const long long total = (long long)sps * n_streams;
+    if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator segments in one call");
+    long long ctas = 2LL * (g_sm_count[dev] > 0 ? g_sm_count[dev] : 148);
+    if (ctas > total) ctas = total;
+    decimate_stream12_kernel<FMT><<<(unsigned)ctas, kStrThreads, decim_stream12_smem_bytes<FMT>(), st>>>(
         d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total, g_debug_flags[0]);
   } else if ((decim == 8 || decim == 4) && !force_any && !(g_debug_flags[1] & 2)) {
     // streaming variant for D = 8, 4 (debug flag 1 bit 1 selects the tiled kernel instead)

@@ -45,8 +45,8 @@ template <> struct fmt_elem<LTB_FMT_SC8> { typedef char2 type; };
 __constant__ float2 c_pss_coef[2][65][2];
 // full 128-tap filters per N_id_2 (CFO estimate): (re, im)
 __constant__ float2 c_pss_taps[3][128];
-// decimator taps for D = 4, 8, 16 at offsets 72, 208, 472 (padded with zeros): the streaming kernels
-__constant__ float c_decim_taps[1000];
+// decimator taps for D = 4, 8, 16, 12 at offsets 72, 208, 472, 1000 (padded with zeros): the streaming kernels
+__constant__ float c_decim_taps[1400];
 __constant__ float2 c_fft128_tw[64];
 // SSS tables per N_id_2: c0, c1 (31 each); shared s_tilde, z_tilde; N_id_1 table
 __constant__ float c_sss_c0[3][32];
@@ -55,8 +55,8 @@ __constant__ float c_sss_s[32];
 __constant__ float c_sss_z[32];
 __constant__ short c_sss_nid1[900];
 
-__host__ __device__ constexpr int decim_tap_offset(int d) { return d == 2 ? 0 : d == 4 ? 72 : d == 8 ? 208 : 472; }
-__host__ __device__ constexpr int decim_ntaps(int d) { return d == 2 ? 65 : d == 4 ? 131 : d == 8 ? 263 : d == 16 ? 525 : 0; }
+__host__ __device__ constexpr int decim_tap_offset(int d) { return d == 2 ? 0 : d == 4 ? 72 : d == 8 ? 208 : d == 12 ? 1000 : 472; }
+__host__ __device__ constexpr int decim_ntaps(int d) { return d == 2 ? 65 : d == 4 ? 131 : d == 8 ? 263 : d == 12 ? 393 : d == 16 ? 525 : 0; }
 
 // ------------------------------------------------------------------------------------
 // per-chain state (one pss block + one sss block of the reference)
@@ -532,6 +532,197 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
       auto ld = [&](int e) -> float2 {                             // element e of the window
         if (FMT == LTB_FMT_FC32) return reinterpret_cast<const float2 *>(base)[e * 16];
         const elem_t r = base[e * 16];
+        return make_float2((float)r.x, (float)r.y);
+      };
+      constexpr int PF = 4;                                        // elements loaded ahead of their use
+      float2 x[PF];
+#pragma unroll
+      for (int j = 0; j < PF; ++j) x[j] = ld(kDecT - 1 - j);
+#pragma unroll
+      for (int e = kDecT - 1; e >= -(kDecQ - 1); --e) {
+        const int slot = (kDecT - 1 - e) % PF;
+        const float2 xe = x[slot];
+        if (e - PF >= -(kDecQ - 1)) x[slot] = ld(e - PF);
+#pragma unroll
+        for (int o = 0; o < kDecT; ++o) {
+          const int q = o - e;
+          if (q >= 0 && q < kDecQ) {
+            const float2 cc = make_float2(c[q], c[q]);
+            acc[o] = ffma2(cc, xe, q == 0 ? make_float2(0.f, 0.f) : acc[o]);
+          }
+        }
+      }
+    }
+    // transpose through the warp's scratch in two passes of 8 outputs (row = (half, position),
+    // column = output): lane (g, oo) of a half-warp sums positions 8g..8g+7 of output 8*pass + oo
+    // in the canonical pairwise tree, one shuffle adds the two halves of the tree, and the lane
+    // whose g equals the pass keeps the result, so lane l ends with output 32*warp + l
+    {
+      const int g8 = (lane >> 3) & 1, oo = lane & 7;
+      float2 *wr = scratch + p * kStrScratchRow;
+      const float2 *rd = scratch + (8 * g8) * kStrScratchRow + oo;
+      float2 res = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        __syncwarp();
+#pragma unroll
+        for (int o = 0; o < 8; ++o) wr[o] = acc[8 * pass + o];
+        __syncwarp();
+        float2 pp[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) pp[r] = rd[r * kStrScratchRow];
+#pragma unroll
+        for (int w2 = 1; w2 < 8; w2 <<= 1) {
+#pragma unroll
+          for (int r = 0; r < 8; r += 2 * w2) pp[r] = fadd2(pp[r], pp[r + w2]);
+        }
+        float2 other;
+        other.x = __shfl_xor_sync(0xffffffffu, pp[0].x, 8);
+        other.y = __shfl_xor_sync(0xffffffffu, pp[0].y, 8);
+        const float2 tot = g8 ? fadd2(other, pp[0]) : fadd2(pp[0], other);   // (P0..7) + (P8..15)
+        if (g8 == pass) res = tot;
+      }
+      const int k = S.k0 + 32 * warp + lane;
+      if (k < n_out) y_ring[(size_t)S.stream * cap + (unsigned)((n_base + k) & cap_mask)] = res;
+    }
+    // release buffer b without a CTA barrier: the last of the warps to get here requests the
+    // segment that goes into it next, so no warp ever waits for its siblings
+    __syncwarp();
+    if (i + kStrBufs < s_end) {
+      if (lane == 0 && (atomicAdd(&s_done[b], 1u) % kStrWarps) == kStrWarps - 1 && is_fast(req)) request(req, b);
+      advance(req);
+    }
+    advance(cur);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K1s12: the streaming decimator at D = 12 (23.04 Msps, the 15 MHz LTE rate).  The D = 16 kernel with
+// twelve of the sixteen lanes of a half-warp at work: blocks are 12 samples, lanes 12..15 run the same
+// instruction stream on a window of zeros with zero taps, so their partial sums are exact +0 and the
+// 16-row reduction below IS the canonical tree of a non-power-of-two rate (zero partials pad it).
+// A quarter of the FFMA2 lanes is idle, which still beats the tiled kernel's shared-memory limit.
+// ------------------------------------------------------------------------------------
+template <int FMT> __host__ __device__ constexpr int str12_lead() {
+  return (33 * 12 * fmt_bytes(FMT)) % 16 == 0 ? 33 : 34;
+}
+template <int FMT> __host__ __device__ constexpr size_t decim_stream12_smem_bytes() {
+  return (size_t)kStrBufs * (kStrSeg + str12_lead<FMT>()) * 12 * fmt_bytes(FMT) + sizeof(float2) * kStrScratch * kStrWarps +
+         ((kDecT + kDecQ) * 12 + 16) * fmt_bytes(FMT);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kStrThreads, 2)
+decimate_stream12_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
+                       float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int segs_per_stream,
+                       int total_segs, int dbg) {
+  constexpr int D = 12;
+  constexpr int BPS = fmt_bytes(FMT);                              // bytes per input sample
+  constexpr int LEAD = str12_lead<FMT>();                          // blocks copied in front of the segment
+  constexpr int NB = kStrSeg + LEAD;
+  constexpr int BUF = NB * D * BPS;
+  constexpr int ZEROS = (kDecT + kDecQ) * D + 16;                  // elements of the idle lanes' zero window
+  static_assert(BUF % 16 == 0 && (LEAD * D * BPS) % 16 == 0, "cp.async.bulk size and alignment");
+  typedef typename fmt_elem<FMT>::type elem_t;
+  extern __shared__ __align__(128) unsigned char s_raw[];          // [kStrBufs][NB blocks][12 positions], scratch, zeros
+  __shared__ __align__(8) unsigned long long s_full[kStrBufs];
+  __shared__ unsigned s_done[kStrBufs];                            // warps finished with a buffer (monotonic)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p = lane & 15, half = lane >> 4;
+  const bool active = p < D;                                       // lanes 12..15 of a half-warp idle on zeros
+  const long long n_in = (long long)n_out * D;
+
+  const int s_begin = (int)((long long)total_segs * blockIdx.x / gridDim.x);
+  const int s_end = (int)((long long)total_segs * (blockIdx.x + 1) / gridDim.x);
+  if (s_begin >= s_end) return;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < kStrBufs; ++b) { mbar_init(&s_full[b], 1); s_done[b] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  elem_t *zeros = reinterpret_cast<elem_t *>(s_raw + kStrBufs * BUF + sizeof(float2) * kStrScratch * kStrWarps);
+  for (int i = tid; i < ZEROS; i += kStrThreads) memset(&zeros[i], 0, sizeof(elem_t));
+  __syncthreads();
+
+  // this lane's taps: position p <-> polyphase branch v = (16 - p) % 16, c[q] = taps[16 q + v]
+  // (sc16 / sc8: the 2^-15 / 2^-7 input scale is folded into the taps; both products are exact,
+  //  so fma(c * 2^-15, s, acc) == fma(c, s * 2^-15, acc) bit for bit)
+  float c[kDecQ];
+  {
+    const int v = active ? (D - p) % D : 0;
+#pragma unroll
+    for (int q = 0; q < kDecQ; ++q) {
+      const float t = active ? c_decim_taps[decim_tap_offset(D) + q * D + v] : 0.f;   // zero padded beyond ntaps
+      c[q] = FMT == LTB_FMT_FC32 ? t : __fmul_rn(t, fmt_scale(FMT));
+      // keep the 33 taps in registers: without this the compiler re-reads them from the constant
+      // bank inside the FMA loop, and a lane-indexed LDC replays once per distinct address
+      asm volatile("" : "+f"(c[q]));
+    }
+  }
+
+  // segment cursors (stream, k0), advanced incrementally: `cur` is computed on, `req` is the next
+  // one to request (kStrBufs ahead)
+  struct Seg { int stream, k0; };
+  const int k_end = segs_per_stream * kStrSeg;
+  auto advance = [&](Seg &S) { S.k0 += kStrSeg; if (S.k0 >= k_end) { S.k0 = 0; S.stream++; } };
+  auto is_fast = [&](const Seg &S) { return S.k0 >= LEAD && (long long)D * (S.k0 + kStrSeg) <= n_in && !(dbg & 1); };
+  auto request = [&](const Seg &S, int b) {                        // one thread: TMA for segment S into buffer b
+    const char *src = (const char *)in + (long long)S.stream * stride_bytes;
+    mbar_expect_tx(&s_full[b], BUF);
+    bulk_copy_g2s(s_raw + b * BUF, src + (long long)D * (S.k0 - LEAD) * BPS, BUF, &s_full[b]);
+  };
+  Seg cur, req;
+  cur.stream = s_begin / segs_per_stream;
+  cur.k0 = (s_begin - cur.stream * segs_per_stream) * kStrSeg;
+  req = cur;
+  for (int j = 0; j < kStrBufs && s_begin + j < s_end; ++j) {
+    if (tid == 0 && is_fast(req)) request(req, j);
+    advance(req);
+  }
+
+  unsigned phase_bits = 0;                                         // parity of each buffer's barrier
+  // window element e (= o - q) of this lane sits at block  32*warp + 16*half + 32 + (p == 0) + e
+  const int lane_elem = (32 * warp + 16 * half + LEAD - 1 + (p == 0 ? 1 : 0)) * D + p;
+  float2 *scratch = reinterpret_cast<float2 *>(s_raw + kStrBufs * BUF) + warp * kStrScratch + half * 16 * kStrScratchRow;
+
+  for (int i = s_begin; i < s_end; ++i) {
+    const int b = (i - s_begin) % kStrBufs;
+    const Seg S = cur;
+    elem_t *buf = reinterpret_cast<elem_t *>(s_raw + b * BUF);
+    if (is_fast(S)) {
+      mbar_wait(&s_full[b], (phase_bits >> b) & 1u);
+      phase_bits ^= 1u << b;
+    } else if (!(dbg & 1)) {
+      // boundary segment: element-wise, with the carried tail before the chunk and zeros after it
+      // (rare: two per stream and call; the only place where the warps of a CTA meet)
+      __syncthreads();                                             // every warp has left buffer b
+      const char *src = (const char *)in + (long long)S.stream * stride_bytes;
+      const long long i_first = (long long)D * (S.k0 - LEAD);
+      const float2 *tail = tail_in + (size_t)S.stream * kTailCap;
+      for (int j = tid; j < NB * D; j += kStrThreads) {
+        const long long idx = i_first + j;
+        float2 val = make_float2(0.f, 0.f);
+        if (idx >= 0) { if (idx < n_in) val = load_in_sample<FMT>(src, idx); }
+        else if (idx >= -kTailCap) val = tail[kTailCap + idx];
+        if (FMT == LTB_FMT_FC32) reinterpret_cast<float2 *>(buf)[j] = val;
+        else if (FMT == LTB_FMT_SC16) reinterpret_cast<short2 *>(buf)[j] = make_short2((short)__fmul_rn(val.x, 32768.0f), (short)__fmul_rn(val.y, 32768.0f));
+        else reinterpret_cast<char2 *>(buf)[j] = make_char2((signed char)__fmul_rn(val.x, 128.0f), (signed char)__fmul_rn(val.y, 128.0f));
+      }
+      __syncthreads();
+    }
+
+    // Element-major order: window element e (block offset from the lane's base) feeds output o
+    // with tap q = o - e.  Walking e downwards keeps every accumulator's chain in ascending q
+    // (the canonical order) while the up-to-16 consecutive FFMA2 of one element share their data
+    // operand through the register reuse cache: 3 register reads per FFMA2 instead of 4, which is
+    // what lets the pipe run at 2 cycles per FFMA2 (tools/ubench_issue.cu).
+    float2 acc[kDecT];
+    {
+      const elem_t *base = active ? buf + lane_elem : zeros + (kDecQ - 1) * D;
+      auto ld = [&](int e) -> float2 {                             // element e of the window
+        if (FMT == LTB_FMT_FC32) return reinterpret_cast<const float2 *>(base)[e * D];
+        const elem_t r = base[e * D];
         return make_float2((float)r.x, (float)r.y);
       };
       constexpr int PF = 4;                                        // elements loaded ahead of their use

@@ -120,7 +120,7 @@ typedef struct {
   int32_t  input_format;      /* LTB_FMT_* */
   int32_t  decim;             /* input rate / 1.92 Msps, any integer 1..LTB_MAX_DECIM as the reference's
                                  CLI accepts (examples/cell_search_file.py:50-57); streaming kernels for
-                                 4, 8, 16, the tiled kernel for the other rates up to 15, a general one above */
+                                 4, 8, 12, 16, the tiled kernel for the other rates up to 15, a general one above */
   int32_t  root_mask;         /* bit k set: run the N_id_2 = k chain; 0 -> 7 (all three) */
   int64_t  max_chunk;         /* largest n_samples (input rate, per stream) of one process call */
   float    psr_threshold;     /* clamped to > 1.5 like downlink_trigger_c.py:71-73 */

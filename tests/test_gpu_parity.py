@@ -102,7 +102,7 @@ def test_general_decimator_agrees_with_tuned_kernels(lt, oracle, decim):
     for s in range(2):
         assert np.array_equal(general[s].view(np.uint32), want[s].view(np.uint32))
         assert np.array_equal(tuned[s].view(np.uint32), want[s].view(np.uint32))
-    if decim in (4, 8):                      # these rates also have the tiled kernel (flag bit 1)
+    if decim in (4, 8, 12):                  # these rates also have the tiled kernel (flag bit 1)
         lt.lib().ltb_debug_set_flag(1, 2)
         try:
             tiled = lt.kernel_decimate(x, decim, 0)
