@@ -25,6 +25,11 @@ for name in FIXTURES:
         out[name][field] = recs[field].tolist()
     out[name]["psr_bits"] = recs["psr"].view(np.uint32).tolist()
     out[name]["cfo_bits"] = recs["cfo"].view(np.uint32).tolist()
+    # the overlap-save evaluation of the matched filter (ORC_CONV_OS): same decisions, own PSR bits
+    os_recs = O.trigger_run(x[None, :], decim=decim, conv_mode=O.CONV_OS)
+    assert all((os_recs[f] == recs[f]).all() for f in ("win_start", "emit_start", "flags", "peak_pos", "m0", "m1", "cell_id"))
+    out[name]["os_psr_bits"] = os_recs["psr"].view(np.uint32).tolist()
+    out[name]["os_peak_value_bits"] = os_recs["peak_value"].view(np.uint32).tolist()
 with open(os.path.join(HERE, "fixture_traces.json"), "w") as f:
     json.dump(out, f)
 print("wrote", {k: v["n_records"] for k, v in out.items()})

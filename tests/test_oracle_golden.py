@@ -87,6 +87,9 @@ def test_golden_traces(oracle):
             assert recs[field].tolist() == g[field], (name, field)
         assert recs["psr"].view(np.uint32).tolist() == g["psr_bits"], name
         assert recs["cfo"].view(np.uint32).tolist() == g["cfo_bits"], name
+        os_recs = oracle.trigger_run(x[None, :], decim=decim, conv_mode=oracle.CONV_OS)
+        assert os_recs["psr"].view(np.uint32).tolist() == g["os_psr_bits"], name
+        assert os_recs["peak_value"].view(np.uint32).tolist() == g["os_peak_value_bits"], name
 
 
 def test_edge_cases(oracle):
