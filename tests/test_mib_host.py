@@ -156,3 +156,28 @@ def test_mib_block_drop_protocol():
     assert feed([lt.tag_t(0, "tracking_lost", None)]) == 0 and dropped == tracked and dropped[0] is tracked[0]
     assert feed([lt.tag_t(0, "tracking_lost", None)]) == 0 and len(dropped) == 1   # nothing published: no second drop
     assert feed(good) == 9600 and len(tracked) == 2
+
+
+def test_cellstore_track_drop_by_identity():
+    """lib/cellstore_impl.cc:46-105 (python/qa_cellstore.py is an empty shell in the reference): "track"
+    appends, "drop" removes the identical object only, accessors as include/ltetrigger/cellstore.h:59-65."""
+    import ltetrigger_b200 as lt
+    store = lt.cellstore()
+    assert store.message_ports() == ["track", "drop"] and not store.tracking() and store.latest_cell() is None
+    a, b, twin = {"cell_id": 1}, {"cell_id": 2}, {"cell_id": 1}
+    store.track_cell(a)
+    store.track_cell(b)
+    assert store.tracking() and store.cells() == [a, b] and store.latest_cell() is b
+    store.drop_cell(twin)                          # equal but not the same object: stays (pmt identity, :103)
+    assert store.cells() == [a, b]
+    store.drop_cell(a)
+    assert store.cells() == [b] and store.latest_cell() is b
+    store.drop_cell(b)
+    assert not store.tracking() and store.cells() == []
+    # wired to a mib stage like examples/cell_search_file.py:82-88
+    mb = lt.mib()
+    store.connect(mb)
+    mb._pub("track", a)
+    assert store.latest_cell() is a
+    mb._pub("drop", a)
+    assert not store.tracking()
