@@ -479,3 +479,34 @@ def test_fft_correlator_edge_cases(lt, oracle):
     assert 123 in a[a["stream"] == 0]["cell_id"] and np.isnan(a[a["stream"] == 1]["psr"]).all()
     trig.reset()
     assert trig.run(iq).tobytes() == a.tobytes()
+
+
+def test_two_engines_from_two_host_threads(lt, oracle):
+    """The ABI's threading contract: one host thread per object at a time, different objects from
+    different threads concurrently (the reference runs one scheduler thread per block).  Two engines
+    with different rates, formats and correlators run in parallel threads and both match the oracle."""
+    import threading
+    from ltetrigger_b200 import synth
+    xa = np.stack([synth.capture(c, 16 * 200000, snr_db=6.0, decim=16, seed=c) for c in (21, 400)])
+    xb16 = synth.to_sc16(np.stack([synth.capture(c, 480000, snr_db=3.0, seed=c) for c in (77, 78, 79)]))
+    out, err = {}, []
+
+    def run(key, iq, **kw):
+        try:
+            trig = lt.Trigger(n_streams=iq.shape[0], **kw)
+            parts = []
+            for _ in range(3):                       # several passes so the two threads really overlap
+                trig.reset()
+                parts.append(trig.run(iq, chunk=kw["max_chunk"]).copy())
+            assert parts[0].tobytes() == parts[1].tobytes() == parts[2].tobytes()
+            out[key] = parts[0]
+            trig.close()
+        except Exception as e:                       # surfaced in the main thread below
+            err.append((key, e))
+
+    ta = threading.Thread(target=run, args=("a", xa), kwargs=dict(decim=16, max_chunk=16 * 50000, corr_mode=lt.CORR_FFT))
+    tb = threading.Thread(target=run, args=("b", xb16), kwargs=dict(decim=1, max_chunk=96000, input_format=lt.FMT_SC16))
+    ta.start(); tb.start(); ta.join(); tb.join()
+    assert not err, err
+    assert_recs_equal(out["a"], oracle.trigger_run(xa, decim=16, conv_mode=oracle.CONV_OS))
+    assert_recs_equal(out["b"], oracle.trigger_run(xb16, decim=1, fmt=1))
