@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstddef>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -61,9 +62,9 @@ int ensure_constants(int device) {
   for (int r = 0; r < 3; ++r)
     for (int n = 0; n < 128; ++n) full[r][n] = make_float2(taps[r].re[n], taps[r].im[n]);
   LTB_CUDA(cudaMemcpyToSymbol(c_pss_taps, full, sizeof full));
-  float dt[1400];
+  static float dt[sizeof(c_decim_taps) / sizeof(float)];
   std::memset(dt, 0, sizeof dt);
-  const int stream_rates[4] = {4, 8, 12, 16};
+  const int stream_rates[7] = {4, 8, 12, 13, 14, 15, 16};
   for (int d : stream_rates) {
     std::vector<float> v = make_decim_taps(d);
     if ((int)v.size() != decim_ntaps(d)) return fail(LTB_ERROR, "unexpected decimator tap count");
@@ -111,7 +112,10 @@ int ensure_constants(int device) {
 #define LTB_SMEM_ATTR_FMT(FMT)                                                                  \
   LTB_SMEM_ATTR(decimate_stream_kernel<FMT>, decim_stream_smem_bytes<FMT>());                   \
   LTB_SMEM_ATTR(decimate_any_kernel<FMT>, decim_any_smem_bytes(kMaxDecim));                     \
-  LTB_SMEM_ATTR(decimate_stream12_kernel<FMT>, decim_stream12_smem_bytes<FMT>());               \
+  LTB_SMEM_ATTR((decimate_stream12_kernel<FMT, 12>), (decim_stream12_smem_bytes<FMT, 12>()));   \
+  LTB_SMEM_ATTR((decimate_stream12_kernel<FMT, 13>), (decim_stream12_smem_bytes<FMT, 13>()));   \
+  LTB_SMEM_ATTR((decimate_stream12_kernel<FMT, 14>), (decim_stream12_smem_bytes<FMT, 14>()));   \
+  LTB_SMEM_ATTR((decimate_stream12_kernel<FMT, 15>), (decim_stream12_smem_bytes<FMT, 15>()));   \
   LTB_SMEM_ATTR((decimate_stream2_kernel<FMT, 8>), (decim_stream2_smem_bytes<FMT, 8>()));       \
   LTB_SMEM_ATTR((decimate_stream2_kernel<FMT, 4>), (decim_stream2_smem_bytes<FMT, 4>()));       \
   LTB_SMEM_ATTR((decimate_kernel<FMT, 4>), decim_smem_bytes(4)); \
@@ -190,7 +194,7 @@ int make_cexp_device(float2 **out) {
 }
 
 // ltb_debug_set_flag: [0] decimator dissection bits, [1] bit 0: decimate with the general kernel at
-// every rate, bit 1: D = 12, 8, 4 with the tiled kernel instead of the streaming one, [2] extra dynamic smem for the tiled decimator (occupancy experiments), [3] unused
+// every rate, bit 1: D = 12..15, 8, 4 with the tiled kernel instead of the streaming one, [2] extra dynamic smem for the tiled decimator (occupancy experiments), [3] unused
 int g_debug_flags[4] = {0, 0, 0, 0};
 
 bool valid_decim(int d) { return d >= 1 && d <= kMaxDecim; }
@@ -221,7 +225,12 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
   }
   const dim3 grid((m + kDecOut - 1) / kDecOut, n_streams);
   const bool force_any = (g_debug_flags[1] & 1) != 0;      // parity tests: run the general kernel at every rate
-  if (decim == 16 && !force_any) {
+  // the streaming kernels move whole segments with 16-byte bulk copies: a base or row stride that is
+  // only sample aligned takes the tiled / general kernel instead (same bits, lower rate)
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(d_iq) | (uintptr_t)stride) & 15u) == 0;
+  if ((reinterpret_cast<uintptr_t>(d_iq) | (uintptr_t)stride) & (uintptr_t)(fmt_bytes(FMT) - 1))
+    return fail(LTB_ERROR_INVALID_INPUTS, "input pointer and row stride must be multiples of the sample size");
+  if (decim == 16 && !force_any && aligned16) {
     // streaming variant: two persistent 8-warp CTAs per SM, each a contiguous run of 256-output segments
     int dev = 0;
     LTB_CUDA(cudaGetDevice(&dev));
@@ -232,8 +241,8 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
     if (ctas > total) ctas = total;
     decimate_stream_kernel<FMT><<<(unsigned)ctas, kStrThreads, decim_stream_smem_bytes<FMT>(), st>>>(
         d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total, g_debug_flags[0]);
-  } else if (decim == 12 && !force_any && !(g_debug_flags[1] & 2)) {
-    // streaming variant for D = 12: the D = 16 kernel with twelve of sixteen lanes at work
+  } else if (decim >= 12 && decim <= 15 && !force_any && aligned16 && !(g_debug_flags[1] & 2)) {
+    // streaming variant for D = 12..15: the D = 16 kernel with D of sixteen lanes at work
     int dev = 0;
     LTB_CUDA(cudaGetDevice(&dev));
     const int sps = (m + kStrSeg - 1) / kStrSeg;
@@ -241,9 +250,14 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
     if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator segments in one call");
     long long ctas = 2LL * (g_sm_count[dev] > 0 ? g_sm_count[dev] : 148);
     if (ctas > total) ctas = total;
-    decimate_stream12_kernel<FMT><<<(unsigned)ctas, kStrThreads, decim_stream12_smem_bytes<FMT>(), st>>>(
-        d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total, g_debug_flags[0]);
-  } else if ((decim == 8 || decim == 4) && !force_any && !(g_debug_flags[1] & 2)) {
+#define LTB_STREAM12_CASE(D)                                                                                        \
+  case D:                                                                                                           \
+    decimate_stream12_kernel<FMT, D><<<(unsigned)ctas, kStrThreads, decim_stream12_smem_bytes<FMT, D>(), st>>>(    \
+        d_iq, stride, m, tail_old, y_ring, n_base, mask, cap, sps, (int)total, g_debug_flags[0]);                  \
+    break;
+    switch (decim) { LTB_STREAM12_CASE(12) LTB_STREAM12_CASE(13) LTB_STREAM12_CASE(14) LTB_STREAM12_CASE(15) }
+#undef LTB_STREAM12_CASE
+  } else if ((decim == 8 || decim == 4) && !force_any && aligned16 && !(g_debug_flags[1] & 2)) {
     // streaming variant for D = 8, 4 (debug flag 1 bit 1 selects the tiled kernel instead)
     int dev = 0;
     LTB_CUDA(cudaGetDevice(&dev));
@@ -859,19 +873,20 @@ int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, 
   const int m = (int)(n_in / decim);
   const int cap = next_pow2(m + 8);
   const size_t in_row = (size_t)n_in * fmt_bytes(fmt);
+  const size_t dev_row = (in_row + 127) / 128 * 128;   // the streaming kernels' bulk copies need 16-byte aligned rows
   void *d_in = nullptr; float2 *d_y = nullptr, *d_t0 = nullptr, *d_t1 = nullptr;
   float *d_bt = nullptr;
   rc = make_branch_taps_device(decim, &d_bt);
   if (rc) return rc;
-  cudaError_t e = cudaMalloc(&d_in, in_row * n_streams);
+  cudaError_t e = cudaMalloc(&d_in, dev_row * n_streams);
   if (e == cudaSuccess) e = cudaMalloc(&d_y, sizeof(float2) * (size_t)n_streams * cap);
   if (e == cudaSuccess) e = cudaMalloc(&d_t0, sizeof(float2) * (size_t)n_streams * kTailCap);
   if (e == cudaSuccess) e = cudaMalloc(&d_t1, sizeof(float2) * (size_t)n_streams * kTailCap);
   if (e == cudaSuccess) e = cudaMemset(d_t0, 0, sizeof(float2) * (size_t)n_streams * kTailCap);
-  if (e == cudaSuccess) e = cudaMemcpy(d_in, x, in_row * n_streams, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy2D(d_in, dev_row, x, in_row, in_row, n_streams, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     int launches = 0;
-    rc = launch_frontend_fmt(fmt, decim, d_in, (long long)in_row, n_streams, m, d_t0, d_t1, d_bt, d_y, 0, (unsigned)(cap - 1), cap, 0, &launches);
+    rc = launch_frontend_fmt(fmt, decim, d_in, (long long)dev_row, n_streams, m, d_t0, d_t1, d_bt, d_y, 0, (unsigned)(cap - 1), cap, 0, &launches);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy2D(y, sizeof(float2) * (size_t)m, d_y, sizeof(float2) * (size_t)cap, sizeof(float2) * (size_t)m, n_streams, cudaMemcpyDeviceToHost);

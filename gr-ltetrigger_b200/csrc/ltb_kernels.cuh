@@ -45,8 +45,9 @@ template <> struct fmt_elem<LTB_FMT_SC8> { typedef char2 type; };
 __constant__ float2 c_pss_coef[2][65][2];
 // full 128-tap filters per N_id_2 (CFO estimate): (re, im)
 __constant__ float2 c_pss_taps[3][128];
-// decimator taps for D = 4, 8, 16, 12 at offsets 72, 208, 472, 1000 (padded with zeros): the streaming kernels
-__constant__ float c_decim_taps[1400];
+// decimator taps for D = 4, 8, 16 at offsets 72, 208, 472 and D = 12..15 from 1000 (padded with zeros):
+// the streaming kernels
+__constant__ float c_decim_taps[1000 + 33 * (12 + 13 + 14 + 15)];
 __constant__ float2 c_fft128_tw[64];
 // SSS tables per N_id_2: c0, c1 (31 each); shared s_tilde, z_tilde; N_id_1 table
 __constant__ float c_sss_c0[3][32];
@@ -55,8 +56,12 @@ __constant__ float c_sss_s[32];
 __constant__ float c_sss_z[32];
 __constant__ short c_sss_nid1[900];
 
-__host__ __device__ constexpr int decim_tap_offset(int d) { return d == 2 ? 0 : d == 4 ? 72 : d == 8 ? 208 : d == 12 ? 1000 : 472; }
-__host__ __device__ constexpr int decim_ntaps(int d) { return d == 2 ? 65 : d == 4 ? 131 : d == 8 ? 263 : d == 12 ? 393 : d == 16 ? 525 : 0; }
+__host__ __device__ constexpr int decim_tap_offset(int d) {
+  return d == 2 ? 0 : d == 4 ? 72 : d == 8 ? 208 : d == 16 ? 472 : 1000 + 33 * ((d - 12) * (d + 11) / 2);   // 12..15 back to back
+}
+__host__ __device__ constexpr int decim_ntaps(int d) {
+  return d == 2 ? 65 : d == 4 ? 131 : d == 8 ? 263 : d == 12 ? 393 : d == 13 ? 427 : d == 14 ? 459 : d == 15 ? 493 : d == 16 ? 525 : 0;
+}
 
 // ------------------------------------------------------------------------------------
 // per-chain state (one pss block + one sss block of the reference)
@@ -597,39 +602,43 @@ decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int 
 }
 
 // ------------------------------------------------------------------------------------
-// K1s12: the streaming decimator at D = 12 (23.04 Msps, the 15 MHz LTE rate).  The D = 16 kernel with
-// twelve of the sixteen lanes of a half-warp at work: blocks are 12 samples, lanes 12..15 run the same
+// K1s12: the streaming decimator at D = 12..15 (12: 23.04 Msps, the 15 MHz LTE rate).  The D = 16 kernel
+// with D of the sixteen lanes of a half-warp at work: blocks are D samples, lanes D..15 run the same
 // instruction stream on a window of zeros with zero taps, so their partial sums are exact +0 and the
 // 16-row reduction below IS the canonical tree of a non-power-of-two rate (zero partials pad it).
-// A quarter of the FFMA2 lanes is idle, which still beats the tiled kernel's shared-memory limit.
+// Up to a quarter of the FFMA2 lanes is idle, which still beats the tiled kernel's shared-memory limit.
 // ------------------------------------------------------------------------------------
-template <int FMT> __host__ __device__ constexpr int str12_lead() {
-  return (33 * 12 * fmt_bytes(FMT)) % 16 == 0 ? 33 : 34;
+// blocks copied in front of a segment: 33 of filter history plus what starts the bulk copy on a 16-byte
+// boundary and makes its size a multiple of 16 (segments start at multiples of 256 outputs)
+template <int FMT, int D> __host__ __device__ constexpr int str12_lead() {
+  int l = 33;
+  while ((l * D * fmt_bytes(FMT)) % 16 != 0 || ((kStrSeg + l) * D * fmt_bytes(FMT)) % 16 != 0) ++l;
+  return l;
 }
-template <int FMT> __host__ __device__ constexpr size_t decim_stream12_smem_bytes() {
-  return (size_t)kStrBufs * (kStrSeg + str12_lead<FMT>()) * 12 * fmt_bytes(FMT) + sizeof(float2) * kStrScratch * kStrWarps +
-         ((kDecT + kDecQ) * 12 + 16) * fmt_bytes(FMT);
+template <int FMT, int D> __host__ __device__ constexpr size_t decim_stream12_smem_bytes() {
+  return (size_t)kStrBufs * (kStrSeg + str12_lead<FMT, D>()) * D * fmt_bytes(FMT) + sizeof(float2) * kStrScratch * kStrWarps +
+         ((kDecT + kDecQ + str12_lead<FMT, D>() - 33) * D + 16) * fmt_bytes(FMT);
 }
 
-template <int FMT>
+template <int FMT, int D>
 __global__ void __launch_bounds__(kStrThreads, 2)
 decimate_stream12_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
                        float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int segs_per_stream,
                        int total_segs, int dbg) {
-  constexpr int D = 12;
+  static_assert(D >= 12 && D <= 15, "D = 16: decimate_stream_kernel");
   constexpr int BPS = fmt_bytes(FMT);                              // bytes per input sample
-  constexpr int LEAD = str12_lead<FMT>();                          // blocks copied in front of the segment
+  constexpr int LEAD = str12_lead<FMT, D>();                       // blocks copied in front of the segment
   constexpr int NB = kStrSeg + LEAD;
   constexpr int BUF = NB * D * BPS;
-  constexpr int ZEROS = (kDecT + kDecQ) * D + 16;                  // elements of the idle lanes' zero window
+  constexpr int ZEROS = (kDecT + kDecQ + LEAD - 33) * D + 16;      // elements of the idle lanes' zero window
   static_assert(BUF % 16 == 0 && (LEAD * D * BPS) % 16 == 0, "cp.async.bulk size and alignment");
   typedef typename fmt_elem<FMT>::type elem_t;
-  extern __shared__ __align__(128) unsigned char s_raw[];          // [kStrBufs][NB blocks][12 positions], scratch, zeros
+  extern __shared__ __align__(128) unsigned char s_raw[];          // [kStrBufs][NB blocks][D positions], scratch, zeros
   __shared__ __align__(8) unsigned long long s_full[kStrBufs];
   __shared__ unsigned s_done[kStrBufs];                            // warps finished with a buffer (monotonic)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = lane & 15, half = lane >> 4;
-  const bool active = p < D;                                       // lanes 12..15 of a half-warp idle on zeros
+  const bool active = p < D;                                       // lanes D..15 of a half-warp idle on zeros
   const long long n_in = (long long)n_out * D;
 
   const int s_begin = (int)((long long)total_segs * blockIdx.x / gridDim.x);

@@ -147,7 +147,9 @@ LTB_API int ltb_trigger_set_psr_threshold(ltb_trigger *t, int stream, int n_id_2
 
 /* Feed n_samples new input-rate samples per stream (a multiple of 8*decim) and run every
  * chain as far as the lookahead rule allows.  Stream s starts at
- * (char*)iq + s*stream_stride_bytes.  *_host takes host memory (pinned for full PCIe
+ * (char*)iq + s*stream_stride_bytes; pointer and stride must be multiples of the sample size, and
+ * multiples of 16 bytes for the fastest decimators (otherwise a slower kernel gives the same bits).
+ * *_host takes host memory (pinned for full PCIe
  * rate) and copies it in; *_device takes device memory on cfg.device.  Records are
  * written to `recs` ordered by (stream, n_id_2, win_index); *n_recs is the count
  * (if it exceeds max_recs the call returns LTB_ERROR_INVALID_INPUTS after filling

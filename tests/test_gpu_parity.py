@@ -73,7 +73,7 @@ def _decim_case(oracle, rng, decim, fmt, n):
     return x, want
 
 
-@pytest.mark.parametrize("decim", [2, 3, 4, 5, 6, 7, 8, 11, 12, 13, 16, 24, 64])
+@pytest.mark.parametrize("decim", [2, 3, 4, 5, 6, 7, 8, 11, 12, 13, 14, 15, 16, 24, 64])
 @pytest.mark.parametrize("fmt", [0, 1, 2])
 def test_decimate_kernel_bit_exact(lt, oracle, decim, fmt):
     """rational_resampler_ccc(1, D) for any integer D (examples/cell_search_file.py:50-57): the
@@ -87,7 +87,7 @@ def test_decimate_kernel_bit_exact(lt, oracle, decim, fmt):
             assert np.array_equal(got[s].view(np.uint32), want[s].view(np.uint32)), n_out
 
 
-@pytest.mark.parametrize("decim", [2, 4, 8, 12, 16])
+@pytest.mark.parametrize("decim", [2, 4, 8, 12, 15, 16])
 def test_general_decimator_agrees_with_tuned_kernels(lt, oracle, decim):
     """Debug flag 1 routes every rate through decimate_any_kernel: three independent kernels and
     the oracle give the same bits."""
@@ -102,7 +102,7 @@ def test_general_decimator_agrees_with_tuned_kernels(lt, oracle, decim):
     for s in range(2):
         assert np.array_equal(general[s].view(np.uint32), want[s].view(np.uint32))
         assert np.array_equal(tuned[s].view(np.uint32), want[s].view(np.uint32))
-    if decim in (4, 8, 12):                  # these rates also have the tiled kernel (flag bit 1)
+    if decim in (4, 8, 12, 15):              # these rates also have the tiled kernel (flag bit 1)
         lt.lib().ltb_debug_set_flag(1, 2)
         try:
             tiled = lt.kernel_decimate(x, decim, 0)
@@ -510,3 +510,25 @@ def test_two_engines_from_two_host_threads(lt, oracle):
     assert not err, err
     assert_recs_equal(out["a"], oracle.trigger_run(xa, decim=16, conv_mode=oracle.CONV_OS))
     assert_recs_equal(out["b"], oracle.trigger_run(xb16, decim=1, fmt=1))
+
+
+@pytest.mark.parametrize("decim", [16, 12, 8])
+def test_device_input_that_is_only_sample_aligned(lt, oracle, decim):
+    """The streaming decimators copy 16-byte aligned segments; a device buffer whose base or row
+    stride is merely sample aligned (8 bytes for fc32) runs a slower kernel and gives the same
+    records.  A pointer that is not even sample aligned is refused."""
+    import torch
+    from ltetrigger_b200 import synth
+    n = 8 * decim * 12000
+    x = np.stack([synth.capture(c, n, snr_db=8.0, decim=decim, seed=c) for c in (55, 56)])
+    want = oracle.trigger_run(x, decim=decim)
+    buf = torch.zeros(2 * (n + 3) + 1, dtype=torch.complex64, device="cuda")
+    view = buf[1:1 + 2 * (n + 3)].view(2, n + 3)          # base 8 bytes off, row stride 8 (n + 3) bytes
+    view[:, :n] = torch.from_numpy(x).cuda()
+    assert view.data_ptr() % 16 == 8
+    trig = lt.Trigger(n_streams=2, decim=decim, max_chunk=n)
+    got = trig.process_device_ptr(view.data_ptr(), 8 * (n + 3), n).copy()
+    got = got[np.lexsort((got["win_index"], got["n_id_2"], got["stream"]))]
+    assert_recs_equal(got, want)
+    with pytest.raises(lt.LtbError):
+        trig.process_device_ptr(view.data_ptr() + 4, 8 * (n + 3), n)
