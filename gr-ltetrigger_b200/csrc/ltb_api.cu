@@ -216,10 +216,14 @@ template <int FMT>
 int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams, int m, float2 *tail_old,
                     float2 *tail_new, const float *branch_taps, float2 *y_ring, long long n_base, unsigned mask,
                     int cap, cudaStream_t st, int *launches) {
+  const uintptr_t addr_bits = reinterpret_cast<uintptr_t>(d_iq) | (uintptr_t)stride;
+  if (addr_bits & (uintptr_t)(fmt_bytes(FMT) - 1))
+    return fail(LTB_ERROR_INVALID_INPUTS, "input pointer and row stride must be multiples of the sample size");
   if (decim == 1) {
     int gx = (m / 2 + 255) / 256;
     if (gx > 1024) gx = 1024;
-    ingest_kernel<FMT><<<dim3(gx, n_streams), 256, 0, st>>>(d_iq, stride, m, y_ring, n_base, mask, cap);
+    const int pairs = (addr_bits & (uintptr_t)(2 * fmt_bytes(FMT) - 1)) == 0;    // two samples per load
+    ingest_kernel<FMT><<<dim3(gx, n_streams), 256, 0, st>>>(d_iq, stride, m, y_ring, n_base, mask, cap, pairs);
     *launches += 1;
     return LTB_SUCCESS;
   }
@@ -227,9 +231,7 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
   const bool force_any = (g_debug_flags[1] & 1) != 0;      // parity tests: run the general kernel at every rate
   // the streaming kernels move whole segments with 16-byte bulk copies: a base or row stride that is
   // only sample aligned takes the tiled / general kernel instead (same bits, lower rate)
-  const bool aligned16 = ((reinterpret_cast<uintptr_t>(d_iq) | (uintptr_t)stride) & 15u) == 0;
-  if ((reinterpret_cast<uintptr_t>(d_iq) | (uintptr_t)stride) & (uintptr_t)(fmt_bytes(FMT) - 1))
-    return fail(LTB_ERROR_INVALID_INPUTS, "input pointer and row stride must be multiples of the sample size");
+  const bool aligned16 = (addr_bits & 15u) == 0;
   if (decim == 16 && !force_any && aligned16) {
     // streaming variant: two persistent 8-warp CTAs per SM, each a contiguous run of 256-output segments
     int dev = 0;

@@ -166,16 +166,32 @@ __device__ double canon_atan2(double y, double x) {
   return r;
 }
 
+// one input sample as float2, whatever the wire format
+template <int FMT>
+__device__ __forceinline__ float2 load_in_sample(const char *src, long long idx) {
+  if (FMT == LTB_FMT_FC32) return *reinterpret_cast<const float2 *>(src + idx * 8);
+  typedef typename fmt_elem<FMT>::type raw_t;
+  const raw_t s = *reinterpret_cast<const raw_t *>(src + idx * fmt_bytes(FMT));
+  const float k = fmt_scale(FMT);
+  return make_float2(__fmul_rn((float)s.x, k), __fmul_rn((float)s.y, k));
+}
+
 // ------------------------------------------------------------------------------------
 // K0: ingest at D = 1 -- convert (sc16) / copy (fc32) the new chunk into the sample ring
 // ------------------------------------------------------------------------------------
 template <int FMT>
 __global__ void __launch_bounds__(256) ingest_kernel(const void *__restrict__ in, long long stride_bytes,
                                                      int n_new, float2 *__restrict__ y_ring,
-                                                     long long n_base, unsigned cap_mask, int cap) {
+                                                     long long n_base, unsigned cap_mask, int cap, int pairs) {
   const int stream = blockIdx.y;
   const char *src = (const char *)in + (long long)stream * stride_bytes;
   float2 *dst = y_ring + (size_t)stream * cap;
+  if (!pairs) {
+    // rows that are only sample aligned: one sample per load
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x)
+      dst[(unsigned)((n_base + i) & cap_mask)] = load_in_sample<FMT>(src, i);
+    return;
+  }
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n_new; i += gridDim.x * blockDim.x * 2) {
     float4 v;
     if (FMT == LTB_FMT_FC32) {
@@ -199,14 +215,6 @@ __global__ void __launch_bounds__(256) ingest_kernel(const void *__restrict__ in
 // K1: polyphase decimator  y[k] = sum_j taps[j] x[kD - j]   (rational_resampler_ccc(1, D))
 // canonical order: branch v = j mod D outer, q = j div D inner, one fma chain per component.
 // ------------------------------------------------------------------------------------
-template <int FMT>
-__device__ __forceinline__ float2 load_in_sample(const char *src, long long idx) {
-  if (FMT == LTB_FMT_FC32) return *reinterpret_cast<const float2 *>(src + idx * 8);
-  typedef typename fmt_elem<FMT>::type raw_t;
-  const raw_t s = *reinterpret_cast<const raw_t *>(src + idx * fmt_bytes(FMT));
-  const float k = fmt_scale(FMT);
-  return make_float2(__fmul_rn((float)s.x, k), __fmul_rn((float)s.y, k));
-}
 
 // Canonical order.  Write the input as aligned blocks X[b][p] = x[b*D + p]
 // (p = "position" 0..D-1).  Output k needs, for polyphase branch v = (D - p) % D and tap q,

@@ -512,7 +512,7 @@ def test_two_engines_from_two_host_threads(lt, oracle):
     assert_recs_equal(out["b"], oracle.trigger_run(xb16, decim=1, fmt=1))
 
 
-@pytest.mark.parametrize("decim", [16, 12, 8])
+@pytest.mark.parametrize("decim", [16, 12, 8, 1])
 def test_device_input_that_is_only_sample_aligned(lt, oracle, decim):
     """The streaming decimators copy 16-byte aligned segments; a device buffer whose base or row
     stride is merely sample aligned (8 bytes for fc32) runs a slower kernel and gives the same
