@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-formats", action="store_true", help="skip the e2e legs on the other wire formats")
+    ap.add_argument("--no-spot-check", action="store_true", help="skip the per-rank oracle check after timing")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the extra sustained run (0: skip)")
     return ap.parse_args()
 
 
@@ -248,6 +250,7 @@ def main():
 
     stream = torch.cuda.current_stream()
     corr_mode = lt.CORR_FFT if a.corr == "fft" else lt.CORR_DIRECT
+    frontend_kw, oracle_front_flag = {}, 0
     trig = lt.Trigger(n_streams=a.streams, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
                       record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode)
     ptr, stride = d_in.data_ptr(), n * bps
@@ -271,8 +274,11 @@ def main():
     e0.record(stream)
     # two calls in flight (ltb_trigger_submit_device / ltb_trigger_collect): call i+1 is enqueued
     # before the records of call i are read, so the stream does not idle on the host round trip
+    last_recs = None
+
     def account(recs):
-        nonlocal stage_ms, launches, n_cells
+        nonlocal stage_ms, launches, n_cells, last_recs
+        last_recs = recs
         stage_ms += np.array(trig.last_kernel_times())
         launches += trig.last_timing()[1]
         n_cells += int(((recs["flags"] & lt.F_CELL) != 0).sum())
@@ -345,6 +351,76 @@ def main():
                    "cells_tagged_per_step": n_cells / a.steps},
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
     }
+
+    last_recs = last_recs.copy()
+
+    # ---- the same step sustained for >= 2 s: the clock the board settles at under its power cap ----
+    if a.sustained_s > 0:
+        k_sus = max(a.steps, int(np.ceil(a.sustained_s * 1e3 / (elapsed_ms / a.steps))))
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        s2.begin()
+        e0.record(stream)
+        trig.submit_device_ptr(ptr, stride, n)
+        for _ in range(k_sus - 1):
+            trig.submit_device_ptr(ptr, stride, n)
+            trig.collect()
+        trig.collect()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        sus_ms = e0.elapsed_time(e1)
+        c2 = s2.result()
+        if world > 1:
+            tt = torch.tensor([sus_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sus_ms = float(tt.item())
+        out["sustained"] = {"value": float(a.streams) * n * k_sus * world / (sus_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                            "steps": k_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / k_sus, "clocks": c2}
+
+    # ---- every rank checks records of its own shard against the oracle (the checker, not the product) ----
+    # the benchmarked configuration (rate, format, correlator, front-end mode) on eight of this rank's own
+    # streams, every record compared bit for bit; the verdicts are AND-reduced over the ranks
+    if not a.no_spot_check:
+        from oracle import oracle as O
+        nchk = min(8, a.streams)
+        pick = torch.linspace(0, a.streams - 1, nchk).round().long().to(dev)
+        iq = d_in.index_select(0, pick).cpu().numpy()
+        chk = lt.Trigger(n_streams=nchk, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
+                         device=local_rank, corr_mode=corr_mode, **frontend_kw)
+        got = chk.run(iq)
+        chk.close()
+        conv = (O.CONV_OS if a.corr == "fft" else O.CONV_DIRECT) | oracle_front_flag
+        want = O.trigger_run(iq, decim=a.decim, fmt=fmt, psr_threshold=4.0, conv_mode=conv)
+        same = len(got) == len(want)
+        for f in (want.dtype.names if same else ()):
+            g_, w_ = got[f], want[f]
+            if g_.dtype.kind == "f":
+                same = same and bool(((g_.view(np.uint32) == w_.view(np.uint32)) | ((g_ == 0) & (w_ == 0))).all())
+            else:
+                same = same and bool((g_ == w_).all())
+        verdict = torch.tensor([1 if same else 0, len(want)], device=dev, dtype=torch.int64)
+        if world > 1:
+            v0 = verdict.clone()
+            dist.all_reduce(verdict[0:1], op=dist.ReduceOp.MIN)
+            dist.all_reduce(v0[1:2], op=dist.ReduceOp.SUM)
+            verdict[1] = v0[1]
+        out["parity_spot_check"] = {"ranks": world, "streams_per_rank": nchk, "records": int(verdict[1].item()),
+                                    "bit_identical_to_oracle": bool(verdict[0].item() == 1),
+                                    "checker": "oracle/ (CPU restatement), same rate/format/correlator/front end as the timed run"}
+
+    # ---- host merge of the (tiny) record lists of the last step: the only exchange between ranks ----
+    from ltetrigger_b200 import shard
+    owned = np.arange(rank * a.streams, (rank + 1) * a.streams, dtype=np.int64)     # weak scaling: rank-major ids
+    t0 = time.perf_counter()
+    merged = shard.merge_records(shard.to_global(last_recs, owned), dst=0)
+    merge_ms = 1e3 * (time.perf_counter() - t0)
+    if rank == 0:
+        out["merge"] = {"records": int(len(merged)), "ms": merge_ms, "ranks": world,
+                        "what": "shard.merge_records of the last step's window records over %s (all-gather, sorted by stream/root/window)"
+                                % ("NCCL" if world > 1 else "no process group: local sort")}
 
     # ---- end to end through the C ABI with host buffers (H2D + D2H inside the timed region) --
     if not a.no_e2e:
@@ -422,25 +498,6 @@ def main():
                                    "sample": "%d passes over %d streams x %d ms of the same workload (%.1f s wall); oracle in "
                                              "reference-class mode (SIMD dot-product decimator, 9728-point FFT convolution per window "
                                              "and root), one job per stream / (stream, root) on all cores" % (reps, sc, a.segment_ms, dt)}
-            # the same leg also uses the oracle as what it is, the checker: the benchmarked configuration
-            # (rate, format, correlator) on a few of the bench's own streams, every record compared bit for bit
-            from oracle import oracle as O
-            nchk = min(8, sc)
-            chk = lt.Trigger(n_streams=nchk, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
-                             device=local_rank, corr_mode=corr_mode)
-            got = chk.run(iq[:nchk])
-            chk.close()
-            want = O.trigger_run(iq[:nchk], decim=a.decim, psr_threshold=4.0,
-                                 conv_mode=O.CONV_OS if a.corr == "fft" else O.CONV_DIRECT)
-            same = len(got) == len(want)
-            for f in (want.dtype.names if same else ()):
-                g, w = got[f], want[f]
-                if g.dtype.kind == "f":
-                    same = same and bool(((g.view(np.uint32) == w.view(np.uint32)) | ((g == 0) & (w == 0))).all())
-                else:
-                    same = same and bool((g == w).all())
-            out["cpu_baseline"]["parity_spot_check"] = {"streams": nchk, "records": int(len(want)),
-                                                        "bit_identical_to_oracle": bool(same)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

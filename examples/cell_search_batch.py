@@ -83,7 +83,7 @@ def search(args):
                                 "cp_len": "Normal" if cp_norm else "Extended", "nof_prb": int(m.nof_prb),
                                 "phich_len": "Normal" if m.phich_length == 0 else "Extended",
                                 "nof_phich_resources": PHICH_RESOURCES[m.phich_resources],
-                                "sfn_offset": int(m.sfn_offset), "tracking_start_time": int(time.time())}
+                                "sfn_offset": int(m.sfn) & ~3, "tracking_start_time": int(time.time())}
         fed += chunk
     trig.close()
     return found
@@ -118,7 +118,7 @@ def parse(argv=None):
     parser.add_argument("--format", default="fc32", choices=["fc32", "sc16", "sc8"],
                         help="sample format of the files [default=%(default)s, the reference's]")
     parser.add_argument("--repeat", action="store_true", help="loop files until all cells found or cut-off reached")
-    parser.add_argument("-c", "--cut-off", type=eng_int, metavar="N", default=-1, help="stop after N samples per file")
+    parser.add_argument("-c", "--cut-off", type=eng_int, metavar="N", default=-1, help="stop after N input-rate samples per file")
     parser.add_argument("--time-out", type=eng_float, metavar="sec", default=-1, help="max time in seconds to perform search")
     parser.add_argument("--threshold", type=eng_float, default=4, help="peak to side-lobe ratio threshold")
     return parser.parse_args(argv)

@@ -52,8 +52,11 @@ def search(args):
     chunk = 96000 * decim                                     # 50 ms per scheduler pass
     fed, t_start = 0, time.time()
     done = lambda: any(m.done for m in (trigger.mib0, trigger.mib1, trigger.mib2))   # WORK_DONE
+    # the reference puts head(cut_off) AFTER the resampler (examples/cell_search_file.py:47-48, 69-77), so
+    # -c counts search-rate samples: here the resampler is fused into the engine, i.e. cut_off * decim inputs
+    cut_in = args.cut_off * decim if args.cut_off > -1 else -1
     while not done():
-        if args.cut_off > -1 and fed >= args.cut_off:
+        if cut_in > -1 and fed >= cut_in:
             break
         if args.cut_off == -1 and args.time_out > -1 and time.time() - t_start >= args.time_out:
             break
@@ -61,8 +64,8 @@ def search(args):
         if pos >= len(data):
             break                                             # end of file without --repeat
         take = min(chunk, len(data) - pos)
-        if args.cut_off > -1:
-            take = min(take, args.cut_off - fed)
+        if cut_in > -1:
+            take = min(take, cut_in - fed)
         trigger.work(data[pos:pos + take])
         fed += take
     return store

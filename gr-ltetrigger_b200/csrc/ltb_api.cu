@@ -193,9 +193,14 @@ int make_cexp_device(float2 **out) {
   return LTB_SUCCESS;
 }
 
-// ltb_debug_set_flag: [0] decimator dissection bits, [1] bit 0: decimate with the general kernel at
+// debug build only (-DLTB_DEBUG, ltb_debug_set_flag; all zero and constant in the release library):
+// [0] decimator dissection bits, [1] bit 0: decimate with the general kernel at
 // every rate, bit 1: D = 12..15, 8, 4 with the tiled kernel instead of the streaming one, [2] extra dynamic smem for the tiled decimator (occupancy experiments), [3] unused
+#ifdef LTB_DEBUG
 int g_debug_flags[4] = {0, 0, 0, 0};
+#else
+constexpr int g_debug_flags[4] = {0, 0, 0, 0};
+#endif
 
 bool valid_decim(int d) { return d >= 1 && d <= kMaxDecim; }
 bool valid_format(int f) { return f == LTB_FMT_FC32 || f == LTB_FMT_SC16 || f == LTB_FMT_SC8; }
@@ -597,7 +602,8 @@ int ltb_trigger_reset(ltb_trigger *t) {
 }
 
 int ltb_trigger_set_psr_threshold(ltb_trigger *t, int stream, int n_id_2, float thr, int clamp) {
-  if (!t || stream >= t->cfg.n_streams || n_id_2 > 2) return fail(LTB_ERROR_INVALID_INPUTS, "bad chain selector");
+  if (!t || stream < -1 || stream >= t->cfg.n_streams || n_id_2 < -1 || n_id_2 > 2)
+    return fail(LTB_ERROR_INVALID_INPUTS, "bad chain selector");
   if (clamp && !(thr > LTB_MIN_PSR_THRESHOLD)) thr = LTB_MIN_PSR_THRESHOLD;
   for (int s = 0; s < t->cfg.n_streams; ++s)
     for (int r = 0; r < 3; ++r)
@@ -620,6 +626,12 @@ int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int 
   LTB_CUDA(cudaSetDevice(t->cfg.device));
   ltb_trigger::Slot &sl = t->slot[t->head];
   LTB_CUDA(cudaEventSynchronize(sl.done));
+  // count first: a buffer that is too small leaves the call pending, so the caller can retry with
+  // *n_recs entries instead of losing the records of a call whose chain state has already advanced
+  int total = 0;
+  for (int ch = 0; ch < t->n_chains; ++ch) total += sl.h_rec_count[ch];
+  *n_recs = total;
+  if (total > max_recs) return fail(LTB_ERROR_INVALID_INPUTS, "record buffer too small: *n_recs entries are needed; the call stays pending");
   t->last = t->head;
   t->head ^= 1;
   t->n_pending--;
@@ -629,17 +641,12 @@ int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int 
   cudaEventElapsedTime(&t->last_kernel_ms[1], sl.ev_k[0], sl.ev_k[1]);
   cudaEventElapsedTime(&t->last_kernel_ms[2], sl.ev_k[1], sl.ev_k[2]);
   cudaEventElapsedTime(&t->last_kernel_ms[3], sl.ev_k[2], sl.ev1);
-  int total = 0, written = 0;
+  int written = 0;
   for (int ch = 0; ch < t->n_chains; ++ch) {
     const int n = sl.h_rec_count[ch];
     const ltb_window_rec *src = sl.h_recs + (size_t)ch * sl.w_cur;
-    for (int i = 0; i < n; ++i) {
-      if (written < max_recs) recs[written++] = src[i];
-      total++;
-    }
+    for (int i = 0; i < n; ++i) recs[written++] = src[i];
   }
-  *n_recs = total;
-  if (total > max_recs) return fail(LTB_ERROR_INVALID_INPUTS, "record buffer too small");
   return LTB_SUCCESS;
 }
 
@@ -661,8 +668,14 @@ int ltb_trigger_submit_host(ltb_trigger *t, const void *iq, int64_t stride, int6
   const int slot = (t->head + t->n_pending) & 1;
   if (!t->d_in[slot]) LTB_CUDA(cudaMalloc(&t->d_in[slot], t->d_in_stride * (size_t)t->cfg.n_streams));
   const size_t row = (size_t)n_samples * fmt_bytes(t->cfg.input_format);
-  LTB_CUDA(cudaMemcpy2DAsync(t->d_in[slot], t->d_in_stride, iq, (size_t)stride, row, (size_t)t->cfg.n_streams,
-                             cudaMemcpyHostToDevice, t->in_stream));
+  if (t->cfg.n_streams == 1) {
+    // one row: the stride is irrelevant (and may be 0), which a pitched copy would reject
+    LTB_CUDA(cudaMemcpyAsync(t->d_in[slot], iq, row, cudaMemcpyHostToDevice, t->in_stream));
+  } else {
+    if ((size_t)stride < row) return fail(LTB_ERROR_INVALID_INPUTS, "stream_stride_bytes is smaller than one row of n_samples");
+    LTB_CUDA(cudaMemcpy2DAsync(t->d_in[slot], t->d_in_stride, iq, (size_t)stride, row, (size_t)t->cfg.n_streams,
+                               cudaMemcpyHostToDevice, t->in_stream));
+  }
   LTB_CUDA(cudaEventRecord(t->in_ready[slot], t->in_stream));
   LTB_CUDA(cudaStreamWaitEvent(t->stream, t->in_ready[slot], 0));
   return trigger_enqueue(t, t->d_in[slot], (long long)t->d_in_stride, n_samples);
@@ -729,11 +742,14 @@ int ltb_trigger_last_timing(ltb_trigger *t, float *ms_total, int *n_launches) {
   return LTB_SUCCESS;
 }
 
+#ifdef LTB_DEBUG
+// only in lib/libltetrigger_b200_debug.so (make debug): the release library has no way to set the flags
 int ltb_debug_set_flag(int flag, int value) {
   if (flag < 0 || flag >= 4) return LTB_ERROR_INVALID_INPUTS;
   g_debug_flags[flag] = value;
   return LTB_SUCCESS;
 }
+#endif
 
 int ltb_trigger_last_kernel_times(ltb_trigger *t, float ms[4]) {
   if (!t || !ms) return LTB_ERROR_INVALID_INPUTS;

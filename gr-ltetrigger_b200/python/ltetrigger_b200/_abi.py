@@ -62,22 +62,39 @@ SYMBOLS = [
     "ltb_trigger_collect", "ltb_trigger_get_stats", "ltb_trigger_fetch_halfframes",
     "ltb_trigger_last_timing", "ltb_trigger_last_kernel_times", "ltb_last_error", "ltb_version", "ltb_device_count",
     "ltb_sss_create", "ltb_sss_destroy", "ltb_sss_set_frame_type", "ltb_sss_work", "ltb_mib_decode",
-    "ltb_kernel_pss_corr_host", "ltb_kernel_pss_corr_fft_host", "ltb_kernel_decimate_host", "ltb_debug_set_flag",
+    "ltb_kernel_pss_corr_host", "ltb_kernel_pss_corr_fft_host", "ltb_kernel_decimate_host",
     "ltb_table_pss_taps", "ltb_table_decim_taps", "ltb_table_sss", "ltb_table_cexp",
     "ltb_table_fft128_twiddles", "ltb_table_fft1024_twiddles", "ltb_table_os_filter",
 ]
 
+DEBUG_LIB_PATH = os.path.join(ROOT, "lib", "libltetrigger_b200_debug.so")
+
 _lib = None
+_debug_lib = None
 
 
 def lib():
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+    if _lib is None:
+        _lib = _load(LIB_PATH)
+    return _lib
+
+
+def debug_lib():
+    """The -DLTB_DEBUG build of the same sources: exports ltb_debug_set_flag (decimator dissection and
+    kernel selection).  Only tests and tools/dissect.py load it; the release library has no such switch."""
+    global _debug_lib
+    if _debug_lib is None:
+        _debug_lib = _load(DEBUG_LIB_PATH)
+        _debug_lib.ltb_debug_set_flag.argtypes = [C.c_int, C.c_int]
+    return _debug_lib
+
+
+def _load(path):
+    if not os.path.exists(path):
         raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                          "(or make -C gr-ltetrigger_b200)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+                          "(or make -C gr-ltetrigger_b200)" % path)
+    L = C.CDLL(path)
     vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)
     L.ltb_last_error.restype = C.c_char_p
     L.ltb_version.restype = C.c_char_p
@@ -104,13 +121,11 @@ def lib():
     L.ltb_table_fft1024_twiddles.argtypes = [fp, fp]
     L.ltb_table_os_filter.argtypes = [C.c_int, fp, fp]
     L.ltb_kernel_decimate_host.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp]
-    L.ltb_debug_set_flag.argtypes = [C.c_int, C.c_int]
     L.ltb_table_pss_taps.argtypes = [C.c_int, fp, fp]
     L.ltb_table_decim_taps.argtypes = [C.c_int, fp, C.c_int]
     L.ltb_table_sss.argtypes = [C.c_int, ip, ip, ip, ip, ip]
     L.ltb_table_cexp.argtypes = [fp, fp]
     L.ltb_table_fft128_twiddles.argtypes = [fp, fp]
-    _lib = L
     return L
 
 

@@ -240,7 +240,10 @@ class mib(_block):
                 "cp_len": "Normal" if cps[0].value else "Extended", "nof_prb": int(m.nof_prb),
                 "phich_len": "Normal" if m.phich_length == 0 else "Extended",
                 "nof_phich_resources": self.PHICH_RESOURCES[m.phich_resources],
-                "sfn_offset": int(m.sfn_offset), "tracking_start_time": int(time.time())}
+                # the reference passes &d_sfn_offset as the `sfn` argument of srslte_pbch_mib_unpack
+                # (lib/mib_impl.cc:167-172), which overwrites it with the MIB's 8-bit SFN field << 2
+                # before pack_cell runs: that, not the 0..3 scrambling phase, is what the message carries
+                "sfn_offset": int(m.sfn) & ~3, "tracking_start_time": int(time.time())}
             self._pub("track", self._current)
             self._published = True
             if self._exit_on_success:

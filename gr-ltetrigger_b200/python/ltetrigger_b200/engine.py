@@ -144,14 +144,15 @@ def kernel_pss_corr_fft(x, device=0):
     return p
 
 
-def kernel_decimate(x, decim, fmt=A.FMT_FC32, device=0):
+def kernel_decimate(x, decim, fmt=A.FMT_FC32, device=0, L=None):
+    """L: the library to call (default the release build; tests pass A.debug_lib())."""
     if fmt == A.FMT_FC32:
         x = np.ascontiguousarray(np.atleast_2d(x), np.complex64)
     else:
         x = np.ascontiguousarray(x, A.FMT_DTYPE[fmt])
     s, n = x.shape[0], x.shape[1]
     y = np.zeros((s, n // decim), np.complex64)
-    A.check(A.lib().ltb_kernel_decimate_host(device, x.ctypes.data, fmt, s, n, decim, y.ctypes.data),
+    A.check((L or A.lib()).ltb_kernel_decimate_host(device, x.ctypes.data, fmt, s, n, decim, y.ctypes.data),
             "ltb_kernel_decimate_host")
     return y
 

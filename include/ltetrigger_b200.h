@@ -141,8 +141,8 @@ LTB_API int ltb_trigger_destroy(ltb_trigger *t);
 /* back to the just-constructed state (new flowgraph run) */
 LTB_API int ltb_trigger_reset(ltb_trigger *t);
 /* downlink_trigger_c.set_psr_threshold (python/downlink_trigger_c.py:63-69) /
- * pss::set_psr_threshold (lib/pss_impl.h:98).  stream / n_id_2 = -1 selects all;
- * clamp != 0 applies the hier block's > 1.5 floor. */
+ * pss::set_psr_threshold (lib/pss_impl.h:98).  stream / n_id_2 = -1 selects all (other negative
+ * values are rejected); clamp != 0 applies the hier block's > 1.5 floor. */
 LTB_API int ltb_trigger_set_psr_threshold(ltb_trigger *t, int stream, int n_id_2, float thr, int clamp);
 
 /* Feed n_samples new input-rate samples per stream (a multiple of 8*decim) and run every
@@ -152,8 +152,8 @@ LTB_API int ltb_trigger_set_psr_threshold(ltb_trigger *t, int stream, int n_id_2
  * *_host takes host memory (pinned for full PCIe
  * rate) and copies it in; *_device takes device memory on cfg.device.  Records are
  * written to `recs` ordered by (stream, n_id_2, win_index); *n_recs is the count
- * (if it exceeds max_recs the call returns LTB_ERROR_INVALID_INPUTS after filling
- * max_recs).  Replaces one scheduler pass of general_work/work calls over the chunk
+ * (if it exceeds max_recs, collect returns LTB_ERROR_INVALID_INPUTS with the needed count in *n_recs and
+ * leaves the call pending: call ltb_trigger_collect again with a larger buffer).  Replaces one scheduler pass of general_work/work calls over the chunk
  * (lib/pss_impl.cc:154-223, lib/sss_impl.cc:83-156). */
 LTB_API int ltb_trigger_process_host(ltb_trigger *t, const void *iq, int64_t stream_stride_bytes,
                                      int64_t n_samples, ltb_window_rec *recs, int max_recs, int *n_recs);
@@ -232,9 +232,13 @@ LTB_API int ltb_kernel_pss_corr_fft_host(int device, const ltb_cf *x, int n_stre
 LTB_API int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in,
                                      int decim, ltb_cf *y);
 
-/* Profiling aid, never needed for results.  flag 0: decimator dissection (bit 0: skip the staging
- * copies, bit 1: skip the FMA body; outputs are garbage while set). */
+#ifdef LTB_DEBUG
+/* Only in the debug build (make -C gr-ltetrigger_b200 debug -> lib/libltetrigger_b200_debug.so, -DLTB_DEBUG);
+ * the release library does not export it.  Profiling / cross-check aid, never needed for results.
+ * flag 0: decimator dissection (bit 0: skip the staging copies, bit 1: skip the FMA body; outputs are
+ * garbage while set); flag 1: route the decimator through its general (bit 0) or tiled (bit 1) kernel. */
 LTB_API int ltb_debug_set_flag(int flag, int value);
+#endif
 
 /* ---- tables (host only; no GPU needed) -------------------------------------------------- */
 /* srslte_pss_init + srslte_pss_set_N_id_2: 128 conj time-domain taps (lib/pss_impl.cc:72-75) */

@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <deque>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -97,7 +98,18 @@ class pss : public block {
   float max_psr() const { return stats().max_psr; }
   float mean_psr() const { return stats().mean_psr; }
   float mean_cfo() const { return stats().mean_cfo; }
-  void set_psr_threshold(float threshold) { ltb_trigger_set_psr_threshold(d_ltb, 0, d_N_id_2, threshold, 0); }
+  // GNU Radio calls setters and getters from the GUI / Python thread while the scheduler thread is inside
+  // general_work; the C ABI wants one host thread per engine at a time, so every use of d_ltb takes d_mu
+  void set_psr_threshold(float threshold) {
+    std::lock_guard<std::mutex> lk(d_mu);
+    ltb_trigger_set_psr_threshold(d_ltb, 0, d_N_id_2, threshold, 0);
+  }
+  // How far the engine may run ahead of the scheduler, in general_work calls.  1 (default): the engine
+  // receives exactly what the next call needs (nitems_read + 18365 items), so set_psr_threshold applies to
+  // the next call and the accessors describe the call that just returned, as in the reference.  Larger
+  // values hand the engine up to that many windows per push (file playback at full rate): the accessors
+  // then describe up to n - 1 calls in the future and a new threshold applies that much later.
+  void set_lookahead_windows(int n) { d_lookahead_windows = n < 1 ? 1 : n; }
   float psr_threshold() const { return stats().psr_threshold; }
   float tracking_score() const { return stats().tracking_score; }
 
@@ -114,8 +126,13 @@ class pss : public block {
     const gr_complex *in = static_cast<const gr_complex *>(input_items[0]) + (history() - 1);
     gr_complex *out = static_cast<gr_complex *>(output_items[0]);
     const uint64_t avail_end = nitems_read(0) + (uint64_t)(ninput_items[0] - (int)(history() - 1));
-    while (avail_end > d_pushed + 7) {                   // hand new items to the engine, multiples of 8
-      int64_t n = (int64_t)((avail_end - d_pushed) / 8 * 8);
+    // hand the engine what the next d_lookahead_windows calls need (multiples of 8), no more: the first
+    // call needs nitems_read + LTB_LOOKAHEAD, every further one at most another 18365 - 960 items
+    uint64_t want_end = nitems_read(0) + (uint64_t)LTB_LOOKAHEAD + 7 +
+                        (uint64_t)(d_lookahead_windows - 1) * (uint64_t)(LTB_LOOKAHEAD - LTB_SLOT_LEN);
+    if (want_end > avail_end) want_end = avail_end;
+    while (d_ready.empty() && want_end > d_pushed + 7) {
+      int64_t n = (int64_t)((want_end - d_pushed) / 8 * 8);
       if (n > d_max_chunk) n = d_max_chunk;
       push(in + (d_pushed - nitems_read(0)), n);
     }
@@ -159,14 +176,16 @@ class pss : public block {
     set_output_multiple(half_frame_length);   // :82
   }
   ltb_pss_stats stats() const {
+    std::lock_guard<std::mutex> lk(d_mu);
     ltb_pss_stats s = ltb_pss_stats();
     ltb_trigger_get_stats(d_ltb, 0, d_N_id_2, &s);
     return s;
   }
   void push(const gr_complex *x, int64_t n) {
+    std::lock_guard<std::mutex> lk(d_mu);
     std::vector<ltb_window_rec> recs((size_t)(n / 8640 + 8));
     int n_recs = 0;
-    if (ltb_trigger_process_host(d_ltb, x, 0, n, recs.data(), (int)recs.size(), &n_recs))
+    if (ltb_trigger_process_host(d_ltb, x, (int64_t)(n * (int64_t)sizeof(gr_complex)), n, recs.data(), (int)recs.size(), &n_recs))
       throw std::runtime_error(std::string("pss: ") + ltb_last_error());
     std::vector<ltb_cf> hf((size_t)(n_recs > 0 ? n_recs : 1) * half_frame_length);
     int n_hf = 0;
@@ -185,6 +204,8 @@ class pss : public block {
 
   int d_N_id_2;
   ltb_trigger *d_ltb = nullptr;
+  mutable std::mutex d_mu;                                 // serialises every ltb_trigger_* call on d_ltb
+  int d_lookahead_windows = 1;
   int64_t d_max_chunk = 1 << 18;
   uint64_t d_pushed = 0;                                   // absolute count of items handed to the engine
   std::deque<std::pair<ltb_window_rec, std::vector<gr_complex> > > d_ready;   // calls already evaluated

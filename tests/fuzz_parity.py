@@ -26,15 +26,24 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--max-cases", type=int, default=100000)
     a = ap.parse_args()
+    n_cases, bad = campaign(a.seconds, a.seed, a.max_cases)
+    if bad is not None:
+        sys.exit(1)
+    print("fuzz_parity: %d cases bit-identical to the oracle" % n_cases)
+
+
+def campaign(seconds, seed, max_cases=100000, log=print):
+    """Run random cases for `seconds`; returns (cases run, None) or (cases run, (config, error)) at the
+    first mismatch.  tests/test_gpu_campaigns.py runs a 60 s campaign inside `pytest -m gpu`."""
     import ltetrigger_b200 as lt
     from ltetrigger_b200 import synth
     from oracle import oracle as O
     from conftest import assert_recs_equal
 
-    rng = np.random.default_rng(a.seed)
-    t_end = time.time() + a.seconds
+    rng = np.random.default_rng(seed)
+    t_end = time.time() + seconds
     n_cases = 0
-    while time.time() < t_end and n_cases < a.max_cases:
+    while time.time() < t_end and n_cases < max_cases:
         decim = int(rng.choice([1, 1, 2, 3, 4, 5, 6, 8, 8, 10, 12, 13, 15, 16, 16, 20]))
         fmt = int(rng.integers(0, 3))
         corr = int(rng.integers(0, 2))
@@ -74,13 +83,13 @@ def main():
         try:
             assert_recs_equal(got, want)
         except AssertionError as e:
-            print("MISMATCH", cfg, e, flush=True)
-            sys.exit(1)
+            log("MISMATCH %r %s" % (cfg, e))
+            return n_cases, (cfg, str(e))
         n_cases += 1
         cells = int(((got["flags"] & lt.F_CELL) != 0).sum())
-        print("ok %4d D=%-2d fmt=%d corr=%d tdd=%d S=%d thr=%.1f ta=%d te=%d chunk=%d recs=%d tagged=%d" % (
-            n_cases, decim, fmt, corr, tdd, n_streams, thr, track_after, track_every, chunk, len(got), cells), flush=True)
-    print("fuzz_parity: %d cases bit-identical to the oracle" % n_cases)
+        log("ok %4d D=%-2d fmt=%d corr=%d tdd=%d S=%d thr=%.1f ta=%d te=%d chunk=%d recs=%d tagged=%d" % (
+            n_cases, decim, fmt, corr, tdd, n_streams, thr, track_after, track_every, chunk, len(got), cells))
+    return n_cases, None
 
 
 if __name__ == "__main__":

@@ -13,6 +13,7 @@ from conftest import ROOT, has_gpu
 
 def header_symbols():
     text = open(os.path.join(ROOT, "include", "ltetrigger_b200.h")).read()
+    text = re.sub(r"#ifdef LTB_DEBUG.*?#endif", "", text, flags=re.S)        # debug-build-only declarations
     return sorted(set(re.findall(r"LTB_API\s+[\w\s\*]+?\b(ltb_\w+)\s*\(", text)))
 
 
@@ -26,6 +27,9 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert b"sm_100a" in L.ltb_version()
+    # the process-wide debug switch exists only in the -DLTB_DEBUG build, never in the release library
+    assert not hasattr(L, "ltb_debug_set_flag")
+    assert hasattr(_abi.debug_lib(), "ltb_debug_set_flag")
 
 
 def test_struct_layouts():

@@ -191,6 +191,13 @@ def test_cell_search_file_cli(lt, name, rate, capsys):
     cell = json.loads(results[0])
     assert cell["status"] == "FOUND" and cell["cell_id"] == cell_id and cell["nof_prb"] == NOF_PRB[name]
     assert cell["cp_len"] == "Normal" and cell["nof_tx_ports"] == 1
+    # --cut-off counts samples AFTER the resampler, as the reference's head block does
+    # (examples/cell_search_file.py:47-48, 69-77): 200 ms of search-rate samples find the cell at every
+    # rate; counted at the input rate they would be 200 ms / decim and find nothing at decim >= 4
+    res = cli.main(cli.parse([os.path.join(GOLDEN, "test_frames", fname), "-s", rate, "--repeat", "--cut-off", "384000"]))
+    assert json.loads(res[0])["status"] == "FOUND"
+    res = cli.main(cli.parse([os.path.join(GOLDEN, "test_frames", fname), "-s", rate, "--repeat", "--cut-off", "96000"]))
+    assert json.loads(res[0]) == {"status": "NOT_FOUND"}          # 50 ms: fewer than track_after windows
     # no cell: noise capture without --repeat runs to the end of the file
     noise = (np.random.default_rng(3).standard_normal((400000, 2)) * 0.3).astype(np.float32)
     path = os.path.join(str(os.environ.get("TMPDIR", "/tmp")), "ltb_noise_%d.fc32" % os.getpid())

@@ -89,25 +89,28 @@ def test_decimate_kernel_bit_exact(lt, oracle, decim, fmt):
 
 @pytest.mark.parametrize("decim", [2, 4, 8, 12, 15, 16])
 def test_general_decimator_agrees_with_tuned_kernels(lt, oracle, decim):
-    """Debug flag 1 routes every rate through decimate_any_kernel: three independent kernels and
-    the oracle give the same bits."""
+    """Debug flag 1 (debug build of the library only: lib/libltetrigger_b200_debug.so) routes every rate
+    through decimate_any_kernel: three independent kernels and the oracle give the same bits."""
+    from ltetrigger_b200 import _abi as A
+    D = A.debug_lib()
+    assert not hasattr(lt.lib(), "no_such") and "ltb_debug_set_flag" not in A.SYMBOLS
     rng = np.random.default_rng(decim)
     x, want = _decim_case(oracle, rng, decim, 0, 777 * decim)
     tuned = lt.kernel_decimate(x, decim, 0)
-    lt.lib().ltb_debug_set_flag(1, 1)
+    D.ltb_debug_set_flag(1, 1)
     try:
-        general = lt.kernel_decimate(x, decim, 0)
+        general = lt.kernel_decimate(x, decim, 0, L=D)
     finally:
-        lt.lib().ltb_debug_set_flag(1, 0)
+        D.ltb_debug_set_flag(1, 0)
     for s in range(2):
         assert np.array_equal(general[s].view(np.uint32), want[s].view(np.uint32))
         assert np.array_equal(tuned[s].view(np.uint32), want[s].view(np.uint32))
     if decim in (4, 8, 12, 15):              # these rates also have the tiled kernel (flag bit 1)
-        lt.lib().ltb_debug_set_flag(1, 2)
+        D.ltb_debug_set_flag(1, 2)
         try:
-            tiled = lt.kernel_decimate(x, decim, 0)
+            tiled = lt.kernel_decimate(x, decim, 0, L=D)
         finally:
-            lt.lib().ltb_debug_set_flag(1, 0)
+            D.ltb_debug_set_flag(1, 0)
         for s in range(2):
             assert np.array_equal(tiled[s].view(np.uint32), want[s].view(np.uint32))
 

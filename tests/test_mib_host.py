@@ -113,6 +113,10 @@ def test_mib_on_synthetic_cells_one_and_two_ports(oracle, n_ports, nof_prb, deci
     cell = tracked[0]
     assert (cell["cell_id"], cell["nof_prb"], cell["nof_tx_ports"]) == (cell_id, nof_prb, n_ports)
     assert cell["cp_len"] == ("Extended" if ext_cp else "Normal") and cell["nof_phich_resources"] == "1/2"
+    # "sfn_offset" is what the reference publishes under that key: the MIB's 8-bit SFN field << 2
+    # (lib/mib_impl.cc:167-172 hands &d_sfn_offset to srslte_pbch_mib_unpack as its sfn output).  The
+    # capture tiles four frames with SFN 4..7 (synth.capture), so the field is 1 and the value 4.
+    assert cell["sfn_offset"] == 4, cell["sfn_offset"]
 
 
 def test_mib_decode_rejects_noise_sf5_and_bad_arguments():
