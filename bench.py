@@ -63,6 +63,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-formats", action="store_true", help="skip the e2e legs on the other wire formats")
+    ap.add_argument("--frontend", default="fp32", choices=["fp32", "tc"],
+                    help="fp32: canonical FFMA2 decimator; tc: exact-integer tensor-core front end (sc16, D=16)")
+    ap.add_argument("--pipeline", default="overlap", choices=["overlap", "serial"],
+                    help="overlap: track+SSS of call i under the front end of call i+1 (two streams); serial: one stream")
     ap.add_argument("--no-spot-check", action="store_true", help="skip the per-rank oracle check after timing")
     ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the extra sustained run (0: skip)")
     return ap.parse_args()
@@ -251,8 +255,13 @@ def main():
     stream = torch.cuda.current_stream()
     corr_mode = lt.CORR_FFT if a.corr == "fft" else lt.CORR_DIRECT
     frontend_kw, oracle_front_flag = {}, 0
+    if a.frontend == "tc":
+        from oracle import oracle as O_
+        frontend_kw, oracle_front_flag = {"frontend_mode": lt.FRONTEND_TC_INT}, O_.FRONT_TCINT
+    pipeline = lt.PIPE_OVERLAP if a.pipeline == "overlap" else lt.PIPE_SERIAL
     trig = lt.Trigger(n_streams=a.streams, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
-                      record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode)
+                      record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode,
+                      pipeline=pipeline, **frontend_kw)
     ptr, stride = d_in.data_ptr(), n * bps
 
     def step():
@@ -333,6 +342,8 @@ def main():
                 "frac": alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 6535.7e9, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"},
         "peak_source": "measured FFMA peak, tools/ubench_fp32.cu (profiles/ubench_fp32_r01.jsonl); MEASURED_PEAKS.json has no fp32 figure",
         "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
+        "stages_overlap": a.pipeline == "overlap",      # track + sss of call i run under the front end of call i+1:
+                                                        # the stage times then sum to more than ms_per_step
         "path_frac_of_fp32": f_alg * per_gpu_rate / (FP32_PEAK_TFLOPS * 1e12),
         "path_frac_of_fp32_executed": f_exec * per_gpu_rate / (FP32_PEAK_TFLOPS * 1e12),
         "flop_per_input_sample": {"algorithmic_direct_form": f_alg, "executed": f_exec},
@@ -345,7 +356,7 @@ def main():
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "streams_per_gpu": a.streams, "decim": a.decim,
-                   "format": a.format, "correlator": a.corr, "segment_ms": a.segment_ms, "snr_db": a.snr_db,
+                   "format": a.format, "frontend": a.frontend, "correlator": a.corr, "pipeline": a.pipeline, "segment_ms": a.segment_ms, "snr_db": a.snr_db,
                    "l2": "inputs larger than L2 (%.1f GB per step)" % (a.streams * n * bps / 1e9),
                    "input": "%d seeded synthetic LTE captures tiled over the streams with per-stream timing shift + AWGN" % a.unique,
                    "cells_tagged_per_step": n_cells / a.steps},
@@ -435,7 +446,8 @@ def main():
             torch.cuda.synchronize()
             b = FMT_BYTES[name]
             trig2 = lt.Trigger(n_streams=se, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmts[name],
-                               record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode)
+                               record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode,
+                               pipeline=pipeline, **(frontend_kw if name == a.format else {}))
             hptr, hstride = host.data_ptr(), n * b
             for _ in range(3):                                      # warm-up: allocates both staging buffers,
                 trig2.submit_host_ptr(hptr, hstride, n)             # touches every pinned page

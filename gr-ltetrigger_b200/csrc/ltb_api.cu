@@ -6,6 +6,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -14,6 +15,7 @@
 #include "../../include/ltetrigger_b200.h"
 #include "ltb_kernels.cuh"
 #include "ltb_tables.h"
+#include "ltb_tc_frontend.cuh"
 
 using namespace ltb;
 
@@ -304,6 +306,91 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
   return LTB_SUCCESS;
 }
 
+// ---- LTB_FRONTEND_TC_INT: integer tensor-core front end (sc16, decim 16) ----------------------------------
+#ifndef LTB_TC_G
+#define LTB_TC_G 1            // k-steps per accumulator column offset (ltb_tc_frontend.cuh); LTB_TC_G env overrides
+#endif
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+int g_tc_g = 0;
+int8_t *g_tc_btab[64] = {nullptr};
+long long g_tc_sum_t = 0;
+
+int tc_group() {
+  if (g_tc_g) return g_tc_g;
+  int g = LTB_TC_G;
+  if (const char *e = std::getenv("LTB_TC_G")) g = std::atoi(e);
+  if (g != 1 && g != 2 && g != 4 && g != 8) g = LTB_TC_G;
+  g_tc_g = g;
+  return g;
+}
+
+int ensure_tc_tables(int device) {
+  std::lock_guard<std::mutex> lk(g_const_mu);
+  if (g_tc_btab[device]) return LTB_SUCCESS;
+  if (!g_encode_tiled) {
+    cudaDriverEntryPointQueryResult qres;
+    void *fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return fail(LTB_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+    g_encode_tiled = (EncodeTiledFn)fn;
+  }
+  const int G = tc_group();
+  const std::vector<int8_t> tab = make_tc_btab(G);
+  make_tc_taps(&g_tc_sum_t);
+  if (tab.empty()) return fail(LTB_ERROR, "decimator taps do not fit three base-256 digits");
+  int8_t *d = nullptr;
+  LTB_CUDA(cudaMalloc(&d, tab.size()));
+  LTB_CUDA(cudaMemcpy(d, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(1)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(2)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(4)));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(8)));
+  g_tc_btab[device] = d;
+  return LTB_SUCCESS;
+}
+
+// n_in new sc16 samples per stream (multiple of 128) -> n_in / 16 search-rate samples in y_ring; tail_old holds the
+// 768 samples before the chunk, tail_new receives the last 768 for the next call
+int launch_frontend_tc(int device, const void *d_iq, long long stride, int n_streams, int n_in, const short2 *tail_old,
+                       short2 *tail_new, float2 *y_ring, long long n_base, unsigned mask, int cap, int *d_err,
+                       cudaStream_t st, int *launches) {
+  if ((reinterpret_cast<uintptr_t>(d_iq) | (uintptr_t)stride) & 15u)
+    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT needs a 16-byte aligned input pointer and row stride (TMA)");
+  const int full_rows = n_in / kTcRowSamples;
+  CUtensorMap map;
+  const cuuint64_t gdim[3] = {1024, (cuuint64_t)(full_rows > 0 ? full_rows : 1), (cuuint64_t)n_streams};
+  const cuuint64_t gstr[2] = {1024, (cuuint64_t)stride};
+  const cuuint32_t box[3] = {256, (cuuint32_t)kTcTileRows, 1}, estr[3] = {1, 1, 1};
+  if (n_streams > 1 && stride < (long long)n_in * 4) return fail(LTB_ERROR_INVALID_INPUTS, "row stride smaller than a row");
+  const CUresult r = g_encode_tiled(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(d_iq), gdim, gstr, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LTB_ERROR, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  TcParams P;
+  P.in = d_iq; P.stride_bytes = stride; P.n_in = n_in; P.n_streams = n_streams; P.tail = tail_old; P.y_ring = y_ring;
+  P.n_base = n_base; P.cap_mask = mask; P.cap = cap;
+  const int rows = (n_in + kTcRowSamples - 1) / kTcRowSamples;
+  P.tiles_per_stream = (rows + kTcUseful - 1) / kTcUseful;
+  const long long total = (long long)P.tiles_per_stream * n_streams;
+  if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator tiles in one call");
+  P.total_tiles = (int)total;
+  P.btab = g_tc_btab[device]; P.c_const = 128 * g_tc_sum_t; P.err = d_err;
+  const int sms = g_sm_count[device] > 0 ? g_sm_count[device] : 148;
+  const int grid = P.total_tiles < sms ? P.total_tiles : sms;
+  switch (tc_group()) {
+    case 1: decimate_tc_kernel<1><<<grid, kTcThreads, tc_smem_bytes(1), st>>>(map, P); break;
+    case 2: decimate_tc_kernel<2><<<grid, kTcThreads, tc_smem_bytes(2), st>>>(map, P); break;
+    case 4: decimate_tc_kernel<4><<<grid, kTcThreads, tc_smem_bytes(4), st>>>(map, P); break;
+    default: decimate_tc_kernel<8><<<grid, kTcThreads, tc_smem_bytes(8), st>>>(map, P); break;
+  }
+  tc_tail_kernel<<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);
+  *launches += 2;
+  return LTB_SUCCESS;
+}
+
 // format dispatch
 int launch_frontend_fmt(int fmt, int decim, const void *d_iq, long long stride, int n_streams, int m, float2 *tail_old,
                         float2 *tail_new, const float *branch_taps, float2 *y_ring, long long n_base, unsigned mask,
@@ -325,13 +412,22 @@ struct ltb_trigger {
   ltb_trigger_config cfg;
   int n_chains = 0, cap = 0, max_m = 0, w_cap = 0, w_cur = 0;
   unsigned cap_mask = 0;
+  // Two launch streams.  `stream` (highest priority) carries the stateless part of a call -- front end and
+  // all-lag correlator; `track_stream` (lowest priority) the per-chain sequential part -- chain order, track
+  // kernel, SSS.  With two calls in flight the track kernel of call i runs while the front end of call i+1
+  // does: the front end's CTAs are placed first (priority) and leave registers for one track CTA per SM,
+  // which fills issue slots the FFMA2-bound decimator cannot use.  LTB_PIPE_SERIAL puts both on one stream.
   cudaStream_t stream = nullptr;
-  bool own_stream = false;
+  cudaStream_t track_stream = nullptr;
+  cudaStream_t user_stream = nullptr;     // cfg.cuda_stream: the front end of a call waits for work queued there
+  bool overlap = false;
   // up to two submitted-but-not-collected calls: the host enqueues call i+1 while the records
   // of call i are still in flight, so the stream never idles between calls
   struct Slot {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, done = nullptr;
     cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};   // after front end, corr, track, sss
+    cudaEvent_t ev_b0 = nullptr;          // track stream reaches this call (after waiting for its correlator)
+    cudaEvent_t ev_user = nullptr;        // recorded on cfg.cuda_stream at submit
     ltb_window_rec *h_recs = nullptr;     // pinned
     int *h_rec_count = nullptr;           // pinned
     ltb_window_rec *d_recs = nullptr;     // this call's records on the device
@@ -359,6 +455,8 @@ struct ltb_trigger {
   float2 *d_hf = nullptr;
   float2 *d_tail[2] = {nullptr, nullptr};
   int tail_cur = 0;
+  short2 *d_tc_tail[2] = {nullptr, nullptr};   // LTB_FRONTEND_TC_INT: raw history, [n_streams][768]
+  int *d_tc_err = nullptr;
   float2 *d_cexp = nullptr;
   float *d_branch_taps = nullptr;         // [decim][33], decimate_any_kernel
   long long n_total = 0;
@@ -378,8 +476,14 @@ int trigger_zero_state(ltb_trigger *t) {
   LTB_CUDA(cudaMemsetAsync(t->d_avg, 0, sizeof(float) * (size_t)t->n_chains * kAvgLen, t->stream));
   LTB_CUDA(cudaMemsetAsync(t->d_tail[0], 0, sizeof(float2) * (size_t)S * kTailCap, t->stream));
   LTB_CUDA(cudaMemsetAsync(t->d_tail[1], 0, sizeof(float2) * (size_t)S * kTailCap, t->stream));
+  if (t->d_tc_tail[0]) {
+    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[0], 0, sizeof(short2) * (size_t)S * kTcTailSamples, t->stream));
+    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[1], 0, sizeof(short2) * (size_t)S * kTcTailSamples, t->stream));
+    LTB_CUDA(cudaMemsetAsync(t->d_tc_err, 0, sizeof(int), t->stream));
+  }
   LTB_CUDA(cudaMemcpyAsync(t->d_thr, t->h_thr.data(), sizeof(float) * t->n_chains, cudaMemcpyHostToDevice, t->stream));
   LTB_CUDA(cudaStreamSynchronize(t->stream));
+  LTB_CUDA(cudaStreamSynchronize(t->track_stream));
   t->n_total = 0;
   t->os_blocks_done = 0;
   t->tail_cur = 0;
@@ -394,6 +498,7 @@ void trigger_free(ltb_trigger *t) {
   cudaFree(t->d_thr); cudaFree(t->d_sss_sym);
   cudaFree(t->d_sss_rec); cudaFree(t->d_sss_count); cudaFree(t->d_chain_order); cudaFree(t->d_hf); cudaFree(t->d_tail[0]);
   cudaFree(t->d_tail[1]); cudaFree(t->d_cexp); cudaFree(t->d_branch_taps);
+  cudaFree(t->d_tc_tail[0]); cudaFree(t->d_tc_tail[1]); cudaFree(t->d_tc_err);
   for (auto &sl : t->slot) {
     cudaFree(sl.d_recs); cudaFree(sl.d_rec_count);
     if (sl.h_recs) cudaFreeHost(sl.h_recs);
@@ -402,11 +507,14 @@ void trigger_free(ltb_trigger *t) {
     if (sl.ev1) cudaEventDestroy(sl.ev1);
     if (sl.done) cudaEventDestroy(sl.done);
     for (int i = 0; i < 4; ++i) if (sl.ev_k[i]) cudaEventDestroy(sl.ev_k[i]);
+    if (sl.ev_b0) cudaEventDestroy(sl.ev_b0);
+    if (sl.ev_user) cudaEventDestroy(sl.ev_user);
   }
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->in_stream) cudaStreamDestroy(t->in_stream);
   for (auto &e : t->in_ready) if (e) cudaEventDestroy(e);
-  if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
+  if (t->track_stream && t->track_stream != t->stream) cudaStreamDestroy(t->track_stream);
+  if (t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
 
@@ -421,9 +529,18 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   const int S = c.n_streams;
   const long long n_base = t->n_total;
   int launches = 0;
+  if (t->user_stream) {                    // inputs produced on the caller's stream are ordered before our reads
+    LTB_CUDA(cudaEventRecord(sl.ev_user, t->user_stream));
+    LTB_CUDA(cudaStreamWaitEvent(t->stream, sl.ev_user, 0));
+  }
   LTB_CUDA(cudaEventRecord(sl.ev0, t->stream));
-  int rc = launch_frontend_fmt(c.input_format, c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
-                               t->d_branch_taps, t->d_y, n_base, t->cap_mask, t->cap, t->stream, &launches);
+  int rc;
+  if (c.frontend_mode == LTB_FRONTEND_TC_INT)
+    rc = launch_frontend_tc(c.device, d_iq, stride, S, (int)n_samples, t->d_tc_tail[t->tail_cur], t->d_tc_tail[t->tail_cur ^ 1],
+                            t->d_y, n_base, t->cap_mask, t->cap, t->d_tc_err, t->stream, &launches);
+  else
+    rc = launch_frontend_fmt(c.input_format, c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
+                             t->d_branch_taps, t->d_y, n_base, t->cap_mask, t->cap, t->stream, &launches);
   if (rc) return rc;
   if (c.decim > 1) t->tail_cur ^= 1;
   LTB_CUDA(cudaEventRecord(sl.ev_k[0], t->stream));
@@ -447,8 +564,12 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   t->n_total += m;
   t->w_cur = m / (kHalf - kSlot) + 4;
   if (t->w_cur > t->w_cap) t->w_cur = t->w_cap;
-  LTB_CUDA(cudaMemsetAsync(t->d_sss_count, 0, 4 * sizeof(int), t->stream));
-  chain_order_kernel<<<(t->n_chains + 255) / 256, 256, 0, t->stream>>>(t->d_state, t->n_chains, t->d_chain_order, t->d_sss_count + 2);
+  // ---- the sequential part, on the track stream: it needs this call's correlator, nothing of the next call ----
+  cudaStream_t ts = t->track_stream;
+  if (ts != t->stream) LTB_CUDA(cudaStreamWaitEvent(ts, sl.ev_k[1], 0));
+  LTB_CUDA(cudaEventRecord(sl.ev_b0, ts));
+  LTB_CUDA(cudaMemsetAsync(t->d_sss_count, 0, 4 * sizeof(int), ts));
+  chain_order_kernel<<<(t->n_chains + 255) / 256, 256, 0, ts>>>(t->d_state, t->n_chains, t->d_chain_order, t->d_sss_count + 2);
   launches++;
   TrackParams P;
   P.y_ring = t->d_y; P.p_ring = t->d_p; P.state = t->d_state; P.avg = t->d_avg; P.thr = t->d_thr;
@@ -463,15 +584,15 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   {
     int ctas = 4 * (g_sm_count[c.device] > 0 ? g_sm_count[c.device] : 148);
     if (ctas > t->n_chains) ctas = t->n_chains;
-    pss_track_kernel<<<ctas, kTrackThreads, sizeof(TrackShared), t->stream>>>(P);
+    pss_track_kernel<<<ctas, kTrackThreads, sizeof(TrackShared), ts>>>(P);
   }
   launches++;
-  LTB_CUDA(cudaEventRecord(sl.ev_k[2], t->stream));
+  LTB_CUDA(cudaEventRecord(sl.ev_k[2], ts));
   int sss_grid = (t->n_chains * t->w_cur + kSssWarps - 1) / kSssWarps;
   if (sss_grid > 148 * 8) sss_grid = 148 * 8;
-  sss_kernel<<<sss_grid, kSssWarps * 32, 0, t->stream>>>(t->d_sss_sym, t->d_sss_rec, t->d_sss_count, t->sss_cap, sl.d_recs);
+  sss_kernel<<<sss_grid, kSssWarps * 32, 0, ts>>>(t->d_sss_sym, t->d_sss_rec, t->d_sss_count, t->sss_cap, sl.d_recs);
   launches++;
-  LTB_CUDA(cudaEventRecord(sl.ev1, t->stream));
+  LTB_CUDA(cudaEventRecord(sl.ev1, ts));
   // read the records back on the copy stream: the next call's kernels need not wait for it
   LTB_CUDA(cudaStreamWaitEvent(t->copy_stream, sl.ev1, 0));
   LTB_CUDA(cudaMemcpyAsync(sl.h_rec_count, sl.d_rec_count, sizeof(int) * t->n_chains, cudaMemcpyDeviceToHost, t->copy_stream));
@@ -501,7 +622,7 @@ int ltb_device_count(void) {
 int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   // ABI evolution: a caller built against the header before corr_mode was appended passes the
   // shorter size and gets the defaults of the fields it does not know
-  constexpr size_t kMinConfig = offsetof(ltb_trigger_config, corr_mode);
+  constexpr size_t kMinConfig = offsetof(ltb_trigger_config, corr_mode);   // later fields default to 0
   if (!cfg || !out || cfg->struct_size < kMinConfig || cfg->struct_size > sizeof(ltb_trigger_config))
     return fail(LTB_ERROR_INVALID_INPUTS, "bad config pointer or struct_size");
   *out = nullptr;
@@ -510,8 +631,12 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   c.struct_size = sizeof c;
   if (c.n_streams <= 0 || !valid_decim(c.decim) || !valid_format(c.input_format) ||
       c.max_chunk <= 0 || (c.root_mask & ~7) || (c.corr_mode != LTB_CORR_DIRECT && c.corr_mode != LTB_CORR_FFT) ||
-      (c.frame_type != LTB_FRAME_FDD && c.frame_type != LTB_FRAME_TDD))
+      (c.frame_type != LTB_FRAME_FDD && c.frame_type != LTB_FRAME_TDD) ||
+      (c.pipeline != LTB_PIPE_OVERLAP && c.pipeline != LTB_PIPE_SERIAL) ||
+      (c.frontend_mode != LTB_FRONTEND_FP32 && c.frontend_mode != LTB_FRONTEND_TC_INT))
     return fail(LTB_ERROR_INVALID_INPUTS, "invalid trigger configuration");
+  if (c.frontend_mode == LTB_FRONTEND_TC_INT && (c.input_format != LTB_FMT_SC16 || c.decim != 16))
+    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT is available for sc16 input at decim = 16");
   if (c.root_mask == 0) c.root_mask = 7;
   if (c.track_after <= 0) c.track_after = 16;
   if (c.track_every <= 0) c.track_every = 8;
@@ -521,6 +646,7 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   LTB_CUDA(cudaSetDevice(c.device));
   int rc = ensure_constants(c.device);
   if (!rc && c.corr_mode == LTB_CORR_FFT) rc = ensure_os_tables(c.device);
+  if (!rc && c.frontend_mode == LTB_FRONTEND_TC_INT) rc = ensure_tc_tables(c.device);
   if (rc) return rc;
 
   ltb_trigger *t = new ltb_trigger();
@@ -528,7 +654,11 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   const int S = c.n_streams;
   t->n_chains = S * 3;
   t->max_m = (int)(c.max_chunk / c.decim);
-  t->cap = next_pow2((long long)t->max_m + kLookahead + kSlot + 256);
+  t->overlap = c.pipeline == LTB_PIPE_OVERLAP && !c.keep_halfframes;
+  // the rings are indexed by absolute sample number.  One call in flight: the chunk being written plus what the
+  // oldest unfinished window still reads.  Overlapped: the front end of call i+1 writes while the track kernel
+  // of call i reads back to its chains' oldest window (about one chunk + a look-ahead + a half-frame behind).
+  t->cap = next_pow2((long long)t->max_m * (t->overlap ? 2 : 1) + kLookahead + (t->overlap ? 2 * kHalf : 0) + kSlot + 256);
   t->cap_mask = (unsigned)(t->cap - 1);
   t->w_cap = t->max_m / (kHalf - kSlot) + 4;
   t->sss_cap = t->n_chains * t->w_cap;
@@ -541,9 +671,17 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
       return fail(LTB_ERROR, std::string(#call) + ": " + cudaGetErrorString(e__));          \
     }                                                                                      \
   } while (0)
-  if (c.cuda_stream) t->stream = (cudaStream_t)c.cuda_stream;
-  else { LTB_CUDA_T(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking)); t->own_stream = true; }
+  {
+    int prio_least = 0, prio_greatest = 0;
+    LTB_CUDA_T(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    t->user_stream = (cudaStream_t)c.cuda_stream;
+    LTB_CUDA_T(cudaStreamCreateWithPriority(&t->stream, cudaStreamNonBlocking, prio_greatest));
+    if (t->overlap) LTB_CUDA_T(cudaStreamCreateWithPriority(&t->track_stream, cudaStreamNonBlocking, prio_least));
+    else t->track_stream = t->stream;
+  }
   for (auto &sl : t->slot) {
+    LTB_CUDA_T(cudaEventCreate(&sl.ev_b0));
+    LTB_CUDA_T(cudaEventCreateWithFlags(&sl.ev_user, cudaEventDisableTiming));
     LTB_CUDA_T(cudaEventCreate(&sl.ev0));
     LTB_CUDA_T(cudaEventCreate(&sl.ev1));
     LTB_CUDA_T(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
@@ -568,6 +706,11 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   LTB_CUDA_T(cudaMalloc(&t->d_chain_order, sizeof(int) * t->n_chains));
   LTB_CUDA_T(cudaMalloc(&t->d_tail[0], sizeof(float2) * (size_t)S * kTailCap));
   LTB_CUDA_T(cudaMalloc(&t->d_tail[1], sizeof(float2) * (size_t)S * kTailCap));
+  if (c.frontend_mode == LTB_FRONTEND_TC_INT) {
+    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[0], sizeof(short2) * (size_t)S * kTcTailSamples));
+    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[1], sizeof(short2) * (size_t)S * kTcTailSamples));
+    LTB_CUDA_T(cudaMalloc(&t->d_tc_err, sizeof(int)));
+  }
   if (c.keep_halfframes) LTB_CUDA_T(cudaMalloc(&t->d_hf, sizeof(float2) * kHalf * (size_t)t->n_chains * t->w_cap));
   for (auto &sl : t->slot) {
     LTB_CUDA_T(cudaMallocHost(&sl.h_recs, sizeof(ltb_window_rec) * (size_t)t->n_chains * t->w_cap));
@@ -587,6 +730,7 @@ int ltb_trigger_destroy(ltb_trigger *t) {
   cudaSetDevice(t->cfg.device);
   if (t->in_stream) cudaStreamSynchronize(t->in_stream);
   cudaStreamSynchronize(t->stream);
+  if (t->track_stream) cudaStreamSynchronize(t->track_stream);
   if (t->copy_stream) cudaStreamSynchronize(t->copy_stream);
   trigger_free(t);
   return LTB_SUCCESS;
@@ -597,6 +741,7 @@ int ltb_trigger_reset(ltb_trigger *t) {
   LTB_CUDA(cudaSetDevice(t->cfg.device));
   LTB_CUDA(cudaStreamSynchronize(t->in_stream));
   LTB_CUDA(cudaStreamSynchronize(t->stream));
+  LTB_CUDA(cudaStreamSynchronize(t->track_stream));
   LTB_CUDA(cudaStreamSynchronize(t->copy_stream));
   return trigger_zero_state(t);
 }
@@ -609,8 +754,10 @@ int ltb_trigger_set_psr_threshold(ltb_trigger *t, int stream, int n_id_2, float 
     for (int r = 0; r < 3; ++r)
       if ((stream < 0 || stream == s) && (n_id_2 < 0 || n_id_2 == r)) t->h_thr[s * 3 + r] = thr;
   LTB_CUDA(cudaSetDevice(t->cfg.device));
-  LTB_CUDA(cudaMemcpyAsync(t->d_thr, t->h_thr.data(), sizeof(float) * t->n_chains, cudaMemcpyHostToDevice, t->stream));
+  // the track kernel reads d_thr: the new value applies to the calls submitted after this returns
   LTB_CUDA(cudaStreamSynchronize(t->stream));
+  LTB_CUDA(cudaMemcpyAsync(t->d_thr, t->h_thr.data(), sizeof(float) * t->n_chains, cudaMemcpyHostToDevice, t->track_stream));
+  LTB_CUDA(cudaStreamSynchronize(t->track_stream));
   return LTB_SUCCESS;
 }
 
@@ -639,7 +786,7 @@ int ltb_trigger_collect(ltb_trigger *t, ltb_window_rec *recs, int max_recs, int 
   cudaEventElapsedTime(&t->last_ms, sl.ev0, sl.ev1);
   cudaEventElapsedTime(&t->last_kernel_ms[0], sl.ev0, sl.ev_k[0]);
   cudaEventElapsedTime(&t->last_kernel_ms[1], sl.ev_k[0], sl.ev_k[1]);
-  cudaEventElapsedTime(&t->last_kernel_ms[2], sl.ev_k[1], sl.ev_k[2]);
+  cudaEventElapsedTime(&t->last_kernel_ms[2], sl.ev_b0, sl.ev_k[2]);
   cudaEventElapsedTime(&t->last_kernel_ms[3], sl.ev_k[2], sl.ev1);
   int written = 0;
   for (int ch = 0; ch < t->n_chains; ++ch) {
@@ -694,8 +841,9 @@ int ltb_trigger_get_stats(ltb_trigger *t, int stream, int n_id_2, ltb_pss_stats 
     return fail(LTB_ERROR_INVALID_INPUTS, "bad chain selector");
   LTB_CUDA(cudaSetDevice(t->cfg.device));
   ChainState st;
-  LTB_CUDA(cudaMemcpyAsync(&st, t->d_state + (stream * 3 + n_id_2), sizeof st, cudaMemcpyDeviceToHost, t->stream));
   LTB_CUDA(cudaStreamSynchronize(t->stream));
+  LTB_CUDA(cudaMemcpyAsync(&st, t->d_state + (stream * 3 + n_id_2), sizeof st, cudaMemcpyDeviceToHost, t->track_stream));
+  LTB_CUDA(cudaStreamSynchronize(t->track_stream));
   auto mean = [](const float *d, unsigned n) -> float {      // compute_moving_avg, lib/pss_impl.cc:94-109
     if (!n) return 0.0f;
     if (n > (unsigned)kMavg) n = kMavg;
@@ -910,6 +1058,42 @@ int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, 
   if (e == cudaSuccess) e = cudaMemcpy2D(y, sizeof(float2) * (size_t)m, d_y, sizeof(float2) * (size_t)cap, sizeof(float2) * (size_t)m, n_streams, cudaMemcpyDeviceToHost);
   cudaFree(d_in); cudaFree(d_y); cudaFree(d_t0); cudaFree(d_t1); cudaFree(d_bt);
   if (e != cudaSuccess) return fail(LTB_ERROR, std::string("ltb_kernel_decimate_host: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int ltb_kernel_decimate_tc_host(int device, const int16_t *x, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y) {
+  if (!x || !y || n_streams <= 0 || n_in <= 0 || (n_in % 128) != 0 || chunk <= 0 || (chunk % 128) != 0)
+    return fail(LTB_ERROR_INVALID_INPUTS, "n_in and chunk must be positive multiples of 128");
+  if (ltb_device_count() <= device || device < 0) return fail(LTB_ERROR, "no such CUDA device");
+  LTB_CUDA(cudaSetDevice(device));
+  int rc = ensure_constants(device);
+  if (!rc) rc = ensure_tc_tables(device);
+  if (rc) return rc;
+  const int m = (int)(n_in / 16);
+  const int cap = next_pow2(m + 8);
+  const size_t in_row = (size_t)n_in * 4, dev_row = (in_row + 127) / 128 * 128;
+  void *d_in = nullptr; float2 *d_y = nullptr; short2 *d_t[2] = {nullptr, nullptr}; int *d_err = nullptr;
+  cudaError_t e = cudaMalloc(&d_in, dev_row * n_streams);
+  if (e == cudaSuccess) e = cudaMalloc(&d_y, sizeof(float2) * (size_t)n_streams * cap);
+  if (e == cudaSuccess) e = cudaMalloc(&d_t[0], sizeof(short2) * (size_t)n_streams * kTcTailSamples);
+  if (e == cudaSuccess) e = cudaMalloc(&d_t[1], sizeof(short2) * (size_t)n_streams * kTcTailSamples);
+  if (e == cudaSuccess) e = cudaMalloc(&d_err, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(d_err, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(d_t[0], 0, sizeof(short2) * (size_t)n_streams * kTcTailSamples);
+  if (e == cudaSuccess) e = cudaMemcpy2D(d_in, dev_row, x, in_row, in_row, n_streams, cudaMemcpyHostToDevice);
+  int cur = 0;
+  for (int64_t c0 = 0; c0 < n_in && e == cudaSuccess && !rc; c0 += chunk) {
+    const int nc = (int)(n_in - c0 < chunk ? n_in - c0 : chunk);
+    int launches = 0;
+    rc = launch_frontend_tc(device, (const char *)d_in + c0 * 4, (long long)dev_row, n_streams, nc, d_t[cur], d_t[cur ^ 1], d_y,
+                            c0 / 16, (unsigned)(cap - 1), cap, d_err, 0, &launches);
+    cur ^= 1;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy2D(y, sizeof(float2) * (size_t)m, d_y, sizeof(float2) * (size_t)cap, sizeof(float2) * (size_t)m, n_streams, cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_y); cudaFree(d_t[0]); cudaFree(d_t[1]); cudaFree(d_err);
+  if (e != cudaSuccess) return fail(LTB_ERROR, std::string("ltb_kernel_decimate_tc_host: ") + cudaGetErrorString(e));
   return rc;
 }
 

@@ -439,8 +439,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
                "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// LTB_STREAM_MAXNREG (build option): cap the kernel at that many registers instead of the launch-bounds
+// allocation (108 used).  At 96 two CTAs leave room for one track-kernel CTA per SM under the overlapped
+// pipeline; measured, the cap costs this kernel 2 % and the co-resident track kernel takes the issue slots
+// it needs from this one anyway (5.19 ms per step against 5.08 ms uncapped), so it is off by default.
 template <int FMT>
+#ifdef LTB_STREAM_MAXNREG
+__global__ void __maxnreg__(LTB_STREAM_MAXNREG)
+#else
 __global__ void __launch_bounds__(kStrThreads, 2)
+#endif
 decimate_stream_kernel(const void *__restrict__ in, long long stride_bytes, int n_out, const float2 *__restrict__ tail_in,
                        float2 *__restrict__ y_ring, long long n_base, unsigned cap_mask, int cap, int segs_per_stream,
                        int total_segs, int dbg) {

@@ -125,6 +125,48 @@ std::vector<float> make_decim_branch_taps(int decim) {
   return out;
 }
 
+std::vector<int32_t> make_tc_taps(long long *sum_t) {
+  const std::vector<float> taps = make_decim_taps(16);
+  std::vector<int32_t> T(taps.size());
+  long long sum = 0;
+  for (size_t j = 0; j < taps.size(); ++j) {
+    T[j] = (int32_t)std::llrint((double)taps[j] * 134217728.0);     // 2^27
+    sum += T[j];
+  }
+  if (sum_t) *sum_t = sum;
+  return T;
+}
+
+std::vector<int8_t> make_tc_btab(int G) {
+  constexpr int kRows = 208, kTile = kRows * 128;
+  const std::vector<int32_t> T = make_tc_taps(nullptr);
+  std::vector<int8_t> tab((size_t)((G + 3) / 4) * kTile, 0);
+  auto sw_off = [](int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); };
+  auto digit = [](int t, int v, bool *ok) {            // balanced base-256 digits, v = 0..2
+    const int d0 = ((t + 128) & 255) - 128, t1 = (t - d0) >> 8;
+    const int d1 = ((t1 + 128) & 255) - 128, t2 = (t1 - d1) >> 8;
+    if (t2 < -128 || t2 > 127) *ok = false;
+    return v == 0 ? d0 : v == 1 ? d1 : v == 2 ? t2 : 0;
+  };
+  bool ok = true;
+  for (int i = 0; i < G; ++i)
+    for (int n = 0; n < kRows; ++n) {
+      const int d = n / 4 - i, v = n % 4;
+      if (d < 0 || d > 33) continue;
+      for (int pp = 0; pp < 16; ++pp) {
+        const int j = 16 * d - pp;
+        const int t = (j >= 0 && j < (int)T.size()) ? T[j] : 0;
+        const int b_lo = v <= 2 ? digit(t, v, &ok) : 0, b_hi = v >= 1 ? digit(t, v - 1, &ok) : 0;
+        const int kb = (i & 3) * 32 + 2 * pp;
+        int8_t *tile = tab.data() + (size_t)(i >> 2) * kTile;
+        tile[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)b_lo;
+        tile[sw_off(n, (kb + 1) >> 4) + ((kb + 1) & 15)] = (int8_t)b_hi;
+      }
+    }
+  if (!ok) tab.clear();                                 // a tap that needs a fourth digit: never for these taps
+  return tab;
+}
+
 void make_sss_tables(int n_id_2, SssTables &out) {
   int c_tilde[31];
   const int s_taps[2] = {2, 0}, c_taps[2] = {3, 0}, z_taps[4] = {4, 2, 1, 0};

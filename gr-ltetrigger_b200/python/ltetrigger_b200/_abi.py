@@ -20,6 +20,8 @@ FMT_FC32, FMT_SC16, FMT_SC8 = 0, 1, 2
 MAX_DECIM = 64
 CORR_DIRECT, CORR_FFT, OS_STEP = 0, 1, 896
 FRAME_FDD, FRAME_TDD = 0, 1
+FRONTEND_FP32, FRONTEND_TC_INT = 0, 1
+PIPE_OVERLAP, PIPE_SERIAL = 0, 1
 FMT_BYTES = {FMT_FC32: 8, FMT_SC16: 4, FMT_SC8: 2}
 FMT_DTYPE = {FMT_FC32: np.complex64, FMT_SC16: np.int16, FMT_SC8: np.int8}
 MIN_PSR_THRESHOLD = 1.5
@@ -41,7 +43,8 @@ class TriggerConfig(C.Structure):
                 ("input_format", C.c_int32), ("decim", C.c_int32), ("root_mask", C.c_int32),
                 ("max_chunk", C.c_int64), ("psr_threshold", C.c_float), ("track_after", C.c_int32),
                 ("track_every", C.c_int32), ("record_all", C.c_int32), ("keep_halfframes", C.c_int32),
-                ("cuda_stream", C.c_void_p), ("corr_mode", C.c_int32), ("frame_type", C.c_int32)]
+                ("cuda_stream", C.c_void_p), ("corr_mode", C.c_int32), ("frame_type", C.c_int32),
+                ("frontend_mode", C.c_int32), ("pipeline", C.c_int32)]
 
 
 class Mib(C.Structure):
@@ -62,7 +65,7 @@ SYMBOLS = [
     "ltb_trigger_collect", "ltb_trigger_get_stats", "ltb_trigger_fetch_halfframes",
     "ltb_trigger_last_timing", "ltb_trigger_last_kernel_times", "ltb_last_error", "ltb_version", "ltb_device_count",
     "ltb_sss_create", "ltb_sss_destroy", "ltb_sss_set_frame_type", "ltb_sss_work", "ltb_mib_decode",
-    "ltb_kernel_pss_corr_host", "ltb_kernel_pss_corr_fft_host", "ltb_kernel_decimate_host",
+    "ltb_kernel_pss_corr_host", "ltb_kernel_pss_corr_fft_host", "ltb_kernel_decimate_host", "ltb_kernel_decimate_tc_host",
     "ltb_table_pss_taps", "ltb_table_decim_taps", "ltb_table_sss", "ltb_table_cexp",
     "ltb_table_fft128_twiddles", "ltb_table_fft1024_twiddles", "ltb_table_os_filter",
 ]
@@ -121,6 +124,7 @@ def _load(path):
     L.ltb_table_fft1024_twiddles.argtypes = [fp, fp]
     L.ltb_table_os_filter.argtypes = [C.c_int, fp, fp]
     L.ltb_kernel_decimate_host.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp]
+    L.ltb_kernel_decimate_tc_host.argtypes = [C.c_int, vp, C.c_int, C.c_int64, C.c_int64, vp]
     L.ltb_table_pss_taps.argtypes = [C.c_int, fp, fp]
     L.ltb_table_decim_taps.argtypes = [C.c_int, fp, C.c_int]
     L.ltb_table_sss.argtypes = [C.c_int, ip, ip, ip, ip, ip]

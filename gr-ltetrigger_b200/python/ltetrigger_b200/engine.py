@@ -19,7 +19,8 @@ class Trigger:
 
     def __init__(self, n_streams, decim=1, psr_threshold=4.0, max_chunk=1 << 20, input_format=A.FMT_FC32,
                  track_after=16, track_every=8, record_all=True, keep_halfframes=False, device=0,
-                 root_mask=7, cuda_stream=None, corr_mode=A.CORR_DIRECT, frame_type=A.FRAME_FDD):
+                 root_mask=7, cuda_stream=None, corr_mode=A.CORR_DIRECT, frame_type=A.FRAME_FDD,
+                 frontend_mode=A.FRONTEND_FP32, pipeline=A.PIPE_OVERLAP):
         cfg = A.TriggerConfig()
         cfg.struct_size = C.sizeof(A.TriggerConfig)
         cfg.device, cfg.n_streams, cfg.input_format, cfg.decim = device, n_streams, input_format, decim
@@ -29,6 +30,8 @@ class Trigger:
         cfg.cuda_stream = cuda_stream
         cfg.corr_mode = corr_mode
         cfg.frame_type = frame_type
+        cfg.frontend_mode = frontend_mode
+        cfg.pipeline = pipeline
         self._h = C.c_void_p()
         A.check(A.lib().ltb_trigger_create(C.byref(cfg), C.byref(self._h)), "ltb_trigger_create")
         self.n_streams, self.decim, self.input_format = n_streams, decim, input_format
@@ -154,6 +157,17 @@ def kernel_decimate(x, decim, fmt=A.FMT_FC32, device=0, L=None):
     y = np.zeros((s, n // decim), np.complex64)
     A.check((L or A.lib()).ltb_kernel_decimate_host(device, x.ctypes.data, fmt, s, n, decim, y.ctypes.data),
             "ltb_kernel_decimate_host")
+    return y
+
+
+def kernel_decimate_tc(iq, chunk=None, device=0):
+    """LTB_FRONTEND_TC_INT at kernel level: iq [n_streams, n, 2] int16 -> [n_streams, n // 16] complex64, the
+    input fed in calls of `chunk` samples (multiple of 128; default: one call)."""
+    iq = np.ascontiguousarray(iq, np.int16)
+    s, n = iq.shape[0], iq.shape[1]
+    y = np.zeros((s, n // 16), np.complex64)
+    A.check(A.lib().ltb_kernel_decimate_tc_host(device, iq.ctypes.data, s, n, chunk or n, y.ctypes.data),
+            "ltb_kernel_decimate_tc_host")
     return y
 
 

@@ -57,6 +57,19 @@ extern "C" {
                                       half-frame keeps the reference's PSS alignment, which in TDD does not
                                       start at a subframe boundary, so ltb_mib_decode does not apply */
 
+/* arithmetic of the decimating front end */
+#define LTB_FRONTEND_FP32   0      /* canonical float32 expression trees (FFMA2), every format and rate */
+#define LTB_FRONTEND_TC_INT 1      /* exact integer arithmetic on the tensor cores (tcgen05.mma kind::i8): taps
+                                      quantised to three balanced base-256 digits, the int16 / int8 samples are
+                                      their own digits, int32 accumulation in TMEM, one rounding to float32 per
+                                      output.  sc16 / sc8 input at decim = 16 only */
+
+/* how the stages of consecutive calls are scheduled (results are identical) */
+#define LTB_PIPE_OVERLAP 0         /* with two calls in flight (submit/collect), the per-chain track + SSS kernels of
+                                      call i run on a second, low-priority stream under the front end and correlator
+                                      of call i+1 (rings sized for two chunks); forced off by keep_halfframes */
+#define LTB_PIPE_SERIAL  1         /* every kernel of a call on one stream, calls back to back */
+
 typedef struct { float re, im; } ltb_cf;
 
 /* ---- per-window record ---------------------------------------------------------
@@ -128,9 +141,13 @@ typedef struct {
   int32_t  track_every;       /* 0 -> 8 */
   int32_t  record_all;        /* 1: record every general_work call; 0: emitted half-frames only */
   int32_t  keep_halfframes;   /* 1: keep each emitted (CFO-corrected) half-frame for ltb_trigger_fetch_halfframes */
-  void    *cuda_stream;       /* cudaStream_t to launch on; NULL -> the library's own stream */
+  void    *cuda_stream;       /* cudaStream_t the caller produces device input on (NULL: none): the front end of a
+                                 call waits for the work queued there at submit time.  The kernels themselves run
+                                 on the library's own two streams; results are complete when collect returns */
   int32_t  corr_mode;         /* LTB_CORR_*; a struct_size that ends before this field selects LTB_CORR_DIRECT */
   int32_t  frame_type;        /* LTB_FRAME_*; default (0, or a shorter struct_size) is FDD like the reference */
+  int32_t  frontend_mode;     /* LTB_FRONTEND_*; default 0 = canonical FP32 */
+  int32_t  pipeline;          /* LTB_PIPE_*; default 0 = overlapped */
 } ltb_trigger_config;
 
 /* pss::make + sss::make + hier-block construction (lib/pss_impl.cc:42-83,
@@ -231,6 +248,11 @@ LTB_API int ltb_kernel_pss_corr_fft_host(int device, const ltb_cf *x, int n_stre
  * (multiple of decim); fmt as above; y: [n_streams][n_in/decim]. */
 LTB_API int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in,
                                      int decim, ltb_cf *y);
+
+/* LTB_FRONTEND_TC_INT at kernel level: decimate-by-16 of n_streams host streams of n_in interleaved int16 I/Q
+ * samples, fed to the tensor-core kernel in calls of `chunk` samples (both multiples of 128; the raw history
+ * is carried between the calls as the engine does); y: [n_streams][n_in / 16]. */
+LTB_API int ltb_kernel_decimate_tc_host(int device, const int16_t *x, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y);
 
 #ifdef LTB_DEBUG
 /* Only in the debug build (make -C gr-ltetrigger_b200 debug -> lib/libltetrigger_b200_debug.so, -DLTB_DEBUG);

@@ -254,6 +254,38 @@ int64_t orc_decimate_fast(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
   return n_out;
 }
 
+/* ORC_FRONT_TCINT: the arithmetic of the product's integer tensor-core front end (LTB_FRONTEND_TC_INT,
+ * gr-ltetrigger_b200/csrc/ltb_tc_frontend.cuh), restated with 64-bit integers.  The default taps of
+ * rational_resampler_ccc(1, 16) are quantised once, T[j] = rint(taps[j] * 2^27) (|T| < 2^23: three balanced
+ * base-256 digits on the tensor core); the int16 samples are used as they are; per component
+ *   A[k] = sum_j T[j] x[16 k - j]          exact, |A| < 2^44
+ *   y[k] = (float)A[k] * 2^-42             one rounding (2^-27 for the taps, 2^-15 for the sc16 scale)
+ * Exact arithmetic does not depend on evaluation order, so any correct integer evaluation -- this loop, or
+ * int8 digit products accumulated in int32 and recombined -- gives the same bits. */
+int64_t orc_decimate_tcint_sc16(const int16_t *iq, int64_t n_in, orc_cf *y)
+{
+  const int decim = 16;
+  float taps[4096];
+  int ntaps = orc_decim_taps(decim, taps, 4096);
+  if (ntaps != 525) return -1;
+  int32_t T[528];
+  for (int j = 0; j < ntaps; j++) T[j] = (int32_t)llrint((double)taps[j] * 134217728.0);
+  int64_t n_out = (n_in + decim - 1) / decim;
+  for (int64_t k = 0; k < n_out; k++) {
+    int64_t are = 0, aim = 0;
+    const int64_t top = k * decim;
+    const int jmax = top < ntaps - 1 ? (int)top : ntaps - 1;      /* zero history before the stream */
+    const int16_t *xp = iq + 2 * top;
+    for (int j = 0; j <= jmax; j++) {
+      are += (int64_t)T[j] * xp[-2 * j];
+      aim += (int64_t)T[j] * xp[-2 * j + 1];
+    }
+    y[k].re = (float)are * 2.2737367544323206e-13f;
+    y[k].im = (float)aim * 2.2737367544323206e-13f;
+  }
+  return n_out;
+}
+
 /* ------------------------------------------------------------------------- */
 /* PSS matched filter                                                         */
 /* ------------------------------------------------------------------------- */
@@ -1136,6 +1168,11 @@ typedef struct {
 static void trig_frontend(int s, void *arg)
 {
   trig_t *t = (trig_t *)arg;
+  if ((t->conv_mode & ORC_FRONT_TCINT) && t->fmt == 1 && t->decim == 16) {   /* integer front end */
+    t->ys[s] = malloc(sizeof(orc_cf) * t->n_out);
+    if (orc_decimate_tcint_sc16((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->ys[s]) < 0) t->fail = 1;
+    return;
+  }
   orc_cf *x = malloc(sizeof(orc_cf) * t->n_in);
   if (t->fmt == 1) orc_sc16_to_fc32((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, 1.0f / 32768.0f, x);
   else if (t->fmt == 2) orc_sc8_to_fc32((const int8_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, 1.0f / 128.0f, x);

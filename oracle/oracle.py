@@ -13,6 +13,7 @@ _SO = os.path.join(_HERE, "libltetrigger_oracle.so")
 
 CONV_DIRECT, CONV_FFT, CONV_OS = 0, 1, 2
 FRAME_TDD = 0x100          # or-ed into conv_mode: TDD SSS position
+FRONT_TCINT = 0x200        # or-ed into conv_mode of trigger_run: exact integer front end (sc16, decim 16)
 OS_STEP = 896
 SLOT, HALF, SYM, CONV_LEN, LOOKAHEAD = 960, 9600, 128, 9726, 18365
 
@@ -58,6 +59,8 @@ def lib():
         L.orc_decimate.restype = C.c_int64
         L.orc_decimate_fast.argtypes = [vp, C.c_int64, C.c_int, vp]
         L.orc_decimate_fast.restype = C.c_int64
+        L.orc_decimate_tcint_sc16.argtypes = [vp, C.c_int64, vp]
+        L.orc_decimate_tcint_sc16.restype = C.c_int64
         L.orc_sc16_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_sc8_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_pss_corr_window.argtypes = [vp, C.c_int, C.c_int, fp]
@@ -138,6 +141,16 @@ def decimate(x, decim):
     y = np.zeros(n_out, np.complex64)
     if lib().orc_decimate(x.ctypes.data, len(x), decim, y.ctypes.data) < 0:
         raise RuntimeError("orc_decimate: unsupported decimation %d" % decim)
+    return y
+
+
+def decimate_tcint_sc16(iq):
+    """LTB_FRONTEND_TC_INT restated: exact integer decimate-by-16 of [n, 2] int16 I/Q -> complex64."""
+    iq = np.ascontiguousarray(iq, np.int16)
+    n = iq.shape[0]
+    y = np.zeros((n + 15) // 16, np.complex64)
+    if lib().orc_decimate_tcint_sc16(iq.ctypes.data, n, y.ctypes.data) < 0:
+        raise RuntimeError("orc_decimate_tcint_sc16 failed")
     return y
 
 

@@ -432,8 +432,9 @@ def test_full_path_scaling_and_permutation_properties(lt, corr):
 
 def test_c_abi_error_behaviour(lt):
     """Return codes of the engine entry points (srsLTE convention 0 / -1 / -2, lib/sss_impl.cc:119): a
-    record buffer that is too small is filled as far as it goes and reported, oversized and misaligned
-    chunks are refused without side effects, optional features say so when they are off."""
+    record buffer that is too small is reported with the needed count and leaves the call pending (collect
+    again with a larger buffer: nothing is lost), oversized and misaligned chunks are refused without side
+    effects, optional features say so when they are off."""
     import ctypes as C
     from ltetrigger_b200 import _abi as A
     L = lt.lib()
@@ -445,8 +446,18 @@ def test_c_abi_error_behaviour(lt):
     n = C.c_int32(0)
     iq = np.ascontiguousarray(x[:96000])
     rc = L.ltb_trigger_process_host(trig._h, iq.ctypes.data, 0, 96000, small.ctypes.data, 5, C.byref(n))
-    assert rc == lt.ERROR_INVALID_INPUTS and n.value > 5              # says how many there were
-    assert small.tobytes() == full[:5].tobytes()                      # and filled what fitted
+    assert rc == lt.ERROR_INVALID_INPUTS and n.value > 5              # says how many there are
+    n_first = n.value
+    # the call is still pending: a new submit is refused, a retry with enough room gets every record
+    assert L.ltb_trigger_submit_host(trig._h, iq.ctypes.data, 0, 96000) == lt.SUCCESS      # second slot
+    assert L.ltb_trigger_submit_host(trig._h, iq.ctypes.data, 0, 96000) == lt.ERROR_INVALID_INPUTS
+    retry = np.zeros(n_first, A.WINDOW_REC)
+    assert L.ltb_trigger_collect(trig._h, retry.ctypes.data, n_first, C.byref(n)) == lt.SUCCESS and n.value == n_first
+    first = full[full["win_start"] + lt.LOOKAHEAD <= 96000]          # the calls the first chunk allows, in record order
+    assert len(first) == n_first and retry.tobytes() == first.tobytes()
+    second = np.zeros(64, A.WINDOW_REC)
+    assert L.ltb_trigger_collect(trig._h, second.ctypes.data, 64, C.byref(n)) == lt.SUCCESS
+    n_second = n.value
     big = np.zeros(96008, np.complex64)
     assert L.ltb_trigger_process_host(trig._h, big.ctypes.data, 0, 96008, small.ctypes.data, 5, C.byref(n)) == lt.ERROR_INVALID_INPUTS
     assert L.ltb_trigger_process_host(trig._h, None, 0, 96000, small.ctypes.data, 5, C.byref(n)) == lt.ERROR_INVALID_INPUTS
@@ -457,8 +468,8 @@ def test_c_abi_error_behaviour(lt):
     assert L.ltb_trigger_get_stats(trig._h, 3, 0, C.byref(st)) == lt.ERROR_INVALID_INPUTS
     assert L.ltb_trigger_get_stats(trig._h, 0, 3, C.byref(st)) == lt.ERROR_INVALID_INPUTS
     # the refused calls left the engine where it was: the remaining chunks give the remaining records
-    rest = trig.run(x[None, 96000:96000 * 4])
-    assert len(rest) == len(full) - n.value
+    rest = trig.run(x[None, 96000 * 2:96000 * 4])
+    assert len(rest) == len(full) - n_first - n_second
     for k in range(3):
         fk, rk = full[full["n_id_2"] == k], rest[rest["n_id_2"] == k]
         assert fk[len(fk) - len(rk):].tobytes() == rk.tobytes()

@@ -1,0 +1,88 @@
+"""LTB_FRONTEND_TC_INT: the exact-integer tensor-core front end (tcgen05.mma kind::i8, sc16 input at
+decim 16) against the oracle's int64 restatement (ORC_FRONT_TCINT): bit for bit, in ragged chunks, at
+the digit extremes, through the engine, and within the north_star's tolerance of the canonical float32
+front end.  Last in the GPU suite on purpose: a protocol error in this kernel traps (its watchdogs never
+hang) and would take the CUDA context of the test process with it."""
+import numpy as np
+import pytest
+
+from conftest import assert_recs_equal, load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lt():
+    import ltetrigger_b200 as lt
+    if lt.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU path")
+    return lt
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("n_out,chunk", [(976 * 3, None), (5000, None), (20000, 128 * 37), (20000, 128 * 2), (61 * 16 * 5 + 8, 128 * 125)])
+def test_tc_decimator_bit_exact(lt, oracle, n_out, chunk):
+    """Random full-scale int16 streams; chunk sizes that are not multiples of a 256-sample row, smaller
+    than the 768-sample history, and tile-aligned; every output equal to the int64 evaluation."""
+    rng = np.random.default_rng(n_out)
+    n = n_out * 16
+    x = rng.integers(-32768, 32768, size=(3, n, 2)).astype(np.int16)
+    x[1, :, :] = 32767                      # digit extremes: all-max and all-min streams
+    x[2, :, 0] = -32768
+    got = lt.kernel_decimate_tc(x, chunk=chunk)
+    for s in range(3):
+        want = oracle.decimate_tcint_sc16(x[s])
+        assert np.array_equal(_bits(got[s]), _bits(want)), (s, int(np.argmax(_bits(got[s]) != _bits(want))))
+
+
+def test_tc_decimator_within_tolerance_of_float32_front_end(lt, oracle):
+    """north_star: magnitudes within 1e-4 relative.  The integer front end differs from the canonical
+    float32 decimator only by tap quantisation (2^-28) and one rounding: ~3e-7 of full scale."""
+    rng = np.random.default_rng(7)
+    x = rng.integers(-20000, 20000, size=(2, 16 * 4000, 2)).astype(np.int16)
+    got = lt.kernel_decimate_tc(x)
+    ref = lt.kernel_decimate(x, 16, lt.FMT_SC16)
+    assert np.abs(got - ref).max() < 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("corr", ["fft", "direct"])
+def test_tc_front_end_through_the_engine(lt, oracle, corr):
+    """The 100 PRB fixture and synthetic cells as sc16 at 30.72 Msps through the whole chain with the
+    integer front end, in ragged chunks: records bit-identical to the oracle in the same mode, the same
+    decisions as the float32 front end, the reference's known cell id."""
+    from ltetrigger_b200 import synth
+    x, decim, cell_id = load_fixture("100prb", 0.25)
+    rows = [x, synth.capture(77, len(x), snr_db=3.0, decim=16, seed=5, cfo_hz=1500.0),
+            synth.capture(300, len(x), snr_db=0.0, decim=16, seed=6, noise_only=True)]
+    iq = synth.to_sc16(np.stack(rows))
+    mode = lt.CORR_FFT if corr == "fft" else lt.CORR_DIRECT
+    conv = (oracle.CONV_OS if corr == "fft" else oracle.CONV_DIRECT) | oracle.FRONT_TCINT
+    chunk = 16 * 8 * 4001
+    trig = lt.Trigger(n_streams=3, decim=16, max_chunk=chunk, input_format=lt.FMT_SC16, corr_mode=mode,
+                      frontend_mode=lt.FRONTEND_TC_INT)
+    got = trig.run(iq, chunk=chunk)
+    trig.close()
+    want = oracle.trigger_run(iq, decim=16, fmt=1, conv_mode=conv)
+    assert_recs_equal(got, want)
+    cells = got[(got["flags"] & lt.F_CELL) != 0]
+    assert set(cells[cells["stream"] == 0]["cell_id"].tolist()) == {cell_id}
+    assert set(cells[cells["stream"] == 1]["cell_id"].tolist()) == {77}
+    # the float32 front end on the same input: same windows, flags, peaks and cell ids; magnitudes within 1e-4
+    ref = lt.Trigger(n_streams=3, decim=16, max_chunk=chunk, input_format=lt.FMT_SC16, corr_mode=mode)
+    fp = ref.run(iq, chunk=chunk)
+    ref.close()
+    sel = (got["stream"] < 2)                                  # noise-only stream: argmax of noise may move
+    for f in ("win_start", "emit_start", "flags", "peak_pos", "m0", "m1", "n_id_1", "cell_id"):
+        assert (got[f][sel] == fp[f][sel]).all(), f
+    np.testing.assert_allclose(got["psr"][sel], fp["psr"][sel], rtol=1e-4)
+    np.testing.assert_allclose(got["peak_value"][sel], fp["peak_value"][sel], rtol=1e-4)
+
+
+def test_tc_front_end_argument_checks(lt):
+    with pytest.raises(lt.LtbError):
+        lt.Trigger(n_streams=1, decim=16, input_format=lt.FMT_FC32, frontend_mode=lt.FRONTEND_TC_INT)   # integer input only
+    with pytest.raises(lt.LtbError):
+        lt.Trigger(n_streams=1, decim=8, input_format=lt.FMT_SC16, frontend_mode=lt.FRONTEND_TC_INT)    # decim 16 only

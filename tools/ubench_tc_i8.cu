@@ -1,0 +1,187 @@
+// Stand-alone driver of the integer tensor-core front end (gr-ltetrigger_b200/csrc/ltb_tc_frontend.cuh):
+// random sc16 streams through decimate_tc_kernel<G>, every checked output compared EXACTLY with an int64
+// evaluation on the host, then timed.  One variant per process (a watchdog trap poisons the context):
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o tools/ubench_tc_i8 tools/ubench_tc_i8.cu
+//   ./tools/ubench_tc_i8 <G = 1|2|4|8> [n_streams] [n_in per stream] [chunks]
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../gr-ltetrigger_b200/csrc/ltb_tc_frontend.cuh"
+
+using namespace ltb;
+
+static double izero(double v) {
+  double sum = 1, u = 1, h = v / 2; int n = 1;
+  do { double t = h / n; n++; t *= t; u *= t; sum += u; } while (u >= 1e-21 * sum);
+  return sum;
+}
+// the 525 float32 taps of rational_resampler_ccc(1, 16) (same design as ltb_tables.cpp)
+static std::vector<float> taps16() {
+  const int ntaps = 525, M = 262;
+  const double beta = 7.0, tw = 0.1 / 16, mid = 0.5 / 16 - tw / 2, fw = 2 * M_PI * mid;
+  std::vector<float> w(ntaps), t(ntaps);
+  for (int i = 0; i < ntaps; ++i) { const double x = 2.0 * i / (ntaps - 1) - 1; w[i] = (float)(izero(beta * sqrt(1 - x * x)) / izero(beta)); }
+  for (int n = -M; n <= M; ++n) t[n + M] = (float)((n == 0 ? fw / M_PI : sin(n * fw) / (n * M_PI)) * w[n + M]);
+  double g = t[M];
+  for (int n = 1; n <= M; ++n) g += 2 * t[n + M];
+  for (auto &v : t) v = (float)(v / g);
+  return t;
+}
+
+static int sw_off(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
+
+// tap tables in the kernel's shared-memory image (see ltb_tc_frontend.cuh)
+static std::vector<int8_t> make_btab(int G, const std::vector<int> &T) {
+  std::vector<int8_t> tab((size_t)tc_btiles(G) * kTcBTileBytes, 0);
+  auto tapq = [&](int j) { return (j >= 0 && j < (int)T.size()) ? T[j] : 0; };
+  auto digit = [&](int t, int v) {            // balanced base-256 digits v = 0..2
+    int d0 = ((t + 128) & 255) - 128; int t1 = (t - d0) >> 8;
+    int d1 = ((t1 + 128) & 255) - 128; int t2 = (t1 - d1) >> 8;
+    if (t2 < -128 || t2 > 127) { fprintf(stderr, "tap does not fit three digits\n"); exit(2); }
+    return v == 0 ? d0 : v == 1 ? d1 : v == 2 ? t2 : 0;
+  };
+  for (int i = 0; i < G; ++i)
+    for (int n = 0; n < kTcBRows; ++n) {
+      const int d = n / 4 - i, v = n % 4;
+      if (d < 0 || d > 33) continue;
+      for (int pp = 0; pp < 16; ++pp) {
+        const int t = tapq(16 * d - pp);
+        const int b_lo = v <= 2 ? digit(t, v) : 0, b_hi = v >= 1 ? digit(t, v - 1) : 0;
+        const int kb = (i & 3) * 32 + 2 * pp;
+        int8_t *tile = tab.data() + (size_t)(i >> 2) * kTcBTileBytes;
+        tile[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)b_lo;
+        tile[sw_off(n, (kb + 1) >> 4) + ((kb + 1) & 15)] = (int8_t)b_hi;
+      }
+    }
+  return tab;
+}
+
+typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int G>
+static void launch(const CUtensorMap &map, const TcParams &P, int grid) {
+  cudaFuncSetAttribute(decimate_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(G));
+  decimate_tc_kernel<G><<<grid, kTcThreads, tc_smem_bytes(G)>>>(map, P);
+}
+
+int main(int argc, char **argv) {
+  const int G = argc > 1 ? atoi(argv[1]) : 1;
+  const int S = argc > 2 ? atoi(argv[2]) : 64;
+  const int n_in = argc > 3 ? atoi(argv[3]) : 3072000;
+  const int chunks = argc > 4 ? atoi(argv[4]) : 1;       // > 1: feed the stream in `chunks` calls (tail carried)
+  if (G != 1 && G != 2 && G != 4 && G != 8) { fprintf(stderr, "G must be 1, 2, 4 or 8\n"); return 2; }
+  const std::vector<float> tf = taps16();
+  std::vector<int> T(tf.size());
+  long long sumT = 0;
+  for (size_t j = 0; j < tf.size(); ++j) { T[j] = (int)llrint((double)tf[j] * (double)(1 << kTcTapShift)); sumT += T[j]; }
+  const std::vector<int8_t> btab = make_btab(G, T);
+
+  const size_t row_bytes = (size_t)n_in * 4;
+  std::vector<short> x((size_t)S * n_in * 2);
+  srand(12345);
+  for (auto &v : x) v = (short)((rand() & 0xffff) - 32768);
+  // a few structured streams: extremes exercise the digit bounds
+  for (int i = 0; i < n_in * 2 && S > 2; ++i) { x[(size_t)1 * n_in * 2 + i] = 32767; x[(size_t)2 * n_in * 2 + i] = -32768; }
+
+  void *d_x; short2 *d_tail[2]; float2 *d_y; int8_t *d_b; int *d_err;
+  const int m_total = n_in / 16;
+  int cap = 1; while (cap < m_total + 64) cap <<= 1;
+  cudaMalloc(&d_x, (size_t)S * row_bytes);
+  cudaMalloc(&d_tail[0], (size_t)S * kTcTailSamples * 4); cudaMalloc(&d_tail[1], (size_t)S * kTcTailSamples * 4);
+  cudaMemset(d_tail[0], 0, (size_t)S * kTcTailSamples * 4);
+  cudaMalloc(&d_y, (size_t)S * cap * 8); cudaMemset(d_y, 0xff, (size_t)S * cap * 8);
+  cudaMalloc(&d_b, btab.size()); cudaMalloc(&d_err, 4); cudaMemset(d_err, 0, 4);
+  cudaMemcpy(d_x, x.data(), (size_t)S * row_bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_b, btab.data(), btab.size(), cudaMemcpyHostToDevice);
+
+  EncodeTiled encode = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres) != cudaSuccess || !encode) {
+    printf("{\"error\": \"cuTensorMapEncodeTiled not found\"}\n"); return 1;
+  }
+  int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+
+  auto run_chunk = [&](int c0, int n_chunk, int tail_cur) -> int {
+    CUtensorMap map;
+    const int full_rows = n_chunk / kTcRowSamples;
+    const cuuint64_t gdim[3] = {1024, (cuuint64_t)(full_rows > 0 ? full_rows : 1), (cuuint64_t)S};
+    const cuuint64_t gstr[2] = {1024, (cuuint64_t)row_bytes};
+    const cuuint32_t box[3] = {256, (cuuint32_t)kTcTileRows, 1}, estr[3] = {1, 1, 1};
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (char *)d_x + (size_t)c0 * 4, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("{\"error\": \"cuTensorMapEncodeTiled -> %d\"}\n", (int)r); return 1; }
+    TcParams P;
+    P.in = (char *)d_x + (size_t)c0 * 4; P.stride_bytes = (long long)row_bytes; P.n_in = n_chunk; P.n_streams = S;
+    P.tail = d_tail[tail_cur]; P.y_ring = d_y; P.n_base = c0 / 16; P.cap_mask = (unsigned)(cap - 1); P.cap = cap;
+    const int rows = (n_chunk + kTcRowSamples - 1) / kTcRowSamples;
+    P.tiles_per_stream = (rows + kTcUseful - 1) / kTcUseful; P.total_tiles = P.tiles_per_stream * S;
+    P.btab = d_b; P.c_const = 128 * sumT; P.err = d_err;
+    const int grid = P.total_tiles < sms ? P.total_tiles : sms;
+    switch (G) { case 1: launch<1>(map, P, grid); break; case 2: launch<2>(map, P, grid); break;
+                 case 4: launch<4>(map, P, grid); break; default: launch<8>(map, P, grid); }
+    tc_tail_kernel<<<S, 256>>>(P.in, P.stride_bytes, n_chunk, d_tail[tail_cur], d_tail[tail_cur ^ 1]);
+    return 0;
+  };
+  auto run_all = [&]() -> int {
+    cudaMemset(d_tail[0], 0, (size_t)S * kTcTailSamples * 4);
+    int tc = 0, c0 = 0;
+    for (int c = 0; c < chunks; ++c) {
+      int n_chunk = (c == chunks - 1) ? n_in - c0 : (n_in / chunks) / 128 * 128;
+      if (c < chunks - 1 && (c & 1)) n_chunk += 128;                     // ragged: not always a multiple of 256
+      if (run_chunk(c0, n_chunk, tc)) return 1;
+      c0 += n_chunk; tc ^= 1;
+    }
+    return 0;
+  };
+  if (run_all()) return 1;
+  cudaError_t e = cudaDeviceSynchronize();
+  int herr = 0; cudaMemcpy(&herr, d_err, 4, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { printf("{\"G\": %d, \"error\": \"%s\", \"watchdog\": %d}\n", G, cudaGetErrorString(e), herr); return 1; }
+
+  // ---- exact check against int64 on the host ----
+  std::vector<float2> y((size_t)S * cap);
+  cudaMemcpy(y.data(), d_y, y.size() * 8, cudaMemcpyDeviceToHost);
+  long long checked = 0, bad = 0; int first_bad_s = -1, first_bad_k = -1; float gb = 0, wb = 0;
+  for (int s = 0; s < S; ++s) {
+    const short *xs = x.data() + (size_t)s * n_in * 2;
+    const int step = (s < 4) ? 1 : 97;                                   // four streams in full, the others sampled
+    for (int k = 0; k < m_total; k += step) {
+      long long are = 0, aim = 0;
+      for (int j = 0; j < 525; ++j) {
+        const long long n = 16LL * k - j;
+        if (n < 0) break;
+        are += (long long)T[j] * xs[2 * n]; aim += (long long)T[j] * xs[2 * n + 1];
+      }
+      const float wre = (float)are * 2.2737367544323206e-13f, wim = (float)aim * 2.2737367544323206e-13f;
+      const float2 g = y[(size_t)s * cap + k];
+      checked++;
+      if (memcmp(&g.x, &wre, 4) || memcmp(&g.y, &wim, 4)) {
+        if (!bad) { first_bad_s = s; first_bad_k = k; gb = g.x; wb = wre; }
+        bad++;
+      }
+    }
+  }
+  // ---- timing ----
+  float ms = 0;
+  if (!bad && chunks == 1) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    run_all();
+    cudaEventRecord(e0);
+    for (int i = 0; i < 5; ++i) run_all();
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+  }
+  e = cudaDeviceSynchronize();
+  printf("{\"G\": %d, \"streams\": %d, \"n_in\": %d, \"chunks\": %d, \"checked\": %lld, \"mismatches\": %lld, \"first_bad\": [%d, %d, %g, %g], "
+         "\"ms\": %.4f, \"input_Gsamples_per_s\": %.1f, \"GB_per_s\": %.1f, \"status\": \"%s\"}\n",
+         G, S, n_in, chunks, checked, bad, first_bad_s, first_bad_k, gb, wb, ms, ms > 0 ? (double)S * n_in / ms / 1e6 : 0.0,
+         ms > 0 ? (double)S * n_in * 4 / ms / 1e6 : 0.0, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+  return bad ? 3 : 0;
+}
