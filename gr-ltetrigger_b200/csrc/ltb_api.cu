@@ -377,7 +377,7 @@ int launch_frontend_tc(int device, const void *d_iq, long long stride, int n_str
   const long long total = (long long)P.tiles_per_stream * n_streams;
   if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator tiles in one call");
   P.total_tiles = (int)total;
-  P.btab = g_tc_btab[device]; P.c_const = 128 * g_tc_sum_t; P.err = d_err;
+  P.btab = g_tc_btab[device]; P.c_const = 128 * g_tc_sum_t; P.err = d_err; P.dbg_acc = nullptr;
   const int sms = g_sm_count[device] > 0 ? g_sm_count[device] : 148;
   const int grid = P.total_tiles < sms ? P.total_tiles : sms;
   switch (tc_group()) {

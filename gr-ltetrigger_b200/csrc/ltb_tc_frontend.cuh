@@ -74,6 +74,7 @@ struct TcParams {
   const int8_t *btab;          // [tc_btiles(G)][208][128]: tap tables, k-slice i = table for k-step s with s % G == i
   long long c_const;           // 128 * sum_j T[j]
   int *err;                    // device flag: 0 ok, else the code of the watchdog that fired
+  int *dbg_acc;                // null, or [128][208] int32: the raw accumulator tile of tile 0 (tools/ubench_tc_i8)
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------
@@ -227,7 +228,11 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
       for (int t = t_begin; t < t_end; ++t) {
         const int stream = t / P.tiles_per_stream, ti = t - stream * P.tiles_per_stream;
         const int row0 = ti * kTcUseful - kTcHalo;
+#ifdef LTB_TC_NO_TMA
+        const bool any = false;                                          // bisection build: every row takes the patch path
+#else
         const bool any = row0 + kTcTileRows > 0 && row0 < full_rows;     // rows out of range are zero-filled
+#endif
         for (int a = 0; a < 4; ++a, ++it) {
           const int rs = it % kTcRawStages;
           tc_mbar_wait(raw_empty(rs), ((it / kTcRawStages) & 1) ^ 1, P.err, 1);
@@ -275,7 +280,11 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
     for (int t = t_begin; t < t_end; ++t) {
       const int stream = t / P.tiles_per_stream, ti = t - stream * P.tiles_per_stream;
       const int row0 = ti * kTcUseful - kTcHalo;
+#ifdef LTB_TC_NO_TMA
+      const bool patch = true;
+#else
       const bool patch = row0 < 0 || row0 + kTcTileRows > full_rows;     // some rows are not plain tensor rows
+#endif
       for (int a = 0; a < 4; ++a, ++it) {
         const int rs = it % kTcRawStages, as = it % kTcAStages;
         tc_mbar_wait(raw_full(rs), (it / kTcRawStages) & 1, P.err, 4);
@@ -283,7 +292,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
         const unsigned char *raw = s_raw + (size_t)rs * kTcRawBytes;
         unsigned char *dst = s_a + (size_t)as * kTcABytes;
 #pragma unroll 4
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < kTcTileRows * 16 / 128; ++j) {               // 64 rows x 16 four-sample items, 128 threads
           const int item = j * 128 + tt, row = item >> 4, c = item & 15;
           uint4 w = *reinterpret_cast<const uint4 *>(raw + row * 256 + c * 16);
           if (patch) {
@@ -291,7 +300,11 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
             if (ra < 0) {                                                // history: the carried tail (rows -3..-1)
               w = *reinterpret_cast<const uint4 *>(P.tail + (size_t)stream * kTcTailSamples + (ra + kTcHalo) * kTcRowSamples +
                                                    a * kTcAtomSamples + c * 4);
+#ifdef LTB_TC_NO_TMA
+            } else {
+#else
             } else if (ra >= full_rows) {                                // the partial last row, then nothing
+#endif
               const int n0 = ra * kTcRowSamples + a * kTcAtomSamples + c * 4;
               const unsigned *src = reinterpret_cast<const unsigned *>((const char *)P.in + (long long)stream * P.stride_bytes);
               w.x = n0 + 0 < P.n_in ? src[n0 + 0] : 0u;
@@ -333,12 +346,20 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int u = 0; u < 8; ++u) p[8 * c0 + u] = tc_combine(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+        if (P.dbg_acc && t == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) P.dbg_acc[(warp * 32 + lane) * kTcBRows + 32 * c0 + i] = (int)r[i];
+        }
       }
       {
         uint32_t r[4];                                                   // columns 192..195: u = 48
         tc_ld4(taddr + 192, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         p[48] = tc_combine(r[0], r[1], r[2], r[3]);
+        if (P.dbg_acc && t == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) P.dbg_acc[(warp * 32 + lane) * kTcBRows + 192 + i] = (int)r[i];
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();

@@ -84,13 +84,117 @@ class block {
   std::vector<tag_t> d_in_tags, d_out_tags;
 };
 
+// ---- one engine for the three chains of a hier block ----------------------------------------------
+// downlink_trigger_c connects ONE input stream to three pss blocks (python/downlink_trigger_c.py:27-45).
+// Built on their own, the three adapters would create three engines and copy the same samples to the GPU
+// three times.  An engine_group owns one ltb_trigger with all three roots; the pss (and sss) adapters made
+// with it hand their scheduler calls to the group, which feeds each new sample once (whichever block the
+// scheduler happens to run first brings it) and queues the window records per root.
+class engine_group {
+ public:
+  typedef std::shared_ptr<engine_group> sptr;
+  static sptr make(float psr_threshold, int track_after = 16, int track_every = 8, int device = 0) {
+    return sptr(new engine_group(psr_threshold, track_after, track_every, device));
+  }
+  ~engine_group() { if (d_ltb) ltb_trigger_destroy(d_ltb); }
+
+  struct item { ltb_window_rec rec; std::vector<gr_complex> halfframe; };
+
+  // Called from pss(N_id_2 = root)::general_work.  `in` holds the stream from absolute item `abs0` to
+  // `avail_end`; the engine is fed up to want_end.  Returns false if no call of this root is ready.
+  bool next(int root, const gr_complex *in, uint64_t abs0, uint64_t avail_end, uint64_t want_end, item &out) {
+    std::lock_guard<std::mutex> lk(d_mu);
+    if (want_end > avail_end) want_end = avail_end;
+    while (d_ready[root].empty() && want_end > d_pushed + 7) {
+      if (d_pushed < abs0) throw std::runtime_error("engine_group: the blocks do not read the same stream");
+      int64_t n = (int64_t)((want_end - d_pushed) / 8 * 8);
+      if (n > d_max_chunk) n = d_max_chunk;
+      push(in + (d_pushed - abs0), n);
+    }
+    if (d_ready[root].empty()) return false;
+    out = std::move(d_ready[root].front());
+    d_ready[root].pop_front();
+    if (out.rec.flags & LTB_F_EMIT) d_sss[root].push_back(out.rec);      // what sss::work will say about it
+    return true;
+  }
+  // the SSS result of the next half-frame pss(root) emitted (computed on the GPU in the same call)
+  bool next_sss(int root, ltb_window_rec &rec) {
+    std::lock_guard<std::mutex> lk(d_mu);
+    if (d_sss[root].empty()) return false;
+    rec = d_sss[root].front();
+    d_sss[root].pop_front();
+    return true;
+  }
+  void set_psr_threshold(int root, float thr) {
+    std::lock_guard<std::mutex> lk(d_mu);
+    ltb_trigger_set_psr_threshold(d_ltb, 0, root, thr, 0);
+  }
+  ltb_pss_stats stats(int root) {
+    std::lock_guard<std::mutex> lk(d_mu);
+    ltb_pss_stats s = ltb_pss_stats();
+    ltb_trigger_get_stats(d_ltb, 0, root, &s);
+    return s;
+  }
+
+ private:
+  engine_group(float psr_threshold, int track_after, int track_every, int device) {
+    ltb_trigger_config cfg = ltb_trigger_config();
+    cfg.struct_size = sizeof cfg;
+    cfg.device = device;
+    cfg.n_streams = 1;
+    cfg.input_format = LTB_FMT_FC32;
+    cfg.decim = 1;
+    cfg.root_mask = 7;
+    cfg.max_chunk = d_max_chunk;
+    cfg.psr_threshold = psr_threshold;
+    cfg.track_after = track_after;
+    cfg.track_every = track_every;
+    cfg.record_all = 1;
+    cfg.keep_halfframes = 1;
+    if (ltb_trigger_create(&cfg, &d_ltb)) throw std::runtime_error(std::string("Error initializing PSS: ") + ltb_last_error());
+    ltb_trigger_set_psr_threshold(d_ltb, 0, -1, psr_threshold, 0);      // the blocks themselves do not clamp
+  }
+  void push(const gr_complex *x, int64_t n) {
+    std::vector<ltb_window_rec> recs((size_t)(3 * (n / 8640 + 8)));
+    int n_recs = 0;
+    if (ltb_trigger_process_host(d_ltb, x, (int64_t)(n * (int64_t)sizeof(gr_complex)), n, recs.data(), (int)recs.size(), &n_recs))
+      throw std::runtime_error(std::string("pss: ") + ltb_last_error());
+    std::vector<ltb_cf> hf((size_t)(n_recs > 0 ? n_recs : 1) * half_frame_length);
+    int n_hf = 0;
+    if (n_recs > 0 && ltb_trigger_fetch_halfframes(d_ltb, hf.data(), n_recs, &n_hf))
+      throw std::runtime_error(std::string("pss: ") + ltb_last_error());
+    for (int i = 0, k = 0; i < n_recs; ++i) {                            // records come ordered (root, win_index)
+      item it;
+      it.rec = recs[i];
+      if (recs[i].flags & LTB_F_EMIT) {
+        const gr_complex *p = reinterpret_cast<const gr_complex *>(&hf[(size_t)k++ * half_frame_length]);
+        it.halfframe.assign(p, p + half_frame_length);
+      }
+      d_ready[recs[i].n_id_2].push_back(std::move(it));
+    }
+    d_pushed += (uint64_t)n;
+  }
+
+  ltb_trigger *d_ltb = nullptr;
+  std::mutex d_mu;
+  int64_t d_max_chunk = 1 << 18;
+  uint64_t d_pushed = 0;
+  std::deque<item> d_ready[3];
+  std::deque<ltb_window_rec> d_sss[3];
+};
+
 // ---- ltetrigger::pss ---------------------------------------------------------------------
 class pss : public block {
  public:
   typedef std::shared_ptr<pss> sptr;
   // include/ltetrigger/pss.h:66-69
   static sptr make(int N_id_2, float psr_threshold, int track_after = 16, int track_every = 8, int device = 0) {
-    return sptr(new pss(N_id_2, psr_threshold, track_after, track_every, device));
+    return sptr(new pss(N_id_2, psr_threshold, track_after, track_every, device, engine_group::sptr()));
+  }
+  // the same block as one of the three chains of a shared engine (see engine_group); its threshold and tracking
+  // parameters are the group's until set_psr_threshold changes this root's
+  static sptr make(int N_id_2, const engine_group::sptr &group) {
+    return sptr(new pss(N_id_2, 0.f, 0, 0, 0, group));
   }
   ~pss() { if (d_ltb) ltb_trigger_destroy(d_ltb); }
 
@@ -101,6 +205,7 @@ class pss : public block {
   // GNU Radio calls setters and getters from the GUI / Python thread while the scheduler thread is inside
   // general_work; the C ABI wants one host thread per engine at a time, so every use of d_ltb takes d_mu
   void set_psr_threshold(float threshold) {
+    if (d_group) { d_group->set_psr_threshold(d_N_id_2, threshold); return; }
     std::lock_guard<std::mutex> lk(d_mu);
     ltb_trigger_set_psr_threshold(d_ltb, 0, d_N_id_2, threshold, 0);
   }
@@ -131,15 +236,24 @@ class pss : public block {
     uint64_t want_end = nitems_read(0) + (uint64_t)LTB_LOOKAHEAD + 7 +
                         (uint64_t)(d_lookahead_windows - 1) * (uint64_t)(LTB_LOOKAHEAD - LTB_SLOT_LEN);
     if (want_end > avail_end) want_end = avail_end;
-    while (d_ready.empty() && want_end > d_pushed + 7) {
-      int64_t n = (int64_t)((want_end - d_pushed) / 8 * 8);
-      if (n > d_max_chunk) n = d_max_chunk;
-      push(in + (d_pushed - nitems_read(0)), n);
+    ltb_window_rec rec;
+    std::vector<gr_complex> hf;
+    if (d_group) {
+      engine_group::item it;
+      if (!d_group->next(d_N_id_2, in, nitems_read(0), avail_end, want_end, it)) { consume_each(0); return 0; }
+      rec = it.rec;
+      hf = std::move(it.halfframe);
+    } else {
+      while (d_ready.empty() && want_end > d_pushed + 7) {
+        int64_t n = (int64_t)((want_end - d_pushed) / 8 * 8);
+        if (n > d_max_chunk) n = d_max_chunk;
+        push(in + (d_pushed - nitems_read(0)), n);
+      }
+      if (d_ready.empty()) { consume_each(0); return 0; }
+      rec = d_ready.front().first;
+      hf = std::move(d_ready.front().second);
+      d_ready.pop_front();
     }
-    if (d_ready.empty()) { consume_each(0); return 0; }
-    ltb_window_rec rec = d_ready.front().first;
-    std::vector<gr_complex> hf = std::move(d_ready.front().second);
-    d_ready.pop_front();
     if ((uint64_t)rec.win_start != nitems_read(0)) throw std::runtime_error("pss: scheduler and engine out of step");
     d_last = rec;
     if (rec.flags & LTB_F_EMIT) {
@@ -155,8 +269,12 @@ class pss : public block {
   const ltb_window_rec &last_record() const { return d_last; }
 
  private:
-  pss(int N_id_2, float psr_threshold, int track_after, int track_every, int device) : block("pss"), d_N_id_2(N_id_2) {
+  pss(int N_id_2, float psr_threshold, int track_after, int track_every, int device, const engine_group::sptr &group)
+      : block("pss"), d_N_id_2(N_id_2), d_group(group) {
     if (N_id_2 < 0 || N_id_2 > 2) throw std::runtime_error("Error initializing PSS N_id_2");
+    set_history(half_frame_length);           // lib/pss_impl.cc:81
+    set_output_multiple(half_frame_length);   // :82
+    if (d_group) return;
     ltb_trigger_config cfg = ltb_trigger_config();
     cfg.struct_size = sizeof cfg;
     cfg.device = device;
@@ -172,10 +290,9 @@ class pss : public block {
     cfg.keep_halfframes = 1;
     if (ltb_trigger_create(&cfg, &d_ltb)) throw std::runtime_error(std::string("Error initializing PSS: ") + ltb_last_error());
     ltb_trigger_set_psr_threshold(d_ltb, 0, N_id_2, psr_threshold, 0);   // the block itself does not clamp
-    set_history(half_frame_length);           // lib/pss_impl.cc:81
-    set_output_multiple(half_frame_length);   // :82
   }
   ltb_pss_stats stats() const {
+    if (d_group) return d_group->stats(d_N_id_2);
     std::lock_guard<std::mutex> lk(d_mu);
     ltb_pss_stats s = ltb_pss_stats();
     ltb_trigger_get_stats(d_ltb, 0, d_N_id_2, &s);
@@ -203,6 +320,7 @@ class pss : public block {
   }
 
   int d_N_id_2;
+  engine_group::sptr d_group;                              // null: this block owns its engine
   ltb_trigger *d_ltb = nullptr;
   mutable std::mutex d_mu;                                 // serialises every ltb_trigger_* call on d_ltb
   int d_lookahead_windows = 1;
@@ -216,7 +334,10 @@ class pss : public block {
 class sss : public block {
  public:
   typedef std::shared_ptr<sss> sptr;
-  static sptr make(int N_id_2, int device = 0) { return sptr(new sss(N_id_2, device)); }   // include/ltetrigger/sss.h:51
+  static sptr make(int N_id_2, int device = 0) { return sptr(new sss(N_id_2, device, engine_group::sptr())); }   // include/ltetrigger/sss.h:51
+  // downstream of pss::make(N_id_2, group): the engine has already decoded the SSS of every half-frame that pss
+  // emitted, so work() only attaches the tags.  The input MUST be that pss block's output, in order.
+  static sptr make(int N_id_2, const engine_group::sptr &group) { return sptr(new sss(N_id_2, 0, group)); }
   ~sss() { if (d_sss) ltb_sss_destroy(d_sss); }
 
   // lib/sss_impl.cc:83-156: one aligned half-frame per call, returns 9600
@@ -228,8 +349,12 @@ class sss : public block {
     int32_t lost = !tags.empty();
     ltb_window_rec rec = ltb_window_rec();
     rec.m0 = rec.m1 = rec.n_id_1 = rec.cell_id = -1;
-    if (ltb_sss_work(d_sss, reinterpret_cast<const ltb_cf *>(in), &lost, 1, &rec))
+    if (d_group) {
+      if (!d_group->next_sss(d_N_id_2, rec)) throw std::runtime_error("sss: no half-frame pending from the shared engine");
+      if (((rec.flags & LTB_F_TAG_LOST) != 0) != (lost != 0)) throw std::runtime_error("sss: input is not the paired pss block's output");
+    } else if (ltb_sss_work(d_sss, reinterpret_cast<const ltb_cf *>(in), &lost, 1, &rec)) {
       throw std::runtime_error(std::string("sss: ") + ltb_last_error());
+    }
     d_last = rec;
     if (!lost && !(rec.flags & LTB_F_CELL)) return half_frame_length;               // :119-120, out not written
     if (!lost) {
@@ -242,10 +367,13 @@ class sss : public block {
   const ltb_window_rec &last_record() const { return d_last; }
 
  private:
-  sss(int N_id_2, int device) : block("sss") {
-    if (ltb_sss_create(device, N_id_2, &d_sss)) throw std::runtime_error("Error initializing SSS SYNC");
+  sss(int N_id_2, int device, const engine_group::sptr &group) : block("sss"), d_N_id_2(N_id_2), d_group(group) {
+    if (N_id_2 < 0 || N_id_2 > 2) throw std::runtime_error("Error initializing SSS N_id_2");
+    if (!d_group && ltb_sss_create(device, N_id_2, &d_sss)) throw std::runtime_error("Error initializing SSS SYNC");
     set_output_multiple(half_frame_length);   // lib/sss_impl.cc:72
   }
+  int d_N_id_2;
+  engine_group::sptr d_group;
   ltb_sss *d_sss = nullptr;
   ltb_window_rec d_last = ltb_window_rec();
 };

@@ -1,0 +1,142 @@
+"""Single-stream configurations of BASELINE.json (`bench.py --workload c1|c2|c3`): the reference's own use
+case, one capture through one trigger (examples/test.sh:3-6, examples/cell_search_file.py:56-60).
+
+  c1  test_frames/lte_frame_50prb_cellid_125  @ 15.36 Msps (decimate by 8)   cell_search_file.py --repeat
+  c2  test_frames/lte_frame_6prb_cellid_123   @  1.92 Msps (no decimation)
+  c3  test_frames/lte_frame_100prb_cellid_369 @ 30.72 Msps (decimate by 16)
+
+Per configuration, on the fixture tiled to `seconds` of signal (file_source(repeat) -> head):
+  (a) wall time from the first work() call to the "track" message through the hier-block mirror
+      `downlink_trigger_c.work` (50 ms scheduler passes, H2D + kernels + host MIB decode), and the
+      signal time it corresponds to;
+  (b) sustained input samples/s through ltb_trigger_process_host (one call at a time) and through
+      ltb_trigger_submit_host / collect (two calls in flight), host buffers, 100 ms calls;
+  (c) the same stream at 1.92 Msps through the C++ block adapters pss::general_work / sss::work, three
+      chains, driven like the GNU Radio scheduler does (tools/bench_blocks.cpp): one engine per pss block
+      versus one shared engine_group, look-ahead 1 and 32 windows;
+and the CPU restatement (oracle, all cores: one job per (stream, root)) on the same input beside them.
+With one stream the three chains are three CTAs on 148 SMs: these are latency numbers, not a roofline."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONFIGS = {"c1": ("lte_frame_50prb_cellid_125", 8, 125), "c2": ("lte_frame_6prb_cellid_123", 1, 123),
+           "c3": ("lte_frame_100prb_cellid_369", 16, 369)}
+
+
+def _build_blocks_bench(tmp):
+    exe = os.path.join(tmp, "bench_blocks")
+    libdir = os.path.join(ROOT, "gr-ltetrigger_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tools", "bench_blocks.cpp"), "-L", libdir, "-lltetrigger_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+def run(workload, seconds=1.0, device=0, threshold=4.0):
+    import ltetrigger_b200 as lt
+    from oracle import oracle as O
+    fname, decim, cell_id = CONFIGS[workload]
+    frame = np.fromfile(os.path.join(ROOT, "tests", "golden", "test_frames", fname), np.complex64)
+    n = int(round(seconds * 1.92e6)) * decim
+    n -= n % (8 * decim)
+    x = np.tile(frame, -(-n // len(frame)))[:n]
+    out = {"workload": workload, "fixture": fname, "sample_rate_msps": 1.92 * decim, "decim": decim,
+           "seconds_of_signal": n / (1.92e6 * decim)}
+
+    # (a) time to the first "track" message through downlink_trigger_c.work
+    trig = lt.downlink_trigger_c(psr_threshold=threshold, exit_on_success=True, decim=decim, device=device)
+    tracked = []
+    trig.msg_connect("track", tracked.append)
+    trig.work(x[:8 * decim * 1200])                      # warm-up call: CUDA context, tables, first launches
+    trig = lt.downlink_trigger_c(psr_threshold=threshold, exit_on_success=True, decim=decim, device=device)
+    tracked = []
+    trig.msg_connect("track", tracked.append)
+    chunk = 96000 * decim
+    t0 = time.perf_counter()
+    fed = 0
+    while not tracked and fed < n:
+        trig.work(x[fed:fed + chunk])
+        fed += chunk
+    out["first_track"] = {"wall_ms": 1e3 * (time.perf_counter() - t0), "signal_ms_fed": 1e3 * fed / (1.92e6 * decim),
+                          "cell_id": tracked[0]["cell_id"] if tracked else None,
+                          "nof_prb": tracked[0]["nof_prb"] if tracked else None,
+                          "path": "downlink_trigger_c.work, 50 ms passes, host MIB decode included"}
+
+    # (b) sustained throughput through the C ABI with host buffers, 100 ms calls
+    import torch
+    call = 192000 * decim
+    calls = max(1, n // call)
+    host = torch.empty((call,), dtype=torch.complex64, pin_memory=True)
+    host.copy_(torch.from_numpy(x[:call]))
+    eng = lt.Trigger(n_streams=1, decim=decim, psr_threshold=threshold, max_chunk=call, device=device, corr_mode=lt.CORR_FFT)
+    for _ in range(3):
+        eng.process_host_ptr(host.data_ptr(), call * 8, call)
+    t0 = time.perf_counter()
+    cells = 0
+    for _ in range(calls):
+        r = eng.process_host_ptr(host.data_ptr(), call * 8, call)
+        cells += int(((r["flags"] & lt.F_CELL) != 0).sum())
+    dt_sync = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.submit_host_ptr(host.data_ptr(), call * 8, call)
+    for _ in range(calls - 1):
+        eng.submit_host_ptr(host.data_ptr(), call * 8, call)
+        eng.collect()
+    eng.collect()
+    dt_async = time.perf_counter() - t0
+    stage = eng.last_kernel_times()
+    eng.close()
+    out["c_abi"] = {"process_host_msamples_per_s": calls * call / dt_sync / 1e6,
+                    "submit_collect_msamples_per_s": calls * call / dt_async / 1e6,
+                    "ms_per_100ms_call": 1e3 * dt_sync / calls, "cells_tagged": cells,
+                    "last_call_stage_ms": {"frontend": stage[0], "pss_corr": stage[1], "pss_track": stage[2], "sss": stage[3]},
+                    "realtime_factor": (calls * call / dt_sync) / (1.92e6 * decim)}
+
+    # (c) the C++ block adapters (1.92 Msps in: the reference's pss block sits behind the resampler too)
+    y = lt.kernel_decimate(x[None, :], decim)[0] if decim > 1 else x
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = _build_blocks_bench(tmp)
+        path = os.path.join(tmp, "stream_1p92.fc32")
+        y.astype(np.complex64).tofile(path)
+        rows = []
+        for mode, look in (("separate", 1), ("shared", 1), ("shared", 32)):
+            p = subprocess.run([exe, path, "%.3f" % (len(y) / 1.92e6), str(threshold), mode, str(look)], capture_output=True, text=True)
+            rows.append(json.loads(p.stdout.strip().splitlines()[-1]) if p.returncode == 0 and p.stdout.strip() else
+                        {"mode": mode, "lookahead_windows": look, "error": (p.stderr or p.stdout)[-300:]})
+        out["blocks_cpp"] = rows
+
+    # CPU restatement on the same input, all cores
+    O.trigger_run(x[None, :min(n, 8 * decim * 4800)], decim=decim, psr_threshold=threshold, conv_mode=O.CONV_FFT)
+    t0 = time.perf_counter()
+    want = O.trigger_run(x[None, :], decim=decim, psr_threshold=threshold, conv_mode=O.CONV_FFT)
+    dt_cpu = time.perf_counter() - t0
+    out["cpu_port"] = {"msamples_per_s": n / dt_cpu / 1e6, "cores": os.cpu_count(), "kind": "port",
+                       "what": "oracle in reference-class mode (9728-point FFT convolution per window and root), one stream: "
+                               "three chain jobs, so at most three cores work",
+                       "cells_tagged": int(((want["flags"] & O.F_CELL) != 0).sum())}
+    # and as the checker: the GPU engine's records of this stream against the canonical oracle mode
+    eng = lt.Trigger(n_streams=1, decim=decim, psr_threshold=threshold, max_chunk=call, device=device, corr_mode=lt.CORR_FFT)
+    got = eng.run(x[None, :], chunk=call)
+    eng.close()
+    chk = O.trigger_run(x[None, :], decim=decim, psr_threshold=threshold, conv_mode=O.CONV_OS)
+    same = len(got) == len(chk)
+    for f in (chk.dtype.names if same else ()):
+        g, w = got[f], chk[f]
+        same = same and bool(((g.view(np.uint32) == w.view(np.uint32)) | ((g == 0) & (w == 0))).all() if g.dtype.kind == "f" else (g == w).all())
+    out["parity"] = {"records": int(len(chk)), "bit_identical_to_oracle": bool(same),
+                     "cell_ids": sorted(set(got["cell_id"][(got["flags"] & lt.F_CELL) != 0].tolist())), "expected_cell_id": cell_id}
+    return out
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "gr-ltetrigger_b200", "python"))
+    for w in (sys.argv[1:] or ["c1", "c2", "c3"]):
+        print(json.dumps(run(w)), flush=True)

@@ -89,7 +89,8 @@ int main(int argc, char **argv) {
   // a few structured streams: extremes exercise the digit bounds
   for (int i = 0; i < n_in * 2 && S > 2; ++i) { x[(size_t)1 * n_in * 2 + i] = 32767; x[(size_t)2 * n_in * 2 + i] = -32768; }
 
-  void *d_x; short2 *d_tail[2]; float2 *d_y; int8_t *d_b; int *d_err;
+  void *d_x; short2 *d_tail[2]; float2 *d_y; int8_t *d_b; int *d_err; int *d_acc;
+  cudaMalloc(&d_acc, 128 * kTcBRows * 4); cudaMemset(d_acc, 0x7f, 128 * kTcBRows * 4);
   const int m_total = n_in / 16;
   int cap = 1; while (cap < m_total + 64) cap <<= 1;
   cudaMalloc(&d_x, (size_t)S * row_bytes);
@@ -122,7 +123,7 @@ int main(int argc, char **argv) {
     P.tail = d_tail[tail_cur]; P.y_ring = d_y; P.n_base = c0 / 16; P.cap_mask = (unsigned)(cap - 1); P.cap = cap;
     const int rows = (n_chunk + kTcRowSamples - 1) / kTcRowSamples;
     P.tiles_per_stream = (rows + kTcUseful - 1) / kTcUseful; P.total_tiles = P.tiles_per_stream * S;
-    P.btab = d_b; P.c_const = 128 * sumT; P.err = d_err;
+    P.btab = d_b; P.c_const = 128 * sumT; P.err = d_err; P.dbg_acc = c0 == 0 ? d_acc : nullptr;
     const int grid = P.total_tiles < sms ? P.total_tiles : sms;
     switch (G) { case 1: launch<1>(map, P, grid); break; case 2: launch<2>(map, P, grid); break;
                  case 4: launch<4>(map, P, grid); break; default: launch<8>(map, P, grid); }
@@ -145,6 +146,33 @@ int main(int argc, char **argv) {
   int herr = 0; cudaMemcpy(&herr, d_err, 4, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { printf("{\"G\": %d, \"error\": \"%s\", \"watchdog\": %d}\n", G, cudaGetErrorString(e), herr); return 1; }
 
+  // ---- raw accumulators of tile 0 (stream 0, rows -3..60; lanes 0..63 re, 64..127 im) against the host ----
+  long long acc_bad = 0; int acc_first[4] = {-1, -1, 0, 0};
+  {
+    std::vector<int> acc(128 * kTcBRows);
+    cudaMemcpy(acc.data(), d_acc, acc.size() * 4, cudaMemcpyDeviceToHost);
+    auto digit = [&](int t, int v) {
+      int d0 = ((t + 128) & 255) - 128; int t1 = (t - d0) >> 8; int d1 = ((t1 + 128) & 255) - 128; int t2 = (t1 - d1) >> 8;
+      return v == 0 ? d0 : v == 1 ? d1 : v == 2 ? t2 : 0;
+    };
+    for (int lanei = 0; lanei < 128; ++lanei) {
+      const int comp = lanei >> 6, row = (lanei & 63) - kTcHalo;
+      for (int col = 0; col < 196; ++col) {
+        const int u = col >> 2, v = col & 3;
+        long long want = 0;
+        for (int p = 0; p < 256; ++p) {
+          const int j = 16 * u - p;
+          if (j < 0 || j > 524) continue;
+          const long long nidx = (long long)row * 256 + p;
+          const int xv = nidx >= 0 && nidx < n_in ? x[2 * nidx + comp] : 0;
+          const int lo = (xv & 255) - 128, hi = xv >> 8;
+          want += (long long)lo * (v <= 2 ? digit(T[j], v) : 0) + (long long)hi * (v >= 1 ? digit(T[j], v - 1) : 0);
+        }
+        const int got = acc[lanei * kTcBRows + col];
+        if ((long long)got != want) { if (!acc_bad) { acc_first[0] = lanei; acc_first[1] = col; acc_first[2] = got; acc_first[3] = (int)want; } acc_bad++; }
+      }
+    }
+  }
   // ---- exact check against int64 on the host ----
   std::vector<float2> y((size_t)S * cap);
   cudaMemcpy(y.data(), d_y, y.size() * 8, cudaMemcpyDeviceToHost);
@@ -179,9 +207,9 @@ int main(int argc, char **argv) {
     cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
   }
   e = cudaDeviceSynchronize();
-  printf("{\"G\": %d, \"streams\": %d, \"n_in\": %d, \"chunks\": %d, \"checked\": %lld, \"mismatches\": %lld, \"first_bad\": [%d, %d, %g, %g], "
+  printf("{\"G\": %d, \"acc_tile0_mismatches\": %lld, \"acc_first_bad\": [%d, %d, %d, %d], \"streams\": %d, \"n_in\": %d, \"chunks\": %d, \"checked\": %lld, \"mismatches\": %lld, \"first_bad\": [%d, %d, %g, %g], "
          "\"ms\": %.4f, \"input_Gsamples_per_s\": %.1f, \"GB_per_s\": %.1f, \"status\": \"%s\"}\n",
-         G, S, n_in, chunks, checked, bad, first_bad_s, first_bad_k, gb, wb, ms, ms > 0 ? (double)S * n_in / ms / 1e6 : 0.0,
+         G, acc_bad, acc_first[0], acc_first[1], acc_first[2], acc_first[3], S, n_in, chunks, checked, bad, first_bad_s, first_bad_k, gb, wb, ms, ms > 0 ? (double)S * n_in / ms / 1e6 : 0.0,
          ms > 0 ? (double)S * n_in * 4 / ms / 1e6 : 0.0, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
   return bad ? 3 : 0;
 }
