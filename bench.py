@@ -63,6 +63,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-formats", action="store_true", help="skip the e2e legs on the other wire formats")
+    ap.add_argument("--workload", default="c5", choices=["c5", "c1", "c2", "c3"],
+                    help="c5 (default): BASELINE's batched shard, the metric's configuration; c1/c2/c3: the single-stream "
+                         "configurations (latency to first track, C-ABI and block-path throughput; tools/bench_single.py)")
     ap.add_argument("--frontend", default="fp32", choices=["fp32", "tc"],
                     help="fp32: canonical FFMA2 decimator; tc: exact-integer tensor-core front end (sc16, D=16)")
     ap.add_argument("--pipeline", default="overlap", choices=["overlap", "serial"],
@@ -193,6 +196,23 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
         run_reference(a, rank, world)
+        return
+    if a.workload != "c5":
+        # single-stream configurations: replicas only beyond one GPU, so rank 0 alone runs them
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_single
+            r = bench_single.run(a.workload, device=local_rank)
+            line = {"metric": "PSS+SSS search Msamples/s", "value": r["c_abi"]["submit_collect_msamples_per_s"], "unit": "Msamples/s",
+                    "n_gpus": 1, "steps": 1, "warmup": 3, "ms_per_step": r["c_abi"]["ms_per_100ms_call"], "higher_is_better": True,
+                    "scaling": "replicas only", "vs_baseline": None, "dtype": "f32", "data": "reference test frame, tiled",
+                    "config": {"workload": "%s: %s @ %.2f Msps, one stream" % (a.workload, r["fixture"], r["sample_rate_msps"])},
+                    "e2e": {"value": r["c_abi"]["submit_collect_msamples_per_s"], "unit": "Msamples/s",
+                            "api": "ltb_trigger_submit_host + ltb_trigger_collect, host buffers"},
+                    "cpu_baseline": {"value": r["cpu_port"]["msamples_per_s"], "unit": "Msamples/s", "cores": r["cpu_port"]["cores"],
+                                     "kind": "port", "sample": r["cpu_port"]["what"]},
+                    "single_stream": r}
+            print(json.dumps(line), flush=True)
         return
 
     import torch

@@ -306,30 +306,17 @@ int launch_frontend(int decim, const void *d_iq, long long stride, int n_streams
   return LTB_SUCCESS;
 }
 
-// ---- LTB_FRONTEND_TC_INT: integer tensor-core front end (sc16, decim 16) ----------------------------------
-#ifndef LTB_TC_G
-#define LTB_TC_G 1            // k-steps per accumulator column offset (ltb_tc_frontend.cuh); LTB_TC_G env overrides
-#endif
+// ---- LTB_FRONTEND_TC_INT: integer tensor-core front end (sc16 / sc8, decim 16) ----------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
-int g_tc_g = 0;
-int8_t *g_tc_btab[64] = {nullptr};
+int8_t *g_tc_btab[64][3] = {{nullptr}};          // per device and input format
 long long g_tc_sum_t = 0;
-
-int tc_group() {
-  if (g_tc_g) return g_tc_g;
-  int g = LTB_TC_G;
-  if (const char *e = std::getenv("LTB_TC_G")) g = std::atoi(e);
-  if (g != 1 && g != 2 && g != 4 && g != 8) g = LTB_TC_G;
-  g_tc_g = g;
-  return g;
-}
 
 int ensure_tc_tables(int device) {
   std::lock_guard<std::mutex> lk(g_const_mu);
-  if (g_tc_btab[device]) return LTB_SUCCESS;
+  if (g_tc_btab[device][LTB_FMT_SC16]) return LTB_SUCCESS;
   if (!g_encode_tiled) {
     cudaDriverEntryPointQueryResult qres;
     void *fn = nullptr;
@@ -337,34 +324,35 @@ int ensure_tc_tables(int device) {
       return fail(LTB_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
     g_encode_tiled = (EncodeTiledFn)fn;
   }
-  const int G = tc_group();
-  const std::vector<int8_t> tab = make_tc_btab(G);
   make_tc_taps(&g_tc_sum_t);
-  if (tab.empty()) return fail(LTB_ERROR, "decimator taps do not fit three base-256 digits");
-  int8_t *d = nullptr;
-  LTB_CUDA(cudaMalloc(&d, tab.size()));
-  LTB_CUDA(cudaMemcpy(d, tab.data(), tab.size(), cudaMemcpyHostToDevice));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(1)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(2)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(4)));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(8)));
-  g_tc_btab[device] = d;
+  for (int fmt : {LTB_FMT_SC16, LTB_FMT_SC8}) {
+    const std::vector<int8_t> tab = make_tc_btab(fmt);
+    if (tab.empty()) return fail(LTB_ERROR, "decimator taps do not fit three base-256 digits");
+    int8_t *d = nullptr;
+    LTB_CUDA(cudaMalloc(&d, tab.size()));
+    LTB_CUDA(cudaMemcpy(d, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+    g_tc_btab[device][fmt] = d;
+  }
+  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<LTB_FMT_SC16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<LTB_FMT_SC8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
   return LTB_SUCCESS;
 }
 
-// n_in new sc16 samples per stream (multiple of 128) -> n_in / 16 search-rate samples in y_ring; tail_old holds the
-// 768 samples before the chunk, tail_new receives the last 768 for the next call
-int launch_frontend_tc(int device, const void *d_iq, long long stride, int n_streams, int n_in, const short2 *tail_old,
-                       short2 *tail_new, float2 *y_ring, long long n_base, unsigned mask, int cap, int *d_err,
+// n_in new integer samples per stream (multiple of 128) -> n_in / 16 search-rate samples in y_ring; tail_old holds the
+// 768 raw samples before the chunk, tail_new receives the last 768 for the next call
+int launch_frontend_tc(int device, int fmt, const void *d_iq, long long stride, int n_streams, int n_in, const void *tail_old,
+                       void *tail_new, float2 *y_ring, long long n_base, unsigned mask, int cap, int *d_err,
                        cudaStream_t st, int *launches) {
   if ((reinterpret_cast<uintptr_t>(d_iq) | (uintptr_t)stride) & 15u)
     return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT needs a 16-byte aligned input pointer and row stride (TMA)");
+  const int bps = tc_sample_bytes(fmt);
   const int full_rows = n_in / kTcRowSamples;
   CUtensorMap map;
-  const cuuint64_t gdim[3] = {1024, (cuuint64_t)(full_rows > 0 ? full_rows : 1), (cuuint64_t)n_streams};
-  const cuuint64_t gstr[2] = {1024, (cuuint64_t)stride};
+  const cuuint64_t row_bytes = (cuuint64_t)kTcRowSamples * bps;
+  const cuuint64_t gdim[3] = {row_bytes, (cuuint64_t)(full_rows > 0 ? full_rows : 1), (cuuint64_t)n_streams};
+  const cuuint64_t gstr[2] = {row_bytes, (cuuint64_t)stride};
   const cuuint32_t box[3] = {256, (cuuint32_t)kTcTileRows, 1}, estr[3] = {1, 1, 1};
-  if (n_streams > 1 && stride < (long long)n_in * 4) return fail(LTB_ERROR_INVALID_INPUTS, "row stride smaller than a row");
+  if (n_streams > 1 && stride < (long long)n_in * bps) return fail(LTB_ERROR_INVALID_INPUTS, "row stride smaller than a row");
   const CUresult r = g_encode_tiled(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(d_iq), gdim, gstr, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -377,16 +365,16 @@ int launch_frontend_tc(int device, const void *d_iq, long long stride, int n_str
   const long long total = (long long)P.tiles_per_stream * n_streams;
   if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator tiles in one call");
   P.total_tiles = (int)total;
-  P.btab = g_tc_btab[device]; P.c_const = 128 * g_tc_sum_t; P.err = d_err; P.dbg_acc = nullptr;
+  P.btab = g_tc_btab[device][fmt]; P.c_const = fmt == LTB_FMT_SC16 ? 128 * g_tc_sum_t : 0; P.err = d_err; P.dbg_acc = nullptr;
   const int sms = g_sm_count[device] > 0 ? g_sm_count[device] : 148;
   const int grid = P.total_tiles < sms ? P.total_tiles : sms;
-  switch (tc_group()) {
-    case 1: decimate_tc_kernel<1><<<grid, kTcThreads, tc_smem_bytes(1), st>>>(map, P); break;
-    case 2: decimate_tc_kernel<2><<<grid, kTcThreads, tc_smem_bytes(2), st>>>(map, P); break;
-    case 4: decimate_tc_kernel<4><<<grid, kTcThreads, tc_smem_bytes(4), st>>>(map, P); break;
-    default: decimate_tc_kernel<8><<<grid, kTcThreads, tc_smem_bytes(8), st>>>(map, P); break;
+  if (fmt == LTB_FMT_SC16) {
+    decimate_tc_kernel<LTB_FMT_SC16><<<grid, kTcThreads, tc_smem_bytes(), st>>>(map, P);
+    tc_tail_kernel<LTB_FMT_SC16><<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);
+  } else {
+    decimate_tc_kernel<LTB_FMT_SC8><<<grid, kTcThreads, tc_smem_bytes(), st>>>(map, P);
+    tc_tail_kernel<LTB_FMT_SC8><<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);
   }
-  tc_tail_kernel<<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);
   *launches += 2;
   return LTB_SUCCESS;
 }
@@ -455,7 +443,7 @@ struct ltb_trigger {
   float2 *d_hf = nullptr;
   float2 *d_tail[2] = {nullptr, nullptr};
   int tail_cur = 0;
-  short2 *d_tc_tail[2] = {nullptr, nullptr};   // LTB_FRONTEND_TC_INT: raw history, [n_streams][768]
+  void *d_tc_tail[2] = {nullptr, nullptr};     // LTB_FRONTEND_TC_INT: raw history, [n_streams][768] samples
   int *d_tc_err = nullptr;
   float2 *d_cexp = nullptr;
   float *d_branch_taps = nullptr;         // [decim][33], decimate_any_kernel
@@ -477,8 +465,8 @@ int trigger_zero_state(ltb_trigger *t) {
   LTB_CUDA(cudaMemsetAsync(t->d_tail[0], 0, sizeof(float2) * (size_t)S * kTailCap, t->stream));
   LTB_CUDA(cudaMemsetAsync(t->d_tail[1], 0, sizeof(float2) * (size_t)S * kTailCap, t->stream));
   if (t->d_tc_tail[0]) {
-    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[0], 0, sizeof(short2) * (size_t)S * kTcTailSamples, t->stream));
-    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[1], 0, sizeof(short2) * (size_t)S * kTcTailSamples, t->stream));
+    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[0], 0, 4 * (size_t)S * kTcTailSamples, t->stream));
+    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[1], 0, 4 * (size_t)S * kTcTailSamples, t->stream));
     LTB_CUDA(cudaMemsetAsync(t->d_tc_err, 0, sizeof(int), t->stream));
   }
   LTB_CUDA(cudaMemcpyAsync(t->d_thr, t->h_thr.data(), sizeof(float) * t->n_chains, cudaMemcpyHostToDevice, t->stream));
@@ -536,7 +524,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   LTB_CUDA(cudaEventRecord(sl.ev0, t->stream));
   int rc;
   if (c.frontend_mode == LTB_FRONTEND_TC_INT)
-    rc = launch_frontend_tc(c.device, d_iq, stride, S, (int)n_samples, t->d_tc_tail[t->tail_cur], t->d_tc_tail[t->tail_cur ^ 1],
+    rc = launch_frontend_tc(c.device, c.input_format, d_iq, stride, S, (int)n_samples, t->d_tc_tail[t->tail_cur], t->d_tc_tail[t->tail_cur ^ 1],
                             t->d_y, n_base, t->cap_mask, t->cap, t->d_tc_err, t->stream, &launches);
   else
     rc = launch_frontend_fmt(c.input_format, c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
@@ -635,8 +623,8 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
       (c.pipeline != LTB_PIPE_OVERLAP && c.pipeline != LTB_PIPE_SERIAL) ||
       (c.frontend_mode != LTB_FRONTEND_FP32 && c.frontend_mode != LTB_FRONTEND_TC_INT))
     return fail(LTB_ERROR_INVALID_INPUTS, "invalid trigger configuration");
-  if (c.frontend_mode == LTB_FRONTEND_TC_INT && (c.input_format != LTB_FMT_SC16 || c.decim != 16))
-    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT is available for sc16 input at decim = 16");
+  if (c.frontend_mode == LTB_FRONTEND_TC_INT && (c.input_format == LTB_FMT_FC32 || c.decim != 16))
+    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT is available for sc16 / sc8 input at decim = 16");
   if (c.root_mask == 0) c.root_mask = 7;
   if (c.track_after <= 0) c.track_after = 16;
   if (c.track_every <= 0) c.track_every = 8;
@@ -707,8 +695,8 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   LTB_CUDA_T(cudaMalloc(&t->d_tail[0], sizeof(float2) * (size_t)S * kTailCap));
   LTB_CUDA_T(cudaMalloc(&t->d_tail[1], sizeof(float2) * (size_t)S * kTailCap));
   if (c.frontend_mode == LTB_FRONTEND_TC_INT) {
-    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[0], sizeof(short2) * (size_t)S * kTcTailSamples));
-    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[1], sizeof(short2) * (size_t)S * kTcTailSamples));
+    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[0], 4 * (size_t)S * kTcTailSamples));
+    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[1], 4 * (size_t)S * kTcTailSamples));
     LTB_CUDA_T(cudaMalloc(&t->d_tc_err, sizeof(int)));
   }
   if (c.keep_halfframes) LTB_CUDA_T(cudaMalloc(&t->d_hf, sizeof(float2) * kHalf * (size_t)t->n_chains * t->w_cap));
@@ -1061,31 +1049,33 @@ int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, 
   return rc;
 }
 
-int ltb_kernel_decimate_tc_host(int device, const int16_t *x, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y) {
-  if (!x || !y || n_streams <= 0 || n_in <= 0 || (n_in % 128) != 0 || chunk <= 0 || (chunk % 128) != 0)
-    return fail(LTB_ERROR_INVALID_INPUTS, "n_in and chunk must be positive multiples of 128");
+int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y) {
+  if (!x || !y || n_streams <= 0 || n_in <= 0 || (n_in % 128) != 0 || chunk <= 0 || (chunk % 128) != 0 ||
+      (fmt != LTB_FMT_SC16 && fmt != LTB_FMT_SC8))
+    return fail(LTB_ERROR_INVALID_INPUTS, "integer input, n_in and chunk positive multiples of 128");
   if (ltb_device_count() <= device || device < 0) return fail(LTB_ERROR, "no such CUDA device");
   LTB_CUDA(cudaSetDevice(device));
   int rc = ensure_constants(device);
   if (!rc) rc = ensure_tc_tables(device);
   if (rc) return rc;
+  const int bps = tc_sample_bytes(fmt);
   const int m = (int)(n_in / 16);
   const int cap = next_pow2(m + 8);
-  const size_t in_row = (size_t)n_in * 4, dev_row = (in_row + 127) / 128 * 128;
-  void *d_in = nullptr; float2 *d_y = nullptr; short2 *d_t[2] = {nullptr, nullptr}; int *d_err = nullptr;
+  const size_t in_row = (size_t)n_in * bps, dev_row = (in_row + 127) / 128 * 128;
+  void *d_in = nullptr; float2 *d_y = nullptr; void *d_t[2] = {nullptr, nullptr}; int *d_err = nullptr;
   cudaError_t e = cudaMalloc(&d_in, dev_row * n_streams);
   if (e == cudaSuccess) e = cudaMalloc(&d_y, sizeof(float2) * (size_t)n_streams * cap);
-  if (e == cudaSuccess) e = cudaMalloc(&d_t[0], sizeof(short2) * (size_t)n_streams * kTcTailSamples);
-  if (e == cudaSuccess) e = cudaMalloc(&d_t[1], sizeof(short2) * (size_t)n_streams * kTcTailSamples);
+  if (e == cudaSuccess) e = cudaMalloc(&d_t[0], 4 * (size_t)n_streams * kTcTailSamples);
+  if (e == cudaSuccess) e = cudaMalloc(&d_t[1], 4 * (size_t)n_streams * kTcTailSamples);
   if (e == cudaSuccess) e = cudaMalloc(&d_err, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(d_err, 0, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(d_t[0], 0, sizeof(short2) * (size_t)n_streams * kTcTailSamples);
+  if (e == cudaSuccess) e = cudaMemset(d_t[0], 0, 4 * (size_t)n_streams * kTcTailSamples);
   if (e == cudaSuccess) e = cudaMemcpy2D(d_in, dev_row, x, in_row, in_row, n_streams, cudaMemcpyHostToDevice);
   int cur = 0;
   for (int64_t c0 = 0; c0 < n_in && e == cudaSuccess && !rc; c0 += chunk) {
     const int nc = (int)(n_in - c0 < chunk ? n_in - c0 : chunk);
     int launches = 0;
-    rc = launch_frontend_tc(device, (const char *)d_in + c0 * 4, (long long)dev_row, n_streams, nc, d_t[cur], d_t[cur ^ 1], d_y,
+    rc = launch_frontend_tc(device, fmt, (const char *)d_in + c0 * bps, (long long)dev_row, n_streams, nc, d_t[cur], d_t[cur ^ 1], d_y,
                             c0 / 16, (unsigned)(cap - 1), cap, d_err, 0, &launches);
     cur ^= 1;
     e = cudaGetLastError();

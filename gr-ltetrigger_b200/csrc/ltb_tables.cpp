@@ -137,10 +137,10 @@ std::vector<int32_t> make_tc_taps(long long *sum_t) {
   return T;
 }
 
-std::vector<int8_t> make_tc_btab(int G) {
+std::vector<int8_t> make_tc_btab(int fmt) {
   constexpr int kRows = 208, kTile = kRows * 128;
   const std::vector<int32_t> T = make_tc_taps(nullptr);
-  std::vector<int8_t> tab((size_t)((G + 3) / 4) * kTile, 0);
+  std::vector<int8_t> tab((size_t)kTile, 0);
   auto sw_off = [](int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); };
   auto digit = [](int t, int v, bool *ok) {            // balanced base-256 digits, v = 0..2
     const int d0 = ((t + 128) & 255) - 128, t1 = (t - d0) >> 8;
@@ -148,21 +148,23 @@ std::vector<int8_t> make_tc_btab(int G) {
     if (t2 < -128 || t2 > 127) *ok = false;
     return v == 0 ? d0 : v == 1 ? d1 : v == 2 ? t2 : 0;
   };
+  auto tap = [&](int j) { return (j >= 0 && j < (int)T.size()) ? T[j] : 0; };
   bool ok = true;
-  for (int i = 0; i < G; ++i)
-    for (int n = 0; n < kRows; ++n) {
-      const int d = n / 4 - i, v = n % 4;
-      if (d < 0 || d > 33) continue;
-      for (int pp = 0; pp < 16; ++pp) {
-        const int j = 16 * d - pp;
-        const int t = (j >= 0 && j < (int)T.size()) ? T[j] : 0;
-        const int b_lo = v <= 2 ? digit(t, v, &ok) : 0, b_hi = v >= 1 ? digit(t, v - 1, &ok) : 0;
-        const int kb = (i & 3) * 32 + 2 * pp;
-        int8_t *tile = tab.data() + (size_t)(i >> 2) * kTile;
-        tile[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)b_lo;
-        tile[sw_off(n, (kb + 1) >> 4) + ((kb + 1) & 15)] = (int8_t)b_hi;
+  const bool sc16 = fmt == 1;
+  for (int n = 0; n < kRows; ++n) {
+    const int d = n / 4, v = n % 4;
+    if (d > (sc16 ? 33 : 34)) continue;
+    for (int pp = 0; pp < (sc16 ? 16 : 32); ++pp) {
+      const int t = tap(16 * d - pp);
+      if (sc16) {
+        const int kb = 2 * pp;
+        tab[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)(v <= 2 ? digit(t, v, &ok) : 0);
+        tab[sw_off(n, (kb + 1) >> 4) + ((kb + 1) & 15)] = (int8_t)(v >= 1 ? digit(t, v - 1, &ok) : 0);
+      } else {
+        tab[sw_off(n, pp >> 4) + (pp & 15)] = (int8_t)(v <= 2 ? digit(t, v, &ok) : 0);
       }
     }
+  }
   if (!ok) tab.clear();                                 // a tap that needs a fourth digit: never for these taps
   return tab;
 }

@@ -18,11 +18,11 @@ std::vector<float> make_decim_taps(int decim);
 std::vector<float> make_decim_branch_taps(int decim);
 
 // LTB_FRONTEND_TC_INT (csrc/ltb_tc_frontend.cuh): the D = 16 taps quantised to T[j] = rint(taps[j] * 2^27), and
-// the tap tables of the tensor-core kernel in its shared-memory image (K-major, 128-byte swizzle): k-slice i of
-// row 4 d + v holds digit v (lo byte) / digit v - 1 (hi byte) of T[16 (d - i) - p'], p' = 0..15.  G = k-steps
-// sharing one accumulator column offset.  sum_t receives sum_j T[j].
+// the tap table of the tensor-core kernel in its shared-memory image ([208 rows][128 B], K-major, 128-byte
+// swizzle, the first 32 bytes of a row used).  sc16 (fmt 1): row 4 d + v holds digit v (lo byte) / digit v - 1
+// (hi byte) of T[16 d - p'], p' = 0..15; sc8 (fmt 2): digit v of T[16 d - p'], p' = 0..31.  sum_t receives sum_j T[j].
 std::vector<int32_t> make_tc_taps(long long *sum_t);
-std::vector<int8_t> make_tc_btab(int G);
+std::vector<int8_t> make_tc_btab(int fmt);
 
 struct SssTables {
   int32_t c0[31], c1[31], s_tilde[31], z_tilde[31];

@@ -16,6 +16,18 @@
 namespace gr {
 namespace ltetrigger {
 
+// Opt-in sharing of one GPU engine by the three chains of a hier block (LTB_SHARE_ENGINE=1 in the environment
+// while the blocks are constructed, e.g. set by python/downlink_trigger_c.py around its three pss / sss
+// constructors).  The reference's Python hier block makes pss(0), pss(1), pss(2) with the same parameters on
+// the same input (python/downlink_trigger_c.py:27-45) and has no handle to pass between them, so the wrappers
+// group by construction order: a pss block joins the open group if its parameters match and its N_id_2 is not
+// taken yet, otherwise it opens a new one; an sss block joins the most recent group whose N_id_2 has no sss.
+// Without the variable every block owns its engine (three host-to-device copies of the same stream).
+struct b200_engine_registry {
+  static ltetrigger_b200::engine_group::sptr join_pss(int N_id_2, float psr_threshold, int track_after, int track_every);
+  static ltetrigger_b200::engine_group::sptr join_sss(int N_id_2);
+};
+
 class pss_b200_impl : public pss {
  public:
   pss_b200_impl(int N_id_2, float psr_threshold, int track_after, int track_every);
@@ -33,6 +45,7 @@ class pss_b200_impl : public pss {
                    gr_vector_void_star &output_items);
 
  private:
+  static ltetrigger_b200::pss::sptr make_core(int N_id_2, float psr_threshold, int track_after, int track_every);
   static const pmt::pmt_t tracking_lost_tag_key;
   ltetrigger_b200::pss::sptr d_core;
 };

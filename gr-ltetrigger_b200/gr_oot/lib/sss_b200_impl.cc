@@ -3,6 +3,8 @@
 
 #include <gnuradio/io_signature.h>
 
+#include "pss_b200_impl.h"
+
 namespace gr {
 namespace ltetrigger {
 
@@ -14,9 +16,14 @@ sss::sptr sss::make(int N_id_2) { return gnuradio::get_initial_sptr(new sss_b200
 
 sss_b200_impl::sss_b200_impl(int N_id_2)
     : gr::sync_block("sss", gr::io_signature::make(1, 1, sizeof(gr_complex)), gr::io_signature::make(1, 1, sizeof(gr_complex))),
-      d_core(ltetrigger_b200::sss::make(N_id_2)) {   // throws "Error initializing SSS SYNC" (lib/sss_impl.cc:63-70)
+      d_core(make_core(N_id_2)) {                    // throws "Error initializing SSS SYNC" (lib/sss_impl.cc:63-70)
   set_tag_propagation_policy(TPP_ALL_TO_ALL);        // :61
   set_output_multiple(d_core->output_multiple());    // :72
+}
+
+ltetrigger_b200::sss::sptr sss_b200_impl::make_core(int N_id_2) {
+  ltetrigger_b200::engine_group::sptr g = b200_engine_registry::join_sss(N_id_2);   // LTB_SHARE_ENGINE=1: see pss_b200_impl.h
+  return g ? ltetrigger_b200::sss::make(N_id_2, g) : ltetrigger_b200::sss::make(N_id_2);
 }
 
 sss_b200_impl::~sss_b200_impl() {}

@@ -19,6 +19,7 @@ class sss_b200_impl : public sss {
   int work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items);
 
  private:
+  static ltetrigger_b200::sss::sptr make_core(int N_id_2);
   static const pmt::pmt_t cell_id_tag_key, cp_type_tag_key, tracking_lost_tag_key;
   ltetrigger_b200::sss::sptr d_core;
   std::vector<gr::tag_t> d_tags;

@@ -124,7 +124,7 @@ def _load(path):
     L.ltb_table_fft1024_twiddles.argtypes = [fp, fp]
     L.ltb_table_os_filter.argtypes = [C.c_int, fp, fp]
     L.ltb_kernel_decimate_host.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp]
-    L.ltb_kernel_decimate_tc_host.argtypes = [C.c_int, vp, C.c_int, C.c_int64, C.c_int64, vp]
+    L.ltb_kernel_decimate_tc_host.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, vp]
     L.ltb_table_pss_taps.argtypes = [C.c_int, fp, fp]
     L.ltb_table_decim_taps.argtypes = [C.c_int, fp, C.c_int]
     L.ltb_table_sss.argtypes = [C.c_int, ip, ip, ip, ip, ip]

@@ -161,12 +161,14 @@ def kernel_decimate(x, decim, fmt=A.FMT_FC32, device=0, L=None):
 
 
 def kernel_decimate_tc(iq, chunk=None, device=0):
-    """LTB_FRONTEND_TC_INT at kernel level: iq [n_streams, n, 2] int16 -> [n_streams, n // 16] complex64, the
-    input fed in calls of `chunk` samples (multiple of 128; default: one call)."""
-    iq = np.ascontiguousarray(iq, np.int16)
+    """LTB_FRONTEND_TC_INT at kernel level: iq [n_streams, n, 2] int16 (sc16) or int8 (sc8) ->
+    [n_streams, n // 16] complex64, the input fed in calls of `chunk` samples (multiple of 128; default: one call)."""
+    iq = np.asarray(iq)
+    fmt = A.FMT_SC8 if iq.dtype == np.int8 else A.FMT_SC16
+    iq = np.ascontiguousarray(iq, A.FMT_DTYPE[fmt])
     s, n = iq.shape[0], iq.shape[1]
     y = np.zeros((s, n // 16), np.complex64)
-    A.check(A.lib().ltb_kernel_decimate_tc_host(device, iq.ctypes.data, s, n, chunk or n, y.ctypes.data),
+    A.check(A.lib().ltb_kernel_decimate_tc_host(device, iq.ctypes.data, fmt, s, n, chunk or n, y.ctypes.data),
             "ltb_kernel_decimate_tc_host")
     return y
 

@@ -62,7 +62,7 @@ extern "C" {
 #define LTB_FRONTEND_TC_INT 1      /* exact integer arithmetic on the tensor cores (tcgen05.mma kind::i8): taps
                                       quantised to three balanced base-256 digits, the int16 / int8 samples are
                                       their own digits, int32 accumulation in TMEM, one rounding to float32 per
-                                      output.  sc16 / sc8 input at decim = 16 only */
+                                      output.  sc16 / sc8 input at decim = 16 only; needs 16-byte aligned rows */
 
 /* how the stages of consecutive calls are scheduled (results are identical) */
 #define LTB_PIPE_OVERLAP 0         /* with two calls in flight (submit/collect), the per-chain track + SSS kernels of
@@ -249,10 +249,11 @@ LTB_API int ltb_kernel_pss_corr_fft_host(int device, const ltb_cf *x, int n_stre
 LTB_API int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in,
                                      int decim, ltb_cf *y);
 
-/* LTB_FRONTEND_TC_INT at kernel level: decimate-by-16 of n_streams host streams of n_in interleaved int16 I/Q
- * samples, fed to the tensor-core kernel in calls of `chunk` samples (both multiples of 128; the raw history
- * is carried between the calls as the engine does); y: [n_streams][n_in / 16]. */
-LTB_API int ltb_kernel_decimate_tc_host(int device, const int16_t *x, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y);
+/* LTB_FRONTEND_TC_INT at kernel level: decimate-by-16 of n_streams host streams of n_in interleaved int16
+ * (fmt LTB_FMT_SC16) or int8 (LTB_FMT_SC8) I/Q samples, fed to the tensor-core kernel in calls of `chunk`
+ * samples (both multiples of 128; the raw history is carried between the calls as the engine does);
+ * y: [n_streams][n_in / 16]. */
+LTB_API int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y);
 
 #ifdef LTB_DEBUG
 /* Only in the debug build (make -C gr-ltetrigger_b200 debug -> lib/libltetrigger_b200_debug.so, -DLTB_DEBUG);

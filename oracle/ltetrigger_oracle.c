@@ -262,7 +262,7 @@ int64_t orc_decimate_fast(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
  *   y[k] = (float)A[k] * 2^-42             one rounding (2^-27 for the taps, 2^-15 for the sc16 scale)
  * Exact arithmetic does not depend on evaluation order, so any correct integer evaluation -- this loop, or
  * int8 digit products accumulated in int32 and recombined -- gives the same bits. */
-int64_t orc_decimate_tcint_sc16(const int16_t *iq, int64_t n_in, orc_cf *y)
+static int64_t tcint_run(const int16_t *iq16, const int8_t *iq8, int64_t n_in, float scale, orc_cf *y)
 {
   const int decim = 16;
   float taps[4096];
@@ -275,15 +275,28 @@ int64_t orc_decimate_tcint_sc16(const int16_t *iq, int64_t n_in, orc_cf *y)
     int64_t are = 0, aim = 0;
     const int64_t top = k * decim;
     const int jmax = top < ntaps - 1 ? (int)top : ntaps - 1;      /* zero history before the stream */
-    const int16_t *xp = iq + 2 * top;
-    for (int j = 0; j <= jmax; j++) {
-      are += (int64_t)T[j] * xp[-2 * j];
-      aim += (int64_t)T[j] * xp[-2 * j + 1];
+    if (iq16) {
+      const int16_t *xp = iq16 + 2 * top;
+      for (int j = 0; j <= jmax; j++) { are += (int64_t)T[j] * xp[-2 * j]; aim += (int64_t)T[j] * xp[-2 * j + 1]; }
+    } else {
+      const int8_t *xp = iq8 + 2 * top;
+      for (int j = 0; j <= jmax; j++) { are += (int64_t)T[j] * xp[-2 * j]; aim += (int64_t)T[j] * xp[-2 * j + 1]; }
     }
-    y[k].re = (float)are * 2.2737367544323206e-13f;
-    y[k].im = (float)aim * 2.2737367544323206e-13f;
+    y[k].re = (float)are * scale;
+    y[k].im = (float)aim * scale;
   }
   return n_out;
+}
+
+int64_t orc_decimate_tcint_sc16(const int16_t *iq, int64_t n_in, orc_cf *y)
+{
+  return tcint_run(iq, NULL, n_in, 2.2737367544323206e-13f /* 2^-42 */, y);
+}
+
+/* the same for int8 I/Q: y[k] = (float)A[k] * 2^-34 (2^-27 for the taps, 2^-7 for the sc8 scale) */
+int64_t orc_decimate_tcint_sc8(const int8_t *iq, int64_t n_in, orc_cf *y)
+{
+  return tcint_run(NULL, iq, n_in, 5.8207660913467407e-11f /* 2^-34 */, y);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1168,9 +1181,11 @@ typedef struct {
 static void trig_frontend(int s, void *arg)
 {
   trig_t *t = (trig_t *)arg;
-  if ((t->conv_mode & ORC_FRONT_TCINT) && t->fmt == 1 && t->decim == 16) {   /* integer front end */
+  if ((t->conv_mode & ORC_FRONT_TCINT) && t->fmt != 0 && t->decim == 16) {   /* integer front end */
     t->ys[s] = malloc(sizeof(orc_cf) * t->n_out);
-    if (orc_decimate_tcint_sc16((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->ys[s]) < 0) t->fail = 1;
+    int64_t rc = t->fmt == 1 ? orc_decimate_tcint_sc16((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->ys[s])
+                             : orc_decimate_tcint_sc8((const int8_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->ys[s]);
+    if (rc < 0) t->fail = 1;
     return;
   }
   orc_cf *x = malloc(sizeof(orc_cf) * t->n_in);

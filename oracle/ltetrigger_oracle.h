@@ -43,7 +43,7 @@ typedef struct { float re, im; } orc_cf;
 
 enum { ORC_CONV_DIRECT = 0, ORC_CONV_FFT = 1, ORC_CONV_OS = 2 };
 #define ORC_FRAME_TDD 0x100    /* or-ed into conv_mode of orc_chain_run / orc_trigger_run: TDD SSS position */
-#define ORC_FRONT_TCINT 0x200  /* or-ed into conv_mode of orc_trigger_run: sc16 input at decim 16 goes through the exact
+#define ORC_FRONT_TCINT 0x200  /* or-ed into conv_mode of orc_trigger_run: sc16 / sc8 input at decim 16 goes through the exact
                                   integer front end (orc_decimate_tcint_sc16) instead of the float32 decimator */
 #define ORC_OS_STEP 896        /* outputs per 1024-point overlap-save block (ORC_CONV_OS) */
 
@@ -148,6 +148,7 @@ int      orc_sss_work(orc_sss *, const orc_cf *in, int tag_lost, orc_cf *out, or
 /* LTB_FRONTEND_TC_INT restated: exact integer decimate-by-16 of interleaved int16 I/Q (zero history), one
  * rounding per output.  Returns the number of outputs, -1 on error. */
 int64_t orc_decimate_tcint_sc16(const int16_t *iq, int64_t n_in, orc_cf *y);
+int64_t orc_decimate_tcint_sc8(const int8_t *iq, int64_t n_in, orc_cf *y);
 
 /* ---- whole chains ------------------------------------------------------------ */
 /* pss(N_id_2) -> sss(N_id_2) over one search-rate stream y[0..n) (GR zero history before it),

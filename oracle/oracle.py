@@ -61,6 +61,8 @@ def lib():
         L.orc_decimate_fast.restype = C.c_int64
         L.orc_decimate_tcint_sc16.argtypes = [vp, C.c_int64, vp]
         L.orc_decimate_tcint_sc16.restype = C.c_int64
+        L.orc_decimate_tcint_sc8.argtypes = [vp, C.c_int64, vp]
+        L.orc_decimate_tcint_sc8.restype = C.c_int64
         L.orc_sc16_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_sc8_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_pss_corr_window.argtypes = [vp, C.c_int, C.c_int, fp]
@@ -151,6 +153,16 @@ def decimate_tcint_sc16(iq):
     y = np.zeros((n + 15) // 16, np.complex64)
     if lib().orc_decimate_tcint_sc16(iq.ctypes.data, n, y.ctypes.data) < 0:
         raise RuntimeError("orc_decimate_tcint_sc16 failed")
+    return y
+
+
+def decimate_tcint_sc8(iq):
+    """The same for [n, 2] int8 I/Q."""
+    iq = np.ascontiguousarray(iq, np.int8)
+    n = iq.shape[0]
+    y = np.zeros((n + 15) // 16, np.complex64)
+    if lib().orc_decimate_tcint_sc8(iq.ctypes.data, n, y.ctypes.data) < 0:
+        raise RuntimeError("orc_decimate_tcint_sc8 failed")
     return y
 
 

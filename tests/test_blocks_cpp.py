@@ -38,11 +38,15 @@ def test_adapters_compile_and_link(tmp_path, gr_oot):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gr_oot", [False, True])
+@pytest.mark.parametrize("gr_oot", [False, True, "hier"])
 def test_cpp_blocks_match_oracle(tmp_path, oracle, gr_oot):
-    exe = build(tmp_path, gr_oot)
+    """gr_oot = "hier": the GNU Radio wrappers of all three chains on ONE shared engine (LTB_SHARE_ENGINE=1),
+    driven under GNU Radio's input-buffer limit; chain 0's calls must still equal the oracle's."""
+    exe = build(tmp_path, bool(gr_oot))
     fixture = os.path.join(GOLDEN, "test_frames", "lte_frame_6prb_cellid_123")
-    out = subprocess.run([exe, fixture, "0.4", "0", "4"], capture_output=True, text=True, check=True).stdout.splitlines()
+    env = dict(os.environ, LTB_SHARE_ENGINE="1") if gr_oot == "hier" else dict(os.environ)
+    args = [exe, fixture, "0.4", "0", "4"] + (["hier"] if gr_oot == "hier" else [])
+    out = subprocess.run(args, capture_output=True, text=True, check=True, env=env).stdout.splitlines()
     assert out[0] == "E Error initializing PSS N_id_2"                      # lib/pss_impl.cc:75-76
     x = np.fromfile(fixture, np.complex64)
     n = int(0.4 * 1.92e6) // 8 * 8

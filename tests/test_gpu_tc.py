@@ -23,18 +23,21 @@ def _bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
+@pytest.mark.parametrize("fmt", ["sc16", "sc8"])
 @pytest.mark.parametrize("n_out,chunk", [(976 * 3, None), (5000, None), (20000, 128 * 37), (20000, 128 * 2), (61 * 16 * 5 + 8, 128 * 125)])
-def test_tc_decimator_bit_exact(lt, oracle, n_out, chunk):
-    """Random full-scale int16 streams; chunk sizes that are not multiples of a 256-sample row, smaller
+def test_tc_decimator_bit_exact(lt, oracle, n_out, chunk, fmt):
+    """Random full-scale integer streams; chunk sizes that are not multiples of a 256-sample row, smaller
     than the 768-sample history, and tile-aligned; every output equal to the int64 evaluation."""
     rng = np.random.default_rng(n_out)
     n = n_out * 16
-    x = rng.integers(-32768, 32768, size=(3, n, 2)).astype(np.int16)
-    x[1, :, :] = 32767                      # digit extremes: all-max and all-min streams
-    x[2, :, 0] = -32768
+    lo, hi, dt = (-32768, 32767, np.int16) if fmt == "sc16" else (-128, 127, np.int8)
+    x = rng.integers(lo, hi + 1, size=(3, n, 2)).astype(dt)
+    x[1, :, :] = hi                         # digit extremes: all-max and all-min streams
+    x[2, :, 0] = lo
     got = lt.kernel_decimate_tc(x, chunk=chunk)
+    ref = oracle.decimate_tcint_sc16 if fmt == "sc16" else oracle.decimate_tcint_sc8
     for s in range(3):
-        want = oracle.decimate_tcint_sc16(x[s])
+        want = ref(x[s])
         assert np.array_equal(_bits(got[s]), _bits(want)), (s, int(np.argmax(_bits(got[s]) != _bits(want))))
 
 
@@ -48,8 +51,9 @@ def test_tc_decimator_within_tolerance_of_float32_front_end(lt, oracle):
     assert np.abs(got - ref).max() < 1e-5 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("fmt", ["sc16", "sc8"])
 @pytest.mark.parametrize("corr", ["fft", "direct"])
-def test_tc_front_end_through_the_engine(lt, oracle, corr):
+def test_tc_front_end_through_the_engine(lt, oracle, corr, fmt):
     """The 100 PRB fixture and synthetic cells as sc16 at 30.72 Msps through the whole chain with the
     integer front end, in ragged chunks: records bit-identical to the oracle in the same mode, the same
     decisions as the float32 front end, the reference's known cell id."""
@@ -57,21 +61,22 @@ def test_tc_front_end_through_the_engine(lt, oracle, corr):
     x, decim, cell_id = load_fixture("100prb", 0.25)
     rows = [x, synth.capture(77, len(x), snr_db=3.0, decim=16, seed=5, cfo_hz=1500.0),
             synth.capture(300, len(x), snr_db=0.0, decim=16, seed=6, noise_only=True)]
-    iq = synth.to_sc16(np.stack(rows))
+    iq = synth.to_sc16(np.stack(rows)) if fmt == "sc16" else synth.to_sc8(np.stack(rows))
+    code = lt.FMT_SC16 if fmt == "sc16" else lt.FMT_SC8
     mode = lt.CORR_FFT if corr == "fft" else lt.CORR_DIRECT
     conv = (oracle.CONV_OS if corr == "fft" else oracle.CONV_DIRECT) | oracle.FRONT_TCINT
     chunk = 16 * 8 * 4001
-    trig = lt.Trigger(n_streams=3, decim=16, max_chunk=chunk, input_format=lt.FMT_SC16, corr_mode=mode,
+    trig = lt.Trigger(n_streams=3, decim=16, max_chunk=chunk, input_format=code, corr_mode=mode,
                       frontend_mode=lt.FRONTEND_TC_INT)
     got = trig.run(iq, chunk=chunk)
     trig.close()
-    want = oracle.trigger_run(iq, decim=16, fmt=1, conv_mode=conv)
+    want = oracle.trigger_run(iq, decim=16, fmt=code, conv_mode=conv)
     assert_recs_equal(got, want)
     cells = got[(got["flags"] & lt.F_CELL) != 0]
     assert set(cells[cells["stream"] == 0]["cell_id"].tolist()) == {cell_id}
     assert set(cells[cells["stream"] == 1]["cell_id"].tolist()) == {77}
     # the float32 front end on the same input: same windows, flags, peaks and cell ids; magnitudes within 1e-4
-    ref = lt.Trigger(n_streams=3, decim=16, max_chunk=chunk, input_format=lt.FMT_SC16, corr_mode=mode)
+    ref = lt.Trigger(n_streams=3, decim=16, max_chunk=chunk, input_format=code, corr_mode=mode)
     fp = ref.run(iq, chunk=chunk)
     ref.close()
     sel = (got["stream"] < 2)                                  # noise-only stream: argmax of noise may move

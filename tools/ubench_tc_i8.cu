@@ -3,7 +3,7 @@
 // evaluation on the host, then timed.  One variant per process (a watchdog trap poisons the context):
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o tools/ubench_tc_i8 tools/ubench_tc_i8.cu
-//   ./tools/ubench_tc_i8 <G = 1|2|4|8> [n_streams] [n_in per stream] [chunks]
+//   ./tools/ubench_tc_i8 <fmt = 1 (sc16) | 2 (sc8)> [n_streams] [n_in per stream] [chunks]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -34,29 +34,31 @@ static std::vector<float> taps16() {
 
 static int sw_off(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
 
-// tap tables in the kernel's shared-memory image (see ltb_tc_frontend.cuh)
-static std::vector<int8_t> make_btab(int G, const std::vector<int> &T) {
-  std::vector<int8_t> tab((size_t)tc_btiles(G) * kTcBTileBytes, 0);
+// tap table in the kernel's shared-memory image (see ltb_tc_frontend.cuh, ltb_tables.cpp make_tc_btab)
+static int digit(int t, int v) {              // balanced base-256 digits v = 0..2
+  int d0 = ((t + 128) & 255) - 128; int t1 = (t - d0) >> 8;
+  int d1 = ((t1 + 128) & 255) - 128; int t2 = (t1 - d1) >> 8;
+  if (t2 < -128 || t2 > 127) { fprintf(stderr, "tap does not fit three digits\n"); exit(2); }
+  return v == 0 ? d0 : v == 1 ? d1 : v == 2 ? t2 : 0;
+}
+static std::vector<int8_t> make_btab(int fmt, const std::vector<int> &T) {
+  std::vector<int8_t> tab((size_t)kTcBTileBytes, 0);
   auto tapq = [&](int j) { return (j >= 0 && j < (int)T.size()) ? T[j] : 0; };
-  auto digit = [&](int t, int v) {            // balanced base-256 digits v = 0..2
-    int d0 = ((t + 128) & 255) - 128; int t1 = (t - d0) >> 8;
-    int d1 = ((t1 + 128) & 255) - 128; int t2 = (t1 - d1) >> 8;
-    if (t2 < -128 || t2 > 127) { fprintf(stderr, "tap does not fit three digits\n"); exit(2); }
-    return v == 0 ? d0 : v == 1 ? d1 : v == 2 ? t2 : 0;
-  };
-  for (int i = 0; i < G; ++i)
-    for (int n = 0; n < kTcBRows; ++n) {
-      const int d = n / 4 - i, v = n % 4;
-      if (d < 0 || d > 33) continue;
-      for (int pp = 0; pp < 16; ++pp) {
-        const int t = tapq(16 * d - pp);
-        const int b_lo = v <= 2 ? digit(t, v) : 0, b_hi = v >= 1 ? digit(t, v - 1) : 0;
-        const int kb = (i & 3) * 32 + 2 * pp;
-        int8_t *tile = tab.data() + (size_t)(i >> 2) * kTcBTileBytes;
-        tile[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)b_lo;
-        tile[sw_off(n, (kb + 1) >> 4) + ((kb + 1) & 15)] = (int8_t)b_hi;
+  const bool sc16 = fmt == 1;
+  for (int n = 0; n < kTcBRows; ++n) {
+    const int d = n / 4, v = n % 4;
+    if (d > (sc16 ? 33 : 34)) continue;
+    for (int pp = 0; pp < (sc16 ? 16 : 32); ++pp) {
+      const int t = tapq(16 * d - pp);
+      if (sc16) {
+        const int kb = 2 * pp;
+        tab[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)(v <= 2 ? digit(t, v) : 0);
+        tab[sw_off(n, (kb + 1) >> 4) + ((kb + 1) & 15)] = (int8_t)(v >= 1 ? digit(t, v - 1) : 0);
+      } else {
+        tab[sw_off(n, pp >> 4) + (pp & 15)] = (int8_t)(v <= 2 ? digit(t, v) : 0);
       }
     }
+  }
   return tab;
 }
 
@@ -64,32 +66,35 @@ typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, 
                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int G>
+template <int FMT>
 static void launch(const CUtensorMap &map, const TcParams &P, int grid) {
-  cudaFuncSetAttribute(decimate_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(G));
-  decimate_tc_kernel<G><<<grid, kTcThreads, tc_smem_bytes(G)>>>(map, P);
+  cudaFuncSetAttribute(decimate_tc_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes());
+  decimate_tc_kernel<FMT><<<grid, kTcThreads, tc_smem_bytes()>>>(map, P);
 }
 
 int main(int argc, char **argv) {
-  const int G = argc > 1 ? atoi(argv[1]) : 1;
+  const int G = argc > 1 ? atoi(argv[1]) : 1;            // input format: 1 sc16, 2 sc8
+  const int bps = G == 1 ? 4 : 2;
   const int S = argc > 2 ? atoi(argv[2]) : 64;
   const int n_in = argc > 3 ? atoi(argv[3]) : 3072000;
   const int chunks = argc > 4 ? atoi(argv[4]) : 1;       // > 1: feed the stream in `chunks` calls (tail carried)
-  if (G != 1 && G != 2 && G != 4 && G != 8) { fprintf(stderr, "G must be 1, 2, 4 or 8\n"); return 2; }
+  if (G != 1 && G != 2) { fprintf(stderr, "fmt must be 1 (sc16) or 2 (sc8)\n"); return 2; }
   const std::vector<float> tf = taps16();
   std::vector<int> T(tf.size());
   long long sumT = 0;
   for (size_t j = 0; j < tf.size(); ++j) { T[j] = (int)llrint((double)tf[j] * (double)(1 << kTcTapShift)); sumT += T[j]; }
   const std::vector<int8_t> btab = make_btab(G, T);
 
-  const size_t row_bytes = (size_t)n_in * 4;
-  std::vector<short> x((size_t)S * n_in * 2);
+  const size_t row_bytes = (size_t)n_in * bps;
+  std::vector<short> x((size_t)S * n_in * 2);        // sample values (sc8: within -128..127), packed below
   srand(12345);
-  for (auto &v : x) v = (short)((rand() & 0xffff) - 32768);
+  for (auto &v : x) v = G == 1 ? (short)((rand() & 0xffff) - 32768) : (short)((rand() & 0xff) - 128);
   // a few structured streams: extremes exercise the digit bounds
-  for (int i = 0; i < n_in * 2 && S > 2; ++i) { x[(size_t)1 * n_in * 2 + i] = 32767; x[(size_t)2 * n_in * 2 + i] = -32768; }
+  for (int i = 0; i < n_in * 2 && S > 2; ++i) { x[(size_t)1 * n_in * 2 + i] = G == 1 ? 32767 : 127; x[(size_t)2 * n_in * 2 + i] = G == 1 ? -32768 : -128; }
+  std::vector<signed char> x8;
+  if (G == 2) { x8.resize(x.size()); for (size_t i = 0; i < x.size(); ++i) x8[i] = (signed char)x[i]; }
 
-  void *d_x; short2 *d_tail[2]; float2 *d_y; int8_t *d_b; int *d_err; int *d_acc;
+  void *d_x; void *d_tail[2]; float2 *d_y; int8_t *d_b; int *d_err; int *d_acc;
   cudaMalloc(&d_acc, 128 * kTcBRows * 4); cudaMemset(d_acc, 0x7f, 128 * kTcBRows * 4);
   const int m_total = n_in / 16;
   int cap = 1; while (cap < m_total + 64) cap <<= 1;
@@ -98,7 +103,7 @@ int main(int argc, char **argv) {
   cudaMemset(d_tail[0], 0, (size_t)S * kTcTailSamples * 4);
   cudaMalloc(&d_y, (size_t)S * cap * 8); cudaMemset(d_y, 0xff, (size_t)S * cap * 8);
   cudaMalloc(&d_b, btab.size()); cudaMalloc(&d_err, 4); cudaMemset(d_err, 0, 4);
-  cudaMemcpy(d_x, x.data(), (size_t)S * row_bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_x, G == 1 ? (const void *)x.data() : (const void *)x8.data(), (size_t)S * row_bytes, cudaMemcpyHostToDevice);
   cudaMemcpy(d_b, btab.data(), btab.size(), cudaMemcpyHostToDevice);
 
   EncodeTiled encode = nullptr;
@@ -111,23 +116,22 @@ int main(int argc, char **argv) {
   auto run_chunk = [&](int c0, int n_chunk, int tail_cur) -> int {
     CUtensorMap map;
     const int full_rows = n_chunk / kTcRowSamples;
-    const cuuint64_t gdim[3] = {1024, (cuuint64_t)(full_rows > 0 ? full_rows : 1), (cuuint64_t)S};
-    const cuuint64_t gstr[2] = {1024, (cuuint64_t)row_bytes};
+    const cuuint64_t gdim[3] = {(cuuint64_t)256 * bps, (cuuint64_t)(full_rows > 0 ? full_rows : 1), (cuuint64_t)S};
+    const cuuint64_t gstr[2] = {(cuuint64_t)256 * bps, (cuuint64_t)row_bytes};
     const cuuint32_t box[3] = {256, (cuuint32_t)kTcTileRows, 1}, estr[3] = {1, 1, 1};
-    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (char *)d_x + (size_t)c0 * 4, gdim, gstr, box, estr,
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (char *)d_x + (size_t)c0 * bps, gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("{\"error\": \"cuTensorMapEncodeTiled -> %d\"}\n", (int)r); return 1; }
     TcParams P;
-    P.in = (char *)d_x + (size_t)c0 * 4; P.stride_bytes = (long long)row_bytes; P.n_in = n_chunk; P.n_streams = S;
+    P.in = (char *)d_x + (size_t)c0 * bps; P.stride_bytes = (long long)row_bytes; P.n_in = n_chunk; P.n_streams = S;
     P.tail = d_tail[tail_cur]; P.y_ring = d_y; P.n_base = c0 / 16; P.cap_mask = (unsigned)(cap - 1); P.cap = cap;
     const int rows = (n_chunk + kTcRowSamples - 1) / kTcRowSamples;
     P.tiles_per_stream = (rows + kTcUseful - 1) / kTcUseful; P.total_tiles = P.tiles_per_stream * S;
-    P.btab = d_b; P.c_const = 128 * sumT; P.err = d_err; P.dbg_acc = c0 == 0 ? d_acc : nullptr;
+    P.btab = d_b; P.c_const = G == 1 ? 128 * sumT : 0; P.err = d_err; P.dbg_acc = c0 == 0 ? d_acc : nullptr;
     const int grid = P.total_tiles < sms ? P.total_tiles : sms;
-    switch (G) { case 1: launch<1>(map, P, grid); break; case 2: launch<2>(map, P, grid); break;
-                 case 4: launch<4>(map, P, grid); break; default: launch<8>(map, P, grid); }
-    tc_tail_kernel<<<S, 256>>>(P.in, P.stride_bytes, n_chunk, d_tail[tail_cur], d_tail[tail_cur ^ 1]);
+    if (G == 1) { launch<LTB_FMT_SC16>(map, P, grid); tc_tail_kernel<LTB_FMT_SC16><<<S, 256>>>(P.in, P.stride_bytes, n_chunk, d_tail[tail_cur], d_tail[tail_cur ^ 1]); }
+    else { launch<LTB_FMT_SC8>(map, P, grid); tc_tail_kernel<LTB_FMT_SC8><<<S, 256>>>(P.in, P.stride_bytes, n_chunk, d_tail[tail_cur], d_tail[tail_cur ^ 1]); }
     return 0;
   };
   auto run_all = [&]() -> int {
@@ -144,17 +148,13 @@ int main(int argc, char **argv) {
   if (run_all()) return 1;
   cudaError_t e = cudaDeviceSynchronize();
   int herr = 0; cudaMemcpy(&herr, d_err, 4, cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) { printf("{\"G\": %d, \"error\": \"%s\", \"watchdog\": %d}\n", G, cudaGetErrorString(e), herr); return 1; }
+  if (e != cudaSuccess) { printf("{\"fmt\": %d, \"error\": \"%s\", \"watchdog\": %d}\n", G, cudaGetErrorString(e), herr); return 1; }
 
   // ---- raw accumulators of tile 0 (stream 0, rows -3..60; lanes 0..63 re, 64..127 im) against the host ----
   long long acc_bad = 0; int acc_first[4] = {-1, -1, 0, 0};
   {
     std::vector<int> acc(128 * kTcBRows);
     cudaMemcpy(acc.data(), d_acc, acc.size() * 4, cudaMemcpyDeviceToHost);
-    auto digit = [&](int t, int v) {
-      int d0 = ((t + 128) & 255) - 128; int t1 = (t - d0) >> 8; int d1 = ((t1 + 128) & 255) - 128; int t2 = (t1 - d1) >> 8;
-      return v == 0 ? d0 : v == 1 ? d1 : v == 2 ? t2 : 0;
-    };
     for (int lanei = 0; lanei < 128; ++lanei) {
       const int comp = lanei >> 6, row = (lanei & 63) - kTcHalo;
       for (int col = 0; col < 196; ++col) {
@@ -165,8 +165,12 @@ int main(int argc, char **argv) {
           if (j < 0 || j > 524) continue;
           const long long nidx = (long long)row * 256 + p;
           const int xv = nidx >= 0 && nidx < n_in ? x[2 * nidx + comp] : 0;
-          const int lo = (xv & 255) - 128, hi = xv >> 8;
-          want += (long long)lo * (v <= 2 ? digit(T[j], v) : 0) + (long long)hi * (v >= 1 ? digit(T[j], v - 1) : 0);
+          if (G == 1) {
+            const int lo = (xv & 255) - 128, hi = xv >> 8;
+            want += (long long)lo * (v <= 2 ? digit(T[j], v) : 0) + (long long)hi * (v >= 1 ? digit(T[j], v - 1) : 0);
+          } else {
+            want += (long long)xv * (v <= 2 ? digit(T[j], v) : 0);
+          }
         }
         const int got = acc[lanei * kTcBRows + col];
         if ((long long)got != want) { if (!acc_bad) { acc_first[0] = lanei; acc_first[1] = col; acc_first[2] = got; acc_first[3] = (int)want; } acc_bad++; }
@@ -187,7 +191,8 @@ int main(int argc, char **argv) {
         if (n < 0) break;
         are += (long long)T[j] * xs[2 * n]; aim += (long long)T[j] * xs[2 * n + 1];
       }
-      const float wre = (float)are * 2.2737367544323206e-13f, wim = (float)aim * 2.2737367544323206e-13f;
+      const float sc = G == 1 ? 2.2737367544323206e-13f : 5.8207660913467407e-11f;
+      const float wre = (float)are * sc, wim = (float)aim * sc;
       const float2 g = y[(size_t)s * cap + k];
       checked++;
       if (memcmp(&g.x, &wre, 4) || memcmp(&g.y, &wim, 4)) {
@@ -207,9 +212,9 @@ int main(int argc, char **argv) {
     cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
   }
   e = cudaDeviceSynchronize();
-  printf("{\"G\": %d, \"acc_tile0_mismatches\": %lld, \"acc_first_bad\": [%d, %d, %d, %d], \"streams\": %d, \"n_in\": %d, \"chunks\": %d, \"checked\": %lld, \"mismatches\": %lld, \"first_bad\": [%d, %d, %g, %g], "
+  printf("{\"fmt\": %d, \"acc_tile0_mismatches\": %lld, \"acc_first_bad\": [%d, %d, %d, %d], \"streams\": %d, \"n_in\": %d, \"chunks\": %d, \"checked\": %lld, \"mismatches\": %lld, \"first_bad\": [%d, %d, %g, %g], "
          "\"ms\": %.4f, \"input_Gsamples_per_s\": %.1f, \"GB_per_s\": %.1f, \"status\": \"%s\"}\n",
          G, acc_bad, acc_first[0], acc_first[1], acc_first[2], acc_first[3], S, n_in, chunks, checked, bad, first_bad_s, first_bad_k, gb, wb, ms, ms > 0 ? (double)S * n_in / ms / 1e6 : 0.0,
-         ms > 0 ? (double)S * n_in * 4 / ms / 1e6 : 0.0, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+         ms > 0 ? (double)S * n_in * bps / ms / 1e6 : 0.0, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
   return bad ? 3 : 0;
 }
