@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--corr", default="fft", choices=["direct", "fft"],
                     help="matched-filter evaluation: folded direct form or overlap-save FFT blocks")
     ap.add_argument("--snr-db", type=float, default=5.0)
+    ap.add_argument("--noise-only", action="store_true",
+                    help="no cell in any stream: every chain searches every window (the detector's worst case; "
+                         "the default batch carries a cell per stream, so its matching chain skips 8 of 9 searches)")
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic captures tiled over the streams")
     ap.add_argument("--e2e-streams", type=int, default=128)
     ap.add_argument("--e2e-steps", type=int, default=10)
@@ -253,7 +256,10 @@ def main():
     shifts = torch.randint(0, n, (a.streams,), generator=torch.Generator().manual_seed(7 + rank))
     for s in range(a.streams):
         noise = torch.randn((n, 2), generator=g, device=dev, dtype=torch.float32)
-        x[s] = torch.roll(base_d[s % a.unique], int(shifts[s])) + sigma * torch.view_as_complex(noise)
+        if a.noise_only:
+            x[s] = float(np.sqrt(0.5)) * torch.view_as_complex(noise)
+        else:
+            x[s] = torch.roll(base_d[s % a.unique], int(shifts[s])) + sigma * torch.view_as_complex(noise)
     del noise, base_d
     def quantise(xc, name):
         """fc32 -> the named wire format (full scale = 8 x the signal's rms)."""
@@ -353,23 +359,39 @@ def main():
     # (DESIGN.md K2f), the folded direct form 64 FADD2 + 260 FFMA2 per search-rate sample
     f_corr_exec = (2.0 * 4700 * 32 / 896) if a.corr == "fft" else (64 * 2 + 260 * 4)
     f_exec = (f_corr_exec + 4.0 * ntaps(a.decim)) / a.decim
-    roofline = {
-        "bound": "fp32", "kernel": names[dom], "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-        "frac": achieved / FP32_PEAK_TFLOPS, "traffic": traffic,
+    hbm_peak = 6535.7
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    hbm_gbs = alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    # the integer tensor-core front end does its multiply-adds on the tensor pipe (18 % busy, profiles/): what
+    # binds that kernel is memory, so its roofline is HBM; the float32 kernels stay FFMA bound
+    tc_dom = a.frontend == "tc" and dom == 0
+    head = ({"bound": "hbm", "kernel": names[dom], "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak}
+            if tc_dom else
+            {"bound": "fp32", "kernel": names[dom], "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+             "frac": achieved / FP32_PEAK_TFLOPS})
+    roofline = dict(head)
+    roofline.update({
+        "traffic": traffic,
         "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
         "algorithmic_bytes_per_launch": alg_bytes[dom],
-        "hbm": {"achieved": alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9, "peak": 6535.7, "unit": "GB/s",
-                "frac": alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 6535.7e9, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"},
-        "peak_source": "measured FFMA peak, tools/ubench_fp32.cu (profiles/ubench_fp32_r01.jsonl); MEASURED_PEAKS.json has no fp32 figure",
+        "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"},
+        "fp32": {"achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP32_PEAK_TFLOPS,
+                 "note": "direct-form algorithmic flop of the dominant kernel; with --frontend tc they run as int8 tensor-core MACs"},
+        "peak_source": ("MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if tc_dom else
+                        "measured FFMA peak, tools/ubench_fp32.cu (profiles/ubench_fp32_r01.jsonl); MEASURED_PEAKS.json has no fp32 figure"),
         "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
         "stages_overlap": a.pipeline == "overlap",      # track + sss of call i run under the front end of call i+1:
                                                         # the stage times then sum to more than ms_per_step
         "path_frac_of_fp32": f_alg * per_gpu_rate / (FP32_PEAK_TFLOPS * 1e12),
         "path_frac_of_fp32_executed": f_exec * per_gpu_rate / (FP32_PEAK_TFLOPS * 1e12),
         "flop_per_input_sample": {"algorithmic_direct_form": f_alg, "executed": f_exec},
-        "path_frac_of_hbm": bps * per_gpu_rate / (6535.7e9),
-        "note": "achieved = SURVEY 8d algorithmic flop (direct form) per launch / CUDA-event duration; path_frac_of_fp32 uses the same direct-form count and exceeds 1 because the correlator runs as FFT blocks (or folds the taps); path_frac_of_fp32_executed counts the flop the kernels execute",
-    }
+        "path_frac_of_hbm": bps * per_gpu_rate / (hbm_peak * 1e9),
+        "note": "achieved = SURVEY 8d algorithmic bytes (hbm) or direct-form flop (fp32) of the dominant kernel per launch / its CUDA-event duration; path_frac_of_fp32 uses the same direct-form count and exceeds 1 because the correlator runs as FFT blocks (or folds the taps); path_frac_of_fp32_executed counts the flop the kernels execute",
+    })
 
     out = {
         "metric": "PSS+SSS search Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
@@ -378,7 +400,8 @@ def main():
         "config": {"workload": workload_name(a), "streams_per_gpu": a.streams, "decim": a.decim,
                    "format": a.format, "frontend": a.frontend, "correlator": a.corr, "pipeline": a.pipeline, "segment_ms": a.segment_ms, "snr_db": a.snr_db,
                    "l2": "inputs larger than L2 (%.1f GB per step)" % (a.streams * n * bps / 1e9),
-                   "input": "%d seeded synthetic LTE captures tiled over the streams with per-stream timing shift + AWGN" % a.unique,
+                   "input": ("noise only (no cell in any stream)" if a.noise_only else
+                             "%d seeded synthetic LTE captures tiled over the streams with per-stream timing shift + AWGN" % a.unique),
                    "cells_tagged_per_step": n_cells / a.steps},
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
     }

@@ -30,7 +30,7 @@
 // Pipeline (one 576-thread CTA per SM, persistent over a contiguous run of tiles):
 //   warp 8        TMA producer: one cp.async.bulk.tensor.3d box (256 B x 64 rows) per stage -> raw ring (4 stages)
 //   warps 10..17  transform: raw interleaved I/Q -> two planar rows (re, im), written in the UMMA K-major
-//                 SWIZZLE_128B layout (3 stages of 16 kB)
+//                 SWIZZLE_128B layout (4 stages of 16 kB)
 //   warp 9        MMA issuer: 4 x tcgen05.mma.kind::i8 (M = 128, N = 144, K = 32) per stage, accumulators in TMEM
 //   warps 0..7    epilogue: tcgen05.ld -> int64 recombination -> diagonal sum -> float -> y_ring (coalesced);
 //                 warp w reads TMEM lane quarter w % 4 and owns outputs r = 8 (w / 4) .. 8 (w / 4) + 7 of its rows
@@ -52,7 +52,7 @@ constexpr int kTcRowSamples = 256;                 // input samples per A row (1
 constexpr int kTcTileRows = 64;                    // stream rows per tile (x 2 components = M 128)
 constexpr int kTcHalo = 3;                         // rows a tile re-reads from the tile above
 constexpr int kTcUseful = kTcTileRows - kTcHalo;   // 61
-constexpr int kTcRawStages = 4, kTcAStages = 3;
+constexpr int kTcRawStages = 4, kTcAStages = 4;   // powers of two: stage = iteration & 3
 constexpr int kTcRawBytes = kTcTileRows * 256;     // 16384: 256 raw bytes per row and stage (64 sc16 / 128 sc8 samples)
 constexpr int kTcABytes = 128 * 128;               // 16384
 constexpr int kTcBRows = 208;                      // accumulator columns of one tile (49 u's x 4, padded to 16)
@@ -164,6 +164,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -234,6 +242,9 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
   const int t_end = (int)((long long)P.total_tiles * (blockIdx.x + 1) / gridDim.x);
   const int full_rows = P.n_in / kTcRowSamples;             // rows the tensor map covers
   const int m_out = P.n_in / 16;
+  // every role walks the same tiles; (stream, tile-in-stream) advances incrementally (one division up front)
+  int stream = t_begin / P.tiles_per_stream, ti = t_begin - stream * P.tiles_per_stream;
+  auto next_tile = [&]() { if (++ti == P.tiles_per_stream) { ti = 0; ++stream; } };
 
   // tap table -> shared memory (generic proxy writes, made visible to the tensor core by the fence below)
   for (int i = tid; i < kTcBTileBytes / 16; i += kTcThreads)
@@ -258,8 +269,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int stream = t / P.tiles_per_stream, ti = t - stream * P.tiles_per_stream;
+      for (int t = t_begin; t < t_end; ++t, next_tile()) {
         const int row0 = ti * kTcUseful - kTcHalo;
 #ifdef LTB_TC_NO_TMA
         const bool any = false;                                          // bisection build: every row takes the patch path
@@ -317,8 +327,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
     const int dst_off = tc_sw_off(r_t, c >> 1) + (c & 1) * 8;
     static_assert(ROWSTEP % 8 == 0, "swizzle phase must not change between a thread's items");
     int it = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      const int stream = t / P.tiles_per_stream, ti = t - stream * P.tiles_per_stream;
+    for (int t = t_begin; t < t_end; ++t, next_tile()) {
       const int row0 = ti * kTcUseful - kTcHalo;
 #ifdef LTB_TC_NO_TMA
       const bool patch = true;
@@ -378,8 +387,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
     const int quarter = warp & 3, half = warp >> 2;
     const int comp = quarter >> 1, row = (quarter & 1) * 32 + lane;
     int tl = 0;
-    for (int t = t_begin; t < t_end; ++t, ++tl) {
-      const int stream = t / P.tiles_per_stream, ti = t - stream * P.tiles_per_stream;
+    for (int t = t_begin; t < t_end; ++t, ++tl, next_tile()) {
       const int row0 = ti * kTcUseful - kTcHalo;
       const int buf = tl & 1;
       tc_mbar_wait<64>(acc_full(buf), (tl >> 1) & 1, P.err, 6);
@@ -389,15 +397,18 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
       long long p48 = 0;
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        uint32_t r[32];
-        const int c0 = 2 * q + half;                                     // 32-column chunk
-        tc_ld32(taddr + 32 * c0, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int c0 = 2 * q + half;                                     // 32-column chunk, loaded as two halves
 #pragma unroll
-        for (int j = 0; j < 8; ++j) p[q][j] = tc_combine(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        if (P.dbg_acc && t == 0) {
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t r[16];
+          tc_ld16(taddr + 32 * c0 + 16 * h2, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 32; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 32 * c0 + i] = (int)r[i];
+          for (int j = 0; j < 4; ++j) p[q][4 * h2 + j] = tc_combine(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          if (P.dbg_acc && t == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 32 * c0 + 16 * h2 + i] = (int)r[i];
+          }
         }
       }
       if (half == 0) {
