@@ -284,6 +284,10 @@ def main():
     if a.frontend == "tc":
         from oracle import oracle as O_
         frontend_kw, oracle_front_flag = {"frontend_mode": lt.FRONTEND_TC_INT}, O_.FRONT_TCINT
+        if a.format == "fc32":
+            # fc32 through the integer tensor-core front end: 23-bit fixed point over the same range the sc16 / sc8
+            # quantiser above uses (8 x the signal's rms)
+            frontend_kw["fc32_full_scale"] = 8.0
     pipeline = lt.PIPE_OVERLAP if a.pipeline == "overlap" else lt.PIPE_SERIAL
     trig = lt.Trigger(n_streams=a.streams, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
                       record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode,
@@ -447,7 +451,8 @@ def main():
         got = chk.run(iq)
         chk.close()
         conv = (O.CONV_OS if a.corr == "fft" else O.CONV_DIRECT) | oracle_front_flag
-        want = O.trigger_run(iq, decim=a.decim, fmt=fmt, psr_threshold=4.0, conv_mode=conv)
+        want = O.trigger_run(iq, decim=a.decim, fmt=fmt, psr_threshold=4.0, conv_mode=conv,
+                             fc32_full_scale=frontend_kw.get("fc32_full_scale", 0.0))
         same = len(got) == len(want)
         for f in (want.dtype.names if same else ()):
             g_, w_ = got[f], want[f]

@@ -317,6 +317,7 @@ long long g_tc_sum_t = 0;
 int ensure_tc_tables(int device) {
   std::lock_guard<std::mutex> lk(g_const_mu);
   if (g_tc_btab[device][LTB_FMT_SC16]) return LTB_SUCCESS;
+  static_assert(LTB_FMT_FC32 == 0 && LTB_FMT_SC16 == 1 && LTB_FMT_SC8 == 2, "tap tables are indexed by format");
   if (!g_encode_tiled) {
     cudaDriverEntryPointQueryResult qres;
     void *fn = nullptr;
@@ -325,7 +326,7 @@ int ensure_tc_tables(int device) {
     g_encode_tiled = (EncodeTiledFn)fn;
   }
   make_tc_taps(&g_tc_sum_t);
-  for (int fmt : {LTB_FMT_SC16, LTB_FMT_SC8}) {
+  for (int fmt : {LTB_FMT_FC32, LTB_FMT_SC8, LTB_FMT_SC16}) {                 // sc16 last: it marks the tables as built
     const std::vector<int8_t> tab = make_tc_btab(fmt);
     if (tab.empty()) return fail(LTB_ERROR, "decimator taps do not fit three base-256 digits");
     int8_t *d = nullptr;
@@ -335,13 +336,15 @@ int ensure_tc_tables(int device) {
   }
   LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<LTB_FMT_SC16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
   LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<LTB_FMT_SC8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
+  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<LTB_FMT_FC32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
   return LTB_SUCCESS;
 }
 
-// n_in new integer samples per stream (multiple of 128) -> n_in / 16 search-rate samples in y_ring; tail_old holds the
-// 768 raw samples before the chunk, tail_new receives the last 768 for the next call
-int launch_frontend_tc(int device, int fmt, const void *d_iq, long long stride, int n_streams, int n_in, const void *tail_old,
-                       void *tail_new, float2 *y_ring, long long n_base, unsigned mask, int cap, int *d_err,
+// n_in new samples per stream (multiple of 128) -> n_in / 16 search-rate samples in y_ring; tail_old holds the
+// 768 raw samples before the chunk, tail_new receives the last 768 for the next call.  full_scale: fc32 only
+// (the input is taken as 23-bit fixed point of that range, ltb_tc_frontend.cuh)
+int launch_frontend_tc(int device, int fmt, float full_scale, const void *d_iq, long long stride, int n_streams, int n_in,
+                       const void *tail_old, void *tail_new, float2 *y_ring, long long n_base, unsigned mask, int cap, int *d_err,
                        cudaStream_t st, int *launches) {
   if ((reinterpret_cast<uintptr_t>(d_iq) | (uintptr_t)stride) & 15u)
     return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT needs a 16-byte aligned input pointer and row stride (TMA)");
@@ -365,10 +368,17 @@ int launch_frontend_tc(int device, int fmt, const void *d_iq, long long stride, 
   const long long total = (long long)P.tiles_per_stream * n_streams;
   if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator tiles in one call");
   P.total_tiles = (int)total;
-  P.btab = g_tc_btab[device][fmt]; P.c_const = fmt == LTB_FMT_SC16 ? 128 * g_tc_sum_t : 0; P.err = d_err; P.dbg_acc = nullptr;
+  P.btab = g_tc_btab[device][fmt]; P.err = d_err; P.dbg_acc = nullptr;
+  P.c_const = fmt == LTB_FMT_SC16 ? 128 * g_tc_sum_t : fmt == LTB_FMT_FC32 ? -16384 * g_tc_sum_t : 0;
+  P.q_inv = fmt == LTB_FMT_FC32 ? (float)(0.5 / (double)full_scale) : 0.f;
+  P.out_scale = fmt == LTB_FMT_FC32 ? (float)((double)full_scale / 4194303.0 / 524288.0)
+                                    : fmt == LTB_FMT_SC16 ? 2.2737367544323206e-13f : 5.8207660913467407e-11f;   // 2^-42, 2^-34
   const int sms = g_sm_count[device] > 0 ? g_sm_count[device] : 148;
   const int grid = P.total_tiles < sms ? P.total_tiles : sms;
-  if (fmt == LTB_FMT_SC16) {
+  if (fmt == LTB_FMT_FC32) {
+    decimate_tc_kernel<LTB_FMT_FC32><<<grid, kTcThreads, tc_smem_bytes(), st>>>(map, P);
+    tc_tail_kernel<LTB_FMT_FC32><<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);
+  } else if (fmt == LTB_FMT_SC16) {
     decimate_tc_kernel<LTB_FMT_SC16><<<grid, kTcThreads, tc_smem_bytes(), st>>>(map, P);
     tc_tail_kernel<LTB_FMT_SC16><<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);
   } else {
@@ -465,8 +475,8 @@ int trigger_zero_state(ltb_trigger *t) {
   LTB_CUDA(cudaMemsetAsync(t->d_tail[0], 0, sizeof(float2) * (size_t)S * kTailCap, t->stream));
   LTB_CUDA(cudaMemsetAsync(t->d_tail[1], 0, sizeof(float2) * (size_t)S * kTailCap, t->stream));
   if (t->d_tc_tail[0]) {
-    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[0], 0, 4 * (size_t)S * kTcTailSamples, t->stream));
-    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[1], 0, 4 * (size_t)S * kTcTailSamples, t->stream));
+    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[0], 0, 8 * (size_t)S * kTcTailSamples, t->stream));
+    LTB_CUDA(cudaMemsetAsync(t->d_tc_tail[1], 0, 8 * (size_t)S * kTcTailSamples, t->stream));
     LTB_CUDA(cudaMemsetAsync(t->d_tc_err, 0, sizeof(int), t->stream));
   }
   LTB_CUDA(cudaMemcpyAsync(t->d_thr, t->h_thr.data(), sizeof(float) * t->n_chains, cudaMemcpyHostToDevice, t->stream));
@@ -524,7 +534,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   LTB_CUDA(cudaEventRecord(sl.ev0, t->stream));
   int rc;
   if (c.frontend_mode == LTB_FRONTEND_TC_INT)
-    rc = launch_frontend_tc(c.device, c.input_format, d_iq, stride, S, (int)n_samples, t->d_tc_tail[t->tail_cur], t->d_tc_tail[t->tail_cur ^ 1],
+    rc = launch_frontend_tc(c.device, c.input_format, c.fc32_full_scale, d_iq, stride, S, (int)n_samples, t->d_tc_tail[t->tail_cur], t->d_tc_tail[t->tail_cur ^ 1],
                             t->d_y, n_base, t->cap_mask, t->cap, t->d_tc_err, t->stream, &launches);
   else
     rc = launch_frontend_fmt(c.input_format, c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
@@ -623,8 +633,12 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
       (c.pipeline != LTB_PIPE_OVERLAP && c.pipeline != LTB_PIPE_SERIAL) ||
       (c.frontend_mode != LTB_FRONTEND_FP32 && c.frontend_mode != LTB_FRONTEND_TC_INT))
     return fail(LTB_ERROR_INVALID_INPUTS, "invalid trigger configuration");
-  if (c.frontend_mode == LTB_FRONTEND_TC_INT && (c.input_format == LTB_FMT_FC32 || c.decim != 16))
-    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT is available for sc16 / sc8 input at decim = 16");
+  if (c.frontend_mode == LTB_FRONTEND_TC_INT && c.decim != 16)
+    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT is available at decim = 16");
+  if (c.frontend_mode == LTB_FRONTEND_TC_INT && c.input_format == LTB_FMT_FC32 &&
+      !(c.fc32_full_scale > 0.f && c.fc32_full_scale < 1e30f))
+    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT on fc32 input takes the samples as 23-bit fixed point: "
+                                          "set fc32_full_scale > 0 (the largest |re|, |im| the source delivers)");
   if (c.root_mask == 0) c.root_mask = 7;
   if (c.track_after <= 0) c.track_after = 16;
   if (c.track_every <= 0) c.track_every = 8;
@@ -695,8 +709,8 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   LTB_CUDA_T(cudaMalloc(&t->d_tail[0], sizeof(float2) * (size_t)S * kTailCap));
   LTB_CUDA_T(cudaMalloc(&t->d_tail[1], sizeof(float2) * (size_t)S * kTailCap));
   if (c.frontend_mode == LTB_FRONTEND_TC_INT) {
-    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[0], 4 * (size_t)S * kTcTailSamples));
-    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[1], 4 * (size_t)S * kTcTailSamples));
+    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[0], 8 * (size_t)S * kTcTailSamples));
+    LTB_CUDA_T(cudaMalloc(&t->d_tc_tail[1], 8 * (size_t)S * kTcTailSamples));
     LTB_CUDA_T(cudaMalloc(&t->d_tc_err, sizeof(int)));
   }
   if (c.keep_halfframes) LTB_CUDA_T(cudaMalloc(&t->d_hf, sizeof(float2) * kHalf * (size_t)t->n_chains * t->w_cap));
@@ -1050,9 +1064,15 @@ int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, 
 }
 
 int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y) {
+  if (fmt != LTB_FMT_SC16 && fmt != LTB_FMT_SC8) return fail(LTB_ERROR_INVALID_INPUTS, "integer input only (fc32: ltb_kernel_decimate_tc_host2)");
+  return ltb_kernel_decimate_tc_host2(device, x, fmt, 0.f, n_streams, n_in, chunk, y);
+}
+
+int ltb_kernel_decimate_tc_host2(int device, const void *x, int fmt, float full_scale, int n_streams, int64_t n_in,
+                                 int64_t chunk, ltb_cf *y) {
   if (!x || !y || n_streams <= 0 || n_in <= 0 || (n_in % 128) != 0 || chunk <= 0 || (chunk % 128) != 0 ||
-      (fmt != LTB_FMT_SC16 && fmt != LTB_FMT_SC8))
-    return fail(LTB_ERROR_INVALID_INPUTS, "integer input, n_in and chunk positive multiples of 128");
+      !valid_format(fmt) || (fmt == LTB_FMT_FC32 && !(full_scale > 0.f && full_scale < 1e30f)))
+    return fail(LTB_ERROR_INVALID_INPUTS, "n_in and chunk positive multiples of 128; fc32 needs full_scale > 0");
   if (ltb_device_count() <= device || device < 0) return fail(LTB_ERROR, "no such CUDA device");
   LTB_CUDA(cudaSetDevice(device));
   int rc = ensure_constants(device);
@@ -1065,17 +1085,17 @@ int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int n_stream
   void *d_in = nullptr; float2 *d_y = nullptr; void *d_t[2] = {nullptr, nullptr}; int *d_err = nullptr;
   cudaError_t e = cudaMalloc(&d_in, dev_row * n_streams);
   if (e == cudaSuccess) e = cudaMalloc(&d_y, sizeof(float2) * (size_t)n_streams * cap);
-  if (e == cudaSuccess) e = cudaMalloc(&d_t[0], 4 * (size_t)n_streams * kTcTailSamples);
-  if (e == cudaSuccess) e = cudaMalloc(&d_t[1], 4 * (size_t)n_streams * kTcTailSamples);
+  if (e == cudaSuccess) e = cudaMalloc(&d_t[0], 8 * (size_t)n_streams * kTcTailSamples);
+  if (e == cudaSuccess) e = cudaMalloc(&d_t[1], 8 * (size_t)n_streams * kTcTailSamples);
   if (e == cudaSuccess) e = cudaMalloc(&d_err, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(d_err, 0, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(d_t[0], 0, 4 * (size_t)n_streams * kTcTailSamples);
+  if (e == cudaSuccess) e = cudaMemset(d_t[0], 0, 8 * (size_t)n_streams * kTcTailSamples);
   if (e == cudaSuccess) e = cudaMemcpy2D(d_in, dev_row, x, in_row, in_row, n_streams, cudaMemcpyHostToDevice);
   int cur = 0;
   for (int64_t c0 = 0; c0 < n_in && e == cudaSuccess && !rc; c0 += chunk) {
     const int nc = (int)(n_in - c0 < chunk ? n_in - c0 : chunk);
     int launches = 0;
-    rc = launch_frontend_tc(device, fmt, (const char *)d_in + c0 * bps, (long long)dev_row, n_streams, nc, d_t[cur], d_t[cur ^ 1], d_y,
+    rc = launch_frontend_tc(device, fmt, full_scale, (const char *)d_in + c0 * bps, (long long)dev_row, n_streams, nc, d_t[cur], d_t[cur ^ 1], d_y,
                             c0 / 16, (unsigned)(cap - 1), cap, d_err, 0, &launches);
     cur ^= 1;
     e = cudaGetLastError();
@@ -1126,6 +1146,17 @@ int ltb_table_fft1024_twiddles(float w_re[1024], float w_im[1024]) {
 int ltb_table_os_filter(int n_id_2, float H_re[1024], float H_im[1024]) {
   if (n_id_2 < 0 || n_id_2 > 2 || !H_re || !H_im) return LTB_ERROR_INVALID_INPUTS;
   make_os_filter(n_id_2, H_re, H_im);
+  return LTB_SUCCESS;
+}
+
+int ltb_table_tc_btab(int fmt, int8_t tab[208 * 128], int64_t *sum_t) {
+  if (!valid_format(fmt) || !tab) return LTB_ERROR_INVALID_INPUTS;
+  long long sum = 0;
+  make_tc_taps(&sum);
+  const std::vector<int8_t> t = make_tc_btab(fmt);
+  if (t.size() != 208 * 128) return LTB_ERROR;
+  std::memcpy(tab, t.data(), t.size());
+  if (sum_t) *sum_t = sum;
   return LTB_SUCCESS;
 }
 

@@ -151,6 +151,25 @@ std::vector<int8_t> make_tc_btab(int fmt) {
   auto tap = [&](int j) { return (j >= 0 && j < (int)T.size()) ? T[j] : 0; };
   bool ok = true;
   const bool sc16 = fmt == 1;
+  if (fmt == 0) {
+    // fc32 as 23-bit fixed point: a k-step is 8 samples x 4 bytes (byte 3 is not a digit: zero row entries); the
+    // even and odd k-steps of an output's 16 samples have their own tables at bytes 0..31 and 32..63 of a row.
+    // Column v' holds weight 256^(v'+1): the weight-1 product (lowest sample byte x lowest tap digit) is not formed.
+    for (int n = 0; n < kRows; ++n) {
+      const int d = n / 4, v = n % 4 + 1;
+      if (d > 33) continue;
+      for (int h = 0; h < 2; ++h)
+        for (int p8 = 0; p8 < 8; ++p8) {
+          const int t = tap(16 * d - 8 * h - p8);
+          for (int bi = 0; bi < 3; ++bi) {
+            const int i = v - bi, kb = 32 * h + 4 * p8 + bi;
+            if (i >= 0 && i <= 2) tab[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)digit(t, i, &ok);
+          }
+        }
+    }
+    if (!ok) tab.clear();
+    return tab;
+  }
   for (int n = 0; n < kRows; ++n) {
     const int d = n / 4, v = n % 4;
     if (d > (sc16 ? 33 : 34)) continue;

@@ -20,7 +20,9 @@ std::vector<float> make_decim_branch_taps(int decim);
 // LTB_FRONTEND_TC_INT (csrc/ltb_tc_frontend.cuh): the D = 16 taps quantised to T[j] = rint(taps[j] * 2^27), and
 // the tap table of the tensor-core kernel in its shared-memory image ([208 rows][128 B], K-major, 128-byte
 // swizzle, the first 32 bytes of a row used).  sc16 (fmt 1): row 4 d + v holds digit v (lo byte) / digit v - 1
-// (hi byte) of T[16 d - p'], p' = 0..15; sc8 (fmt 2): digit v of T[16 d - p'], p' = 0..31.  sum_t receives sum_j T[j].
+// (hi byte) of T[16 d - p'], p' = 0..15; sc8 (fmt 2): digit v of T[16 d - p'], p' = 0..31; fc32 as 23-bit fixed point
+// (fmt 0): two tables, bytes 0..31 (samples 0..7 of an output's 16) and 32..63 (samples 8..15), byte 4 p8 + bi of
+// row 4 d + v' holds digit v' + 1 - bi of T[16 d - 8 h - p8].  sum_t receives sum_j T[j].
 std::vector<int32_t> make_tc_taps(long long *sum_t);
 std::vector<int8_t> make_tc_btab(int fmt);
 

@@ -64,8 +64,13 @@ constexpr int kTcTailSamples = kTcHalo * kTcRowSamples;   // 768 raw samples of 
 constexpr int kTcTapShift = 27;
 constexpr int kTcStagePitch = 17;                  // floats per (row, component) in the output staging
 
-__host__ __device__ constexpr int tc_sample_bytes(int fmt) { return fmt == LTB_FMT_SC16 ? 4 : 2; }
-__host__ __device__ constexpr int tc_stages_per_tile(int fmt) { return fmt == LTB_FMT_SC16 ? 4 : 2; }
+__host__ __device__ constexpr int tc_sample_bytes(int fmt) { return fmt == LTB_FMT_FC32 ? 8 : fmt == LTB_FMT_SC16 ? 4 : 2; }
+__host__ __device__ constexpr int tc_stages_per_tile(int fmt) { return fmt == LTB_FMT_FC32 ? 8 : fmt == LTB_FMT_SC16 ? 4 : 2; }
+// fc32 input: fixed point with 23 bits.  q(x) = bits(fma(fma.sat(x, 0.5 / full_scale, 0.5), 2^23 - 2, 2^23 + 1)) & 0x7fffff
+// is an integer 1 .. 2^23 - 1 whose distance from 2^22 is x / full_scale * (2^22 - 1) rounded (two roundings, both
+// restated by the oracle); values beyond +-full_scale saturate.
+constexpr float kTcQMul = 8388606.0f, kTcQAdd = 8388609.0f;
+constexpr int kTcQMid = 1 << 22;
 __host__ __device__ constexpr size_t tc_smem_bytes() {
   return (size_t)kTcBTileBytes + (size_t)kTcAStages * kTcABytes + (size_t)kTcRawStages * kTcRawBytes +
          2 * kTcTileRows * kTcStagePitch * 4 + 2 * 2 * 3 * 17 * 8;
@@ -83,7 +88,9 @@ struct TcParams {
   int cap;
   int tiles_per_stream, total_tiles;
   const int8_t *btab;          // [208][128]: tap table in its shared-memory image (ltb_tables.cpp make_tc_btab)
-  long long c_const;           // sc16: 128 * sum_j T[j]; sc8: 0
+  long long c_const;           // sc16: 128 * sum_j T[j]; sc8: 0; fc32: -2^14 * sum_j T[j]
+  float q_inv;                 // fc32: 0.5 / full_scale
+  float out_scale;             // fc32: float(full_scale / (2^22 - 1) * 2^-19); sc16 2^-42, sc8 2^-34
   int *err;                    // device flag: 0 ok, else the code of the watchdog that fired
   int *dbg_acc;                // null, or [128][208] int32: the raw accumulator tile of tile 0 (tools/ubench_tc_i8)
 };
@@ -136,9 +143,10 @@ __device__ __forceinline__ uint64_t tc_make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// kind::i8: D = S32 (2 << 4), A and B signed 8 bit (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-__host__ __device__ constexpr uint32_t tc_idesc(int n) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::i8: D = S32 (2 << 4), A signed (1 << 7) or unsigned (0) 8 bit, B signed 8 bit (1 << 10), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t tc_idesc(int n, bool a_signed = true) {
+  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 // byte offset of (row r, 16-byte chunk c) in a [rows][128 B] K-major tile with the 128-byte swizzle
 __host__ __device__ constexpr int tc_sw_off(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
@@ -197,8 +205,20 @@ __device__ __forceinline__ long long tc_shfl_up(long long v, int delta) {
 // 16 raw bytes -> the planar (re, im) halves of an A row, 8 bytes each.  sc16: four samples, lo bytes flipped
 // (XOR 0x80: unsigned lo -> signed lo - 128); sc8: eight samples, signed bytes as they are.
 template <int FMT>
-__device__ __forceinline__ void tc_split(const uint4 w, uint2 &re, uint2 &im) {
-  if (FMT == LTB_FMT_SC16) {
+__device__ __forceinline__ void tc_split(const uint4 w, uint2 &re, uint2 &im, const float q_inv) {
+  if (FMT == LTB_FMT_FC32) {
+    // two samples (re0, im0, re1, im1) -> their 23-bit fixed-point words; the top byte of each word (the float's
+    // exponent bits, 0x4b) meets a zero row of the tap table, so it is not masked off
+    float u;
+    asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(u) : "f"(__uint_as_float(w.x)), "f"(q_inv));
+    re.x = __float_as_uint(__fmaf_rn(u, kTcQMul, kTcQAdd));
+    asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(u) : "f"(__uint_as_float(w.z)), "f"(q_inv));
+    re.y = __float_as_uint(__fmaf_rn(u, kTcQMul, kTcQAdd));
+    asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(u) : "f"(__uint_as_float(w.y)), "f"(q_inv));
+    im.x = __float_as_uint(__fmaf_rn(u, kTcQMul, kTcQAdd));
+    asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(u) : "f"(__uint_as_float(w.w)), "f"(q_inv));
+    im.y = __float_as_uint(__fmaf_rn(u, kTcQMul, kTcQAdd));
+  } else if (FMT == LTB_FMT_SC16) {
     re.x = __byte_perm(w.x, w.y, 0x5410) ^ 0x00800080u;
     re.y = __byte_perm(w.z, w.w, 0x5410) ^ 0x00800080u;
     im.x = __byte_perm(w.x, w.y, 0x7632) ^ 0x00800080u;
@@ -219,8 +239,10 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
   constexpr int SPT = tc_stages_per_tile(FMT);              // pipeline stages (128-byte A atoms) per tile
   constexpr int ITEM = 16 / BPS;                            // samples per 16-byte transform item
   constexpr int STAGE_SAMPLES = 256 / BPS;                  // samples per row and stage
-  constexpr int COLSTEP = FMT == LTB_FMT_SC16 ? 4 : 8;      // accumulator columns per k-step
-  constexpr float SCALE = FMT == LTB_FMT_SC16 ? 2.2737367544323206e-13f : 5.8207660913467407e-11f;   // 2^-42, 2^-34
+  // accumulator columns per k-step: a k-step is 16 sc16 samples (one output: 4 columns), 32 sc8 samples (8) or
+  // 8 fc32 samples (half an output: the column offset advances every other k-step and the two halves of an
+  // output's 16 samples have their own tap tables, bytes 0..31 and 32..63 of the table's rows)
+  constexpr int COLSTEP = FMT == LTB_FMT_SC8 ? 8 : 4;
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   unsigned char *s_b = tc_smem;                                         // [208][128]
   unsigned char *s_a = s_b + kTcBTileBytes;                             // [kTcAStages][128][128]
@@ -302,13 +324,21 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
         if (lane == 0) {
           const uint32_t a_base = tc_smem_u32(s_a + (size_t)as * kTcABytes);
           const uint64_t bdesc = tc_make_desc(tc_smem_u32(s_b));
+          const uint64_t bdesc1 = tc_make_desc(tc_smem_u32(s_b) + 32);       // fc32: taps of the odd k-steps
+          (void)bdesc1;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int s = 4 * a + k;                                     // k-step of the row
             const bool first = s == 0;
             const uint64_t adesc = tc_make_desc(a_base + 32 * k);
-            const uint32_t d = tmem + buf * 256 + COLSTEP * s;
-            tc_mma_i8(d, adesc, bdesc, first ? tc_idesc(kTcBRows) : tc_idesc(kTcNStep), first ? 0u : 1u);
+            if (FMT == LTB_FMT_FC32) {
+              const uint32_t d = tmem + buf * 256 + COLSTEP * (s >> 1);
+              tc_mma_i8(d, adesc, (s & 1) ? bdesc1 : bdesc, first ? tc_idesc(kTcBRows, false) : tc_idesc(kTcNStep, false),
+                        first ? 0u : 1u);
+            } else {
+              const uint32_t d = tmem + buf * 256 + COLSTEP * s;
+              tc_mma_i8(d, adesc, bdesc, first ? tc_idesc(kTcBRows) : tc_idesc(kTcNStep), first ? 0u : 1u);
+            }
           }
           tc_commit(a_empty(as));
           if (a == SPT - 1) tc_commit(acc_full(buf));
@@ -362,8 +392,8 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
               unsigned v[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {                                        // 4 bytes at a time
-                const int n1 = n0 + q * (4 / BPS);                                 // sc16: one sample, sc8: two
-                v[q] = n1 < P.n_in ? *reinterpret_cast<const unsigned *>(src + (size_t)n1 * BPS) : 0u;
+                const int n1 = n0 + q * 4 / BPS;                                   // sc16: one sample, sc8: two, fc32: half
+                v[q] = n1 < P.n_in ? *reinterpret_cast<const unsigned *>(src + (size_t)n0 * BPS + 4 * q) : 0u;
               }
               w[j] = make_uint4(v[0], v[1], v[2], v[3]);
             }
@@ -372,7 +402,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           uint2 re, im;
-          tc_split<FMT>(w[j], re, im);
+          tc_split<FMT>(w[j], re, im, P.q_inv);
           *reinterpret_cast<uint2 *>(dst + j * ROWSTEP * 128) = re;                // rows 0..63: real parts
           *reinterpret_cast<uint2 *>(dst + 64 * 128 + j * ROWSTEP * 128) = im;     // rows 64..127: imaginary parts
         }
@@ -447,7 +477,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
           acc += v;
         }
         acc += P.c_const;
-        stg[j] = __fmul_rn(__ll2float_rn(acc), SCALE);
+        stg[j] = __fmul_rn(__ll2float_rn(acc), P.out_scale);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // coalesced store: 16 consecutive float2 per row
@@ -476,7 +506,8 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
 template <int FMT>
 __global__ void __launch_bounds__(256) tc_tail_kernel(const void *__restrict__ in, long long stride_bytes, int n_in,
                                                       const void *__restrict__ tail_old, void *__restrict__ tail_new) {
-  typedef typename std::conditional<FMT == LTB_FMT_SC16, unsigned, unsigned short>::type raw_t;   // one complex sample
+  typedef typename std::conditional<FMT == LTB_FMT_FC32, unsigned long long,
+                                    typename std::conditional<FMT == LTB_FMT_SC16, unsigned, unsigned short>::type>::type raw_t;   // one complex sample
   const int stream = blockIdx.x;
   const raw_t *src = reinterpret_cast<const raw_t *>((const char *)in + (long long)stream * stride_bytes);
   const raw_t *told = reinterpret_cast<const raw_t *>(tail_old) + (size_t)stream * kTcTailSamples;

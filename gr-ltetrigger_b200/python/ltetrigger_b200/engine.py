@@ -20,7 +20,7 @@ class Trigger:
     def __init__(self, n_streams, decim=1, psr_threshold=4.0, max_chunk=1 << 20, input_format=A.FMT_FC32,
                  track_after=16, track_every=8, record_all=True, keep_halfframes=False, device=0,
                  root_mask=7, cuda_stream=None, corr_mode=A.CORR_DIRECT, frame_type=A.FRAME_FDD,
-                 frontend_mode=A.FRONTEND_FP32, pipeline=A.PIPE_OVERLAP):
+                 frontend_mode=A.FRONTEND_FP32, pipeline=A.PIPE_OVERLAP, fc32_full_scale=0.0):
         cfg = A.TriggerConfig()
         cfg.struct_size = C.sizeof(A.TriggerConfig)
         cfg.device, cfg.n_streams, cfg.input_format, cfg.decim = device, n_streams, input_format, decim
@@ -32,6 +32,7 @@ class Trigger:
         cfg.frame_type = frame_type
         cfg.frontend_mode = frontend_mode
         cfg.pipeline = pipeline
+        cfg.fc32_full_scale = fc32_full_scale
         self._h = C.c_void_p()
         A.check(A.lib().ltb_trigger_create(C.byref(cfg), C.byref(self._h)), "ltb_trigger_create")
         self.n_streams, self.decim, self.input_format = n_streams, decim, input_format
@@ -160,16 +161,17 @@ def kernel_decimate(x, decim, fmt=A.FMT_FC32, device=0, L=None):
     return y
 
 
-def kernel_decimate_tc(iq, chunk=None, device=0):
-    """LTB_FRONTEND_TC_INT at kernel level: iq [n_streams, n, 2] int16 (sc16) or int8 (sc8) ->
-    [n_streams, n // 16] complex64, the input fed in calls of `chunk` samples (multiple of 128; default: one call)."""
+def kernel_decimate_tc(iq, chunk=None, device=0, full_scale=0.0):
+    """LTB_FRONTEND_TC_INT at kernel level: iq [n_streams, n, 2] int16 (sc16) or int8 (sc8), or [n_streams, n]
+    complex64 taken as 23-bit fixed point over +-full_scale -> [n_streams, n // 16] complex64, the input fed in
+    calls of `chunk` samples (multiple of 128; default: one call)."""
     iq = np.asarray(iq)
-    fmt = A.FMT_SC8 if iq.dtype == np.int8 else A.FMT_SC16
+    fmt = A.FMT_SC8 if iq.dtype == np.int8 else A.FMT_SC16 if iq.dtype == np.int16 else A.FMT_FC32
     iq = np.ascontiguousarray(iq, A.FMT_DTYPE[fmt])
     s, n = iq.shape[0], iq.shape[1]
     y = np.zeros((s, n // 16), np.complex64)
-    A.check(A.lib().ltb_kernel_decimate_tc_host(device, iq.ctypes.data, fmt, s, n, chunk or n, y.ctypes.data),
-            "ltb_kernel_decimate_tc_host")
+    A.check(A.lib().ltb_kernel_decimate_tc_host2(device, iq.ctypes.data, fmt, full_scale, s, n, chunk or n, y.ctypes.data),
+            "ltb_kernel_decimate_tc_host2")
     return y
 
 
@@ -214,6 +216,19 @@ class tables:
         r, i = np.zeros(1024, np.float32), np.zeros(1024, np.float32)
         A.check(A.lib().ltb_table_os_filter(n_id_2, A.fptr(r), A.fptr(i)), "ltb_table_os_filter")
         return r, i
+
+    @staticmethod
+    def tc_btab(fmt):
+        """Tap table of the tensor-core front end, un-swizzled: ([208, 128] int8, sum of the integer taps)."""
+        raw = np.zeros(208 * 128, np.int8)
+        sum_t = C.c_int64(0)
+        A.check(A.lib().ltb_table_tc_btab(fmt, raw.ctypes.data, C.addressof(sum_t)), "ltb_table_tc_btab")
+        raw = raw.reshape(208, 8, 16)
+        out = np.zeros_like(raw)
+        for r in range(208):
+            for c in range(8):
+                out[r, c] = raw[r, c ^ (r & 7)]
+        return out.reshape(208, 128), int(sum_t.value)
 
     @staticmethod
     def fft128_twiddles():

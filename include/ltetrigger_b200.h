@@ -62,7 +62,9 @@ extern "C" {
 #define LTB_FRONTEND_TC_INT 1      /* exact integer arithmetic on the tensor cores (tcgen05.mma kind::i8): taps
                                       quantised to three balanced base-256 digits, the int16 / int8 samples are
                                       their own digits, int32 accumulation in TMEM, one rounding to float32 per
-                                      output.  sc16 / sc8 input at decim = 16 only; needs 16-byte aligned rows */
+                                      output.  decim = 16 only; needs 16-byte aligned rows.  fc32 input is first
+                                      put on a 23-bit fixed-point grid over +-fc32_full_scale (what a float sample
+                                      of an ADC-fed source carries anyway); from there on the same exact integers */
 
 /* how the stages of consecutive calls are scheduled (results are identical) */
 #define LTB_PIPE_OVERLAP 0         /* with two calls in flight (submit/collect), the per-chain track + SSS kernels of
@@ -148,6 +150,8 @@ typedef struct {
   int32_t  frame_type;        /* LTB_FRAME_*; default (0, or a shorter struct_size) is FDD like the reference */
   int32_t  frontend_mode;     /* LTB_FRONTEND_*; default 0 = canonical FP32 */
   int32_t  pipeline;          /* LTB_PIPE_*; default 0 = overlapped */
+  float    fc32_full_scale;   /* LTB_FRONTEND_TC_INT on fc32 input only: the range the samples are quantised over
+                                 (23-bit fixed point, |re|, |im| beyond it saturate); 1.0 for a UHD-style source */
 } ltb_trigger_config;
 
 /* pss::make + sss::make + hier-block construction (lib/pss_impl.cc:42-83,
@@ -254,6 +258,9 @@ LTB_API int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_s
  * samples (both multiples of 128; the raw history is carried between the calls as the engine does);
  * y: [n_streams][n_in / 16]. */
 LTB_API int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y);
+/* the same with the fc32 variant available: fmt LTB_FMT_FC32 takes float I/Q as 23-bit fixed point over +-full_scale */
+LTB_API int ltb_kernel_decimate_tc_host2(int device, const void *x, int fmt, float full_scale, int n_streams, int64_t n_in,
+                                         int64_t chunk, ltb_cf *y);
 
 #ifdef LTB_DEBUG
 /* Only in the debug build (make -C gr-ltetrigger_b200 debug -> lib/libltetrigger_b200_debug.so, -DLTB_DEBUG);
@@ -277,6 +284,10 @@ LTB_API int ltb_table_fft128_twiddles(float w_re[64], float w_im[64]);
 /* LTB_CORR_FFT: W_1024^i and the filter spectrum 2^-10 DFT_1024(h) of one N_id_2, natural order */
 LTB_API int ltb_table_fft1024_twiddles(float w_re[1024], float w_im[1024]);
 LTB_API int ltb_table_os_filter(int n_id_2, float H_re[1024], float H_im[1024]);
+/* LTB_FRONTEND_TC_INT: the tap table of the tensor-core kernel for input format fmt, in its shared-memory image
+ * ([208 rows][128 bytes], K-major, 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)), and the sum
+ * of the 525 integer taps T[j] = rint(taps[j] * 2^27).  tests/test_tc_formulation.py replays the kernel's k-steps from it. */
+LTB_API int ltb_table_tc_btab(int fmt, int8_t tab[208 * 128], int64_t *sum_t);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,60 @@
 #define FFTN 9728                  /* frame_size + fft_size: the reference's conv FFT size [A.2] */
 #define PSS_EMA_ALPHA 0.2f         /* q->ema_alpha default [A.2 step 3] */
 
+/* fc32 input through the same front end: the product first puts each float on a 23-bit fixed-point grid over
+ * +-full_scale (ltb_tc_frontend.cuh tc_split<LTB_FMT_FC32>; two fused multiply-adds, the first saturating to [0, 1]):
+ *   u = sat(fma(x, 0.5 / full_scale, 0.5))     m = bits(fma(u, 2^23 - 2, 2^23 + 1)) & 0x7fffff     1 <= m <= 2^23 - 1
+ * and then evaluates, exactly,
+ *   A[k] = sum_j ( T[j] (m[16 k - j] - 2^22) - lo8(m[16 k - j]) * d0(T[j]) )
+ * i.e. the sum of all byte x tap-digit products except the one of weight 1 (lowest sample byte times lowest balanced
+ * tap digit: four accumulator columns per output hold the weights 256 .. 256^4, nothing is kept for weight 1; the
+ * omitted term is some 2^-30 of full scale).  A is a multiple of 256;
+ *   y[k] = (float)(A[k] / 256) * out_scale     out_scale = (float)(full_scale / (2^22 - 1) / 2^19)
+ * Samples before the stream are zeros (m = 2^22, low byte 0: no contribution). */
+static uint32_t tcq_fc32(float x, float q_inv)
+{
+  float u = fmaf(x, q_inv, 0.5f);
+  if (!(u > 0.0f)) u = 0.0f;                 /* also NaN -> 0, as fma.rn.sat does */
+  if (u > 1.0f) u = 1.0f;
+  float t = fmaf(u, 8388606.0f, 8388609.0f);
+  uint32_t b; memcpy(&b, &t, 4);
+  return b & 0x7fffffu;
+}
+
+int64_t orc_decimate_tcint_fc32(const orc_cf *x, int64_t n_in, float full_scale, orc_cf *y)
+{
+  const int decim = 16;
+  float taps[4096];
+  int ntaps = orc_decim_taps(decim, taps, 4096);
+  if (ntaps != 525 || !(full_scale > 0.0f)) return -1;
+  int32_t T[528], D0[528];
+  for (int j = 0; j < ntaps; j++) {
+    T[j] = (int32_t)llrint((double)taps[j] * 134217728.0);
+    D0[j] = ((T[j] + 128) & 255) - 128;      /* lowest balanced base-256 digit */
+  }
+  const float q_inv = (float)(0.5 / (double)full_scale);
+  const float out_scale = (float)((double)full_scale / 4194303.0 / 524288.0);
+  int32_t *m = malloc(sizeof(int32_t) * 2 * (size_t)n_in);
+  for (int64_t i = 0; i < n_in; i++) { m[2 * i] = (int32_t)tcq_fc32(x[i].re, q_inv); m[2 * i + 1] = (int32_t)tcq_fc32(x[i].im, q_inv); }
+  int64_t n_out = (n_in + decim - 1) / decim;
+  for (int64_t k = 0; k < n_out; k++) {
+    int64_t are = 0, aim = 0;
+    const int64_t top = k * decim;
+    const int jmax = top < ntaps - 1 ? (int)top : ntaps - 1;
+    const int32_t *mp = m + 2 * top;
+    for (int j = 0; j <= jmax; j++) {
+      const int32_t mr = mp[-2 * j], mi = mp[-2 * j + 1];
+      are += (int64_t)T[j] * (mr - 4194304) - (int64_t)(mr & 255) * D0[j];
+      aim += (int64_t)T[j] * (mi - 4194304) - (int64_t)(mi & 255) * D0[j];
+    }
+    if ((are & 255) || (aim & 255)) { free(m); return -1; }      /* cannot happen: every kept product has weight >= 256 */
+    y[k].re = (float)(are / 256) * out_scale;
+    y[k].im = (float)(aim / 256) * out_scale;
+  }
+  free(m);
+  return n_out;
+}
+
 /* ------------------------------------------------------------------------- */
 /* Tables                                                                     */
 /* ------------------------------------------------------------------------- */
@@ -1176,14 +1230,16 @@ typedef struct {
   const void *iq; int fmt; int64_t n_in, n_out; int decim;
   float thr; int track_after, track_every, conv_mode;
   orc_cf **ys; orc_rec *tmp; int *cnt; size_t per_stream; int per_chain; int fail;
+  float full_scale;
 } trig_t;
 
 static void trig_frontend(int s, void *arg)
 {
   trig_t *t = (trig_t *)arg;
-  if ((t->conv_mode & ORC_FRONT_TCINT) && t->fmt != 0 && t->decim == 16) {   /* integer front end */
+  if ((t->conv_mode & ORC_FRONT_TCINT) && t->decim == 16 && (t->fmt != 0 || t->full_scale > 0.0f)) {   /* integer front end */
     t->ys[s] = malloc(sizeof(orc_cf) * t->n_out);
-    int64_t rc = t->fmt == 1 ? orc_decimate_tcint_sc16((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->ys[s])
+    int64_t rc = t->fmt == 0 ? orc_decimate_tcint_fc32((const orc_cf *)t->iq + (size_t)s * t->n_in, t->n_in, t->full_scale, t->ys[s])
+               : t->fmt == 1 ? orc_decimate_tcint_sc16((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->ys[s])
                              : orc_decimate_tcint_sc8((const int8_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->ys[s]);
     if (rc < 0) t->fail = 1;
     return;
@@ -1215,9 +1271,16 @@ int orc_trigger_run(const void *iq, int fmt, int64_t n_in, int n_streams, int de
                     float thr, int track_after, int track_every, int conv_mode,
                     int nthreads, orc_rec *recs, int max_recs)
 {
+  return orc_trigger_run2(iq, fmt, n_in, n_streams, decim, thr, track_after, track_every, conv_mode, 0.0f, nthreads, recs, max_recs);
+}
+
+int orc_trigger_run2(const void *iq, int fmt, int64_t n_in, int n_streams, int decim,
+                     float thr, int track_after, int track_every, int conv_mode, float fc32_full_scale,
+                     int nthreads, orc_rec *recs, int max_recs)
+{
   tables_init();
   if (thr <= 1.5f) thr = 1.5f;                              /* downlink_trigger_c.py:71-73 */
-  trig_t t = { iq, fmt, n_in, 0, decim, thr, track_after, track_every, conv_mode, NULL, NULL, NULL, 0, 0, 0 };
+  trig_t t = { iq, fmt, n_in, 0, decim, thr, track_after, track_every, conv_mode, NULL, NULL, NULL, 0, 0, 0, fc32_full_scale };
   t.n_out = (decim <= 1) ? n_in : (n_in + decim - 1) / decim;
   t.per_chain = (int)(t.n_out / (ORC_HALF - ORC_SLOT)) + 2;
   t.per_stream = 3 * (size_t)t.per_chain;

@@ -149,6 +149,8 @@ int      orc_sss_work(orc_sss *, const orc_cf *in, int tag_lost, orc_cf *out, or
  * rounding per output.  Returns the number of outputs, -1 on error. */
 int64_t orc_decimate_tcint_sc16(const int16_t *iq, int64_t n_in, orc_cf *y);
 int64_t orc_decimate_tcint_sc8(const int8_t *iq, int64_t n_in, orc_cf *y);
+/* fc32 input taken as 23-bit fixed point over +-full_scale, then the same exact integers (see the .c file) */
+int64_t orc_decimate_tcint_fc32(const orc_cf *x, int64_t n_in, float full_scale, orc_cf *y);
 
 /* ---- whole chains ------------------------------------------------------------ */
 /* pss(N_id_2) -> sss(N_id_2) over one search-rate stream y[0..n) (GR zero history before it),
@@ -165,6 +167,11 @@ int orc_chain_run(const orc_cf *y, int64_t n, int stream, int n_id_2, float psr_
 int orc_trigger_run(const void *iq, int fmt, int64_t n_in_per_stream, int n_streams, int decim,
                     float psr_threshold, int track_after, int track_every, int conv_mode,
                     int nthreads, orc_rec *recs, int max_recs);
+/* the same with the range of the fixed-point grid that ORC_FRONT_TCINT puts fc32 input on (0: fc32 input keeps the
+ * float32 decimator) */
+int orc_trigger_run2(const void *iq, int fmt, int64_t n_in_per_stream, int n_streams, int decim,
+                     float psr_threshold, int track_after, int track_every, int conv_mode, float fc32_full_scale,
+                     int nthreads, orc_rec *recs, int max_recs);
 
 #ifdef __cplusplus
 }

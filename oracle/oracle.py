@@ -63,6 +63,11 @@ def lib():
         L.orc_decimate_tcint_sc16.restype = C.c_int64
         L.orc_decimate_tcint_sc8.argtypes = [vp, C.c_int64, vp]
         L.orc_decimate_tcint_sc8.restype = C.c_int64
+        L.orc_decimate_tcint_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
+        L.orc_decimate_tcint_fc32.restype = C.c_int64
+        L.orc_trigger_run2.argtypes = [vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                       C.c_int, C.c_float, C.c_int, vp, C.c_int]
+        L.orc_trigger_run2.restype = C.c_int
         L.orc_sc16_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_sc8_to_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_pss_corr_window.argtypes = [vp, C.c_int, C.c_int, fp]
@@ -163,6 +168,16 @@ def decimate_tcint_sc8(iq):
     y = np.zeros((n + 15) // 16, np.complex64)
     if lib().orc_decimate_tcint_sc8(iq.ctypes.data, n, y.ctypes.data) < 0:
         raise RuntimeError("orc_decimate_tcint_sc8 failed")
+    return y
+
+
+def decimate_tcint_fc32(x, full_scale):
+    """The same for complex64 input taken as 23-bit fixed point over +-full_scale."""
+    x = np.ascontiguousarray(x, np.complex64)
+    n = x.shape[0]
+    y = np.zeros((n + 15) // 16, np.complex64)
+    if lib().orc_decimate_tcint_fc32(x.ctypes.data, n, float(full_scale), y.ctypes.data) < 0:
+        raise RuntimeError("orc_decimate_tcint_fc32 failed")
     return y
 
 
@@ -309,8 +324,9 @@ def chain_run(y, n_id_2, psr_threshold=4.0, track_after=16, track_every=8, conv_
 
 
 def trigger_run(iq, decim=1, fmt=0, psr_threshold=4.0, track_after=16, track_every=8,
-                conv_mode=CONV_DIRECT, nthreads=0):
-    """iq: [n_streams, n_in] complex64 (fmt 0), [n_streams, n_in, 2] int16 (fmt 1) or int8 (fmt 2)."""
+                conv_mode=CONV_DIRECT, nthreads=0, fc32_full_scale=0.0):
+    """iq: [n_streams, n_in] complex64 (fmt 0), [n_streams, n_in, 2] int16 (fmt 1) or int8 (fmt 2).
+    fc32_full_scale: with FRONT_TCINT in conv_mode, fc32 input goes through the fixed-point integer front end."""
     if fmt == 0:
         iq = np.ascontiguousarray(iq, np.complex64)
         n_streams, n_in = iq.shape
@@ -320,8 +336,8 @@ def trigger_run(iq, decim=1, fmt=0, psr_threshold=4.0, track_after=16, track_eve
     n_out = (n_in + decim - 1) // decim if decim > 1 else n_in
     max_recs = n_streams * 3 * (n_out // (HALF - SLOT) + 2)
     recs = np.zeros(max_recs, REC_DTYPE)
-    n = lib().orc_trigger_run(iq.ctypes.data, fmt, n_in, n_streams, decim, psr_threshold, track_after,
-                              track_every, conv_mode, nthreads, recs.ctypes.data, max_recs)
+    n = lib().orc_trigger_run2(iq.ctypes.data, fmt, n_in, n_streams, decim, psr_threshold, track_after,
+                               track_every, conv_mode, float(fc32_full_scale), nthreads, recs.ctypes.data, max_recs)
     if n < 0:
         raise RuntimeError("orc_trigger_run failed")
     return recs[:n].copy()

@@ -35,8 +35,9 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts():
     from ltetrigger_b200 import _abi
     assert _abi.WINDOW_REC.itemsize == 88
-    assert C.sizeof(_abi.TriggerConfig) == 80 and _abi.TriggerConfig.corr_mode.offset == 64
+    assert C.sizeof(_abi.TriggerConfig) == 88 and _abi.TriggerConfig.corr_mode.offset == 64
     assert _abi.TriggerConfig.frontend_mode.offset == 72 and _abi.TriggerConfig.pipeline.offset == 76
+    assert _abi.TriggerConfig.fc32_full_scale.offset == 80
     assert C.sizeof(_abi.PssStats) == 32
     from oracle import oracle as O
     assert O.REC_DTYPE == _abi.WINDOW_REC

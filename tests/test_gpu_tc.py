@@ -86,8 +86,73 @@ def test_tc_front_end_through_the_engine(lt, oracle, corr, fmt):
     np.testing.assert_allclose(got["peak_value"][sel], fp["peak_value"][sel], rtol=1e-4)
 
 
+@pytest.mark.parametrize("n_out,chunk", [(976 * 3, None), (5000, None), (20000, 128 * 37), (20000, 128 * 2), (61 * 16 * 5 + 8, 128 * 125)])
+def test_tc_decimator_fc32_fixed_point_bit_exact(lt, oracle, n_out, chunk):
+    """fc32 input taken as 23-bit fixed point over +-full_scale: gaussian samples, streams pinned at the two
+    saturation levels and beyond them, NaN / Inf / denormal samples; every output equal to the oracle's
+    int64 evaluation of the same quantised samples, in ragged chunks."""
+    rng = np.random.default_rng(n_out + 1)
+    n = n_out * 16
+    fs = 3.0
+    x = (rng.standard_normal((4, n)) + 1j * rng.standard_normal((4, n))).astype(np.complex64) * np.float32(0.6)
+    x[1] = fs * (1 + 1j)                                   # upper saturation level exactly
+    x[2] = -5 * fs + 0j                                    # far below the range: saturates
+    odd = np.array([np.nan, np.inf, -np.inf, 1e-42, -0.0, fs, -fs, fs * (1 - 2.0 ** -23)], np.float32)
+    x[3, :4096].real = np.tile(odd, 512)
+    x[3, 4096:8192].imag = np.tile(odd[::-1], 512)
+    got = lt.kernel_decimate_tc(x, chunk=chunk, full_scale=fs)
+    for s in range(4):
+        want = oracle.decimate_tcint_fc32(x[s], fs)
+        assert np.array_equal(_bits(got[s]), _bits(want)), (s, int(np.argmax(_bits(got[s]) != _bits(want))))
+
+
+def test_tc_decimator_fc32_within_tolerance_of_float32_front_end(lt, oracle):
+    """north_star: magnitudes within 1e-4 relative.  With the signal's rms at 1/8 of the declared range the
+    fixed-point grid (2^-23 of the range per sample) leaves ~1e-6 of the output's rms."""
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal((2, 16 * 4000)) + 1j * rng.standard_normal((2, 16 * 4000))).astype(np.complex64)
+    got = lt.kernel_decimate_tc(x, full_scale=8.0)
+    ref = lt.kernel_decimate(x, 16, lt.FMT_FC32)
+    assert np.abs(got - ref).max() < 2e-5 * np.sqrt(np.mean(np.abs(ref) ** 2))
+
+
+@pytest.mark.parametrize("corr", ["fft", "direct"])
+def test_tc_front_end_fc32_through_the_engine(lt, oracle, corr):
+    """The 100 PRB fixture and synthetic cells as fc32 at 30.72 Msps through the whole chain with the fixed-point
+    tensor-core front end, in ragged chunks: records bit-identical to the oracle in the same mode, the same
+    decisions as the float32 front end and magnitudes within 1e-4 of it."""
+    from ltetrigger_b200 import synth
+    x, decim, cell_id = load_fixture("100prb", 0.25)
+    rows = [x, synth.capture(77, len(x), snr_db=3.0, decim=16, seed=5, cfo_hz=1500.0),
+            synth.capture(300, len(x), snr_db=0.0, decim=16, seed=6, noise_only=True)]
+    iq = np.stack(rows).astype(np.complex64)
+    fs = float(8 * np.sqrt(np.mean(np.abs(iq) ** 2)))
+    mode = lt.CORR_FFT if corr == "fft" else lt.CORR_DIRECT
+    conv = (oracle.CONV_OS if corr == "fft" else oracle.CONV_DIRECT) | oracle.FRONT_TCINT
+    chunk = 16 * 8 * 4001
+    trig = lt.Trigger(n_streams=3, decim=16, max_chunk=chunk, input_format=lt.FMT_FC32, corr_mode=mode,
+                      frontend_mode=lt.FRONTEND_TC_INT, fc32_full_scale=fs)
+    got = trig.run(iq, chunk=chunk)
+    trig.close()
+    want = oracle.trigger_run(iq, decim=16, fmt=lt.FMT_FC32, conv_mode=conv, fc32_full_scale=fs)
+    assert_recs_equal(got, want)
+    cells = got[(got["flags"] & lt.F_CELL) != 0]
+    assert set(cells[cells["stream"] == 0]["cell_id"].tolist()) == {cell_id}
+    assert set(cells[cells["stream"] == 1]["cell_id"].tolist()) == {77}
+    ref = lt.Trigger(n_streams=3, decim=16, max_chunk=chunk, input_format=lt.FMT_FC32, corr_mode=mode)
+    fp = ref.run(iq, chunk=chunk)
+    ref.close()
+    sel = (got["stream"] < 2)
+    for f in ("win_start", "emit_start", "flags", "peak_pos", "m0", "m1", "n_id_1", "cell_id"):
+        assert (got[f][sel] == fp[f][sel]).all(), f
+    np.testing.assert_allclose(got["psr"][sel], fp["psr"][sel], rtol=1e-4)
+    np.testing.assert_allclose(got["peak_value"][sel], fp["peak_value"][sel], rtol=1e-4)
+
+
 def test_tc_front_end_argument_checks(lt):
     with pytest.raises(lt.LtbError):
-        lt.Trigger(n_streams=1, decim=16, input_format=lt.FMT_FC32, frontend_mode=lt.FRONTEND_TC_INT)   # integer input only
+        lt.Trigger(n_streams=1, decim=16, input_format=lt.FMT_FC32, frontend_mode=lt.FRONTEND_TC_INT)   # fc32 needs its range
+    with pytest.raises(lt.LtbError):
+        lt.Trigger(n_streams=1, decim=16, input_format=lt.FMT_FC32, frontend_mode=lt.FRONTEND_TC_INT, fc32_full_scale=-1.0)
     with pytest.raises(lt.LtbError):
         lt.Trigger(n_streams=1, decim=8, input_format=lt.FMT_SC16, frontend_mode=lt.FRONTEND_TC_INT)    # decim 16 only

@@ -3,7 +3,7 @@
 // evaluation on the host, then timed.  One variant per process (a watchdog trap poisons the context):
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o tools/ubench_tc_i8 tools/ubench_tc_i8.cu
-//   ./tools/ubench_tc_i8 <fmt = 1 (sc16) | 2 (sc8)> [n_streams] [n_in per stream] [chunks]
+//   ./tools/ubench_tc_i8 <fmt = 0 (fc32 as 23-bit fixed point) | 1 (sc16) | 2 (sc8)> [n_streams] [n_in per stream] [chunks]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -45,6 +45,19 @@ static std::vector<int8_t> make_btab(int fmt, const std::vector<int> &T) {
   std::vector<int8_t> tab((size_t)kTcBTileBytes, 0);
   auto tapq = [&](int j) { return (j >= 0 && j < (int)T.size()) ? T[j] : 0; };
   const bool sc16 = fmt == 1;
+  if (fmt == 0) {
+    for (int n = 0; n < kTcBRows; ++n) {
+      const int d = n / 4, v = n % 4 + 1;
+      if (d > 33) continue;
+      for (int h = 0; h < 2; ++h)
+        for (int p8 = 0; p8 < 8; ++p8)
+          for (int bi = 0; bi < 3; ++bi) {
+            const int i = v - bi, kb = 32 * h + 4 * p8 + bi;
+            if (i >= 0 && i <= 2) tab[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)digit(tapq(16 * d - 8 * h - p8), i);
+          }
+    }
+    return tab;
+  }
   for (int n = 0; n < kTcBRows; ++n) {
     const int d = n / 4, v = n % 4;
     if (d > (sc16 ? 33 : 34)) continue;
@@ -73,12 +86,14 @@ static void launch(const CUtensorMap &map, const TcParams &P, int grid) {
 }
 
 int main(int argc, char **argv) {
-  const int G = argc > 1 ? atoi(argv[1]) : 1;            // input format: 1 sc16, 2 sc8
-  const int bps = G == 1 ? 4 : 2;
+  const int G = argc > 1 ? atoi(argv[1]) : 1;            // input format: 0 fc32, 1 sc16, 2 sc8
+  const int bps = G == 0 ? 8 : G == 1 ? 4 : 2;
+  const float FS = 2.0f;                                 // fc32: declared range
+  const float q_inv = (float)(0.5 / (double)FS), out_scale = (float)((double)FS / 4194303.0 / 524288.0);
   const int S = argc > 2 ? atoi(argv[2]) : 64;
   const int n_in = argc > 3 ? atoi(argv[3]) : 3072000;
   const int chunks = argc > 4 ? atoi(argv[4]) : 1;       // > 1: feed the stream in `chunks` calls (tail carried)
-  if (G != 1 && G != 2) { fprintf(stderr, "fmt must be 1 (sc16) or 2 (sc8)\n"); return 2; }
+  if (G < 0 || G > 2) { fprintf(stderr, "fmt must be 0 (fc32), 1 (sc16) or 2 (sc8)\n"); return 2; }
   const std::vector<float> tf = taps16();
   std::vector<int> T(tf.size());
   long long sumT = 0;
@@ -88,22 +103,32 @@ int main(int argc, char **argv) {
   const size_t row_bytes = (size_t)n_in * bps;
   std::vector<short> x((size_t)S * n_in * 2);        // sample values (sc8: within -128..127), packed below
   srand(12345);
-  for (auto &v : x) v = G == 1 ? (short)((rand() & 0xffff) - 32768) : (short)((rand() & 0xff) - 128);
+  for (auto &v : x) v = G != 2 ? (short)((rand() & 0xffff) - 32768) : (short)((rand() & 0xff) - 128);
   // a few structured streams: extremes exercise the digit bounds
-  for (int i = 0; i < n_in * 2 && S > 2; ++i) { x[(size_t)1 * n_in * 2 + i] = G == 1 ? 32767 : 127; x[(size_t)2 * n_in * 2 + i] = G == 1 ? -32768 : -128; }
+  for (int i = 0; i < n_in * 2 && S > 2; ++i) { x[(size_t)1 * n_in * 2 + i] = G != 2 ? 32767 : 127; x[(size_t)2 * n_in * 2 + i] = G != 2 ? -32768 : -128; }
   std::vector<signed char> x8;
   if (G == 2) { x8.resize(x.size()); for (size_t i = 0; i < x.size(); ++i) x8[i] = (signed char)x[i]; }
+  // fc32: floats over +-1.25 x the declared range (some saturate); mq = the 23-bit fixed-point value the kernel must form
+  std::vector<float> xf; std::vector<int> mq;
+  auto quant = [&](float v) {
+    float u = fmaf(v, q_inv, 0.5f); if (!(u > 0.f)) u = 0.f; if (u > 1.f) u = 1.f;
+    const float t = fmaf(u, kTcQMul, kTcQAdd); unsigned b; memcpy(&b, &t, 4); return (int)(b & 0x7fffffu);
+  };
+  if (G == 0) {
+    xf.resize(x.size()); mq.resize(x.size());
+    for (size_t i = 0; i < x.size(); ++i) { xf[i] = (float)x[i] * (1.25f * FS / 32768.0f) * (1.0f + 1e-3f * (float)(rand() & 1023)); mq[i] = quant(xf[i]); }
+  }
 
   void *d_x; void *d_tail[2]; float2 *d_y; int8_t *d_b; int *d_err; int *d_acc;
   cudaMalloc(&d_acc, 128 * kTcBRows * 4); cudaMemset(d_acc, 0x7f, 128 * kTcBRows * 4);
   const int m_total = n_in / 16;
   int cap = 1; while (cap < m_total + 64) cap <<= 1;
   cudaMalloc(&d_x, (size_t)S * row_bytes);
-  cudaMalloc(&d_tail[0], (size_t)S * kTcTailSamples * 4); cudaMalloc(&d_tail[1], (size_t)S * kTcTailSamples * 4);
-  cudaMemset(d_tail[0], 0, (size_t)S * kTcTailSamples * 4);
+  cudaMalloc(&d_tail[0], (size_t)S * kTcTailSamples * 8); cudaMalloc(&d_tail[1], (size_t)S * kTcTailSamples * 8);
+  cudaMemset(d_tail[0], 0, (size_t)S * kTcTailSamples * 8);
   cudaMalloc(&d_y, (size_t)S * cap * 8); cudaMemset(d_y, 0xff, (size_t)S * cap * 8);
   cudaMalloc(&d_b, btab.size()); cudaMalloc(&d_err, 4); cudaMemset(d_err, 0, 4);
-  cudaMemcpy(d_x, G == 1 ? (const void *)x.data() : (const void *)x8.data(), (size_t)S * row_bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_x, G == 0 ? (const void *)xf.data() : G == 1 ? (const void *)x.data() : (const void *)x8.data(), (size_t)S * row_bytes, cudaMemcpyHostToDevice);
   cudaMemcpy(d_b, btab.data(), btab.size(), cudaMemcpyHostToDevice);
 
   EncodeTiled encode = nullptr;
@@ -128,14 +153,16 @@ int main(int argc, char **argv) {
     P.tail = d_tail[tail_cur]; P.y_ring = d_y; P.n_base = c0 / 16; P.cap_mask = (unsigned)(cap - 1); P.cap = cap;
     const int rows = (n_chunk + kTcRowSamples - 1) / kTcRowSamples;
     P.tiles_per_stream = (rows + kTcUseful - 1) / kTcUseful; P.total_tiles = P.tiles_per_stream * S;
-    P.btab = d_b; P.c_const = G == 1 ? 128 * sumT : 0; P.err = d_err; P.dbg_acc = c0 == 0 ? d_acc : nullptr;
+    P.btab = d_b; P.c_const = G == 1 ? 128 * sumT : G == 0 ? -16384 * sumT : 0; P.err = d_err; P.dbg_acc = c0 == 0 ? d_acc : nullptr;
+    P.q_inv = q_inv; P.out_scale = G == 0 ? out_scale : G == 1 ? 2.2737367544323206e-13f : 5.8207660913467407e-11f;
     const int grid = P.total_tiles < sms ? P.total_tiles : sms;
-    if (G == 1) { launch<LTB_FMT_SC16>(map, P, grid); tc_tail_kernel<LTB_FMT_SC16><<<S, 256>>>(P.in, P.stride_bytes, n_chunk, d_tail[tail_cur], d_tail[tail_cur ^ 1]); }
+    if (G == 0) { launch<LTB_FMT_FC32>(map, P, grid); tc_tail_kernel<LTB_FMT_FC32><<<S, 256>>>(P.in, P.stride_bytes, n_chunk, d_tail[tail_cur], d_tail[tail_cur ^ 1]); }
+    else if (G == 1) { launch<LTB_FMT_SC16>(map, P, grid); tc_tail_kernel<LTB_FMT_SC16><<<S, 256>>>(P.in, P.stride_bytes, n_chunk, d_tail[tail_cur], d_tail[tail_cur ^ 1]); }
     else { launch<LTB_FMT_SC8>(map, P, grid); tc_tail_kernel<LTB_FMT_SC8><<<S, 256>>>(P.in, P.stride_bytes, n_chunk, d_tail[tail_cur], d_tail[tail_cur ^ 1]); }
     return 0;
   };
   auto run_all = [&]() -> int {
-    cudaMemset(d_tail[0], 0, (size_t)S * kTcTailSamples * 4);
+    cudaMemset(d_tail[0], 0, (size_t)S * kTcTailSamples * 8);
     int tc = 0, c0 = 0;
     for (int c = 0; c < chunks; ++c) {
       int n_chunk = (c == chunks - 1) ? n_in - c0 : (n_in / chunks) / 128 * 128;
@@ -165,7 +192,10 @@ int main(int argc, char **argv) {
           if (j < 0 || j > 524) continue;
           const long long nidx = (long long)row * 256 + p;
           const int xv = nidx >= 0 && nidx < n_in ? x[2 * nidx + comp] : 0;
-          if (G == 1) {
+          if (G == 0) {
+            const int m = nidx >= 0 && nidx < n_in ? mq[2 * nidx + comp] : kTcQMid;
+            for (int bi = 0; bi < 3; ++bi) { const int i = v + 1 - bi; if (i >= 0 && i <= 2) want += (long long)((m >> (8 * bi)) & 255) * digit(T[j], i); }
+          } else if (G == 1) {
             const int lo = (xv & 255) - 128, hi = xv >> 8;
             want += (long long)lo * (v <= 2 ? digit(T[j], v) : 0) + (long long)hi * (v >= 1 ? digit(T[j], v - 1) : 0);
           } else {
@@ -189,9 +219,14 @@ int main(int argc, char **argv) {
       for (int j = 0; j < 525; ++j) {
         const long long n = 16LL * k - j;
         if (n < 0) break;
-        are += (long long)T[j] * xs[2 * n]; aim += (long long)T[j] * xs[2 * n + 1];
+        if (G == 0) {
+          const int mr = mq[(size_t)s * n_in * 2 + 2 * n], mi = mq[(size_t)s * n_in * 2 + 2 * n + 1];
+          are += (long long)T[j] * (mr - kTcQMid) - (long long)(mr & 255) * digit(T[j], 0);
+          aim += (long long)T[j] * (mi - kTcQMid) - (long long)(mi & 255) * digit(T[j], 0);
+        } else { are += (long long)T[j] * xs[2 * n]; aim += (long long)T[j] * xs[2 * n + 1]; }
       }
-      const float sc = G == 1 ? 2.2737367544323206e-13f : 5.8207660913467407e-11f;
+      if (G == 0) { are /= 256; aim /= 256; }
+      const float sc = G == 0 ? out_scale : G == 1 ? 2.2737367544323206e-13f : 5.8207660913467407e-11f;
       const float wre = (float)are * sc, wim = (float)aim * sc;
       const float2 g = y[(size_t)s * cap + k];
       checked++;
