@@ -69,13 +69,20 @@ def parse():
     ap.add_argument("--workload", default="c5", choices=["c5", "c1", "c2", "c3"],
                     help="c5 (default): BASELINE's batched shard, the metric's configuration; c1/c2/c3: the single-stream "
                          "configurations (latency to first track, C-ABI and block-path throughput; tools/bench_single.py)")
-    ap.add_argument("--frontend", default="fp32", choices=["fp32", "tc"],
-                    help="fp32: canonical FFMA2 decimator; tc: exact-integer tensor-core front end (sc16, D=16)")
+    ap.add_argument("--frontend", default="auto", choices=["auto", "fp32", "tc"],
+                    help="fp32: canonical FFMA2 decimator; tc: exact-integer tensor-core front end (D = 16; fc32 input on a "
+                         "23-bit fixed-point grid); auto: tc where it exists (D = 16: it meets the tolerance and wins), else "
+                         "fp32.  The other mode is timed on the same input and reported under other_frontend")
     ap.add_argument("--pipeline", default="overlap", choices=["overlap", "serial"],
                     help="overlap: track+SSS of call i under the front end of call i+1 (two streams); serial: one stream")
     ap.add_argument("--no-spot-check", action="store_true", help="skip the per-rank oracle check after timing")
+    ap.add_argument("--no-alt", action="store_true", help="skip the run of the other front-end mode on the same input")
+    ap.add_argument("--no-alone", action="store_true", help="skip the 3-step serial pass that times every kernel alone")
     ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the extra sustained run (0: skip)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.frontend == "auto":
+        a.frontend = "tc" if (a.decim == 16 and a.workload == "c5" and a.impl == "b200") else "fp32"
+    return a
 
 
 def workload_name(a):
@@ -280,129 +287,163 @@ def main():
 
     stream = torch.cuda.current_stream()
     corr_mode = lt.CORR_FFT if a.corr == "fft" else lt.CORR_DIRECT
-    frontend_kw, oracle_front_flag = {}, 0
-    if a.frontend == "tc":
-        from oracle import oracle as O_
-        frontend_kw, oracle_front_flag = {"frontend_mode": lt.FRONTEND_TC_INT}, O_.FRONT_TCINT
-        if a.format == "fc32":
-            # fc32 through the integer tensor-core front end: 23-bit fixed point over the same range the sc16 / sc8
-            # quantiser above uses (8 x the signal's rms)
-            frontend_kw["fc32_full_scale"] = 8.0
     pipeline = lt.PIPE_OVERLAP if a.pipeline == "overlap" else lt.PIPE_SERIAL
-    trig = lt.Trigger(n_streams=a.streams, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
-                      record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode,
-                      pipeline=pipeline, **frontend_kw)
     ptr, stride = d_in.data_ptr(), n * bps
+    FC32_FULL_SCALE = 8.0      # fc32 through the integer front end: 23-bit fixed point over the range the sc16 / sc8
+                               # quantiser above uses (8 x the signal's rms)
 
-    def step():
-        return trig.process_device_ptr(ptr, stride, n)
+    def mode_kw(frontend, format_name):
+        """(Trigger keyword arguments, oracle conv_mode flag, oracle full scale) of a front-end mode."""
+        if frontend != "tc":
+            return {}, 0, 0.0
+        from oracle import oracle as O_
+        kw = {"frontend_mode": lt.FRONTEND_TC_INT}
+        if format_name == "fc32":
+            kw["fc32_full_scale"] = FC32_FULL_SCALE
+        return kw, O_.FRONT_TCINT, kw.get("fc32_full_scale", 0.0)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(a.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler.begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = np.zeros(4)
-    launches = 0
-    n_cells = 0
-    torch.cuda.synchronize()
-    e0.record(stream)
-    # two calls in flight (ltb_trigger_submit_device / ltb_trigger_collect): call i+1 is enqueued
-    # before the records of call i are read, so the stream does not idle on the host round trip
-    last_recs = None
-
-    def account(recs):
-        nonlocal stage_ms, launches, n_cells, last_recs
-        last_recs = recs
-        stage_ms += np.array(trig.last_kernel_times())
-        launches += trig.last_timing()[1]
-        n_cells += int(((recs["flags"] & lt.F_CELL) != 0).sum())
-
-    trig.submit_device_ptr(ptr, stride, n)
-    for _ in range(a.steps - 1):
-        trig.submit_device_ptr(ptr, stride, n)
-        account(trig.collect())
-    account(trig.collect())
-    e1.record(stream)
-    torch.cuda.synchronize()
-    elapsed_ms = e0.elapsed_time(e1)
-    clocks = sampler.result()
-    if world > 1:
-        tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.barrier()
-        elapsed_ms = float(tt.item())
-    total_samples = float(a.streams) * n * a.steps * world
-    value = total_samples / (elapsed_ms * 1e-3) / 1e6
-
-    # ---- roofline of the dominant kernel (live CUDA-event durations of the timed steps) -----
-    stage_ms /= a.steps
     names = ["frontend(convert+decimate)", "pss_corr(3 roots)", "pss_track", "sss"]
     names_short = ["frontend", "pss_corr", "pss_track", "sss"]
-    alg_flop = [4.0 * ntaps(a.decim) * m * a.streams, float(F_PSS) * m * a.streams, 0.0, 0.0]
-    dom = int(np.argmax(stage_ms))
-    if alg_flop[dom] == 0.0:
-        dom = int(np.argmax(stage_ms[:2]))
-    achieved = alg_flop[dom] / (stage_ms[dom] * 1e-3) / 1e12
-    alg_bytes = [float(bps) * n * a.streams + 8.0 * m * a.streams, 20.0 * m * a.streams, 0.0, 0.0]
-    traffic = None                                                  # dram read+write per launch, ncu --set full
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tr.get("workload") == workload_name(a):
-            traffic = tr["dram_bytes_per_launch"].get(names_short[dom])
-    except Exception:
-        pass
-    f_alg = (F_PSS + 4.0 * ntaps(a.decim)) / a.decim                # flop per input sample, SURVEY 8d
-    per_gpu_rate = value * 1e6 / world
-    # flop the kernels execute per input sample: the decimator runs the direct form (4 flop per real
-    # tap and complex sample); the FFT correlator ~4700 FP32 operations per lane and 896-output block
-    # (DESIGN.md K2f), the folded direct form 64 FADD2 + 260 FFMA2 per search-rate sample
-    f_corr_exec = (2.0 * 4700 * 32 / 896) if a.corr == "fft" else (64 * 2 + 260 * 4)
-    f_exec = (f_corr_exec + 4.0 * ntaps(a.decim)) / a.decim
     hbm_peak = 6535.7
     try:
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    hbm_gbs = alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
-    # the integer tensor-core front end does its multiply-adds on the tensor pipe (18 % busy, profiles/): what
-    # binds that kernel is memory, so its roofline is HBM; the float32 kernels stay FFMA bound
-    tc_dom = a.frontend == "tc" and dom == 0
-    head = ({"bound": "hbm", "kernel": names[dom], "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak}
-            if tc_dom else
-            {"bound": "fp32", "kernel": names[dom], "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-             "frac": achieved / FP32_PEAK_TFLOPS})
-    roofline = dict(head)
-    roofline.update({
-        "traffic": traffic,
-        "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
-        "algorithmic_bytes_per_launch": alg_bytes[dom],
-        "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"},
-        "fp32": {"achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP32_PEAK_TFLOPS,
-                 "note": "direct-form algorithmic flop of the dominant kernel; with --frontend tc they run as int8 tensor-core MACs"},
-        "peak_source": ("MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if tc_dom else
-                        "measured FFMA peak, tools/ubench_fp32.cu (profiles/ubench_fp32_r01.jsonl); MEASURED_PEAKS.json has no fp32 figure"),
-        "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
-        "stages_overlap": a.pipeline == "overlap",      # track + sss of call i run under the front end of call i+1:
-                                                        # the stage times then sum to more than ms_per_step
-        "path_frac_of_fp32": f_alg * per_gpu_rate / (FP32_PEAK_TFLOPS * 1e12),
-        "path_frac_of_fp32_executed": f_exec * per_gpu_rate / (FP32_PEAK_TFLOPS * 1e12),
-        "flop_per_input_sample": {"algorithmic_direct_form": f_alg, "executed": f_exec},
-        "path_frac_of_hbm": bps * per_gpu_rate / (hbm_peak * 1e9),
-        "note": "achieved = SURVEY 8d algorithmic bytes (hbm) or direct-form flop (fp32) of the dominant kernel per launch / its CUDA-event duration; path_frac_of_fp32 uses the same direct-form count and exceeds 1 because the correlator runs as FFT blocks (or folds the taps); path_frac_of_fp32_executed counts the flop the kernels execute",
-    })
 
+    def timed_run(frontend, pipe, steps, warmup, keep_open=False):
+        """W warm-up and K timed steps of one front-end mode: CUDA events on the launch stream around the K steps,
+        barrier + synchronize on both sides, max over ranks; per-stage CUDA-event times of the same steps."""
+        kw = mode_kw(frontend, a.format)[0]
+        trig = lt.Trigger(n_streams=a.streams, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
+                          record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode,
+                          pipeline=pipe, **kw)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        for _ in range(warmup):
+            trig.process_device_ptr(ptr, stride, n)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler.begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r = {"stage_ms": np.zeros(4), "launches": 0, "n_cells": 0, "last_recs": None}
+
+        def account(recs):
+            r["last_recs"] = recs
+            r["stage_ms"] += np.array(trig.last_kernel_times())
+            r["launches"] += trig.last_timing()[1]
+            r["n_cells"] += int(((recs["flags"] & lt.F_CELL) != 0).sum())
+
+        torch.cuda.synchronize()
+        e0.record(stream)
+        # two calls in flight (ltb_trigger_submit_device / ltb_trigger_collect): call i+1 is enqueued
+        # before the records of call i are read, so the stream does not idle on the host round trip
+        trig.submit_device_ptr(ptr, stride, n)
+        for _ in range(steps - 1):
+            trig.submit_device_ptr(ptr, stride, n)
+            account(trig.collect())
+        account(trig.collect())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        r["clocks"] = sampler.result()
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(tt.item())
+        r["elapsed_ms"] = ms
+        r["value"] = float(a.streams) * n * steps * world / (ms * 1e-3) / 1e6
+        r["stage_ms"] = r["stage_ms"] / steps
+        r["last_recs"] = r["last_recs"].copy()
+        if keep_open:
+            r["trig"] = trig
+        else:
+            trig.close()
+        return r
+
+    def roofline_of(frontend, r, alone_ms=None):
+        """Roofline object of the dominant kernel of a mode (live CUDA-event stage times of the timed steps)."""
+        stage_ms = r["stage_ms"]
+        alg_flop = [4.0 * ntaps(a.decim) * m * a.streams, float(F_PSS) * m * a.streams, 0.0, 0.0]
+        dom = int(np.argmax(stage_ms))
+        if alg_flop[dom] == 0.0:
+            dom = int(np.argmax(stage_ms[:2]))
+        achieved = alg_flop[dom] / (stage_ms[dom] * 1e-3) / 1e12
+        alg_bytes = [float(bps) * n * a.streams + 8.0 * m * a.streams, 20.0 * m * a.streams, 0.0, 0.0]
+        traffic, traffic_src = None, None                           # dram read+write per launch, ncu --set full
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tr.get(frontend, tr) if frontend in tr else (tr if frontend == "fp32" else {})
+            if ent.get("workload") == workload_name(a):
+                traffic = ent["dram_bytes_per_launch"].get(names_short[dom])
+                traffic_src = ent.get("source")
+        except Exception:
+            pass
+        f_alg = (F_PSS + 4.0 * ntaps(a.decim)) / a.decim            # flop per input sample, SURVEY 8d
+        per_gpu_rate = r["value"] * 1e6 / world
+        # flop the kernels execute per input sample: the decimator runs the direct form (4 flop per real
+        # tap and complex sample); the FFT correlator ~4700 FP32 operations per lane and 896-output block
+        # (DESIGN.md K2f), the folded direct form 64 FADD2 + 260 FFMA2 per search-rate sample
+        f_corr_exec = (2.0 * 4700 * 32 / 896) if a.corr == "fft" else (64 * 2 + 260 * 4)
+        f_exec = (f_corr_exec + 4.0 * ntaps(a.decim)) / a.decim
+        hbm_gbs = alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        # the integer tensor-core front end does its multiply-adds on the tensor pipe (30 % busy, profiles/): what
+        # binds that kernel is memory, so its roofline is HBM; the float32 kernels stay FFMA bound
+        tc_dom = frontend == "tc" and dom == 0
+        head = ({"bound": "hbm", "kernel": names[dom], "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak}
+                if tc_dom else
+                {"bound": "fp32", "kernel": names[dom], "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                 "frac": achieved / FP32_PEAK_TFLOPS})
+        roofline = dict(head)
+        roofline.update({
+            "traffic": traffic,
+            "traffic_source": traffic_src or "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+            "algorithmic_bytes_per_launch": alg_bytes[dom],
+            "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"},
+            "fp32": {"achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP32_PEAK_TFLOPS,
+                     "note": "direct-form algorithmic flop of the dominant kernel; with the tc front end they run as int8 tensor-core MACs"},
+            "peak_source": ("MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if tc_dom else
+                            "measured FFMA peak, tools/ubench_fp32.cu (profiles/ubench_fp32_r01.jsonl); MEASURED_PEAKS.json has no fp32 figure"),
+            "stage_ms": {k: float(v) for k, v in zip(names, stage_ms)},
+            "stages_overlap": a.pipeline == "overlap",      # track + sss of call i run under the front end of call i+1:
+                                                            # the stage times then sum to more than ms_per_step
+            "path_frac_of_fp32": f_alg * per_gpu_rate / (FP32_PEAK_TFLOPS * 1e12),
+            "path_frac_of_fp32_executed": f_exec * per_gpu_rate / (FP32_PEAK_TFLOPS * 1e12),
+            "flop_per_input_sample": {"algorithmic_direct_form": f_alg, "executed": f_exec},
+            "path_frac_of_hbm": bps * per_gpu_rate / (hbm_peak * 1e9),
+            "note": "achieved = SURVEY 8d algorithmic bytes (hbm) or direct-form flop (fp32) of the dominant kernel per launch / its CUDA-event duration inside the timed (pipelined) steps; kernel_alone repeats it with the stages run back to back on one stream; path_frac_of_fp32 uses the same direct-form count and exceeds 1 because the correlator runs as FFT blocks (or folds the taps); path_frac_of_fp32_executed counts the flop the kernels execute",
+        })
+        if alone_ms is not None:
+            ka = alone_ms[dom]
+            roofline["kernel_alone"] = {
+                "ms": float(ka), "stage_ms": {k: float(v) for k, v in zip(names, alone_ms)},
+                "frac": (alg_bytes[dom] / (ka * 1e-3) / 1e9 / hbm_peak) if tc_dom else (alg_flop[dom] / (ka * 1e-3) / 1e12 / FP32_PEAK_TFLOPS),
+                "what": "the same kernels with the stages of a call back to back on one stream (pipeline serial, 3 steps): no other kernel shares the SMs"}
+        return roofline
+
+    main = timed_run(a.frontend, pipeline, a.steps, a.warmup, keep_open=True)
+    trig = main["trig"]
+    elapsed_ms, value, launches, n_cells, clocks = main["elapsed_ms"], main["value"], main["launches"], main["n_cells"], main["clocks"]
+    last_recs = main["last_recs"]
+    frontend_kw, oracle_front_flag, oracle_fs = mode_kw(a.frontend, a.format)
+    alone = None
+    if a.pipeline == "overlap" and not a.no_alone:
+        alone = timed_run(a.frontend, lt.PIPE_SERIAL, 3, 2)["stage_ms"]
+    roofline = roofline_of(a.frontend, main, alone)
+
+    frontend_text = {"fp32": "fp32 (canonical float32 expression trees, FFMA2)",
+                     "tc": "tc (exact integer arithmetic on the tensor cores: tcgen05.mma kind::i8, TMA, TMEM%s)" % (
+                         "; fc32 samples taken as 23-bit fixed point over +-%.1f" % FC32_FULL_SCALE if a.format == "fc32" else "")}
     out = {
         "metric": "PSS+SSS search Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if a.frontend == "fp32" else "s8 x s8 -> s32 (front end, exact), f32 (correlator, tracker, SSS)",
+        "data": "synthetic",
         "config": {"workload": workload_name(a), "streams_per_gpu": a.streams, "decim": a.decim,
-                   "format": a.format, "frontend": a.frontend, "correlator": a.corr, "pipeline": a.pipeline, "segment_ms": a.segment_ms, "snr_db": a.snr_db,
+                   "format": a.format, "frontend": frontend_text[a.frontend], "correlator": a.corr, "pipeline": a.pipeline, "segment_ms": a.segment_ms, "snr_db": a.snr_db,
                    "l2": "inputs larger than L2 (%.1f GB per step)" % (a.streams * n * bps / 1e9),
                    "input": ("noise only (no cell in any stream)" if a.noise_only else
                              "%d seeded synthetic LTE captures tiled over the streams with per-stream timing shift + AWGN" % a.unique),
@@ -410,7 +451,23 @@ def main():
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
     }
 
-    last_recs = last_recs.copy()
+    # ---- the other front-end mode on the same input, same steps (D = 16 only: the tensor-core kernel's rate) ----
+    if a.decim == 16 and not a.no_alt:
+        other = "fp32" if a.frontend == "tc" else "tc"
+        trig.close()
+        alt = timed_run(other, pipeline, a.steps, a.warmup)
+        alt_alone = timed_run(other, lt.PIPE_SERIAL, 3, 2)["stage_ms"] if (a.pipeline == "overlap" and not a.no_alone) else None
+        out["other_frontend"] = {"frontend": frontend_text[other], "value": alt["value"], "unit": "Msamples/s",
+                                 "ms_per_step": alt["elapsed_ms"] / a.steps, "steps": a.steps, "warmup": a.warmup,
+                                 "clocks": alt["clocks"], "gpu_launches": alt["launches"],
+                                 "cells_tagged_per_step": alt["n_cells"] / a.steps,
+                                 "roofline": roofline_of(other, alt, alt_alone)}
+        trig = lt.Trigger(n_streams=a.streams, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
+                          record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode,
+                          pipeline=pipeline, **frontend_kw)
+        for _ in range(2):
+            trig.process_device_ptr(ptr, stride, n)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     # ---- the same step sustained for >= 2 s: the clock the board settles at under its power cap ----
     if a.sustained_s > 0:
@@ -451,8 +508,7 @@ def main():
         got = chk.run(iq)
         chk.close()
         conv = (O.CONV_OS if a.corr == "fft" else O.CONV_DIRECT) | oracle_front_flag
-        want = O.trigger_run(iq, decim=a.decim, fmt=fmt, psr_threshold=4.0, conv_mode=conv,
-                             fc32_full_scale=frontend_kw.get("fc32_full_scale", 0.0))
+        want = O.trigger_run(iq, decim=a.decim, fmt=fmt, psr_threshold=4.0, conv_mode=conv, fc32_full_scale=oracle_fs)
         same = len(got) == len(want)
         for f in (want.dtype.names if same else ()):
             g_, w_ = got[f], want[f]
@@ -460,15 +516,45 @@ def main():
                 same = same and bool(((g_.view(np.uint32) == w_.view(np.uint32)) | ((g_ == 0) & (w_ == 0))).all())
             else:
                 same = same and bool((g_ == w_).all())
-        verdict = torch.tensor([1 if same else 0, len(want)], device=dev, dtype=torch.int64)
+        # the two front ends against each other on the same streams (north_star: decisions bit-exact, correlation
+        # magnitudes and PSR within 1e-4 relative): the integer front end's records next to the canonical float32 ones
+        agree, worst = 1, 0.0
+        if a.decim == 16:
+            okw = mode_kw("fp32" if a.frontend == "tc" else "tc", a.format)[0]
+            chk = lt.Trigger(n_streams=nchk, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
+                             device=local_rank, corr_mode=corr_mode, **okw)
+            oth = chk.run(iq)
+            chk.close()
+            keys = ("stream", "n_id_2", "win_start", "emit_start", "flags", "peak_pos", "m0", "m1", "n_id_1", "cell_id")
+            agree = int(len(oth) == len(got) and all(bool((oth[f] == got[f]).all()) for f in keys))
+            if not agree and len(oth) == len(got) and all(bool((oth[f] == got[f]).all()) for f in keys if f != "peak_pos"):
+                # a window under the threshold is noise: its argmax may sit on another of two nearly equal maxima
+                over = ((got["flags"] | oth["flags"]) & lt.F_OVER) != 0
+                agree = int(bool((oth["peak_pos"][over] == got["peak_pos"][over]).all()))
+            if agree:
+                for f in ("psr", "peak_value"):
+                    den = np.maximum(np.abs(got[f]), 1e-30)
+                    fin = np.isfinite(got[f]) & np.isfinite(oth[f])
+                    if fin.any():
+                        worst = max(worst, float((np.abs(got[f] - oth[f])[fin] / den[fin]).max()))
+        verdict = torch.tensor([1 if same else 0, len(want), agree], device=dev, dtype=torch.int64)
+        wt = torch.tensor([worst], device=dev, dtype=torch.float64)
         if world > 1:
             v0 = verdict.clone()
             dist.all_reduce(verdict[0:1], op=dist.ReduceOp.MIN)
+            dist.all_reduce(verdict[2:3], op=dist.ReduceOp.MIN)
             dist.all_reduce(v0[1:2], op=dist.ReduceOp.SUM)
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX)
             verdict[1] = v0[1]
         out["parity_spot_check"] = {"ranks": world, "streams_per_rank": nchk, "records": int(verdict[1].item()),
                                     "bit_identical_to_oracle": bool(verdict[0].item() == 1),
                                     "checker": "oracle/ (CPU restatement), same rate/format/correlator/front end as the timed run"}
+        if a.decim == 16:
+            out["tc_vs_fp32"] = {"decisions_identical": bool(verdict[2].item() == 1), "max_rel_diff_psr_peak": float(wt.item()),
+                                 "tolerance": 1e-4, "records": int(verdict[1].item()),
+                                 "what": "window records of the integer tensor-core front end against the canonical float32 front end on the "
+                                         "spot-check streams: window starts, flags, peak positions, m0/m1, N_id_1, cell ids equal; PSR and "
+                                         "peak value compared relatively"}
 
     # ---- host merge of the (tiny) record lists of the last step: the only exchange between ranks ----
     from ltetrigger_b200 import shard
@@ -495,7 +581,7 @@ def main():
             b = FMT_BYTES[name]
             trig2 = lt.Trigger(n_streams=se, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmts[name],
                                record_all=False, device=local_rank, cuda_stream=stream.cuda_stream, corr_mode=corr_mode,
-                               pipeline=pipeline, **(frontend_kw if name == a.format else {}))
+                               pipeline=pipeline, **mode_kw(a.frontend, name)[0])
             hptr, hstride = host.data_ptr(), n * b
             for _ in range(3):                                      # warm-up: allocates both staging buffers,
                 trig2.submit_host_ptr(hptr, hstride, n)             # touches every pinned page

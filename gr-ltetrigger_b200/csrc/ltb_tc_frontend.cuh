@@ -28,9 +28,9 @@
 // 61 rows = 976 outputs.
 //
 // Pipeline (one 576-thread CTA per SM, persistent over a contiguous run of tiles):
-//   warp 8        TMA producer: one cp.async.bulk.tensor.3d box (256 B x 64 rows) per stage -> raw ring (4 stages)
+//   warp 8        TMA producer: one cp.async.bulk.tensor.3d box (256 B x 64 rows) per stage -> raw ring (6 stages)
 //   warps 10..17  transform: raw interleaved I/Q -> two planar rows (re, im), written in the UMMA K-major
-//                 SWIZZLE_128B layout (4 stages of 16 kB)
+//                 SWIZZLE_128B layout (3 stages of 16 kB), in two groups of four warps that take alternate stages
 //   warp 9        MMA issuer: 4 x tcgen05.mma.kind::i8 (M = 128, N = 144, K = 32) per stage, accumulators in TMEM
 //   warps 0..7    epilogue: tcgen05.ld -> int64 recombination -> diagonal sum -> float -> y_ring (coalesced);
 //                 warp w reads TMEM lane quarter w % 4 and owns outputs r = 8 (w / 4) .. 8 (w / 4) + 7 of its rows
@@ -52,13 +52,31 @@ constexpr int kTcRowSamples = 256;                 // input samples per A row (1
 constexpr int kTcTileRows = 64;                    // stream rows per tile (x 2 components = M 128)
 constexpr int kTcHalo = 3;                         // rows a tile re-reads from the tile above
 constexpr int kTcUseful = kTcTileRows - kTcHalo;   // 61
-constexpr int kTcRawStages = 4, kTcAStages = 4;   // powers of two: stage = iteration & 3
+#ifndef LTB_TC_RAW_STAGES
+#define LTB_TC_RAW_STAGES 6
+#endif
+#ifndef LTB_TC_A_STAGES
+#define LTB_TC_A_STAGES 3      // measured: three planar stages beat four by 13 % on sc16 (profiles/tc_sweep_r02.log)
+#endif
+#ifndef LTB_TC_BISECT
+#define LTB_TC_BISECT 0     // profiling builds only (tools/ubench_tc_i8): 1 no transform work, 2 no MMAs, 4 no epilogue work, 8 no proxy fence,
+                            // 16 epilogue stops after its TMEM loads, 32 epilogue without its TMEM loads
+#endif
+#ifndef LTB_TC_LB_THREADS
+#define LTB_TC_LB_THREADS kTcThreads               // a larger value here only lowers the register budget ptxas may use
+#endif
+constexpr int kTcRawStages = LTB_TC_RAW_STAGES, kTcAStages = LTB_TC_A_STAGES;
 constexpr int kTcRawBytes = kTcTileRows * 256;     // 16384: 256 raw bytes per row and stage (64 sc16 / 128 sc8 samples)
 constexpr int kTcABytes = 128 * 128;               // 16384
 constexpr int kTcBRows = 208;                      // accumulator columns of one tile (49 u's x 4, padded to 16)
 constexpr int kTcNStep = 144;                      // N of a k-step's MMA: 34 (35) u's x 4, padded to 16
 constexpr int kTcBTileBytes = kTcBRows * 128;      // 26624 (the first 32 bytes of each 128-byte row are used)
 constexpr int kTcEpiWarps = 8, kTcXformWarps = 8;  // warps 0..7; 8 producer, 9 MMA; 10..17
+#ifndef LTB_TC_XFORM_GROUPS
+#define LTB_TC_XFORM_GROUPS 2
+#endif
+constexpr int kTcXformGroups = LTB_TC_XFORM_GROUPS;                 // groups of transform warps that take alternate stages
+constexpr int kTcXformGroupWarps = kTcXformWarps / kTcXformGroups;
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 2 + kTcXformWarps);   // 576
 constexpr int kTcTailSamples = kTcHalo * kTcRowSamples;   // 768 raw samples of history per stream
 constexpr int kTcTapShift = 27;
@@ -231,9 +249,118 @@ __device__ __forceinline__ void tc_split(const uint4 w, uint2 &re, uint2 &im, co
   }
 }
 
+// ---- epilogue role (warps 0..7 of both kernels): warp w reads TMEM lane quarter w % 4 (w % 4 = 0,1: re rows 0..63; 2,3: im
+// rows 0..63) and owns the outputs r = 8 h .. 8 h + 7 (h = w / 4) of its 32 rows: column groups u = 8 (2 c + h) .. + 7, c = 0..2
+__device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const uint32_t tmem, const uint32_t acc_full0,
+                                                 const uint32_t acc_empty0, float *s_stage, long long *s_xchg,
+                                                 const int t_begin, const int t_end) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_out = P.n_in / 16;
+  int stream = t_begin / P.tiles_per_stream, ti = t_begin - stream * P.tiles_per_stream;
+  auto next_tile = [&]() { if (++ti == P.tiles_per_stream) { ti = 0; ++stream; } };
+  auto acc_full = [&](int i) { return acc_full0 + 8u * i; };
+  auto acc_empty = [&](int i) { return acc_empty0 + 8u * i; };
+  {
+    const int quarter = warp & 3, half = warp >> 2;
+    const int comp = quarter >> 1, row = (quarter & 1) * 32 + lane;
+    int tl = 0;
+    for (int t = t_begin; t < t_end; ++t, ++tl, next_tile()) {
+      const int row0 = ti * kTcUseful - kTcHalo;
+      const int buf = tl & 1;
+      tc_mbar_wait<64>(acc_full(buf), (tl >> 1) & 1, P.err, 6);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (LTB_TC_BISECT & 4) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(acc_empty(buf));
+        continue;
+      }
+      const uint32_t taddr = tmem + buf * 256 + ((uint32_t)(quarter * 32) << 16);
+      long long p[3][8];                                                 // p[q][j]: u = 16 q + 8 half + j
+      long long p48 = 0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int c0 = 2 * q + half;                                     // 32-column chunk, loaded as two halves
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t r[16];
+          if (LTB_TC_BISECT & 32) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = (uint32_t)(lane * 3 + i + tl);
+          } else {
+            tc_ld16(taddr + 32 * c0 + 16 * h2, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) p[q][4 * h2 + j] = tc_combine(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          if (P.dbg_acc && t == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 32 * c0 + 16 * h2 + i] = (int)r[i];
+          }
+        }
+      }
+      if (half == 0) {
+        uint32_t r[4];                                                   // columns 192..195: u = 48 (q = 3, r = 0)
+        tc_ld4(taddr + 192, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        p48 = tc_combine(r[0], r[1], r[2], r[3]);
+        if (P.dbg_acc && t == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 192 + i] = (int)r[i];
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(acc_empty(buf));                     // the MMA warp may refill this buffer
+      if (LTB_TC_BISECT & 16) continue;
+
+      // contributions to the rows below: rows 29..31 of the upper quarter hand theirs over in shared memory
+      long long *xq = s_xchg + (size_t)((comp * 2 + half) * 3) * 17;
+      if ((quarter & 1) == 0 && lane >= 29) {
+        long long *x = xq + (lane - 29) * 17;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { x[j] = p[1][j]; x[8 + j] = p[2][j]; }
+        x[16] = p48;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float *stg = s_stage + (comp * kTcTileRows + row) * kTcStagePitch + 8 * half;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        long long acc = p[0][j];
+#pragma unroll
+        for (int q = 1; q <= 3; ++q) {
+          if (q == 3 && j != 0) continue;
+          long long v = tc_shfl_up(q == 3 ? p48 : p[q][j], q);
+          if (lane < q) v = xq[(3 + lane - q) * 17 + (q == 3 ? 16 : 8 * (q - 1) + j)];   // row 32 + lane - q of the upper quarter
+          if (q == 3 && half != 0) v = 0;                                // u = 48 only feeds output r = 0
+          acc += v;
+        }
+        acc += P.c_const;
+        stg[j] = __fmul_rn(__ll2float_rn(acc), P.out_scale);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // coalesced store: 16 consecutive float2 per row
+      {
+        float2 *yr = P.y_ring + (size_t)stream * P.cap;
+        const int rr = tid & 15;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rw = (tid >> 4) + 16 * j;                            // tile row 0..63
+          const long long k = (long long)(row0 + rw) * 16 + rr;
+          if (rw >= kTcHalo && k < m_out) {
+            const float2 v = make_float2(s_stage[(0 * kTcTileRows + rw) * kTcStagePitch + rr],
+                                         s_stage[(1 * kTcTileRows + rw) * kTcStagePitch + rr]);
+            yr[(unsigned)((P.n_base + k) & P.cap_mask)] = v;
+          }
+        }
+      }
+    }
+    }
+}
+
 // ---- the kernel ----------------------------------------------------------------------------------------------
 template <int FMT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(LTB_TC_LB_THREADS, 1)
 decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
   constexpr int BPS = tc_sample_bytes(FMT);                 // bytes per complex input sample
   constexpr int SPT = tc_stages_per_tile(FMT);              // pipeline stages (128-byte A atoms) per tile
@@ -272,8 +399,8 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
   for (int i = tid; i < kTcBTileBytes / 16; i += kTcThreads)
     reinterpret_cast<uint4 *>(s_b)[i] = reinterpret_cast<const uint4 *>(P.btab)[i];
   if (tid == 0) {
-    for (int i = 0; i < kTcRawStages; ++i) { tc_mbar_init(raw_full(i), 1); tc_mbar_init(raw_empty(i), kTcXformWarps); }
-    for (int i = 0; i < kTcAStages; ++i) { tc_mbar_init(a_full(i), kTcXformWarps); tc_mbar_init(a_empty(i), 1); }
+    for (int i = 0; i < kTcRawStages; ++i) { tc_mbar_init(raw_full(i), 1); tc_mbar_init(raw_empty(i), kTcXformGroupWarps); }
+    for (int i = 0; i < kTcAStages; ++i) { tc_mbar_init(a_full(i), kTcXformGroupWarps); tc_mbar_init(a_empty(i), 1); }
     for (int i = 0; i < 2; ++i) { tc_mbar_init(acc_full(i), 1); tc_mbar_init(acc_empty(i), kTcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -331,6 +458,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
             const int s = 4 * a + k;                                     // k-step of the row
             const bool first = s == 0;
             const uint64_t adesc = tc_make_desc(a_base + 32 * k);
+            if (LTB_TC_BISECT & 2) continue;
             if (FMT == LTB_FMT_FC32) {
               const uint32_t d = tmem + buf * 256 + COLSTEP * (s >> 1);
               tc_mma_i8(d, adesc, (s & 1) ? bdesc1 : bdesc, first ? tc_idesc(kTcBRows, false) : tc_idesc(kTcNStep, false),
@@ -348,28 +476,38 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
     }
   } else if (warp >= 10) {
     // ===== transform: raw interleaved I/Q -> planar re / im rows in the swizzled K-major layout =====
-    const int tt = tid - 10 * 32;                                        // 0..255
-    constexpr int NJ = kTcTileRows * 16 / (32 * kTcXformWarps);          // 64 rows x 16 items per stage / threads
-    constexpr int ROWSTEP = 32 * kTcXformWarps / 16;                     // rows between a thread's items
+    // two groups of four warps take alternate stages, so two stages are in flight: one group's chain of waits,
+    // loads, stores and the proxy fence (~600 cycles) overlaps the other's
+    const int grp = (warp - 10) / kTcXformGroupWarps;
+    const int tt = tid - 10 * 32 - grp * 32 * kTcXformGroupWarps;        // 0..127
+    constexpr int NJ = kTcTileRows * 16 / (32 * kTcXformGroupWarps);     // 64 rows x 16 items per stage / threads of a group
+    constexpr int ROWSTEP = 32 * kTcXformGroupWarps / 16;                // rows between a thread's items
     const int r_t = tt >> 4, c = tt & 15;                                // this thread's first row, its 16-byte column
     // item j: row r_t + ROWSTEP j; ROWSTEP is a multiple of 8, so (row & 7) and the swizzled chunk stay fixed
     const int src_off = r_t * 256 + c * 16;
     const int dst_off = tc_sw_off(r_t, c >> 1) + (c & 1) * 8;
     static_assert(ROWSTEP % 8 == 0, "swizzle phase must not change between a thread's items");
-    int it = 0;
-    for (int t = t_begin; t < t_end; ++t, next_tile()) {
+    static_assert(SPT % kTcXformGroups == 0, "a tile's stages are dealt evenly to the groups");
+    int it0 = 0;
+    for (int t = t_begin; t < t_end; ++t, next_tile(), it0 += SPT) {
       const int row0 = ti * kTcUseful - kTcHalo;
 #ifdef LTB_TC_NO_TMA
       const bool patch = true;
 #else
       const bool patch = row0 < 0 || row0 + kTcTileRows > full_rows;     // some rows are not plain tensor rows
 #endif
-      for (int a = 0; a < SPT; ++a, ++it) {
+      for (int a = grp; a < SPT; a += kTcXformGroups) {
+        const int it = it0 + a;
         const int rs = it % kTcRawStages, as = it % kTcAStages;
         tc_mbar_wait<0>(raw_full(rs), (it / kTcRawStages) & 1, P.err, 4);
         tc_mbar_wait<0>(a_empty(as), ((it / kTcAStages) & 1) ^ 1, P.err, 5);
         const unsigned char *raw = s_raw + (size_t)rs * kTcRawBytes + src_off;
         unsigned char *dst = s_a + (size_t)as * kTcABytes + dst_off;
+        if (LTB_TC_BISECT & 1) {
+          __syncwarp();
+          if (lane == 0) { tc_mbar_arrive(a_full(as)); tc_mbar_arrive(raw_empty(rs)); }
+          continue;
+        }
         uint4 w[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) w[j] = *reinterpret_cast<const uint4 *>(raw + j * ROWSTEP * 256);
@@ -406,96 +544,13 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
           *reinterpret_cast<uint2 *>(dst + j * ROWSTEP * 128) = re;                // rows 0..63: real parts
           *reinterpret_cast<uint2 *>(dst + 64 * 128 + j * ROWSTEP * 128) = im;     // rows 64..127: imaginary parts
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> tensor-core reads
+        if (!(LTB_TC_BISECT & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> tensor-core reads
         __syncwarp();
         if (lane == 0) { tc_mbar_arrive(a_full(as)); tc_mbar_arrive(raw_empty(rs)); }
       }
     }
   } else {
-    // ===== epilogue: warp w reads TMEM lane quarter w % 4 (w % 4 = 0,1: re rows 0..63; 2,3: im rows 0..63) and
-    // owns the outputs r = 8 h .. 8 h + 7 (h = w / 4) of its 32 rows: column groups u = 8 (2 c + h) .. + 7, c = 0..2 =====
-    const int quarter = warp & 3, half = warp >> 2;
-    const int comp = quarter >> 1, row = (quarter & 1) * 32 + lane;
-    int tl = 0;
-    for (int t = t_begin; t < t_end; ++t, ++tl, next_tile()) {
-      const int row0 = ti * kTcUseful - kTcHalo;
-      const int buf = tl & 1;
-      tc_mbar_wait<64>(acc_full(buf), (tl >> 1) & 1, P.err, 6);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem + buf * 256 + ((uint32_t)(quarter * 32) << 16);
-      long long p[3][8];                                                 // p[q][j]: u = 16 q + 8 half + j
-      long long p48 = 0;
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int c0 = 2 * q + half;                                     // 32-column chunk, loaded as two halves
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint32_t r[16];
-          tc_ld16(taddr + 32 * c0 + 16 * h2, r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 4; ++j) p[q][4 * h2 + j] = tc_combine(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          if (P.dbg_acc && t == 0) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 32 * c0 + 16 * h2 + i] = (int)r[i];
-          }
-        }
-      }
-      if (half == 0) {
-        uint32_t r[4];                                                   // columns 192..195: u = 48 (q = 3, r = 0)
-        tc_ld4(taddr + 192, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        p48 = tc_combine(r[0], r[1], r[2], r[3]);
-        if (P.dbg_acc && t == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 192 + i] = (int)r[i];
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) tc_mbar_arrive(acc_empty(buf));                     // the MMA warp may refill this buffer
-
-      // contributions to the rows below: rows 29..31 of the upper quarter hand theirs over in shared memory
-      long long *xq = s_xchg + (size_t)((comp * 2 + half) * 3) * 17;
-      if ((quarter & 1) == 0 && lane >= 29) {
-        long long *x = xq + (lane - 29) * 17;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { x[j] = p[1][j]; x[8 + j] = p[2][j]; }
-        x[16] = p48;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      float *stg = s_stage + (comp * kTcTileRows + row) * kTcStagePitch + 8 * half;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        long long acc = p[0][j];
-#pragma unroll
-        for (int q = 1; q <= 3; ++q) {
-          if (q == 3 && j != 0) continue;
-          long long v = tc_shfl_up(q == 3 ? p48 : p[q][j], q);
-          if (lane < q) v = xq[(3 + lane - q) * 17 + (q == 3 ? 16 : 8 * (q - 1) + j)];   // row 32 + lane - q of the upper quarter
-          if (q == 3 && half != 0) v = 0;                                // u = 48 only feeds output r = 0
-          acc += v;
-        }
-        acc += P.c_const;
-        stg[j] = __fmul_rn(__ll2float_rn(acc), P.out_scale);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      // coalesced store: 16 consecutive float2 per row
-      {
-        float2 *yr = P.y_ring + (size_t)stream * P.cap;
-        const int rr = tid & 15;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int rw = (tid >> 4) + 16 * j;                            // tile row 0..63
-          const long long k = (long long)(row0 + rw) * 16 + rr;
-          if (rw >= kTcHalo && k < m_out) {
-            const float2 v = make_float2(s_stage[(0 * kTcTileRows + rw) * kTcStagePitch + rr],
-                                         s_stage[(1 * kTcTileRows + rw) * kTcStagePitch + rr]);
-            yr[(unsigned)((P.n_base + k) & P.cap_mask)] = v;
-          }
-        }
-      }
-    }
+    tc_epilogue_role(P, tmem, acc_full(0), acc_empty(0), s_stage, s_xchg, t_begin, t_end);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
