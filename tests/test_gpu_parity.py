@@ -373,6 +373,31 @@ def test_two_calls_in_flight_match_synchronous_calls(lt, oracle):
     assert_recs_equal(recs, want)
 
 
+@pytest.mark.parametrize("pipe", ["overlap", "serial"])
+def test_pipeline_modes_give_the_same_records(lt, oracle, pipe):
+    """The two ways the kernels of consecutive calls are scheduled (track + SSS of call i under the front end of call
+    i+1, or everything on one stream) only move kernels in time: with two calls in flight over five chunks every
+    record equals the oracle's."""
+    import torch
+    x, decim, _ = load_fixture("100prb", 0.3)
+    n = len(x) // 5 // (8 * decim) * (8 * decim)
+    iq = np.stack([x[:5 * n], np.roll(x[:5 * n], 12345)])
+    want = oracle.trigger_run(iq, decim=decim, conv_mode=oracle.CONV_OS)
+    d = torch.from_numpy(iq.copy()).cuda()
+    mode = {"overlap": lt.PIPE_OVERLAP, "serial": lt.PIPE_SERIAL}[pipe]
+    trig = lt.Trigger(n_streams=2, decim=decim, max_chunk=n, corr_mode=lt.CORR_FFT, pipeline=mode)
+    got = []
+    trig.submit_device_ptr(d.data_ptr(), 8 * 5 * n, n)
+    for k in range(1, 5):
+        trig.submit_device_ptr(d.data_ptr() + 8 * k * n, 8 * 5 * n, n)
+        got.append(trig.collect().copy())
+    got.append(trig.collect().copy())
+    trig.close()
+    recs = np.concatenate(got)
+    recs = recs[np.lexsort((recs["win_index"], recs["n_id_2"], recs["stream"]))]
+    assert_recs_equal(recs, want)
+
+
 def test_two_host_calls_in_flight(lt, oracle):
     """ltb_trigger_submit_host: the copy of call i+1 overlaps call i; records equal the oracle's."""
     import torch
