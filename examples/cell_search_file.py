@@ -9,6 +9,10 @@ cell ("status": "FOUND") or {"status": "NOT_FOUND"}, optionally also written to 
 and ignored (there is no CPU load to lower).
 
   python examples/cell_search_file.py tests/golden/test_frames/lte_frame_50prb_cellid_125 -s 15.36M --repeat --time-out 1
+
+Beyond the reference: a SigMF recording (`name.sigmf-meta` + `name.sigmf-data`, datatype cf32_le, ci16_le or ci8) is
+read with its own sample rate and type -- `-s` then is optional and must agree if given -- and integer types go to
+the GPU as they are (the short-to-complex conversion is fused into the front end).
 """
 from __future__ import print_function
 
@@ -41,14 +45,31 @@ def eng_int(s):
 
 def search(args):
     import ltetrigger_b200 as lt
+    from ltetrigger_b200 import sigmf
+    input_format, data = lt.FMT_FC32, None
+    if sigmf.is_sigmf(args.filename):
+        try:
+            rec = sigmf.load(args.filename)
+        except sigmf.SigMFError as e:
+            sys.stderr.write("%s\n" % e)
+            sys.exit(-1)
+        if args.sample_rate is not None and abs(args.sample_rate - rec["sample_rate"]) > 0.5:
+            sys.stderr.write("Sample rate {:.6f} MHz given, but the SigMF metadata says {:.6f} MHz.\n".format(
+                args.sample_rate / 1e6, rec["sample_rate"] / 1e6))
+            sys.exit(-1)
+        args.sample_rate, input_format, data = rec["sample_rate"], rec["input_format"], rec["samples"]
+    elif args.sample_rate is None:
+        sys.stderr.write("-s/--sample-rate is required for a raw fc32 file.\n")
+        sys.exit(-1)
     if args.sample_rate % REQUIRED_SAMPLE_RATE:
         sys.stderr.write("Sample rate {:.2f} MHz is not a multiple of 1.92 MHz. "
                          "Arbitrary resampling not supported at this time.\n".format(args.sample_rate / 1e6))
         sys.exit(-1)
     decim = int(args.sample_rate / REQUIRED_SAMPLE_RATE)
-    trigger = lt.downlink_trigger_c(psr_threshold=args.threshold, exit_on_success=True, decim=decim)
+    trigger = lt.downlink_trigger_c(psr_threshold=args.threshold, exit_on_success=True, decim=decim, input_format=input_format)
     store = lt.cellstore().connect(trigger)
-    data = np.fromfile(args.filename, np.complex64)
+    if data is None:
+        data = np.fromfile(args.filename, np.complex64)
     chunk = 96000 * decim                                     # 50 ms per scheduler pass
     fed, t_start = 0, time.time()
     done = lambda: any(m.done for m in (trigger.mib0, trigger.mib1, trigger.mib2))   # WORK_DONE
@@ -99,14 +120,14 @@ def main(args):
 def parse(argv=None):
     """The reference CLI's flags (examples/cell_search_file.py:140-200): same names, types and defaults."""
     def existing_file(name):
-        if not os.path.isfile(name):
+        if not os.path.isfile(name) and not os.path.isfile(name + ".sigmf-meta"):
             raise argparse.ArgumentTypeError("file {} does not exist".format(name))
         return name
 
     ap = argparse.ArgumentParser(description="search an IQ capture (fc32) for LTE cells on the GPU")
     ap.add_argument("filename", type=existing_file)
     options = [
-        (("-s", "--sample-rate"), dict(type=eng_float, required=True, metavar="Hz", help="sample rate of the capture (a multiple of 1.92 MHz)")),
+        (("-s", "--sample-rate"), dict(type=eng_float, default=None, metavar="Hz", help="sample rate of the capture (a multiple of 1.92 MHz); required unless the file is a SigMF recording")),
         (("-f", "--frequency"), dict(type=eng_float, metavar="Hz", help="center frequency of the capture (informational)")),
         (("--repeat",), dict(action="store_true", help="start over at the end of the file until a cell is found, the cut-off or the time-out")),
         (("-c", "--cut-off"), dict(type=eng_int, metavar="N", default=-1, help="give up after N input samples")),

@@ -281,15 +281,18 @@ class downlink_trigger_c:
     """
 
     def __init__(self, psr_threshold, exit_on_success=False, device=0, max_chunk=1 << 18, keep_halfframes=True,
-                 decim=1):
+                 decim=1, input_format=A.FMT_FC32):
         """`decim` > 1 fuses the `rational_resampler_ccc(1, decim)` the reference's apps put in
         front of the hier block (examples/cell_search_file.py:56-57) into the engine's front end;
-        the input of work() is then at decim x 1.92 Msps.  Default: the reference's interface."""
+        the input of work() is then at decim x 1.92 Msps.  `input_format` other than fc32 also fuses the
+        interleaved-short / interleaved-char to complex conversion a flowgraph on an SDR's wire format starts with
+        (work() then takes [n, 2] int16 / int8 arrays).  Defaults: the reference's interface."""
         self.psr_threshold = self._ensure_safe_threshold(psr_threshold)
         self.exit_on_success = exit_on_success
         self._step = 8 * decim
+        self._fmt = input_format
         self._engine = Trigger(1, decim=decim, psr_threshold=self.psr_threshold, max_chunk=max_chunk * decim,
-                               record_all=True, keep_halfframes=keep_halfframes, device=device)
+                               record_all=True, keep_halfframes=keep_halfframes, device=device, input_format=input_format)
         self._keep = keep_halfframes
         self.pss0, self.pss1, self.pss2 = (_chain_view(self._engine, k) for k in range(3))
         self._ports = {"track": [], "drop": []}
@@ -298,7 +301,7 @@ class downlink_trigger_c:
         for m_ in (self.mib0, self.mib1, self.mib2):
             for port in ("track", "drop"):
                 m_.msg_connect(port, lambda msg, port=port: [cb(msg) for cb in self._ports[port]])
-        self._carry = np.zeros(0, np.complex64)
+        self._carry = np.zeros((0,) if input_format == A.FMT_FC32 else (0, 2), A.FMT_DTYPE[input_format])
         self.records = []
 
     def message_ports(self): return list(self._ports)
@@ -316,7 +319,7 @@ class downlink_trigger_c:
     def work(self, samples):
         """Consume a run of input items; returns the stream tags produced by the three sss
         blocks as (k, tag_t) pairs (offsets count items written by chain k's pss)."""
-        x = np.concatenate([self._carry, np.asarray(samples, np.complex64)])
+        x = np.concatenate([self._carry, np.asarray(samples, A.FMT_DTYPE[self._fmt])])
         n = len(x) // self._step * self._step
         self._carry = x[n:].copy()
         tags = []
