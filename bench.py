@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-formats", action="store_true", help="skip the e2e legs on the other wire formats")
+    ap.add_argument("--no-e2e-balance", action="store_true",
+                    help="N > 1: equal stream shares per rank in the e2e leg instead of shares by measured host-link rate")
     ap.add_argument("--workload", default="c5", choices=["c5", "c1", "c2", "c3"],
                     help="c5 (default): BASELINE's batched shard, the metric's configuration; c1/c2/c3: the single-stream "
                          "configurations (latency to first track, C-ABI and block-path throughput; tools/bench_single.py)")
@@ -571,6 +573,35 @@ def main():
     if not a.no_e2e:
         se = min(a.e2e_streams, a.streams)
         trig.close()
+        # Several GPUs of one box do not get equal shares of the host side (profiles/e2e_probe_r02_n8.json: with eight
+        # copies at once four links run at 23.8 and four at 35.5 GB/s, each 55.6 GB/s alone), and the end-to-end leg is as
+        # slow as its slowest rank.  Streams are independent, so the host deals them in proportion to what each rank's link
+        # delivers while all ranks copy: measured here, barrier-aligned, before the timed region.
+        balance = None
+        if world > 1:
+            probe = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+            probe.fill_(1)
+            pd = torch.empty_like(probe, device=dev)
+            pd.copy_(probe, non_blocking=True)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0.record(stream)
+            for _ in range(6):
+                pd.copy_(probe, non_blocking=True)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            bw = torch.zeros(world, device=dev, dtype=torch.float64)
+            bw[rank] = 6 * probe.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            dist.all_reduce(bw, op=dist.ReduceOp.SUM)
+            del probe, pd
+            bw_l = [float(v) for v in bw.tolist()]
+            if not a.no_e2e_balance:
+                share = [max(8, min(a.streams, int(round(se * world * v / sum(bw_l))))) for v in bw_l]
+                balance = {"concurrent_h2d_gbs": bw_l, "streams_per_rank": share,
+                           "what": "streams dealt in proportion to each rank's host-link rate with all ranks copying at once"}
+                se = share[rank]
+            else:
+                balance = {"concurrent_h2d_gbs": bw_l, "streams_per_rank": [se] * world, "what": "equal shares (--no-e2e-balance)"}
 
         def run_e2e(name):
             src = d_in[:se] if name == a.format else quantise(x_e2e[:se], name)
@@ -617,12 +648,19 @@ def main():
             torch.cuda.synchronize()
             h2d_gbs = 4 * host.numel() * host.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9
             del dst
-            link = {"h2d_copy_alone_gbs": h2d_gbs,
+            link = {("h2d_copy_alone_gbs" if world == 1 else "h2d_copy_all_ranks_at_once_gbs"): h2d_gbs,
                     "frac_of_h2d_copy": (se * n * b * a.e2e_steps / (e2e_ms_local * 1e-3) / 1e9) / h2d_gbs}
-            return host, {"value": se * n * a.e2e_steps * world / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
-                          "h2d_bytes_per_step": se * n * b, "d2h_bytes_per_step": d2h // a.e2e_steps,
-                          "streams": se, "steps": a.e2e_steps, "host_memory": "pinned", "format": name, "cpu_affinity": numa, "host_link": link,
-                          "api": "ltb_trigger_submit_host + ltb_trigger_collect (two calls in flight)"}
+            tot = torch.tensor([float(se), float(d2h // a.e2e_steps)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            se_all = float(tot[0].item())
+            res = {"value": se_all * n * a.e2e_steps / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                   "h2d_bytes_per_step": int(se_all * n * b), "d2h_bytes_per_step": int(tot[1].item()),
+                   "streams": int(se_all), "steps": a.e2e_steps, "host_memory": "pinned", "format": name, "cpu_affinity": numa, "host_link": link,
+                   "api": "ltb_trigger_submit_host + ltb_trigger_collect (two calls in flight)"}
+            if balance is not None:
+                res["balance"] = balance
+            return host, res
 
         host, out["e2e"] = run_e2e(a.format)
         # the same streams on the narrower wire formats an SDR delivers: the host link is the e2e bound
