@@ -6,8 +6,8 @@
 // path, and it never touches the GPU.  srsLTE's source is absent, so this restates the 3GPP
 // procedure it implements -- 36.211 6.6 (PBCH), 6.10.1 (CRS), 7.2 (Gold sequence); 36.212 5.1.1
 // (CRC16), 5.1.3.1 (tail-biting convolutional code), 5.1.4.2 (rate matching), 5.3.1 (BCH) -- for
-// one antenna port and for two ports with transmit diversity (36.211 6.3.4.3); the 4-port CRC mask is
-// recognised but 4-port SFBC-FSTD is not demodulated.  Its results are pinned by the
+// one antenna port and for two and four ports with transmit diversity (36.211 6.3.4.3: SFBC, and SFBC-FSTD
+// on the port pairs (0, 2) / (1, 3)).  Its results are pinned by the
 // reference's own tests: nof_prb 6 / 25 / 50 / 100, phich_len Normal, nof_phich_resources "1",
 // nof_tx_ports 1 for the four bundled test_frames (python/qa_downlink_trigger_c.py:46-65).
 #include <cmath>
@@ -129,21 +129,26 @@ extern "C" int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_norma
   auto sym_start = [&](int slot, int l) {                  // first sample after the CP
     return cp_normal ? slot * 960 + 10 + 137 * l : slot * 960 + 32 + 160 * l;
   };
-  // ---- OFDM demodulation of slot 1 -----------------------------------------------------------
-  cf grid[7][72];
+  // ---- OFDM demodulation of slot 1, and of symbol 1 of slot 0 (second comb of ports 2 / 3) ----------
+  cf grid[7][72], grid01[72];
   for (int l = 0; l < nsym; ++l) demod72(x + sym_start(1, l), grid[l]);
+  demod72(x + sym_start(0, 1), grid01);
   // ---- channel estimates from the CRS of slot 1 (36.211 6.10.1) ------------------------------------
   // port 0: symbols l = 0 (v = 0) and l = nsym - 3 (v = 3); port 1: the mirrored comb (v = 3, 0);
   // subcarriers k = 6 m + (v + v_shift) % 6
+  // ports 2 / 3: symbol l = 1 of every slot, v = 3 (n_s mod 2) / 3 + 3 (n_s mod 2): slots 0 and 1 give the two combs
   const int vshift = cell_id % 6;
-  cf hk[2][72];
-  for (int port = 0; port < 2; ++port) {
+  cf hk[4][72];
+  for (int port = 0; port < 4; ++port) {
     std::vector<int> pos;
     std::vector<cf> val;
-    const int ls[2] = {0, nsym - 3}, vs[2] = {port == 0 ? 0 : 3, port == 0 ? 3 : 0};
+    const int ls[2] = {port < 2 ? 0 : 1, port < 2 ? nsym - 3 : 1};
+    const int nss[2] = {port < 2 ? 1 : 0, 1};
+    const int vs[2] = {port == 0 ? 0 : port == 1 ? 3 : port == 2 ? 0 : 3, port == 0 ? 3 : port == 1 ? 0 : port == 2 ? 3 : 6};
     for (int a = 0; a < 2; ++a) {
       std::vector<uint8_t> c;
-      const int ns = 1, l = ls[a];
+      const int ns = nss[a], l = ls[a];
+      const cf *g = (ns == 1) ? grid[l] : grid01;
       const uint32_t c_init = 1024u * (7u * (ns + 1) + l + 1) * (2u * cell_id + 1) + 2u * cell_id + ncp;
       gold(c_init, 2 * 220, c);
       for (int m = 0; m < 12; ++m) {
@@ -151,7 +156,7 @@ extern "C" int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_norma
         const int mp = m + 110 - 6;                        // central 6 RB of any bandwidth
         const cf r((1 - 2 * (int)c[2 * mp]) * (float)M_SQRT1_2, (1 - 2 * (int)c[2 * mp + 1]) * (float)M_SQRT1_2);
         pos.push_back(k);
-        val.push_back(grid[l][k] * std::conj(r));
+        val.push_back(g[k] * std::conj(r));
       }
     }
     // merge the two staggered combs (static channel over the slot), sort by subcarrier, interpolate
@@ -171,7 +176,7 @@ extern "C" int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_norma
     }
   }
   // ---- PBCH resource elements: symbols 0..3, all CRS positions of ports 0..3 reserved ----------
-  std::vector<cf> rx, h0, h1;
+  std::vector<cf> rx, h0, h1, h2, h3;
   for (int l = 0; l < 4; ++l)
     for (int k = 0; k < 72; ++k) {
       const bool crs_sym = (l == 0 || l == 1 || (!cp_normal && l == 3));
@@ -179,6 +184,8 @@ extern "C" int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_norma
       rx.push_back(grid[l][k]);
       h0.push_back(hk[0][k]);
       h1.push_back(hk[1][k]);
+      h2.push_back(hk[2][k]);
+      h3.push_back(hk[3][k]);
     }
   const int nre = (int)rx.size();                          // 240 (normal) / 216 (extended)
   const int E = 2 * nre;
@@ -186,9 +193,8 @@ extern "C" int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_norma
   gold((uint32_t)cell_id, 4 * E, c);
   int order[120];
   ratematch_order(order);
-  // srslte_pbch_decode tries 1, 2 and 4 antenna ports and accepts a CRC that matches that number's
-  // mask; here 1 and 2 (a 4-port mask seen under the 1-port hypothesis is still reported)
-  for (int nant = 1; nant <= 2; ++nant) {
+  // srslte_pbch_decode tries 1, 2 and 4 antenna ports and accepts a CRC that matches that number's mask
+  for (int nant = 1; nant <= 4; nant *= 2) {
     std::vector<float> llr((size_t)E);
     if (nant == 1) {
       for (int i = 0; i < nre; ++i) {
@@ -196,9 +202,12 @@ extern "C" int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_norma
         llr[2 * i] = z.real(); llr[2 * i + 1] = z.imag();
       }
     } else {
-      // 36.211 6.3.4.3: r(2i) = h0 d(2i) - h1 conj(d(2i+1)),  r(2i+1) = h0 d(2i+1) + h1 conj(d(2i))
+      // 36.211 6.3.4.3: r(2i) = ha d(2i) - hb conj(d(2i+1)),  r(2i+1) = ha d(2i+1) + hb conj(d(2i)); two ports:
+      // (ha, hb) = (h0, h1) on every pair; four ports: (h0, h2) on the pairs 4i, 4i+1 and (h1, h3) on 4i+2, 4i+3
       for (int i = 0; i + 1 < nre; i += 2) {
-        const cf a0 = 0.5f * (h0[i] + h0[i + 1]), a1 = 0.5f * (h1[i] + h1[i + 1]);
+        const bool second = nant == 4 && (i & 2);
+        const std::vector<cf> &ha = nant == 2 ? h0 : second ? h1 : h0, &hb = nant == 2 ? h1 : second ? h3 : h2;
+        const cf a0 = 0.5f * (ha[i] + ha[i + 1]), a1 = 0.5f * (hb[i] + hb[i + 1]);
         const cf d0 = std::conj(a0) * rx[i] + a1 * std::conj(rx[i + 1]);
         const cf d1 = std::conj(a0) * rx[i + 1] - a1 * std::conj(rx[i]);
         llr[2 * i] = d0.real(); llr[2 * i + 1] = d0.imag();
@@ -225,7 +234,7 @@ extern "C" int ltb_mib_decode(const ltb_cf *halfframe, int cell_id, int cp_norma
       int ports = 0;
       if (nant == 1 && diff == 0x0000u) ports = 1;
       else if (nant == 2 && diff == 0xFFFFu) ports = 2;
-      else if (nant == 1 && diff == 0x5555u) ports = 4;
+      else if (nant == 4 && diff == 0x5555u) ports = 4;
       if (!ports) continue;
       static const int prb[8] = {6, 15, 25, 50, 75, 100, 0, 0};
       const int bw = (bits[0] << 2) | (bits[1] << 1) | bits[2];

@@ -146,9 +146,10 @@ def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False, tdd=False, m
     ext_cp: 6 symbols per slot with a 32*decim-sample prefix (36.211 table 6.12-1).
     tdd: frame structure type 2 -- PSS in symbol 2 of slots 2 and 12, SSS in the last symbol of
     slots 1 and 11 (36.211 6.11.1.2, 6.11.2.2); every subframe is filled like a downlink one.
-    mib: dict(nof_prb, n_ports=1|2, phich_ext=0, phich_res=2, sfn0=0, h=(h0, h1)) adds the cell-specific
+    mib: dict(nof_prb, n_ports=1|2|4, phich_ext=0, phich_res=2, sfn0=0, h=(h0, h1, h2, h3)) adds the cell-specific
     reference signals of the central six resource blocks and the PBCH (FDD position: slot 1 of
-    subframe 0), for one antenna port or two with transmit diversity through flat channels h."""
+    subframe 0), for one antenna port, or two / four with transmit diversity (SFBC / SFBC-FSTD) through flat
+    channels h."""
     rng = rng or np.random.default_rng(cell_id)
     nfft = 128 * decim
     n_used = N_USED.get(decim, 12 * (6 * decim - decim // 2))
@@ -191,8 +192,8 @@ def lte_frame(cell_id, decim=1, rng=None, n_frames=1, ext_cp=False, tdd=False, m
 
 def _add_crs_pbch(grid, cell_id, n_frames, per_slot, ext_cp, nfft, mib):
     n_ports = mib.get("n_ports", 1)
-    h = mib.get("h", (1.0, 0.6 - 0.5j))
-    ports = [grid.copy(), np.zeros_like(grid)]        # payload, PSS and SSS leave from port 0 only
+    h = mib.get("h", (1.0, 0.6 - 0.5j, -0.3 + 0.7j, 0.5 + 0.4j))
+    ports = [grid.copy()] + [np.zeros_like(grid) for _ in range(3)]   # payload, PSS and SSS leave from port 0 only
     cols = _central(np.arange(72)) % nfft
     vshift = cell_id % 6
     n_bits = 1728 if ext_cp else 1920
@@ -202,12 +203,19 @@ def _add_crs_pbch(grid, cell_id, n_frames, per_slot, ext_cp, nfft, mib):
         d = pbch_symbols(cell_id, mib_bits(mib["nof_prb"], mib.get("phich_ext", 0), mib.get("phich_res", 2), sfn),
                          n_ports, n_bits)[(sfn % 4) * per_frame:(sfn % 4 + 1) * per_frame]
         for ns in range(20):
-            for l, v0 in ((0, 0), (per_slot - 3, 3)):
+            # 36.211 6.10.1.2: ports 0 / 1 in symbols 0 and N_symb - 3 (v = 0, 3 / 3, 0); ports 2 / 3 in symbol 1
+            # (v = 3 (n_s mod 2) / 3 + 3 (n_s mod 2)); a pilot RE of one port is empty on every other port
+            for l, vs in ((0, (0, 3, None, None)), (per_slot - 3, (3, 0, None, None)),
+                          (1, (None, None, 3 * (ns % 2), 3 + 3 * (ns % 2)))):
                 sym = (f * 20 + ns) * per_slot + l
                 r = crs_central(cell_id, ns, l, ext_cp)
-                for p in range(2):                    # port 1 mirrors the comb; its REs are empty on port 0
-                    k = 6 * np.arange(12) + ((v0 if p == 0 else 3 - v0) + vshift) % 6
-                    for q in range(2):
+                for p in range(4):
+                    if vs[p] is None:
+                        continue
+                    k = 6 * np.arange(12) + (vs[p] + vshift) % 6
+                    if p >= 2 and n_ports < 4:
+                        continue                      # one- and two-port cells carry data in these REs
+                    for q in range(4):
                         ports[q][sym, cols[k]] = 0
                     if p < n_ports:
                         ports[p][sym, cols[k]] = r
@@ -220,15 +228,25 @@ def _add_crs_pbch(grid, cell_id, n_frames, per_slot, ext_cp, nfft, mib):
                     continue
                 res.append(((f * 20 + 1) * per_slot + l, cols[k]))
         assert len(res) == per_frame
-        for i in range(0, per_frame, 2):
-            (s0, c0), (s1, c1) = res[i], res[i + 1]
-            if n_ports == 1:
-                ports[0][s0, c0], ports[0][s1, c1] = d[i], d[i + 1]
-                ports[1][s0, c0] = ports[1][s1, c1] = 0
-            else:                                     # 36.211 6.3.4.3
-                ports[0][s0, c0], ports[0][s1, c1] = d[i] / np.sqrt(2), d[i + 1] / np.sqrt(2)
-                ports[1][s0, c0], ports[1][s1, c1] = -np.conj(d[i + 1]) / np.sqrt(2), np.conj(d[i]) / np.sqrt(2)
-    return h[0] * ports[0] + (h[1] * ports[1] if n_ports > 1 else 0)
+        for sym_, col_ in res:
+            for q in range(1, 4):
+                ports[q][sym_, col_] = 0
+        r2 = np.sqrt(2)
+        if n_ports == 1:
+            for i in range(per_frame):
+                ports[0][res[i]] = d[i]
+        elif n_ports == 2:                            # 36.211 6.3.4.3, two ports
+            for i in range(0, per_frame, 2):
+                ports[0][res[i]], ports[0][res[i + 1]] = d[i] / r2, d[i + 1] / r2
+                ports[1][res[i]], ports[1][res[i + 1]] = -np.conj(d[i + 1]) / r2, np.conj(d[i]) / r2
+        else:                                         # four ports: SFBC on ports (0, 2), then on ports (1, 3)
+            for i in range(0, per_frame, 4):
+                ports[0][res[i]] = ports[0][res[i + 1]] = ports[0][res[i + 2]] = ports[0][res[i + 3]] = 0
+                ports[0][res[i]], ports[0][res[i + 1]] = d[i] / r2, d[i + 1] / r2
+                ports[2][res[i]], ports[2][res[i + 1]] = -np.conj(d[i + 1]) / r2, np.conj(d[i]) / r2
+                ports[1][res[i + 2]], ports[1][res[i + 3]] = d[i + 2] / r2, d[i + 3] / r2
+                ports[3][res[i + 2]], ports[3][res[i + 3]] = -np.conj(d[i + 3]) / r2, np.conj(d[i + 2]) / r2
+    return sum(h[q] * ports[q] for q in range(n_ports))
 
 
 def capture(cell_id, n_samples, snr_db=None, decim=1, seed=0, offset=None, cfo_hz=0.0, noise_only=False,

@@ -78,17 +78,18 @@ def test_reference_snr_demo_screenshot(oracle, seed):
 
 
 @pytest.mark.parametrize("n_ports,nof_prb,decim,ext_cp", [(1, 15, 2, False), (2, 6, 1, False), (2, 75, 12, False),
-                                                         (2, 25, 4, True)])
-def test_mib_on_synthetic_cells_one_and_two_ports(oracle, n_ports, nof_prb, decim, ext_cp):
+                                                         (2, 25, 4, True), (4, 50, 8, False), (4, 6, 1, True)])
+def test_mib_on_synthetic_cells_one_two_and_four_ports(oracle, n_ports, nof_prb, decim, ext_cp):
     """Synthetic cells with CRS and PBCH (synth.py's transmitter: CRC mask, tail-biting code, rate
-    matching, scrambling, transmit diversity for two ports) through the oracle chain and the host mib:
-    bandwidths the bundled frames do not cover (15 and 75 PRB), extended CP, and two antenna ports
-    -- what srslte_ue_mib_decode reports as nof_ports (lib/mib_impl.cc:163-166)."""
+    matching, scrambling, transmit diversity: SFBC for two ports, SFBC-FSTD for four) through the oracle chain and
+    the host mib: bandwidths the bundled frames do not cover (15 and 75 PRB), extended CP, and two / four antenna
+    ports -- what srslte_ue_mib_decode reports as nof_ports (lib/mib_impl.cc:163-166)."""
     import ltetrigger_b200 as lt
     from ltetrigger_b200 import synth
     cell_id = 100 + 3 * nof_prb + n_ports
     x = synth.capture(cell_id, 19200 * decim * 14, snr_db=12.0, decim=decim, seed=nof_prb, ext_cp=ext_cp,
-                      mib=dict(nof_prb=nof_prb, n_ports=n_ports, phich_res=1, sfn0=4, h=(0.9 + 0.2j, -0.4 + 0.7j)))
+                      mib=dict(nof_prb=nof_prb, n_ports=n_ports, phich_res=1, sfn0=4,
+                               h=(0.9 + 0.2j, -0.4 + 0.7j, 0.3 - 0.8j, -0.6 - 0.5j)))
     y = oracle.decimate(x, decim) if decim > 1 else x
     k = cell_id % 3
     op, os_, mb = oracle.Pss(k, 4.0), oracle.Sss(k), lt.mib(exit_on_success=True)
