@@ -83,8 +83,16 @@ def parse():
     ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the extra sustained run (0: skip)")
     a = ap.parse_args()
     if a.frontend == "auto":
-        a.frontend = "tc" if (a.decim == 16 and a.workload == "c5" and a.impl == "b200") else "fp32"
+        # measured (profiles/tc_rates_r02.log): the tensor-core front end wins wherever it exists except fc32 at D <= 4,
+        # where a tile is so few input bytes that its epilogue outweighs the FFMA2 kernel's 129 / 65 taps
+        wins = tc_exists(a.format, a.decim) and not (a.format == "fc32" and a.decim <= 4)
+        a.frontend = "tc" if (wins and a.workload == "c5" and a.impl == "b200") else "fp32"
     return a
+
+
+def tc_exists(fmt, decim):
+    """(format, rate) pairs the tensor-core front end is built for (include/ltetrigger_b200.h LTB_FRONTEND_TC_INT)."""
+    return decim in {"fc32": (2, 4, 8, 12, 16), "sc16": (4, 8, 12, 16), "sc8": (8, 16)}[fmt]
 
 
 def workload_name(a):
@@ -296,7 +304,7 @@ def main():
 
     def mode_kw(frontend, format_name):
         """(Trigger keyword arguments, oracle conv_mode flag, oracle full scale) of a front-end mode."""
-        if frontend != "tc":
+        if frontend != "tc" or not tc_exists(format_name, a.decim):
             return {}, 0, 0.0
         from oracle import oracle as O_
         kw = {"frontend_mode": lt.FRONTEND_TC_INT}
@@ -454,7 +462,7 @@ def main():
     }
 
     # ---- the other front-end mode on the same input, same steps (D = 16 only: the tensor-core kernel's rate) ----
-    if a.decim == 16 and not a.no_alt:
+    if tc_exists(a.format, a.decim) and not a.no_alt:
         other = "fp32" if a.frontend == "tc" else "tc"
         trig.close()
         alt = timed_run(other, pipeline, a.steps, a.warmup)
@@ -521,7 +529,7 @@ def main():
         # the two front ends against each other on the same streams (north_star: decisions bit-exact, correlation
         # magnitudes and PSR within 1e-4 relative): the integer front end's records next to the canonical float32 ones
         agree, worst = 1, 0.0
-        if a.decim == 16:
+        if tc_exists(a.format, a.decim):
             okw = mode_kw("fp32" if a.frontend == "tc" else "tc", a.format)[0]
             chk = lt.Trigger(n_streams=nchk, decim=a.decim, psr_threshold=4.0, max_chunk=n, input_format=fmt,
                              device=local_rank, corr_mode=corr_mode, **okw)
@@ -551,7 +559,7 @@ def main():
         out["parity_spot_check"] = {"ranks": world, "streams_per_rank": nchk, "records": int(verdict[1].item()),
                                     "bit_identical_to_oracle": bool(verdict[0].item() == 1),
                                     "checker": "oracle/ (CPU restatement), same rate/format/correlator/front end as the timed run"}
-        if a.decim == 16:
+        if tc_exists(a.format, a.decim):
             out["tc_vs_fp32"] = {"decisions_identical": bool(verdict[2].item() == 1), "max_rel_diff_psr_peak": float(wt.item()),
                                  "tolerance": 1e-4, "records": int(verdict[1].item()),
                                  "what": "window records of the integer tensor-core front end against the canonical float32 front end on the "

@@ -311,13 +311,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
-int8_t *g_tc_btab[64][3] = {{nullptr}};          // per device and input format
-long long g_tc_sum_t = 0;
+struct TcTable { int8_t *d = nullptr; long long sum_t = 0; };
+TcTable g_tc_tab[64][3][LTB_MAX_DECIM + 1];      // per device, input format and rate
 
-int ensure_tc_tables(int device) {
+// every supported (format, rate) pair; X(fmt, D)
+#define LTB_TC_VARIANTS(X)                                                                                    \
+  X(LTB_FMT_FC32, 2) X(LTB_FMT_FC32, 4) X(LTB_FMT_FC32, 8) X(LTB_FMT_FC32, 12) X(LTB_FMT_FC32, 16)              \
+  X(LTB_FMT_SC16, 4) X(LTB_FMT_SC16, 8) X(LTB_FMT_SC16, 12) X(LTB_FMT_SC16, 16)                                \
+  X(LTB_FMT_SC8, 8) X(LTB_FMT_SC8, 16)
+
+int ensure_tc_tables(int device, int fmt, int decim) {
   std::lock_guard<std::mutex> lk(g_const_mu);
-  if (g_tc_btab[device][LTB_FMT_SC16]) return LTB_SUCCESS;
   static_assert(LTB_FMT_FC32 == 0 && LTB_FMT_SC16 == 1 && LTB_FMT_SC8 == 2, "tap tables are indexed by format");
+  if (!tc_supported(fmt, decim)) return fail(LTB_ERROR_INVALID_INPUTS, "no tensor-core front end for this format and rate");
+  TcTable &tt = g_tc_tab[device][fmt][decim];
+  if (tt.d) return LTB_SUCCESS;
   if (!g_encode_tiled) {
     cudaDriverEntryPointQueryResult qres;
     void *fn = nullptr;
@@ -325,33 +333,35 @@ int ensure_tc_tables(int device) {
       return fail(LTB_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
     g_encode_tiled = (EncodeTiledFn)fn;
   }
-  make_tc_taps(&g_tc_sum_t);
-  for (int fmt : {LTB_FMT_FC32, LTB_FMT_SC8, LTB_FMT_SC16}) {                 // sc16 last: it marks the tables as built
-    const std::vector<int8_t> tab = make_tc_btab(fmt);
-    if (tab.empty()) return fail(LTB_ERROR, "decimator taps do not fit three base-256 digits");
-    int8_t *d = nullptr;
-    LTB_CUDA(cudaMalloc(&d, tab.size()));
-    LTB_CUDA(cudaMemcpy(d, tab.data(), tab.size(), cudaMemcpyHostToDevice));
-    g_tc_btab[device][fmt] = d;
-  }
-  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<LTB_FMT_SC16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<LTB_FMT_SC8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
-  LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<LTB_FMT_FC32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
+  long long sum = 0;
+  make_tc_taps(decim, &sum);
+  const std::vector<int8_t> tab = make_tc_btab(fmt, decim);
+  if (tab.empty()) return fail(LTB_ERROR, "decimator taps do not fit three base-256 digits");
+  int8_t *d = nullptr;
+  LTB_CUDA(cudaMalloc(&d, tab.size()));
+  LTB_CUDA(cudaMemcpy(d, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+#define X(F, DD) if (fmt == F && decim == DD) LTB_CUDA(cudaFuncSetAttribute(decimate_tc_kernel<F, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes()));
+  LTB_TC_VARIANTS(X)
+#undef X
+  tt.sum_t = sum;
+  tt.d = d;
   return LTB_SUCCESS;
 }
 
-// n_in new samples per stream (multiple of 128) -> n_in / 16 search-rate samples in y_ring; tail_old holds the
-// 768 raw samples before the chunk, tail_new receives the last 768 for the next call.  full_scale: fc32 only
+// n_in new samples per stream (multiple of 8 decim) -> n_in / decim search-rate samples in y_ring; tail_old holds the
+// 48 decim raw samples before the chunk, tail_new receives the last 48 decim for the next call.  full_scale: fc32 only
 // (the input is taken as 23-bit fixed point of that range, ltb_tc_frontend.cuh)
-int launch_frontend_tc(int device, int fmt, float full_scale, const void *d_iq, long long stride, int n_streams, int n_in,
+int launch_frontend_tc(int device, int fmt, int decim, float full_scale, const void *d_iq, long long stride, int n_streams, int n_in,
                        const void *tail_old, void *tail_new, float2 *y_ring, long long n_base, unsigned mask, int cap, int *d_err,
                        cudaStream_t st, int *launches) {
   if ((reinterpret_cast<uintptr_t>(d_iq) | (uintptr_t)stride) & 15u)
     return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT needs a 16-byte aligned input pointer and row stride (TMA)");
+  if (!tc_supported(fmt, decim) || !g_tc_tab[device][fmt][decim].d) return fail(LTB_ERROR, "tensor-core front end not initialised for this format and rate");
   const int bps = tc_sample_bytes(fmt);
-  const int full_rows = n_in / kTcRowSamples;
+  const int row = 16 * decim;
+  const int full_rows = n_in / row;
   CUtensorMap map;
-  const cuuint64_t row_bytes = (cuuint64_t)kTcRowSamples * bps;
+  const cuuint64_t row_bytes = (cuuint64_t)row * bps;
   const cuuint64_t gdim[3] = {row_bytes, (cuuint64_t)(full_rows > 0 ? full_rows : 1), (cuuint64_t)n_streams};
   const cuuint64_t gstr[2] = {row_bytes, (cuuint64_t)stride};
   const cuuint32_t box[3] = {256, (cuuint32_t)kTcTileRows, 1}, estr[3] = {1, 1, 1};
@@ -360,31 +370,33 @@ int launch_frontend_tc(int device, int fmt, float full_scale, const void *d_iq, 
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LTB_ERROR, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  const TcTable &tt = g_tc_tab[device][fmt][decim];
   TcParams P;
   P.in = d_iq; P.stride_bytes = stride; P.n_in = n_in; P.n_streams = n_streams; P.tail = tail_old; P.y_ring = y_ring;
-  P.n_base = n_base; P.cap_mask = mask; P.cap = cap;
-  const int rows = (n_in + kTcRowSamples - 1) / kTcRowSamples;
+  P.n_base = n_base; P.cap_mask = mask; P.cap = cap; P.m_out = n_in / decim;
+  const int rows = (n_in + row - 1) / row;
   P.tiles_per_stream = (rows + kTcUseful - 1) / kTcUseful;
   const long long total = (long long)P.tiles_per_stream * n_streams;
   if (total > 0x7fffffffLL) return fail(LTB_ERROR_INVALID_INPUTS, "too many decimator tiles in one call");
   P.total_tiles = (int)total;
-  P.btab = g_tc_btab[device][fmt]; P.err = d_err; P.dbg_acc = nullptr;
-  P.c_const = fmt == LTB_FMT_SC16 ? 128 * g_tc_sum_t : fmt == LTB_FMT_FC32 ? -16384 * g_tc_sum_t : 0;
+  P.btab = tt.d; P.err = d_err; P.dbg_acc = nullptr;
+  const int shift = tc_tap_shift_for(decim);
+  P.c_const = fmt == LTB_FMT_SC16 ? 128 * tt.sum_t : fmt == LTB_FMT_FC32 ? -16384 * tt.sum_t : 0;
   P.q_inv = fmt == LTB_FMT_FC32 ? (float)(0.5 / (double)full_scale) : 0.f;
-  P.out_scale = fmt == LTB_FMT_FC32 ? (float)((double)full_scale / 4194303.0 / 524288.0)
-                                    : fmt == LTB_FMT_SC16 ? 2.2737367544323206e-13f : 5.8207660913467407e-11f;   // 2^-42, 2^-34
+  P.out_scale = fmt == LTB_FMT_FC32 ? (float)((double)full_scale / 4194303.0 * std::ldexp(1.0, 8 - shift))
+                                    : (float)std::ldexp(1.0, -(shift + (fmt == LTB_FMT_SC16 ? 15 : 7)));
   const int sms = g_sm_count[device] > 0 ? g_sm_count[device] : 148;
   const int grid = P.total_tiles < sms ? P.total_tiles : sms;
-  if (fmt == LTB_FMT_FC32) {
-    decimate_tc_kernel<LTB_FMT_FC32><<<grid, kTcThreads, tc_smem_bytes(), st>>>(map, P);
-    tc_tail_kernel<LTB_FMT_FC32><<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);
-  } else if (fmt == LTB_FMT_SC16) {
-    decimate_tc_kernel<LTB_FMT_SC16><<<grid, kTcThreads, tc_smem_bytes(), st>>>(map, P);
-    tc_tail_kernel<LTB_FMT_SC16><<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);
-  } else {
-    decimate_tc_kernel<LTB_FMT_SC8><<<grid, kTcThreads, tc_smem_bytes(), st>>>(map, P);
-    tc_tail_kernel<LTB_FMT_SC8><<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);
+  bool launched = false;
+#define X(F, DD)                                                                                             \
+  if (fmt == F && decim == DD) {                                                                             \
+    decimate_tc_kernel<F, DD><<<grid, kTcThreads, tc_smem_bytes(), st>>>(map, P);                            \
+    tc_tail_kernel<F, DD><<<n_streams, 256, 0, st>>>(d_iq, stride, n_in, tail_old, tail_new);                \
+    launched = true;                                                                                         \
   }
+  LTB_TC_VARIANTS(X)
+#undef X
+  if (!launched) return fail(LTB_ERROR, "no tensor-core kernel for this format and rate");
   *launches += 2;
   return LTB_SUCCESS;
 }
@@ -534,7 +546,7 @@ int trigger_enqueue(ltb_trigger *t, const void *d_iq, long long stride, long lon
   LTB_CUDA(cudaEventRecord(sl.ev0, t->stream));
   int rc;
   if (c.frontend_mode == LTB_FRONTEND_TC_INT)
-    rc = launch_frontend_tc(c.device, c.input_format, c.fc32_full_scale, d_iq, stride, S, (int)n_samples, t->d_tc_tail[t->tail_cur], t->d_tc_tail[t->tail_cur ^ 1],
+    rc = launch_frontend_tc(c.device, c.input_format, c.decim, c.fc32_full_scale, d_iq, stride, S, (int)n_samples, t->d_tc_tail[t->tail_cur], t->d_tc_tail[t->tail_cur ^ 1],
                             t->d_y, n_base, t->cap_mask, t->cap, t->d_tc_err, t->stream, &launches);
   else
     rc = launch_frontend_fmt(c.input_format, c.decim, d_iq, stride, S, m, t->d_tail[t->tail_cur], t->d_tail[t->tail_cur ^ 1],
@@ -633,8 +645,9 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
       (c.pipeline != LTB_PIPE_OVERLAP && c.pipeline != LTB_PIPE_SERIAL) ||
       (c.frontend_mode != LTB_FRONTEND_FP32 && c.frontend_mode != LTB_FRONTEND_TC_INT))
     return fail(LTB_ERROR_INVALID_INPUTS, "invalid trigger configuration");
-  if (c.frontend_mode == LTB_FRONTEND_TC_INT && c.decim != 16)
-    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT is available at decim = 16");
+  if (c.frontend_mode == LTB_FRONTEND_TC_INT && !tc_supported(c.input_format, c.decim))
+    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT is available at decim 2 / 4 / 8 / 12 / 16 for fc32, 4 / 8 / 12 / 16 for sc16 "
+                                          "and 8 / 16 for sc8 input (a 16-output row must be whole 256-byte pieces)");
   if (c.frontend_mode == LTB_FRONTEND_TC_INT && c.input_format == LTB_FMT_FC32 &&
       !(c.fc32_full_scale > 0.f && c.fc32_full_scale < 1e30f))
     return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT on fc32 input takes the samples as 23-bit fixed point: "
@@ -648,7 +661,7 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
   LTB_CUDA(cudaSetDevice(c.device));
   int rc = ensure_constants(c.device);
   if (!rc && c.corr_mode == LTB_CORR_FFT) rc = ensure_os_tables(c.device);
-  if (!rc && c.frontend_mode == LTB_FRONTEND_TC_INT) rc = ensure_tc_tables(c.device);
+  if (!rc && c.frontend_mode == LTB_FRONTEND_TC_INT) rc = ensure_tc_tables(c.device, c.input_format, c.decim);
   if (rc) return rc;
 
   ltb_trigger *t = new ltb_trigger();
@@ -1063,23 +1076,18 @@ int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, 
   return rc;
 }
 
-int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y) {
-  if (fmt != LTB_FMT_SC16 && fmt != LTB_FMT_SC8) return fail(LTB_ERROR_INVALID_INPUTS, "integer input only (fc32: ltb_kernel_decimate_tc_host2)");
-  return ltb_kernel_decimate_tc_host2(device, x, fmt, 0.f, n_streams, n_in, chunk, y);
-}
-
-int ltb_kernel_decimate_tc_host2(int device, const void *x, int fmt, float full_scale, int n_streams, int64_t n_in,
-                                 int64_t chunk, ltb_cf *y) {
-  if (!x || !y || n_streams <= 0 || n_in <= 0 || (n_in % 128) != 0 || chunk <= 0 || (chunk % 128) != 0 ||
-      !valid_format(fmt) || (fmt == LTB_FMT_FC32 && !(full_scale > 0.f && full_scale < 1e30f)))
-    return fail(LTB_ERROR_INVALID_INPUTS, "n_in and chunk positive multiples of 128; fc32 needs full_scale > 0");
+int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int decim, float full_scale, int n_streams, int64_t n_in,
+                                int64_t chunk, ltb_cf *y) {
+  if (!x || !y || n_streams <= 0 || !valid_format(fmt) || !tc_supported(fmt, decim) || n_in <= 0 || (n_in % (8 * decim)) != 0 ||
+      chunk <= 0 || (chunk % (8 * decim)) != 0 || (fmt == LTB_FMT_FC32 && !(full_scale > 0.f && full_scale < 1e30f)))
+    return fail(LTB_ERROR_INVALID_INPUTS, "a supported (format, rate) pair, n_in and chunk positive multiples of 8 decim; fc32 needs full_scale > 0");
   if (ltb_device_count() <= device || device < 0) return fail(LTB_ERROR, "no such CUDA device");
   LTB_CUDA(cudaSetDevice(device));
   int rc = ensure_constants(device);
-  if (!rc) rc = ensure_tc_tables(device);
+  if (!rc) rc = ensure_tc_tables(device, fmt, decim);
   if (rc) return rc;
   const int bps = tc_sample_bytes(fmt);
-  const int m = (int)(n_in / 16);
+  const int m = (int)(n_in / decim);
   const int cap = next_pow2(m + 8);
   const size_t in_row = (size_t)n_in * bps, dev_row = (in_row + 127) / 128 * 128;
   void *d_in = nullptr; float2 *d_y = nullptr; void *d_t[2] = {nullptr, nullptr}; int *d_err = nullptr;
@@ -1095,8 +1103,8 @@ int ltb_kernel_decimate_tc_host2(int device, const void *x, int fmt, float full_
   for (int64_t c0 = 0; c0 < n_in && e == cudaSuccess && !rc; c0 += chunk) {
     const int nc = (int)(n_in - c0 < chunk ? n_in - c0 : chunk);
     int launches = 0;
-    rc = launch_frontend_tc(device, fmt, full_scale, (const char *)d_in + c0 * bps, (long long)dev_row, n_streams, nc, d_t[cur], d_t[cur ^ 1], d_y,
-                            c0 / 16, (unsigned)(cap - 1), cap, d_err, 0, &launches);
+    rc = launch_frontend_tc(device, fmt, decim, full_scale, (const char *)d_in + c0 * bps, (long long)dev_row, n_streams, nc, d_t[cur], d_t[cur ^ 1], d_y,
+                            c0 / decim, (unsigned)(cap - 1), cap, d_err, 0, &launches);
     cur ^= 1;
     e = cudaGetLastError();
   }
@@ -1149,11 +1157,11 @@ int ltb_table_os_filter(int n_id_2, float H_re[1024], float H_im[1024]) {
   return LTB_SUCCESS;
 }
 
-int ltb_table_tc_btab(int fmt, int8_t tab[208 * 128], int64_t *sum_t) {
-  if (!valid_format(fmt) || !tab) return LTB_ERROR_INVALID_INPUTS;
+int ltb_table_tc_btab(int fmt, int decim, int8_t tab[208 * 128], int64_t *sum_t) {
+  if (!valid_format(fmt) || !tab || !tc_supported(fmt, decim)) return LTB_ERROR_INVALID_INPUTS;
   long long sum = 0;
-  make_tc_taps(&sum);
-  const std::vector<int8_t> t = make_tc_btab(fmt);
+  make_tc_taps(decim, &sum);
+  const std::vector<int8_t> t = make_tc_btab(fmt, decim);
   if (t.size() != 208 * 128) return LTB_ERROR;
   std::memcpy(tab, t.data(), t.size());
   if (sum_t) *sum_t = sum;

@@ -125,21 +125,25 @@ std::vector<float> make_decim_branch_taps(int decim) {
   return out;
 }
 
-std::vector<int32_t> make_tc_taps(long long *sum_t) {
-  const std::vector<float> taps = make_decim_taps(16);
+static int tc_ilog2(int d) { int l = 0; while (d > 1) { d >>= 1; ++l; } return l; }
+int tc_tap_shift_for(int decim) { return 23 + tc_ilog2(decim); }
+
+std::vector<int32_t> make_tc_taps(int decim, long long *sum_t) {
+  const std::vector<float> taps = make_decim_taps(decim);
   std::vector<int32_t> T(taps.size());
   long long sum = 0;
+  const double scale = std::ldexp(1.0, tc_tap_shift_for(decim));
   for (size_t j = 0; j < taps.size(); ++j) {
-    T[j] = (int32_t)std::llrint((double)taps[j] * 134217728.0);     // 2^27
+    T[j] = (int32_t)std::llrint((double)taps[j] * scale);
     sum += T[j];
   }
   if (sum_t) *sum_t = sum;
   return T;
 }
 
-std::vector<int8_t> make_tc_btab(int fmt) {
+std::vector<int8_t> make_tc_btab(int fmt, int decim) {
   constexpr int kRows = 208, kTile = kRows * 128;
-  const std::vector<int32_t> T = make_tc_taps(nullptr);
+  const std::vector<int32_t> T = make_tc_taps(decim, nullptr);
   std::vector<int8_t> tab((size_t)kTile, 0);
   auto sw_off = [](int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); };
   auto digit = [](int t, int v, bool *ok) {            // balanced base-256 digits, v = 0..2
@@ -149,40 +153,26 @@ std::vector<int8_t> make_tc_btab(int fmt) {
     return v == 0 ? d0 : v == 1 ? d1 : v == 2 ? t2 : 0;
   };
   auto tap = [&](int j) { return (j >= 0 && j < (int)T.size()) ? T[j] : 0; };
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
   bool ok = true;
-  const bool sc16 = fmt == 1;
-  if (fmt == 0) {
-    // fc32 as 23-bit fixed point: a k-step is 8 samples x 4 bytes (byte 3 is not a digit: zero row entries); the
-    // even and odd k-steps of an output's 16 samples have their own tables at bytes 0..31 and 32..63 of a row.
-    // Column v' holds weight 256^(v'+1): the weight-1 product (lowest sample byte x lowest tap digit) is not formed.
-    for (int n = 0; n < kRows; ++n) {
-      const int d = n / 4, v = n % 4 + 1;
-      if (d > 33) continue;
-      for (int h = 0; h < 2; ++h)
-        for (int p8 = 0; p8 < 8; ++p8) {
-          const int t = tap(16 * d - 8 * h - p8);
-          for (int bi = 0; bi < 3; ++bi) {
-            const int i = v - bi, kb = 32 * h + 4 * p8 + bi;
-            if (i >= 0 && i <= 2) tab[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)digit(t, i, &ok);
-          }
-        }
-    }
-    if (!ok) tab.clear();
-    return tab;
-  }
+  // a k-step is 32 bytes of one component: spk samples of bps bytes each (fc32: three digit bytes and one byte that
+  // meets zeros).  Row 4 d + v of the table of phase ph holds, at byte bps' p + byte, the tap digit that byte of
+  // sample p multiplies into weight 256^v (fc32: 256^(v+1), its weight-1 product is not formed): T[decim d - ph - p].
+  const int bpc = fmt == 0 ? 4 : fmt == 1 ? 2 : 1, spk = 32 / bpc, g = gcd(spk, decim), nph = decim / g;
+  if (nph > 4) return std::vector<int8_t>();
   for (int n = 0; n < kRows; ++n) {
     const int d = n / 4, v = n % 4;
-    if (d > (sc16 ? 33 : 34)) continue;
-    for (int pp = 0; pp < (sc16 ? 16 : 32); ++pp) {
-      const int t = tap(16 * d - pp);
-      if (sc16) {
-        const int kb = 2 * pp;
-        tab[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)(v <= 2 ? digit(t, v, &ok) : 0);
-        tab[sw_off(n, (kb + 1) >> 4) + ((kb + 1) & 15)] = (int8_t)(v >= 1 ? digit(t, v - 1, &ok) : 0);
-      } else {
-        tab[sw_off(n, pp >> 4) + (pp & 15)] = (int8_t)(v <= 2 ? digit(t, v, &ok) : 0);
+    for (int i = 0; i < nph; ++i)
+      for (int p = 0; p < spk; ++p) {
+        const int t = tap(decim * d - i * g - p);
+        if (!t) continue;
+        for (int byte = 0; byte < (fmt == 0 ? 3 : bpc); ++byte) {
+          const int dg = fmt == 0 ? v + 1 - byte : v - byte;                    // tap digit index
+          if (dg < 0 || dg > 2) continue;
+          const int kb = 32 * i + bpc * p + byte;
+          tab[sw_off(n, kb >> 4) + (kb & 15)] = (int8_t)digit(t, dg, &ok);
+        }
       }
-    }
   }
   if (!ok) tab.clear();                                 // a tap that needs a fourth digit: never for these taps
   return tab;

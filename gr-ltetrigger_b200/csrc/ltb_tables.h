@@ -17,14 +17,16 @@ std::vector<float> make_decim_taps(int decim);
 // a branch would need more than 33 taps (never for decim <= 64)
 std::vector<float> make_decim_branch_taps(int decim);
 
-// LTB_FRONTEND_TC_INT (csrc/ltb_tc_frontend.cuh): the D = 16 taps quantised to T[j] = rint(taps[j] * 2^27), and
-// the tap table of the tensor-core kernel in its shared-memory image ([208 rows][128 B], K-major, 128-byte
-// swizzle, the first 32 bytes of a row used).  sc16 (fmt 1): row 4 d + v holds digit v (lo byte) / digit v - 1
-// (hi byte) of T[16 d - p'], p' = 0..15; sc8 (fmt 2): digit v of T[16 d - p'], p' = 0..31; fc32 as 23-bit fixed point
-// (fmt 0): two tables, bytes 0..31 (samples 0..7 of an output's 16) and 32..63 (samples 8..15), byte 4 p8 + bi of
-// row 4 d + v' holds digit v' + 1 - bi of T[16 d - 8 h - p8].  sum_t receives sum_j T[j].
-std::vector<int32_t> make_tc_taps(long long *sum_t);
-std::vector<int8_t> make_tc_btab(int fmt);
+// LTB_FRONTEND_TC_INT (csrc/ltb_tc_frontend.cuh): the taps of rate `decim` quantised to T[j] = rint(taps[j] * 2^shift),
+// shift = 23 + floor(log2(decim)) (27 at decim 16: |T| < 2^23, three balanced base-256 digits), and the tap table of the
+// tensor-core kernel in its shared-memory image ([208 rows][128 B], K-major, 128-byte swizzle).  A k-step is 32 bytes of
+// one component (sc16: 16 samples x {lo, hi}; sc8: 32 samples; fc32 as 23-bit fixed point: 8 samples x {b0, b1, b2, -});
+// row 4 d + v of the table of phase ph (bytes 32 i .. 32 i + 31 of the row, ph = i gcd(samples per k-step, decim)) holds
+// at each byte the digit of T[decim d - ph - p] that byte of sample p multiplies into weight 256^v (fc32: 256^(v+1)).
+// sum_t receives sum_j T[j].
+int tc_tap_shift_for(int decim);
+std::vector<int32_t> make_tc_taps(int decim, long long *sum_t);
+std::vector<int8_t> make_tc_btab(int fmt, int decim);
 
 struct SssTables {
   int32_t c0[31], c1[31], s_tilde[31], z_tilde[31];

@@ -48,7 +48,7 @@
 
 namespace ltb {
 
-constexpr int kTcRowSamples = 256;                 // input samples per A row (16 outputs)
+constexpr int kTcRowSamples = 256;                 // input samples per A row (16 outputs) at D = 16; in general 16 D
 constexpr int kTcTileRows = 64;                    // stream rows per tile (x 2 components = M 128)
 constexpr int kTcHalo = 3;                         // rows a tile re-reads from the tile above
 constexpr int kTcUseful = kTcTileRows - kTcHalo;   // 61
@@ -69,7 +69,6 @@ constexpr int kTcRawStages = LTB_TC_RAW_STAGES, kTcAStages = LTB_TC_A_STAGES;
 constexpr int kTcRawBytes = kTcTileRows * 256;     // 16384: 256 raw bytes per row and stage (64 sc16 / 128 sc8 samples)
 constexpr int kTcABytes = 128 * 128;               // 16384
 constexpr int kTcBRows = 208;                      // accumulator columns of one tile (49 u's x 4, padded to 16)
-constexpr int kTcNStep = 144;                      // N of a k-step's MMA: 34 (35) u's x 4, padded to 16
 constexpr int kTcBTileBytes = kTcBRows * 128;      // 26624 (the first 32 bytes of each 128-byte row are used)
 constexpr int kTcEpiWarps = 8, kTcXformWarps = 8;  // warps 0..7; 8 producer, 9 MMA; 10..17
 #ifndef LTB_TC_XFORM_GROUPS
@@ -78,12 +77,48 @@ constexpr int kTcEpiWarps = 8, kTcXformWarps = 8;  // warps 0..7; 8 producer, 9 
 constexpr int kTcXformGroups = LTB_TC_XFORM_GROUPS;                 // groups of transform warps that take alternate stages
 constexpr int kTcXformGroupWarps = kTcXformWarps / kTcXformGroups;
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 2 + kTcXformWarps);   // 576
-constexpr int kTcTailSamples = kTcHalo * kTcRowSamples;   // 768 raw samples of history per stream
-constexpr int kTcTapShift = 27;
+constexpr int kTcTailSamples = kTcHalo * kTcRowSamples;   // 768 raw samples of history per stream at D = 16 (the largest)
+constexpr int kTcTapShift = 27;                    // at D = 16; tc_tap_shift(D) in general
+
+// ---- geometry of the (format, decimation) variants ------------------------------------------------------------
+// A row is always 16 outputs = 16 D input samples of one component; a k-step is 32 bytes of it = SPK samples
+// (sc16 16, sc8 32, fc32 8), i.e. SPK / D outputs: the accumulator column offset of k-step s is 4 floor(s SPK / D) and the
+// taps it meets are T[D d - phase - p] with phase = (s SPK) mod D -- one tap table per distinct phase (one when D
+// divides SPK; two for fc32 at D = 16; three at D = 12), side by side in the 128-byte rows of the table tile.
+__host__ __device__ constexpr int tc_gcd(int a, int b) { return b == 0 ? a : tc_gcd(b, a % b); }
+__host__ __device__ constexpr int tc_ntaps(int D) {           // gr-filter's default design (ltb_tables.cpp make_decim_taps)
+  return (int)((7.0 / 0.1102 + 8.7) / (22.0 * 0.1 / D)) + 1 - ((int)((7.0 / 0.1102 + 8.7) / (22.0 * 0.1 / D)) & 1);
+}
+__host__ __device__ constexpr int tc_log2(int D) { return D <= 1 ? 0 : 1 + tc_log2(D / 2); }
+__host__ __device__ constexpr int tc_tap_shift(int D) { return 23 + tc_log2(D); }    // max |T| = 0.9 / 0.6 x 2^23: three digits
+template <int FMT, int D>
+struct TcGeom {
+  static constexpr int BPS = FMT == LTB_FMT_FC32 ? 8 : FMT == LTB_FMT_SC16 ? 4 : 2;   // bytes per complex input sample
+  static constexpr int ROW = 16 * D;                           // samples per A row
+  static constexpr int ROW_BYTES = ROW * BPS;
+  static constexpr int SPT = ROW_BYTES / 256;                  // pipeline stages (128-byte A atoms) per tile
+  static constexpr int SPK = 64 / BPS;                         // samples per k-step
+  static constexpr int KSTEPS = ROW / SPK;                     // = 4 SPT
+  static constexpr int G = tc_gcd(SPK, D);
+  static constexpr int NPH = D / G;                            // distinct phases (tap tables)
+  static constexpr int NTAPS = tc_ntaps(D);
+  static constexpr int ND = (NTAPS - 1 + (D - G) + SPK - 1) / D + 1;   // tap-table row groups a k-step can meet
+  static constexpr int NSTEP = (4 * ND + 15) / 16 * 16;        // N of a k-step's MMA
+  static constexpr int TAIL = kTcHalo * ROW;                   // raw samples of history per stream
+  static constexpr bool ok = ROW_BYTES % 256 == 0 && NPH <= 4 && 4 * (((KSTEPS - 1) * SPK) / D) + NSTEP <= kTcBRows &&
+                             ((KSTEPS - 1) * SPK) / D + ND - 1 <= 48 && NTAPS <= 3 * ROW + D;
+};
+__host__ inline bool tc_supported(int fmt, int D) {
+  switch (fmt * 100 + D) {
+    case 2: case 4: case 8: case 12: case 16: return true;                     // fc32
+    case 104: case 108: case 112: case 116: return true;                       // sc16
+    case 208: case 216: return true;                                           // sc8
+  }
+  return false;
+}
 constexpr int kTcStagePitch = 17;                  // floats per (row, component) in the output staging
 
 __host__ __device__ constexpr int tc_sample_bytes(int fmt) { return fmt == LTB_FMT_FC32 ? 8 : fmt == LTB_FMT_SC16 ? 4 : 2; }
-__host__ __device__ constexpr int tc_stages_per_tile(int fmt) { return fmt == LTB_FMT_FC32 ? 8 : fmt == LTB_FMT_SC16 ? 4 : 2; }
 // fc32 input: fixed point with 23 bits.  q(x) = bits(fma(fma.sat(x, 0.5 / full_scale, 0.5), 2^23 - 2, 2^23 + 1)) & 0x7fffff
 // is an integer 1 .. 2^23 - 1 whose distance from 2^22 is x / full_scale * (2^22 - 1) rounded (two roundings, both
 // restated by the oracle); values beyond +-full_scale saturate.
@@ -108,7 +143,8 @@ struct TcParams {
   const int8_t *btab;          // [208][128]: tap table in its shared-memory image (ltb_tables.cpp make_tc_btab)
   long long c_const;           // sc16: 128 * sum_j T[j]; sc8: 0; fc32: -2^14 * sum_j T[j]
   float q_inv;                 // fc32: 0.5 / full_scale
-  float out_scale;             // fc32: float(full_scale / (2^22 - 1) * 2^-19); sc16 2^-42, sc8 2^-34
+  float out_scale;             // fc32: float(full_scale / (2^22 - 1) * 2^-(shift - 8)); sc16 2^-(shift + 15), sc8 2^-(shift + 7)
+  int m_out;                   // outputs per stream of this call: n_in / D
   int *err;                    // device flag: 0 ok, else the code of the watchdog that fired
   int *dbg_acc;                // null, or [128][208] int32: the raw accumulator tile of tile 0 (tools/ubench_tc_i8)
 };
@@ -255,7 +291,7 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const uint32
                                                  const uint32_t acc_empty0, float *s_stage, long long *s_xchg,
                                                  const int t_begin, const int t_end) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m_out = P.n_in / 16;
+  const int m_out = P.m_out;
   int stream = t_begin / P.tiles_per_stream, ti = t_begin - stream * P.tiles_per_stream;
   auto next_tile = [&]() { if (++ti == P.tiles_per_stream) { ti = 0; ++stream; } };
   auto acc_full = [&](int i) { return acc_full0 + 8u * i; };
@@ -359,17 +395,16 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const uint32
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
-template <int FMT>
+template <int FMT, int D>
 __global__ void __launch_bounds__(LTB_TC_LB_THREADS, 1)
 decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
-  constexpr int BPS = tc_sample_bytes(FMT);                 // bytes per complex input sample
-  constexpr int SPT = tc_stages_per_tile(FMT);              // pipeline stages (128-byte A atoms) per tile
+  typedef TcGeom<FMT, D> GEO;
+  static_assert(GEO::ok, "unsupported (format, decimation) for the tensor-core front end");
+  constexpr int BPS = GEO::BPS;                             // bytes per complex input sample
+  constexpr int SPT = GEO::SPT;                             // pipeline stages (128-byte A atoms) per tile
   constexpr int ITEM = 16 / BPS;                            // samples per 16-byte transform item
   constexpr int STAGE_SAMPLES = 256 / BPS;                  // samples per row and stage
-  // accumulator columns per k-step: a k-step is 16 sc16 samples (one output: 4 columns), 32 sc8 samples (8) or
-  // 8 fc32 samples (half an output: the column offset advances every other k-step and the two halves of an
-  // output's 16 samples have their own tap tables, bytes 0..31 and 32..63 of the table's rows)
-  constexpr int COLSTEP = FMT == LTB_FMT_SC8 ? 8 : 4;
+  constexpr int ROW = GEO::ROW;
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   unsigned char *s_b = tc_smem;                                         // [208][128]
   unsigned char *s_a = s_b + kTcBTileBytes;                             // [kTcAStages][128][128]
@@ -389,8 +424,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t_begin = (int)((long long)P.total_tiles * blockIdx.x / gridDim.x);
   const int t_end = (int)((long long)P.total_tiles * (blockIdx.x + 1) / gridDim.x);
-  const int full_rows = P.n_in / kTcRowSamples;             // rows the tensor map covers
-  const int m_out = P.n_in / 16;
+  const int full_rows = P.n_in / ROW;                       // rows the tensor map covers
   // every role walks the same tiles; (stream, tile-in-stream) advances incrementally (one division up front)
   int stream = t_begin / P.tiles_per_stream, ti = t_begin - stream * P.tiles_per_stream;
   auto next_tile = [&]() { if (++ti == P.tiles_per_stream) { ti = 0; ++stream; } };
@@ -450,23 +484,18 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
           const uint32_t a_base = tc_smem_u32(s_a + (size_t)as * kTcABytes);
-          const uint64_t bdesc = tc_make_desc(tc_smem_u32(s_b));
-          const uint64_t bdesc1 = tc_make_desc(tc_smem_u32(s_b) + 32);       // fc32: taps of the odd k-steps
-          (void)bdesc1;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int s = 4 * a + k;                                     // k-step of the row
             const bool first = s == 0;
             const uint64_t adesc = tc_make_desc(a_base + 32 * k);
             if (LTB_TC_BISECT & 2) continue;
-            if (FMT == LTB_FMT_FC32) {
-              const uint32_t d = tmem + buf * 256 + COLSTEP * (s >> 1);
-              tc_mma_i8(d, adesc, (s & 1) ? bdesc1 : bdesc, first ? tc_idesc(kTcBRows, false) : tc_idesc(kTcNStep, false),
-                        first ? 0u : 1u);
-            } else {
-              const uint32_t d = tmem + buf * 256 + COLSTEP * s;
-              tc_mma_i8(d, adesc, bdesc, first ? tc_idesc(kTcBRows) : tc_idesc(kTcNStep), first ? 0u : 1u);
-            }
+            const int off = s * GEO::SPK;                                // first sample of the k-step in its row
+            const int u0 = off / D, ph = (off - u0 * D) / GEO::G;        // accumulator column group, tap table
+            const uint32_t d = tmem + buf * 256 + 4 * u0;
+            const uint64_t bd = tc_make_desc(tc_smem_u32(s_b) + 32 * ph);
+            constexpr bool a_signed = FMT != LTB_FMT_FC32;
+            tc_mma_i8(d, adesc, bd, first ? tc_idesc(kTcBRows, a_signed) : tc_idesc(GEO::NSTEP, a_signed), first ? 0u : 1u);
           }
           tc_commit(a_empty(as));
           if (a == SPT - 1) tc_commit(acc_full(buf));
@@ -487,7 +516,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
     const int src_off = r_t * 256 + c * 16;
     const int dst_off = tc_sw_off(r_t, c >> 1) + (c & 1) * 8;
     static_assert(ROWSTEP % 8 == 0, "swizzle phase must not change between a thread's items");
-    static_assert(SPT % kTcXformGroups == 0, "a tile's stages are dealt evenly to the groups");
+    static_assert(kTcXformGroups == 1 || kTcXformGroups == 2, "stages are dealt to the groups by the parity of their running index");
     int it0 = 0;
     for (int t = t_begin; t < t_end; ++t, next_tile(), it0 += SPT) {
       const int row0 = ti * kTcUseful - kTcHalo;
@@ -496,8 +525,9 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
 #else
       const bool patch = row0 < 0 || row0 + kTcTileRows > full_rows;     // some rows are not plain tensor rows
 #endif
-      for (int a = grp; a < SPT; a += kTcXformGroups) {
+      for (int a = 0; a < SPT; ++a) {
         const int it = it0 + a;
+        if (kTcXformGroups == 2 && (it & 1) != grp) continue;
         const int rs = it % kTcRawStages, as = it % kTcAStages;
         tc_mbar_wait<0>(raw_full(rs), (it / kTcRawStages) & 1, P.err, 4);
         tc_mbar_wait<0>(a_empty(as), ((it / kTcAStages) & 1) ^ 1, P.err, 5);
@@ -517,10 +547,9 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
             const int ra = row0 + r_t + ROWSTEP * j;
-            const int n0 = ra * kTcRowSamples + a * STAGE_SAMPLES + c * ITEM;      // first sample of the item
+            const int n0 = ra * ROW + a * STAGE_SAMPLES + c * ITEM;                // first sample of the item
             if (ra < 0) {
-              w[j] = *reinterpret_cast<const uint4 *>((const char *)P.tail + ((size_t)stream * kTcTailSamples +
-                                                                             (n0 + kTcTailSamples)) * BPS);
+              w[j] = *reinterpret_cast<const uint4 *>((const char *)P.tail + ((size_t)stream * GEO::TAIL + (n0 + GEO::TAIL)) * BPS);
 #ifdef LTB_TC_NO_TMA
             } else {
 #else
@@ -557,19 +586,20 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
   if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-// keep the last 768 raw samples of each stream for the next call (the three halo rows of its first tile)
-template <int FMT>
+// keep the last three rows (48 D raw samples) of each stream for the next call (the halo rows of its first tile)
+template <int FMT, int D>
 __global__ void __launch_bounds__(256) tc_tail_kernel(const void *__restrict__ in, long long stride_bytes, int n_in,
                                                       const void *__restrict__ tail_old, void *__restrict__ tail_new) {
   typedef typename std::conditional<FMT == LTB_FMT_FC32, unsigned long long,
                                     typename std::conditional<FMT == LTB_FMT_SC16, unsigned, unsigned short>::type>::type raw_t;   // one complex sample
+  constexpr int TAIL = TcGeom<FMT, D>::TAIL;
   const int stream = blockIdx.x;
   const raw_t *src = reinterpret_cast<const raw_t *>((const char *)in + (long long)stream * stride_bytes);
-  const raw_t *told = reinterpret_cast<const raw_t *>(tail_old) + (size_t)stream * kTcTailSamples;
-  raw_t *tnew = reinterpret_cast<raw_t *>(tail_new) + (size_t)stream * kTcTailSamples;
-  for (int i = threadIdx.x; i < kTcTailSamples; i += blockDim.x) {
-    const int idx = n_in - kTcTailSamples + i;
-    tnew[i] = idx >= 0 ? src[idx] : told[kTcTailSamples + idx];
+  const raw_t *told = reinterpret_cast<const raw_t *>(tail_old) + (size_t)stream * TAIL;
+  raw_t *tnew = reinterpret_cast<raw_t *>(tail_new) + (size_t)stream * TAIL;
+  for (int i = threadIdx.x; i < TAIL; i += blockDim.x) {
+    const int idx = n_in - TAIL + i;
+    tnew[i] = idx >= 0 ? src[idx] : told[TAIL + idx];
   }
 }
 

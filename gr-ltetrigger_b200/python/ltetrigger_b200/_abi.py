@@ -65,7 +65,7 @@ SYMBOLS = [
     "ltb_trigger_collect", "ltb_trigger_get_stats", "ltb_trigger_fetch_halfframes",
     "ltb_trigger_last_timing", "ltb_trigger_last_kernel_times", "ltb_last_error", "ltb_version", "ltb_device_count",
     "ltb_sss_create", "ltb_sss_destroy", "ltb_sss_set_frame_type", "ltb_sss_work", "ltb_mib_decode",
-    "ltb_kernel_pss_corr_host", "ltb_kernel_pss_corr_fft_host", "ltb_kernel_decimate_host", "ltb_kernel_decimate_tc_host", "ltb_kernel_decimate_tc_host2",
+    "ltb_kernel_pss_corr_host", "ltb_kernel_pss_corr_fft_host", "ltb_kernel_decimate_host", "ltb_kernel_decimate_tc_host",
     "ltb_table_pss_taps", "ltb_table_decim_taps", "ltb_table_sss", "ltb_table_cexp",
     "ltb_table_fft128_twiddles", "ltb_table_fft1024_twiddles", "ltb_table_os_filter", "ltb_table_tc_btab",
 ]
@@ -123,10 +123,9 @@ def _load(path):
     L.ltb_kernel_pss_corr_fft_host.argtypes = [C.c_int, vp, C.c_int, C.c_int64, vp]
     L.ltb_table_fft1024_twiddles.argtypes = [fp, fp]
     L.ltb_table_os_filter.argtypes = [C.c_int, fp, fp]
-    L.ltb_table_tc_btab.argtypes = [C.c_int, vp, vp]
+    L.ltb_table_tc_btab.argtypes = [C.c_int, C.c_int, vp, vp]
     L.ltb_kernel_decimate_host.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int, vp]
-    L.ltb_kernel_decimate_tc_host.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, vp]
-    L.ltb_kernel_decimate_tc_host2.argtypes = [C.c_int, vp, C.c_int, C.c_float, C.c_int, C.c_int64, C.c_int64, vp]
+    L.ltb_kernel_decimate_tc_host.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int64, C.c_int64, vp]
     L.ltb_table_pss_taps.argtypes = [C.c_int, fp, fp]
     L.ltb_table_decim_taps.argtypes = [C.c_int, fp, C.c_int]
     L.ltb_table_sss.argtypes = [C.c_int, ip, ip, ip, ip, ip]

@@ -161,17 +161,17 @@ def kernel_decimate(x, decim, fmt=A.FMT_FC32, device=0, L=None):
     return y
 
 
-def kernel_decimate_tc(iq, chunk=None, device=0, full_scale=0.0):
+def kernel_decimate_tc(iq, chunk=None, device=0, full_scale=0.0, decim=16):
     """LTB_FRONTEND_TC_INT at kernel level: iq [n_streams, n, 2] int16 (sc16) or int8 (sc8), or [n_streams, n]
-    complex64 taken as 23-bit fixed point over +-full_scale -> [n_streams, n // 16] complex64, the input fed in
-    calls of `chunk` samples (multiple of 128; default: one call)."""
+    complex64 taken as 23-bit fixed point over +-full_scale -> [n_streams, n // decim] complex64, the input fed in
+    calls of `chunk` samples (multiple of 8 decim; default: one call)."""
     iq = np.asarray(iq)
     fmt = A.FMT_SC8 if iq.dtype == np.int8 else A.FMT_SC16 if iq.dtype == np.int16 else A.FMT_FC32
     iq = np.ascontiguousarray(iq, A.FMT_DTYPE[fmt])
     s, n = iq.shape[0], iq.shape[1]
-    y = np.zeros((s, n // 16), np.complex64)
-    A.check(A.lib().ltb_kernel_decimate_tc_host2(device, iq.ctypes.data, fmt, full_scale, s, n, chunk or n, y.ctypes.data),
-            "ltb_kernel_decimate_tc_host2")
+    y = np.zeros((s, n // decim), np.complex64)
+    A.check(A.lib().ltb_kernel_decimate_tc_host(device, iq.ctypes.data, fmt, decim, full_scale, s, n, chunk or n, y.ctypes.data),
+            "ltb_kernel_decimate_tc_host")
     return y
 
 
@@ -218,11 +218,11 @@ class tables:
         return r, i
 
     @staticmethod
-    def tc_btab(fmt):
+    def tc_btab(fmt, decim=16):
         """Tap table of the tensor-core front end, un-swizzled: ([208, 128] int8, sum of the integer taps)."""
         raw = np.zeros(208 * 128, np.int8)
         sum_t = C.c_int64(0)
-        A.check(A.lib().ltb_table_tc_btab(fmt, raw.ctypes.data, C.addressof(sum_t)), "ltb_table_tc_btab")
+        A.check(A.lib().ltb_table_tc_btab(fmt, decim, raw.ctypes.data, C.addressof(sum_t)), "ltb_table_tc_btab")
         raw = raw.reshape(208, 8, 16)
         out = np.zeros_like(raw)
         for r in range(208):

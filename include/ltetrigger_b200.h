@@ -62,7 +62,9 @@ extern "C" {
 #define LTB_FRONTEND_TC_INT 1      /* exact integer arithmetic on the tensor cores (tcgen05.mma kind::i8): taps
                                       quantised to three balanced base-256 digits, the int16 / int8 samples are
                                       their own digits, int32 accumulation in TMEM, one rounding to float32 per
-                                      output.  decim = 16 only; needs 16-byte aligned rows.  fc32 input is first
+                                      output.  decim 2 / 4 / 8 / 12 / 16 for fc32, 4 / 8 / 12 / 16 for sc16, 8 / 16 for
+                                      sc8 (the LTE sampling rates; a 16-output row must be whole 256-byte pieces);
+                                      needs 16-byte aligned rows.  fc32 input is first
                                       put on a 23-bit fixed-point grid over +-fc32_full_scale (what a float sample
                                       of an ADC-fed source carries anyway); from there on the same exact integers */
 
@@ -253,14 +255,12 @@ LTB_API int ltb_kernel_pss_corr_fft_host(int device, const ltb_cf *x, int n_stre
 LTB_API int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_streams, int64_t n_in,
                                      int decim, ltb_cf *y);
 
-/* LTB_FRONTEND_TC_INT at kernel level: decimate-by-16 of n_streams host streams of n_in interleaved int16
- * (fmt LTB_FMT_SC16) or int8 (LTB_FMT_SC8) I/Q samples, fed to the tensor-core kernel in calls of `chunk`
- * samples (both multiples of 128; the raw history is carried between the calls as the engine does);
- * y: [n_streams][n_in / 16]. */
-LTB_API int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int n_streams, int64_t n_in, int64_t chunk, ltb_cf *y);
-/* the same with the fc32 variant available: fmt LTB_FMT_FC32 takes float I/Q as 23-bit fixed point over +-full_scale */
-LTB_API int ltb_kernel_decimate_tc_host2(int device, const void *x, int fmt, float full_scale, int n_streams, int64_t n_in,
-                                         int64_t chunk, ltb_cf *y);
+/* LTB_FRONTEND_TC_INT at kernel level: decimate-by-`decim` of n_streams host streams of n_in interleaved int16
+ * (fmt LTB_FMT_SC16: decim 4, 8, 12, 16), int8 (LTB_FMT_SC8: 8, 16) or float (LTB_FMT_FC32: 2, 4, 8, 12, 16; taken as
+ * 23-bit fixed point over +-full_scale) I/Q samples, fed to the tensor-core kernel in calls of `chunk` samples (both
+ * multiples of 8 decim; the raw history is carried between the calls as the engine does); y: [n_streams][n_in / decim]. */
+LTB_API int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int decim, float full_scale, int n_streams,
+                                        int64_t n_in, int64_t chunk, ltb_cf *y);
 
 #ifdef LTB_DEBUG
 /* Only in the debug build (make -C gr-ltetrigger_b200 debug -> lib/libltetrigger_b200_debug.so, -DLTB_DEBUG);
@@ -284,10 +284,11 @@ LTB_API int ltb_table_fft128_twiddles(float w_re[64], float w_im[64]);
 /* LTB_CORR_FFT: W_1024^i and the filter spectrum 2^-10 DFT_1024(h) of one N_id_2, natural order */
 LTB_API int ltb_table_fft1024_twiddles(float w_re[1024], float w_im[1024]);
 LTB_API int ltb_table_os_filter(int n_id_2, float H_re[1024], float H_im[1024]);
-/* LTB_FRONTEND_TC_INT: the tap table of the tensor-core kernel for input format fmt, in its shared-memory image
+/* LTB_FRONTEND_TC_INT: the tap table of the tensor-core kernel for input format fmt at rate decim, in its shared-memory image
  * ([208 rows][128 bytes], K-major, 128-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)), and the sum
- * of the 525 integer taps T[j] = rint(taps[j] * 2^27).  tests/test_tc_formulation.py replays the kernel's k-steps from it. */
-LTB_API int ltb_table_tc_btab(int fmt, int8_t tab[208 * 128], int64_t *sum_t);
+ * of the integer taps T[j] = rint(taps[j] * 2^(23 + floor(log2 decim))).  tests/test_tc_formulation.py replays the kernel's
+ * k-steps from it. */
+LTB_API int ltb_table_tc_btab(int fmt, int decim, int8_t tab[208 * 128], int64_t *sum_t);
 
 #ifdef __cplusplus
 }

@@ -44,19 +44,26 @@ static uint32_t tcq_fc32(float x, float q_inv)
   return b & 0x7fffffu;
 }
 
+static int tcint_shift(int decim) { int l = 0; while (decim > 1) { decim >>= 1; l++; } return 23 + l; }   /* 27 at decim 16 */
+
 int64_t orc_decimate_tcint_fc32(const orc_cf *x, int64_t n_in, float full_scale, orc_cf *y)
 {
-  const int decim = 16;
+  return orc_decimate_tcint_fc32_d(x, n_in, 16, full_scale, y);
+}
+
+int64_t orc_decimate_tcint_fc32_d(const orc_cf *x, int64_t n_in, int decim, float full_scale, orc_cf *y)
+{
   float taps[4096];
   int ntaps = orc_decim_taps(decim, taps, 4096);
-  if (ntaps != 525 || !(full_scale > 0.0f)) return -1;
+  if (ntaps <= 0 || ntaps > 528 || !(full_scale > 0.0f)) return -1;
   int32_t T[528], D0[528];
+  const int shift = tcint_shift(decim);
   for (int j = 0; j < ntaps; j++) {
-    T[j] = (int32_t)llrint((double)taps[j] * 134217728.0);
+    T[j] = (int32_t)llrint(ldexp((double)taps[j], shift));
     D0[j] = ((T[j] + 128) & 255) - 128;      /* lowest balanced base-256 digit */
   }
   const float q_inv = (float)(0.5 / (double)full_scale);
-  const float out_scale = (float)((double)full_scale / 4194303.0 / 524288.0);
+  const float out_scale = (float)((double)full_scale / 4194303.0 * ldexp(1.0, 8 - shift));
   int32_t *m = malloc(sizeof(int32_t) * 2 * (size_t)n_in);
   for (int64_t i = 0; i < n_in; i++) { m[2 * i] = (int32_t)tcq_fc32(x[i].re, q_inv); m[2 * i + 1] = (int32_t)tcq_fc32(x[i].im, q_inv); }
   int64_t n_out = (n_in + decim - 1) / decim;
@@ -316,14 +323,15 @@ int64_t orc_decimate_fast(const orc_cf *x, int64_t n_in, int decim, orc_cf *y)
  *   y[k] = (float)A[k] * 2^-42             one rounding (2^-27 for the taps, 2^-15 for the sc16 scale)
  * Exact arithmetic does not depend on evaluation order, so any correct integer evaluation -- this loop, or
  * int8 digit products accumulated in int32 and recombined -- gives the same bits. */
-static int64_t tcint_run(const int16_t *iq16, const int8_t *iq8, int64_t n_in, float scale, orc_cf *y)
+static int64_t tcint_run(const int16_t *iq16, const int8_t *iq8, int64_t n_in, int decim, orc_cf *y)
 {
-  const int decim = 16;
   float taps[4096];
   int ntaps = orc_decim_taps(decim, taps, 4096);
-  if (ntaps != 525) return -1;
+  if (ntaps <= 0 || ntaps > 528) return -1;
   int32_t T[528];
-  for (int j = 0; j < ntaps; j++) T[j] = (int32_t)llrint((double)taps[j] * 134217728.0);
+  const int shift = tcint_shift(decim);
+  for (int j = 0; j < ntaps; j++) T[j] = (int32_t)llrint(ldexp((double)taps[j], shift));
+  const float scale = (float)ldexp(1.0, -(shift + (iq16 ? 15 : 7)));
   int64_t n_out = (n_in + decim - 1) / decim;
   for (int64_t k = 0; k < n_out; k++) {
     int64_t are = 0, aim = 0;
@@ -342,16 +350,13 @@ static int64_t tcint_run(const int16_t *iq16, const int8_t *iq8, int64_t n_in, f
   return n_out;
 }
 
-int64_t orc_decimate_tcint_sc16(const int16_t *iq, int64_t n_in, orc_cf *y)
-{
-  return tcint_run(iq, NULL, n_in, 2.2737367544323206e-13f /* 2^-42 */, y);
-}
+int64_t orc_decimate_tcint_sc16(const int16_t *iq, int64_t n_in, orc_cf *y) { return tcint_run(iq, NULL, n_in, 16, y); }
+/* other rates: taps scaled by 2^(23 + floor(log2 decim)) (|T| < 2^23 at every rate), y = (float)A * 2^-(shift + 15) */
+int64_t orc_decimate_tcint_sc16_d(const int16_t *iq, int64_t n_in, int decim, orc_cf *y) { return tcint_run(iq, NULL, n_in, decim, y); }
 
 /* the same for int8 I/Q: y[k] = (float)A[k] * 2^-34 (2^-27 for the taps, 2^-7 for the sc8 scale) */
-int64_t orc_decimate_tcint_sc8(const int8_t *iq, int64_t n_in, orc_cf *y)
-{
-  return tcint_run(NULL, iq, n_in, 5.8207660913467407e-11f /* 2^-34 */, y);
-}
+int64_t orc_decimate_tcint_sc8(const int8_t *iq, int64_t n_in, orc_cf *y) { return tcint_run(NULL, iq, n_in, 16, y); }
+int64_t orc_decimate_tcint_sc8_d(const int8_t *iq, int64_t n_in, int decim, orc_cf *y) { return tcint_run(NULL, iq, n_in, decim, y); }
 
 /* ------------------------------------------------------------------------- */
 /* PSS matched filter                                                         */
@@ -1236,11 +1241,11 @@ typedef struct {
 static void trig_frontend(int s, void *arg)
 {
   trig_t *t = (trig_t *)arg;
-  if ((t->conv_mode & ORC_FRONT_TCINT) && t->decim == 16 && (t->fmt != 0 || t->full_scale > 0.0f)) {   /* integer front end */
+  if ((t->conv_mode & ORC_FRONT_TCINT) && t->decim > 1 && (t->fmt != 0 || t->full_scale > 0.0f)) {   /* integer front end */
     t->ys[s] = malloc(sizeof(orc_cf) * t->n_out);
-    int64_t rc = t->fmt == 0 ? orc_decimate_tcint_fc32((const orc_cf *)t->iq + (size_t)s * t->n_in, t->n_in, t->full_scale, t->ys[s])
-               : t->fmt == 1 ? orc_decimate_tcint_sc16((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->ys[s])
-                             : orc_decimate_tcint_sc8((const int8_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->ys[s]);
+    int64_t rc = t->fmt == 0 ? orc_decimate_tcint_fc32_d((const orc_cf *)t->iq + (size_t)s * t->n_in, t->n_in, t->decim, t->full_scale, t->ys[s])
+               : t->fmt == 1 ? orc_decimate_tcint_sc16_d((const int16_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->decim, t->ys[s])
+                             : orc_decimate_tcint_sc8_d((const int8_t *)t->iq + (size_t)s * t->n_in * 2, t->n_in, t->decim, t->ys[s]);
     if (rc < 0) t->fail = 1;
     return;
   }

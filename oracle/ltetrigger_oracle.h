@@ -151,6 +151,10 @@ int64_t orc_decimate_tcint_sc16(const int16_t *iq, int64_t n_in, orc_cf *y);
 int64_t orc_decimate_tcint_sc8(const int8_t *iq, int64_t n_in, orc_cf *y);
 /* fc32 input taken as 23-bit fixed point over +-full_scale, then the same exact integers (see the .c file) */
 int64_t orc_decimate_tcint_fc32(const orc_cf *x, int64_t n_in, float full_scale, orc_cf *y);
+/* the same at the other rates the product's kernel has (decim 2 .. 16): taps scaled by 2^(23 + floor(log2 decim)) */
+int64_t orc_decimate_tcint_sc16_d(const int16_t *iq, int64_t n_in, int decim, orc_cf *y);
+int64_t orc_decimate_tcint_sc8_d(const int8_t *iq, int64_t n_in, int decim, orc_cf *y);
+int64_t orc_decimate_tcint_fc32_d(const orc_cf *x, int64_t n_in, int decim, float full_scale, orc_cf *y);
 
 /* ---- whole chains ------------------------------------------------------------ */
 /* pss(N_id_2) -> sss(N_id_2) over one search-rate stream y[0..n) (GR zero history before it),

@@ -65,6 +65,12 @@ def lib():
         L.orc_decimate_tcint_sc8.restype = C.c_int64
         L.orc_decimate_tcint_fc32.argtypes = [vp, C.c_int64, C.c_float, vp]
         L.orc_decimate_tcint_fc32.restype = C.c_int64
+        L.orc_decimate_tcint_sc16_d.argtypes = [vp, C.c_int64, C.c_int, vp]
+        L.orc_decimate_tcint_sc16_d.restype = C.c_int64
+        L.orc_decimate_tcint_sc8_d.argtypes = [vp, C.c_int64, C.c_int, vp]
+        L.orc_decimate_tcint_sc8_d.restype = C.c_int64
+        L.orc_decimate_tcint_fc32_d.argtypes = [vp, C.c_int64, C.c_int, C.c_float, vp]
+        L.orc_decimate_tcint_fc32_d.restype = C.c_int64
         L.orc_trigger_run2.argtypes = [vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                        C.c_int, C.c_float, C.c_int, vp, C.c_int]
         L.orc_trigger_run2.restype = C.c_int
@@ -151,32 +157,32 @@ def decimate(x, decim):
     return y
 
 
-def decimate_tcint_sc16(iq):
-    """LTB_FRONTEND_TC_INT restated: exact integer decimate-by-16 of [n, 2] int16 I/Q -> complex64."""
+def decimate_tcint_sc16(iq, decim=16):
+    """LTB_FRONTEND_TC_INT restated: exact integer decimate-by-`decim` of [n, 2] int16 I/Q -> complex64."""
     iq = np.ascontiguousarray(iq, np.int16)
     n = iq.shape[0]
-    y = np.zeros((n + 15) // 16, np.complex64)
-    if lib().orc_decimate_tcint_sc16(iq.ctypes.data, n, y.ctypes.data) < 0:
+    y = np.zeros((n + decim - 1) // decim, np.complex64)
+    if lib().orc_decimate_tcint_sc16_d(iq.ctypes.data, n, decim, y.ctypes.data) < 0:
         raise RuntimeError("orc_decimate_tcint_sc16 failed")
     return y
 
 
-def decimate_tcint_sc8(iq):
+def decimate_tcint_sc8(iq, decim=16):
     """The same for [n, 2] int8 I/Q."""
     iq = np.ascontiguousarray(iq, np.int8)
     n = iq.shape[0]
-    y = np.zeros((n + 15) // 16, np.complex64)
-    if lib().orc_decimate_tcint_sc8(iq.ctypes.data, n, y.ctypes.data) < 0:
+    y = np.zeros((n + decim - 1) // decim, np.complex64)
+    if lib().orc_decimate_tcint_sc8_d(iq.ctypes.data, n, decim, y.ctypes.data) < 0:
         raise RuntimeError("orc_decimate_tcint_sc8 failed")
     return y
 
 
-def decimate_tcint_fc32(x, full_scale):
+def decimate_tcint_fc32(x, full_scale, decim=16):
     """The same for complex64 input taken as 23-bit fixed point over +-full_scale."""
     x = np.ascontiguousarray(x, np.complex64)
     n = x.shape[0]
-    y = np.zeros((n + 15) // 16, np.complex64)
-    if lib().orc_decimate_tcint_fc32(x.ctypes.data, n, float(full_scale), y.ctypes.data) < 0:
+    y = np.zeros((n + decim - 1) // decim, np.complex64)
+    if lib().orc_decimate_tcint_fc32_d(x.ctypes.data, n, decim, float(full_scale), y.ctypes.data) < 0:
         raise RuntimeError("orc_decimate_tcint_fc32 failed")
     return y
 

@@ -149,10 +149,71 @@ def test_tc_front_end_fc32_through_the_engine(lt, oracle, corr):
     np.testing.assert_allclose(got["peak_value"][sel], fp["peak_value"][sel], rtol=1e-4)
 
 
+@pytest.mark.parametrize("fmt,decim", [("fc32", 2), ("fc32", 4), ("fc32", 8), ("fc32", 12), ("sc16", 4), ("sc16", 8), ("sc16", 12), ("sc8", 8)])
+@pytest.mark.parametrize("n_out,chunk_outs", [(976 * 2 + 40, None), (9000, 8 * 37), (9000, 8 * 1), (61 * 16 * 3 + 8, 8 * 250)])
+def test_tc_decimator_other_rates_bit_exact(lt, oracle, fmt, decim, n_out, chunk_outs):
+    """The LTE sampling rates below 30.72 Msps (decimation 2, 4, 8, 12): the same kernel with 16 D samples per row, its
+    k-steps meeting one, two or three tap tables (the phase of a k-step's first sample within an output); random and
+    extreme streams in ragged chunks, every output equal to the oracle's int64 evaluation."""
+    rng = np.random.default_rng(n_out + decim)
+    n = n_out * decim
+    chunk = None if chunk_outs is None else chunk_outs * decim
+    if fmt == "fc32":
+        fs = 3.0
+        x = (rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))).astype(np.complex64) * np.float32(0.6)
+        x[1] = fs * (1 - 1j)
+        x[2, ::7] = 10 * fs
+        got = lt.kernel_decimate_tc(x, chunk=chunk, full_scale=fs, decim=decim)
+        ref = lambda v: oracle.decimate_tcint_fc32(v, fs, decim)
+    else:
+        lo, hi, dt = (-32768, 32767, np.int16) if fmt == "sc16" else (-128, 127, np.int8)
+        x = rng.integers(lo, hi + 1, size=(3, n, 2)).astype(dt)
+        x[1, :, :] = hi
+        x[2, :, 0] = lo
+        got = lt.kernel_decimate_tc(x, chunk=chunk, decim=decim)
+        ref = (lambda v: oracle.decimate_tcint_sc16(v, decim)) if fmt == "sc16" else (lambda v: oracle.decimate_tcint_sc8(v, decim))
+    for s in range(3):
+        want = ref(x[s])
+        assert np.array_equal(_bits(got[s]), _bits(want)), (s, int(np.argmax(_bits(got[s]) != _bits(want))))
+
+
+@pytest.mark.parametrize("name,fmt", [("50prb", "sc16"), ("25prb", "fc32"), ("50prb", "sc8"), ("25prb", "sc16")])
+def test_tc_front_end_other_rates_through_the_engine(lt, oracle, name, fmt):
+    """The 50 PRB (15.36 Msps, D = 8) and 25 PRB (7.68 Msps, D = 4) fixtures through the whole chain with the integer front
+    end: records bit-identical to the oracle in the same mode, the reference's cell id, the same decisions as the float32
+    front end."""
+    from ltetrigger_b200 import synth
+    x, decim, cell_id = load_fixture(name, 0.25)
+    n = len(x) // (8 * decim) * (8 * decim)
+    x = x[:n]
+    code = {"fc32": lt.FMT_FC32, "sc16": lt.FMT_SC16, "sc8": lt.FMT_SC8}[fmt]
+    iq = x[None] if fmt == "fc32" else synth.to_sc16(x[None]) if fmt == "sc16" else synth.to_sc8(x[None])
+    fs = float(8 * np.sqrt(np.mean(np.abs(x) ** 2))) if fmt == "fc32" else 0.0
+    chunk = decim * 8 * 3001
+    trig = lt.Trigger(n_streams=1, decim=decim, max_chunk=chunk, input_format=code, corr_mode=lt.CORR_FFT,
+                      frontend_mode=lt.FRONTEND_TC_INT, fc32_full_scale=fs)
+    got = trig.run(iq, chunk=chunk)
+    trig.close()
+    want = oracle.trigger_run(iq, decim=decim, fmt=code, conv_mode=oracle.CONV_OS | oracle.FRONT_TCINT, fc32_full_scale=fs)
+    assert_recs_equal(got, want)
+    cells = got[(got["flags"] & lt.F_CELL) != 0]
+    assert set(cells["cell_id"].tolist()) == {cell_id}
+    ref = lt.Trigger(n_streams=1, decim=decim, max_chunk=chunk, input_format=code, corr_mode=lt.CORR_FFT)
+    fp = ref.run(iq, chunk=chunk)
+    ref.close()
+    for f in ("win_start", "emit_start", "flags", "m0", "m1", "n_id_1", "cell_id"):
+        assert (got[f] == fp[f]).all(), f
+    over = (got["flags"] & lt.F_OVER) != 0
+    assert (got["peak_pos"][over] == fp["peak_pos"][over]).all()
+    np.testing.assert_allclose(got["psr"][over], fp["psr"][over], rtol=1e-4)
+
+
 def test_tc_front_end_argument_checks(lt):
     with pytest.raises(lt.LtbError):
         lt.Trigger(n_streams=1, decim=16, input_format=lt.FMT_FC32, frontend_mode=lt.FRONTEND_TC_INT)   # fc32 needs its range
     with pytest.raises(lt.LtbError):
         lt.Trigger(n_streams=1, decim=16, input_format=lt.FMT_FC32, frontend_mode=lt.FRONTEND_TC_INT, fc32_full_scale=-1.0)
     with pytest.raises(lt.LtbError):
-        lt.Trigger(n_streams=1, decim=8, input_format=lt.FMT_SC16, frontend_mode=lt.FRONTEND_TC_INT)    # decim 16 only
+        lt.Trigger(n_streams=1, decim=2, input_format=lt.FMT_SC16, frontend_mode=lt.FRONTEND_TC_INT)    # a 16-output row would be 128 bytes
+    with pytest.raises(lt.LtbError):
+        lt.Trigger(n_streams=1, decim=5, input_format=lt.FMT_FC32, frontend_mode=lt.FRONTEND_TC_INT, fc32_full_scale=1.0)
