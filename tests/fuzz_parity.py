@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Randomised parity campaign (a script, not a pytest module): seeded random engine configurations --
-rate, wire format, correlator, frame type, stream count, chunking, threshold, tracking parameters,
+rate, wire format, front end (canonical FP32 or, where it exists, the integer tensor-core one with a random
+fixed-point range for fc32), correlator, frame type, stream count, chunking, threshold, tracking parameters,
 SNR, CP type, carrier offset -- each run through the C ABI in ragged chunks and compared record for
 record, bit for bit, with the CPU oracle.  Prints one line per case and exits non-zero on the first
 mismatch with the configuration that produced it.
@@ -56,8 +57,13 @@ def campaign(seconds, seed, max_cases=100000, log=print):
         n = n_search * decim
         step = 8 * decim
         chunk = int(rng.integers(20, 6000)) * step
+        # the integer tensor-core front end where the kernel exists (half of those cases); fc32 gets a declared range
+        # between 3 x and 40 x the signal's rms, so some cases clip and others use few of the grid's bits
+        tc_ok = decim in {0: (2, 4, 8, 12, 16), 1: (4, 8, 12, 16), 2: (8, 16)}[fmt]
+        tc = bool(tc_ok and rng.integers(0, 2))
+        fs = float(rng.uniform(3.0, 40.0)) if (tc and fmt == 0) else 0.0
         cfg = dict(decim=decim, fmt=fmt, corr=corr, tdd=tdd, n_streams=n_streams, thr=thr, track_after=track_after,
-                   track_every=track_every, n=n, chunk=chunk)
+                   track_every=track_every, n=n, chunk=chunk, tc=tc, fs=fs)
         rows = []
         for s in range(n_streams):
             kind = rng.integers(0, 6)
@@ -73,11 +79,12 @@ def campaign(seconds, seed, max_cases=100000, log=print):
             rows.append(x)
         x = np.stack(rows)
         iq = x if fmt == 0 else (synth.to_sc16(x) if fmt == 1 else synth.to_sc8(x))
-        conv = (O.CONV_OS if corr else O.CONV_DIRECT) | (O.FRAME_TDD if tdd else 0)
+        conv = (O.CONV_OS if corr else O.CONV_DIRECT) | (O.FRAME_TDD if tdd else 0) | (O.FRONT_TCINT if tc else 0)
         want = O.trigger_run(iq, decim=decim, fmt=fmt, psr_threshold=thr, track_after=track_after, track_every=track_every,
-                             conv_mode=conv)
+                             conv_mode=conv, fc32_full_scale=fs)
         trig = lt.Trigger(n_streams=n_streams, decim=decim, psr_threshold=thr, max_chunk=chunk, input_format=fmt,
-                          track_after=track_after, track_every=track_every, corr_mode=corr, frame_type=tdd)
+                          track_after=track_after, track_every=track_every, corr_mode=corr, frame_type=tdd,
+                          frontend_mode=lt.FRONTEND_TC_INT if tc else lt.FRONTEND_FP32, fc32_full_scale=fs)
         got = trig.run(iq, chunk=chunk)
         trig.close()
         try:
@@ -87,8 +94,9 @@ def campaign(seconds, seed, max_cases=100000, log=print):
             return n_cases, (cfg, str(e))
         n_cases += 1
         cells = int(((got["flags"] & lt.F_CELL) != 0).sum())
-        log("ok %4d D=%-2d fmt=%d corr=%d tdd=%d S=%d thr=%.1f ta=%d te=%d chunk=%d recs=%d tagged=%d" % (
-            n_cases, decim, fmt, corr, tdd, n_streams, thr, track_after, track_every, chunk, len(got), cells))
+        log("ok %4d D=%-2d fmt=%d fe=%s corr=%d tdd=%d S=%d thr=%.1f ta=%d te=%d chunk=%d recs=%d tagged=%d" % (
+            n_cases, decim, fmt, ("tc(%.1f)" % fs if fmt == 0 else "tc") if tc else "fp32", corr, tdd, n_streams, thr, track_after,
+            track_every, chunk, len(got), cells))
     return n_cases, None
 
 
