@@ -89,10 +89,12 @@ def test_fuzz_parity_60s(lt):
     assert n_cases >= 20, n_cases
 
 
-def test_c5_shard_one_call_512_streams_vs_oracle(lt, oracle):
+@pytest.mark.parametrize("frontend", ["fp32", "tc"])
+def test_c5_shard_one_call_512_streams_vs_oracle(lt, oracle, frontend):
     """One bench-sized call -- 512 streams x 100 ms x 30.72 Msps fc32, decimate by 16, FFT correlator,
-    fed from device memory like bench.py -- with ALL records compared with the oracle (run on the host
-    in four groups of 128 streams to bound host memory)."""
+    fed from device memory like bench.py, with the canonical FP32 front end and with the integer tensor-core
+    one (fc32 as fixed point over +-8, bench.py's setting) -- with ALL records compared with the oracle in the
+    same mode (run on the host in four groups of 128 streams to bound host memory)."""
     import torch
     S, decim, n, U = 512, 16, 16 * 192000, 8
     from ltetrigger_b200 import synth
@@ -111,7 +113,9 @@ def test_c5_shard_one_call_512_streams_vs_oracle(lt, oracle):
         x[s] = torch.roll(base[s % U], int(shifts[s])) + sigma * torch.view_as_complex(noise)
     del base, noise
     torch.cuda.synchronize()
-    trig = lt.Trigger(n_streams=S, decim=decim, psr_threshold=4.0, max_chunk=n, device=0, corr_mode=lt.CORR_FFT)
+    tc = frontend == "tc"
+    trig = lt.Trigger(n_streams=S, decim=decim, psr_threshold=4.0, max_chunk=n, device=0, corr_mode=lt.CORR_FFT,
+                      frontend_mode=lt.FRONTEND_TC_INT if tc else lt.FRONTEND_FP32, fc32_full_scale=8.0 if tc else 0.0)
     got = trig.process_device_ptr(x.data_ptr(), n * 8, n).copy()
     trig.close()
     got = got[np.lexsort((got["win_index"], got["n_id_2"], got["stream"]))]
@@ -119,9 +123,10 @@ def test_c5_shard_one_call_512_streams_vs_oracle(lt, oracle):
     t0 = time.time()
     for g0 in range(0, S, 128):
         iq = x[g0:g0 + 128].cpu().numpy()
-        want = oracle.trigger_run(iq, decim=decim, psr_threshold=4.0, conv_mode=oracle.CONV_OS)
+        want = oracle.trigger_run(iq, decim=decim, psr_threshold=4.0, conv_mode=oracle.CONV_OS | (oracle.FRONT_TCINT if tc else 0),
+                                  fc32_full_scale=8.0 if tc else 0.0)
         want["stream"] += g0
         sel = got[(got["stream"] >= g0) & (got["stream"] < g0 + 128)]
         assert_recs_equal(sel, want)
-    _save("c5_shard_parity_pytest.json", {"streams": S, "records": int(len(got)), "oracle_seconds": time.time() - t0,
-                                          "bit_identical_to_oracle": True})
+    _save("c5_shard_parity_%s_pytest.json" % frontend, {"streams": S, "frontend": frontend, "records": int(len(got)),
+                                                        "oracle_seconds": time.time() - t0, "bit_identical_to_oracle": True})
