@@ -1574,13 +1574,15 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
 
   if (tid == 0) S.st = P.state[chain];
   {
-    // 39 kB of EMA state per chain: all of a thread's loads in flight at once (one round trip)
-    constexpr int kN = (kAvgLen + kTrackThreads - 1) / kTrackThreads;   // 39
-    float v[kN];
+    // 39 kB of EMA state per chain: all of a thread's loads in flight at once (one round trip), 16 bytes each
+    constexpr int kN4 = (kAvgLen / 4 + kTrackThreads - 1) / kTrackThreads;   // 10
+    static_assert(kAvgLen % 4 == 0, "EMA state moves as float4");
+    const float4 *ag4 = reinterpret_cast<const float4 *>(avg_g);
+    float4 v[kN4];
 #pragma unroll
-    for (int j = 0; j < kN; ++j) { const int k = tid + j * kTrackThreads; v[j] = k < kAvgLen ? avg_g[k] : 0.f; }
+    for (int j = 0; j < kN4; ++j) { const int g = tid + j * kTrackThreads; v[j] = g < kAvgLen / 4 ? ag4[g] : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
-    for (int j = 0; j < kN; ++j) { const int k = tid + j * kTrackThreads; if (k < kAvgLen) S.avg[k] = v[j]; }
+    for (int j = 0; j < kN4; ++j) { const int g = tid + j * kTrackThreads; if (g < kAvgLen / 4) reinterpret_cast<float4 *>(S.avg)[g] = v[j]; }
   }
   S.lead[tid] = make_float2(0.f, 0.f);
   S.trail[tid] = make_float2(0.f, 0.f);
@@ -1594,17 +1596,39 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
     __syncthreads();                                                // everyone has read S.st
     if (search) {
       // ---- srslte_pss_find_pss ------------------------------------------------
-      // the lags this thread owns (k = tid + 256 j) are requested in two batches of 19 (register
-      // budget for four CTAs per SM); the first batch is in flight during the edge computation,
-      // and both mostly hit L2 thanks to the prefetch issued at the end of the previous window
-      constexpr int kPerThread = (kNLag + kTrackThreads - 1) / kTrackThreads;   // 38
-      constexpr int kBatch = kPerThread / 2;                                    // 19
-      float a[kBatch];
+      // thread t owns the lags 4 (t + 256 j) .. + 3, j = 0..9: four consecutive lags move as one 16-byte load of the power
+      // ring (when the window start is a multiple of four samples: always for a chain that has not triggered yet) and one
+      // LDS.128 / STS.128 of the moving average.  They are requested in two batches of five (register budget for four
+      // CTAs per SM); the first batch is in flight during the edge computation, and both mostly hit L2 thanks to the
+      // prefetch issued at the end of the previous window.  Lags below 127 and from 9600 on come from the truncated
+      // window (S.edge) instead: groups 0..31 (warp 0, j = 0) and 2400..2431 (warp 3, j = 9).
+      constexpr int kGrp = (kNLag + 3) / 4;                                     // 2432 groups of four lags
+      constexpr int kPerThread = (kGrp + kTrackThreads - 1) / kTrackThreads;    // 10
+      constexpr int kBatch = kPerThread / 2;                                    // 5
+      static_assert(kPerThread == 2 * kBatch, "two equal batches");
+      const bool aligned4 = ((unsigned)R & 3u) == 0u;
+      float4 a[kBatch];
+      auto load_batch = [&](const int h) {
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) {
-        const int k = tid + j * kTrackThreads;
-        a[j] = (k >= 127 && k < kHalf) ? __ldg(&pr[(unsigned)((R + k) & P.cap_mask)]) : 0.f;
-      }
+        for (int j = 0; j < kBatch; ++j) {
+          const int k0 = 4 * (tid + (h * kBatch + j) * kTrackThreads);
+          float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k0 >= 128 && k0 < kHalf) {
+            if (aligned4) {
+              pv = __ldg(reinterpret_cast<const float4 *>(&pr[(unsigned)((R + k0) & P.cap_mask)]));
+            } else {
+              pv.x = __ldg(&pr[(unsigned)((R + k0) & P.cap_mask)]);
+              pv.y = __ldg(&pr[(unsigned)((R + k0 + 1) & P.cap_mask)]);
+              pv.z = __ldg(&pr[(unsigned)((R + k0 + 2) & P.cap_mask)]);
+              pv.w = __ldg(&pr[(unsigned)((R + k0 + 3) & P.cap_mask)]);
+            }
+          } else if (k0 == 124) {
+            pv.w = __ldg(&pr[(unsigned)((R + 127) & P.cap_mask)]);               // lag 127: the first whole one
+          }
+          a[j] = pv;
+        }
+      };
+      load_batch(0);
       if (tid < 127) {
         S.lead[128 + tid] = yr[(unsigned)((R + tid) & P.cap_mask)];
         S.trail[1 + tid] = yr[(unsigned)((R + 9473 + tid) & P.cap_mask)];
@@ -1620,23 +1644,37 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
       float best = -3.402823466e+38f; int bi = 0;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        if (h == 1) {
-#pragma unroll
-          for (int j = 0; j < kBatch; ++j) {
-            const int k = tid + (kBatch + j) * kTrackThreads;
-            a[j] = (k >= 127 && k < kHalf) ? __ldg(&pr[(unsigned)((R + k) & P.cap_mask)]) : 0.f;
-          }
-        }
+        if (h == 1) load_batch(1);
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
-          const int k = tid + (h * kBatch + j) * kTrackThreads;
-          if (k < kNLag) {
-            float av = a[j];
-            if (k < 127) av = S.edge[k];
-            else if (k >= kHalf) av = S.edge[127 + (k - kHalf)];
-            const float v = __fadd_rn(__fmul_rn(av, 0.2f), __fmul_rn(S.avg[k], 0.8f));   // EMA, alpha 0.2
-            S.avg[k] = v;
-            if (v > best) { best = v; bi = k; }
+          const int k0 = 4 * (tid + (h * kBatch + j) * kTrackThreads);
+          if (k0 < kNLag) {
+            float4 av = a[j];
+            if (k0 < 128) {                                          // leading edge: lags k0 .. k0 + 3 < 127 (127 itself is whole)
+              av.x = S.edge[k0]; av.y = S.edge[k0 + 1]; av.z = S.edge[k0 + 2];
+              if (k0 + 3 < 127) av.w = S.edge[k0 + 3];
+            } else if (k0 >= kHalf) {                                // trailing edge: lags 9600 .. 9725
+              av.x = S.edge[127 + (k0 - kHalf)]; av.y = S.edge[128 + (k0 - kHalf)];
+              if (k0 + 3 < kNLag) { av.z = S.edge[129 + (k0 - kHalf)]; av.w = S.edge[130 + (k0 - kHalf)]; }
+            }
+            float4 *slot = reinterpret_cast<float4 *>(&S.avg[k0]);
+            const float4 o = *slot;
+            float4 v;                                                // EMA, alpha 0.2
+            v.x = __fadd_rn(__fmul_rn(av.x, 0.2f), __fmul_rn(o.x, 0.8f));
+            v.y = __fadd_rn(__fmul_rn(av.y, 0.2f), __fmul_rn(o.y, 0.8f));
+            v.z = __fadd_rn(__fmul_rn(av.z, 0.2f), __fmul_rn(o.z, 0.8f));
+            v.w = __fadd_rn(__fmul_rn(av.w, 0.2f), __fmul_rn(o.w, 0.8f));
+            if (k0 + 3 < kNLag) {
+              *slot = v;
+              if (v.x > best) { best = v.x; bi = k0; }
+              if (v.y > best) { best = v.y; bi = k0 + 1; }
+              if (v.z > best) { best = v.z; bi = k0 + 2; }
+              if (v.w > best) { best = v.w; bi = k0 + 3; }
+            } else {                                                 // the last group: lags 9724, 9725 only
+              S.avg[k0] = v.x; S.avg[k0 + 1] = v.y;
+              if (v.x > best) { best = v.x; bi = k0; }
+              if (v.y > best) { best = v.y; bi = k0 + 1; }
+            }
           }
         }
       }
@@ -1665,18 +1703,29 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
       }
       __syncthreads();
       {
+        // largest side lobe: the maximum over the lags outside [lb, ub).  Thread 0 below wants the maxima to the left
+        // and to the right separately only to take the larger (and to replace an empty side by its fall-back value), so
+        // one maximum over everything outside the main lobe serves as both
         const int lb = S.lb, ub = S.ub;
-        float lm = -3.402823466e+38f, rm = -3.402823466e+38f;
-        for (int k = tid; k < kNLag; k += kTrackThreads) {
-          const float v = S.avg[k];
-          if (k < lb) lm = fmaxf(lm, v);
-          if (k >= ub) rm = fmaxf(rm, v);
+        float om = -3.402823466e+38f;
+#pragma unroll
+        for (int j = 0; j < (kNLag + 3) / 4 / kTrackThreads + 1; ++j) {
+          const int k0 = 4 * (tid + j * kTrackThreads);
+          if (k0 < kNLag) {
+            const float4 v = *reinterpret_cast<const float4 *>(&S.avg[k0]);
+            if ((k0 + 3 < lb || k0 >= ub) && k0 + 3 < kNLag) {
+              om = fmaxf(om, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+            } else {
+              if (k0 < lb || k0 >= ub) om = fmaxf(om, v.x);
+              if (k0 + 1 < kNLag && (k0 + 1 < lb || k0 + 1 >= ub)) om = fmaxf(om, v.y);
+              if (k0 + 2 < kNLag && (k0 + 2 < lb || k0 + 2 >= ub)) om = fmaxf(om, v.z);
+              if (k0 + 3 < kNLag && (k0 + 3 < lb || k0 + 3 >= ub)) om = fmaxf(om, v.w);
+            }
+          }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          lm = fmaxf(lm, __shfl_down_sync(0xffffffffu, lm, off));
-          rm = fmaxf(rm, __shfl_down_sync(0xffffffffu, rm, off));
-        }
+        for (int off = 16; off > 0; off >>= 1) om = fmaxf(om, __shfl_down_sync(0xffffffffu, om, off));
+        const float lm = om, rm = om;
         if (lane == 0) { S.red_l[warp] = lm; S.red_r[warp] = rm; }
       }
       __syncthreads();
@@ -1760,7 +1809,7 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
       }
     }
     if (S.zero_avg) {                                               // srslte_pss_reset
-      for (int k = tid; k < kAvgLen; k += kTrackThreads) S.avg[k] = 0.f;
+      for (int g = tid; g < kAvgLen / 4; g += kTrackThreads) reinterpret_cast<float4 *>(S.avg)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (S.do_emit) {
       const long long E = S.emit_abs;
@@ -1887,7 +1936,7 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
   }
   __syncthreads();
   if (tid == 0) { P.state[chain] = S.st; P.rec_count[chain] = n_rec; }
-  for (int k = tid; k < kAvgLen; k += kTrackThreads) avg_g[k] = S.avg[k];
+  for (int g = tid; g < kAvgLen / 4; g += kTrackThreads) reinterpret_cast<float4 *>(avg_g)[g] = reinterpret_cast<const float4 *>(S.avg)[g];
   }
 }
 
