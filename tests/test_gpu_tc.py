@@ -177,6 +177,26 @@ def test_tc_decimator_other_rates_bit_exact(lt, oracle, fmt, decim, n_out, chunk
         assert np.array_equal(_bits(got[s]), _bits(want)), (s, int(np.argmax(_bits(got[s]) != _bits(want))))
 
 
+@pytest.mark.parametrize("fmt,decim", [("sc16", 16), ("fc32", 16), ("sc8", 8), ("fc32", 2), ("sc16", 12)])
+def test_tc_decimator_smallest_chunks_and_heavy_clipping(lt, oracle, fmt, decim):
+    """Calls of 8 D samples -- half a row: the tensor map covers no whole row and every row of the tile comes from the
+    carried history or sample by sample -- and, for fc32, a declared range of a third of the signal's rms (most samples
+    clip): still every output equal to the oracle's."""
+    rng = np.random.default_rng(decim)
+    n = 8 * decim * 41
+    if fmt == "fc32":
+        x = (rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))).astype(np.complex64)
+        got = lt.kernel_decimate_tc(x, chunk=8 * decim, full_scale=0.33, decim=decim)
+        want = [oracle.decimate_tcint_fc32(x[s], 0.33, decim) for s in range(2)]
+    else:
+        lo, hi, dt = (-32768, 32767, np.int16) if fmt == "sc16" else (-128, 127, np.int8)
+        x = rng.integers(lo, hi + 1, size=(2, n, 2)).astype(dt)
+        got = lt.kernel_decimate_tc(x, chunk=8 * decim, decim=decim)
+        want = [(oracle.decimate_tcint_sc16 if fmt == "sc16" else oracle.decimate_tcint_sc8)(x[s], decim) for s in range(2)]
+    for s in range(2):
+        assert np.array_equal(_bits(got[s]), _bits(want[s])), (s, int(np.argmax(_bits(got[s]) != _bits(want[s]))))
+
+
 @pytest.mark.parametrize("name,fmt", [("50prb", "sc16"), ("25prb", "fc32"), ("50prb", "sc8"), ("25prb", "sc16")])
 def test_tc_front_end_other_rates_through_the_engine(lt, oracle, name, fmt):
     """The 50 PRB (15.36 Msps, D = 8) and 25 PRB (7.68 Msps, D = 4) fixtures through the whole chain with the integer front
