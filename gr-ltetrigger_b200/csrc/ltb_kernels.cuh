@@ -1444,6 +1444,7 @@ constexpr int kNEdge = 253;            // lags 0..126 and 9600..9725 see a trunc
 // that loop).
 struct PhaseSeg { int start; unsigned bits0; int dk; int len; };
 constexpr int kMaxSeg = 64;
+constexpr int kSegPingPong = (int)0x80000000u;   // PhaseSeg::dk marker: indices alternate 0, 4096, 0, ... from the segment's start
 
 __device__ int plan_phase_scan(float &phase, bool &stable, float inc, int n, PhaseSeg *segs,
                                unsigned short *idx_out) {
@@ -1453,6 +1454,22 @@ __device__ int plan_phase_scan(float &phase, bool &stable, float inc, int n, Pha
     while (phase >= 4096.0f) phase = __fadd_rn(phase, -4096.0f);
     while (phase < 0.f) phase = __fadd_rn(phase, 4096.0f);
     if (phase != before) stable = false;
+    if (inc == 0.f && ns < kMaxSeg) {
+      // no frequency offset at all (a noiseless capture at its native rate measures exactly zero): the phase never
+      // moves, which the binade logic below would walk one sample at a time (phase 0 is in no binade) -- 960 serial
+      // steps per window on thread 0, ten times the cost of the whole search (profiles/ncu_track_c2_r02.txt)
+      segs[ns].start = i; segs[ns].bits0 = __float_as_uint(phase); segs[ns].dk = 0; segs[ns].len = n - i;
+      return ns + 1;
+    }
+    if (inc < 0.f && phase == 0.f && ns < kMaxSeg && __fadd_rn(4096.0f, inc) == 4096.0f) {
+      // an offset below zero and smaller than half an ulp of 4096 (|f| < 6e-8 cycles per sample: a noiseless capture
+      // at its native rate, e.g. the 6 PRB fixture): the recurrence ping-pongs 0 -> inc -> (+4096, rounds to) 4096 ->
+      // (-4096) 0 ..., indices 0, 4096, 0, 4096, ...; the binade logic below would take it one sample at a time
+      segs[ns].start = i; segs[ns].bits0 = 0u; segs[ns].dk = kSegPingPong; segs[ns].len = n - i;
+      phase = ((n - i) & 1) ? inc : 4096.0f;
+      stable = false;
+      return ns + 1;
+    }
     if (ns == kMaxSeg) {                           // table full (huge |inc|): finish one by one
       idx_out[i++] = (unsigned short)(unsigned)phase;
       phase = __fadd_rn(phase, inc);
@@ -1687,19 +1704,38 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
       }
       if (lane == 0) { S.red_v[warp] = best; S.red_i[warp] = bi; }
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         float bv = S.red_v[0]; int bidx = S.red_i[0];
         for (int w = 1; w < kTrackThreads / 32; ++w)
           if (S.red_v[w] > bv || (S.red_v[w] == bv && S.red_i[w] < bidx)) { bv = S.red_v[w]; bidx = S.red_i[w]; }
         const int p = bidx;
-        // main-lobe walk
+        // main-lobe walk (srslte_pss_find_pss: ub climbs from p + 1 while avg[ub + 1] <= avg[ub], lb descends from p - 1
+        // while avg[lb - 1] <= avg[lb]), 32 lags per step by the lanes of one warp: the first lane whose lag ends the walk
+        // gives the same bound as the one-by-one loop, and a plateau (silence, or a noiseless capture with empty symbols,
+        // where the loop runs over thousands of equal values) costs 1/32 of the steps
         const int conv_output_len = kNLag + 1;
         int ub = p + 1;
-        while (S.avg[ub + 1] <= S.avg[ub] && ub < conv_output_len) ub++;
-        int lb;
-        if (p > 2) { lb = p - 1; while (S.avg[lb - 1] <= S.avg[lb] && lb > 1) lb--; }
-        else lb = 0;
-        S.p = p; S.peak = S.avg[p]; S.lb = lb; S.ub = ub;
+        for (;;) {
+          const int i = ub + lane;
+          bool stop = true;                                            // beyond the array: the loop has ended before
+          if (i + 1 < kAvgLen) stop = !(S.avg[i + 1] <= S.avg[i] && i < conv_output_len);
+          const unsigned m = __ballot_sync(0xffffffffu, stop);
+          if (m) { ub += __ffs(m) - 1; break; }
+          ub += 32;
+        }
+        int lb = 0;
+        if (p > 2) {
+          lb = p - 1;
+          for (;;) {
+            const int i = lb - lane;
+            bool stop = true;
+            if (i >= 1) stop = !(S.avg[i - 1] <= S.avg[i] && i > 1);
+            const unsigned m = __ballot_sync(0xffffffffu, stop);
+            if (m) { lb -= __ffs(m) - 1; break; }
+            lb -= 32;
+          }
+        }
+        if (lane == 0) { S.p = p; S.peak = S.avg[p]; S.lb = lb; S.ub = ub; }
       }
       __syncthreads();
       {
@@ -1858,7 +1894,8 @@ __global__ void __launch_bounds__(kTrackThreads, 4) pss_track_kernel(TrackParams
           for (int sg = 0; sg < S.nseg; ++sg) {
             const PhaseSeg q = S.seg[sg];
             for (int j = tid; j < q.len; j += kTrackThreads)
-              S.ph_idx[q.start + j] = (unsigned short)(unsigned)__uint_as_float(q.bits0 + (unsigned)(j * q.dk));
+              S.ph_idx[q.start + j] = q.dk == kSegPingPong ? (unsigned short)((j & 1) ? 4096 : 0)
+                                                           : (unsigned short)(unsigned)__uint_as_float(q.bits0 + (unsigned)(j * q.dk));
           }
           __syncthreads();
           if (b == 0) {
