@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--noise-only", action="store_true",
                     help="no cell in any stream: every chain searches every window (the detector's worst case; "
                          "the default batch carries a cell per stream, so its matching chain skips 8 of 9 searches)")
+    ap.add_argument("--cfo-hz", type=float, default=0.0,
+                    help="carrier frequency offset of the synthetic streams: stream s gets cfo * (s mod 5 - 2) / 2, i.e. offsets "
+                         "between -cfo and +cfo (the tracker's CFO correction then works on non-trivial phase ramps)")
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic captures tiled over the streams")
     ap.add_argument("--e2e-streams", type=int, default=128)
     ap.add_argument("--e2e-steps", type=int, default=10)
@@ -276,7 +279,12 @@ def main():
         if a.noise_only:
             x[s] = float(np.sqrt(0.5)) * torch.view_as_complex(noise)
         else:
-            x[s] = torch.roll(base_d[s % a.unique], int(shifts[s])) + sigma * torch.view_as_complex(noise)
+            sig = torch.roll(base_d[s % a.unique], int(shifts[s]))
+            if a.cfo_hz:
+                f = a.cfo_hz * ((s % 5) - 2) / 2.0 / (SEARCH_RATE * a.decim)
+                ph = (2.0 * np.pi * f) * torch.arange(n, device=dev, dtype=torch.float64)
+                sig = sig * torch.polar(torch.ones_like(ph), ph).to(torch.complex64)
+            x[s] = sig + sigma * torch.view_as_complex(noise)
     del noise, base_d
     def quantise(xc, name):
         """fc32 -> the named wire format (full scale = 8 x the signal's rms)."""
@@ -456,7 +464,8 @@ def main():
                    "format": a.format, "frontend": frontend_text[a.frontend], "correlator": a.corr, "pipeline": a.pipeline, "segment_ms": a.segment_ms, "snr_db": a.snr_db,
                    "l2": "inputs larger than L2 (%.1f GB per step)" % (a.streams * n * bps / 1e9),
                    "input": ("noise only (no cell in any stream)" if a.noise_only else
-                             "%d seeded synthetic LTE captures tiled over the streams with per-stream timing shift + AWGN" % a.unique),
+                             "%d seeded synthetic LTE captures tiled over the streams with per-stream timing shift + AWGN%s" % (
+                                 a.unique, (", carrier offsets up to +-%.0f Hz" % a.cfo_hz) if a.cfo_hz else "")),
                    "cells_tagged_per_step": n_cells / a.steps},
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
     }
