@@ -92,6 +92,36 @@ def test_golden_traces(oracle):
         assert os_recs["peak_value"].view(np.uint32).tolist() == g["os_peak_value_bits"], name
 
 
+def test_golden_traces_integer_front_end(oracle):
+    """Committed traces of the integer front end (tests/golden/fixture_traces_tcint.json, written by
+    tests/golden/make_golden_tcint.py: 25 / 50 / 100 PRB frames as fc32-fixed-point, sc16 and sc8) still come out of the
+    oracle bit for bit, every frame yields the reference's cell id, and the decisions equal the float32 front end's."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_tcint", os.path.join(GOLDEN, "make_golden_tcint.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    with open(os.path.join(GOLDEN, "fixture_traces_tcint.json")) as f:
+        gold = json.load(f)
+    seen = 0
+    for key, iq, decim, fmt, cell_id in mg.cases():
+        recs, g = mg.trace(iq, decim, fmt), gold[key]
+        assert len(recs) == g["n_records"], key
+        for field in ("win_start", "emit_start", "flags", "peak_pos", "m0", "m1", "cell_id"):
+            assert recs[field].tolist() == g[field], (key, field)
+        for field in ("psr", "peak_value", "cfo"):
+            assert recs[field].view(np.uint32).tolist() == g[field + "_bits"], (key, field)
+        cells = recs["cell_id"][(recs["flags"] & oracle.F_CELL) != 0]
+        assert len(cells) and set(cells.tolist()) == {cell_id}, key
+        fp = oracle.trigger_run(iq, decim=decim, fmt=fmt, conv_mode=oracle.CONV_OS)
+        for field in ("win_start", "emit_start", "flags", "m0", "m1", "cell_id"):
+            assert (recs[field] == fp[field]).all(), (key, field)
+        over = (recs["flags"] & oracle.F_OVER) != 0
+        assert (recs["peak_pos"][over] == fp["peak_pos"][over]).all(), key
+        np.testing.assert_allclose(recs["psr"][over], fp["psr"][over], rtol=1e-4)
+        seen += 1
+    assert seen == 8
+
+
 def test_edge_cases(oracle):
     # shorter than the lookahead: no general_work call at all
     assert len(oracle.trigger_run(np.zeros((1, 18360), np.complex64))) == 0
