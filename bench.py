@@ -95,7 +95,7 @@ def parse():
 
 def tc_exists(fmt, decim):
     """(format, rate) pairs the tensor-core front end is built for (include/ltetrigger_b200.h LTB_FRONTEND_TC_INT)."""
-    return decim in {"fc32": (2, 4, 8, 12, 16), "sc16": (4, 8, 12, 16), "sc8": (8, 16)}[fmt]
+    return decim in {"fc32": (2, 4, 8, 12, 16, 24, 32), "sc16": (4, 8, 12, 16, 24, 32), "sc8": (8, 16, 24, 32)}[fmt]
 
 
 def workload_name(a):

@@ -317,8 +317,9 @@ TcTable g_tc_tab[64][3][LTB_MAX_DECIM + 1];      // per device, input format and
 // every supported (format, rate) pair; X(fmt, D)
 #define LTB_TC_VARIANTS(X)                                                                                    \
   X(LTB_FMT_FC32, 2) X(LTB_FMT_FC32, 4) X(LTB_FMT_FC32, 8) X(LTB_FMT_FC32, 12) X(LTB_FMT_FC32, 16)              \
-  X(LTB_FMT_SC16, 4) X(LTB_FMT_SC16, 8) X(LTB_FMT_SC16, 12) X(LTB_FMT_SC16, 16)                                \
-  X(LTB_FMT_SC8, 8) X(LTB_FMT_SC8, 16)
+  X(LTB_FMT_FC32, 24) X(LTB_FMT_FC32, 32)                                                                       \
+  X(LTB_FMT_SC16, 4) X(LTB_FMT_SC16, 8) X(LTB_FMT_SC16, 12) X(LTB_FMT_SC16, 16) X(LTB_FMT_SC16, 24) X(LTB_FMT_SC16, 32) \
+  X(LTB_FMT_SC8, 8) X(LTB_FMT_SC8, 16) X(LTB_FMT_SC8, 24) X(LTB_FMT_SC8, 32)
 
 int ensure_tc_tables(int device, int fmt, int decim) {
   std::lock_guard<std::mutex> lk(g_const_mu);
@@ -646,8 +647,8 @@ int ltb_trigger_create(const ltb_trigger_config *cfg, ltb_trigger **out) {
       (c.frontend_mode != LTB_FRONTEND_FP32 && c.frontend_mode != LTB_FRONTEND_TC_INT))
     return fail(LTB_ERROR_INVALID_INPUTS, "invalid trigger configuration");
   if (c.frontend_mode == LTB_FRONTEND_TC_INT && !tc_supported(c.input_format, c.decim))
-    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT is available at decim 2 / 4 / 8 / 12 / 16 for fc32, 4 / 8 / 12 / 16 for sc16 "
-                                          "and 8 / 16 for sc8 input (a 16-output row must be whole 256-byte pieces)");
+    return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT is available at decim 2 / 4 / 8 / 12 / 16 / 24 / 32 for fc32, from 4 for sc16 "
+                                          "and from 8 for sc8 input (a 16-output row must be whole 256-byte pieces)");
   if (c.frontend_mode == LTB_FRONTEND_TC_INT && c.input_format == LTB_FMT_FC32 &&
       !(c.fc32_full_scale > 0.f && c.fc32_full_scale < 1e30f))
     return fail(LTB_ERROR_INVALID_INPUTS, "LTB_FRONTEND_TC_INT on fc32 input takes the samples as 23-bit fixed point: "

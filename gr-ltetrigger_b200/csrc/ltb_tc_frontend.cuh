@@ -77,7 +77,7 @@ constexpr int kTcEpiWarps = 8, kTcXformWarps = 8;  // warps 0..7; 8 producer, 9 
 constexpr int kTcXformGroups = LTB_TC_XFORM_GROUPS;                 // groups of transform warps that take alternate stages
 constexpr int kTcXformGroupWarps = kTcXformWarps / kTcXformGroups;
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 2 + kTcXformWarps);   // 576
-constexpr int kTcTailSamples = kTcHalo * kTcRowSamples;   // 768 raw samples of history per stream at D = 16 (the largest)
+constexpr int kTcTailSamples = kTcHalo * 16 * 32;         // raw samples of history per stream at D = 32 (the largest rate built)
 constexpr int kTcTapShift = 27;                    // at D = 16; tc_tap_shift(D) in general
 
 // ---- geometry of the (format, decimation) variants ------------------------------------------------------------
@@ -106,13 +106,13 @@ struct TcGeom {
   static constexpr int NSTEP = (4 * ND + 15) / 16 * 16;        // N of a k-step's MMA
   static constexpr int TAIL = kTcHalo * ROW;                   // raw samples of history per stream
   static constexpr bool ok = ROW_BYTES % 256 == 0 && NPH <= 4 && 4 * (((KSTEPS - 1) * SPK) / D) + NSTEP <= kTcBRows &&
-                             ((KSTEPS - 1) * SPK) / D + ND - 1 <= 48 && NTAPS <= 3 * ROW + D;
+                             (ROW - 1 + NTAPS - 1) / D <= 48 && NTAPS <= 3 * ROW + D;   // a row reaches output 48 of its tile at most
 };
 __host__ inline bool tc_supported(int fmt, int D) {
   switch (fmt * 100 + D) {
-    case 2: case 4: case 8: case 12: case 16: return true;                     // fc32
-    case 104: case 108: case 112: case 116: return true;                       // sc16
-    case 208: case 216: return true;                                           // sc8
+    case 2: case 4: case 8: case 12: case 16: case 24: case 32: return true;               // fc32
+    case 104: case 108: case 112: case 116: case 124: case 132: return true;               // sc16
+    case 208: case 216: case 224: case 232: return true;                                   // sc8
   }
   return false;
 }

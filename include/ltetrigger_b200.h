@@ -62,8 +62,9 @@ extern "C" {
 #define LTB_FRONTEND_TC_INT 1      /* exact integer arithmetic on the tensor cores (tcgen05.mma kind::i8): taps
                                       quantised to three balanced base-256 digits, the int16 / int8 samples are
                                       their own digits, int32 accumulation in TMEM, one rounding to float32 per
-                                      output.  decim 2 / 4 / 8 / 12 / 16 for fc32, 4 / 8 / 12 / 16 for sc16, 8 / 16 for
-                                      sc8 (the LTE sampling rates; a 16-output row must be whole 256-byte pieces);
+                                      output.  decim 2 / 4 / 8 / 12 / 16 / 24 / 32 for fc32, from 4 for sc16, from 8 for
+                                      sc8 (the LTE sampling rates and 46.08 / 61.44 Msps; a 16-output row must be whole
+                                      256-byte pieces);
                                       needs 16-byte aligned rows.  fc32 input is first
                                       put on a 23-bit fixed-point grid over +-fc32_full_scale (what a float sample
                                       of an ADC-fed source carries anyway); from there on the same exact integers */
@@ -256,7 +257,7 @@ LTB_API int ltb_kernel_decimate_host(int device, const void *x, int fmt, int n_s
                                      int decim, ltb_cf *y);
 
 /* LTB_FRONTEND_TC_INT at kernel level: decimate-by-`decim` of n_streams host streams of n_in interleaved int16
- * (fmt LTB_FMT_SC16: decim 4, 8, 12, 16), int8 (LTB_FMT_SC8: 8, 16) or float (LTB_FMT_FC32: 2, 4, 8, 12, 16; taken as
+ * (fmt LTB_FMT_SC16: decim 4, 8, 12, 16, 24, 32), int8 (LTB_FMT_SC8: 8 ... 32) or float (LTB_FMT_FC32: 2 ... 32; taken as
  * 23-bit fixed point over +-full_scale) I/Q samples, fed to the tensor-core kernel in calls of `chunk` samples (both
  * multiples of 8 decim; the raw history is carried between the calls as the engine does); y: [n_streams][n_in / decim]. */
 LTB_API int ltb_kernel_decimate_tc_host(int device, const void *x, int fmt, int decim, float full_scale, int n_streams,

@@ -55,8 +55,8 @@ int64_t orc_decimate_tcint_fc32_d(const orc_cf *x, int64_t n_in, int decim, floa
 {
   float taps[4096];
   int ntaps = orc_decim_taps(decim, taps, 4096);
-  if (ntaps <= 0 || ntaps > 528 || !(full_scale > 0.0f)) return -1;
-  int32_t T[528], D0[528];
+  if (ntaps <= 0 || ntaps > 2112 || !(full_scale > 0.0f)) return -1;
+  int32_t T[2112], D0[2112];
   const int shift = tcint_shift(decim);
   for (int j = 0; j < ntaps; j++) {
     T[j] = (int32_t)llrint(ldexp((double)taps[j], shift));
@@ -327,8 +327,8 @@ static int64_t tcint_run(const int16_t *iq16, const int8_t *iq8, int64_t n_in, i
 {
   float taps[4096];
   int ntaps = orc_decim_taps(decim, taps, 4096);
-  if (ntaps <= 0 || ntaps > 528) return -1;
-  int32_t T[528];
+  if (ntaps <= 0 || ntaps > 2112) return -1;
+  int32_t T[2112];
   const int shift = tcint_shift(decim);
   for (int j = 0; j < ntaps; j++) T[j] = (int32_t)llrint(ldexp((double)taps[j], shift));
   const float scale = (float)ldexp(1.0, -(shift + (iq16 ? 15 : 7)));

@@ -45,7 +45,7 @@ def campaign(seconds, seed, max_cases=100000, log=print):
     t_end = time.time() + seconds
     n_cases = 0
     while time.time() < t_end and n_cases < max_cases:
-        decim = int(rng.choice([1, 1, 2, 3, 4, 5, 6, 8, 8, 10, 12, 13, 15, 16, 16, 20]))
+        decim = int(rng.choice([1, 1, 2, 3, 4, 5, 6, 8, 8, 10, 12, 13, 15, 16, 16, 20, 24, 32]))
         fmt = int(rng.integers(0, 3))
         corr = int(rng.integers(0, 2))
         tdd = int(rng.integers(0, 4) == 0)
@@ -59,7 +59,7 @@ def campaign(seconds, seed, max_cases=100000, log=print):
         chunk = int(rng.integers(20, 6000)) * step
         # the integer tensor-core front end where the kernel exists (half of those cases); fc32 gets a declared range
         # between 3 x and 40 x the signal's rms, so some cases clip and others use few of the grid's bits
-        tc_ok = decim in {0: (2, 4, 8, 12, 16), 1: (4, 8, 12, 16), 2: (8, 16)}[fmt]
+        tc_ok = decim in {0: (2, 4, 8, 12, 16, 24, 32), 1: (4, 8, 12, 16, 24, 32), 2: (8, 16, 24, 32)}[fmt]
         tc = bool(tc_ok and rng.integers(0, 2))
         fs = float(rng.uniform(3.0, 40.0)) if (tc and fmt == 0) else 0.0
         cfg = dict(decim=decim, fmt=fmt, corr=corr, tdd=tdd, n_streams=n_streams, thr=thr, track_after=track_after,

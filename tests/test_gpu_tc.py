@@ -149,7 +149,8 @@ def test_tc_front_end_fc32_through_the_engine(lt, oracle, corr):
     np.testing.assert_allclose(got["peak_value"][sel], fp["peak_value"][sel], rtol=1e-4)
 
 
-@pytest.mark.parametrize("fmt,decim", [("fc32", 2), ("fc32", 4), ("fc32", 8), ("fc32", 12), ("sc16", 4), ("sc16", 8), ("sc16", 12), ("sc8", 8)])
+@pytest.mark.parametrize("fmt,decim", [("fc32", 2), ("fc32", 4), ("fc32", 8), ("fc32", 12), ("sc16", 4), ("sc16", 8), ("sc16", 12), ("sc8", 8),
+                                       ("fc32", 24), ("sc16", 24), ("sc8", 24), ("fc32", 32), ("sc16", 32), ("sc8", 32)])
 @pytest.mark.parametrize("n_out,chunk_outs", [(976 * 2 + 40, None), (9000, 8 * 37), (9000, 8 * 1), (61 * 16 * 3 + 8, 8 * 250)])
 def test_tc_decimator_other_rates_bit_exact(lt, oracle, fmt, decim, n_out, chunk_outs):
     """The LTE sampling rates below 30.72 Msps (decimation 2, 4, 8, 12): the same kernel with 16 D samples per row, its

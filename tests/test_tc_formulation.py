@@ -72,7 +72,8 @@ def _replay(comp, fmt, btab, sum_t, q_inv=None, out_scale=None, decim=16):
     return ((out.reshape(-1) + c).astype(np.float32) * np.float32(sc))[48:]   # int64 -> float32 rounds to nearest even, as I2F.S64 does
 
 
-@pytest.mark.parametrize("fmt,decim", [(0, 16), (1, 16), (2, 16), (0, 8), (1, 8), (2, 8), (0, 4), (1, 4), (0, 2), (0, 12), (1, 12)])
+@pytest.mark.parametrize("fmt,decim", [(0, 16), (1, 16), (2, 16), (0, 8), (1, 8), (2, 8), (0, 4), (1, 4), (0, 2), (0, 12), (1, 12),
+                                       (0, 24), (1, 24), (2, 24), (0, 32), (1, 32), (2, 32)])
 def test_kernel_schedule_equals_oracle(oracle, fmt, decim):
     import math
     import ltetrigger_b200 as lt

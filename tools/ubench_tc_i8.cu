@@ -74,7 +74,7 @@ static void launch(const CUtensorMap &map, const TcParams &P, int grid, int S, i
   decimate_tc_kernel<FMT, D><<<grid, kTcThreads, tc_smem_bytes()>>>(map, P);
   tc_tail_kernel<FMT, D><<<S, 256>>>(P.in, P.stride_bytes, n_chunk, t_old, t_new);
 }
-#define UB_VARIANTS(X) X(0, 2) X(0, 4) X(0, 8) X(0, 12) X(0, 16) X(1, 4) X(1, 8) X(1, 12) X(1, 16) X(2, 8) X(2, 16)
+#define UB_VARIANTS(X) X(0, 2) X(0, 4) X(0, 8) X(0, 12) X(0, 16) X(0, 24) X(0, 32) X(1, 4) X(1, 8) X(1, 12) X(1, 16) X(1, 24) X(1, 32) X(2, 8) X(2, 16) X(2, 24) X(2, 32)
 
 int main(int argc, char **argv) {
   const int G = argc > 1 ? atoi(argv[1]) : 1;            // input format: 0 fc32, 1 sc16, 2 sc8
