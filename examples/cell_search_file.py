@@ -66,7 +66,13 @@ def search(args):
                          "Arbitrary resampling not supported at this time.\n".format(args.sample_rate / 1e6))
         sys.exit(-1)
     decim = int(args.sample_rate / REQUIRED_SAMPLE_RATE)
-    trigger = lt.downlink_trigger_c(psr_threshold=args.threshold, exit_on_success=True, decim=decim, input_format=input_format)
+    tc = args.frontend == "tc"
+    if tc and input_format == lt.FMT_FC32 and not args.full_scale:
+        sys.stderr.write("--frontend tc on fc32 input needs --full-scale (the range of the source, e.g. 1.0).\n")
+        sys.exit(-1)
+    trigger = lt.downlink_trigger_c(psr_threshold=args.threshold, exit_on_success=True, decim=decim, input_format=input_format,
+                                    frontend_mode=lt.FRONTEND_TC_INT if tc else lt.FRONTEND_FP32,
+                                    fc32_full_scale=args.full_scale if (tc and input_format == lt.FMT_FC32) else 0.0)
     store = lt.cellstore().connect(trigger)
     if data is None:
         data = np.fromfile(args.filename, np.complex64)
@@ -137,6 +143,8 @@ def parse(argv=None):
         (("--gui",), dict(action="store_true", help=argparse.SUPPRESS)),
         (("--debug",), dict(action="store_true", help=argparse.SUPPRESS)),
         (("--fifoname",), dict(default=None, help="also write every result to this FIFO as '<length>\\n<json>'")),
+        (("--frontend",), dict(default="fp32", choices=["fp32", "tc"], help="resampler arithmetic: canonical float32 (default) or exact integers on the tensor cores (rates 2 ... 32 x 1.92 MHz)")),
+        (("--full-scale",), dict(type=float, default=0.0, metavar="A", help="with --frontend tc on fc32 input: the range of the source (samples are taken as 23-bit fixed point over +-A)")),
     ]
     for flags, kw in options:
         ap.add_argument(*flags, **kw)

@@ -281,18 +281,21 @@ class downlink_trigger_c:
     """
 
     def __init__(self, psr_threshold, exit_on_success=False, device=0, max_chunk=1 << 18, keep_halfframes=True,
-                 decim=1, input_format=A.FMT_FC32):
+                 decim=1, input_format=A.FMT_FC32, frontend_mode=A.FRONTEND_FP32, fc32_full_scale=0.0):
         """`decim` > 1 fuses the `rational_resampler_ccc(1, decim)` the reference's apps put in
         front of the hier block (examples/cell_search_file.py:56-57) into the engine's front end;
         the input of work() is then at decim x 1.92 Msps.  `input_format` other than fc32 also fuses the
         interleaved-short / interleaved-char to complex conversion a flowgraph on an SDR's wire format starts with
-        (work() then takes [n, 2] int16 / int8 arrays).  Defaults: the reference's interface."""
+        (work() then takes [n, 2] int16 / int8 arrays).  `frontend_mode = FRONTEND_TC_INT` runs that fused resampler as
+        exact-integer GEMMs on the tensor cores (decim 2 ... 32, see include/ltetrigger_b200.h; fc32 input then needs
+        `fc32_full_scale`, the range of the source).  Defaults: the reference's interface."""
         self.psr_threshold = self._ensure_safe_threshold(psr_threshold)
         self.exit_on_success = exit_on_success
         self._step = 8 * decim
         self._fmt = input_format
         self._engine = Trigger(1, decim=decim, psr_threshold=self.psr_threshold, max_chunk=max_chunk * decim,
-                               record_all=True, keep_halfframes=keep_halfframes, device=device, input_format=input_format)
+                               record_all=True, keep_halfframes=keep_halfframes, device=device, input_format=input_format,
+                               frontend_mode=frontend_mode, fc32_full_scale=fc32_full_scale)
         self._keep = keep_halfframes
         self.pss0, self.pss1, self.pss2 = (_chain_view(self._engine, k) for k in range(3))
         self._ports = {"track": [], "drop": []}

@@ -211,6 +211,27 @@ def test_cell_search_file_cli(lt, name, rate, capsys):
         os.remove(path)
 
 
+@pytest.mark.parametrize("name,rate", [("50prb", "15.36M"), ("100prb", "30.72M")])
+def test_cell_search_file_cli_with_the_tensor_core_front_end(lt, name, rate):
+    """The CLI with --frontend tc --full-scale 4: the fused resampler runs as exact-integer GEMMs on the tensor cores, the
+    hier block with its host-side MIB decode finds the same cell with the same MIB as with the float32 resampler."""
+    import importlib.util
+    import json
+    import os
+    from conftest import GOLDEN, ROOT
+    spec = importlib.util.spec_from_file_location("cell_search_file", os.path.join(ROOT, "examples", "cell_search_file.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    fname, _, cell_id = FIXTURES[name]
+    path = os.path.join(GOLDEN, "test_frames", fname)
+    tc = json.loads(cli.main(cli.parse([path, "-s", rate, "--repeat", "--time-out", "5", "--frontend", "tc", "--full-scale", "4"]))[0])
+    fp = json.loads(cli.main(cli.parse([path, "-s", rate, "--repeat", "--time-out", "5"]))[0])
+    assert tc["status"] == "FOUND" and tc["cell_id"] == cell_id and tc["nof_prb"] == NOF_PRB[name]
+    assert tc == fp
+    with pytest.raises(SystemExit):
+        cli.main(cli.parse([path, "-s", rate, "--repeat", "--time-out", "1", "--frontend", "tc"]))      # fc32 needs its range
+
+
 def test_cell_search_batch_cli(lt, tmp_path):
     """examples/cell_search_batch.py: several captures as the streams of one engine; per file the
     reference's cell dictionary or NOT_FOUND (same fields as cell_search_file.py)."""
