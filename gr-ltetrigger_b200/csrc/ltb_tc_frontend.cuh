@@ -1,5 +1,6 @@
-// LTB_FRONTEND_TC_INT: the D = 16 decimating front end for integer input (sc16, sc8) on the 5th-generation
-// tensor cores, in exact integer arithmetic.  Included by ltb_api.cu and by tools/ubench_tc_i8.cu.
+// LTB_FRONTEND_TC_INT: the decimating front end on the 5th-generation tensor cores, in exact integer arithmetic, for
+// sc16 / sc8 input and for fc32 input taken as 23-bit fixed point, at D = 2 ... 32 (TcGeom below lists the pairs).
+// Included by ltb_api.cu and by tools/ubench_tc_i8.cu.  Described for D = 16; "geometry" below has the other rates.
 //
 // Arithmetic (what the oracle's ORC_FRONT_TCINT restates with int64 on the CPU):
 //   T[j] = rint(taps[j] * 2^27)                        525 integers, |T| < 2^23, three balanced base-256 digits
@@ -7,6 +8,8 @@
 //   y[k] = float32(A[k]) * 2^-42  (sc8: 2^-34)         ONE rounding per output (2^-27 taps, 2^-15 / 2^-7 input scale)
 // Nothing else rounds, so the result does not depend on accumulation order: the tensor core's int32
 // accumulators, the digit recombination and the diagonal sums below are all exact.
+// fc32: x = q(sample) - 2^22 with q() the two-FFMA fixed-point step at tc_split below (1 <= q < 2^23), the product of the
+// lowest sample byte with the lowest tap digit is not formed, y[k] = float32(A[k] / 256) * float32(F / (2^22 - 1) * 2^-19).
 //
 // GEMM form (sc16).  A row of the A operand is 256 consecutive samples of one component of one stream (16
 // outputs), as the 512 bytes they occupy (lo byte XOR 0x80 -> signed "lo - 128", hi byte signed:
