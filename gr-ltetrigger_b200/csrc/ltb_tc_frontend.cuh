@@ -290,6 +290,11 @@ __device__ __forceinline__ void tc_split(const uint4 w, uint2 &re, uint2 &im, co
 
 // ---- epilogue role (warps 0..7 of both kernels): warp w reads TMEM lane quarter w % 4 (w % 4 = 0,1: re rows 0..63; 2,3: im
 // rows 0..63) and owns the outputs r = 8 h .. 8 h + 7 (h = w / 4) of its 32 rows: column groups u = 8 (2 c + h) .. + 7, c = 0..2
+// SYSTOLIC picks how the q = 0..3 contributions of the rows above are summed -- running sums that move down a row between
+// the column groups (80 registers, the accumulator buffer is released after the last sum) or all groups recombined first
+// (96 registers, released right after the loads); measured: the first is 4 % faster on fc32, whose tiles are long, the
+// second 6 % on sc16 / sc8, where the MMA warp waits for the buffer (profiles/tc_epilogue_r02.log)
+template <bool SYSTOLIC>
 __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const uint32_t tmem, const uint32_t acc_full0,
                                                  const uint32_t acc_empty0, float *s_stage, long long *s_xchg,
                                                  const int t_begin, const int t_end) {
@@ -315,81 +320,165 @@ __device__ __forceinline__ void tc_epilogue_role(const TcParams &P, const uint32
         continue;
       }
       const uint32_t taddr = tmem + buf * 256 + ((uint32_t)(quarter * 32) << 16);
-      long long p[3][8];                                                 // p[q][j]: u = 16 q + 8 half + j
-      long long p48 = 0;
+      if constexpr (SYSTOLIC) {
+        // Output r of row b is p0_b + p1_(b-1) + p2_(b-2) (+ p48_(b-3) for r = 0), p_q = the recombined column group
+        // u = 16 q + r.  The groups are taken q = 2, 1, 0 and the running sums move down one row (one lane) between them, so
+        // only eight 64-bit sums and one 16-column piece of the accumulator are live at a time.  What crosses from the
+        // upper quarter's rows 29..31 into the lower quarter's rows 0..2 goes through shared memory and is added after the
+        // barrier; the top quarter's rows 0..2 are the tile's halo (their outputs are not stored).
+        long long acc[8];
+        long long *xq = s_xchg + (size_t)((comp * 2 + half) * 3) * 17;
+        const bool pub = (quarter & 1) == 0 && lane >= 29;
+        long long *xp = xq + (lane - 29) * 17;                              // this row's slot when pub
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int c0 = 2 * q + half;                                     // 32-column chunk, loaded as two halves
+        for (int q = 2; q >= 0; --q) {
+          const int c0 = 2 * q + half;                                     // 32-column chunk, loaded as two halves
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint32_t r[16];
-          if (LTB_TC_BISECT & 32) {
+          for (int h2 = 0; h2 < 2; ++h2) {
+            uint32_t r[16];
+            if (LTB_TC_BISECT & 32) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = (uint32_t)(lane * 3 + i + tl);
-          } else {
-            tc_ld16(taddr + 32 * c0 + 16 * h2, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              for (int i = 0; i < 16; ++i) r[i] = (uint32_t)(lane * 3 + i + tl);
+            } else {
+              tc_ld16(taddr + 32 * c0 + 16 * h2, r);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+#ifdef LTB_TC_DBG_ACC
+            if (P.dbg_acc && t == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 32 * c0 + 16 * h2 + i] = (int)r[i];
+            }
+#endif
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int jj = 4 * h2 + j;
+              const long long v = tc_combine(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+              if (q == 2) {
+                acc[jj] = v;
+                if (pub) xp[8 + jj] = v;
+              } else {
+                if (q == 1 && pub) xp[jj] = v;
+                const long long up = tc_shfl_up(acc[jj], 1);
+                acc[jj] = (lane == 0 ? 0LL : up) + v;
+              }
+            }
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) p[q][4 * h2 + j] = tc_combine(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+        if (half == 0) {
+          uint32_t r[4];                                                   // columns 192..195: u = 48 (q = 3, r = 0)
+          tc_ld4(taddr + 192, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const long long p48 = tc_combine(r[0], r[1], r[2], r[3]);
+#ifdef LTB_TC_DBG_ACC
           if (P.dbg_acc && t == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 32 * c0 + 16 * h2 + i] = (int)r[i];
+            for (int i = 0; i < 4; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 192 + i] = (int)r[i];
+          }
+#endif
+          if (pub) xp[16] = p48;
+          const long long up = tc_shfl_up(p48, 3);
+          acc[0] += lane < 3 ? 0LL : up;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(acc_empty(buf));                     // the MMA warp may refill this buffer
+        if (LTB_TC_BISECT & 16) continue;
+
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if ((quarter & 1) == 1 && lane < 3) {                              // rows 32..34: what rows 29..31 contribute
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (lane == 0) acc[j] += xq[2 * 17 + j] + xq[1 * 17 + 8 + j];  // p1 of row 31 + p2 of row 30
+            else if (lane == 1) acc[j] += xq[2 * 17 + 8 + j];              // p2 of row 31
+          }
+          if (half == 0) acc[0] += xq[lane * 17 + 16];                     // p48 of row 29 + lane
+        }
+        float *stg = s_stage + (comp * kTcTileRows + row) * kTcStagePitch + 8 * half;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) stg[j] = __fmul_rn(__ll2float_rn(acc[j] + P.c_const), P.out_scale);
+      } else {
+        long long p[3][8];                                                 // p[q][j]: u = 16 q + 8 half + j
+        long long p48 = 0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int c0 = 2 * q + half;                                     // 32-column chunk, loaded as two halves
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            uint32_t r[16];
+            if (LTB_TC_BISECT & 32) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] = (uint32_t)(lane * 3 + i + tl);
+            } else {
+              tc_ld16(taddr + 32 * c0 + 16 * h2, r);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[q][4 * h2 + j] = tc_combine(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+#ifdef LTB_TC_DBG_ACC
+            if (P.dbg_acc && t == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 32 * c0 + 16 * h2 + i] = (int)r[i];
+            }
+#endif
           }
         }
-      }
-      if (half == 0) {
-        uint32_t r[4];                                                   // columns 192..195: u = 48 (q = 3, r = 0)
-        tc_ld4(taddr + 192, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        p48 = tc_combine(r[0], r[1], r[2], r[3]);
-        if (P.dbg_acc && t == 0) {
+        if (half == 0) {
+          uint32_t r[4];                                                   // columns 192..195: u = 48 (q = 3, r = 0)
+          tc_ld4(taddr + 192, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          p48 = tc_combine(r[0], r[1], r[2], r[3]);
+#ifdef LTB_TC_DBG_ACC
+          if (P.dbg_acc && t == 0) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 192 + i] = (int)r[i];
+            for (int i = 0; i < 4; ++i) P.dbg_acc[(quarter * 32 + lane) * kTcBRows + 192 + i] = (int)r[i];
+          }
+#endif
         }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) tc_mbar_arrive(acc_empty(buf));                     // the MMA warp may refill this buffer
-      if (LTB_TC_BISECT & 16) continue;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(acc_empty(buf));                     // the MMA warp may refill this buffer
+        if (LTB_TC_BISECT & 16) continue;
 
-      // contributions to the rows below: rows 29..31 of the upper quarter hand theirs over in shared memory
-      long long *xq = s_xchg + (size_t)((comp * 2 + half) * 3) * 17;
-      if ((quarter & 1) == 0 && lane >= 29) {
-        long long *x = xq + (lane - 29) * 17;
+        // contributions to the rows below: rows 29..31 of the upper quarter hand theirs over in shared memory
+        long long *xq = s_xchg + (size_t)((comp * 2 + half) * 3) * 17;
+        if ((quarter & 1) == 0 && lane >= 29) {
+          long long *x = xq + (lane - 29) * 17;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { x[j] = p[1][j]; x[8 + j] = p[2][j]; }
-        x[16] = p48;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      float *stg = s_stage + (comp * kTcTileRows + row) * kTcStagePitch + 8 * half;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        long long acc = p[0][j];
-#pragma unroll
-        for (int q = 1; q <= 3; ++q) {
-          if (q == 3 && j != 0) continue;
-          long long v = tc_shfl_up(q == 3 ? p48 : p[q][j], q);
-          if (lane < q) v = xq[(3 + lane - q) * 17 + (q == 3 ? 16 : 8 * (q - 1) + j)];   // row 32 + lane - q of the upper quarter
-          if (q == 3 && half != 0) v = 0;                                // u = 48 only feeds output r = 0
-          acc += v;
+          for (int j = 0; j < 8; ++j) { x[j] = p[1][j]; x[8 + j] = p[2][j]; }
+          x[16] = p48;
         }
-        acc += P.c_const;
-        stg[j] = __fmul_rn(__ll2float_rn(acc), P.out_scale);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float *stg = s_stage + (comp * kTcTileRows + row) * kTcStagePitch + 8 * half;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          long long acc = p[0][j];
+#pragma unroll
+          for (int q = 1; q <= 3; ++q) {
+            if (q == 3 && j != 0) continue;
+            long long v = tc_shfl_up(q == 3 ? p48 : p[q][j], q);
+            if (lane < q) v = xq[(3 + lane - q) * 17 + (q == 3 ? 16 : 8 * (q - 1) + j)];   // row 32 + lane - q of the upper quarter
+            if (q == 3 && half != 0) v = 0;                                // u = 48 only feeds output r = 0
+            acc += v;
+          }
+          acc += P.c_const;
+          stg[j] = __fmul_rn(__ll2float_rn(acc), P.out_scale);
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      // coalesced store: 16 consecutive float2 per row
+      // coalesced store: 16 consecutive float2 per row; ring offsets in 32 bits (the ring is at most 2^31 entries, so the
+      // low word of the absolute index decides the slot)
       {
         float2 *yr = P.y_ring + (size_t)stream * P.cap;
-        const int rr = tid & 15;
+        const int rr = tid & 15, rw0 = tid >> 4;
+        const int k0 = (row0 + rw0) * 16 + rr;                           // output index of this thread's first row
+        const unsigned slot0 = (unsigned)P.n_base + (unsigned)k0;
+        const float *sg = s_stage + rw0 * kTcStagePitch + rr;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int rw = (tid >> 4) + 16 * j;                            // tile row 0..63
-          const long long k = (long long)(row0 + rw) * 16 + rr;
-          if (rw >= kTcHalo && k < m_out) {
-            const float2 v = make_float2(s_stage[(0 * kTcTileRows + rw) * kTcStagePitch + rr],
-                                         s_stage[(1 * kTcTileRows + rw) * kTcStagePitch + rr]);
-            yr[(unsigned)((P.n_base + k) & P.cap_mask)] = v;
+          const int rw = rw0 + 16 * j;                                   // tile row 0..63
+          if (rw >= kTcHalo && k0 + 256 * j < m_out) {
+            const float2 v = make_float2(sg[16 * j * kTcStagePitch], sg[(kTcTileRows + 16 * j) * kTcStagePitch]);
+            yr[(slot0 + 256u * j) & P.cap_mask] = v;
           }
         }
       }
@@ -582,7 +671,7 @@ decimate_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
       }
     }
   } else {
-    tc_epilogue_role(P, tmem, acc_full(0), acc_empty(0), s_stage, s_xchg, t_begin, t_end);
+    tc_epilogue_role<FMT == LTB_FMT_FC32>(P, tmem, acc_full(0), acc_empty(0), s_stage, s_xchg, t_begin, t_end);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -10,6 +10,9 @@
 #include <cstring>
 #include <vector>
 
+#ifndef UBENCH_NO_DBG         // -DUBENCH_NO_DBG: time the kernel as the library builds it (the accumulator check then reports mismatches)
+#define LTB_TC_DBG_ACC 1      // this tool reads back the raw accumulators of tile 0
+#endif
 #include "../gr-ltetrigger_b200/csrc/ltb_tc_frontend.cuh"
 
 using namespace ltb;
