@@ -78,24 +78,31 @@ def run(workload, seconds=1.0, device=0, threshold=4.0):
     eng = lt.Trigger(n_streams=1, decim=decim, psr_threshold=threshold, max_chunk=call, device=device, corr_mode=lt.CORR_FFT)
     for _ in range(3):
         eng.process_host_ptr(host.data_ptr(), call * 8, call)
-    t0 = time.perf_counter()
-    cells = 0
-    for _ in range(calls):
-        r = eng.process_host_ptr(host.data_ptr(), call * 8, call)
-        cells += int(((r["flags"] & lt.F_CELL) != 0).sum())
-    dt_sync = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    eng.submit_host_ptr(host.data_ptr(), call * 8, call)
-    for _ in range(calls - 1):
+    # one stream is host-bound (a 100 ms call is ~0.4 ms of kernels): the wall time of a pass of `calls` calls moves with
+    # whatever else the host does, so both loops run five times and the median pass is reported (best beside it)
+    sync_t, async_t, cells = [], [], 0
+    for rep in range(5):
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            r = eng.process_host_ptr(host.data_ptr(), call * 8, call)
+            if rep == 0:
+                cells += int(((r["flags"] & lt.F_CELL) != 0).sum())
+        sync_t.append(time.perf_counter() - t0)
+    for rep in range(5):
+        t0 = time.perf_counter()
         eng.submit_host_ptr(host.data_ptr(), call * 8, call)
+        for _ in range(calls - 1):
+            eng.submit_host_ptr(host.data_ptr(), call * 8, call)
+            eng.collect()
         eng.collect()
-    eng.collect()
-    dt_async = time.perf_counter() - t0
+        async_t.append(time.perf_counter() - t0)
+    dt_sync, dt_async = sorted(sync_t)[2], sorted(async_t)[2]
     stage = eng.last_kernel_times()
     eng.close()
     out["c_abi"] = {"process_host_msamples_per_s": calls * call / dt_sync / 1e6,
                     "submit_collect_msamples_per_s": calls * call / dt_async / 1e6,
                     "ms_per_100ms_call": 1e3 * dt_sync / calls, "cells_tagged": cells,
+                    "passes": 5, "best_submit_collect_msamples_per_s": calls * call / min(async_t) / 1e6,
                     "last_call_stage_ms": {"frontend": stage[0], "pss_corr": stage[1], "pss_track": stage[2], "sss": stage[3]},
                     "realtime_factor": (calls * call / dt_sync) / (1.92e6 * decim)}
 
