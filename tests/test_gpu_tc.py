@@ -229,6 +229,39 @@ def test_tc_front_end_other_rates_through_the_engine(lt, oracle, name, fmt):
     np.testing.assert_allclose(got["psr"][over], fp["psr"][over], rtol=1e-4)
 
 
+@pytest.mark.parametrize("fmt,decim", [("sc16", 32), ("fc32", 32), ("sc8", 24), ("fc32", 12)])
+def test_tc_front_end_wide_rates_through_the_engine(lt, oracle, fmt, decim):
+    """Synthetic cells at 61.44 / 46.08 / 23.04 Msps (no bundled frame has these rates) through the whole chain with the
+    integer front end, two streams in ragged chunks: records bit-identical to the oracle in the same mode, the right cell
+    ids, the same decisions as the float32 front end (which at these rates is the general kernel)."""
+    from ltetrigger_b200 import synth
+    n = 19200 * decim * 12
+    rows = [synth.capture(211, n, snr_db=6.0, decim=decim, seed=3, cfo_hz=700.0),
+            synth.capture(88, n, snr_db=2.0, decim=decim, seed=4)]
+    x = np.stack(rows)
+    code = {"fc32": lt.FMT_FC32, "sc16": lt.FMT_SC16, "sc8": lt.FMT_SC8}[fmt]
+    iq = x if fmt == "fc32" else synth.to_sc16(x) if fmt == "sc16" else synth.to_sc8(x)
+    fs = 6.0 if fmt == "fc32" else 0.0
+    chunk = decim * 8 * 2777
+    trig = lt.Trigger(n_streams=2, decim=decim, max_chunk=chunk, input_format=code, corr_mode=lt.CORR_FFT,
+                      frontend_mode=lt.FRONTEND_TC_INT, fc32_full_scale=fs)
+    got = trig.run(iq, chunk=chunk)
+    trig.close()
+    want = oracle.trigger_run(iq, decim=decim, fmt=code, conv_mode=oracle.CONV_OS | oracle.FRONT_TCINT, fc32_full_scale=fs)
+    assert_recs_equal(got, want)
+    cells = got[(got["flags"] & lt.F_CELL) != 0]
+    assert set(cells[cells["stream"] == 0]["cell_id"].tolist()) == {211}
+    assert set(cells[cells["stream"] == 1]["cell_id"].tolist()) == {88}
+    ref = lt.Trigger(n_streams=2, decim=decim, max_chunk=chunk, input_format=code, corr_mode=lt.CORR_FFT)
+    fp = ref.run(iq, chunk=chunk)
+    ref.close()
+    for f in ("win_start", "emit_start", "flags", "m0", "m1", "n_id_1", "cell_id"):
+        assert (got[f] == fp[f]).all(), f
+    over = (got["flags"] & lt.F_OVER) != 0
+    assert (got["peak_pos"][over] == fp["peak_pos"][over]).all()
+    np.testing.assert_allclose(got["psr"][over], fp["psr"][over], rtol=1e-4)
+
+
 def test_tc_front_end_argument_checks(lt):
     with pytest.raises(lt.LtbError):
         lt.Trigger(n_streams=1, decim=16, input_format=lt.FMT_FC32, frontend_mode=lt.FRONTEND_TC_INT)   # fc32 needs its range
