@@ -571,3 +571,35 @@ def test_device_input_that_is_only_sample_aligned(lt, oracle, decim):
     assert_recs_equal(got, want)
     with pytest.raises(lt.LtbError):
         trig.process_device_ptr(view.data_ptr() + 4, 8 * (n + 3), n)
+
+
+def test_product_reports_the_transmitted_truth_without_the_oracle(lt):
+    """The CUDA path against what was transmitted (tests/test_oracle_truth.py does the same for the oracle): known cell id,
+    CP type, frame timing and carrier offset of seeded synthetic captures, at the search rate and through both decimating
+    front ends at D = 16 (group delay (525 - 1) / 2 input samples)."""
+    from ltetrigger_b200 import synth
+    rng = np.random.default_rng(4242)
+    for decim, frontend, fs in ((1, lt.FRONTEND_FP32, 0.0), (16, lt.FRONTEND_FP32, 0.0), (16, lt.FRONTEND_TC_INT, 8.0)):
+        cases = [(int(rng.integers(0, 504)), int(rng.integers(0, 19200 * decim)), float(rng.uniform(-2500.0, 2500.0)),
+                  bool(i == 2)) for i in range(6)]
+        # the delayed frame boundary on a whole search-rate sample (a fractional one biases the half-symbol CFO estimate:
+        # a Zadoff-Chu sequence sampled off the grid looks frequency-shifted)
+        cases = [(c, o + (262 - o) % decim, f, e) for c, o, f, e in cases]
+        n = 19200 * decim * 24
+        x = np.stack([synth.capture(c, n, snr_db=12.0, decim=decim, seed=50 + i, offset=o, cfo_hz=f, ext_cp=e)
+                      for i, (c, o, f, e) in enumerate(cases)])
+        trig = lt.Trigger(n_streams=len(cases), decim=decim, psr_threshold=4.0, max_chunk=96000 * decim,
+                          corr_mode=lt.CORR_FFT, frontend_mode=frontend, fc32_full_scale=fs)
+        recs = trig.run(x, chunk=96000 * decim)
+        trig.close()
+        delay = (525 - 1) / 2.0 / decim if decim == 16 else 0.0
+        for s, (cell, offset, cfo_hz, ext_cp) in enumerate(cases):
+            t = recs[(recs["stream"] == s) & ((recs["flags"] & lt.F_CELL) != 0)]
+            what = (decim, frontend, cell, offset, cfo_hz, ext_cp)
+            assert len(t) >= 4 and set(t["cell_id"].tolist()) == {cell}, what
+            assert set(((t["flags"] & lt.F_CP_NORM) != 0).tolist()) == {not ext_cp}, what
+            truth = (-offset / decim + delay) % 9600.0
+            d = (t["emit_start"] % 9600 - truth + 4800.0) % 9600.0 - 4800.0
+            assert np.abs(d).max() == 0.0, (what, truth)
+            trk = t[(t["flags"] & lt.F_TRACKING) != 0]
+            assert len(trk) and abs(float(trk["mean_cfo"][-1]) - cfo_hz / 15000.0) < 0.01, what

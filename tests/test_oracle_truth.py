@@ -3,7 +3,7 @@ oracle/ltetrigger_oracle.c.  synth.py builds an LTE downlink from 36.211 (Zadoff
 with a known cell id, cyclic-prefix type, frame timing and carrier offset; the restated search must report exactly
 those: cell_id and cp_type on every tagged half-frame, the emitted half-frame starting on the transmitted subframe-0/5
 boundary (to the sample at the search rate; shifted by the decimator's group delay (ntaps - 1) / 2 input samples when
-there is one), and mean_cfo within 0.02 (300 Hz: it is a mean that includes the first noisy estimates) of the
+there is one), and mean_cfo within 0.01 (150 Hz: it is a mean that includes the first noisy estimates) of the
 offset in units of the 15 kHz subcarrier spacing
 (srslte_pss_cfo_compute's unit, lib/pss_impl.cc:197-199).  The GPU path is bit-identical to the oracle
 (tests/test_gpu_*.py), so this pins both to the physical answer."""
@@ -37,21 +37,28 @@ def test_search_rate_captures_report_the_transmitted_cell_timing_and_offset(orac
         # aligned half-frames start where the transmitter put subframe 0 or 5
         assert set((t["emit_start"] % 9600).tolist()) == {(-offset) % 9600}, what
         trk = t[(t["flags"] & F_TRACKING) != 0]
-        assert len(trk) and abs(float(trk["mean_cfo"][-1]) - cfo_hz / 15000.0) < 0.02, (what, trk["mean_cfo"][-1])
+        assert len(trk) and abs(float(trk["mean_cfo"][-1]) - cfo_hz / 15000.0) < 0.01, (what, trk["mean_cfo"][-1])
 
 
 @pytest.mark.parametrize("decim,ntaps", [(4, 131), (16, 525)])
 def test_decimated_captures_report_the_transmitted_timing_after_the_group_delay(oracle, decim, ntaps):
+    """Even cases put the delayed frame boundary on a whole search-rate sample (timing exact, carrier offset checked);
+    odd cases leave it fractional: timing to the nearest sample, and no statement about the carrier offset, because a
+    Zadoff-Chu sequence sampled a fraction of a sample off looks frequency-shifted to the half-symbol estimator."""
     rng = np.random.default_rng(decim)
-    for i in range(2):
+    half = (ntaps - 1) // 2                      # group delay in input samples
+    for i in range(4):
         cell = int(rng.integers(0, 504))
         offset = int(rng.integers(0, 19200 * decim))
+        if i % 2 == 0:
+            offset += (half - offset) % decim
         cfo_hz = float(rng.uniform(-2500.0, 2500.0))
         t = _case(oracle, cell, decim, offset, cfo_hz, False, snr_db=12.0, seed=7 + i, n_frames=24)
         what = (decim, cell, offset, cfo_hz)
         assert len(t) >= 4 and set(t["cell_id"].tolist()) == {cell}, what
-        truth = (-offset / decim + (ntaps - 1) / 2.0 / decim) % 9600.0
+        truth = (-offset / decim + half / decim) % 9600.0
         d = (t["emit_start"] % 9600 - truth + 4800.0) % 9600.0 - 4800.0
-        assert np.abs(d).max() <= 1.0, (what, truth, set((t["emit_start"] % 9600).tolist()))
-        trk = t[(t["flags"] & F_TRACKING) != 0]
-        assert len(trk) and abs(float(trk["mean_cfo"][-1]) - cfo_hz / 15000.0) < 0.02, what
+        assert np.abs(d).max() <= (0.0 if i % 2 == 0 else 1.0), (what, truth, set((t["emit_start"] % 9600).tolist()))
+        if i % 2 == 0:
+            trk = t[(t["flags"] & F_TRACKING) != 0]
+            assert len(trk) and abs(float(trk["mean_cfo"][-1]) - cfo_hz / 15000.0) < 0.01, what
