@@ -136,7 +136,7 @@ def parse(argv=None):
         (("-s", "--sample-rate"), dict(type=eng_float, default=None, metavar="Hz", help="sample rate of the capture (a multiple of 1.92 MHz); required unless the file is a SigMF recording")),
         (("-f", "--frequency"), dict(type=eng_float, metavar="Hz", help="center frequency of the capture (informational)")),
         (("--repeat",), dict(action="store_true", help="start over at the end of the file until a cell is found, the cut-off or the time-out")),
-        (("-c", "--cut-off"), dict(type=eng_int, metavar="N", default=-1, help="give up after N input samples")),
+        (("-c", "--cut-off"), dict(type=eng_int, metavar="N", default=-1, help="give up after N samples at the 1.92 Msps search rate (the reference counts them after the resampler)")),
         (("--throttle",), dict(type=eng_float, metavar="Hz", help="accepted for compatibility; the GPU path is not throttled")),
         (("--time-out",), dict(type=eng_float, metavar="sec", default=-1, help="give up after this many seconds")),
         (("--threshold",), dict(type=eng_float, default=4, help="PSR threshold of the trigger (clamped to > 1.5)")),
