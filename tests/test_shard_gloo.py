@@ -86,3 +86,86 @@ def test_ownership_and_global_ids():
     assert out["stream"].tolist() == [1, 5, 9, 5]
     assert len(shard.merge_records(recs)) == 4                      # no process group: identity (sorted)
     assert len(shard.detections(np.zeros(0, _abi.WINDOW_REC))) == 0
+
+
+# ---- time-segment sharding of ONE capture (north_star: "by time segment with a one-PSS-length halo")
+
+SEG_DECIM, SEG_FRAMES, SEG_N = 4, 100, 6
+
+
+def make_capture():
+    from ltetrigger_b200 import synth
+    return synth.capture(301, 19200 * SEG_DECIM * SEG_FRAMES, snr_db=6.0, decim=SEG_DECIM, seed=5, cfo_hz=800.0)
+
+
+class OracleSegEngine(OracleEngine):
+    def __init__(self, n_local):
+        OracleEngine.__init__(self, n_local, decim=SEG_DECIM)
+
+    def run(self, iq):
+        return self.O.trigger_run(iq, decim=self.decim, psr_threshold=self.thr, conv_mode=self.O.CONV_OS, nthreads=2)
+
+
+def _seg_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "gr-ltetrigger_b200", "python"))
+    import torch.distributed as dist
+    from ltetrigger_b200 import shard
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        x = make_capture()
+        plan = shard.plan_time_segments(len(x), SEG_DECIM, SEG_N)
+        st = shard.ShardedTrigger(plan.n_segments, rank, world, engine_factory=OracleSegEngine)   # segments dealt like streams
+        rows = shard.cut_segments(x, plan)
+        merged = st.run_and_merge(st.local_view(rows), dst=0)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "stitched.npy"), shard.stitch_segments(merged, plan))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_time_segments_two_rank_gloo(tmp_path, oracle):
+    """One 1 s capture cut into six overlapping segments, three per rank; the stitched list holds exactly the
+    cell-tagged half-frames of the sequential search (same starts, same cell, same CP type), and every segment's
+    records are those of the reference's search started at the segment's first sample."""
+    import torch.multiprocessing as mp
+    from ltetrigger_b200 import shard, _abi as A
+    mp.spawn(_seg_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = np.load(os.path.join(str(tmp_path), "stitched.npy"))
+    x = make_capture()
+    plan = shard.plan_time_segments(len(x), SEG_DECIM, SEG_N)
+    assert plan.n_segments == SEG_N and (plan.starts % (8 * SEG_DECIM) == 0).all()
+    assert plan.starts[-1] + plan.length <= len(x) < plan.starts[-1] + plan.length + 8 * SEG_DECIM
+    one = shard.stitch_segments(oracle.trigger_run(shard.cut_segments(x, plan), decim=SEG_DECIM, psr_threshold=4.0,
+                                                   conv_mode=oracle.CONV_OS), plan)
+    assert got.tobytes() == one.tobytes()                           # two ranks == one process
+    seq = oracle.trigger_run(x[None, :], decim=SEG_DECIM, psr_threshold=4.0, conv_mode=oracle.CONV_OS)
+    cells_seq, cells_got = (r[(r["flags"] & A.F_CELL) != 0] for r in (seq, got))
+    assert len(cells_seq) > 150
+    assert cells_got["emit_start"].tolist() == cells_seq["emit_start"].tolist()
+    assert set(cells_got["cell_id"].tolist()) == {301}
+    assert ((cells_got["flags"] & A.F_CP_NORM) != 0).all()
+    d_seq, d_got = shard.detections(seq), shard.detections(got)
+    for f in ("stream", "cell_id", "n_id_2", "n_id_1", "cp_normal", "count", "frame_start", "first_seen"):
+        assert d_seq[f].tolist() == d_got[f].tolist(), f
+    # each chain's stitched records advance in time and are numbered consecutively
+    for r in range(3):
+        g = got[got["n_id_2"] == r]
+        assert (np.diff(g["win_start"]) > 0).all() and g["win_index"].tolist() == list(range(len(g)))
+
+
+def test_segment_plan_edges():
+    from ltetrigger_b200 import shard
+    p = shard.plan_time_segments(19200 * 10, 1, 8)                  # 100 ms: too short to split, one segment
+    assert p.n_segments == 1 and p.starts.tolist() == [0] and p.halo == 0
+    p = shard.plan_time_segments(30720000, 16, 16)                  # 1 s at 30.72 Msps
+    assert p.n_segments == 7                                        # each segment must own at least one halo of signal
+    p = shard.plan_time_segments(30720000 * 10, 16, 64)
+    assert p.n_segments == 64 and p.length % 128 == 0
+    assert (p.own_from[1:] == p.own_to[:-1]).all() and p.own_from[0] == 0
+    assert ((p.starts[1:] + p.length) // 16 - p.own_to[:-1] >= 0).all()
+    with pytest.raises(ValueError):
+        shard.plan_time_segments(1000, 1, 0)
+    with pytest.raises(ValueError):
+        shard.plan_time_segments(10 ** 7, 1, 4, halo_halfframes=4)
