@@ -169,3 +169,26 @@ def test_segment_plan_edges():
         shard.plan_time_segments(1000, 1, 0)
     with pytest.raises(ValueError):
         shard.plan_time_segments(10 ** 7, 1, 4, halo_halfframes=4)
+
+
+def test_time_segments_stated_limit_under_interference(oracle):
+    """The limit DESIGN section 7 states: a chain that is already tracking holds on through interference under which a
+    fresh chain does not acquire.  A second cell comes up at 0.8 of the first one's amplitude half way through; neither the
+    sequential search nor any segment acquires the second cell at threshold 4, the sequential search keeps tagging the
+    first for a while after the interferer appears, the segments that start inside the interference do not.  What the
+    stitched list reports is a subset of the sequential one -- never a half-frame the sequential search does not have."""
+    from ltetrigger_b200 import shard, synth, _abi as A
+    n = 19200 * 200
+    a = synth.capture(301, n, snr_db=10.0, seed=1)
+    b = synth.capture(77, n, seed=2)
+    b[:n // 2] = 0
+    x = (a + 0.8 * b).astype(np.complex64)
+    plan = shard.plan_time_segments(len(x), 1, 8)
+    st = shard.stitch_segments(oracle.trigger_run(shard.cut_segments(x, plan), decim=1, psr_threshold=4.0, conv_mode=oracle.CONV_OS), plan)
+    seq = oracle.trigger_run(x[None, :], decim=1, psr_threshold=4.0, conv_mode=oracle.CONV_OS)
+    got, want = (set(r["emit_start"][((r["flags"] & A.F_CELL) != 0) & (r["cell_id"] == 301)].tolist()) for r in (st, seq))
+    assert got < want and len(want - got) < 0.2 * len(want)
+    assert min(want - got) > n // 2                       # everything that is missing lies inside the interference
+    before = {e for e in want if e < n // 2}
+    assert before <= got                                  # and nothing is missing before it
+    assert not (((st["flags"] & A.F_CELL) != 0) & (st["cell_id"] == 77)).any()
