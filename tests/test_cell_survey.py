@@ -5,6 +5,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 
 from conftest import ROOT
 
@@ -30,8 +31,11 @@ def test_cell_survey_with_the_oracle_as_engine(oracle, tmp_path, monkeypatch):
         """Collects the passes and answers the last one with the oracle's records of the whole segments; half-frames are
         raw slices (no carrier offset in this capture, so the CFO rotation the engine applies is negligible)."""
 
+        made = []
+
         def __init__(self, n_streams, decim, psr_threshold, **kw):
             self.decim, self.thr, self.parts, self.last = decim, psr_threshold, [], np.zeros(0, A.WINDOW_REC)
+            OracleTrigger.made.append(dict(kw, n_streams=n_streams, decim=decim))
 
         def process(self, chunk):
             self.parts.append(np.array(chunk))
@@ -64,3 +68,17 @@ def test_cell_survey_with_the_oracle_as_engine(oracle, tmp_path, monkeypatch):
     seq = oracle.trigger_run(x[None, :], decim=1, psr_threshold=4.0, conv_mode=oracle.CONV_OS)
     for cell, n in ((301, 167), (77, 177)):
         assert int((((seq["flags"] & lt.F_CELL) != 0) & (seq["cell_id"] == cell)).sum()) == n
+
+    # the same capture as a SigMF recording: rate and sample type come from the metadata, the options reach the engine
+    from ltetrigger_b200 import sigmf
+    sigmf.write(str(tmp_path / "two_cells"), x, 1.92e6, frequency=2.11e9)
+    again = cell_survey.main(cell_survey.parse(["--segments", "8", "--frontend", "tc", "--full-scale", "8", str(tmp_path / "two_cells.sigmf-meta")]))
+    assert sorted(c["cell_id"] for c in again) == [77, 301]
+    kw = OracleTrigger.made[-1]
+    assert (kw["n_streams"], kw["decim"], kw["input_format"], kw["frontend_mode"], kw["fc32_full_scale"]) == \
+        (8, 1, lt.FMT_FC32, lt.FRONTEND_TC_INT, 8.0)
+    assert OracleTrigger.made[0]["frontend_mode"] == lt.FRONTEND_FP32 and OracleTrigger.made[0]["fc32_full_scale"] == 0.0
+    with pytest.raises(SystemExit):
+        cell_survey.survey(cell_survey.parse(["--frontend", "tc", "-s", "1.92M", path]))          # fc32 + tc needs the range
+    with pytest.raises(SystemExit):
+        cell_survey.survey(cell_survey.parse([path]))                                             # raw file without a rate
