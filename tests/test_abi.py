@@ -129,3 +129,29 @@ def test_c_client_finds_the_fixture_cell(tmp_path):
     out = subprocess.run([_build_c_client(tmp_path), fixture], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "cell_id 123" in out.stdout
+
+
+def test_built_library_holds_the_tensor_core_and_tma_paths():
+    """The shipped .so, disassembled (cuobjdump -sass; tools/sass_evidence.py): every variant of the integer front end
+    issues tcgen05.mma kind::i8 (UTCIMMA), reads its accumulators from tensor memory (LDTM), loads its operands by TMA
+    (UTMALDG) and signals completion through tcgen05.commit (UTCBAR) and mbarriers (SYNCS); the FP32 streaming decimators
+    stage their input with bulk copies (UBLKCP) and compute in packed FFMA2.  No mma.sync / wgmma-era HMMA anywhere."""
+    import shutil
+    import subprocess
+    import sys
+    if not shutil.which("cuobjdump") or not shutil.which("cu++filt"):
+        pytest.skip("CUDA binary utilities not installed")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_evidence
+    k = sass_evidence.per_kernel()
+    tc = {n: c for n, c in k.items() if "decimate_tc_kernel<" in n}
+    assert len(tc) == 17, sorted(tc)                 # fc32 at 7 rates (D = 2 ... 32), sc16 at 6 (from D = 4), sc8 at 4 (from D = 8)
+    for n, c in tc.items():
+        assert c["UTCIMMA"] >= 4 and c["LDTM"] >= 1 and c["UTMALDG"] >= 1 and c["UTCBAR"] >= 1 and c["SYNCS"] >= 8, (n, dict(c))
+        assert c["FFMA2"] == 0, n
+    for fmt in range(3):
+        c = k["ltb::decimate_stream_kernel<%d>" % fmt]
+        assert c["UBLKCP"] >= 1 and c["SYNCS"] >= 1 and c["FFMA2"] >= 500, dict(c)
+    assert k["ltb::pss_corr_fft_kernel"]["FFMA2"] > 100 and k["ltb::pss_track_kernel"]["FFMA2"] > 100
+    sass = subprocess.run(["cuobjdump", "-sass", sass_evidence.LIB], capture_output=True, text=True).stdout
+    assert " HMMA" not in sass and "WGMMA" not in sass
