@@ -21,7 +21,7 @@ F_BITS = (("searched", 1), ("over", 2), ("emit", 4), ("tracking", 8), ("tag_lost
 
 def one_case(rng, O, F, synth):
     cell = int(rng.integers(0, 504))
-    decim = int(rng.choice([1, 1, 1, 4, 8]))
+    decim = int(rng.choice([1, 1, 4, 8, 16]))
     snr = float(rng.uniform(-8.0, 12.0))
     thr = float(rng.choice([4.0, 4.0, 2.5, 1.7]))
     ext = bool(rng.random() < 0.2)
@@ -30,9 +30,15 @@ def one_case(rng, O, F, synth):
     conv = int(rng.choice([O.CONV_OS, O.CONV_OS, O.CONV_DIRECT, O.CONV_FFT]))
     x = synth.capture(cell, 19200 * decim * frames, snr_db=snr, decim=decim, seed=int(rng.integers(1 << 30)),
                       cfo_hz=cfo, ext_cp=ext, noise_only=bool(rng.random() < 0.1))
-    y32 = O.decimate(x, decim) if decim > 1 else x
-    y64 = F.decimate(x, decim)
-    label = "cell=%d D=%d snr=%.1f thr=%.1f ext=%d cfo=%.0f frames=%d conv=%d" % (cell, decim, snr, thr, ext, cfo, frames, conv)
+    fe = str(rng.choice(["fp32", "fp32", "tc-sc16", "tc-fc32"])) if decim > 1 else "fp32"
+    if fe == "tc-sc16":                                       # LTB_FRONTEND_TC_INT restated, on int16 wire samples
+        iq = synth.to_sc16(x[None, :])[0]
+        y32, y64 = O.decimate_tcint_sc16(iq, decim), F.decimate(O.sc16_to_fc32(iq).astype(np.complex128), decim)
+    elif fe == "tc-fc32":                                     # the same on fc32 taken as 23-bit fixed point over 8 rms
+        y32, y64 = O.decimate_tcint_fc32(x, float(8 * np.sqrt(np.mean(np.abs(x) ** 2))), decim), F.decimate(x, decim)
+    else:
+        y32, y64 = (O.decimate(x, decim) if decim > 1 else x), F.decimate(x, decim)
+    label = "cell=%d D=%d fe=%s snr=%.1f thr=%.1f ext=%d cfo=%.0f frames=%d conv=%d" % (cell, decim, fe, snr, thr, ext, cfo, frames, conv)
     res = dict(windows=0, differ=[], psr=0.0, peak=0.0, cfo=0.0, sss=0.0, cells=0)
     for r in range(3):
         got = O.chain_run(y32, r, psr_threshold=thr, conv_mode=conv)
