@@ -1,0 +1,139 @@
+"""The hier-block mirror `downlink_trigger_c` (python/downlink_trigger_c.py:13-73), its three host `mib` blocks and
+`cellstore` on CPU, with the oracle's restated blocks standing in for the CUDA engine behind `Trigger`'s interface: the
+reference's QA flowgraphs (python/qa_downlink_trigger_c.py:67-203) and the host logic around the engine -- message ports,
+threshold clamp, tag offsets per chain, records, exit_on_success -- without a device.  tests/test_gpu_blocks.py runs the
+same assertions on the real engine."""
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, load_fixture
+
+NOF_PRB = {"6prb": 6, "25prb": 25, "50prb": 50, "100prb": 100}
+
+
+def oracle_engine(oracle):
+    """A class with Trigger's constructor and the methods the block mirrors call, computing with oracle.Pss / oracle.Sss
+    call by call under the engine's scheduler rule (a window runs once 18365 samples from its start have arrived)."""
+    import ltetrigger_b200 as lt
+    from ltetrigger_b200 import _abi as A
+
+    class Engine:
+        def __init__(self, n_streams, decim=1, psr_threshold=4.0, max_chunk=1 << 18, **kw):
+            assert n_streams == 1 and decim == 1
+            self.max_chunk, self.thr = max_chunk, psr_threshold
+            self.pss = [oracle.Pss(k, psr_threshold, conv_mode=oracle.CONV_DIRECT) for k in range(3)]
+            self.sss = [oracle.Sss(k) for k in range(3)]
+            self.buf = np.zeros(960, np.complex64)               # the zero history GNU Radio puts in front
+            self.pos = [960, 960, 960]
+            self.hfs = []
+
+        def process(self, x):
+            self.buf = np.concatenate([self.buf, np.asarray(x[0], np.complex64)])
+            out = []
+            for k in range(3):
+                while self.pos[k] - 960 + oracle.LOOKAHEAD <= len(self.buf) - 960:
+                    nout, ncons, hf, rec = self.pss[k].work(self.buf, self.pos[k])
+                    rec = rec.copy()
+                    rec["win_start"] = self.pos[k] - 960
+                    rec["emit_start"] = self.pos[k] - 960 + rec["emit_start"] if nout else -1
+                    if nout:
+                        _, rec = self.sss[k].work(hf, bool(rec["flags"] & oracle.F_TAG_LOST), rec)
+                    out.append((k, rec, hf if nout else None))
+                    self.pos[k] += ncons
+            recs = np.zeros(len(out), A.WINDOW_REC)
+            self.hfs = []
+            for i, (k, rec, hf) in enumerate(out):               # engine order: by chain, then by call
+                for f in rec.dtype.names:
+                    recs[i][f] = rec[f]
+                if hf is not None:
+                    self.hfs.append(hf)
+            return recs
+
+        def fetch_halfframes(self, n):
+            assert n == len(self.hfs)
+            return np.stack(self.hfs)
+
+        def stats(self, stream, k):
+            st = A.PssStats()
+            p = self.pss[k]
+            st.max_psr, st.mean_psr, st.mean_cfo = p.max_psr(), p.mean_psr(), p.mean_cfo()
+            st.psr_threshold, st.tracking_score = p.psr_threshold(), p.tracking_score()
+            return st
+
+        def set_psr_threshold(self, t, stream=-1, n_id_2=-1, clamp=True):
+            if clamp:
+                t = max(t, lt.MIN_PSR_THRESHOLD)
+            for k in range(3):
+                if n_id_2 in (-1, k):
+                    self.pss[k].set_psr_threshold(t)
+
+    return Engine
+
+
+@pytest.fixture()
+def hier(oracle, monkeypatch):
+    import ltetrigger_b200 as lt
+    from ltetrigger_b200 import blocks
+    monkeypatch.setattr(blocks, "Trigger", oracle_engine(oracle))
+    return lt
+
+
+@pytest.mark.parametrize("name", list(FIXTURES))
+def test_reference_qa_flowgraphs(hier, oracle, name):
+    lt = hier
+    x, decim, cell_id = load_fixture(name, 0.3)
+    y = oracle.decimate(x, decim) if decim > 1 else x            # rational_resampler_ccc(1, D) in front, as in the QA
+    trig = lt.downlink_trigger_c(psr_threshold=4, exit_on_success=True)
+    assert trig.message_ports() == ["track", "drop"]
+    store = lt.cellstore().connect(trig)
+    tracked, dropped = [], []
+    trig.msg_connect("track", tracked.append)
+    trig.msg_connect("drop", dropped.append)
+    tags = []
+    for a in range(0, len(y), 40000):                            # chunks that are no multiple of a half-frame
+        tags += trig.work(y[a:a + 40000])
+    assert len(tracked) == 1 and dropped == []
+    cell = tracked[0]
+    assert cell["cell_id"] == cell_id and cell["cp_len"] == "Normal" and cell["nof_phich_resources"] == "1"
+    assert cell["nof_prb"] == NOF_PRB[name] and cell["nof_tx_ports"] == 1 and cell["phich_len"] == "Normal"
+    assert store.tracking() and store.latest_cell() is cell and store.cells() == [cell]
+    assert [m.done for m in (trig.mib0, trig.mib1, trig.mib2)] == [k == cell_id % 3 for k in range(3)]
+    ids = [(k, t.value) for k, t in tags if t.key == "cell_id"]
+    assert {v for _, v in ids} == {cell_id} and {k for k, _ in ids} == {cell_id % 3}
+    assert all(t.value is True for _, t in tags if t.key == "cp_type")
+    # tag offsets count the items each chain's pss has written: multiples of one half-frame, increasing per chain
+    for k in range(3):
+        offs = [t.offset for kk, t in tags if kk == k and t.key in ("tracking_lost", "cell_id")]
+        assert all(o % 9600 == 0 for o in offs) and offs == sorted(offs)
+    assert (trig.pss0, trig.pss1, trig.pss2)[cell_id % 3].tracking_score() == 16.0
+    assert [p.tracking_score() for i, p in enumerate((trig.pss0, trig.pss1, trig.pss2)) if i != cell_id % 3] == [0.0, 0.0]
+    # one record per general_work call of each chain; windows advance
+    for k in range(3):
+        ws = [int(r["win_start"]) for r in trig.records if r["n_id_2"] == k]
+        assert len(ws) > 20 and ws == sorted(ws)
+    # threshold clamp (python/downlink_trigger_c.py:63-73)
+    trig.set_psr_threshold(0.5)
+    assert trig.psr_threshold == 1.5 and trig.pss1.psr_threshold() == 1.5
+    assert lt.downlink_trigger_c(psr_threshold=0.1).psr_threshold == 1.5
+    trig.set_psr_threshold(7.25)
+    assert trig.psr_threshold == 7.25 and trig.pss2.psr_threshold() == 7.25
+
+
+def test_custom_sink_replaces_the_mib_stage(hier, oracle):
+    """`mib_sink(k, tags, halfframe)`: what a flowgraph gets that connects its own block behind sss -- every emitted
+    half-frame with its tags, in stream order per chain; returned (port, msg) pairs go out on the hier block's ports."""
+    lt = hier
+    x, _, cell_id = load_fixture("6prb", 0.2)
+    trig = lt.downlink_trigger_c(psr_threshold=4)
+    seen, got = [], []
+    trig.msg_connect("track", got.append)
+
+    def sink(k, tags, hf):
+        seen.append((k, [t.key for t in tags], hf.shape))
+        if any(t.key == "cell_id" for t in tags) and not got:
+            return [("track", {"cell_id": [t.value for t in tags if t.key == "cell_id"][0]})]
+    trig.mib_sink = sink
+    trig.work(x)
+    assert got == [{"cell_id": cell_id}]
+    assert {k for k, _, _ in seen} == {cell_id % 3} and all(s == (9600,) for _, _, s in seen)
+    assert seen[0][1] == ["tracking_lost"] and ["cell_id", "cp_type"] in [keys for _, keys, _ in seen]
