@@ -19,8 +19,9 @@ def oracle_engine(oracle):
 
     class Engine:
         def __init__(self, n_streams, decim=1, psr_threshold=4.0, max_chunk=1 << 18, **kw):
-            assert n_streams == 1 and decim == 1
-            self.max_chunk, self.thr = max_chunk, psr_threshold
+            assert n_streams == 1
+            self.max_chunk, self.thr, self.decim = max_chunk, psr_threshold, decim
+            self.raw, self.n_y = np.zeros(0, np.complex64), 0    # decim > 1: the fused resampler, restated by orc_decimate
             self.pss = [oracle.Pss(k, psr_threshold, conv_mode=oracle.CONV_DIRECT) for k in range(3)]
             self.sss = [oracle.Sss(k) for k in range(3)]
             self.buf = np.zeros(960, np.complex64)               # the zero history GNU Radio puts in front
@@ -28,7 +29,12 @@ def oracle_engine(oracle):
             self.hfs = []
 
         def process(self, x):
-            self.buf = np.concatenate([self.buf, np.asarray(x[0], np.complex64)])
+            x = np.asarray(x[0], np.complex64)
+            if self.decim > 1:                                   # y[k] depends on past input only: decimate all, keep the new outputs
+                self.raw = np.concatenate([self.raw, x])
+                y = oracle.decimate(self.raw, self.decim)
+                x, self.n_y = y[self.n_y:], len(y)
+            self.buf = np.concatenate([self.buf, x])
             out = []
             for k in range(3):
                 while self.pos[k] - 960 + oracle.LOOKAHEAD <= len(self.buf) - 960:
@@ -137,3 +143,32 @@ def test_custom_sink_replaces_the_mib_stage(hier, oracle):
     assert got == [{"cell_id": cell_id}]
     assert {k for k, _, _ in seen} == {cell_id % 3} and all(s == (9600,) for _, _, s in seen)
     assert seen[0][1] == ["tracking_lost"] and ["cell_id", "cp_type"] in [keys for _, keys, _ in seen]
+
+
+@pytest.mark.parametrize("name,rate", [("6prb", "1.92M"), ("25prb", "7.68M")])
+def test_cell_search_file_cli_like_reference_test_sh(hier, name, rate, capsys):
+    """examples/test.sh of the reference (:3-6): `cell_search_file.py -s RATE FRAME --repeat --time-out 1` prints the cell as
+    JSON with "status": "FOUND"; with a cut-off too short to reach tracking it prints NOT_FOUND.  (The two wider frames run
+    the same code; the stand-in's decimator is too slow for them here -- they are in tests/test_gpu_blocks.py.)"""
+    import importlib.util
+    import json
+    import os
+    from conftest import GOLDEN, ROOT
+    spec = importlib.util.spec_from_file_location("cell_search_file", os.path.join(ROOT, "examples", "cell_search_file.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    fname, decim, cell_id = FIXTURES[name]
+    path = os.path.join(GOLDEN, "test_frames", fname)
+    out = cli.main(cli.parse(["-s", rate, path, "--repeat", "--time-out", "60"]))
+    cell = json.loads(out[0])
+    assert cell["status"] == "FOUND" and cell["cell_id"] == cell_id and cell["nof_prb"] == NOF_PRB[name]
+    assert cell["cp_len"] == "Normal" and cell["nof_tx_ports"] == 1 and len(out) == 1
+    assert "Starting cell search... done." in capsys.readouterr().out
+    # -c counts search-rate samples (the reference puts head() behind the resampler): 60 ms cannot reach tracking
+    out = cli.main(cli.parse(["-s", rate, path, "--repeat", "-c", "115200"]))
+    assert json.loads(out[0]) == {"status": "NOT_FOUND"}
+    # and 200 ms do
+    out = cli.main(cli.parse(["-s", rate, path, "--repeat", "-c", "384000"]))
+    assert json.loads(out[0])["cell_id"] == cell_id
+    with pytest.raises(SystemExit):
+        cli.main(cli.parse(["-s", "2M", path]))                  # not a multiple of 1.92 MHz
