@@ -18,11 +18,13 @@ def oracle_engine(oracle):
     from ltetrigger_b200 import _abi as A
 
     class Engine:
-        def __init__(self, n_streams, decim=1, psr_threshold=4.0, max_chunk=1 << 18, **kw):
+        def __init__(self, n_streams, decim=1, psr_threshold=4.0, max_chunk=1 << 18, root_mask=7, track_after=16,
+                     track_every=8, **kw):
             assert n_streams == 1
             self.max_chunk, self.thr, self.decim = max_chunk, psr_threshold, decim
+            self.roots = [k for k in range(3) if root_mask >> k & 1]
             self.raw, self.n_y = np.zeros(0, np.complex64), 0    # decim > 1: the fused resampler, restated by orc_decimate
-            self.pss = [oracle.Pss(k, psr_threshold, conv_mode=oracle.CONV_DIRECT) for k in range(3)]
+            self.pss = [oracle.Pss(k, psr_threshold, track_after, track_every, conv_mode=oracle.CONV_DIRECT) for k in range(3)]
             self.sss = [oracle.Sss(k) for k in range(3)]
             self.buf = np.zeros(960, np.complex64)               # the zero history GNU Radio puts in front
             self.pos = [960, 960, 960]
@@ -36,7 +38,7 @@ def oracle_engine(oracle):
                 x, self.n_y = y[self.n_y:], len(y)
             self.buf = np.concatenate([self.buf, x])
             out = []
-            for k in range(3):
+            for k in self.roots:
                 while self.pos[k] - 960 + oracle.LOOKAHEAD <= len(self.buf) - 960:
                     nout, ncons, hf, rec = self.pss[k].work(self.buf, self.pos[k])
                     rec = rec.copy()
@@ -172,3 +174,48 @@ def test_cell_search_file_cli_like_reference_test_sh(hier, name, rate, capsys):
     assert json.loads(out[0])["cell_id"] == cell_id
     with pytest.raises(SystemExit):
         cli.main(cli.parse(["-s", "2M", path]))                  # not a multiple of 1.92 MHz
+
+
+@pytest.mark.parametrize("name", ["6prb", "25prb"])
+def test_pss_block_mirror_scheduler_contract(hier, oracle, name):
+    """The `pss` block mirror under the scheduler stand-in (gr_emu: zero-filled history, forecast, consume_each, tags) with
+    the oracle behind the engine interface, against the oracle's pss block driven directly: what is under test is the
+    mirror's own logic -- look-ahead queue, one window per general_work call, consume 9600 or peak - 960 + 9600, the
+    "tracking_lost" tag on item 0 of half-frames emitted while not tracking, accessors (lib/pss_impl.cc:154-223)."""
+    lt = hier
+    from ltetrigger_b200 import gr_emu
+    from ltetrigger_b200.blocks import _block, HALF_FRAME_LENGTH
+    x, decim, cell_id = load_fixture(name, 0.3)
+    y = oracle.decimate(x, decim) if decim > 1 else x
+    k = cell_id % 3
+
+    class PassThrough(_block):                                   # stands where sss stands; its own mirror needs the device
+        def work(self, noutput_items, input_items, output_items):
+            output_items[0][:HALF_FRAME_LENGTH] = input_items[0][:HALF_FRAME_LENGTH]
+            return HALF_FRAME_LENGTH
+
+    p = lt.pss(k, 4.0)
+    assert p.history() == 9600 and p.output_multiple() == 9600 and p.forecast(9600) == [9599 + 18365]
+    tr = gr_emu.run_chain(y, p, PassThrough("sss"))
+    assert len(tr.pss_calls) >= 50
+    op = oracle.Pss(k, 4.0)
+    buf = np.concatenate([np.zeros(960, np.complex64), y])
+    pos, written, i_emit, n_lost = 960, 0, 0, 0
+    for (r, nout, ncons, tags) in tr.pss_calls:
+        assert r == pos - 960
+        w_nout, w_ncons, w_out, w_rec = op.work(buf, pos)
+        assert (nout, ncons) == (w_nout, w_ncons)
+        lost = bool(w_rec["flags"] & oracle.F_TAG_LOST)
+        n_lost += lost
+        assert [(t.key, t.offset, t.value) for t in tags] == ([("tracking_lost", written, None)] if lost else [])
+        if nout:
+            assert np.array_equal(tr.pss_out[i_emit].view(np.uint32), w_out.view(np.uint32))
+            i_emit += 1
+            written += nout
+        pos += ncons
+    assert n_lost == 15 and i_emit > 40                          # the first track_after - 1 half-frames carry the tag: the 16th window starts tracking before it emits
+    assert p.tracking_score() == op.tracking_score() == 16.0 and p.max_psr() == op.max_psr() and p.mean_cfo() == op.mean_cfo()
+    p.set_psr_threshold(1.0)                                     # the block itself does not clamp
+    assert p.psr_threshold() == 1.0
+    with pytest.raises(RuntimeError):
+        lt.pss(3, 4.0)                                           # lib/pss_impl.cc:75-76
