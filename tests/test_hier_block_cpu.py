@@ -7,82 +7,16 @@ import numpy as np
 import pytest
 
 from conftest import FIXTURES, load_fixture
+import oracle_engine
 
 NOF_PRB = {"6prb": 6, "25prb": 25, "50prb": 50, "100prb": 100}
-
-
-def oracle_engine(oracle):
-    """A class with Trigger's constructor and the methods the block mirrors call, computing with oracle.Pss / oracle.Sss
-    call by call under the engine's scheduler rule (a window runs once 18365 samples from its start have arrived)."""
-    import ltetrigger_b200 as lt
-    from ltetrigger_b200 import _abi as A
-
-    class Engine:
-        def __init__(self, n_streams, decim=1, psr_threshold=4.0, max_chunk=1 << 18, root_mask=7, track_after=16,
-                     track_every=8, **kw):
-            assert n_streams == 1
-            self.max_chunk, self.thr, self.decim = max_chunk, psr_threshold, decim
-            self.roots = [k for k in range(3) if root_mask >> k & 1]
-            self.raw, self.n_y = np.zeros(0, np.complex64), 0    # decim > 1: the fused resampler, restated by orc_decimate
-            self.pss = [oracle.Pss(k, psr_threshold, track_after, track_every, conv_mode=oracle.CONV_DIRECT) for k in range(3)]
-            self.sss = [oracle.Sss(k) for k in range(3)]
-            self.buf = np.zeros(960, np.complex64)               # the zero history GNU Radio puts in front
-            self.pos = [960, 960, 960]
-            self.hfs = []
-
-        def process(self, x):
-            x = np.asarray(x[0], np.complex64)
-            if self.decim > 1:                                   # y[k] depends on past input only: decimate all, keep the new outputs
-                self.raw = np.concatenate([self.raw, x])
-                y = oracle.decimate(self.raw, self.decim)
-                x, self.n_y = y[self.n_y:], len(y)
-            self.buf = np.concatenate([self.buf, x])
-            out = []
-            for k in self.roots:
-                while self.pos[k] - 960 + oracle.LOOKAHEAD <= len(self.buf) - 960:
-                    nout, ncons, hf, rec = self.pss[k].work(self.buf, self.pos[k])
-                    rec = rec.copy()
-                    rec["win_start"] = self.pos[k] - 960
-                    rec["emit_start"] = self.pos[k] - 960 + rec["emit_start"] if nout else -1
-                    if nout:
-                        _, rec = self.sss[k].work(hf, bool(rec["flags"] & oracle.F_TAG_LOST), rec)
-                    out.append((k, rec, hf if nout else None))
-                    self.pos[k] += ncons
-            recs = np.zeros(len(out), A.WINDOW_REC)
-            self.hfs = []
-            for i, (k, rec, hf) in enumerate(out):               # engine order: by chain, then by call
-                for f in rec.dtype.names:
-                    recs[i][f] = rec[f]
-                if hf is not None:
-                    self.hfs.append(hf)
-            return recs
-
-        def fetch_halfframes(self, n):
-            assert n == len(self.hfs)
-            return np.stack(self.hfs)
-
-        def stats(self, stream, k):
-            st = A.PssStats()
-            p = self.pss[k]
-            st.max_psr, st.mean_psr, st.mean_cfo = p.max_psr(), p.mean_psr(), p.mean_cfo()
-            st.psr_threshold, st.tracking_score = p.psr_threshold(), p.tracking_score()
-            return st
-
-        def set_psr_threshold(self, t, stream=-1, n_id_2=-1, clamp=True):
-            if clamp:
-                t = max(t, lt.MIN_PSR_THRESHOLD)
-            for k in range(3):
-                if n_id_2 in (-1, k):
-                    self.pss[k].set_psr_threshold(t)
-
-    return Engine
 
 
 @pytest.fixture()
 def hier(oracle, monkeypatch):
     import ltetrigger_b200 as lt
     from ltetrigger_b200 import blocks
-    monkeypatch.setattr(blocks, "Trigger", oracle_engine(oracle))
+    monkeypatch.setattr(blocks, "Trigger", oracle_engine.make(oracle))
     return lt
 
 
@@ -220,3 +154,32 @@ def test_pss_block_mirror_scheduler_contract(hier, oracle, name):
     assert p.psr_threshold() == 1.0
     with pytest.raises(RuntimeError):
         lt.pss(3, 4.0)                                           # lib/pss_impl.cc:75-76
+
+
+def test_cell_search_batch_cli(oracle, monkeypatch, tmp_path):
+    """examples/cell_search_batch.py: several files as the streams of one engine, one JSON object per file -- a cell, a
+    noise-only capture (NOT_FOUND), and the same cell again from an sc16 file through the restated conversion."""
+    import json
+    import os
+    import sys
+    import ltetrigger_b200 as lt
+    from conftest import GOLDEN, ROOT
+    from ltetrigger_b200 import synth
+    eng = oracle_engine.make(oracle)
+    monkeypatch.setattr(lt, "Trigger", eng)
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import cell_search_batch as cli
+    frame = os.path.join(GOLDEN, "test_frames", "lte_frame_6prb_cellid_123")
+    noise = str(tmp_path / "noise.fc32")
+    synth.capture(0, 19200 * 12, snr_db=0.0, seed=9, noise_only=True).tofile(noise)
+    out = cli.main(cli.parse(["-s", "1.92M", frame, noise, "--repeat", "--cut-off", "384000"]))
+    a, b = (json.loads(o) for o in out)
+    assert (a["status"], a["cell_id"], a["nof_prb"], a["cp_len"], os.path.basename(a["file"])) == \
+        ("FOUND", 123, 6, "Normal", "lte_frame_6prb_cellid_123")
+    assert b == {"status": "NOT_FOUND", "file": noise}
+    assert eng.created[-1]["n_streams"] == 2 and eng.created[-1]["record_all"] is False and eng.created[-1]["keep_halfframes"] is True
+    x = np.fromfile(frame, np.complex64)
+    sc16 = str(tmp_path / "frame.sc16")
+    synth.to_sc16(x[None, :])[0].tofile(sc16)
+    out = cli.main(cli.parse(["-s", "1.92M", "--format", "sc16", sc16, "--repeat", "--cut-off", "384000"]))
+    assert json.loads(out[0])["cell_id"] == 123 and eng.created[-1]["input_format"] == lt.FMT_SC16
